@@ -1,0 +1,277 @@
+"""ctypes binding of the CPU ORACLE (oracle/libwps_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(wps_b200/) must never import this module.  PARITY UNPINNED -- see
+oracle/wps_oracle.h and DESIGN.md.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+NAN = np.float32(1.0e20)
+SIXTEEN_POINT, FOUR_POINT, N_NEIGHBOR, AVERAGE4, AVERAGE16, W_AVERAGE4, W_AVERAGE16, SEARCH = range(1, 9)
+M, U, V, HH, VV, CORNER = range(1, 7)
+PROJ_LATLON, PROJ_LC, PROJ_PS, PROJ_MERC, PROJ_GAUSS, PROJ_CYL, PROJ_CASSINI = 0, 1, 2, 3, 4, 5, 6
+PROJ_PS_WGS84, PROJ_ALBERS_NAD83 = 102, 105
+
+_A = dict(lat1=0, lon1=1, lat0=2, lon0=3, knowni=4, knownj=5, dx=6, dy=7, latinc=8, loninc=9, stdlon=10,
+          truelat1=11, truelat2=12, nlat=13, nlon=14, ixdim=15, jydim=16, nxmin=17, nxmax=18, stagger=19,
+          phi=20, lambda_=21, r_earth=22)
+
+
+class Proj(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("code", "nlat", "nlon", "nxmin", "nxmax", "ixdim", "jydim", "stagger")] + \
+               [(n, C.c_float) for n in ("phi", "lambda_", "lat1", "lon1", "lat0", "lon0", "dx", "dy", "latinc",
+                                         "loninc", "dlat", "dlon", "stdlon", "truelat1", "truelat2", "hemi", "cone",
+                                         "polei", "polej", "rsw", "rebydx", "knowni", "knownj", "re_m", "rho0",
+                                         "nc", "bigc")] + \
+               [(n, C.c_int) for n in ("init", "wrap", "comp_ll", "n_gauss")] + \
+               [("gauss_lat", C.c_float * 2048)]
+
+
+class MapArgs(C.Structure):
+    _fields_ = [("present", C.c_uint)] + \
+               [(n, C.c_float) for n in ("lat1", "lon1", "lat0", "lon0", "knowni", "knownj", "dx", "dy", "latinc",
+                                         "loninc", "stdlon", "truelat1", "truelat2", "phi", "lambda_", "r_earth")] + \
+               [(n, C.c_int) for n in ("nlat", "nlon", "ixdim", "jydim", "nxmin", "nxmax", "stagger")]
+
+
+class FieldOpts(C.Structure):
+    _fields_ = [("ops", C.c_int * 16), ("opts", C.c_int * 16), ("missing_value", C.c_float),
+                ("fill_missing", C.c_float), ("masked", C.c_float), ("mask_val", C.c_float * 3),
+                ("mask_rel", C.c_char * 3)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libwps_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_interp_sequence.restype = C.c_float
+        _LIB.orc_oned.restype = C.c_float
+        _LIB.orc_oned.argtypes = [C.c_float] * 5
+        _LIB.orc_interp_to_latlon.restype = C.c_float
+    return _LIB
+
+
+def fptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def iptr(a):
+    if a is None:
+        return None
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def set_transc_mode(mode):
+    lib().orc_set_transc_mode(int(mode))
+
+
+def map_set(code, **kw):
+    """map_set(module_map_utils.F:243) with keyword OPTIONALs; returns a populated Proj."""
+    a = MapArgs()
+    present = 0
+    for k, v in kw.items():
+        key = "lambda_" if k == "lambda" else k
+        present |= 1 << _A[key]
+        setattr(a, key, v)
+    a.present = present
+    p = Proj()
+    rc = lib().orc_map_set(int(code), C.byref(p), C.byref(a))
+    if rc != 0:
+        raise ValueError("map_set error %d" % rc)
+    return p
+
+
+def push_source_projection(iproj, stand_lon=0., truelat1=0., truelat2=0., dxkm=0., dykm=0., dlat=0., dlon=0.,
+                           known_x=1., known_y=1., known_lat=0., known_lon=0., pole_lat=None, pole_lon=None,
+                           centerlat=None, centerlon=None, centeri=None, centerj=None, earth_radius=None):
+    p = Proj()
+    has_cass = pole_lat is not None
+    f = C.c_float
+    rc = lib().orc_push_source_projection(
+        C.byref(p), int(iproj), f(stand_lon), f(truelat1), f(truelat2), f(dxkm), f(dykm), f(dlat), f(dlon),
+        f(known_x), f(known_y), f(known_lat), f(known_lon), int(has_cass), f(pole_lat or 0.), f(pole_lon or 0.),
+        f(centerlat or 0.), f(centerlon or 0.), f(centeri or 0.), f(centerj or 0.),
+        int(earth_radius is not None), f(earth_radius or 0.))
+    if rc != 0:
+        raise ValueError("push_source_projection error %d" % rc)
+    return p
+
+
+def lltoxy(p, lat, lon, stagger=M):
+    lat = np.ascontiguousarray(lat, np.float32)
+    lon = np.ascontiguousarray(lon, np.float32)
+    x = np.empty_like(lat)
+    y = np.empty_like(lat)
+    lib().orc_lltoxy_array(C.byref(p), C.c_long(lat.size), fptr(lat), fptr(lon), fptr(x), fptr(y), int(stagger))
+    return x, y
+
+
+def xytoll(p, x, y, stagger=M):
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.ascontiguousarray(y, np.float32)
+    lat = np.empty_like(x)
+    lon = np.empty_like(x)
+    lib().orc_xytoll_array(C.byref(p), C.c_long(x.size), fptr(x), fptr(y), fptr(lat), fptr(lon), int(stagger))
+    return lat, lon
+
+
+def parse_interp_option(s, maxn=16):
+    codes = (C.c_int * maxn)()
+    opts = (C.c_int * maxn)()
+    n = lib().orc_interp_array_from_string(s.encode(), codes, maxn)
+    n2 = lib().orc_interp_options_from_string(s.encode(), opts, maxn)
+    if n < 0 or n2 < 0:
+        raise ValueError("bad interp_option %r" % s)
+    return list(codes[:n]), list(opts[:n])
+
+
+def gcell_threshold(s):
+    t = C.c_float()
+    rc = lib().orc_get_gcell_threshold(s.encode(), C.byref(t))
+    if rc != 0:
+        raise ValueError("bad average_gcell threshold in %r" % s)
+    return t.value
+
+
+def _chain(chain):
+    if isinstance(chain, str):
+        codes, opts = parse_interp_option(chain)
+    else:
+        codes, opts = chain
+    codes = np.ascontiguousarray(list(codes) + [0], np.int32)
+    opts = np.ascontiguousarray(list(opts) + [0], np.int32)
+    return codes, opts
+
+
+def interp_sequence(xx, yy, array, sx, sy, msgval, chain, izz=1, sz=1, mask=None, rel=' ', maskval=0.0):
+    """Vectorised interp_sequence (interp_module.F:304) over arrays xx, yy.
+    array is [nz][ny][nx] (x fastest) with lower bounds (sx, sy, sz)."""
+    array = np.ascontiguousarray(array, np.float32)
+    if array.ndim == 2:
+        array = array[None]
+    nz, ny, nx = array.shape
+    xx = np.ascontiguousarray(xx, np.float32)
+    yy = np.ascontiguousarray(yy, np.float32)
+    out = np.empty_like(xx)
+    codes, opts = _chain(chain)
+    m = None if mask is None else np.ascontiguousarray(mask, np.float32)
+    lib().orc_interp_sequence_array(
+        C.c_long(xx.size), fptr(xx), fptr(yy), int(izz), fptr(array), int(sx), int(sx + nx - 1), int(sy),
+        int(sy + ny - 1), int(sz), int(sz + nz - 1), C.c_float(msgval), iptr(codes), iptr(opts),
+        int(m is not None), C.c_char(rel.encode()), C.c_float(maskval), fptr(m), fptr(out))
+    return out
+
+
+def field_opts(chain, missing_value=NAN, fill_missing=NAN, masked=-2.0, mask_val=(NAN, NAN, NAN), mask_rel="   "):
+    fo = FieldOpts()
+    codes, opts = _chain(chain)
+    for i, (c, o) in enumerate(zip(codes, opts)):
+        fo.ops[i] = int(c)
+        fo.opts[i] = int(o)
+    fo.missing_value = missing_value
+    fo.fill_missing = fill_missing
+    fo.masked = masked
+    for i in range(3):
+        fo.mask_val[i] = mask_val[i]
+    fo.mask_rel = mask_rel.encode()
+    return fo
+
+
+def nwords(nx):
+    return (nx + 31) // 32
+
+
+def interp_met_field(src, fo, ifieldstagger, xlat, xlon, sm1, sm2, sd, slab, minx, miny, bdr,
+                     mask=None, land_mask=None, water_mask=None, landmask=None, process_bdy_width=0,
+                     r_arr=None, valid_mask=None, sub=None):
+    """interp_met_field non-gcell branch (process_domain_module.F:2483-2581).
+    xlat/xlon [ny][nx] with lower bounds (sm1, sm2); sd=(sd1,ed1,sd2,ed2); slab [sny][snx] lower bounds (minx,miny).
+    Returns (r_arr, new_pts words)."""
+    xlat = np.ascontiguousarray(xlat, np.float32)
+    xlon = np.ascontiguousarray(xlon, np.float32)
+    ny, nx = xlat.shape
+    slab = np.ascontiguousarray(slab, np.float32)
+    sny, snx = slab.shape
+    if r_arr is None:
+        r_arr = np.zeros((ny, nx), np.float32)
+    if valid_mask is None:
+        valid_mask = np.zeros((ny, nwords(nx)), np.int32)
+    new_pts = np.zeros((ny, nwords(nx)), np.int32)
+    em1, em2 = sm1 + nx - 1, sm2 + ny - 1
+    if sub is None:
+        sub = (sm1, em1, sm2, em2)
+    cm = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    mask, land_mask, water_mask, landmask = cm(mask), cm(land_mask), cm(water_mask), cm(landmask)
+    lib().orc_interp_met_field(
+        C.byref(src), C.byref(fo), int(ifieldstagger), fptr(xlat), fptr(xlon), sm1, em1, sm2, em2,
+        int(sd[0]), int(sd[1]), int(sd[2]), int(sd[3]), fptr(slab), int(minx), int(minx + snx - 1), int(miny),
+        int(miny + sny - 1), int(bdr), fptr(mask), fptr(land_mask), fptr(water_mask), fptr(landmask),
+        int(process_bdy_width), fptr(r_arr), iptr(valid_mask), iptr(new_pts),
+        int(sub[0]), int(sub[1]), int(sub[2]), int(sub[3]))
+    return r_arr, new_pts
+
+
+def interp_met_field_gcell(src, dom, fo, ifieldstagger, xlat, xlon, sm1, sm2, sd, slab, minx, miny, bdr,
+                           mask=None, landmask=None, process_bdy_width=0, r_arr=None, valid_mask=None):
+    xlat = np.ascontiguousarray(xlat, np.float32)
+    xlon = np.ascontiguousarray(xlon, np.float32)
+    ny, nx = xlat.shape
+    slab = np.ascontiguousarray(slab, np.float32)
+    sny, snx = slab.shape
+    if r_arr is None:
+        r_arr = np.zeros((ny, nx), np.float32)
+    if valid_mask is None:
+        valid_mask = np.zeros((ny, nwords(nx)), np.int32)
+    new_pts = np.zeros((ny, nwords(nx)), np.int32)
+    cm = lambda a: None if a is None else np.ascontiguousarray(a, np.float32)
+    mask, landmask = cm(mask), cm(landmask)
+    lib().orc_interp_met_field_gcell(
+        C.byref(src), C.byref(dom), C.byref(fo), int(ifieldstagger), fptr(xlat), fptr(xlon), sm1, sm1 + nx - 1,
+        sm2, sm2 + ny - 1, int(sd[0]), int(sd[1]), int(sd[2]), int(sd[3]), fptr(slab), int(minx),
+        int(minx + snx - 1), int(miny), int(miny + sny - 1), int(bdr), fptr(mask), fptr(landmask),
+        int(process_bdy_width), fptr(r_arr), iptr(valid_mask), iptr(new_pts))
+    return r_arr, new_pts
+
+
+def metmap_xform(proj, u, u_mask, v, v_mask, xlon_u, xlon_v, idir, us=(1, 1), vs=(1, 1)):
+    """metmap_xform (rotate_winds_module.F:85); u [uny][unx], v [vny][vnx]; in place on copies."""
+    u = np.array(u, np.float32, order="C")
+    v = np.array(v, np.float32, order="C")
+    uny, unx = u.shape
+    vny, vnx = v.shape
+    lib().orc_metmap_xform(C.byref(proj), fptr(u), iptr(np.ascontiguousarray(u_mask, np.int32)), fptr(v),
+                           iptr(np.ascontiguousarray(v_mask, np.int32)), us[0], us[1], us[0] + unx - 1,
+                           us[1] + uny - 1, vs[0], vs[1], vs[0] + vnx - 1, vs[1] + vny - 1,
+                           fptr(np.ascontiguousarray(xlon_u, np.float32)),
+                           fptr(np.ascontiguousarray(xlon_v, np.float32)), int(idir))
+    return u, v
+
+
+def smooth(array, npass, opt):
+    """smooth_module.F:20-239 on array [nz][ny][nx]; returns smoothed copy."""
+    a = np.array(array, np.float32, order="C")
+    if a.ndim == 2:
+        a = a[None]
+    nz, ny, nx = a.shape
+    lib().orc_smooth(fptr(a), 1, nx, 1, ny, 1, nz, int(npass), int(opt))
+    return a.reshape(np.shape(array))
