@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- metgrid output points/s (field x level x destination point) on the BASELINE.json configs[1]
+workload: GFS 0.25 deg (1440x721, 34 isobaric levels + surface, default METGRID.TBL.ARW chains) ->
+3-km CONUS Lambert 1799x1059.  One step = one time of the FILE (190 slabs, 3.6e8 output points).
+
+  python bench.py --gpus N --steps K --warmup W           our arm (libwpsgpu.so through the C ABI)
+  python bench.py --impl reference ...                    the reference's CPU path on the host cores
+                                                          (oracle restatement; WPS itself cannot be built here)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_POINT = 4.5   # 4 B store + source bbox + cached coords/L + mask bit
+METRIC = "metgrid output points/s (field*level*pt)"
+WORKLOAD = "config2: GFS 0.25deg 1440x721 x (34 isobaric + sfc) levels, default METGRID.TBL.ARW chains -> 3-km CONUS Lambert 1799x1059; 1 step = 1 time (190 slabs)"
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_sample(config, nslab=16):
+    """Bounded sample of the step for the CPU arm: slab mix proportional to the step's chain mix."""
+    from wps_b200 import synth
+    sx, sy, dlat, dlon = config["src"]
+    ls = synth.landsea_np(sx, sy)
+    lsh = synth.add_halo(ls)
+    picks = [("TT", synth.C3D, 1, 1e20, 0.0, None, "smooth")] * 5 + [("UU", synth.C3D, 2, 1e20, 0.0, None, "wind")] * 4 + \
+            [("VV", synth.C3D, 3, 1e20, 0.0, None, "wind")] * 4 + [("PSFC", "four_pt+average_4pt", 1, 1e20, 1e20, None, "smooth")] + \
+            [("ST000010", synth.SOIL, 1, -1e30, 285.0, lsh, "land")] * 2
+    picks = picks[:nslab]
+    sample = []
+    for k, (name, chain, stag, msg, fill, mask, kind) in enumerate(picks):
+        slab = synth.add_halo(synth.slab_np(sx, sy, 1000 + k, kind, ls, np.float32(msg)))
+        sample.append(dict(name=name, chain=chain, stagger=stag, missing=msg, fill=fill,
+                           masked=0.0 if mask is not None else -2.0,   # soil fields: masked=water, interp_mask=LANDSEA(0)
+                           mask_val=(0.0, 1e20, 1e20) if mask is not None else (1e20, 1e20, 1e20), mask=mask,
+                           land_mask=None, water_mask=None, use_landmask=(stag == 1), slab=slab))
+    return sample
+
+
+def cpu_arm(config, nslab, nprocs, repeats=1):
+    from oracle import oracle as O, cpu_bench
+    from wps_b200 import synth
+    sx, sy, dlat, dlon = config["src"]
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = config["dom"]
+    O.set_transc_mode(0)
+    dom = O.map_set(O.PROJ_LC, truelat1=tl1, truelat2=tl2, stdlon=slon, lat1=rlat, lon1=rlon, knowni=(nx + 1) / 2.0,
+                    knownj=(ny + 1) / 2.0, dx=dx)
+    grids = {1: O.get_lat_lon_fields(dom, 1, 1, nx, ny, O.M), 2: O.get_lat_lon_fields(dom, 1, 1, nx + 1, ny, O.U),
+             3: O.get_lat_lon_fields(dom, 1, 1, nx, ny + 1, O.V)}
+    src_kw = dict(dlat=dlat, dlon=dlon, known_x=1.0, known_y=1.0, known_lat=90.0, known_lon=0.0, earth_radius=6371229.0)
+    sample = cpu_sample(config, nslab)
+    lam = np.deg2rad(grids[1][1]) % (2 * np.pi)
+    landmask = (synth.landsea_fn(np, lam, np.deg2rad(grids[1][0])) > synth.LAND_THRESHOLD).astype(np.float32)
+    pps, dt, pts, nprocs = cpu_bench.run(src_kw, grids, landmask, (1, nx, 1, ny), sample, nprocs, repeats)
+    desc = "%d slabs of the step (TT/UU/VV sixteen_pt chain x13, PSFC four_pt, 2 masked soil search chains) on the full 1799x1059 grid, %d-process patch decomposition" % (len(sample) * repeats, nprocs)
+    return pps, dt, pts, nprocs, desc
+
+
+def run_reference(args, rank):
+    from wps_b200 import synth
+    if rank != 0:
+        return
+    config = synth.CONFIGS["config2"]
+    nprocs = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_arm(config, 2, nprocs)
+    times, pts = [], 0
+    for _ in range(args.steps):
+        pps, dt, p, nprocs, desc = cpu_arm(config, 16, nprocs, 3)
+        times.append(dt)
+        pts = p
+    ms = 1e3 * float(np.mean(times))
+    value = pts / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "step_sample": desc},
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def build_workload(h, torch, dev, config, device_mode=True):
+    """Synthetic inputs resident in HBM.  Returns dict with grids, slabs, outputs and the enqueue plan."""
+    from wps_b200 import capi, synth
+    sx, sy, dlat, dlon = config["src"]
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = config["dom"]
+    dom = synth.lambert_domain(nx, ny, dx, tl1, tl2, slon, rlat, rlon)
+    src = capi.push_source_projection(capi.PROJ_LATLON, dlat=dlat, dlon=dlon, known_x=1.0, known_y=1.0, known_lat=90.0,
+                                      known_lon=0.0, earth_radius=6371229.0)
+    grids = {}
+    for gid, (st, gx, gy) in {0: (capi.M, nx, ny), 1: (capi.U, nx + 1, ny), 2: (capi.V, nx, ny + 1)}.items():
+        xlat = torch.empty((gy, gx), dtype=torch.float32, device=dev)
+        xlon = torch.empty_like(xlat)
+        h.xytoll_grid(dom, st, 1, 1, gx, gy, out=(xlat, xlon))   # get_lat_lon_fields on device
+        grids[gid] = (xlat, xlon)
+    h.synchronize()
+    lam = torch.deg2rad(grids[0][1]) % (2 * np.pi)
+    phi = torch.deg2rad(grids[0][0])
+    landmask = (synth.landsea_fn(torch, lam, phi) > synth.LAND_THRESHOLD).float().contiguous()
+    table = synth.gfs_slab_table(config["nlev"])
+    g = torch.Generator(device=dev)
+    g.manual_seed(20261019)
+    lam_s = torch.linspace(0, 2 * np.pi, sx + 1, device=dev)[:-1][None, :]
+    phi_s = torch.linspace(np.pi / 2, -np.pi / 2, sy, device=dev)[:, None]
+    ls = (synth.landsea_fn(torch, lam_s, phi_s) > synth.LAND_THRESHOLD).float()
+    lsh = synth.add_halo(ls)
+    plan = []
+    seed = 0
+    for e in table:
+        gid = {capi.M: 0, capi.U: 1, capi.V: 2}[e["stagger"]]
+        gy, gx = grids[gid][0].shape
+        n = e["nlev"]
+        if e["kind"] == "landsea":
+            slabs = ls[None].repeat(n, 1, 1)
+        elif e["kind"] == "wind":
+            ph = torch.arange(n, device=dev, dtype=torch.float32)[:, None, None] * 0.1
+            slabs = 12.0 * torch.sin(3 * lam_s[None] + ph) * torch.cos(2 * phi_s[None]) + (torch.rand((n, sy, sx), device=dev, generator=g) - 0.5) * 0.024
+        else:
+            lev = torch.arange(n, device=dev, dtype=torch.float32)[:, None, None] * 0.5
+            slabs = 280.0 + 30.0 * torch.sin(3 * lam_s[None]) * torch.cos(2 * phi_s[None]) + lev + (torch.rand((n, sy, sx), device=dev, generator=g) - 0.5) * 0.06
+        slabs = slabs.float()
+        slabs[torch.rand((n, sy, sx), device=dev, generator=g) < 0.001] = 0.0
+        if e["kind"] == "land":
+            slabs[:, ls == 0] = e["missing"]
+        elif e["kind"] == "water":
+            slabs[:, ls == 1] = e["missing"]
+        slabs = synth.add_halo(slabs)
+        masks, mv = (None, None, None), (1e20, 1e20, 1e20)
+        if e["mask"] is not None:
+            if e["mask"][0] == "mask":
+                masks, mv = (lsh, None, None), (e["mask"][1], 1e20, 1e20)
+            else:
+                masks, mv = (None, lsh, lsh), (1e20, e["mask"][1], e["mask"][2])
+        fo = capi.field_opts(e["chain"], np.float32(e["missing"]), np.float32(e["fill"]), e["masked"], mv)
+        r = torch.empty((n, gy, gx), dtype=torch.float32, device=dev)
+        npw = torch.zeros((n, gy, capi.nwords(gx)), dtype=torch.int32, device=dev)
+        plan.append(dict(e=e, gid=gid, fo=fo, slabs=slabs, masks=masks, r=r, npw=npw,
+                         use_landmask=(e["stagger"] == capi.M)))
+        seed += n
+    return dict(dom=dom, src=src, grids=grids, landmask=landmask, plan=plan, nx=nx, ny=ny)
+
+
+def enqueue_all(h, w, host=None):
+    """The process_intermediate_fields record loop: one enqueue per (field, level) slab, then ONE flush."""
+    pts = 0
+    for pi, p in enumerate(w["plan"]):
+        n = p["slabs"].shape[0]
+        for l in range(n):
+            if host is None:
+                slab, r, npw, masks = p["slabs"][l], p["r"][l], p["npw"][l], p["masks"]
+            else:
+                slab, r, npw, masks = host[pi]["slabs"][l], host[pi]["r"][l], host[pi]["npw"][l], host[pi]["masks"]
+            h.metgrid_enqueue_slab(w["src"], p["fo"], slab, -2, 1, 3, p["gid"], p["e"]["stagger"], r, npw, masks=masks,
+                                   use_landmask=p["use_landmask"])
+            pts += r.shape[0] * r.shape[1]
+    h.metgrid_flush()
+    return pts
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from wps_b200 import capi, synth
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    config = synth.CONFIGS["config2"]
+    h = capi.Handle(local_rank, capi.PTR_DEVICE)
+    w = build_workload(h, torch, dev, config)
+    nx, ny = w["nx"], w["ny"]
+    for gid, (xlat, xlon) in w["grids"].items():
+        h.metgrid_set_grid(gid, xlat, xlon, 1, 1)
+    h.metgrid_set_landmask(0, w["landmask"])
+    h.metgrid_set_domain(1, nx, 1, ny)
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        pts = enqueue_all(h, w)
+    h.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = h.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    ev0.record(stream)
+    for _ in range(args.steps):
+        enqueue_all(h, w)
+        kms.append(None)
+    ev1.record(stream)
+    h.synchronize()
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = h.launch_count - l0
+    # dominant-kernel time: re-run K steps reading the library's own CUDA events around k_metgrid_interp
+    kms = []
+    for _ in range(args.steps):
+        enqueue_all(h, w)
+        ms, kp = h.metgrid_last_kernel()
+        kms.append(ms)
+    sampler.stop_flag = True
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * pts / (ms_per_step / 1e3)
+
+    # ---- e2e: host buffers in pinned memory through the C ABI (H2D + kernels + D2H inside the timed region) ----
+    hh = capi.Handle(local_rank, capi.PTR_HOST)
+    for gid, (xlat, xlon) in w["grids"].items():
+        hh.metgrid_set_grid(gid, xlat.cpu().numpy(), xlon.cpu().numpy(), 1, 1)
+    hh.metgrid_set_landmask(0, w["landmask"].cpu().numpy())
+    hh.metgrid_set_domain(1, nx, 1, ny)
+    host, h2d, d2h = [], 0, 0
+    seen = set()
+    for p in w["plan"]:
+        hs = p["slabs"].cpu().pin_memory()
+        hm = tuple(None if m is None else m.cpu().pin_memory() for m in p["masks"])
+        hr = torch.empty(p["r"].shape, dtype=torch.float32).pin_memory()
+        hn = torch.zeros(p["npw"].shape, dtype=torch.int32).pin_memory()
+        host.append(dict(slabs=hs, masks=hm, r=hr, npw=hn))
+        h2d += hs.numel() * 4
+        for m in hm:
+            if m is not None and "mask" not in seen:
+                h2d += m.numel() * 4
+                seen.add("mask")
+        d2h += hr.numel() * 4 + hn.numel() * 4
+    e2e_steps = max(1, min(args.steps, 3))
+    enqueue_all(hh, w, host)  # warm-up (arena allocation, coordinate cache)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        enqueue_all(hh, w, host)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * pts / float(t.item())
+    hh.close()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        kms_avg = float(np.mean(kms))
+        achieved = ALG_BYTES_PER_POINT * kp / (kms_avg * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "slabs_per_step": len([0 for p in w["plan"] for _ in range(p["slabs"].shape[0])]),
+                           "points_per_step_per_gpu": pts, "l2": "inputs (792 MB of source slabs) and outputs (1.45 GB) per step exceed the 126 MB L2",
+                           "sharding": "one FILE time per GPU per step (field x level x time shard, no collective)"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "k_metgrid_interp", "kernel_ms": kms_avg,
+                             "alg_bytes_per_point": ALG_BYTES_PER_POINT, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+                "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": int(launches), "clocks": sampler.result()}
+        if world == 1 and not args.no_cpu:
+            pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 3)
+            line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

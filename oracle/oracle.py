@@ -275,3 +275,154 @@ def smooth(array, npass, opt):
     nz, ny, nx = a.shape
     lib().orc_smooth(fptr(a), 1, nx, 1, ny, 1, nz, int(npass), int(opt))
     return a.reshape(np.shape(array))
+
+
+# ---- geogrid ----
+def accum_categorical(src, dom, istagger, tile, src_min_x, src_min_y, bdr, dst, start_i, start_j, start_k,
+                      processed, new_pts, ilevel, msgval, sr_x=1.0, sr_y=1.0):
+    """proc_point_module.F:100-206 for one tile; tile [ny][nx]; dst [nk][ny][nx] modified in place."""
+    tile = np.ascontiguousarray(tile, np.float32)
+    ty, tx = tile.shape[-2:]
+    nk, ny, nx = dst.shape
+    inv = C.c_long(0)
+    lib().orc_accum_categorical(C.byref(src), C.byref(dom), int(istagger), fptr(tile), int(src_min_x),
+                                int(src_min_x + tx - 1), int(src_min_y), int(src_min_y + ty - 1), int(bdr), fptr(dst),
+                                int(start_i), int(start_i + nx - 1), int(start_j), int(start_j + ny - 1), int(start_k),
+                                int(start_k + nk - 1), iptr(processed), iptr(new_pts), int(ilevel), C.c_float(msgval),
+                                C.c_float(sr_x), C.c_float(sr_y), C.byref(inv))
+    return inv.value
+
+
+def accum_continuous(src, dom, istagger, tile, src_min_x, src_min_y, src_min_z, bdr, dst, n, start_i, start_j,
+                     start_k, processed, new_pts, msgval, sr_x=1.0, sr_y=1.0):
+    tile = np.ascontiguousarray(tile, np.float32)
+    tz, ty, tx = tile.shape
+    nk, ny, nx = dst.shape
+    lib().orc_accum_continuous(C.byref(src), C.byref(dom), int(istagger), fptr(tile), int(src_min_x),
+                               int(src_min_x + tx - 1), int(src_min_y), int(src_min_y + ty - 1), int(src_min_z),
+                               int(src_min_z + tz - 1), int(bdr), fptr(dst), fptr(n), int(start_i),
+                               int(start_i + nx - 1), int(start_j), int(start_j + ny - 1), int(start_k),
+                               int(start_k + nk - 1), iptr(processed), iptr(new_pts), C.c_float(msgval),
+                               C.c_float(sr_x), C.c_float(sr_y))
+
+
+def tile_point_fallback(src, itype, tile, src_min_x, src_min_y, src_min_z, bdr, xlat, xlon, landmask, use_landmask,
+                        mask_val, chain, msg_val, msg_fill_val, field, data_count, start_i, start_j, start_k,
+                        processed, level):
+    tile = np.ascontiguousarray(tile, np.float32)
+    tz, ty, tx = tile.shape
+    nk, ny, nx = field.shape
+    codes, opts = _chain(chain)
+    inv = C.c_long(0)
+    lib().orc_tile_point_fallback(C.byref(src), int(itype), fptr(tile), int(src_min_x), int(src_min_x + tx - 1),
+                                  int(src_min_y), int(src_min_y + ty - 1), int(src_min_z), int(src_min_z + tz - 1),
+                                  int(bdr), fptr(np.ascontiguousarray(xlat, np.float32)),
+                                  fptr(np.ascontiguousarray(xlon, np.float32)),
+                                  fptr(None if landmask is None else np.ascontiguousarray(landmask, np.float32)),
+                                  int(use_landmask), C.c_float(mask_val), iptr(codes), iptr(opts), C.c_float(msg_val),
+                                  C.c_float(msg_fill_val), fptr(field), fptr(data_count), int(start_i),
+                                  int(start_i + nx - 1), int(start_j), int(start_j + ny - 1), int(start_k),
+                                  int(start_k + nk - 1), iptr(processed), iptr(level), C.byref(inv))
+    return inv.value
+
+
+def calc_field_finish(itype, field, data_count, landmask, use_landmask, mask_val, msg_fill_val, scale_factor,
+                      start_i, start_j, start_k, processed, level):
+    nk, ny, nx = field.shape
+    lib().orc_calc_field_finish(int(itype), fptr(field), fptr(data_count),
+                                fptr(None if landmask is None else np.ascontiguousarray(landmask, np.float32)),
+                                int(use_landmask), C.c_float(mask_val), C.c_float(msg_fill_val),
+                                int(scale_factor is not None), C.c_float(scale_factor or 1.0), int(start_i),
+                                int(start_i + nx - 1), int(start_j), int(start_j + ny - 1), int(start_k),
+                                int(start_k + nk - 1), iptr(processed), iptr(level))
+
+
+def fractions(field, msg_fill_val):
+    f = np.array(field, np.float32, order="C")
+    ncat = f.shape[0]
+    lib().orc_fractions(fptr(f), C.c_long(int(np.prod(f.shape[1:]))), int(ncat), C.c_float(msg_fill_val))
+    return f
+
+
+def landmask_from_fractions(field, min_cat, lm_vals, is_water_mask, msg_fill_val):
+    f = np.ascontiguousarray(field, np.float32)
+    ncat = f.shape[0]
+    out = np.empty(f.shape[1:], np.float32)
+    lm = np.ascontiguousarray(lm_vals, np.int32)
+    lib().orc_landmask_from_fractions(fptr(f), C.c_long(out.size), int(min_cat), int(min_cat + ncat - 1), iptr(lm),
+                                      int(lm.size), int(is_water_mask), C.c_float(msg_fill_val), fptr(out))
+    return out
+
+
+def dominant_category(field, min_cat, msg_fill_val):
+    f = np.ascontiguousarray(field, np.float32)
+    out = np.empty(f.shape[1:], np.float32)
+    lib().orc_dominant_category(fptr(f), C.c_long(out.size), int(min_cat), int(min_cat + f.shape[0] - 1),
+                                C.c_float(msg_fill_val), fptr(out))
+    return out
+
+
+def dominant_category_landmask(field, landmask, min_cat, lm_vals, is_water_mask):
+    f = np.ascontiguousarray(field, np.float32)
+    out = np.empty(f.shape[1:], np.float32)
+    lm = np.ascontiguousarray(lm_vals, np.int32)
+    lib().orc_dominant_category_landmask(fptr(f), fptr(np.ascontiguousarray(landmask, np.float32)),
+                                         C.c_long(out.size), int(min_cat), int(min_cat + f.shape[0] - 1), iptr(lm),
+                                         int(lm.size), int(is_water_mask), fptr(out))
+    return out
+
+
+def get_lat_lon_fields(dom, si, sj, nx, ny, stagger, sub_x=1.0, sub_y=1.0):
+    xlat = np.empty((ny, nx), np.float32)
+    xlon = np.empty((ny, nx), np.float32)
+    lib().orc_get_lat_lon_fields(C.byref(dom), fptr(xlat), fptr(xlon), int(si), int(sj), int(si + nx - 1),
+                                 int(sj + ny - 1), int(stagger), C.c_float(sub_x), C.c_float(sub_y))
+    return xlat, xlon
+
+
+def get_map_factor(dom, xlat, xlon, truelat1, truelat2, pole_lat=90.0, pole_lon=0.0, stand_lon=0.0):
+    xlat = np.ascontiguousarray(xlat, np.float32)
+    xlon = np.ascontiguousarray(xlon, np.float32)
+    mx = np.empty_like(xlat)
+    my = np.empty_like(xlat)
+    f = C.c_float
+    lib().orc_get_map_factor(C.byref(dom), fptr(xlat), fptr(xlon), fptr(mx), fptr(my), C.c_long(xlat.size),
+                             f(truelat1), f(truelat2), f(pole_lat), f(pole_lon), f(stand_lon))
+    return mx, my
+
+
+def get_coriolis(xlat):
+    xlat = np.ascontiguousarray(xlat, np.float32)
+    fo = np.empty_like(xlat)
+    e = np.empty_like(xlat)
+    lib().orc_get_coriolis(fptr(xlat), fptr(fo), fptr(e), C.c_long(xlat.size))
+    return fo, e
+
+
+def get_rotang(iproj, xlat, xlon, truelat1, truelat2, stand_lon):
+    xlat = np.ascontiguousarray(xlat, np.float32)
+    xlon = np.ascontiguousarray(xlon, np.float32)
+    ny, nx = xlat.shape
+    cosa = np.empty_like(xlat)
+    sina = np.empty_like(xlat)
+    f = C.c_float
+    lib().orc_get_rotang(int(iproj), fptr(xlat), fptr(xlon), fptr(cosa), fptr(sina), 1, 1, nx, ny, f(truelat1),
+                         f(truelat2), f(stand_lon))
+    return cosa, sina
+
+
+def calc_dfd(which, src, sr, mapfac, dom_d):
+    src = np.ascontiguousarray(src, np.float32)
+    a3 = src if src.ndim == 3 else src[None]
+    nz, ny, nx = a3.shape
+    dst = np.empty_like(src)
+    fn = lib().orc_calc_dfdx if which == "x" else lib().orc_calc_dfdy
+    fn(fptr(src), fptr(dst), 1, 1, 1, nx, ny, nz, int(sr), fptr(None if mapfac is None else np.ascontiguousarray(mapfac, np.float32)), C.c_float(dom_d))
+    return dst
+
+
+def search_order(x0, y0, sx, ex, sy, ey, maxdepth, maxn=100000):
+    xs = np.zeros(maxn, np.int32)
+    ys = np.zeros(maxn, np.int32)
+    n = lib().orc_search_order(int(x0), int(y0), int(sx), int(ex), int(sy), int(ey), int(maxdepth), iptr(xs), iptr(ys), maxn)
+    return xs[:n], ys[:n]

@@ -1,0 +1,193 @@
+"""GPU parity: geogrid calc_field pieces (accumulators with the quadtree rule, per-point fallback, finish)."""
+import numpy as np
+import pytest
+
+from tests.util import assert_bitexact, conus_like, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def tiles_for(domain_ll, dxdeg, tile_n, bdr, known_lat=-89.99583, known_lon=-179.99583):
+    """regular_ll dataset like topo_30s / modis_landuse_30s: global index space, tile_n x tile_n tiles."""
+    lat0, lat1, lon0, lon1 = domain_ll
+    ix0 = int(np.floor((lon0 - known_lon) / dxdeg)) + 1
+    ix1 = int(np.ceil((lon1 - known_lon) / dxdeg)) + 1
+    iy0 = int(np.floor((lat0 - known_lat) / dxdeg)) + 1
+    iy1 = int(np.ceil((lat1 - known_lat) / dxdeg)) + 1
+    tiles = []
+    ty = tile_n * ((iy0 - 1) // tile_n) + 1
+    while ty <= iy1:
+        tx = tile_n * ((ix0 - 1) // tile_n) + 1
+        while tx <= ix1:
+            tiles.append((tx - bdr, ty - bdr))
+            tx += tile_n
+        ty += tile_n
+    return tiles
+
+
+def run_field(orc, handle, itype, chain, nk, start_k, tile_fn, tile_n, bdr, dxdeg, nx=60, ny=50, dx=9000.0,
+              landmask=None, mask_val=-1.0, msg=1e20, fill=1e20, ilevel=1, scale=None, stag=1, sr=1):
+    from wps_b200 import capi
+    odom, gdom = conus_like(nx, ny, dx, 30.0, 60.0, -98.0, 39.0, -105.0)
+    orc.set_transc_mode(1)
+    gx, gy = nx + 6, ny + 6  # patch +- HALO_WIDTH as process_tile does
+    xlat, xlon = orc.get_lat_lon_fields(odom, -2, -2, gx, gy, stag)
+    kw = dict(dlat=dxdeg, dlon=dxdeg, known_x=1.0, known_y=1.0, known_lat=-89.99583, known_lon=-179.99583)
+    osrc, gsrc = orc.push_source_projection(orc.PROJ_LATLON, **kw), capi.push_source_projection(capi.PROJ_LATLON, **kw)
+    dom_ll = (float(xlat.min()) - 0.3, float(xlat.max()) + 0.3, float(xlon.min()) - 0.3, float(xlon.max()) + 0.3)
+    tiles = tiles_for(dom_ll, dxdeg, tile_n, bdr)
+    rng = np.random.default_rng(99)
+    init = rng.uniform(-1, 1, (nk, gy, gx)).astype(np.float32)  # "uninitialised" field content, same on both sides
+    field_g = init.copy()
+    nz = 1 if itype == capi.CATEGORICAL else nk
+    handle.geogrid_field_begin(gdom, stag, xlat, xlon, -2, -2, start_k, field_g, landmask)
+    handle.geogrid_level_begin(gsrc, ilevel, itype, chain, msg, fill, mask_val, scale, sr, sr)
+    field_o = init.copy()
+    count_o = np.zeros_like(field_o)
+    nxw = (gx + 31) // 32
+    processed = np.zeros((gy, nxw), np.int32)
+    level = np.zeros((gy, nxw), np.int32)
+    tn = tile_n + 2 * bdr
+    ninv = 0
+    for (tx, ty) in tiles:
+        tile = tile_fn(tx, ty, tn, nz)
+        handle.geogrid_add_tile(tile, tx, ty, start_k if itype != capi.CATEGORICAL else 1, bdr)
+        if itype == capi.CATEGORICAL:
+            ninv += orc.accum_categorical(osrc, odom, stag, tile[0], tx, ty, bdr, field_o, -2, -2, start_k, processed, level,
+                                          ilevel, msg, float(sr), float(sr))
+        elif itype == capi.SP_CONTINUOUS:
+            orc.accum_continuous(osrc, odom, stag, tile, tx, ty, start_k, bdr, field_o, count_o, -2, -2, start_k, processed,
+                                 level, msg, float(sr), float(sr))
+        ninv += orc.tile_point_fallback(osrc, itype, tile, tx, ty, start_k if itype != capi.CATEGORICAL else 1, bdr, xlat, xlon,
+                                        landmask, landmask is not None and stag == 1, mask_val, chain, msg, fill, field_o,
+                                        count_o, -2, -2, start_k, processed, level)
+    handle.geogrid_level_end()
+    proc_g = np.zeros_like(processed)
+    ninv_g = handle.geogrid_field_finish(proc_g)
+    orc.calc_field_finish(itype, field_o, count_o, landmask, landmask is not None and stag == 1, mask_val, fill, scale,
+                          -2, -2, start_k, processed, level)
+    assert (proc_g == processed).all(), "processed_domain bits differ"
+    assert ninv_g == ninv
+    return field_g, field_o, len(tiles)
+
+
+def cat_tile(tx, ty, tn, nz, ncat=21, missing=None):
+    j, i = np.mgrid[ty:ty + tn, tx:tx + tn]
+    patch = ((i // 7) * 31 + (j // 5) * 17) % ncat + 1
+    noise = (i * 7919 + j * 104729) % 13 == 0
+    t = np.where(noise, (i + j) % ncat + 1, patch).astype(np.float32)
+    if missing is not None:
+        t[(i * 31 + j * 57) % 11 == 0] = missing
+    return t[None]
+
+
+def topo_tile(tx, ty, tn, nz):
+    j, i = np.mgrid[ty:ty + tn, tx:tx + tn]
+    h = np.round(1500 + 1200 * np.sin(i / 37.0) * np.cos(j / 53.0) + ((i * 13 + j * 7) % 17))
+    return np.stack([h + 10 * k for k in range(nz)]).astype(np.float32)
+
+
+def test_categorical_landuse(orc, handle):
+    """30-arcsec 21-category land use onto a 9-km Lambert patch: counts are integer-exact."""
+    from wps_b200 import capi
+    g, o, nt = run_field(orc, handle, capi.CATEGORICAL, "nearest_neighbor", 21, 1, cat_tile, 120, 0, 0.00833333)
+    assert nt >= 4
+    assert_bitexact(g, o, "LANDUSEF counts")
+
+
+def test_categorical_with_missing_landmask_and_invalid(orc, handle):
+    from wps_b200 import capi
+    rng = np.random.default_rng(1)
+    lm = (rng.random((56, 66)) < 0.7).astype(np.float32)
+    fn = lambda tx, ty, tn, nz: cat_tile(tx, ty, tn, nz, ncat=23, missing=np.float32(255.0))
+    g, o, _ = run_field(orc, handle, capi.CATEGORICAL, "nearest_neighbor", 21, 1, fn, 150, 0, 0.00833333, landmask=lm,
+                        mask_val=0.0, msg=255.0)
+    assert_bitexact(g, o, "categorical with missing / invalid categories / landmask")
+
+
+def test_categorical_coarse_source_point_fallback(orc, handle):
+    """Source coarser than the domain (10-arcmin -> 9 km is ~2 pixels per cell... use 0.25 deg): most cells get no
+    pixel from accum_categorical and are filled by get_point + one-hot."""
+    from wps_b200 import capi
+    g, o, _ = run_field(orc, handle, capi.CATEGORICAL, "nearest_neighbor", 21, 1, cat_tile, 40, 0, 0.25, nx=70, ny=60, dx=9000.0)
+    assert_bitexact(g, o, "coarse categorical")
+
+
+def test_categorical_overlay_half_area_rule(orc, handle):
+    """priority level > 1: cells covered by less than half a cell of source data are cleared after each tile."""
+    from wps_b200 import capi
+    g, o, _ = run_field(orc, handle, capi.CATEGORICAL, "nearest_neighbor", 21, 1, cat_tile, 64, 0, 0.05, nx=40, ny=36,
+                        dx=9000.0, ilevel=2)
+    assert_bitexact(g, o, "overlay categorical")
+
+
+def test_sp_continuous_topography(orc, handle):
+    """average_gcell(4.0)+four_pt+average_4pt on 30-arcsec integer topography with tile_bdr=3: sums of integers are
+    exact in binary32, so the result is bit-exact despite the different summation order."""
+    from wps_b200 import capi
+    g, o, nt = run_field(orc, handle, capi.SP_CONTINUOUS, "average_gcell(4.0)+four_pt+average_4pt", 1, 1, topo_tile, 120, 3,
+                         0.00833333, scale=None)
+    assert_bitexact(g, o, "HGT_M")
+
+
+def test_sp_continuous_multilevel_scaled_landmask(orc, handle):
+    from wps_b200 import capi
+    rng = np.random.default_rng(2)
+    lm = (rng.random((56, 66)) < 0.8).astype(np.float32)
+    g, o, _ = run_field(orc, handle, capi.SP_CONTINUOUS, "average_gcell(4.0)+four_pt+average_4pt", 3, 1, topo_tile, 100, 2,
+                        0.00833333, landmask=lm, mask_val=0.0, fill=-999.0, scale=0.01)
+    assert_bitexact(g, o, "3-level SP_CONTINUOUS")
+
+
+@pytest.mark.parametrize("chain", ["four_pt", "sixteen_pt+four_pt+average_4pt+search(5)", "wt_average_4pt+search",
+                                   "average_16pt+average_4pt"])
+def test_continuous_pointwise(orc, handle, chain):
+    """CONTINUOUS fields (e.g. 12 monthly albedo levels from a 0.144-deg dataset): per-point interp_sequence in each tile."""
+    from wps_b200 import capi
+
+    def fn(tx, ty, tn, nz):
+        t = topo_tile(tx, ty, tn, nz)
+        j, i = np.mgrid[ty:ty + tn, tx:tx + tn]
+        t[:, (i * 3 + j) % 9 == 0] = -1e30
+        return t
+    g, o, _ = run_field(orc, handle, capi.CONTINUOUS, chain, 4, 1, fn, 50, 3, 0.144, nx=64, ny=48, dx=9000.0, msg=-1e30,
+                        fill=-500.0)
+    assert_bitexact(g, o, "continuous %s" % chain)
+
+
+def test_raw_tile_decode(orc, handle):
+    """wpsgpu_geogrid_add_tile_raw decodes read_geogrid.c byte layouts (big/little endian, signed, 1-4 bytes, row flip)
+    identically to decoding on the host."""
+    from wps_b200 import capi
+    odom, gdom = conus_like(30, 30, 9000.0, 30.0, 60.0, -98.0, 39.0, -105.0)
+    orc.set_transc_mode(1)
+    xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, 30, 30, 1)
+    kw = dict(dlat=0.01, dlon=0.01, known_x=1.0, known_y=1.0, known_lat=37.5, known_lon=-107.0)
+    gsrc = capi.push_source_projection(capi.PROJ_LATLON, **kw)
+    rng = np.random.default_rng(0)
+    tn = 300
+    for wordsize, signed, endian, row_order in ((1, 0, 0, 1), (2, 1, 0, 1), (2, 1, 1, 2), (3, 1, 0, 1), (4, 1, 1, 1), (1, 1, 0, 2)):
+        hi = 1 << (8 * wordsize - (1 if signed else 0))
+        lo = -hi if signed else 0
+        vals = rng.integers(max(lo, -30000), min(hi, 30000), (1, tn, tn)).astype(np.int64)
+        u = np.where(vals < 0, vals + (1 << (8 * wordsize)), vals).astype(np.uint64)
+        stored = vals[:, ::-1, :] if row_order == 2 else vals
+        us = np.where(stored < 0, stored + (1 << (8 * wordsize)), stored).astype(np.uint64)
+        order = range(wordsize) if endian == 1 else range(wordsize - 1, -1, -1)
+        raw = np.stack([((us >> (8 * b)) & 0xff).astype(np.uint8) for b in order], axis=-1).copy()
+        dec = vals.astype(np.float32)
+        if signed and wordsize < 4:  # read_geogrid.c: `ival > 2^(8w-1)` (strictly greater) => exactly 2^(8w-1) stays positive
+            dec = np.where(u == (1 << (8 * wordsize - 1)), np.float32(1 << (8 * wordsize - 1)), dec).astype(np.float32)
+        res = []
+        for mode in ("raw", "float"):
+            field = np.zeros((1, 30, 30), np.float32)
+            handle.geogrid_field_begin(gdom, 1, xlat, xlon, 1, 1, 1, field, None)
+            handle.geogrid_level_begin(gsrc, 1, capi.SP_CONTINUOUS, "average_gcell(1.0)+four_pt", 1e20, 1e20, -1.0)
+            if mode == "raw":
+                handle.geogrid_add_tile_raw(raw, (1, tn, tn), wordsize, signed, endian, row_order, 1, 1, 1, 0)
+            else:
+                handle.geogrid_add_tile(dec, 1, 1, 1, 0)
+            handle.geogrid_level_end()
+            handle.geogrid_field_finish()
+            res.append(field)
+        assert_bitexact(res[0], res[1], "raw decode wordsize=%d signed=%d endian=%d row_order=%d" % (wordsize, signed, endian, row_order))

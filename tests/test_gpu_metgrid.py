@@ -1,0 +1,239 @@
+"""GPU parity: batched metgrid interpolation (wpsgpu_metgrid_*) vs the CPU oracle's interp_met_field.
+
+Bar: bit-exact r_arr and new_pts for every chain (the CUDA path uses the reference's operation order with
+-fmad=false), on seeded inputs at sizes the oracle finishes in seconds.  Lambert/other-source coordinate
+transforms use the FP64-then-round policy on both sides (oracle transc mode 1)."""
+import numpy as np
+import pytest
+
+from tests.util import (assert_bitexact, bits_to_bool, bool_to_bits, conus_like, halo, landsea, latlon_source,
+                        synth_field)
+
+pytestmark = pytest.mark.gpu
+
+CHAINS = ["sixteen_pt+four_pt+average_4pt", "four_pt+average_4pt", "nearest_neighbor", "four_pt",
+          "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search", "wt_average_4pt", "average_16pt+nearest_neighbor",
+          "wt_average_16pt+four_pt", "sixteen_pt", "four_pt+average_4pt+search", "search", "search(5)",
+          "average_4pt+search(3)", "sixteen_pt+search(12)"]
+
+
+def make_domain(orc, handle, nx=101, ny=91, dx=30000.0, ref_lat=34.83, ref_lon=-81.03, stagger="M"):
+    odom, gdom = conus_like(nx, ny, dx, truelat1=30.0, truelat2=60.0, stand_lon=-98.0, ref_lat=ref_lat, ref_lon=ref_lon)
+    orc.set_transc_mode(1)
+    st = {"M": orc.M, "U": orc.U, "V": orc.V}[stagger]
+    gx, gy = nx, ny
+    xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, gx, gy, st)
+    return xlat, xlon
+
+
+def run_case(orc, handle, xlat, xlon, slabs, src, chain, sm=(1, 1), sd=None, bdr=3, minx=-2, miny=1, missing=1e20,
+             fill=1e20, masked=-2.0, mask_val=(1e20, 1e20, 1e20), mask_rel="   ", masks=(None, None, None),
+             landmask=None, valid=None, r0=None, pbw=0, fstag=1, grid_id=0):
+    from wps_b200 import capi
+    osrc, gsrc = src
+    ny, nx = xlat.shape
+    if sd is None:
+        sd = (sm[0], sm[0] + nx - 1, sm[1], sm[1] + ny - 1)
+    fo_o = orc.field_opts(chain, missing, fill, masked, mask_val, mask_rel)
+    fo_g = capi.field_opts(chain, missing, fill, masked, mask_val, mask_rel)
+    handle.metgrid_set_grid(grid_id, xlat, xlon, sm[0], sm[1])
+    if landmask is not None:
+        handle.metgrid_set_landmask(grid_id, landmask)
+    handle.metgrid_set_domain(*sd)
+    outs = []
+    for slab in slabs:
+        r = np.zeros((ny, nx), np.float32) if r0 is None else r0.copy()
+        npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+        handle.metgrid_enqueue_slab(gsrc, fo_g, slab, minx, miny, bdr, grid_id, fstag, r, npw, valid_mask=valid,
+                                    masks=masks, use_landmask=landmask is not None, process_bdy_width=pbw)
+        outs.append((r, npw))
+    handle.metgrid_flush()
+    orc.set_transc_mode(1)
+    for slab, (r, npw) in zip(slabs, outs):
+        r_ref, np_ref = orc.interp_met_field(osrc, fo_o, fstag, xlat, xlon, sm[0], sm[1], sd, slab, minx, miny, bdr,
+                                             mask=masks[0], land_mask=masks[1], water_mask=masks[2], landmask=landmask,
+                                             process_bdy_width=pbw, r_arr=None if r0 is None else r0.copy(),
+                                             valid_mask=valid)
+        assert (npw == np_ref).all(), "new_pts bits differ for chain %s: %d words" % (chain, (npw != np_ref).sum())
+        bits = bits_to_bool(np_ref, nx) | (bits_to_bool(valid, nx) if valid is not None else False)
+        # r_arr is defined wherever a bit is set (new or previously valid) or it was filled
+        assert_bitexact(r, r_ref, "r_arr chain=%s" % chain)
+    return outs
+
+
+@pytest.mark.parametrize("chain", CHAINS)
+def test_chain_unmasked_global_latlon(orc, handle, chain):
+    """1-degree GFS-like global source -> 30-km Lambert domain (config 1 geometry), clean data + zeros."""
+    xlat, xlon = make_domain(orc, handle)
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    slabs = [halo(synth_field(360, 181, s, zeros=0.002)) for s in range(3)]
+    run_case(orc, handle, xlat, xlon, slabs, src, chain, fill=0.0)
+
+
+@pytest.mark.parametrize("chain", CHAINS)
+def test_chain_missing_values(orc, handle, chain):
+    """Source slabs with 20 % missing values (missing_value=-1.E30): exercises every fallback edge."""
+    xlat, xlon = make_domain(orc, handle, nx=77, ny=63)
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    slabs = [halo(synth_field(360, 181, 10 + s, missing=np.float32(-1e30), frac_missing=0.2, zeros=0.01)) for s in range(2)]
+    run_case(orc, handle, xlat, xlon, slabs, src, chain, missing=np.float32(-1e30), fill=285.0)
+
+
+@pytest.mark.parametrize("rel,mv", [(" ", 0.0), (" ", 1.0), ("<", 0.5), (">", 0.5)])
+@pytest.mark.parametrize("chain", ["sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search", "four_pt+average_4pt",
+                                   "nearest_neighbor", "average_16pt+search(7)", "wt_average_4pt+search"])
+def test_interp_mask(orc, handle, chain, rel, mv):
+    """interp_mask=LANDSEA(v) / (<v) / (>v) with a LANDSEA.mask slab."""
+    xlat, xlon = make_domain(orc, handle, nx=83, ny=71)
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    ls = halo(landsea(360, 181))
+    slabs = [halo(synth_field(360, 181, 20 + s, missing=np.float32(-1e30), frac_missing=0.05)) for s in range(2)]
+    run_case(orc, handle, xlat, xlon, slabs, src, chain, missing=np.float32(-1e30), fill=1.0,
+             mask_val=(mv, 1e20, 1e20), mask_rel=rel + "  ", masks=(ls, None, None))
+
+
+@pytest.mark.parametrize("masked", [0.0, 1.0, -1.0])
+def test_landmask_masked(orc, handle, masked):
+    """masked=water|land|both with the domain LANDMASK (process_domain_module.F:2497-2566)."""
+    xlat, xlon = make_domain(orc, handle, nx=64, ny=70)
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    ls = halo(landsea(360, 181))
+    rng = np.random.default_rng(5)
+    lm = (rng.random(xlat.shape) < 0.6).astype(np.float32)
+    slabs = [halo(synth_field(360, 181, 30, missing=np.float32(-1e30), frac_missing=0.1))]
+    if masked == -1.0:  # SKINTEMP-style: interp_land_mask / interp_water_mask
+        run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search",
+                 missing=np.float32(-1e30), fill=0.0, masked=masked, mask_val=(1e20, 1.0, 0.0), mask_rel="   ",
+                 masks=(None, ls, ls), landmask=lm)
+    else:
+        run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search",
+                 missing=np.float32(-1e30), fill=1.0, masked=masked, mask_val=(masked, 1e20, 1e20), mask_rel="   ",
+                 masks=(ls, None, None), landmask=lm)
+
+
+def test_valid_mask_priority(orc, handle):
+    """Second (higher-priority) source over a field that already holds data: r_arr/valid_mask carry-over."""
+    xlat, xlon = make_domain(orc, handle, nx=70, ny=50)
+    ny, nx = xlat.shape
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    rng = np.random.default_rng(7)
+    r0 = rng.uniform(200, 300, (ny, nx)).astype(np.float32)
+    valid = bool_to_bits(rng.random((ny, nx)) < 0.5)
+    slabs = [halo(synth_field(360, 181, 40, missing=np.float32(-1e30), frac_missing=0.5))]
+    for fill in (1e20, 0.0):
+        run_case(orc, handle, xlat, xlon, slabs, src, "four_pt", missing=np.float32(-1e30), fill=np.float32(fill),
+                 valid=valid, r0=r0)
+
+
+def test_process_bdy_width_and_staggers(orc, handle):
+    """process_only_bdy: interior points get fill_missing; U/V staggered fields widen the band by 2."""
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    slabs = [halo(synth_field(360, 181, 50, kind="wind"))]
+    for stag, fstag in (("M", 1), ("U", 2), ("V", 3)):
+        nx, ny = 60 + (stag == "U"), 48 + (stag == "V")
+        odom, _ = conus_like(60, 48, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)
+        orc.set_transc_mode(1)
+        xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, nx, ny, fstag)
+        run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+average_4pt", fill=0.0, pbw=5, fstag=fstag,
+                 sd=(1, 60, 1, 48), grid_id=fstag)
+
+
+def test_regional_sources(orc, handle):
+    """Non-global sources (bdr=0): regional lat-lon, Lambert, polar stereographic, Mercator; domain partly outside."""
+    from wps_b200 import capi
+    xlat, xlon = make_domain(orc, handle, nx=90, ny=80)
+    rng = np.random.default_rng(11)
+    f = rng.uniform(250, 300, (61, 81)).astype(np.float32)
+    # regional lat-lon 0.5 deg covering 20N-50N, 110W-70W
+    kw = dict(dlat=0.5, dlon=0.5, known_x=1.0, known_y=1.0, known_lat=20.0, known_lon=-110.0)
+    src = (orc.push_source_projection(orc.PROJ_LATLON, **kw), capi.push_source_projection(capi.PROJ_LATLON, **kw))
+    run_case(orc, handle, xlat, xlon, [f], src, "sixteen_pt+four_pt+average_4pt", bdr=0, minx=1, miny=1, fill=0.0)
+    run_case(orc, handle, xlat, xlon, [f], src, "four_pt+average_4pt+search", bdr=0, minx=1, miny=1, fill=0.0)
+    for code, kw in ((orc.PROJ_LC, dict(stand_lon=-95.0, truelat1=25.0, truelat2=25.0, dxkm=40635.0, dykm=40635.0,
+                                        known_x=1.0, known_y=1.0, known_lat=15.0, known_lon=-115.0)),
+                     (orc.PROJ_PS, dict(stand_lon=-100.0, truelat1=60.0, dxkm=50000.0, dykm=50000.0, known_x=1.0,
+                                        known_y=1.0, known_lat=12.0, known_lon=-120.0)),
+                     (orc.PROJ_MERC, dict(truelat1=20.0, dxkm=45000.0, dykm=45000.0, known_x=1.0, known_y=1.0,
+                                          known_lat=15.0, known_lon=-118.0))):
+        src = (orc.push_source_projection(code, **kw), capi.push_source_projection(code, **kw))
+        run_case(orc, handle, xlat, xlon, [f], src, "sixteen_pt+four_pt+average_4pt", bdr=0, minx=1, miny=1, fill=0.0)
+
+
+def test_gaussian_source(orc, handle):
+    from wps_b200 import capi
+    xlat, xlon = make_domain(orc, handle, nx=50, ny=40)
+    nlat = 47  # T62-like: 94 latitudes, 192 longitudes
+    kw = dict(dlat=float(nlat), dlon=1.875, known_x=1.0, known_y=1.0, known_lat=88.542, known_lon=0.0)
+    src = (orc.push_source_projection(orc.PROJ_GAUSS, **kw), capi.push_source_projection(capi.PROJ_GAUSS, **kw))
+    f = halo(synth_field(192, 94, 3))
+    run_case(orc, handle, xlat, xlon, [f], src, "sixteen_pt+four_pt+average_4pt", fill=0.0)
+
+
+def test_dateline_retry_and_southern_hemisphere(orc, handle):
+    """Domain straddling the dateline with a 0..360 source (exercises the lon+360 retry, :2637-2665) and an SH domain."""
+    odom, _ = conus_like(80, 60, 45000.0, -30.0, -60.0, 175.0, -40.0, 178.0)
+    orc.set_transc_mode(1)
+    xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, 80, 60, orc.M)
+    # regional source 120E..240E expressed in 0..360 longitudes (no halo)
+    from wps_b200 import capi
+    kw = dict(dlat=0.5, dlon=0.5, known_x=1.0, known_y=1.0, known_lat=-70.0, known_lon=120.0)
+    src = (orc.push_source_projection(orc.PROJ_LATLON, **kw), capi.push_source_projection(capi.PROJ_LATLON, **kw))
+    f = np.random.default_rng(2).uniform(0, 10, (121, 241)).astype(np.float32)
+    run_case(orc, handle, xlat, xlon, [f], src, "sixteen_pt+four_pt+average_4pt", bdr=0, minx=1, miny=1, fill=0.0)
+    src = latlon_source(720, 361, -0.5, 0.5, 90.0, 0.0)
+    run_case(orc, handle, xlat, xlon, [halo(synth_field(720, 361, 9))], src, "sixteen_pt+four_pt+average_4pt", fill=0.0)
+
+
+def test_search_literal_fallback(orc, handle):
+    """Depth-limited searches and an all-missing slab (search exhausts the array): literal-queue fallback."""
+    xlat, xlon = make_domain(orc, handle, nx=40, ny=30)
+    kw = dict(dlat=0.5, dlon=0.5, known_x=1.0, known_y=1.0, known_lat=25.0, known_lon=-95.0)
+    from wps_b200 import capi
+    src = (orc.push_source_projection(orc.PROJ_LATLON, **kw), capi.push_source_projection(capi.PROJ_LATLON, **kw))
+    rng = np.random.default_rng(3)
+    f = rng.uniform(1, 2, (41, 61)).astype(np.float32)
+    f[rng.random(f.shape) < 0.97] = -1e30
+    allmiss = np.full((41, 61), -1e30, np.float32)
+    for chain in ("search(1)", "search(2)", "search(3)", "search(4)", "search(6)", "search(9)", "search(40)", "search"):
+        run_case(orc, handle, xlat, xlon, [f, allmiss], src, chain, bdr=0, minx=1, miny=1, missing=np.float32(-1e30),
+                 fill=7.0)
+
+
+def test_batch_many_fields_one_flush(orc, handle):
+    """One flush holding slabs of different fields/staggers/chains (the process_intermediate_fields record loop)."""
+    from wps_b200 import capi
+    src_o, src_g = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    odom, _ = conus_like(50, 44, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)
+    orc.set_transc_mode(1)
+    grids = {}
+    for gid, (st, nx, ny) in {0: (orc.M, 50, 44), 1: (orc.U, 51, 44), 2: (orc.V, 50, 45)}.items():
+        grids[gid] = orc.get_lat_lon_fields(odom, 1, 1, nx, ny, st)
+        handle.metgrid_set_grid(gid, grids[gid][0], grids[gid][1], 1, 1)
+    handle.metgrid_set_domain(1, 50, 1, 44)
+    ls = halo(landsea(360, 181))
+    plan = []
+    for lev in range(5):
+        plan.append(("sixteen_pt+four_pt+average_4pt", 0, 1, 1e20, 0.0, None, 100 + lev, "smooth"))
+        plan.append(("sixteen_pt+four_pt+average_4pt", 1, 2, 1e20, 0.0, None, 200 + lev, "wind"))
+        plan.append(("sixteen_pt+four_pt+average_4pt", 2, 3, 1e20, 0.0, None, 300 + lev, "wind"))
+    plan.append(("four_pt+average_4pt", 0, 1, 1e20, 1e20, None, 400, "smooth"))
+    plan.append(("sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search", 0, 1, -1e30, 285.0, ls, 500, "smooth"))
+    plan.append(("nearest_neighbor", 0, 1, 1e20, -1.0, None, 600, "noise"))
+    outs = []
+    for chain, gid, fstag, msg, fill, mask, seed, kind in plan:
+        slab = halo(synth_field(360, 181, seed, kind=kind, missing=np.float32(msg), frac_missing=0.1 if msg < 0 else 0.0))
+        xlat, xlon = grids[gid]
+        ny, nx = xlat.shape
+        r = np.zeros((ny, nx), np.float32)
+        npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+        mv = (0.0, 1e20, 1e20) if mask is not None else (1e20, 1e20, 1e20)
+        fo_g = capi.field_opts(chain, np.float32(msg), np.float32(fill), -2.0, mv)
+        fo_o = orc.field_opts(chain, np.float32(msg), np.float32(fill), -2.0, mv)
+        handle.metgrid_enqueue_slab(src_g, fo_g, slab, -2, 1, 3, gid, fstag, r, npw, masks=(mask, None, None))
+        outs.append((slab, fo_o, gid, fstag, mask, r, npw))
+    handle.metgrid_flush()
+    for slab, fo_o, gid, fstag, mask, r, npw in outs:
+        xlat, xlon = grids[gid]
+        r_ref, np_ref = orc.interp_met_field(src_o, fo_o, fstag, xlat, xlon, 1, 1, (1, 50, 1, 44), slab, -2, 1, 3, mask=mask)
+        assert (npw == np_ref).all()
+        assert_bitexact(r, r_ref, "batched slab")

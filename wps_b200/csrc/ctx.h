@@ -1,0 +1,110 @@
+// ctx.h -- handle, error plumbing and the device arena of libwpsgpu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/wpsgpu.h"
+#include "proj.cuh"
+
+namespace wps {
+
+void set_error(const char* fmt, ...);
+
+#define WPS_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            wps::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+            return -100;                                                                      \
+        }                                                                                     \
+    } while (0)
+#define WPS_CHECK(cond, code, ...)                 \
+    do {                                           \
+        if (!(cond)) { wps::set_error(__VA_ARGS__); return (code); } \
+    } while (0)
+#define WPS_TRY(expr)                   \
+    do {                                \
+        int rc_ = (expr);               \
+        if (rc_ != 0) return rc_;       \
+    } while (0)
+
+// Grow-only bump arena in device memory; reset at the start of every batch.  All per-batch staging
+// (source slabs, masks, outputs, job tables) lives here so a flush does O(1) cudaMalloc calls.
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    std::vector<void*> retired;  // older, smaller blocks still referenced by in-flight work
+    int reserve(size_t bytes, cudaStream_t st);
+    void* take(size_t bytes)
+    {
+        size_t a = (off + 255) & ~size_t(255);
+        if (a + bytes > cap) return nullptr;
+        off = a + bytes;
+        return base + a;
+    }
+    void reset() { off = 0; }
+    void release();
+};
+
+struct DstGrid {
+    bool set = false;
+    int sm1 = 0, em1 = 0, sm2 = 0, em2 = 0;
+    float *d_xlat = nullptr, *d_xlon = nullptr, *d_landmask = nullptr;
+    bool own = false;            // device copies owned by the handle (host pointer mode)
+    uint64_t version = 0;
+    int nx() const { return em1 - sm1 + 1; }
+    int ny() const { return em2 - sm2 + 1; }
+    size_t npts() const { return (size_t)nx() * ny(); }
+};
+
+struct CoordCacheEntry {
+    uint64_t grid_version;
+    float2* d_xy;  // (rx, ry) of lltoxy(xlat, xlon) with the source projection, M stagger
+};
+
+struct QueuedSlab {
+    wpsgpu_proj proj;
+    wpsgpu_field_opts fo;
+    wpsgpu_slab s;
+};
+
+struct GeoState;  // geogrid.cu
+
+}  // namespace wps
+
+struct wpsgpu_ctx {
+    int device = 0;
+    int ptr_mode = WPSGPU_PTR_HOST;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int64_t launches = 0;
+    wps::Arena arena;
+    wps::DstGrid grids[8];
+    int sd1 = 0, ed1 = 0, sd2 = 0, ed2 = 0;
+    bool domain_set = false;
+    uint64_t grid_version_counter = 0;
+    std::map<std::string, wps::CoordCacheEntry> coord_cache;
+    std::vector<wps::QueuedSlab> queue;
+    wps::GeoState* geo = nullptr;
+    // small persistent device scratch (counters etc.)
+    int* d_counters = nullptr;
+    // search fallback scratch
+    void* d_search_scratch = nullptr;
+    size_t search_scratch_bytes = 0;
+    // CUDA events bracketing the dominant kernel of the last metgrid flush (roofline measurement)
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    double last_points = 0.0;
+};
+
+namespace wps {
+// copy helpers honouring the pointer mode: returns a device pointer for `p` (count floats/ints);
+// in host mode stages through the arena with an async H2D on the handle's stream.
+int stage_in(wpsgpu_ctx* h, const void* p, size_t bytes, void** dptr);
+int alloc_out(wpsgpu_ctx* h, void* user_ptr, size_t bytes, void** dptr);
+int copy_out(wpsgpu_ctx* h, void* user_ptr, const void* dptr, size_t bytes);
+int upload_gauss(wpsgpu_ctx* h, const wpsgpu_proj& p, const float** d_gauss);
+}  // namespace wps

@@ -1,0 +1,568 @@
+// geogrid.cu -- calc_field (process_tile_module.F:1208-1681) on device: per-tile accumulation with the
+// reference's quadtree "four corners agree" rule (proc_point_module.F:218-458,553-779), per-point fallback
+// (get_point, :788-855), post-processing, and the raw tile decode of read_geogrid.c.
+#include <algorithm>
+#include "ctx.h"
+#include "interp.cuh"
+
+namespace wps {
+
+#define GEO_OUTSIDE 100000000  // OUTSIDE_DOMAIN, misc_definitions_module.F:18
+
+struct GeoState {
+    bool field_open = false, level_open = false;
+    wpsgpu_geo_field f;
+    wpsgpu_geo_level l;
+    int nx = 0, ny = 0, nk = 0, nxw = 0;
+    size_t npts = 0;
+    float *d_field = nullptr, *d_xlat = nullptr, *d_xlon = nullptr, *d_landmask = nullptr, *d_count = nullptr;
+    int *d_processed = nullptr, *d_level = nullptr;
+    float2* d_src_xy = nullptr;       // lltoxy(SOURCE_PROJ) of every destination point (get_point / is_point_in_tile)
+    int* d_acc_cnt = nullptr;         // per-tile accumulation: counts [nk][ny][nx]
+    double* d_acc_sum = nullptr;      // per-tile accumulation: sums (continuous)
+    int* d_touched = nullptr;         // per-tile: cell was reached by a credit attempt
+    unsigned long long* d_invalid = nullptr;
+    float* d_tile = nullptr; size_t tile_cap = 0;
+    int2* d_wm = nullptr; size_t wm_cap = 0;
+    void* d_raw = nullptr; size_t raw_cap = 0;
+    Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
+    void* d_lit = nullptr; size_t lit_bytes = 0;
+    const float* d_gauss_src = nullptr; const float* d_gauss_dom = nullptr;
+    bool own_field = false, own_ll = false;
+    bool has_search = false; int max_depth = 0;
+};
+
+struct GeoK {  // kernel-side view
+    DevProj src, dom;
+    int istagger, itype;
+    int start_i, end_i, start_j, end_j, start_k, end_k, nx, ny, nk, nxw;
+    size_t npts;
+    float sr_x, sr_y, msg_val, msg_fill_val, mask_val;
+    float* field; float* count; const float* landmask;
+    int* processed; int* level;
+    int* acc_cnt; double* acc_sum; int* touched; unsigned long long* invalid;
+    // current tile
+    const float* tile; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny;
+    int2* wm;
+    int ops[WPSGPU_MAX_OPS], opts[WPSGPU_MAX_OPS];
+};
+
+__device__ __forceinline__ bool bit_test(const int* w, int nxw, int ii, int jj) { return (w[(size_t)jj * nxw + (ii >> 5)] >> (ii & 31)) & 1; }
+__device__ __forceinline__ void bit_set_atomic(int* w, int nxw, int ii, int jj) { atomicOr(w + (size_t)jj * nxw + (ii >> 5), (int)(1u << (ii & 31))); }
+
+// where_maps_to for every pixel of the tile (proc_point_module.F:245-310)
+__global__ void k_geo_wm(GeoK g)
+{
+    int ti = blockIdx.x * blockDim.x + threadIdx.x, tj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ti >= g.tnx || tj >= g.tny) return;
+    float lat, lon, rx, ry;
+    xytoll(g.src, (float)(g.smx + ti), (float)(g.smy + tj), lat, lon, WPSGPU_M);
+    lltoxy(g.dom, lat, lon, rx, ry, g.istagger);
+    rx = (rx - 0.5f) * g.sr_x + 0.5f;
+    ry = (ry - 0.5f) * g.sr_y + 0.5f;
+    int2 w;
+    if ((float)g.start_i <= rx && rx <= (float)g.end_i && (float)g.start_j <= ry && ry <= (float)g.end_j) { w.x = f_nint(rx); w.y = f_nint(ry); }
+    else { w.x = GEO_OUTSIDE; w.y = 0; }
+    g.wm[(size_t)tj * g.tnx + ti] = w;
+}
+
+// Quadtree emulation: walk the block hierarchy of process_*_block top-down for this pixel and credit the
+// first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
+__global__ void k_geo_accum(GeoK g)
+{
+    int I0 = g.smx + g.bdr, I1 = g.sMx - g.bdr, J0 = g.smy + g.bdr, J1 = g.sMy - g.bdr;
+    int pi = I0 + blockIdx.x * blockDim.x + threadIdx.x, pj = J0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (pi > I1 || pj > J1) return;
+    auto W = [&](int i, int j) { return g.wm[(size_t)(j - g.smy) * g.tnx + (i - g.smx)]; };
+    int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
+    int2 dest;
+    for (;;) {
+        int2 a = W(min_i, min_j), b = W(min_i, max_j), c = W(max_i, max_j), d = W(max_i, min_j);
+        if (a.x == b.x && a.x == c.x && a.x == d.x && a.y == b.y && a.y == c.y && a.y == d.y && a.x != GEO_OUTSIDE) { dest = a; break; }
+        if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = W(pi, pj); break; }
+        int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
+        if (pi <= ci) max_i = ci; else min_i = ci + 1;
+        if (pj <= cj) max_j = cj; else min_j = cj + 1;
+    }
+    if (dest.x == GEO_OUTSIDE) return;
+    int ii = dest.x - g.start_i, jj = dest.y - g.start_j;
+    if (bit_test(g.processed, g.nxw, ii, jj)) return;
+    size_t cell = (size_t)jj * g.nx + ii;
+    g.touched[cell] = 1;
+    size_t tn2 = (size_t)g.tnx * g.tny, toff = (size_t)(pj - g.smy) * g.tnx + (pi - g.smx);
+    if (g.itype == WPSGPU_CATEGORICAL) {
+        float v = g.tile[toff];
+        if (v != g.msg_val) {
+            int cat = (int)v;
+            if (cat >= g.start_k && cat <= g.end_k) atomicAdd(g.acc_cnt + (size_t)(cat - g.start_k) * g.npts + cell, 1);
+            else atomicAdd(g.invalid, 1ull);
+        }
+    } else {
+        for (int k = g.smz; k <= g.sMz; ++k) {
+            float v = g.tile[(size_t)(k - g.smz) * tn2 + toff];
+            if (v != g.msg_val) {
+                atomicAdd(g.acc_sum + (size_t)(k - g.start_k) * g.npts + cell, (double)v);
+                atomicAdd(g.acc_cnt + (size_t)(k - g.start_k) * g.npts + cell, 1);
+            }
+        }
+    }
+}
+
+// Fold the tile's accumulation into field / data_count with the reference's first-touch semantics
+// (proc_point_module.F:326-346) and, for ilevel>1 categorical data, the half-area rule (:165-202).
+__global__ void k_geo_merge(GeoK g, int ilevel, float src_area, float dom_area)
+{
+    size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= g.npts) return;
+    int ii = (int)(cell % g.nx), jj = (int)(cell / g.nx);
+    if (g.touched[cell]) {
+        g.touched[cell] = 0;
+        bool isnew = bit_test(g.level, g.nxw, ii, jj);
+        bool any = false;
+        if (g.itype == WPSGPU_CATEGORICAL) {
+            for (int k = 0; k < g.nk; ++k) {
+                size_t o = (size_t)k * g.npts + cell;
+                int c = g.acc_cnt[o];
+                g.acc_cnt[o] = 0;
+                float base = isnew ? g.field[o] : 0.0f;
+                g.field[o] = base + (float)c;
+                any |= c > 0;
+            }
+        } else {
+            int k0 = g.smz - g.start_k, k1 = g.sMz - g.start_k;
+            for (int k = k0; k <= k1; ++k) {
+                size_t o = (size_t)k * g.npts + cell;
+                int c = g.acc_cnt[o];
+                double s = g.acc_sum[o];
+                g.acc_cnt[o] = 0; g.acc_sum[o] = 0.0;
+                float base = isnew ? g.field[o] : 0.0f;
+                g.field[o] = base + (float)s;
+                g.count[o] = g.count[o] + (float)c;
+                any |= c > 0;
+            }
+        }
+        if (any) bit_set_atomic(g.level, g.nxw, ii, jj);
+    }
+    if (ilevel > 1 && g.itype == WPSGPU_CATEGORICAL) {
+        if (bit_test(g.level, g.nxw, ii, jj) && !bit_test(g.processed, g.nxw, ii, jj)) {
+            float rarea = 0.0f;
+            for (int k = 0; k < g.nk; ++k) rarea = rarea + g.field[(size_t)k * g.npts + cell];
+            rarea = rarea * src_area;
+            if (dom_area > 2.0f * rarea) {
+                for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + cell] = 0.0f;
+                atomicAnd(g.level + (size_t)jj * g.nxw + (ii >> 5), (int)~(1u << (ii & 31)));
+            }
+        }
+    }
+}
+
+// source-grid coordinates of every destination point (get_point / is_point_in_tile, :811-823,911-921)
+__global__ void k_geo_src_xy(DevProj src, const float* __restrict__ xlat, const float* __restrict__ xlon, size_t n, float2* __restrict__ xy)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    float rlat = xlat[p], rlon = xlon[p], rx, ry;
+    if (rlon >= 180.0f) rlon = rlon - 360.0f;
+    lltoxy(src, rlat, rlon, rx, ry, WPSGPU_M);
+    xy[p] = make_float2(rx, ry);
+}
+
+// inner loop of calc_field for one destination point (process_tile_module.F:1408-1519)
+template <int MODE>
+__device__ __forceinline__ bool geo_point(const GeoK& g, const float2* __restrict__ src_xy, size_t p, const LitScratch* ls)
+{
+    int ii = (int)(p % g.nx), jj = (int)(p / g.nx);
+    float2 xy = src_xy[p];
+    // is_point_in_tile (proc_point_module.F:928-929)
+    if (!(g.smx + g.bdr <= f_floor(xy.x + 0.5f) && f_ceiling(xy.x - 0.5f) <= g.sMx - g.bdr &&
+          g.smy + g.bdr <= f_floor(xy.y + 0.5f) && f_ceiling(xy.y - 0.5f) <= g.sMy - g.bdr)) return false;
+    if (bit_test(g.level, g.nxw, ii, jj)) return false;
+    bool lead = (MODE != 1) || ((threadIdx.x & 31) == 0);
+    if (bit_test(g.processed, g.nxw, ii, jj)) { if (lead) bit_set_atomic(g.level, g.nxw, ii, jj); return false; }
+    bool lm_ok = true;
+    if (g.landmask && (g.istagger == WPSGPU_M || g.istagger == WPSGPU_HH)) lm_ok = (g.landmask[p] != g.mask_val);
+    Src s;
+    s.m = nullptr; s.sx = g.smx; s.ex = g.sMx; s.sy = g.smy; s.ey = g.sMy; s.nx = g.tnx;
+    s.msg = g.msg_val; s.maskval = 0.0f; s.rel = REL_EQ;
+    size_t tn2 = (size_t)g.tnx * g.tny;
+    if (g.itype != WPSGPU_CATEGORICAL) {
+        if (lm_ok) {
+            float vals[1];
+            // first pass: evaluate (may defer before anything is written)
+            bool setbit = false;
+            for (int k = g.smz; k <= g.sMz; ++k) {
+                s.a = g.tile + (size_t)(k - g.smz) * tn2;
+                float temp;
+                int st = interp_sequence<MODE>(s, g.ops, g.opts, xy.x, xy.y, temp, ls);
+                if (st == ST_DEFER) return true;
+                vals[0] = temp;
+                if (lead) {
+                    size_t o = (size_t)(k - g.start_k) * g.npts + p;
+                    if (vals[0] != g.msg_val) {
+                        g.field[o] = vals[0];
+                        setbit = true;
+                        if (g.itype == WPSGPU_SP_CONTINUOUS) g.count[o] = 1.0f;
+                    } else g.field[o] = g.msg_fill_val;
+                }
+            }
+            if (lead && setbit) bit_set_atomic(g.level, g.nxw, ii, jj);
+        } else if (lead) {
+            for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + p] = g.msg_fill_val;
+        }
+    } else {
+        if (lm_ok) {
+            s.a = g.tile;
+            float temp;
+            int st = interp_sequence<MODE>(s, g.ops, g.opts, xy.x, xy.y, temp, ls);
+            if (st == ST_DEFER) return true;
+            if (lead) {
+                for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + p] = 0.0f;
+                if (temp != g.msg_val) {
+                    int c = (int)temp;
+                    if (c >= g.start_k && c <= g.end_k) g.field[(size_t)(c - g.start_k) * g.npts + p] += 1.0f;
+                    else atomicAdd(g.invalid, 1ull);
+                    bit_set_atomic(g.level, g.nxw, ii, jj);
+                }
+            }
+        } else if (lead) {
+            for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + p] = 0.0f;
+        }
+    }
+    return false;
+}
+
+__global__ void k_geo_points(GeoK g, const float2* __restrict__ src_xy, Deferred* def, unsigned long long* def_cnt)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.npts) return;
+    if (geo_point<0>(g, src_xy, p, nullptr)) {
+        unsigned long long slot = atomicAdd(def_cnt, 1ull);
+        Deferred d; d.slab = 0; d.idx = (int)p;
+        def[slot] = d;
+    }
+}
+__global__ void k_geo_points_warp(GeoK g, const float2* __restrict__ src_xy, const Deferred* def, const unsigned long long* def_cnt,
+                                  Deferred* def2, unsigned long long* def2_cnt)
+{
+    unsigned long long n = *def_cnt;
+    unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long e = warp; e < n; e += nw) {
+        Deferred d = def[e];
+        bool again = geo_point<1>(g, src_xy, (size_t)d.idx, nullptr);
+        if (again && (threadIdx.x & 31) == 0) { unsigned long long slot = atomicAdd(def2_cnt, 1ull); def2[slot] = d; }
+    }
+}
+__global__ void k_geo_points_literal(GeoK g, const float2* __restrict__ src_xy, const Deferred* def2, const unsigned long long* def2_cnt,
+                                     unsigned* scratch, size_t words_per_thread, int R, int qcap)
+{
+    unsigned long long n = *def2_cnt, tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned* mine = scratch + tid * words_per_thread;
+    size_t vis_words = ((size_t)(2 * R + 1) * (2 * R + 1) + 31) / 32;
+    LitScratch ls;
+    ls.visited = mine; ls.R = R; ls.q = reinterpret_cast<QNode*>(mine + ((vis_words + 1) & ~size_t(1))); ls.qcap = qcap;
+    for (unsigned long long e = tid; e < n; e += nth) geo_point<2>(g, src_xy, (size_t)def2[e].idx, &ls);
+}
+
+// calc_field post-processing (process_tile_module.F:1580-1659)
+__global__ void k_geo_finish(GeoK g, int has_scale, float scale_factor)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.npts) return;
+    int ii = (int)(p % g.nx), jj = (int)(p / g.nx);
+    bool proc = bit_test(g.processed, g.nxw, ii, jj), lev = bit_test(g.level, g.nxw, ii, jj);
+    bool use_lm = g.landmask && (g.istagger == WPSGPU_M || g.istagger == WPSGPU_HH);
+    if (g.itype == WPSGPU_SP_CONTINUOUS) {
+        if (!use_lm || g.landmask[p] != g.mask_val) {
+            for (int k = 0; k < g.nk; ++k) {
+                size_t o = (size_t)k * g.npts + p;
+                if (g.count[o] > 0.0f) g.field[o] = g.field[o] / g.count[o];
+                else if (!proc) g.field[o] = g.msg_fill_val;
+            }
+        } else if (!proc) {
+            for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + p] = g.msg_fill_val;
+        }
+    } else if (g.itype == WPSGPU_CATEGORICAL) {
+        if (use_lm && g.landmask[p] == g.mask_val)
+            for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + p] = 0.0f;
+    }
+    if (has_scale && lev && !proc)
+        for (int k = 0; k < g.nk; ++k) {
+            size_t o = (size_t)k * g.npts + p;
+            if (g.field[o] != g.msg_fill_val) g.field[o] = g.field[o] * scale_factor;
+        }
+}
+__global__ void k_geo_merge_bits(int* processed, const int* level, size_t nwords)
+{
+    size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nwords) processed[w] |= level[w];
+}
+
+// read_geogrid.c:91-128 + the TOP_BOTTOM row flip of source_data_module.F:2887-2898
+__global__ void k_geo_decode(const unsigned char* __restrict__ c, int wordsize, int is_signed, int little, int flip,
+                             int tnx, int tny, int tnz, float* __restrict__ out)
+{
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)tnx * tny * tnz;
+    if (e >= n) return;
+    int ival;
+    const unsigned char* b = c + e * wordsize;
+    if (wordsize == 1) { ival = b[0]; if (is_signed && ival > (1 << 7)) ival -= (1 << 8); }
+    else if (wordsize == 2) { ival = little ? ((b[1] << 8) | b[0]) : ((b[0] << 8) | b[1]); if (is_signed && ival > (1 << 15)) ival -= (1 << 16); }
+    else if (wordsize == 3) { ival = little ? ((b[2] << 16) | (b[1] << 8) | b[0]) : ((b[0] << 16) | (b[1] << 8) | b[2]); if (is_signed && ival > (1 << 23)) ival -= (1 << 24); }
+    else { unsigned u = little ? (((unsigned)b[3] << 24) | (b[2] << 16) | (b[1] << 8) | b[0]) : (((unsigned)b[0] << 24) | (b[1] << 16) | (b[2] << 8) | b[3]); ival = (int)u; }
+    size_t i = e % tnx, j = (e / tnx) % tny, k = e / ((size_t)tnx * tny);
+    size_t jo = flip ? (size_t)(tny - 1) - j : j;
+    out[(k * tny + jo) * tnx + i] = (float)ival;
+}
+
+static int geo_grow(void** p, size_t* cap, size_t bytes, cudaStream_t st)
+{
+    if (bytes <= *cap) return 0;
+    WPS_CUDA(cudaStreamSynchronize(st));
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    WPS_CUDA(cudaMalloc(p, bytes + bytes / 8));
+    *cap = bytes + bytes / 8;
+    return 0;
+}
+
+static GeoK make_k(wpsgpu_ctx* h)
+{
+    GeoState* s = h->geo;
+    GeoK g;
+    memset(&g, 0, sizeof(g));
+    g.src = to_dev(s->l.src_proj, s->d_gauss_src); g.dom = to_dev(s->f.dom_proj, s->d_gauss_dom);
+    g.istagger = s->f.istagger; g.itype = s->l.itype;
+    g.start_i = s->f.start_i; g.end_i = s->f.end_i; g.start_j = s->f.start_j; g.end_j = s->f.end_j; g.start_k = s->f.start_k; g.end_k = s->f.end_k;
+    g.nx = s->nx; g.ny = s->ny; g.nk = s->nk; g.nxw = s->nxw; g.npts = s->npts;
+    g.sr_x = (float)s->l.sr_x; g.sr_y = (float)s->l.sr_y; g.msg_val = s->l.msg_val; g.msg_fill_val = s->l.msg_fill_val; g.mask_val = s->l.mask_val;
+    g.field = s->d_field; g.count = s->d_count; g.landmask = s->d_landmask; g.processed = s->d_processed; g.level = s->d_level;
+    g.acc_cnt = s->d_acc_cnt; g.acc_sum = s->d_acc_sum; g.touched = s->d_touched; g.invalid = s->d_invalid;
+    memcpy(g.ops, s->l.ops, sizeof(g.ops)); memcpy(g.opts, s->l.opts, sizeof(g.opts));
+    g.ops[WPSGPU_MAX_OPS - 1] = 0;
+    return g;
+}
+
+static void geo_free_field(GeoState* s)
+{
+    if (s->own_field && s->d_field) cudaFree(s->d_field);
+    if (s->own_ll) { if (s->d_xlat) cudaFree(s->d_xlat); if (s->d_xlon) cudaFree(s->d_xlon); if (s->d_landmask) cudaFree(s->d_landmask); }
+    void* ptrs[] = { s->d_count, s->d_processed, s->d_level, s->d_src_xy, s->d_acc_cnt, s->d_acc_sum, s->d_touched, s->d_def, s->d_def2 };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    s->d_field = s->d_xlat = s->d_xlon = s->d_landmask = s->d_count = nullptr;
+    s->d_processed = s->d_level = nullptr; s->d_src_xy = nullptr; s->d_acc_cnt = nullptr; s->d_acc_sum = nullptr; s->d_touched = nullptr;
+    s->d_def = s->d_def2 = nullptr;
+    s->field_open = s->level_open = false;
+}
+
+}  // namespace wps
+
+using namespace wps;
+
+extern "C" {
+
+void wpsgpu_geo_free(wpsgpu_ctx* h)
+{
+    if (!h->geo) return;
+    GeoState* s = h->geo;
+    geo_free_field(s);
+    if (s->d_tile) cudaFree(s->d_tile);
+    if (s->d_wm) cudaFree(s->d_wm);
+    if (s->d_raw) cudaFree(s->d_raw);
+    if (s->d_lit) cudaFree(s->d_lit);
+    if (s->d_invalid) cudaFree(s->d_invalid);
+    delete s;
+    h->geo = nullptr;
+}
+
+int wpsgpu_geogrid_field_begin(wpsgpu_handle_t h, const wpsgpu_geo_field* f)
+{
+    WPS_CHECK(h && f && f->xlat && f->xlon && f->field, -1, "wpsgpu_geogrid_field_begin: NULL argument");
+    WPS_CHECK(f->dom_proj.init, -1, "domain projection not initialised");
+    WPS_CUDA(cudaSetDevice(h->device));
+    if (!h->geo) { h->geo = new GeoState(); WPS_CUDA(cudaMalloc((void**)&h->geo->d_invalid, 4 * sizeof(unsigned long long))); }
+    GeoState* s = h->geo;
+    WPS_CUDA(cudaStreamSynchronize(h->stream));
+    geo_free_field(s);
+    s->f = *f;
+    s->nx = f->end_i - f->start_i + 1; s->ny = f->end_j - f->start_j + 1; s->nk = f->end_k - f->start_k + 1;
+    WPS_CHECK(s->nx > 0 && s->ny > 0 && s->nk > 0, -1, "empty field");
+    s->nxw = (s->nx + 31) / 32; s->npts = (size_t)s->nx * s->ny;
+    size_t b2 = s->npts * sizeof(float), b3 = b2 * s->nk, wb = (size_t)s->ny * s->nxw * sizeof(int);
+    const bool host = h->ptr_mode == WPSGPU_PTR_HOST;
+    if (host) {
+        WPS_CUDA(cudaMalloc((void**)&s->d_field, b3)); s->own_field = true;
+        WPS_CUDA(cudaMalloc((void**)&s->d_xlat, b2)); WPS_CUDA(cudaMalloc((void**)&s->d_xlon, b2)); s->own_ll = true;
+        WPS_CUDA(cudaMemcpyAsync(s->d_field, f->field, b3, cudaMemcpyHostToDevice, h->stream));
+        WPS_CUDA(cudaMemcpyAsync(s->d_xlat, f->xlat, b2, cudaMemcpyHostToDevice, h->stream));
+        WPS_CUDA(cudaMemcpyAsync(s->d_xlon, f->xlon, b2, cudaMemcpyHostToDevice, h->stream));
+        if (f->landmask) { WPS_CUDA(cudaMalloc((void**)&s->d_landmask, b2)); WPS_CUDA(cudaMemcpyAsync(s->d_landmask, f->landmask, b2, cudaMemcpyHostToDevice, h->stream)); }
+    } else {
+        s->d_field = f->field; s->own_field = false;
+        s->d_xlat = const_cast<float*>(f->xlat); s->d_xlon = const_cast<float*>(f->xlon); s->d_landmask = const_cast<float*>(f->landmask); s->own_ll = false;
+    }
+    WPS_CUDA(cudaMalloc((void**)&s->d_processed, wb)); WPS_CUDA(cudaMalloc((void**)&s->d_level, wb));
+    WPS_CUDA(cudaMemsetAsync(s->d_processed, 0, wb, h->stream));  // bitarray_create at ilevel==1 (:1257)
+    WPS_CUDA(cudaMalloc((void**)&s->d_src_xy, s->npts * sizeof(float2)));
+    WPS_CUDA(cudaMalloc((void**)&s->d_count, b3));
+    WPS_CUDA(cudaMalloc((void**)&s->d_acc_cnt, (size_t)s->nk * s->npts * sizeof(int)));
+    WPS_CUDA(cudaMalloc((void**)&s->d_acc_sum, (size_t)s->nk * s->npts * sizeof(double)));
+    WPS_CUDA(cudaMalloc((void**)&s->d_touched, s->npts * sizeof(int)));
+    WPS_CUDA(cudaMalloc((void**)&s->d_def, s->npts * sizeof(Deferred)));
+    WPS_CUDA(cudaMalloc((void**)&s->d_def2, s->npts * sizeof(Deferred)));
+    WPS_CUDA(cudaMemsetAsync(s->d_acc_cnt, 0, (size_t)s->nk * s->npts * sizeof(int), h->stream));
+    WPS_CUDA(cudaMemsetAsync(s->d_acc_sum, 0, (size_t)s->nk * s->npts * sizeof(double), h->stream));
+    WPS_CUDA(cudaMemsetAsync(s->d_touched, 0, s->npts * sizeof(int), h->stream));
+    WPS_CUDA(cudaMemsetAsync(s->d_invalid, 0, 4 * sizeof(unsigned long long), h->stream));
+    if (host) WPS_CUDA(cudaStreamSynchronize(h->stream));
+    s->field_open = true;
+    return 0;
+}
+
+int wpsgpu_geogrid_level_begin(wpsgpu_handle_t h, const wpsgpu_geo_level* l)
+{
+    WPS_CHECK(h && l && h->geo && h->geo->field_open, -1, "wpsgpu_geogrid_level_begin: no field open");
+    WPS_CHECK(l->src_proj.init, -1, "source projection not initialised");
+    WPS_CHECK(l->src_proj.code != WPSGPU_PROJ_GAUSS && h->geo->f.dom_proj.code != WPSGPU_PROJ_GAUSS, -1, "Gaussian projections are not supported for geogrid data");
+    WPS_CUDA(cudaSetDevice(h->device));
+    GeoState* s = h->geo;
+    s->l = *l;
+    size_t wb = (size_t)s->ny * s->nxw * sizeof(int);
+    WPS_CUDA(cudaMemsetAsync(s->d_level, 0, wb, h->stream));     // bitarray_create(level_domain) (:1345)
+    if (l->itype == WPSGPU_SP_CONTINUOUS) WPS_CUDA(cudaMemsetAsync(s->d_count, 0, s->npts * s->nk * sizeof(float), h->stream));  // data_count = 0. (:1316)
+    s->has_search = false; s->max_depth = 0;
+    for (int k = 0; k < WPSGPU_MAX_OPS && l->ops[k]; ++k) if (l->ops[k] == WPSGPU_SEARCH) { s->has_search = true; s->max_depth = std::max(s->max_depth, l->opts[k]); }
+    GeoK g = make_k(h);
+    k_geo_src_xy<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g.src, s->d_xlat, s->d_xlon, s->npts, s->d_src_xy);
+    h->launches++;
+    WPS_CUDA(cudaGetLastError());
+    s->level_open = true;
+    return 0;
+}
+
+static int geo_process_tile(wpsgpu_ctx* h, int smx, int sMx, int smy, int sMy, int smz, int sMz, int bdr)
+{
+    GeoState* s = h->geo;
+    int tnx = sMx - smx + 1, tny = sMy - smy + 1;
+    GeoK g = make_k(h);
+    g.tile = s->d_tile; g.smx = smx; g.sMx = sMx; g.smy = smy; g.sMy = sMy; g.smz = smz; g.sMz = sMz; g.bdr = bdr; g.tnx = tnx; g.tny = tny;
+    if (s->l.itype != WPSGPU_CATEGORICAL)
+        WPS_CHECK(smz >= s->f.start_k && sMz <= s->f.end_k, -1, "source levels %d..%d outside field levels %d..%d", smz, sMz, s->f.start_k, s->f.end_k);
+    dim3 b(32, 8);
+    if (s->l.itype == WPSGPU_CATEGORICAL || s->l.itype == WPSGPU_SP_CONTINUOUS) {
+        WPS_TRY(geo_grow((void**)&s->d_wm, &s->wm_cap, (size_t)tnx * tny * sizeof(int2), h->stream));
+        g.wm = s->d_wm;
+        k_geo_wm<<<dim3((tnx + 31) / 32, (tny + 7) / 8), b, 0, h->stream>>>(g);
+        int inx = tnx - 2 * bdr, iny = tny - 2 * bdr;
+        if (inx > 0 && iny > 0) k_geo_accum<<<dim3((inx + 31) / 32, (iny + 7) / 8), b, 0, h->stream>>>(g);
+        // areas of the half-area rule (proc_point_module.F:178-197)
+        const wpsgpu_proj &sp = s->l.src_proj, &dp = s->f.dom_proj;
+        float sa = (sp.dx < 0.0f) ? (sp.latinc * 111000.0f) * (sp.latinc * 111000.0f) : sp.dx * sp.dx;
+        float da = (dp.dx < 0.0f) ? (dp.latinc * 111000.0f) * (dp.latinc * 111000.0f) : dp.dx * dp.dx;
+        k_geo_merge<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->l.ilevel, sa, da);
+        h->launches += 3;
+        WPS_CUDA(cudaGetLastError());
+    }
+    unsigned long long* cnt = s->d_invalid + 1;
+    WPS_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), h->stream));
+    k_geo_points<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->d_src_xy, s->d_def, cnt);
+    h->launches++;
+    if (s->has_search) {
+        k_geo_points_warp<<<h->sm_count * 8, 256, 0, h->stream>>>(g, s->d_src_xy, s->d_def, cnt, s->d_def2, cnt + 1);
+        int R = std::min(std::max(s->max_depth, 1), std::max(std::max(tnx, tny), 1));
+        size_t vis_words = ((size_t)(2 * R + 1) * (2 * R + 1) + 31) / 32;
+        int qcap = 8 * R + 64;
+        size_t wpt = ((vis_words + 1) & ~size_t(1)) + (size_t)qcap * sizeof(QNode) / sizeof(unsigned);
+        int lit_threads = 256;
+        WPS_TRY(geo_grow(&s->d_lit, &s->lit_bytes, wpt * sizeof(unsigned) * lit_threads, h->stream));
+        k_geo_points_literal<<<lit_threads / 64, 64, 0, h->stream>>>(g, s->d_src_xy, s->d_def2, cnt + 1, (unsigned*)s->d_lit, wpt, R, qcap);
+        h->launches += 2;
+    }
+    WPS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int wpsgpu_geogrid_add_tile(wpsgpu_handle_t h, const float* tile, int src_min_x, int src_max_x, int src_min_y,
+                            int src_max_y, int src_min_z, int src_max_z, int bdr)
+{
+    WPS_CHECK(h && tile && h->geo && h->geo->level_open, -1, "wpsgpu_geogrid_add_tile: no level open");
+    WPS_CUDA(cudaSetDevice(h->device));
+    GeoState* s = h->geo;
+    size_t n = (size_t)(src_max_x - src_min_x + 1) * (src_max_y - src_min_y + 1) * (src_max_z - src_min_z + 1);
+    WPS_CHECK(n > 0, -1, "empty tile");
+    WPS_TRY(geo_grow((void**)&s->d_tile, &s->tile_cap, n * sizeof(float), h->stream));
+    WPS_CUDA(cudaMemcpyAsync(s->d_tile, tile, n * sizeof(float),
+                             h->ptr_mode == WPSGPU_PTR_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    WPS_TRY(geo_process_tile(h, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
+    if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int wpsgpu_geogrid_add_tile_raw(wpsgpu_handle_t h, const void* bytes, int wordsize, int is_signed, int endian,
+                                int row_order, int src_min_x, int src_max_x, int src_min_y, int src_max_y,
+                                int src_min_z, int src_max_z, int bdr)
+{
+    WPS_CHECK(h && bytes && h->geo && h->geo->level_open, -1, "wpsgpu_geogrid_add_tile_raw: no level open");
+    WPS_CHECK(wordsize >= 1 && wordsize <= 4, -1, "wordsize must be 1..4");
+    WPS_CUDA(cudaSetDevice(h->device));
+    GeoState* s = h->geo;
+    int tnx = src_max_x - src_min_x + 1, tny = src_max_y - src_min_y + 1, tnz = src_max_z - src_min_z + 1;
+    size_t n = (size_t)tnx * tny * tnz;
+    WPS_CHECK(n > 0, -1, "empty tile");
+    WPS_TRY(geo_grow((void**)&s->d_tile, &s->tile_cap, n * sizeof(float), h->stream));
+    const unsigned char* d_bytes = (const unsigned char*)bytes;
+    if (h->ptr_mode == WPSGPU_PTR_HOST) {
+        WPS_TRY(geo_grow(&s->d_raw, &s->raw_cap, n * wordsize, h->stream));
+        WPS_CUDA(cudaMemcpyAsync(s->d_raw, bytes, n * wordsize, cudaMemcpyHostToDevice, h->stream));
+        d_bytes = (const unsigned char*)s->d_raw;
+    }
+    k_geo_decode<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_bytes, wordsize, is_signed, endian == 1, row_order == 2, tnx, tny, tnz, s->d_tile);
+    h->launches++;
+    WPS_CUDA(cudaGetLastError());
+    WPS_TRY(geo_process_tile(h, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
+    if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int wpsgpu_geogrid_level_end(wpsgpu_handle_t h)
+{
+    WPS_CHECK(h && h->geo && h->geo->level_open, -1, "wpsgpu_geogrid_level_end: no level open");
+    WPS_CUDA(cudaSetDevice(h->device));
+    GeoState* s = h->geo;
+    GeoK g = make_k(h);
+    k_geo_finish<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->l.has_scale, s->l.scale_factor);
+    size_t nwords = (size_t)s->ny * s->nxw;
+    k_geo_merge_bits<<<(unsigned)((nwords + 255) / 256), 256, 0, h->stream>>>(s->d_processed, s->d_level, nwords);
+    h->launches += 2;
+    WPS_CUDA(cudaGetLastError());
+    s->level_open = false;
+    return 0;
+}
+
+int wpsgpu_geogrid_field_finish(wpsgpu_handle_t h, int32_t* processed_domain_out, int64_t* n_invalid_category)
+{
+    WPS_CHECK(h && h->geo && h->geo->field_open, -1, "wpsgpu_geogrid_field_finish: no field open");
+    WPS_CHECK(!h->geo->level_open, -1, "wpsgpu_geogrid_field_finish: a level is still open");
+    WPS_CUDA(cudaSetDevice(h->device));
+    GeoState* s = h->geo;
+    size_t b3 = s->npts * s->nk * sizeof(float), wb = (size_t)s->ny * s->nxw * sizeof(int);
+    if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaMemcpyAsync(s->f.field, s->d_field, b3, cudaMemcpyDeviceToHost, h->stream));
+    if (processed_domain_out)
+        WPS_CUDA(cudaMemcpyAsync(processed_domain_out, s->d_processed, wb,
+                                 h->ptr_mode == WPSGPU_PTR_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, h->stream));
+    unsigned long long inv = 0;
+    WPS_CUDA(cudaMemcpyAsync(&inv, s->d_invalid, sizeof(inv), cudaMemcpyDeviceToHost, h->stream));
+    WPS_CUDA(cudaStreamSynchronize(h->stream));
+    if (n_invalid_category) *n_invalid_category = (int64_t)inv;
+    geo_free_field(s);
+    return 0;
+}
+
+int wpsgpu_metgrid_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, const wpsgpu_proj* dom_proj,
+                              const wpsgpu_field_opts* fo, const wpsgpu_slab* slab)
+{
+    (void)src_proj; (void)dom_proj; (void)fo; (void)slab;
+    WPS_CHECK(h != nullptr, -1, "NULL handle");
+    WPS_CHECK(false, -40, "wpsgpu_metgrid_gcell_slab: metgrid average_gcell (process_domain_module.F:2331-2478) is not implemented yet");
+}
+
+}  // extern "C"

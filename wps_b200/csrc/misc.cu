@@ -1,0 +1,519 @@
+// misc.cu -- wind rotation, smoothers, fractions/dominant/landmask and the elementwise geometry outputs.
+#include "ctx.h"
+
+namespace wps {
+
+// ---- metmap_xform (rotate_winds_module.F:85-387), C grid, LC / PS (Cassini branches not ported) ----
+struct RotArgs {
+    const float *u, *v, *xlon_u, *xlon_v;
+    const int *u_mask, *v_mask;
+    float *u_new, *v_new;
+    int us1, us2, ue1, ue2, vs1, vs2, ve1, ve2, unx, uny, vnx, vny, unxw, vnxw;
+    int idir, is_lc;
+    float stdlon, cone, hemi;
+    int do_last_col_u, do_last_row_u, do_last_col_v, do_last_row_v;
+};
+
+__device__ __forceinline__ float rot_alpha(const RotArgs& a, float xlon)
+{
+    float diff = (float)a.idir * (xlon - a.stdlon);
+    if (diff > 180.0f) diff = diff - 360.0f; else if (diff < -180.0f) diff = diff + 360.0f;
+    return a.is_lc ? (diff * a.cone * WPS_RAD_PER_DEG * a.hemi) : (diff * WPS_RAD_PER_DEG * a.hemi);
+}
+
+__global__ void k_rotate_u(RotArgs a, int nlev)
+{
+    int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y * blockDim.y + threadIdx.y, lev = blockIdx.z;
+    if (ii >= a.unx || jj >= a.uny) return;
+    int i = a.us1 + ii, j = a.us2 + jj;
+    size_t un = (size_t)a.unx * a.uny, vn = (size_t)a.vnx * a.vny;
+    const float *u = a.u + lev * un, *v = a.v + lev * vn;
+    const int *um = a.u_mask + (size_t)lev * a.uny * a.unxw, *vm = a.v_mask + (size_t)lev * a.vny * a.vnxw;
+    auto ubit = [&](int x, int y) { int xi = x - a.us1, yi = y - a.us2; return (um[(size_t)yi * a.unxw + (xi >> 5)] >> (xi & 31)) & 1; };
+    auto vmul = [&](int x, int y) { int xi = x - a.vs1, yi = y - a.vs2; return ((vm[(size_t)yi * a.vnxw + (xi >> 5)] >> (xi & 31)) & 1) ? 1.0f : 0.0f; };
+    auto V = [&](int x, int y) { return v[(size_t)(y - a.vs2) * a.vnx + (x - a.vs1)]; };
+    size_t o = (size_t)jj * a.unx + ii;
+    float uold = u[o], res = uold;
+    if (ubit(i, j)) {
+        float alpha = rot_alpha(a, a.xlon_u[o]);
+        float v_weight, v_map;
+        if (i == a.us1) {
+            if (j == a.ue2 && a.do_last_row_u) { v_weight = vmul(i, j); v_map = V(i, j) * vmul(i, j); }
+            else { v_weight = vmul(i, j) + vmul(i, j + 1); v_map = V(i, j) * vmul(i, j) + V(i, j + 1) * vmul(i, j + 1); }
+        } else if (i == a.ue1 && a.do_last_col_u) {
+            if (j == a.ue2 && a.do_last_row_u) { v_weight = vmul(i - 1, j); v_map = V(i - 1, j); /* :244 */ }
+            else { v_weight = vmul(i - 1, j) + vmul(i - 1, j + 1); v_map = V(i - 1, j) * vmul(i - 1, j) + V(i - 1, j + 1) * vmul(i - 1, j + 1); }
+        } else if (j == a.ue2 && a.do_last_row_u) {
+            v_weight = vmul(i - 1, j - 1) + vmul(i, j - 1);
+            v_map = V(i - 1, j - 1) * vmul(i - 1, j - 1) + V(i, j - 1) * vmul(i, j - 1);
+        } else {
+            v_weight = vmul(i - 1, j) + vmul(i - 1, j + 1) + vmul(i, j) + vmul(i, j + 1);
+            v_map = V(i - 1, j) * vmul(i - 1, j) + V(i - 1, j + 1) * vmul(i - 1, j + 1) + V(i, j) * vmul(i, j) + V(i, j + 1) * vmul(i, j + 1);
+        }
+        if (v_weight > 0.0f) res = t_cos(alpha) * uold + t_sin(alpha) * v_map / v_weight;
+    }
+    a.u_new[lev * un + o] = res;
+}
+
+__global__ void k_rotate_v(RotArgs a, int nlev)
+{
+    int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y * blockDim.y + threadIdx.y, lev = blockIdx.z;
+    if (ii >= a.vnx || jj >= a.vny) return;
+    int i = a.vs1 + ii, j = a.vs2 + jj;
+    size_t un = (size_t)a.unx * a.uny, vn = (size_t)a.vnx * a.vny;
+    const float *u = a.u + lev * un, *v = a.v + lev * vn;
+    const int *um = a.u_mask + (size_t)lev * a.uny * a.unxw, *vm = a.v_mask + (size_t)lev * a.vny * a.vnxw;
+    auto vbit = [&](int x, int y) { int xi = x - a.vs1, yi = y - a.vs2; return (vm[(size_t)yi * a.vnxw + (xi >> 5)] >> (xi & 31)) & 1; };
+    auto umul = [&](int x, int y) { int xi = x - a.us1, yi = y - a.us2; return ((um[(size_t)yi * a.unxw + (xi >> 5)] >> (xi & 31)) & 1) ? 1.0f : 0.0f; };
+    auto U = [&](int x, int y) { return u[(size_t)(y - a.us2) * a.unx + (x - a.us1)]; };
+    size_t o = (size_t)jj * a.vnx + ii;
+    float vold = v[o], res = vold;
+    if (vbit(i, j)) {
+        float alpha = rot_alpha(a, a.xlon_v[o]);
+        float u_weight, u_map;
+        if (j == a.vs2) {
+            if (i == a.ve1 && a.do_last_col_v) { u_weight = umul(i, j); u_map = U(i, j) * umul(i, j); }
+            else { u_weight = umul(i, j) + umul(i + 1, j); u_map = U(i, j) * umul(i, j) + U(i + 1, j) * umul(i + 1, j); }
+        } else if (j == a.ve2 && a.do_last_row_v) {
+            if (i == a.ve1 && a.do_last_col_v) { u_weight = umul(i, j - 1); u_map = U(i, j - 1) * umul(i, j - 1); }
+            else { u_weight = umul(i, j - 1) + umul(i + 1, j - 1); u_map = U(i, j - 1) * umul(i, j - 1) + U(i + 1, j - 1) * umul(i + 1, j - 1); }
+        } else if (i == a.ve1 && a.do_last_col_v) {
+            u_weight = umul(i, j) + umul(i, j - 1);
+            u_map = U(i, j) * umul(i, j) + U(i, j - 1) * umul(i, j - 1);
+        } else {
+            u_weight = umul(i, j - 1) + umul(i, j) + umul(i + 1, j - 1) + umul(i + 1, j);
+            u_map = U(i, j - 1) * umul(i, j - 1) + U(i, j) * umul(i, j) + U(i + 1, j - 1) * umul(i + 1, j - 1) + U(i + 1, j) * umul(i + 1, j);
+        }
+        if (u_weight > 0.0f) res = -t_sin(alpha) * u_map / u_weight + t_cos(alpha) * vold;
+    }
+    a.v_new[lev * vn + o] = res;
+}
+
+// ---- smoothers (smooth_module.F:20-239) -----------------------------------------------------------------
+// x sweep: scratch(ix,iy) = c0*a(ix,iy) + c1*(a(ix-1,iy)+a(ix+1,iy)) for ix in sx+1..ex-1, all iy
+__global__ void k_sweep_x(const float* __restrict__ a, float* __restrict__ s, int nx, int ny, float c0, float c1)
+{
+    int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+    size_t lev = (size_t)blockIdx.z * nx * ny;
+    if (ix < 1 || ix > nx - 2 || iy >= ny) return;
+    size_t o = lev + (size_t)iy * nx + ix;
+    s[o] = c0 * a[o] + c1 * (a[o - 1] + a[o + 1]);
+}
+// y sweep: a(ix,iy) = c0*s(ix,iy) + c1*(s(ix,iy-1)+s(ix,iy+1)) for ix in sx+1..ex-1, iy in sy+1..ey-1
+__global__ void k_sweep_y(const float* __restrict__ s, float* __restrict__ a, int nx, int ny, float c0, float c1)
+{
+    int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y * blockDim.y + threadIdx.y;
+    size_t lev = (size_t)blockIdx.z * nx * ny;
+    if (ix < 1 || ix > nx - 2 || iy < 1 || iy > ny - 2) return;
+    size_t o = lev + (size_t)iy * nx + ix;
+    a[o] = c0 * s[o] + c1 * (s[o - nx] + s[o + nx]);
+}
+__global__ void k_restore_negative(float* __restrict__ a, const float* __restrict__ orig, size_t n)
+{
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (a[k] < 0.0f && orig[k] >= 0.0f) a[k] = orig[k];
+}
+
+// ---- fractions / landmask / dominant (process_tile_module.F:539-622,699-727,1035-1051,1123-1144) ---------
+struct FracArgs {
+    float* field; size_t npts; int min_cat, max_cat; float msg_fill;
+    int lm_vals[32]; int n_lm; int is_water_mask;
+    float* landmask; float* dominant;
+};
+__global__ void k_fractions_dominant(FracArgs a)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.npts) return;
+    int ncat = a.max_cat - a.min_cat + 1;
+    float sum = 0.0f;
+    for (int k = 0; k < ncat; ++k) sum = sum + a.field[(size_t)k * a.npts + p];
+    if (sum > 0.0f) { for (int k = 0; k < ncat; ++k) a.field[(size_t)k * a.npts + p] = a.field[(size_t)k * a.npts + p] / sum; }
+    else { for (int k = 0; k < ncat; ++k) a.field[(size_t)k * a.npts + p] = a.msg_fill; }
+    float lm = 0.0f;
+    if (a.n_lm > 0) {
+        float total = -1.0f;
+        for (int k = 0; k < a.n_lm; ++k) {
+            int c = a.lm_vals[k];
+            if (c >= a.min_cat && c <= a.max_cat) {
+                float v = a.field[(size_t)(c - a.min_cat) * a.npts + p];
+                if (v != a.msg_fill) { if (total < 0.0f) total = 0.0f; total = total + v; }
+                else { total = -1.0f; break; }
+            }
+        }
+        if (total >= 0.0f) lm = a.is_water_mask ? ((total < 0.50f) ? 1.0f : 0.0f) : ((total > 0.50f) ? 1.0f : 0.0f);
+        else lm = -1.0f;
+        if (a.landmask) a.landmask[p] = lm;
+    }
+    if (a.dominant) {
+        float dominant = 0.0f, d = (float)(a.min_cat - 1);
+        if (a.n_lm == 0) {
+            for (int k = a.min_cat; k <= a.max_cat; ++k) {
+                float v = a.field[(size_t)(k - a.min_cat) * a.npts + p];
+                if (v > dominant && v != a.msg_fill) { d = (float)k; dominant = v; }
+            }
+            if (d == (float)(a.min_cat - 1)) d = a.msg_fill;
+        } else if ((lm == 1.0f && a.is_water_mask) || (lm == 0.0f && !a.is_water_mask)) {
+            for (int k = a.min_cat; k <= a.max_cat; ++k) {
+                int kk;
+                for (kk = 1; kk <= a.n_lm; ++kk) if (k == a.lm_vals[kk - 1]) break;
+                float v = a.field[(size_t)(k - a.min_cat) * a.npts + p];
+                if (v > dominant && kk > a.n_lm) { d = (float)k; dominant = v; }
+            }
+        } else {
+            for (int k = a.min_cat; k <= a.max_cat; ++k)
+                for (int kk = 1; kk <= a.n_lm; ++kk) {
+                    float v = a.field[(size_t)(k - a.min_cat) * a.npts + p];
+                    if (v > dominant && k == a.lm_vals[kk - 1]) { d = (float)k; dominant = v; }
+                }
+        }
+        a.dominant[p] = d;
+    }
+}
+
+// ---- elementwise geometry (process_tile_module.F:1692-2253) ----------------------------------------------
+__global__ void k_xytoll_grid(DevProj p, int stagger, int si, int sj, int nx, int ny, float sub_x, float sub_y,
+                              float* __restrict__ xlat, float* __restrict__ xlon)
+{
+    int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ii >= nx || jj >= ny) return;
+    float x = ((float)(si + ii) - 0.5f) / sub_x + 0.5f, y = ((float)(sj + jj) - 0.5f) / sub_y + 0.5f;
+    float la, lo;
+    xytoll(p, x, y, la, lo, stagger);
+    xlat[(size_t)jj * nx + ii] = la; xlon[(size_t)jj * nx + ii] = lo;
+}
+
+struct MapfacArgs { int iproj; float truelat1, truelat2, pole_lat, pole_lon, stand_lon; float n, colat0, colat2, s0; };
+__global__ void k_map_factor(MapfacArgs a, const float* __restrict__ xlat, const float* __restrict__ xlon, size_t npts,
+                             float* __restrict__ mx, float* __restrict__ my)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const float R = WPS_RAD_PER_DEG;
+    float la = xlat[p], fx, fy;
+    if (a.iproj == WPSGPU_PROJ_LC) {
+        float colat = R * (90.0f - la);
+        if (a.truelat1 != a.truelat2) fx = t_sin(a.colat2) / t_sin(colat) * t_pow(t_tan(colat / 2.0f) / t_tan(a.colat2 / 2.0f), a.n);
+        else fx = t_sin(a.colat0) / t_sin(colat) * t_pow(t_tan(colat / 2.0f) / t_tan(a.colat0 / 2.0f), t_cos(a.colat0));
+        fy = fx;
+    } else if (a.iproj == WPSGPU_PROJ_PS) {
+        float sg = (a.truelat1 >= 0.0f) ? 1.0f : -1.0f;
+        fx = (1.0f + t_sin(R * fabsf(a.truelat1))) / (1.0f + t_sin(R * sg * la));
+        fy = fx;
+    } else if (a.iproj == WPSGPU_PROJ_MERC) {
+        float colat = R * (90.0f - la);
+        fx = t_sin(a.colat0) / t_sin(colat);
+        fy = fx;
+    } else if (a.iproj == WPSGPU_PROJ_CYL) {
+        fx = (fabsf(la) == 90.0f) ? 0.0f : 1.0f / t_cos(la * R);
+        fy = 1.0f;
+    } else if (a.iproj == WPSGPU_PROJ_CASSINI) {
+        if (fabsf(a.pole_lat) == 90.0f) fx = (fabsf(la) >= 90.0f) ? 0.0f : 1.0f / t_cos(la * R);
+        else {
+            float cl, co;
+            rotate_coords(la, xlon[p], cl, co, a.pole_lat, a.pole_lon, a.stand_lon, -1);
+            fx = (fabsf(cl) >= 90.0f) ? 0.0f : 1.0f / t_cos(cl * R);
+        }
+        fy = 1.0f;
+    } else { fx = 1.0f; fy = 1.0f; }
+    mx[p] = fx; my[p] = fy;
+}
+
+__global__ void k_coriolis(const float* __restrict__ xlat, size_t npts, float* __restrict__ f, float* __restrict__ e)
+{
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const float OMEGA_E = 7.292e-5f;
+    f[p] = 2.0f * OMEGA_E * t_sin(WPS_RAD_PER_DEG * xlat[p]);
+    e[p] = 2.0f * OMEGA_E * t_cos(WPS_RAD_PER_DEG * xlat[p]);
+}
+
+__global__ void k_rotang(int iproj, float cone, float stand_lon, const float* __restrict__ xlat, const float* __restrict__ xlon,
+                         int nx, int ny, float* __restrict__ cosa, float* __restrict__ sina)
+{
+    int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ii >= nx || jj >= ny) return;
+    size_t o = (size_t)jj * nx + ii;
+    if (iproj == WPSGPU_PROJ_LC || iproj == WPSGPU_PROJ_PS) {
+        float d_lon = stand_lon - xlon[o];
+        if (d_lon > 180.0f) d_lon = d_lon - 360.0f; else if (d_lon < -180.0f) d_lon = d_lon + 360.0f;
+        float alpha = (iproj == WPSGPU_PROJ_LC) ? d_lon * cone * WPS_RAD_PER_DEG : d_lon * WPS_RAD_PER_DEG;
+        sina[o] = t_sin(alpha); cosa[o] = t_cos(alpha);
+    } else if (iproj == WPSGPU_PROJ_CASSINI) {
+        int jm = (jj == 0) ? jj : jj - 1, jp = (jj == ny - 1) ? jj : jj + 1;
+        float d_lon = xlon[(size_t)jp * nx + ii] - xlon[(size_t)jm * nx + ii];
+        if (d_lon > 180.0f) d_lon = d_lon - 360.0f; else if (d_lon < -180.0f) d_lon = d_lon + 360.0f;
+        float alpha = t_atan2(-t_cos(xlat[o] * WPS_RAD_PER_DEG) * (d_lon * WPS_RAD_PER_DEG),
+                              ((xlat[(size_t)jp * nx + ii] - xlat[(size_t)jm * nx + ii]) * WPS_RAD_PER_DEG));
+        sina[o] = t_sin(alpha); cosa[o] = t_cos(alpha);
+    } else { sina[o] = 0.0f; cosa[o] = 1.0f; }
+}
+
+// calc_dfdx / calc_dfdy with the stale-index map factor on the edge rows/columns (:2163,2167,2228,2232)
+__global__ void k_dfd(int dir, const float* __restrict__ src, float* __restrict__ dst, int nx, int ny, float sr,
+                      const float* __restrict__ mapfac, float dom_d, int stale)
+{
+    int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ii >= nx || jj >= ny) return;
+    size_t lev = (size_t)blockIdx.z * nx * ny, o2 = (size_t)jj * nx + ii, o = lev + o2;
+    if (dir == 0) {
+        if (ii >= 1 && ii <= nx - 2) {
+            float den = mapfac ? (2.0f * dom_d * mapfac[o2] / sr) : (2.0f * dom_d / sr);
+            dst[o] = (src[o + 1] - src[o - 1]) / den;
+        } else {
+            float den = mapfac ? (dom_d * mapfac[(size_t)jj * nx + stale] / sr) : (dom_d / sr);
+            dst[o] = (ii == 0) ? (src[o + 1] - src[o]) / den : (src[o] - src[o - 1]) / den;
+        }
+    } else {
+        if (jj >= 1 && jj <= ny - 2) {
+            float den = mapfac ? (2.0f * dom_d * mapfac[o2] / sr) : (2.0f * dom_d / sr);
+            dst[o] = (src[o + nx] - src[o - nx]) / den;
+        } else {
+            float den = mapfac ? (dom_d * mapfac[(size_t)stale * nx + ii] / sr) : (dom_d / sr);
+            dst[o] = (jj == 0) ? (src[o + nx] - src[o]) / den : (src[o] - src[o - nx]) / den;
+        }
+    }
+}
+
+}  // namespace wps
+
+using namespace wps;
+
+static int begin_call(wpsgpu_ctx* h, size_t host_bytes)
+{
+    WPS_CHECK(h != nullptr, -1, "NULL handle");
+    WPS_CUDA(cudaSetDevice(h->device));
+    h->arena.reset();
+    return h->arena.reserve((h->ptr_mode == WPSGPU_PTR_HOST ? host_bytes : 0) + (1 << 20), h->stream);
+}
+static int end_call(wpsgpu_ctx* h)
+{
+    WPS_CUDA(cudaGetLastError());
+    if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+// inout array: staged in (host mode) and copied back
+static int stage_inout(wpsgpu_ctx* h, void* p, size_t bytes, void** d) { return stage_in(h, p, bytes, d); }
+
+extern "C" {
+
+int wpsgpu_rotate_winds(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj, float* u, const int32_t* u_mask,
+                        float* v, const int32_t* v_mask, int us1, int us2, int ue1, int ue2,
+                        int vs1, int vs2, int ve1, int ve2, const float* xlon_u, const float* xlon_v, int nlev)
+{
+    WPS_CHECK(h && proj && u && v && u_mask && v_mask && xlon_u && xlon_v, -1, "wpsgpu_rotate_winds: NULL argument");
+    WPS_CHECK(proj->init, -1, "In metmap_xform(), uninitialized proj_info structure.");
+    WPS_CHECK(proj->code != WPSGPU_PROJ_CASSINI, -30, "wpsgpu_rotate_winds: Cassini wind rotation is not ported");
+    if (!(proj->code == WPSGPU_PROJ_LC || proj->code == WPSGPU_PROJ_PS)) return 0;  // only LC / PS rotate (:112-114)
+    RotArgs a;
+    a.unx = ue1 - us1 + 1; a.uny = ue2 - us2 + 1; a.vnx = ve1 - vs1 + 1; a.vny = ve2 - vs2 + 1;
+    a.unxw = (a.unx + 31) / 32; a.vnxw = (a.vnx + 31) / 32;
+    size_t ub = sizeof(float) * a.unx * a.uny, vb = sizeof(float) * a.vnx * a.vny;
+    size_t umb = sizeof(int) * a.uny * a.unxw, vmb = sizeof(int) * a.vny * a.vnxw;
+    WPS_TRY(begin_call(h, 2 * (ub + vb) * nlev + (umb + vmb) * nlev + ub + vb + 8192));
+    if (h->ptr_mode == WPSGPU_PTR_DEVICE) WPS_TRY(h->arena.reserve((ub + vb) * nlev + (1 << 20), h->stream));
+    void *du, *dv, *dum, *dvm, *dxu, *dxv;
+    WPS_TRY(stage_inout(h, u, ub * nlev, &du));
+    WPS_TRY(stage_inout(h, v, vb * nlev, &dv));
+    WPS_TRY(stage_in(h, u_mask, umb * nlev, &dum));
+    WPS_TRY(stage_in(h, v_mask, vmb * nlev, &dvm));
+    WPS_TRY(stage_in(h, xlon_u, ub, &dxu));
+    WPS_TRY(stage_in(h, xlon_v, vb, &dxv));
+    a.u_new = (float*)h->arena.take(ub * nlev);
+    a.v_new = (float*)h->arena.take(vb * nlev);
+    WPS_CHECK(a.u_new && a.v_new, -3, "device arena exhausted");
+    a.u = (const float*)du; a.v = (const float*)dv; a.u_mask = (const int*)dum; a.v_mask = (const int*)dvm;
+    a.xlon_u = (const float*)dxu; a.xlon_v = (const float*)dxv;
+    a.us1 = us1; a.us2 = us2; a.ue1 = ue1; a.ue2 = ue2; a.vs1 = vs1; a.vs2 = vs2; a.ve1 = ve1; a.ve2 = ve2;
+    a.idir = idir; a.is_lc = proj->code == WPSGPU_PROJ_LC; a.stdlon = proj->stdlon; a.cone = proj->cone; a.hemi = proj->hemi;
+    if (ue1 - us1 == ve1 - vs1) { a.do_last_col_u = 0; a.do_last_col_v = 1; } else { a.do_last_col_u = 1; a.do_last_col_v = 0; }
+    if (ue2 - us2 == ve2 - vs2) { a.do_last_row_u = 1; a.do_last_row_v = 0; } else { a.do_last_row_u = 0; a.do_last_row_v = 1; }
+    dim3 b(32, 8);
+    k_rotate_u<<<dim3((a.unx + 31) / 32, (a.uny + 7) / 8, nlev), b, 0, h->stream>>>(a, nlev);
+    k_rotate_v<<<dim3((a.vnx + 31) / 32, (a.vny + 7) / 8, nlev), b, 0, h->stream>>>(a, nlev);
+    h->launches += 2;
+    WPS_CUDA(cudaGetLastError());
+    // "Copy rotated winds back into argument arrays" (:374-375)
+    if (h->ptr_mode == WPSGPU_PTR_DEVICE) {
+        WPS_CUDA(cudaMemcpyAsync(u, a.u_new, ub * nlev, cudaMemcpyDeviceToDevice, h->stream));
+        WPS_CUDA(cudaMemcpyAsync(v, a.v_new, vb * nlev, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+        WPS_CUDA(cudaMemcpyAsync(u, a.u_new, ub * nlev, cudaMemcpyDeviceToHost, h->stream));
+        WPS_CUDA(cudaMemcpyAsync(v, a.v_new, vb * nlev, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return end_call(h);
+}
+
+int wpsgpu_smooth(wpsgpu_handle_t h, int opt, int npass, float* array, int sx, int ex, int sy, int ey, int sz, int ez)
+{
+    WPS_CHECK(h && array, -1, "wpsgpu_smooth: NULL argument");
+    WPS_CHECK(opt >= WPSGPU_ONETWOONE && opt <= WPSGPU_SMTHDESMTH_SPECIAL, -1, "unknown smooth option %d", opt);
+    int nx = ex - sx + 1, ny = ey - sy + 1, nz = ez - sz + 1;
+    size_t n = (size_t)nx * ny * nz, bytes = n * sizeof(float);
+    WPS_TRY(begin_call(h, 3 * bytes + 4096));
+    if (h->ptr_mode == WPSGPU_PTR_DEVICE) WPS_TRY(h->arena.reserve(2 * bytes + (1 << 20), h->stream));
+    void* da;
+    WPS_TRY(stage_inout(h, array, bytes, &da));
+    float* a = (float*)da;
+    float* s = (float*)h->arena.take(bytes);
+    float* orig = nullptr;
+    WPS_CHECK(s != nullptr, -3, "device arena exhausted");
+    if (opt == WPSGPU_SMTHDESMTH_SPECIAL) {
+        orig = (float*)h->arena.take(bytes);
+        WPS_CHECK(orig != nullptr, -3, "device arena exhausted");
+        WPS_CUDA(cudaMemcpyAsync(orig, a, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8, nz);
+    for (int ipass = 0; ipass < npass; ++ipass) {
+        k_sweep_x<<<g, b, 0, h->stream>>>(a, s, nx, ny, 0.5f, 0.25f);
+        k_sweep_y<<<g, b, 0, h->stream>>>(s, a, nx, ny, 0.5f, 0.25f);
+        h->launches += 2;
+        if (opt != WPSGPU_ONETWOONE) {
+            k_sweep_x<<<g, b, 0, h->stream>>>(a, s, nx, ny, 1.52f, -0.26f);
+            k_sweep_y<<<g, b, 0, h->stream>>>(s, a, nx, ny, 1.52f, -0.26f);
+            h->launches += 2;
+        }
+    }
+    if (opt == WPSGPU_SMTHDESMTH_SPECIAL) {
+        k_restore_negative<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(a, orig, n);
+        h->launches++;
+    }
+    WPS_TRY(copy_out(h, array, a, bytes));
+    return end_call(h);
+}
+
+int wpsgpu_fractions_dominant(wpsgpu_handle_t h, float* field, int64_t npts, int min_cat, int max_cat,
+                              float msg_fill_val, const int32_t* lm_vals, int n_lm, int is_water_mask,
+                              float* landmask_out, float* dominant_out)
+{
+    WPS_CHECK(h && field, -1, "wpsgpu_fractions_dominant: NULL argument");
+    WPS_CHECK(n_lm >= 0 && n_lm <= 32, -1, "too many landmask categories (%d)", n_lm);
+    int ncat = max_cat - min_cat + 1;
+    size_t fb = sizeof(float) * (size_t)npts * ncat, pb = sizeof(float) * (size_t)npts;
+    WPS_TRY(begin_call(h, fb + 2 * pb + 4096));
+    FracArgs a;
+    void *df, *dl, *dd;
+    WPS_TRY(stage_inout(h, field, fb, &df));
+    WPS_TRY(alloc_out(h, landmask_out, pb, &dl));
+    WPS_TRY(alloc_out(h, dominant_out, pb, &dd));
+    a.field = (float*)df; a.npts = (size_t)npts; a.min_cat = min_cat; a.max_cat = max_cat; a.msg_fill = msg_fill_val;
+    a.n_lm = n_lm; a.is_water_mask = is_water_mask; a.landmask = (float*)dl; a.dominant = (float*)dd;
+    for (int k = 0; k < n_lm; ++k) a.lm_vals[k] = lm_vals[k];
+    k_fractions_dominant<<<(unsigned)((npts + 255) / 256), 256, 0, h->stream>>>(a);
+    h->launches++;
+    WPS_TRY(copy_out(h, field, df, fb));
+    WPS_TRY(copy_out(h, landmask_out, dl, pb));
+    WPS_TRY(copy_out(h, dominant_out, dd, pb));
+    return end_call(h);
+}
+
+int wpsgpu_xytoll_grid(wpsgpu_handle_t h, const wpsgpu_proj* dom, int stagger, int si, int sj, int ei, int ej,
+                       float sub_x, float sub_y, float* xlat, float* xlon)
+{
+    WPS_CHECK(h && dom && xlat && xlon, -1, "wpsgpu_xytoll_grid: NULL argument");
+    WPS_CHECK(dom->init, -1, "projection not initialised");
+    int nx = ei - si + 1, ny = ej - sj + 1;
+    size_t bytes = sizeof(float) * (size_t)nx * ny;
+    WPS_TRY(begin_call(h, 2 * bytes + 4096 + sizeof(float) * WPSGPU_MAX_GAUSS));
+    const float* dg;
+    WPS_TRY(upload_gauss(h, *dom, &dg));
+    void *d1, *d2;
+    WPS_TRY(alloc_out(h, xlat, bytes, &d1));
+    WPS_TRY(alloc_out(h, xlon, bytes, &d2));
+    k_xytoll_grid<<<dim3((nx + 31) / 32, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(to_dev(*dom, dg), stagger, si, sj, nx, ny, sub_x, sub_y, (float*)d1, (float*)d2);
+    h->launches++;
+    WPS_TRY(copy_out(h, xlat, d1, bytes));
+    WPS_TRY(copy_out(h, xlon, d2, bytes));
+    return end_call(h);
+}
+
+int wpsgpu_map_factor(wpsgpu_handle_t h, int iproj, float truelat1, float truelat2, float pole_lat,
+                      float pole_lon, float stand_lon, const float* xlat, const float* xlon, int64_t npts,
+                      float* mapfac_x, float* mapfac_y)
+{
+    WPS_CHECK(h && xlat && xlon && mapfac_x && mapfac_y, -1, "wpsgpu_map_factor: NULL argument");
+    size_t bytes = sizeof(float) * (size_t)npts;
+    WPS_TRY(begin_call(h, 4 * bytes + 4096));
+    MapfacArgs a;
+    a.iproj = iproj; a.truelat1 = truelat1; a.truelat2 = truelat2; a.pole_lat = pole_lat; a.pole_lon = pole_lon; a.stand_lon = stand_lon;
+    const float R = WPS_RAD_PER_DEG;
+    a.n = 0.0f; a.colat0 = R * (90.0f - truelat1); a.colat2 = R * (90.0f - truelat2); a.s0 = 0.0f;
+    if (iproj == WPSGPU_PROJ_LC && truelat1 != truelat2) {
+        float colat1 = R * (90.0f - truelat1), colat2 = a.colat2;
+        a.n = (t_log(t_sin(colat1)) - t_log(t_sin(colat2))) / (t_log(t_tan(colat1 / 2.0f)) - t_log(t_tan(colat2 / 2.0f)));
+    }
+    void *d1, *d2, *o1, *o2;
+    WPS_TRY(stage_in(h, xlat, bytes, &d1));
+    WPS_TRY(stage_in(h, xlon, bytes, &d2));
+    WPS_TRY(alloc_out(h, mapfac_x, bytes, &o1));
+    WPS_TRY(alloc_out(h, mapfac_y, bytes, &o2));
+    k_map_factor<<<(unsigned)((npts + 255) / 256), 256, 0, h->stream>>>(a, (const float*)d1, (const float*)d2, (size_t)npts, (float*)o1, (float*)o2);
+    h->launches++;
+    WPS_TRY(copy_out(h, mapfac_x, o1, bytes));
+    WPS_TRY(copy_out(h, mapfac_y, o2, bytes));
+    return end_call(h);
+}
+
+int wpsgpu_coriolis(wpsgpu_handle_t h, const float* xlat, int64_t npts, float* f, float* e)
+{
+    WPS_CHECK(h && xlat && f && e, -1, "wpsgpu_coriolis: NULL argument");
+    size_t bytes = sizeof(float) * (size_t)npts;
+    WPS_TRY(begin_call(h, 3 * bytes + 4096));
+    void *d1, *o1, *o2;
+    WPS_TRY(stage_in(h, xlat, bytes, &d1));
+    WPS_TRY(alloc_out(h, f, bytes, &o1));
+    WPS_TRY(alloc_out(h, e, bytes, &o2));
+    k_coriolis<<<(unsigned)((npts + 255) / 256), 256, 0, h->stream>>>((const float*)d1, (size_t)npts, (float*)o1, (float*)o2);
+    h->launches++;
+    WPS_TRY(copy_out(h, f, o1, bytes));
+    WPS_TRY(copy_out(h, e, o2, bytes));
+    return end_call(h);
+}
+
+int wpsgpu_rotang(wpsgpu_handle_t h, int iproj, float truelat1, float truelat2, float stand_lon,
+                  const float* xlat, const float* xlon, int si, int sj, int ei, int ej, float* cosa, float* sina)
+{
+    WPS_CHECK(h && xlat && xlon && cosa && sina, -1, "wpsgpu_rotang: NULL argument");
+    WPS_CHECK(iproj != WPSGPU_PROJ_ROTLL, -1, "The NMM rotated lat-lon grid is no longer supported. Rotation angles cannot be computed.");
+    int nx = ei - si + 1, ny = ej - sj + 1;
+    size_t bytes = sizeof(float) * (size_t)nx * ny;
+    WPS_TRY(begin_call(h, 4 * bytes + 4096));
+    float cone = (iproj == WPSGPU_PROJ_LC) ? lc_cone(truelat1, truelat2) : 1.0f;
+    void *d1, *d2, *o1, *o2;
+    WPS_TRY(stage_in(h, xlat, bytes, &d1));
+    WPS_TRY(stage_in(h, xlon, bytes, &d2));
+    WPS_TRY(alloc_out(h, cosa, bytes, &o1));
+    WPS_TRY(alloc_out(h, sina, bytes, &o2));
+    k_rotang<<<dim3((nx + 31) / 32, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(iproj, cone, stand_lon, (const float*)d1, (const float*)d2, nx, ny, (float*)o1, (float*)o2);
+    h->launches++;
+    WPS_TRY(copy_out(h, cosa, o1, bytes));
+    WPS_TRY(copy_out(h, sina, o2, bytes));
+    return end_call(h);
+}
+
+static int dfd(wpsgpu_handle_t h, int dir, const float* src, float* dst, int si, int sj, int sk, int ei, int ej, int ek,
+               int sr, const float* mapfac, float dom_d)
+{
+    WPS_CHECK(h && src && dst, -1, "wpsgpu_dfdx/dfdy: NULL argument");
+    int nx = ei - si + 1, ny = ej - sj + 1, nz = ek - sk + 1;
+    size_t b2 = sizeof(float) * (size_t)nx * ny, b3 = b2 * nz;
+    WPS_TRY(begin_call(h, 2 * b3 + b2 + 4096));
+    void *d1, *dm, *o1;
+    WPS_TRY(stage_in(h, src, b3, &d1));
+    WPS_TRY(stage_in(h, mapfac, b2, &dm));
+    WPS_TRY(alloc_out(h, dst, b3, &o1));
+    // DO-variable value after the interior loop terminates (0-based here)
+    int stale = (dir == 0) ? ((nx - 2 >= 1) ? nx - 1 : 1) : ((ny - 2 >= 1) ? ny - 1 : 1);
+    k_dfd<<<dim3((nx + 31) / 32, (ny + 7) / 8, nz), dim3(32, 8), 0, h->stream>>>(dir, (const float*)d1, (float*)o1, nx, ny, (float)sr, (const float*)dm, dom_d, stale);
+    h->launches++;
+    WPS_TRY(copy_out(h, dst, o1, b3));
+    return end_call(h);
+}
+int wpsgpu_dfdx(wpsgpu_handle_t h, const float* src, float* dst, int si, int sj, int sk, int ei, int ej, int ek,
+                int sr_x, const float* mapfac, float dom_dx)
+{ return dfd(h, 0, src, dst, si, sj, sk, ei, ej, ek, sr_x, mapfac, dom_dx); }
+int wpsgpu_dfdy(wpsgpu_handle_t h, const float* src, float* dst, int si, int sj, int sk, int ei, int ej, int ek,
+                int sr_y, const float* mapfac, float dom_dy)
+{ return dfd(h, 1, src, dst, si, sj, sk, ei, ej, ek, sr_y, mapfac, dom_dy); }
+
+}  // extern "C"
