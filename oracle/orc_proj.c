@@ -171,8 +171,9 @@ void orc_rotate_coords(float ilat, float ilon, float *olat, float *olon, float l
     if (cosphi != 0.0f) { coslam = coslam / cosphi; sinlam = sinlam / cosphi; }
     *olat = DEG_PER_RAD * o_asin(sinphi);
     float ol = DEG_PER_RAD * (o_atan2(sinlam, coslam) - dlam - lam_0 + lam_np);
-    for (;;) { if (ol >= -180.0f) break; ol = ol + 360.0f; }
-    for (;;) { if (ol <= 180.0f) break; ol = ol - 360.0f; }
+    /* DO ... IF (olon >= -180.) EXIT loops of the reference; bounded here so a NaN cannot hang the test harness */
+    for (int it = 0; it < 64; ++it) { if (ol >= -180.0f) break; ol = ol + 360.0f; }
+    for (int it = 0; it < 64; ++it) { if (ol <= 180.0f) break; ol = ol - 360.0f; }
     *olon = ol;
 }
 

@@ -16,6 +16,7 @@ def pytest_configure(config):
 def orc():
     from oracle import oracle as O
     O.lib()
+    O.set_transc_mode(1)  # FP64-then-round transcendental policy shared with the CUDA product
     return O
 
 

@@ -28,8 +28,8 @@ def tiles_for(domain_ll, dxdeg, tile_n, bdr, known_lat=-89.99583, known_lon=-179
 def run_field(orc, handle, itype, chain, nk, start_k, tile_fn, tile_n, bdr, dxdeg, nx=60, ny=50, dx=9000.0,
               landmask=None, mask_val=-1.0, msg=1e20, fill=1e20, ilevel=1, scale=None, stag=1, sr=1):
     from wps_b200 import capi
-    odom, gdom = conus_like(nx, ny, dx, 30.0, 60.0, -98.0, 39.0, -105.0)
     orc.set_transc_mode(1)
+    odom, gdom = conus_like(nx, ny, dx, 30.0, 60.0, -98.0, 39.0, -105.0)
     gx, gy = nx + 6, ny + 6  # patch +- HALO_WIDTH as process_tile does
     xlat, xlon = orc.get_lat_lon_fields(odom, -2, -2, gx, gy, stag)
     kw = dict(dlat=dxdeg, dlon=dxdeg, known_x=1.0, known_y=1.0, known_lat=-89.99583, known_lon=-179.99583)
@@ -159,8 +159,8 @@ def test_raw_tile_decode(orc, handle):
     """wpsgpu_geogrid_add_tile_raw decodes read_geogrid.c byte layouts (big/little endian, signed, 1-4 bytes, row flip)
     identically to decoding on the host."""
     from wps_b200 import capi
-    odom, gdom = conus_like(30, 30, 9000.0, 30.0, 60.0, -98.0, 39.0, -105.0)
     orc.set_transc_mode(1)
+    odom, gdom = conus_like(30, 30, 9000.0, 30.0, 60.0, -98.0, 39.0, -105.0)
     xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, 30, 30, 1)
     kw = dict(dlat=0.01, dlon=0.01, known_x=1.0, known_y=1.0, known_lat=37.5, known_lon=-107.0)
     gsrc = capi.push_source_projection(capi.PROJ_LATLON, **kw)

@@ -18,8 +18,8 @@ CHAINS = ["sixteen_pt+four_pt+average_4pt", "four_pt+average_4pt", "nearest_neig
 
 
 def make_domain(orc, handle, nx=101, ny=91, dx=30000.0, ref_lat=34.83, ref_lon=-81.03, stagger="M"):
-    odom, gdom = conus_like(nx, ny, dx, truelat1=30.0, truelat2=60.0, stand_lon=-98.0, ref_lat=ref_lat, ref_lon=ref_lon)
     orc.set_transc_mode(1)
+    odom, gdom = conus_like(nx, ny, dx, truelat1=30.0, truelat2=60.0, stand_lon=-98.0, ref_lat=ref_lat, ref_lon=ref_lon)
     st = {"M": orc.M, "U": orc.U, "V": orc.V}[stagger]
     gx, gy = nx, ny
     xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, gx, gy, st)
@@ -131,8 +131,8 @@ def test_process_bdy_width_and_staggers(orc, handle):
     slabs = [halo(synth_field(360, 181, 50, kind="wind"))]
     for stag, fstag in (("M", 1), ("U", 2), ("V", 3)):
         nx, ny = 60 + (stag == "U"), 48 + (stag == "V")
-        odom, _ = conus_like(60, 48, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)
         orc.set_transc_mode(1)
+        odom, _ = conus_like(60, 48, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)
         xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, nx, ny, fstag)
         run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+average_4pt", fill=0.0, pbw=5, fstag=fstag,
                  sd=(1, 60, 1, 48), grid_id=fstag)
@@ -171,8 +171,8 @@ def test_gaussian_source(orc, handle):
 
 def test_dateline_retry_and_southern_hemisphere(orc, handle):
     """Domain straddling the dateline with a 0..360 source (exercises the lon+360 retry, :2637-2665) and an SH domain."""
-    odom, _ = conus_like(80, 60, 45000.0, -30.0, -60.0, 175.0, -40.0, 178.0)
     orc.set_transc_mode(1)
+    odom, _ = conus_like(80, 60, 45000.0, -30.0, -60.0, 175.0, -40.0, 178.0)
     xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, 80, 60, orc.M)
     # regional source 120E..240E expressed in 0..360 longitudes (no halo)
     from wps_b200 import capi
@@ -203,8 +203,8 @@ def test_batch_many_fields_one_flush(orc, handle):
     """One flush holding slabs of different fields/staggers/chains (the process_intermediate_fields record loop)."""
     from wps_b200 import capi
     src_o, src_g = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
-    odom, _ = conus_like(50, 44, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)
     orc.set_transc_mode(1)
+    odom, _ = conus_like(50, 44, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)
     grids = {}
     for gid, (st, nx, ny) in {0: (orc.M, 50, 44), 1: (orc.U, 51, 44), 2: (orc.V, 50, 45)}.items():
         grids[gid] = orc.get_lat_lon_fields(odom, 1, 1, nx, ny, st)
