@@ -245,6 +245,7 @@ def run_b200(args, rank, world, local_rank):
         enqueue_all(h, w)
         ms, kp = h.metgrid_last_kernel()
         kms.append(ms)
+        t3, p3 = h.metgrid_last_timings()
     sampler.stop_flag = True
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -253,38 +254,40 @@ def run_b200(args, rank, world, local_rank):
     value = world * pts / (ms_per_step / 1e3)
 
     # ---- e2e: host buffers in pinned memory through the C ABI (H2D + kernels + D2H inside the timed region) ----
-    hh = capi.Handle(local_rank, capi.PTR_HOST)
-    for gid, (xlat, xlon) in w["grids"].items():
-        hh.metgrid_set_grid(gid, xlat.cpu().numpy(), xlon.cpu().numpy(), 1, 1)
-    hh.metgrid_set_landmask(0, w["landmask"].cpu().numpy())
-    hh.metgrid_set_domain(1, nx, 1, ny)
-    host, h2d, d2h = [], 0, 0
-    seen = set()
-    for p in w["plan"]:
-        hs = p["slabs"].cpu().pin_memory()
-        hm = tuple(None if m is None else m.cpu().pin_memory() for m in p["masks"])
-        hr = torch.empty(p["r"].shape, dtype=torch.float32).pin_memory()
-        hn = torch.zeros(p["npw"].shape, dtype=torch.int32).pin_memory()
-        host.append(dict(slabs=hs, masks=hm, r=hr, npw=hn))
-        h2d += hs.numel() * 4
-        for m in hm:
-            if m is not None and "mask" not in seen:
-                h2d += m.numel() * 4
-                seen.add("mask")
-        d2h += hr.numel() * 4 + hn.numel() * 4
-    e2e_steps = max(1, min(args.steps, 3))
-    enqueue_all(hh, w, host)  # warm-up (arena allocation, coordinate cache)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        enqueue_all(hh, w, host)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * pts / float(t.item())
-    hh.close()
+    e2e_value, e2e_s, h2d, d2h = None, 0.0, 0, 0
+    if not args.no_e2e:
+        hh = capi.Handle(local_rank, capi.PTR_HOST)
+        for gid, (xlat, xlon) in w["grids"].items():
+            hh.metgrid_set_grid(gid, xlat.cpu().numpy(), xlon.cpu().numpy(), 1, 1)
+        hh.metgrid_set_landmask(0, w["landmask"].cpu().numpy())
+        hh.metgrid_set_domain(1, nx, 1, ny)
+        host, h2d, d2h = [], 0, 0
+        seen = set()
+        for p in w["plan"]:
+            hs = p["slabs"].cpu().pin_memory()
+            hm = tuple(None if m is None else m.cpu().pin_memory() for m in p["masks"])
+            hr = torch.empty(p["r"].shape, dtype=torch.float32).pin_memory()
+            hn = torch.zeros(p["npw"].shape, dtype=torch.int32).pin_memory()
+            host.append(dict(slabs=hs, masks=hm, r=hr, npw=hn))
+            h2d += hs.numel() * 4
+            for m in hm:
+                if m is not None and "mask" not in seen:
+                    h2d += m.numel() * 4
+                    seen.add("mask")
+            d2h += hr.numel() * 4 + hn.numel() * 4
+        e2e_steps = max(1, min(args.steps, 3))
+        enqueue_all(hh, w, host)  # warm-up (arena allocation, coordinate cache)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            enqueue_all(hh, w, host)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * pts / float(t.item())
+        hh.close()
 
     if rank == 0:
         peaks = {}
@@ -302,8 +305,10 @@ def run_b200(args, rank, world, local_rank):
                            "points_per_step_per_gpu": pts, "l2": "inputs (792 MB of source slabs) and outputs (1.45 GB) per step exceed the 126 MB L2",
                            "sharding": "one FILE time per GPU per step (field x level x time shard, no collective)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "k_metgrid_interp", "kernel_ms": kms_avg,
-                             "alg_bytes_per_point": ALG_BYTES_PER_POINT, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+                             "traffic": None, "kernel": "k_metgrid_fast16" if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
+                             "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
+                             "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_interp(generic)": t3[2]},
+                             "breakdown_points": {"fast16": p3[1], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches), "clocks": sampler.result()}
@@ -323,6 +328,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

@@ -148,6 +148,10 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h);
 /* Device time (CUDA events on the handle's stream) of the dominant kernel of the last flush and the number of
  * (slab x destination point) outputs it produced -- for roofline reporting only. */
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);
+/* Same, broken down: [0] packing pre-pass, [1] packed sixteen_pt kernel, [2] generic kernel. */
+int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms3, double *points3);
+/* Testing aid: disable!=0 routes every job through the generic kernel (used to test both kernels against the oracle). */
+int wpsgpu_debug_disable_fast(wpsgpu_handle_t h, int disable);
 /* The average_gcell branch (:2331-2478) with metgrid's accum_continuous (:3347-3717); dom_proj is the
  * projection set_domain_projection built (llxy_module.F:191).  Executes immediately. */
 int wpsgpu_metgrid_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj *src_proj, const wpsgpu_proj *dom_proj,

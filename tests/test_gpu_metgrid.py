@@ -40,24 +40,26 @@ def run_case(orc, handle, xlat, xlon, slabs, src, chain, sm=(1, 1), sd=None, bdr
     if landmask is not None:
         handle.metgrid_set_landmask(grid_id, landmask)
     handle.metgrid_set_domain(*sd)
-    outs = []
-    for slab in slabs:
-        r = np.zeros((ny, nx), np.float32) if r0 is None else r0.copy()
-        npw = np.zeros((ny, capi.nwords(nx)), np.int32)
-        handle.metgrid_enqueue_slab(gsrc, fo_g, slab, minx, miny, bdr, grid_id, fstag, r, npw, valid_mask=valid,
-                                    masks=masks, use_landmask=landmask is not None, process_bdy_width=pbw)
-        outs.append((r, npw))
-    handle.metgrid_flush()
     orc.set_transc_mode(1)
-    for slab, (r, npw) in zip(slabs, outs):
-        r_ref, np_ref = orc.interp_met_field(osrc, fo_o, fstag, xlat, xlon, sm[0], sm[1], sd, slab, minx, miny, bdr,
-                                             mask=masks[0], land_mask=masks[1], water_mask=masks[2], landmask=landmask,
-                                             process_bdy_width=pbw, r_arr=None if r0 is None else r0.copy(),
-                                             valid_mask=valid)
-        assert (npw == np_ref).all(), "new_pts bits differ for chain %s: %d words" % (chain, (npw != np_ref).sum())
-        bits = bits_to_bool(np_ref, nx) | (bits_to_bool(valid, nx) if valid is not None else False)
-        # r_arr is defined wherever a bit is set (new or previously valid) or it was filled
-        assert_bitexact(r, r_ref, "r_arr chain=%s" % chain)
+    refs = [orc.interp_met_field(osrc, fo_o, fstag, xlat, xlon, sm[0], sm[1], sd, slab, minx, miny, bdr, mask=masks[0],
+                                 land_mask=masks[1], water_mask=masks[2], landmask=landmask, process_bdy_width=pbw,
+                                 r_arr=None if r0 is None else r0.copy(), valid_mask=valid) for slab in slabs]
+    # both device paths against the oracle: the packed sixteen_pt kernel (when eligible) and the generic kernel
+    for disable_fast in (False, True):
+        handle.debug_disable_fast(disable_fast)
+        outs = []
+        for slab in slabs:
+            r = np.zeros((ny, nx), np.float32) if r0 is None else r0.copy()
+            npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+            handle.metgrid_enqueue_slab(gsrc, fo_g, slab, minx, miny, bdr, grid_id, fstag, r, npw, valid_mask=valid,
+                                        masks=masks, use_landmask=landmask is not None, process_bdy_width=pbw)
+            outs.append((r, npw))
+        handle.metgrid_flush()
+        for (r_ref, np_ref), (r, npw) in zip(refs, outs):
+            assert (npw == np_ref).all(), "new_pts bits differ for chain %s (fast disabled=%s): %d words" % (
+                chain, disable_fast, (npw != np_ref).sum())
+            assert_bitexact(r, r_ref, "r_arr chain=%s fast_disabled=%s" % (chain, disable_fast))
+    handle.debug_disable_fast(False)
     return outs
 
 
@@ -237,3 +239,24 @@ def test_batch_many_fields_one_flush(orc, handle):
         r_ref, np_ref = orc.interp_met_field(src_o, fo_o, fstag, xlat, xlon, 1, 1, (1, 50, 1, 44), slab, -2, 1, 3, mask=mask)
         assert (npw == np_ref).all()
         assert_bitexact(r, r_ref, "batched slab")
+
+
+@pytest.mark.parametrize("missing", [1e20, -1e30, 0.0])
+def test_packed_many_levels(orc, handle, missing):
+    """11 levels of one field in a single flush (3 packs of 4 levels, last one partial) through the packed sixteen_pt
+    kernel: clean levels, levels with missing values, exact zeros, tiny values whose products underflow, and
+    missing_value=0 (zeros are then not replaced by 1.E-20 and take the fallback)."""
+    xlat, xlon = make_domain(orc, handle, nx=131, ny=97, dx=12000.0)
+    src = latlon_source(720, 361, -0.5, 0.5, 90.0, 0.0)
+    slabs = []
+    for s in range(11):
+        f = synth_field(720, 361, 70 + s, kind="wind" if s % 2 else "smooth", zeros=0.01 if s % 3 == 0 else 0.0)
+        if s in (2, 7):
+            f[np.random.default_rng(s).random(f.shape) < 0.03] = np.float32(missing)
+        if s == 5:
+            f *= np.float32(1e-24)   # products of neighbours underflow to zero -> oned special branches
+        if s == 9:
+            f[:] = np.float32(3.25)  # constant field
+        slabs.append(halo(f))
+    run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+average_4pt", missing=np.float32(missing), fill=0.0)
+    run_case(orc, handle, xlat, xlon, slabs[:5], src, "sixteen_pt+four_pt+wt_average_4pt+search", missing=np.float32(missing), fill=0.0)

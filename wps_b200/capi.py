@@ -269,6 +269,15 @@ class Handle:
         check(lib().wpsgpu_metgrid_last_kernel(self._h, C.byref(ms), C.byref(pts)))
         return ms.value, pts.value
 
+    def metgrid_last_timings(self):
+        ms = (C.c_float * 3)()
+        pts = (C.c_double * 3)()
+        check(lib().wpsgpu_metgrid_last_timings(self._h, ms, pts))
+        return list(ms), list(pts)
+
+    def debug_disable_fast(self, disable=True):
+        check(lib().wpsgpu_debug_disable_fast(self._h, int(disable)))
+
     def rotate_winds(self, idir, proj, u, u_mask, v, v_mask, xlon_u, xlon_v, us=(1, 1), vs=(1, 1)):
         """u [nlev][uny][unx], v [nlev][vny][vnx] rotated in place (metmap_xform)."""
         nlev, uny, unx = u.shape

@@ -354,8 +354,9 @@ int wpsgpu_create(int device_id, wpsgpu_handle_t* out)
     h->sm_count = prop.multiProcessorCount;
     WPS_CUDA(cudaMalloc((void**)&h->d_counters, 64 * sizeof(int)));
     WPS_CUDA(cudaMemsetAsync(h->d_counters, 0, 64 * sizeof(int), h->stream));
-    WPS_CUDA(cudaEventCreate(&h->ev_k0));
-    WPS_CUDA(cudaEventCreate(&h->ev_k1));
+    for (int k = 0; k < 6; ++k) WPS_CUDA(cudaEventCreate(&h->ev_t[k]));
+    h->ev_k0 = h->ev_t[4]; h->ev_k1 = h->ev_t[5];
+    for (int k = 0; k < 6; ++k) WPS_CUDA(cudaEventRecord(h->ev_t[k], h->stream));
     *out = h;
     return 0;
 }
@@ -367,15 +368,14 @@ int wpsgpu_destroy(wpsgpu_handle_t h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (auto& kv : h->coord_cache) cudaFree(kv.second.d_xy);
+    for (auto& kv : h->coord_cache) { cudaFree(kv.second.d_xy); if (kv.second.d_gauss) cudaFree(kv.second.d_gauss); }
     for (auto& g : h->grids)
         if (g.own) { cudaFree(g.d_xlat); cudaFree(g.d_xlon); if (g.d_landmask) cudaFree(g.d_landmask); }
     wpsgpu_geo_free(h);
     h->arena.release();
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_search_scratch) cudaFree(h->d_search_scratch);
-    if (h->ev_k0) cudaEventDestroy(h->ev_k0);
-    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
+    for (int k = 0; k < 6; ++k) if (h->ev_t[k]) cudaEventDestroy(h->ev_t[k]);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;

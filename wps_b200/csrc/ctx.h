@@ -64,6 +64,8 @@ struct DstGrid {
 struct CoordCacheEntry {
     uint64_t grid_version;
     float2* d_xy;  // (rx, ry) of lltoxy(xlat, xlon) with the source projection, M stagger
+    int bbox[4];   // min/max of floor(rx), floor(ry) over the destination grid (source-cell bounding box)
+    float* d_gauss; // device copy of the Gaussian latitude table (PROJ_GAUSS sources), else nullptr
 };
 
 struct QueuedSlab {
@@ -96,8 +98,12 @@ struct wpsgpu_ctx {
     void* d_search_scratch = nullptr;
     size_t search_scratch_bytes = 0;
     // CUDA events bracketing the dominant kernel of the last metgrid flush (roofline measurement)
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // aliases into ev_t[] of the dominant kernel
+    cudaEvent_t ev_dummy0 = nullptr, ev_dummy1 = nullptr;
+    cudaEvent_t ev_t[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };  // pack / fast16 / generic brackets
     double last_points = 0.0;
+    double last_pts3[3] = { 0.0, 0.0, 0.0 };
+    bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };
 
 namespace wps {
