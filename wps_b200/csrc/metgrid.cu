@@ -302,41 +302,23 @@ __device__ __forceinline__ float2 ypass2(float2 a, float2 b, float2 c, float2 d,
     return add2(mul2(omy, p, k), mul2(y, q, k), k);
 }
 
-__global__ void __launch_bounds__(TILE_X * TILE_Y, 3)
-k_metgrid_fast16(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_tile0, int ncls,
-                 const SlabPtrs* __restrict__ slabs)
+// Launch parameters live in the constant bank: the job descriptor and the per-level output pointers are
+// warp-uniform constant loads that do not consume LSU write-back bandwidth (the limiter of this kernel).
+struct FastParams {
+    Job jb;
+    float* r_arr[FAST_MAX_SLABS];
+    int* new_pts[FAST_MAX_SLABS];
+    int* slow[FAST_MAX_SLABS];
+};
+
+__global__ void __launch_bounds__(TILE_X * TILE_Y, 4)
+k_metgrid_fast16(const __grid_constant__ FastParams P)
 {
-    __shared__ Job jb;
-    __shared__ int s_job, s_tile0;
-    __shared__ float* s_r[FAST_MAX_SLABS];
-    __shared__ int* s_np[FAST_MAX_SLABS];
-    __shared__ int* s_slow[FAST_MAX_SLABS];
-    const int tid = threadIdx.y * TILE_X + threadIdx.x;
-    if (tid == 0) {
-        int lo = 0, hi = ncls - 1, b = blockIdx.x;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (cls_tile0[mid] <= b) lo = mid; else hi = mid - 1;
-        }
-        s_job = cls_jobs[lo]; s_tile0 = cls_tile0[lo];
-    }
-    __syncthreads();
-    {
-        const int* gsrc = reinterpret_cast<const int*>(jobs + s_job);
-        int* sdst = reinterpret_cast<int*>(&jb);
-        for (int w = tid; w < (int)(sizeof(Job) / sizeof(int)); w += TILE_X * TILE_Y) sdst[w] = gsrc[w];
-    }
-    __syncthreads();
-    if (tid < jb.nslab) {
-        const SlabPtrs sp = slabs[jb.slab0 + tid];
-        s_r[tid] = sp.r_arr; s_np[tid] = sp.new_pts; s_slow[tid] = sp.slow;
-    }
-    __syncthreads();
+    const Job& jb = P.jb;
     const int nslab = jb.nslab, npack = jb.npack, nx = jb.nx, ny = jb.ny;
     const float msg = jb.msg;
-    int t = blockIdx.x - s_tile0;
-    int tx = t % jb.tiles_x, ty = t / jb.tiles_x;
-    int ii = tx * TILE_X + threadIdx.x, jj = ty * TILE_Y + threadIdx.y;
+    const int tx = blockIdx.x % jb.tiles_x, ty = blockIdx.x / jb.tiles_x;
+    const int ii = tx * TILE_X + threadIdx.x, jj = ty * TILE_Y + threadIdx.y;
     const bool active = ii < nx && jj < ny;
     const size_t idx = (size_t)jj * nx + ii;
     const size_t widx = (size_t)jj * jb.nxw + tx;
@@ -405,9 +387,9 @@ k_metgrid_fast16(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs,
             float r = val[lv];
             if (r == 1.0e-20f) r = 0.0f;
             bool ok = ((cfbits >> lv) & 1u) && gen[lv] && r != msg;
-            if (ok) s_r[sl][idx] = r;
+            if (ok) P.r_arr[sl][idx] = r;
             unsigned word = __ballot_sync(0xffffffffu, ok), sword = __ballot_sync(0xffffffffu, active && !ok);
-            if (wlead) { s_np[sl][widx] = (int)word; s_slow[sl][widx] = (int)sword; }
+            if (wlead) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
         }
     }
 }
@@ -888,8 +870,14 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
     WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
-    if (tile_cursor[1] > 0) {
-        k_metgrid_fast16<<<tile_cursor[1], block, 0, h->stream>>>(d_jobs, d_cls_jobs[1], d_cls_tile0[1], (int)cls_jobs[1].size(), d_sp);
+    for (int g : cls_jobs[1]) {
+        FastParams fp;
+        fp.jb = jobs[g];
+        for (int k = 0; k < fp.jb.nslab; ++k) {
+            const SlabPtrs& p = sp[fp.jb.slab0 + k];
+            fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
+        }
+        k_metgrid_fast16<<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
         h->launches++;
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
