@@ -148,8 +148,9 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h);
 /* Device time (CUDA events on the handle's stream) of the dominant kernel of the last flush and the number of
  * (slab x destination point) outputs it produced -- for roofline reporting only. */
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);
-/* Same, broken down: [0] packing pre-pass, [1] packed sixteen_pt kernel, [2] generic kernel. */
-int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms3, double *points3);
+/* Same, broken down (arrays of 4): [0] packing pre-pass, [1] packed sixteen_pt kernel, [2] generic kernel,
+ * [3] four_pt / nearest_neighbor first-method kernels. */
+int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms4, double *points4);
 /* Testing aid: disable!=0 routes every job through the generic kernel (used to test both kernels against the oracle). */
 int wpsgpu_debug_disable_fast(wpsgpu_handle_t h, int disable);
 /* The average_gcell branch (:2331-2478) with metgrid's accum_continuous (:3347-3717); dom_proj is the

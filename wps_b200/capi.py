@@ -270,8 +270,8 @@ class Handle:
         return ms.value, pts.value
 
     def metgrid_last_timings(self):
-        ms = (C.c_float * 3)()
-        pts = (C.c_double * 3)()
+        ms = (C.c_float * 4)()
+        pts = (C.c_double * 4)()
         check(lib().wpsgpu_metgrid_last_timings(self._h, ms, pts))
         return list(ms), list(pts)
 

@@ -100,9 +100,9 @@ struct wpsgpu_ctx {
     // CUDA events bracketing the dominant kernel of the last metgrid flush (roofline measurement)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // aliases into ev_t[] of the dominant kernel
     cudaEvent_t ev_dummy0 = nullptr, ev_dummy1 = nullptr;
-    cudaEvent_t ev_t[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };  // pack / fast16 / generic brackets
+    cudaEvent_t ev_t[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };  // pack / fast16 / generic / fast4 brackets
     double last_points = 0.0;
-    double last_pts3[3] = { 0.0, 0.0, 0.0 };
+    double last_pts3[4] = { 0.0, 0.0, 0.0, 0.0 };
     bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };
 

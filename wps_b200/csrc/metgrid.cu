@@ -252,6 +252,15 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, in
             float w[4];
             row4(r, w);
             clean = clean && w[0] != msg && w[1] != msg && w[2] != msg && w[3] != msg && (w[1] * w[2] != 0.0f) && (w[0] * w[3] != 0.0f);
+            if (jb.mask[0]) {   // interp_mask: any unusable cell in the stencil sends sixteen_pt to the next method (:1244-1270)
+                const float* mp = jb.mask[0] + (size_t)(r - sy) * snx;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float m = __ldg(mp + col[k]);
+                    bool out_ = jb.mask_rel[0] == REL_GT ? (m > jb.mask_val[0]) : (jb.mask_rel[0] == REL_LT ? (m < jb.mask_val[0]) : (m == jb.mask_val[0]));
+                    clean = clean && !out_;
+                }
+            }
         }
         if (clean) cfbits |= 1u << lv;
     }
@@ -324,8 +333,8 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
     const size_t widx = (size_t)jj * jb.nxw + tx;
     const bool wlead = threadIdx.x == 0 && jj < ny;
 
-    // level-independent part of sixteen_pt (interp_module.F:1211-1241)
-    bool fastpt = false;
+    // level-independent part of interp_met_field's point logic (:2490-2541) and of sixteen_pt (interp_module.F:1211-1241)
+    bool fastpt = false, fillpt = false;
     float x = 0.0f, y = 0.0f;
     int roff[4] = {0, 0, 0, 0}, cfoff = 0;
     if (active) {
@@ -333,9 +342,11 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
         int di = jb.sm1 + ii, dj = jb.sm2 + jj;
         const int pw = jb.pw;
         bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+        // process_bdy_width interior, or landmask == masked: the point receives fill_missing and counts as new
+        fillpt = in_fill || (jb.landmask != nullptr && __ldg(jb.landmask + idx) == jb.masked);
         float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
         float xx = xy.x, yy = xy.y;
-        if (!in_fill && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f &&
+        if (!fillpt && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f &&
             (int)xx >= jb.minx && (int)xx <= jb.maxx && (int)yy >= jb.miny && (int)yy <= jb.maxy) {
             int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
             x = xx - (float)i; y = yy - (float)j;
@@ -387,10 +398,94 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
             float r = val[lv];
             if (r == 1.0e-20f) r = 0.0f;
             bool ok = ((cfbits >> lv) & 1u) && gen[lv] && r != msg;
+            if (fillpt) { r = jb.fill; ok = true; }
             if (ok) P.r_arr[sl][idx] = r;
             unsigned word = __ballot_sync(0xffffffffu, ok), sword = __ballot_sync(0xffffffffu, active && !ok);
             if (wlead) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
         }
+    }
+}
+
+// ---- four_pt / nearest_neighbor first-method kernel ------------------------------------------------------------
+// Same structure for chains that start with four_pt (interp_module.F:1055-1171) or nearest_neighbor (:376-442):
+// indices, weights and the interp-mask test are level-independent; per level 4 (or 1) loads and the reference's
+// arithmetic.  Missing corners, degenerate cells (integer coordinates) and out-of-range points go to the slow bitmap.
+struct Fast4Params {
+    Job jb;
+    const float* src[FAST_MAX_SLABS];
+    float* r_arr[FAST_MAX_SLABS];
+    int* new_pts[FAST_MAX_SLABS];
+    int* slow[FAST_MAX_SLABS];
+};
+
+template <int OP>
+__global__ void __launch_bounds__(TILE_X * TILE_Y, 4)
+k_metgrid_fast4(const __grid_constant__ Fast4Params P)
+{
+    const Job& jb = P.jb;
+    const int nslab = jb.nslab, nx = jb.nx, ny = jb.ny;
+    const float msg = jb.msg;
+    const int tx = blockIdx.x % jb.tiles_x, ty = blockIdx.x / jb.tiles_x;
+    const int ii = tx * TILE_X + threadIdx.x, jj = ty * TILE_Y + threadIdx.y;
+    const bool active = ii < nx && jj < ny;
+    const size_t idx = (size_t)jj * nx + ii;
+    const size_t widx = (size_t)jj * jb.nxw + tx;
+    const bool wlead = threadIdx.x == 0 && jj < ny;
+    bool fastpt = false, fillpt = false;
+    float wx0 = 0.0f, wx1 = 0.0f, wy0 = 0.0f, wy1 = 0.0f;   // (max_x-xx), (xx-min_x), (max_y-yy), (yy-min_y)
+    int o00 = 0, o10 = 0, o01 = 0, o11 = 0;
+    if (active) {
+        float2 xy = __ldg(jb.xy + idx);
+        int di = jb.sm1 + ii, dj = jb.sm2 + jj;
+        const int pw = jb.pw;
+        bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+        fillpt = in_fill || (jb.landmask != nullptr && __ldg(jb.landmask + idx) == jb.masked);
+        float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
+        float xx = xy.x, yy = xy.y;
+        const int snx = jb.maxx - jb.minx + 1;
+        if (!fillpt && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f) {
+            Src ms;   // mask view for the level-independent mask tests
+            ms.a = nullptr; ms.m = jb.mask[0]; ms.sx = jb.minx; ms.ex = jb.maxx; ms.sy = jb.miny; ms.ey = jb.maxy; ms.nx = snx;
+            ms.msg = msg; ms.maskval = jb.mask_val[0]; ms.rel = jb.mask_rel[0];
+            if (OP == WPSGPU_FOUR_POINT) {
+                int min_x = f_floor(xx), min_y = f_floor(yy), max_x = f_ceiling(xx), max_y = f_ceiling(yy);
+                if (min_x >= jb.minx && max_x <= jb.maxx && min_y >= jb.miny && max_y <= jb.maxy && min_x != max_x && min_y != max_y) {
+                    bool m = ms.m && (masked_out(ms, min_x, min_y) || masked_out(ms, max_x, min_y) || masked_out(ms, min_x, max_y) || masked_out(ms, max_x, max_y));
+                    if (!m) {
+                        fastpt = true;
+                        wx0 = (float)max_x - xx; wx1 = xx - (float)min_x; wy0 = (float)max_y - yy; wy1 = yy - (float)min_y;
+                        o00 = (min_y - jb.miny) * snx + (min_x - jb.minx); o10 = o00 + 1; o01 = o00 + snx; o11 = o01 + 1;
+                    }
+                }
+            } else {
+                int ix = f_nint(xx), iy = f_nint(yy);
+                if (ix >= jb.minx && ix <= jb.maxx && iy >= jb.miny && iy <= jb.maxy && !(ms.m && masked_out(ms, ix, iy))) {
+                    fastpt = true;
+                    o00 = (iy - jb.miny) * snx + (ix - jb.minx);
+                }
+            }
+        }
+    }
+#pragma unroll 4
+    for (int sl = 0; sl < nslab; ++sl) {
+        const float* __restrict__ src = P.src[sl];
+        bool ok = false;
+        float r = 0.0f;
+        if (fastpt) {
+            if (OP == WPSGPU_FOUR_POINT) {
+                float a00 = __ldg(src + o00), a10 = __ldg(src + o10), a01 = __ldg(src + o01), a11 = __ldg(src + o11);
+                // four_pt general case, interp_module.F:1165-1168
+                r = wy1 * (a01 * wx0 + a11 * wx1) + wy0 * (a00 * wx0 + a10 * wx1);
+                ok = a00 != msg && a10 != msg && a01 != msg && a11 != msg && r != msg;
+            } else {
+                r = __ldg(src + o00);
+                ok = r != msg;
+            }
+        }
+        if (fillpt) { r = jb.fill; ok = true; }
+        if (ok) P.r_arr[sl][idx] = r;
+        unsigned word = __ballot_sync(0xffffffffu, ok), sword = __ballot_sync(0xffffffffu, active && !ok);
+        if (wlead) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
     }
 }
 
@@ -401,41 +496,56 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_job
                    const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count,
                    long long total_words)
 {
+    // each lane fetches one bitmap word (coalesced); the warp then walks the non-empty words together, lane b taking
+    // point b of the word, so the flagged points of a word are processed in parallel
+    const int lane = threadIdx.x & 31;
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= total_words) return;
-    int lo = 0, hi = ncls - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if ((long long)cls_word0[mid] <= w) lo = mid; else hi = mid - 1;
-    }
-    const Job& jb = jobs[cls_jobs[lo]];
-    long long rel = w - cls_word0[lo];
-    long long words_per_slab = (long long)jb.ny * jb.nxw;
-    int sl = (int)(rel / words_per_slab);
-    long long widx = rel % words_per_slab;
-    const SlabPtrs sp = slabs[jb.slab0 + sl];
-    unsigned bits = (unsigned)sp.slow[widx];
-    if (!bits) return;
-    int jj = (int)(widx / jb.nxw), tx = (int)(widx % jb.nxw);
-    unsigned vword = sp.valid ? (unsigned)__ldg(sp.valid + widx) : 0u;
-    unsigned newbits = 0;
-    while (bits) {
-        int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        int ii = tx * 32 + b;
-        size_t idx = (size_t)jj * jb.nx + ii;
-        float out = 0.0f;
-        int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, __ldg(jb.xy + idx), (vword >> b) & 1u, out);
-        if (flags & PF_DEFER) {
-            unsigned long long slot = atomicAdd(defer_count, 1ull);
-            Deferred d; d.slab = jb.slab0 + sl; d.idx = (int)idx;
-            deferred[slot] = d;
-        } else {
-            if (flags & PF_WRITE) sp.r_arr[idx] = out;
-            if (flags & PF_BIT) newbits |= 1u << b;
+    unsigned bits = 0;
+    int job = 0, sl = 0;
+    long long widx = 0;
+    if (w < total_words) {
+        int lo = 0, hi = ncls - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if ((long long)cls_word0[mid] <= w) lo = mid; else hi = mid - 1;
         }
+        job = cls_jobs[lo];
+        const Job& jb = jobs[job];
+        long long rel = w - cls_word0[lo];
+        long long words_per_slab = (long long)jb.ny * jb.nxw;
+        sl = (int)(rel / words_per_slab);
+        widx = rel % words_per_slab;
+        bits = (unsigned)slabs[jb.slab0 + sl].slow[widx];
     }
-    if (newbits) atomicOr(sp.new_pts + widx, (int)newbits);
+    unsigned pending = __ballot_sync(0xffffffffu, bits != 0);
+    while (pending) {
+        int srcl = __ffs(pending) - 1;
+        pending &= pending - 1;
+        unsigned wbits = __shfl_sync(0xffffffffu, bits, srcl);
+        int wjob = __shfl_sync(0xffffffffu, job, srcl), wsl = __shfl_sync(0xffffffffu, sl, srcl);
+        long long wwidx = __shfl_sync(0xffffffffu, widx, srcl);
+        const Job& jb = jobs[wjob];
+        const SlabPtrs sp = slabs[jb.slab0 + wsl];
+        bool newbit = false;
+        if ((wbits >> lane) & 1u) {
+            int jj = (int)(wwidx / jb.nxw), tx = (int)(wwidx % jb.nxw);
+            int ii = tx * 32 + lane;
+            size_t idx = (size_t)jj * jb.nx + ii;
+            bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> lane) & 1u) : false;
+            float out = 0.0f;
+            int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, __ldg(jb.xy + idx), vbit, out);
+            if (flags & PF_DEFER) {
+                unsigned long long slot = atomicAdd(defer_count, 1ull);
+                Deferred d; d.slab = jb.slab0 + wsl; d.idx = (int)idx;
+                deferred[slot] = d;
+            } else {
+                if (flags & PF_WRITE) sp.r_arr[idx] = out;
+                newbit = (flags & PF_BIT) != 0;
+            }
+        }
+        unsigned nb = __ballot_sync(0xffffffffu, newbit);
+        if (lane == 0 && nb) atomicOr(sp.new_pts + wwidx, (int)nb);
+    }
 }
 
 // ---- deferred passes: warp per point (closed-form search), then thread per point (literal) ---------
@@ -627,7 +737,8 @@ int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float* ms3, double* points3)
 {
     WPS_CHECK(h && ms3 && points3, -1, "NULL argument");
     WPS_CUDA(cudaEventSynchronize(h->ev_t[5]));
-    for (int k = 0; k < 3; ++k) {
+    WPS_CUDA(cudaEventSynchronize(h->ev_t[7]));
+    for (int k = 0; k < 4; ++k) {
         WPS_CUDA(cudaEventElapsedTime(&ms3[k], h->ev_t[2 * k], h->ev_t[2 * k + 1]));
         points3[k] = h->last_pts3[k];
     }
@@ -715,16 +826,20 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         Box& b = box[g];
         b.fast = 0; b.bx0 = b.by0 = b.bnx = b.bny = b.npack = 0;
         const int* bb = &job_bbox[4 * g];
-        bool no_mask_path = q0.s.mask[0] == nullptr && (!q0.s.use_landmask || q0.fo.masked == WPSGPU_NOT_MASKED);
-        if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && no_mask_path && bb[0] <= bb[1] && bb[2] <= bb[3] && !h->disable_fast) {
-            long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);
-            long y0 = std::max<long>(q0.s.miny, (long)bb[2] - 2), y1 = std::min<long>(q0.s.maxy, (long)bb[3] + 4);
-            if (x1 >= x0 && y1 >= y0 && (size_t)(x1 - x0 + 1) * (size_t)(y1 - y0 + 1) * 2 <= dg.npts()) {
-                b.fast = 1; b.bx0 = (int)x0; b.by0 = (int)y0; b.bnx = (int)(x1 - x0 + 1); b.bny = (int)(y1 - y0 + 1);
-                b.npack = ((int)groups[g].size() + 3) / 4;
-                need += (size_t)b.npack * b.bnx * b.bny * (6 * sizeof(float4) + 1) + 1024;
-                need += groups[g].size() * ((size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 256);  // slow bitmaps
-            }
+        // eligible for the first-method kernels unless masked=both (two interp masks chosen per point by the landmask)
+        bool simple_mask = !(q0.s.use_landmask && q0.fo.masked == WPSGPU_MASKED_BOTH);
+        if (simple_mask && !h->disable_fast) {
+            if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
+                long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);
+                long y0 = std::max<long>(q0.s.miny, (long)bb[2] - 2), y1 = std::min<long>(q0.s.maxy, (long)bb[3] + 4);
+                if (x1 >= x0 && y1 >= y0 && (size_t)(x1 - x0 + 1) * (size_t)(y1 - y0 + 1) * 2 <= dg.npts()) {
+                    b.fast = 1; b.bx0 = (int)x0; b.by0 = (int)y0; b.bnx = (int)(x1 - x0 + 1); b.bny = (int)(y1 - y0 + 1);
+                    b.npack = ((int)groups[g].size() + 3) / 4;
+                    need += (size_t)b.npack * b.bnx * b.bny * (6 * sizeof(float4) + 1) + 1024;
+                }
+            } else if (q0.fo.ops[0] == WPSGPU_FOUR_POINT) b.fast = 2;
+            else if (q0.fo.ops[0] == WPSGPU_N_NEIGHBOR) b.fast = 3;
+            if (b.fast) need += groups[g].size() * ((size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 256);  // slow bitmaps
         }
         if (host) {
             for (int m = 0; m < 3; ++m) if (q0.s.mask[m]) uniq_in[q0.s.mask[m]] = sbytes;
@@ -762,6 +877,7 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     long long fast_words = 0;
     int tile_cursor[2] = { 0, 0 };
     double cls_points[2] = { 0.0, 0.0 };
+    double fast16_points = 0.0, fast4_points = 0.0;
     int slab_cursor = 0;
     unsigned long long defer_cursor = 0;
     bool any_search = false;
@@ -798,10 +914,12 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         cls_tile0[cls].push_back(tile_cursor[cls]);
         tile_cursor[cls] += jb.tiles_x * jb.tiles_y;
         cls_points[cls] += (double)dg.npts() * groups[g].size();
+        if (box[g].fast == 1) fast16_points += (double)dg.npts() * groups[g].size();
+        if (box[g].fast >= 2) fast4_points += (double)dg.npts() * groups[g].size();
         if (cls == 1) { fast_word0.push_back((int)fast_words); fast_words += (long long)jb.ny * jb.nxw * groups[g].size(); }
         jb.f_negzero = -0.0f; jb.f_one = 1.0f;
         jb.fast = box[g].fast; jb.bx0 = box[g].bx0; jb.by0 = box[g].by0; jb.bnx = box[g].bnx; jb.bny = box[g].bny; jb.npack = box[g].npack;
-        if (jb.fast) {
+        if (jb.fast == 1) {
             size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
             jb.rec = (const float4*)h->arena.take(cells * 6 * sizeof(float4));
             jb.cf = (const unsigned char*)h->arena.take(cells);
@@ -865,12 +983,14 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     WPS_CUDA(cudaEventRecord(h->ev_t[0], h->stream));
     for (int g : cls_jobs[1]) {
         const Job& jb = jobs[g];
+        if (jb.fast != 1) continue;
         k_pack16<<<dim3((jb.bnx * jb.bny + 255) / 256, jb.npack), 256, 0, h->stream>>>(d_jobs, g, d_sp);
         h->launches++;
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
     WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
     for (int g : cls_jobs[1]) {
+        if (jobs[g].fast != 1) continue;
         FastParams fp;
         fp.jb = jobs[g];
         for (int k = 0; k < fp.jb.nslab; ++k) {
@@ -881,6 +1001,20 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         h->launches++;
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
+    WPS_CUDA(cudaEventRecord(h->ev_t[6], h->stream));
+    for (int g : cls_jobs[1]) {
+        if (jobs[g].fast < 2) continue;
+        Fast4Params fp;
+        fp.jb = jobs[g];
+        for (int k = 0; k < fp.jb.nslab; ++k) {
+            const SlabPtrs& p = sp[fp.jb.slab0 + k];
+            fp.src[k] = p.src; fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
+        }
+        if (jobs[g].fast == 2) k_metgrid_fast4<WPSGPU_FOUR_POINT><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
+        else k_metgrid_fast4<WPSGPU_N_NEIGHBOR><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
+        h->launches++;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[7], h->stream));
     if (tile_cursor[1] > 0) {
         k_metgrid_slowbits<<<(unsigned)((fast_words + 127) / 128), 128, 0, h->stream>>>(d_jobs, d_cls_jobs[1], d_fast_word0, (int)cls_jobs[1].size(), d_sp, d_def, d_cnt, fast_words);
         h->launches++;
@@ -892,13 +1026,13 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[5], h->stream));
     WPS_CUDA(cudaGetLastError());
-    h->last_pts3[0] = cls_points[1]; h->last_pts3[1] = cls_points[1]; h->last_pts3[2] = cls_points[0];
+    h->last_pts3[0] = fast16_points; h->last_pts3[1] = fast16_points; h->last_pts3[2] = cls_points[0]; h->last_pts3[3] = fast4_points;
     // the dominant kernel for the roofline line: whichever main kernel produced more outputs
     {
-        int dom = cls_points[1] >= cls_points[0] ? 1 : 2;
+        int dom = fast16_points >= cls_points[0] ? 1 : 2;
         cudaEvent_t t0 = h->ev_t[2 * dom], t1 = h->ev_t[2 * dom + 1];
         h->ev_k0 = t0; h->ev_k1 = t1;
-        h->last_points = cls_points[dom == 1 ? 1 : 0];
+        h->last_points = dom == 1 ? fast16_points : cls_points[0];
     }
     if (any_search) {
         int sblocks = h->sm_count * 8;
