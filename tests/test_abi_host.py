@@ -1,0 +1,103 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/wpsgpu.h declares, fails loudly when no
+device exists, and its host-only entry points (interp_option parsing, map_set) agree with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_every_declared_symbol():
+    from wps_b200 import capi
+    lib = capi.lib()
+    hdr = open(os.path.join(ROOT, "include", "wpsgpu.h")).read()
+    names = sorted(set(re.findall(r"\b(wpsgpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from wps_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(capi.WpsGpuError) as e:
+        capi.Handle(0)
+    assert "no CUDA device" in str(e.value) or "CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "wps_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", "").lower() or f == "__init__.py", (dirpath, f)
+
+
+STRINGS = ["sixteen_pt+four_pt+average_4pt", "four_pt+average_4pt", "nearest_neighbor", "four_pt",
+           "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search", "average_gcell(4.0)+four_pt+average_4pt",
+           "average_gcell(1.5)+sixteen_pt", "search(5)", "four_pt+search(12)+average_4pt", "average_16pt+wt_average_16pt",
+           "four_pt+x", "bogus+four_pt", "wt_average_4pt+search", "sixteen_pt+", "+four_pt"]
+
+
+@pytest.mark.parametrize("s", STRINGS)
+def test_parse_interp_option_matches_oracle(orc, s):
+    from wps_b200 import capi
+    codes, opts, has_gcell, thr = capi.parse_interp_option(s)
+    ocodes, oopts = orc.parse_interp_option(s)
+    assert codes == ocodes and opts == oopts
+    assert has_gcell == ("average_gcell" in s)
+    if has_gcell:
+        assert thr == orc.gcell_threshold(s)
+
+
+def test_parse_errors():
+    from wps_b200 import capi
+    with pytest.raises(capi.WpsGpuError):
+        capi.parse_interp_option("search(abc)")
+
+
+PROJS = [
+    ("PROJ_LC", dict(truelat1=30., truelat2=60., stdlon=-98., lat1=34.83, lon1=-81.03, knowni=50.5, knownj=50.5, dx=30000.)),
+    ("PROJ_LC", dict(truelat1=38.5, truelat2=38.5, stdlon=-97.5, lat1=38.5, lon1=-97.5, knowni=900., knownj=530., dx=3000.)),
+    ("PROJ_LC", dict(truelat1=-30., truelat2=-60., stdlon=140., lat1=-35., lon1=145., knowni=40., knownj=40., dx=12000.)),
+    ("PROJ_PS", dict(truelat1=60., stdlon=-100., lat1=70., lon1=-110., knowni=60., knownj=60., dx=25000.)),
+    ("PROJ_PS", dict(truelat1=-71., stdlon=0., lat1=-75., lon1=20., knowni=50., knownj=50., dx=30000.)),
+    ("PROJ_MERC", dict(truelat1=10., lat1=5., lon1=100., knowni=30., knownj=30., dx=27000.)),
+    ("PROJ_LATLON", dict(latinc=-0.25, loninc=0.25, knowni=1., knownj=1., lat1=90., lon1=0., nxmax=1440)),
+    ("PROJ_LATLON", dict(latinc=0.5, loninc=0.5, knowni=1., knownj=1., lat1=-90., lon1=190., nxmax=720)),
+    ("PROJ_CASSINI", dict(latinc=0.5, loninc=0.5, lat1=10., lon1=-20., lat0=60., lon0=-140., knowni=1., knownj=1., stdlon=-140., dx=55000., dy=55000.)),
+    ("PROJ_PS_WGS84", dict(truelat1=70., stdlon=-45., lat1=65., lon1=-50., knowni=100., knownj=100., dx=5000.)),
+    ("PROJ_ALBERS_NAD83", dict(truelat1=29.5, truelat2=45.5, stdlon=-96., lat1=23., lon1=-96., knowni=1., knownj=1., dx=1000.)),
+    ("PROJ_GAUSS", dict(nlat=47, lat1=88.542, lon1=0., loninc=1.875, nxmax=192)),
+]
+
+
+@pytest.mark.parametrize("name,kw", PROJS)
+def test_map_set_matches_oracle_bit_for_bit(orc, name, kw):
+    """wpsgpu_map_set runs on the host with the FP64-then-round policy: identical to the oracle in transc mode 1"""
+    from wps_b200 import capi
+    orc.set_transc_mode(1)
+    po = orc.map_set(getattr(orc, name), **kw)
+    pg = capi.map_set(getattr(capi, name), **kw)
+    for f in ("lat1", "lon1", "lat0", "lon0", "dx", "dy", "latinc", "loninc", "dlon", "stdlon", "truelat1", "truelat2", "hemi",
+              "cone", "polei", "polej", "rsw", "rebydx", "knowni", "knownj", "re_m", "rho0", "nc", "bigc"):
+        a, b = np.float32(getattr(po, f)), np.float32(getattr(pg, f))
+        assert a.tobytes() == b.tobytes(), (name, f, a, b)
+    assert (po.nxmin, po.nxmax, po.nlat) == (pg.nxmin, pg.nxmax, pg.nlat)
+    if name == "PROJ_GAUSS":
+        assert np.array_equal(np.array(po.gauss_lat[:94], np.float32), np.array(pg.gauss_lat[:94], np.float32))
+
+
+def test_map_set_rejects_what_the_reference_rejects(orc):
+    from wps_b200 import capi
+    with pytest.raises(capi.WpsGpuError):
+        capi.map_set(capi.PROJ_LC, truelat1=30., truelat2=60., stdlon=-98., lat1=34.83, lon1=-81.03, knowni=50.5, knownj=50.5)  # dx missing
+    with pytest.raises(capi.WpsGpuError):
+        capi.map_set(capi.PROJ_LC, truelat1=30., truelat2=60., stdlon=-98., lat1=94.83, lon1=-81.03, knowni=50.5, knownj=50.5, dx=3000.)
+    with pytest.raises(capi.WpsGpuError):
+        capi.map_set(capi.PROJ_ROTLL, lat1=1.0, lon1=1.0)

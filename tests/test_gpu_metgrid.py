@@ -260,3 +260,30 @@ def test_packed_many_levels(orc, handle, missing):
         slabs.append(halo(f))
     run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+average_4pt", missing=np.float32(missing), fill=0.0)
     run_case(orc, handle, xlat, xlon, slabs[:5], src, "sixteen_pt+four_pt+wt_average_4pt+search", missing=np.float32(missing), fill=0.0)
+
+
+def test_against_committed_golden_vectors(handle):
+    """GPU vs tests/golden/metgrid_small.npz (committed fixtures generated by tests/golden/make_golden.py)."""
+    import os
+    from tests.golden import make_golden
+    from wps_b200 import capi
+    g = np.load(os.path.join(os.path.dirname(make_golden.__file__), "metgrid_small.npz"))
+    xlat, xlon, ls = g["xlat"], g["xlon"], g["landsea"]
+    ny, nx = xlat.shape
+    src = capi.push_source_projection(capi.PROJ_LATLON, dlat=-1.0, dlon=1.0, known_x=1.0, known_y=1.0, known_lat=90.0,
+                                      known_lon=0.0, earth_radius=6371229.0)
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    outs = []
+    for name, chain, msg, fill, mval in make_golden.CASES:
+        mv = (mval, 1e20, 1e20) if mval is not None else (1e20, 1e20, 1e20)
+        fo = capi.field_opts(chain, np.float32(msg), np.float32(fill), -2.0, mv)
+        r = np.zeros((ny, nx), np.float32)
+        npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+        slab = np.ascontiguousarray(g[name + "_slab"])
+        handle.metgrid_enqueue_slab(src, fo, slab, -2, 1, 3, 0, capi.M, r, npw, masks=(ls if mval is not None else None, None, None))
+        outs.append((name, r, npw, slab))
+    handle.metgrid_flush()
+    for name, r, npw, _ in outs:
+        assert (npw == g[name + "_new_pts"]).all(), name
+        assert_bitexact(r, g[name + "_r"], "golden " + name)
