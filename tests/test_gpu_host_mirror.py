@@ -1,0 +1,88 @@
+"""GPU: the host-side mirror of metgrid's record loop (wps_b200/metgrid.py) on a synthetic GFS-shaped FILE written in
+the intermediate format, against a per-slab oracle loop that follows process_intermediate_fields by hand."""
+import numpy as np
+import pytest
+
+from tests.test_host_logic import TBL
+from tests.util import assert_bitexact, bits_to_bool, conus_like, landsea, synth_field
+
+pytestmark = pytest.mark.gpu
+
+
+def make_file(tmp_path, name, fields, seed0, nx=360, ny=181):
+    from wps_b200.intermediate import MetData, read_records, write_records
+    ls = landsea(nx, ny)
+    recs = []
+    for k, (f, lvl, kind) in enumerate(fields):
+        if kind == "landsea":
+            slab = ls.copy()
+        elif kind == "land":
+            slab = synth_field(nx, ny, seed0 + k)
+            slab[ls == 0] = -1e30
+        else:
+            slab = synth_field(nx, ny, seed0 + k, kind=kind)
+        recs.append(MetData(f, lvl, slab, startlat=90.0, startlon=0.0, deltalat=-1.0, deltalon=1.0))
+    p = str(tmp_path / name)
+    write_records(p, recs)
+    return read_records(p)
+
+
+def test_record_loop_matches_oracle(orc, handle, tmp_path):
+    from wps_b200 import capi
+    from wps_b200.interp_option import find_entry, read_interp_table
+    from wps_b200.metgrid import MetgridDomain, halo_slab
+    orc.set_transc_mode(1)
+    nx, ny = 64, 52
+    odom, gdom = conus_like(nx, ny, 40000.0, 30.0, 60.0, -98.0, 36.0, -92.0)
+    g = {1: orc.get_lat_lon_fields(odom, 1, 1, nx, ny, orc.M), 2: orc.get_lat_lon_fields(odom, 1, 1, nx + 1, ny, orc.U),
+         3: orc.get_lat_lon_fields(odom, 1, 1, nx, ny + 1, orc.V)}
+    rng = np.random.default_rng(1)
+    landmask = (rng.random((ny, nx)) < 0.6).astype(np.float32)
+    table = read_interp_table(TBL)
+    fields = [("LANDSEA", 200100.0, "landsea"), ("T", 85000.0, "smooth"), ("T", 50000.0, "smooth"), ("UU", 85000.0, "wind"),
+              ("VV", 85000.0, "wind"), ("ST000010", 200100.0, "land"), ("SKINTEMP", 200100.0, "smooth"), ("PSFC", 200100.0, "smooth")]
+    recs = make_file(tmp_path, "FILE:2026-10-19_00", fields, 10)
+    dom = MetgridDomain(handle, g[1][0], g[1][1], g[2][0], g[2][1], g[3][0], g[3][1], landmask)
+    storage = dom.process_intermediate_fields(recs, table, "FILE")
+    assert ("TT", 85000) in storage and ("T", 85000) not in storage          # output_name rename
+    # ---- the same loop by hand through the oracle
+    src = orc.push_source_projection(orc.PROJ_LATLON, dlat=-1.0, dlon=1.0, known_x=1.0, known_y=1.0, known_lat=90.0, known_lon=0.0,
+                                     earth_radius=np.float32(6371.229) * np.float32(1000.0))
+    masks = {"LANDSEA.mask": halo_slab(recs[0])[0]}
+    for fg in recs:
+        idx = find_entry(table, fg.field, "FILE")
+        name = fg.field
+        if table[idx].output_name != " ":
+            name = table[idx].output_name
+            idx = find_entry(table, name, "FILE")
+        e = table[idx]
+        stag = e.output_stagger if e.output_stagger in (2, 3) else 1
+        fo = orc.field_opts(e.interp_method, np.float32(e.missing_value), np.float32(e.fill_missing), e.masked,
+                            (e.interp_mask_val, e.interp_land_mask_val, e.interp_water_mask_val),
+                            e.interp_mask_relational + e.interp_land_mask_relational + e.interp_water_mask_relational)
+        m = [masks.get(nm + ".mask") if nm != " " else None for nm in (e.interp_mask, e.interp_land_mask, e.interp_water_mask)]
+        slab, minx, bdr = halo_slab(fg)
+        r_ref, np_ref = orc.interp_met_field(src, fo, stag, g[stag][0], g[stag][1], 1, 1, (1, nx, 1, ny), slab, minx, 1, bdr,
+                                             mask=m[0], land_mask=m[1], water_mask=m[2], landmask=landmask if stag == 1 else None)
+        got = storage[(name, int(round(fg.xlvl)))]
+        assert (got.modified_mask == np_ref).all(), name
+        assert (got.valid_mask == np_ref).all(), name
+        assert_bitexact(got.r_arr, r_ref, "record loop " + name)
+    # ---- a second, higher-priority source that only partly covers the field: valid_mask carry-over (:1225-1237, :1365)
+    recs2 = make_file(tmp_path, "SST:2026-10-19_00", [("T", 85000.0, "smooth")], 99)
+    recs2[0].slab[:, :180] = 1e20
+    before = storage[("TT", 85000)].r_arr.copy()
+    dom.process_intermediate_fields(recs2, table, "SST", storage)
+    fo = orc.field_opts("sixteen_pt+four_pt+average_4pt", np.float32(1e20), np.float32(0.0))
+    slab, minx, bdr = halo_slab(recs2[0])
+    valid0 = storage[("TT", 85000)].valid_mask    # already merged; reconstruct the pre-merge valid mask = all set for TT
+    r_ref, np_ref = orc.interp_met_field(src, fo, 1, g[1][0], g[1][1], 1, 1, (1, nx, 1, ny), slab, minx, 1, bdr, landmask=landmask,
+                                         r_arr=before.copy(), valid_mask=np.full_like(valid0, -1))
+    assert_bitexact(storage[("TT", 85000)].r_arr, r_ref, "second source")
+    assert (storage[("TT", 85000)].modified_mask == np_ref).all()
+    # ---- met_to_map on the interpolated winds (process_domain_module.F:802-834)
+    u0, v0 = storage[("UU", 85000)].r_arr.copy(), storage[("VV", 85000)].r_arr.copy()
+    dom.rotate_winds(storage, gdom, -1)
+    uo, vo = orc.metmap_xform(odom, u0, storage[("UU", 85000)].modified_mask, v0, storage[("VV", 85000)].modified_mask, g[2][1], g[3][1], -1)
+    from tests.util import ulp_diff
+    assert ulp_diff(storage[("UU", 85000)].r_arr, uo).max() <= 1 and ulp_diff(storage[("VV", 85000)].r_arr, vo).max() <= 1

@@ -1,0 +1,132 @@
+"""CPU: host-side mirrors (METGRID.TBL parser, intermediate format, sharding incl. a world_size-2 gloo run)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TBL = """
+# sample in METGRID.TBL syntax
+========================================
+name=TT
+        interp_option=sixteen_pt+four_pt+average_4pt
+        fill_missing=0.
+========================================
+name=UU ; interp_option=sixteen_pt+four_pt+average_4pt ; is_u_field=yes ; output_stagger=U ; fill_missing=0.
+========================================
+name=ST000010
+        interp_option=sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search
+        masked=water
+        interp_mask=LANDSEA(0)
+        missing_value=-1.E30   # comment
+        fill_missing=285.
+========================================
+name=SKINTEMP ; masked=both ; interp_land_mask = LANDSEA(1) ; interp_water_mask = LANDSEA(0)
+========================================
+name=T ; output_name=TT
+========================================
+name=SST ; interp_mask=LANDSEA(>0.5) ; from_input=SSTFILE
+========================================
+"""
+
+
+def test_read_interp_table():
+    from wps_b200 import capi
+    from wps_b200.interp_option import find_entry, read_interp_table
+    t = read_interp_table(TBL)
+    assert len(t) == 7 and t[-1].fieldname == " " and t[-1].interp_method == "nearest_neighbor"
+    tt = t[find_entry(t, "TT", "FILE")]
+    assert tt.interp_method == "sixteen_pt+four_pt+average_4pt" and tt.fill_missing == 0.0 and tt.missing_value == np.float32(1e20) or tt.missing_value == 1e20
+    uu = t[find_entry(t, "UU", "FILE")]
+    assert uu.output_stagger == capi.U and uu.is_u_field
+    st = t[find_entry(t, "ST000010", "FILE")]
+    assert st.masked == capi.MASKED_WATER and st.interp_mask == "LANDSEA" and st.interp_mask_val == 0.0
+    assert st.missing_value == -1e30 and st.fill_missing == 285.0 and st.interp_mask_relational == " "
+    sk = t[find_entry(t, "SKINTEMP", "FILE")]
+    assert sk.masked == capi.MASKED_BOTH and sk.interp_land_mask_val == 1.0 and sk.interp_water_mask_val == 0.0
+    assert t[find_entry(t, "T", "FILE")].output_name == "TT"
+    # from_input: the SST entry only applies to sources whose name contains SSTFILE; otherwise the default entry
+    assert find_entry(t, "SST", "FILE") == len(t) - 1
+    sst = t[find_entry(t, "SST", "./SSTFILE")]
+    assert sst.interp_mask_relational == ">" and sst.interp_mask_val == 0.5
+    assert find_entry(t, "NOPE", "FILE") == len(t) - 1
+    fo = st.field_opts()
+    assert list(fo.ops[:6]) == [1, 2, 6, 7, 8, 0] and fo.opts[4] == 1200
+
+
+def test_reference_table_if_present():
+    from wps_b200.interp_option import find_entry, read_interp_table
+    p = "/root/reference/metgrid/METGRID.TBL.ARW"
+    if not os.path.exists(p):
+        pytest.skip("reference tree not present")
+    t = read_interp_table(open(p).read())
+    assert t[find_entry(t, "TT", "FILE")].interp_method == "sixteen_pt+four_pt+average_4pt"
+    assert t[find_entry(t, "SM000010", "FILE")].interp_mask == "LANDSEA"
+    assert t[find_entry(t, "SEAICE", "FILE")].masked == 1.0
+
+
+def test_intermediate_roundtrip(tmp_path):
+    from wps_b200.intermediate import MetData, read_records, write_records
+    rng = np.random.default_rng(0)
+    recs = [MetData("TT", 85000.0, rng.uniform(200, 300, (19, 36)).astype(np.float32), startlat=90.0, startlon=0.0, deltalat=-10.0, deltalon=10.0),
+            MetData("HGT", 50000.0, rng.uniform(0, 6000, (19, 36)).astype(np.float32), startlat=90.0, startlon=0.0, deltalat=-10.0, deltalon=10.0),
+            MetData("UU", 200100.0, rng.uniform(-9, 9, (11, 13)).astype(np.float32), iproj=3, startlat=20.0, startlon=-110.0, dx=40.0, dy=40.0,
+                    xlonc=-98.0, truelat1=30.0, truelat2=60.0, is_wind_grid_rel=True)]
+    p = str(tmp_path / "FILE:2026-10-19_00")
+    write_records(p, recs)
+    raw = open(p, "rb").read()
+    assert raw[:12] == b"\x00\x00\x00\x04\x00\x00\x00\x05\x00\x00\x00\x04"      # big-endian record marker + version 5
+    back = read_records(p)
+    assert [r.field for r in back] == ["TT", "GHT", "UU"]                       # HGT renamed on read
+    for a, b in zip(recs, back):
+        assert np.array_equal(a.slab, b.slab) and a.xlvl == b.xlvl and a.iproj == b.iproj
+    assert back[2].is_wind_grid_rel and back[2].truelat2 == 60.0 and abs(back[2].earth_radius - 6371.229) < 1e-3
+
+
+def test_shard_slabs_keeps_wind_pairs_together():
+    from wps_b200.shard import shard_slabs, shard_times
+    keys = [(f, l) for f in ("TT", "RH", "UU", "VV", "GHT") for l in range(34)] + [("PSFC", 200100), ("SKINTEMP", 200100)]
+    for world in (1, 2, 4, 8):
+        sh = shard_slabs(keys, world)
+        allidx = sorted(i for v in sh.values() for i in v)
+        assert allidx == list(range(len(keys)))
+        where = {keys[i]: r for r, v in sh.items() for i in v}
+        for l in range(34):
+            assert where[("UU", l)] == where[("VV", l)]
+        sizes = [len(v) for v in sh.values()]
+        assert max(sizes) - min(sizes) <= 2
+    assert shard_times(24, 1, 8) == [1, 9, 17]
+
+
+def test_sharded_run_gloo_world2(tmp_path):
+    """N>1 host path on CPU: two gloo ranks shard the slab list, each computes a checksum of 'its' work and the
+    rank-0 gather reproduces the single-process result (no data-path collective is needed, only the final gather)."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np, torch, torch.distributed as dist
+        from wps_b200.shard import shard_slabs
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        keys = [(f, l) for f in ("TT", "UU", "VV") for l in range(10)]
+        mine = shard_slabs(keys, world)[rank]
+        vals = torch.zeros(len(keys), dtype=torch.float64)
+        for i in mine:
+            vals[i] = (i + 1) * 1.5      # stands for the slab's output checksum
+        dist.all_reduce(vals)
+        t = torch.tensor([float(len(mine))], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert torch.equal(vals, torch.arange(1, len(keys) + 1, dtype=torch.float64) * 1.5)
+            print("OK", int(t.item()))
+        dist.destroy_process_group()
+    """ % ROOT))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "OK 15" in out.stdout

@@ -1,0 +1,163 @@
+"""Host-side mirror of metgrid's per-file record loop (metgrid/src/process_domain_module.F:999-1449), driving the
+batched CUDA path: every (field, level) record of a FILE becomes one queued slab, and ONE flush replaces the
+per-slab interp_met_field calls.  Storage semantics (valid_mask / modified_mask carry-over between sources of
+different priority, storage_module.F) are kept so that multiple fg_name prefixes behave as in the reference."""
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import capi
+from .intermediate import MetData
+from .interp_option import TableEntry, find_entry
+
+BDR_WIDTH = 3   # process_domain_module.F:1027
+# iproj codes of the intermediate format -> PROJ_* (read_met_module.F:286-386)
+_IPROJ = {0: capi.PROJ_LATLON, 1: capi.PROJ_MERC, 3: capi.PROJ_LC, 4: capi.PROJ_GAUSS, 5: capi.PROJ_PS}
+GRID_OF_STAGGER = {capi.M: 0, capi.U: 1, capi.V: 2}
+
+
+@dataclass
+class FgInput:
+    """fg_input (datatype_module.F:12-64), the part the interpolation path touches"""
+    field: str
+    level: int
+    stagger: int
+    r_arr: np.ndarray
+    valid_mask: np.ndarray
+    modified_mask: Optional[np.ndarray]
+    is_wind_grid_rel: bool = False
+    mask_field: bool = False
+
+
+def source_projection(fg: MetData):
+    """push_source_projection call of process_domain_module.F:1144-1151 for one record."""
+    code = _IPROJ[fg.iproj]
+    if fg.startloc.strip() == "CENTER":
+        starti, startj = (fg.nx + 1) / 2.0, (fg.ny + 1) / 2.0
+    else:
+        starti, startj = 1.0, 1.0
+    return capi.push_source_projection(code, stand_lon=fg.xlonc, truelat1=fg.truelat1, truelat2=fg.truelat2,
+                                       dxkm=fg.dx * 1000.0, dykm=fg.dy * 1000.0,
+                                       dlat=fg.nlats if code == capi.PROJ_GAUSS else fg.deltalat, dlon=fg.deltalon,
+                                       known_x=starti, known_y=startj, known_lat=fg.startlat, known_lon=fg.startlon,
+                                       earth_radius=fg.earth_radius * 1000.0)
+
+
+def is_global(fg: MetData) -> bool:
+    """process_domain_module.F:1121-1122"""
+    return (fg.iproj == 0 and abs(np.float32(fg.nx) * np.float32(fg.deltalon) - np.float32(360.0)) < 0.0001) or fg.iproj == 4
+
+
+def halo_slab(fg: MetData):
+    """:1121-1140 -> (slab incl. halo, minx, bdr)"""
+    s = np.ascontiguousarray(fg.slab, np.float32)
+    if is_global(fg):
+        b = BDR_WIDTH
+        return np.ascontiguousarray(np.concatenate([s[:, fg.nx - b:], s, s[:, :b]], axis=1)), 1 - b, b
+    return s, 1, 0
+
+
+class MetgridDomain:
+    """One model domain: its staggered lat/lon arrays (from geo_em), LANDMASK and the device handle."""
+
+    def __init__(self, handle: capi.Handle, xlat, xlon, xlat_u, xlon_u, xlat_v, xlon_v, landmask, domain=None,
+                 mem_start=(1, 1), process_bdy_width=0, dom_dx=None, dom_dy=None):
+        self.h = handle
+        self.grids = {capi.M: (xlat, xlon), capi.U: (xlat_u, xlon_u), capi.V: (xlat_v, xlon_v)}
+        self.landmask = landmask
+        self.sm = mem_start
+        ny, nx = xlat.shape
+        self.domain = domain or (mem_start[0], mem_start[0] + nx - 1, mem_start[1], mem_start[1] + ny - 1)
+        self.process_bdy_width = process_bdy_width
+        self.dom_dx, self.dom_dy = dom_dx, dom_dy
+        for st, (la, lo) in self.grids.items():
+            handle.metgrid_set_grid(GRID_OF_STAGGER[st], la, lo, mem_start[0], mem_start[1])
+        if landmask is not None:
+            handle.metgrid_set_landmask(0, landmask)
+        handle.metgrid_set_domain(*self.domain)
+
+    def process_intermediate_fields(self, records: List[MetData], table: List[TableEntry], input_name: str = "FILE",
+                                    storage: Optional[Dict[Tuple[str, int], FgInput]] = None):
+        """The record loop of process_intermediate_fields; returns the storage dict keyed by (field, nint(xlvl))."""
+        storage = {} if storage is None else storage
+        # ---- get_interp_masks (:2061-2197): stash "<NAME>.mask" slabs of this source first
+        masks: Dict[str, np.ndarray] = {}
+        mask_names = {e.interp_mask for e in table[:-1] if e.interp_mask != " "}
+        for fg in records:
+            name = self._renamed(fg.field, table, input_name)
+            if name in mask_names and name + ".mask" not in masks:
+                masks[name + ".mask"] = halo_slab(fg)[0]
+        queued = []
+        keep = []   # host buffers must stay alive until the flush
+        for fg in records:
+            idx = find_entry(table, fg.field, input_name)
+            name = fg.field
+            if table[idx].output_name != " ":
+                name = table[idx].output_name[:9]
+                idx = find_entry(table, name, input_name)
+            e = table[idx]
+            slab, minx, bdr = halo_slab(fg)
+            proj = source_projection(fg)
+            _, _, has_gcell, thr = capi.parse_interp_option(e.interp_method)
+            if has_gcell and self._do_gcell(fg, thr):
+                raise NotImplementedError("average_gcell for metgrid sources finer than the domain "
+                                          "(process_domain_module.F:2331-2478) is not ported yet")
+            stag = e.output_stagger if e.output_stagger in (capi.U, capi.V) else capi.M
+            xlat, _ = self.grids[stag]
+            gy, gx = xlat.shape
+            key = (name, int(np.rint(fg.xlvl)))
+            if key in storage:                       # storage_query_field found it (:1225-1233): carry data + valid mask over
+                fld = storage[key]
+                fld.modified_mask = None
+            else:
+                fld = FgInput(name, key[1], stag, np.zeros((gy, gx), np.float32), np.zeros((gy, capi.nwords(gx)), np.int32), None,
+                              fg.is_wind_grid_rel, not e.output_this_field)
+                fld._fresh = True
+            fld.modified_mask = np.zeros((gy, capi.nwords(gx)), np.int32)
+            m = [masks.get(nm + ".mask") if nm != " " else None for nm in (e.interp_mask, e.interp_land_mask, e.interp_water_mask)]
+            fresh = getattr(fld, "_fresh", False)
+            self.h.metgrid_enqueue_slab(proj, e.field_opts(), slab, minx, 1, bdr, GRID_OF_STAGGER[stag], stag, fld.r_arr,
+                                        fld.modified_mask, valid_mask=None if fresh else fld.valid_mask, masks=tuple(m),
+                                        use_landmask=(stag == capi.M and self.landmask is not None),
+                                        process_bdy_width=self.process_bdy_width)
+            fld._fresh = False
+            keep.append((slab, m))
+            queued.append((key, fld))
+            storage[key] = fld
+        self.h.metgrid_flush()
+        for key, fld in queued:                      # bitarray_merge(valid_mask, modified_mask) (:1365)
+            fld.valid_mask |= fld.modified_mask
+        return storage
+
+    def _renamed(self, name, table, input_name):
+        idx = find_entry(table, name, input_name)
+        if table[idx].output_name != " ":
+            return table[idx].output_name[:9]
+        return name
+
+    def _do_gcell(self, fg, threshold):
+        """:1198-1220 (C grid)"""
+        if self.dom_dx is None:
+            return False
+        if fg.dx == 0.0 and fg.dy == 0.0 and fg.deltalat != 0.0 and fg.deltalon != 0.0:
+            dx, dy = abs(fg.deltalon), abs(fg.deltalat)
+        else:
+            dx, dy = fg.dx * 1000.0 / 111000.0, fg.dy * 1000.0 / 111000.0
+        return threshold * max(dx, dy) * 111.0 <= max(self.dom_dx, self.dom_dy) / 1000.0
+
+    def rotate_winds(self, storage, proj, idir, u_name="UU", v_name="VV", only_modified=True):
+        """met_to_map (idir=-1, proj = domain projection, process_domain_module.F:802-834) or map_to_met (idir=+1,
+        proj = source projection, :1392-1437) over every level that holds both components."""
+        levels = sorted(set(l for (n, l) in storage if n == u_name) & set(l for (n, l) in storage if n == v_name))
+        if not levels:
+            return
+        u = np.stack([storage[(u_name, l)].r_arr for l in levels])
+        v = np.stack([storage[(v_name, l)].r_arr for l in levels])
+        pick = (lambda f: f.modified_mask) if only_modified else (lambda f: f.valid_mask)
+        um = np.stack([pick(storage[(u_name, l)]) for l in levels])
+        vm = np.stack([pick(storage[(v_name, l)]) for l in levels])
+        self.h.rotate_winds(idir, proj, u, um, v, vm, self.grids[capi.U][1], self.grids[capi.V][1], us=self.sm, vs=self.sm)
+        for k, l in enumerate(levels):
+            storage[(u_name, l)].r_arr[:] = u[k]
+            storage[(v_name, l)].r_arr[:] = v[k]
