@@ -179,21 +179,25 @@ def build_workload(h, torch, dev, config, device_mode=True):
     return dict(dom=dom, src=src, grids=grids, landmask=landmask, plan=plan, nx=nx, ny=ny)
 
 
-def enqueue_all(h, w, host=None):
-    """The process_intermediate_fields record loop: one enqueue per (field, level) slab, then ONE flush."""
-    pts = 0
+def slab_descs(capi, w, host=None):
+    """wpsgpu_slab descriptors of the whole step, built once (the buffers are re-used by every step)."""
+    out = []
     for pi, p in enumerate(w["plan"]):
-        n = p["slabs"].shape[0]
+        bufs = p if host is None else host[pi]
+        n = bufs["slabs"].shape[0]
+        arr = (capi.Slab * n)()
         for l in range(n):
-            if host is None:
-                slab, r, npw, masks = p["slabs"][l], p["r"][l], p["npw"][l], p["masks"]
-            else:
-                slab, r, npw, masks = host[pi]["slabs"][l], host[pi]["r"][l], host[pi]["npw"][l], host[pi]["masks"]
-            h.metgrid_enqueue_slab(w["src"], p["fo"], slab, -2, 1, 3, p["gid"], p["e"]["stagger"], r, npw, masks=masks,
-                                   use_landmask=p["use_landmask"])
-            pts += r.shape[0] * r.shape[1]
+            capi.Handle.slab_desc(bufs["slabs"][l], -2, 1, 3, p["gid"], p["e"]["stagger"], bufs["r"][l], bufs["npw"][l],
+                                  masks=bufs["masks"], use_landmask=p["use_landmask"], out=arr[l])
+        out.append((p["fo"], arr, n))
+    return out
+
+
+def enqueue_all(h, w, descs):
+    """The process_intermediate_fields record loop: one enqueue call per field (its levels), then ONE flush."""
+    for fo, arr, n in descs:
+        h.metgrid_enqueue_slabs(w["src"], fo, arr, n)
     h.metgrid_flush()
-    return pts
 
 
 def run_b200(args, rank, world, local_rank):
@@ -220,8 +224,10 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    descs = slab_descs(capi, w)
+    pts = sum(p["r"].shape[0] * p["r"].shape[1] * p["r"].shape[2] for p in w["plan"])
     for _ in range(max(args.warmup, 3)):
-        pts = enqueue_all(h, w)
+        enqueue_all(h, w, descs)
     h.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -231,9 +237,11 @@ def run_b200(args, rank, world, local_rank):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kms = []
     ev0.record(stream)
+    th0 = time.perf_counter()
     for _ in range(args.steps):
-        enqueue_all(h, w)
+        enqueue_all(h, w, descs)
         kms.append(None)
+    host_issue_ms = (time.perf_counter() - th0) * 1e3 / args.steps   # host time to queue one step (no sync)
     ev1.record(stream)
     h.synchronize()
     barrier()
@@ -242,7 +250,7 @@ def run_b200(args, rank, world, local_rank):
     # dominant-kernel time: re-run K steps reading the library's own CUDA events around k_metgrid_interp
     kms = []
     for _ in range(args.steps):
-        enqueue_all(h, w)
+        enqueue_all(h, w, descs)
         ms, kp = h.metgrid_last_kernel()
         kms.append(ms)
         t3, p3 = h.metgrid_last_timings()
@@ -276,11 +284,12 @@ def run_b200(args, rank, world, local_rank):
                     seen.add("mask")
             d2h += hr.numel() * 4 + hn.numel() * 4
         e2e_steps = max(1, min(args.steps, 3))
-        enqueue_all(hh, w, host)  # warm-up (arena allocation, coordinate cache)
+        hdescs = slab_descs(capi, w, host)
+        enqueue_all(hh, w, hdescs)  # warm-up (arena allocation, coordinate cache)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            enqueue_all(hh, w, host)
+            enqueue_all(hh, w, hdescs)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -307,11 +316,11 @@ def run_b200(args, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "k_metgrid_fast16" if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
                              "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
-                             "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2]},
+                             "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5]},
                              "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},
-                "gpu_launches": int(launches), "clocks": sampler.result()}
+                "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": sampler.result()}
         if world == 1 and not args.no_cpu:
             pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 3)
             line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}

@@ -143,14 +143,19 @@ typedef struct wpsgpu_slab {
 /* Queue one interp_met_field call (non-average_gcell branch, :2483-2581). */
 int wpsgpu_metgrid_enqueue_slab(wpsgpu_handle_t h, const wpsgpu_proj *src_proj, const wpsgpu_field_opts *fo,
                                 const wpsgpu_slab *slab);
+/* Queue n calls that share projection and options -- the levels of one field (the `do k` record loop around
+ * :1346-1360 visits them one after another); equivalent to n wpsgpu_metgrid_enqueue_slab calls in array order. */
+int wpsgpu_metgrid_enqueue_slabs(wpsgpu_handle_t h, const wpsgpu_proj *src_proj, const wpsgpu_field_opts *fo,
+                                 const wpsgpu_slab *slabs, int32_t n);
 /* Execute everything queued as ONE batched launch over field x level (x time) and fill r_arr / new_pts. */
 int wpsgpu_metgrid_flush(wpsgpu_handle_t h);
 /* Device time (CUDA events on the handle's stream) of the dominant kernel of the last flush and the number of
  * (slab x destination point) outputs it produced -- for roofline reporting only. */
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);
-/* Same, broken down (arrays of 4): [0] packing pre-pass, [1] packed sixteen_pt kernel, [2] generic kernel,
- * [3] four_pt / nearest_neighbor first-method kernels. */
-int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms4, double *points4);
+/* Same, broken down (arrays of 6): [0] packing pre-pass, [1] packed sixteen_pt kernel, [2] generic kernel,
+ * [3] four_pt / nearest_neighbor first-method kernels, [4] slow-bitmap pass (points the first-method kernels handed
+ * back to the full fallback chain), [5] deferred search passes. */
+int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms6, double *points6);
 /* Testing aid: disable!=0 routes every job through the generic kernel (used to test both kernels against the oracle). */
 int wpsgpu_debug_disable_fast(wpsgpu_handle_t h, int disable);
 /* The average_gcell branch (:2331-2478) with metgrid's accum_continuous (:3347-3717); dom_proj is the

@@ -104,6 +104,8 @@ def test_landmask_masked(orc, handle, masked):
     lm = (rng.random(xlat.shape) < 0.6).astype(np.float32)
     slabs = [halo(synth_field(360, 181, 30, missing=np.float32(-1e30), frac_missing=0.1))]
     if masked == -1.0:  # SKINTEMP-style: interp_land_mask / interp_water_mask
+        # (a LANDMASK value other than 0/1 would expose the reference's stale `temp` variable at :2497-2526 -- undefined
+        # behaviour the device path does not reproduce, DESIGN.md "known divergences")
         run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search",
                  missing=np.float32(-1e30), fill=0.0, masked=masked, mask_val=(1e20, 1.0, 0.0), mask_rel="   ",
                  masks=(None, ls, ls), landmask=lm)
@@ -287,3 +289,40 @@ def test_against_committed_golden_vectors(handle):
     for name, r, npw, _ in outs:
         assert (npw == g[name + "_new_pts"]).all(), name
         assert_bitexact(r, g[name + "_r"], "golden " + name)
+
+
+def test_enqueue_slabs_batched_entry(orc, handle):
+    """wpsgpu_metgrid_enqueue_slabs (levels of one field in one call) == the same slabs queued one by one, in host-pointer
+    mode through the copy/compute pipeline (several job groups), and a bad descriptor queues nothing."""
+    from wps_b200 import capi
+    xlat, xlon = make_domain(orc, handle, nx=90, ny=60, dx=20000.0)
+    ny, nx = xlat.shape
+    osrc, gsrc = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    nlev = 37   # more than two host-mode job groups of 16
+    slabs = [halo(synth_field(360, 181, 800 + s, kind="wind" if s % 2 else "smooth", zeros=0.003)) for s in range(nlev)]
+    chain = "sixteen_pt+four_pt+average_4pt"
+    fo_o, fo_g = orc.field_opts(chain, 1e20, 0.0, -2.0), capi.field_opts(chain, 1e20, 0.0, -2.0)
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    r = np.zeros((nlev, ny, nx), np.float32)
+    npw = np.zeros((nlev, ny, capi.nwords(nx)), np.int32)
+    descs = (capi.Slab * nlev)()
+    for l in range(nlev):
+        capi.Handle.slab_desc(slabs[l], -2, 1, 3, 0, capi.M, r[l], npw[l], out=descs[l])
+    handle.metgrid_enqueue_slabs(gsrc, fo_g, descs)
+    handle.metgrid_flush()
+    orc.set_transc_mode(1)
+    for l in range(0, nlev, 6):
+        r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), slabs[l], -2, 1, 3)
+        assert (npw[l] == np_ref).all()
+        assert_bitexact(r[l], r_ref, "level %d" % l)
+    # all-or-nothing: a descriptor with a NULL output pointer rejects the whole call and leaves the queue empty
+    bad = (capi.Slab * 2)()
+    capi.Handle.slab_desc(slabs[0], -2, 1, 3, 0, capi.M, r[0], npw[0], out=bad[0])
+    capi.Handle.slab_desc(slabs[1], -2, 1, 3, 0, capi.M, r[1], npw[1], out=bad[1])
+    bad[1].r_arr = None
+    r[0].fill(-7.0)
+    with pytest.raises(capi.WpsGpuError):
+        handle.metgrid_enqueue_slabs(gsrc, fo_g, bad)
+    handle.metgrid_flush()
+    assert (r[0] == -7.0).all()

@@ -243,6 +243,30 @@ class Handle:
     def metgrid_set_domain(self, sd1, ed1, sd2, ed2):
         check(lib().wpsgpu_metgrid_set_domain(self._h, int(sd1), int(ed1), int(sd2), int(ed2)))
 
+    @staticmethod
+    def slab_desc(slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts, valid_mask=None,
+                  masks=(None, None, None), use_landmask=False, process_bdy_width=0, out=None):
+        """Fill a wpsgpu_slab descriptor (a caller that re-uses its buffers can build these once)."""
+        sny, snx = slab.shape
+        s = Slab() if out is None else out
+        s.slab = ptr(slab)
+        s.minx, s.maxx, s.miny, s.maxy, s.bdr = int(minx), int(minx + snx - 1), int(miny), int(miny + sny - 1), int(bdr)
+        for i in range(3):
+            s.mask[i] = ptr(masks[i])
+        s.grid_id = int(grid_id)
+        s.field_stagger = int(field_stagger)
+        s.use_landmask = int(bool(use_landmask))
+        s.process_bdy_width = int(process_bdy_width)
+        s.r_arr = ptr(r_arr)
+        s.valid_mask = ptr(valid_mask)
+        s.new_pts = ptr(new_pts)
+        return s
+
+    def metgrid_enqueue_slabs(self, proj, fo, descs, n=None):
+        """descs: a ctypes array of Slab descriptors (levels of one field); one C call queues them all."""
+        n = len(descs) if n is None else int(n)
+        check(lib().wpsgpu_metgrid_enqueue_slabs(self._h, C.byref(proj), C.byref(fo), descs, n))
+
     def metgrid_enqueue_slab(self, proj, fo, slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts,
                              valid_mask=None, masks=(None, None, None), use_landmask=False, process_bdy_width=0):
         sny, snx = slab.shape
@@ -270,8 +294,8 @@ class Handle:
         return ms.value, pts.value
 
     def metgrid_last_timings(self):
-        ms = (C.c_float * 4)()
-        pts = (C.c_double * 4)()
+        ms = (C.c_float * 6)()
+        pts = (C.c_double * 6)()
         check(lib().wpsgpu_metgrid_last_timings(self._h, ms, pts))
         return list(ms), list(pts)
 

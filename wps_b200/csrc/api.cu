@@ -354,7 +354,7 @@ int wpsgpu_create(int device_id, wpsgpu_handle_t* out)
     h->sm_count = prop.multiProcessorCount;
     WPS_CUDA(cudaMalloc((void**)&h->d_counters, 64 * sizeof(int)));
     WPS_CUDA(cudaMemsetAsync(h->d_counters, 0, 64 * sizeof(int), h->stream));
-    for (int k = 0; k < 8; ++k) WPS_CUDA(cudaEventCreate(&h->ev_t[k]));
+    for (int k = 0; k < 12; ++k) WPS_CUDA(cudaEventCreate(&h->ev_t[k]));
     h->ev_k0 = h->ev_t[4]; h->ev_k1 = h->ev_t[5];
     for (int k = 0; k < 8; ++k) WPS_CUDA(cudaEventRecord(h->ev_t[k], h->stream));
     *out = h;
@@ -375,7 +375,11 @@ int wpsgpu_destroy(wpsgpu_handle_t h)
     h->arena.release();
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_search_scratch) cudaFree(h->d_search_scratch);
-    for (int k = 0; k < 8; ++k) if (h->ev_t[k]) cudaEventDestroy(h->ev_t[k]);
+    for (int k = 0; k < 12; ++k) if (h->ev_t[k]) cudaEventDestroy(h->ev_t[k]);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;

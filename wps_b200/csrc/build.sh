@@ -14,5 +14,5 @@ for f in api metgrid geogrid misc; do
   fi
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o ../libwpsgpu.so build/api.o build/metgrid.o build/geogrid.o build/misc.o -lcudart
+$NVCC -shared -gencode arch=compute_100a,code=sm_100a -o ../libwpsgpu.so build/api.o build/metgrid.o build/geogrid.o build/misc.o -lcudart
 echo "built $(cd .. && pwd)/libwpsgpu.so"

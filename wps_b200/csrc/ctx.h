@@ -100,9 +100,11 @@ struct wpsgpu_ctx {
     // CUDA events bracketing the dominant kernel of the last metgrid flush (roofline measurement)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // aliases into ev_t[] of the dominant kernel
     cudaEvent_t ev_dummy0 = nullptr, ev_dummy1 = nullptr;
-    cudaEvent_t ev_t[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };  // pack / fast16 / generic / fast4 brackets
+    cudaEvent_t ev_t[12] = {};  // pack / fast16 / generic / fast4 / slow-bitmap / search brackets
     double last_points = 0.0;
-    double last_pts3[4] = { 0.0, 0.0, 0.0, 0.0 };
+    double last_pts3[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
+    cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer pipeline
+    cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
     bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };
 

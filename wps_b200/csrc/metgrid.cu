@@ -131,7 +131,7 @@ __device__ __forceinline__ int process_point(const Job& jb, const float* __restr
 
 // ---- main batched kernel -------------------------------------------------------------------------
 // grid.x = sum over jobs of tiles; block = 32x8 destination points; each thread walks the job's slabs.
-__global__ void __launch_bounds__(TILE_X * TILE_Y)
+__global__ void __launch_bounds__(TILE_X * TILE_Y, 2)
 k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_tile0, int ncls,
                  const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count)
 {
@@ -245,24 +245,33 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, in
         out[3][lv] = 0.5f * (v[2] + v[0]) - v[1];
         out[4][lv] = 0.5f * (v[1] - v[3]);
         out[5][lv] = 0.5f * (v[1] + v[3]) - v[2];
-        bool clean = true;
+        // masked=both: the landmask picks interp_land_mask (water points, bits 0-3) or interp_water_mask (land points,
+        // bits 4-7) per destination point (:2495-2513), so both variants of the flag are kept
+        const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
+        const int selA = both ? 1 : 0;
+        bool clean = true, cleanA = true, cleanB = true;
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             int r = min(max(jj + l - 1, sy), ey);
             float w[4];
             row4(r, w);
             clean = clean && w[0] != msg && w[1] != msg && w[2] != msg && w[3] != msg && (w[1] * w[2] != 0.0f) && (w[0] * w[3] != 0.0f);
-            if (jb.mask[0]) {   // interp_mask: any unusable cell in the stencil sends sixteen_pt to the next method (:1244-1270)
-                const float* mp = jb.mask[0] + (size_t)(r - sy) * snx;
+            // interp_mask: any unusable cell in the stencil sends sixteen_pt to the next method (:1244-1270)
+            auto mask_row = [&](int sel, bool& c) {
+                if (!jb.mask[sel]) return;
+                const float* mp = jb.mask[sel] + (size_t)(r - sy) * snx;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     float m = __ldg(mp + col[k]);
-                    bool out_ = jb.mask_rel[0] == REL_GT ? (m > jb.mask_val[0]) : (jb.mask_rel[0] == REL_LT ? (m < jb.mask_val[0]) : (m == jb.mask_val[0]));
-                    clean = clean && !out_;
+                    bool out_ = jb.mask_rel[sel] == REL_GT ? (m > jb.mask_val[sel]) : (jb.mask_rel[sel] == REL_LT ? (m < jb.mask_val[sel]) : (m == jb.mask_val[sel]));
+                    c = c && !out_;
                 }
-            }
+            };
+            mask_row(selA, cleanA);
+            if (both) mask_row(2, cleanB);
         }
-        if (clean) cfbits |= 1u << lv;
+        if (clean && cleanA) cfbits |= 1u << lv;
+        if (both && clean && cleanB) cfbits |= 16u << lv;
     }
     size_t o = ((size_t)pack * jb.bny + cj) * jb.bnx + ci;
     float4* rec = const_cast<float4*>(jb.rec) + o * 6;
@@ -336,17 +345,24 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
     // level-independent part of interp_met_field's point logic (:2490-2541) and of sixteen_pt (interp_module.F:1211-1241)
     bool fastpt = false, fillpt = false;
     float x = 0.0f, y = 0.0f;
-    int roff[4] = {0, 0, 0, 0}, cfoff = 0;
+    int roff[4] = {0, 0, 0, 0}, cfoff = 0, cfshift = 0;
     if (active) {
         float2 xy = __ldg(jb.xy + idx);
         int di = jb.sm1 + ii, dj = jb.sm2 + jj;
         const int pw = jb.pw;
         bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
         // process_bdy_width interior, or landmask == masked: the point receives fill_missing and counts as new
-        fillpt = in_fill || (jb.landmask != nullptr && __ldg(jb.landmask + idx) == jb.masked);
+        float lm = jb.landmask != nullptr ? __ldg(jb.landmask + idx) : 0.0f;
+        bool lm_ok = true;
+        if (jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH) {
+            // water points use interp_land_mask (flag bits 0-3), land points interp_water_mask (bits 4-7), :2495-2513
+            cfshift = lm == 1.0f ? 4 : 0;
+            lm_ok = lm == 0.0f || lm == 1.0f;
+        } else fillpt = jb.landmask != nullptr && lm == jb.masked;
+        fillpt = fillpt || in_fill;
         float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
         float xx = xy.x, yy = xy.y;
-        if (!fillpt && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f &&
+        if (!fillpt && lm_ok && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f &&
             (int)xx >= jb.minx && (int)xx <= jb.maxx && (int)yy >= jb.miny && (int)yy <= jb.maxy) {
             int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
             x = xx - (float)i; y = yy - (float)j;
@@ -370,7 +386,7 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
     const float4* __restrict__ rec = jb.rec;
     const unsigned char* __restrict__ cf = jb.cf;
     for (int pack = 0; pack < npack; ++pack) {
-        unsigned cfbits = fastpt ? (unsigned)__ldg(cf + cfoff) : 0u;
+        unsigned cfbits = fastpt ? ((unsigned)__ldg(cf + cfoff) >> cfshift) : 0u;
         float2 r01[4], r23[4];  // x-pass results per stencil row, levels (0,1) and (2,3)
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
@@ -491,13 +507,12 @@ k_metgrid_fast4(const __grid_constant__ Fast4Params P)
 
 // Points the packed kernel could not take (missing values in the stencil, points on a node or near the array edge,
 // process_bdy_width interior): full generic operator chain, one thread per flagged word.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_word0, int ncls,
                    const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count,
                    long long total_words)
 {
-    // each lane fetches one bitmap word (coalesced); the warp then walks the non-empty words together, lane b taking
-    // point b of the word, so the flagged points of a word are processed in parallel
+    // each lane fetches one bitmap word (coalesced)
     const int lane = threadIdx.x & 31;
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned bits = 0;
@@ -517,21 +532,34 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_job
         widx = rel % words_per_slab;
         bits = (unsigned)slabs[jb.slab0 + sl].slow[widx];
     }
-    unsigned pending = __ballot_sync(0xffffffffu, bits != 0);
-    while (pending) {
-        int srcl = __ffs(pending) - 1;
-        pending &= pending - 1;
-        unsigned wbits = __shfl_sync(0xffffffffu, bits, srcl);
-        int wjob = __shfl_sync(0xffffffffu, job, srcl), wsl = __shfl_sync(0xffffffffu, sl, srcl);
-        long long wwidx = __shfl_sync(0xffffffffu, widx, srcl);
-        const Job& jb = jobs[wjob];
-        const SlabPtrs sp = slabs[jb.slab0 + wsl];
-        bool newbit = false;
-        if ((wbits >> lane) & 1u) {
+    // The flagged points of the warp's 32 words are ranked by an exclusive scan of the per-word popcounts and dealt
+    // out 32 at a time, so every lane has a point to work on regardless of how the bits are spread over the words.
+    unsigned cnt = __popc(bits), inc = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += v;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, inc, 31), exc = inc - cnt;
+    for (unsigned base = 0; base < total; base += 32) {
+        unsigned r = base + lane;
+        int pos = 0;   // largest lane whose exclusive prefix is <= r: the word holding the r-th flagged point
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            unsigned e = __shfl_sync(0xffffffffu, exc, pos + step);
+            if (e <= r) pos += step;
+        }
+        unsigned wbits = __shfl_sync(0xffffffffu, bits, pos), wexc = __shfl_sync(0xffffffffu, exc, pos);
+        int wjob = __shfl_sync(0xffffffffu, job, pos), wsl = __shfl_sync(0xffffffffu, sl, pos);
+        long long wwidx = __shfl_sync(0xffffffffu, widx, pos);
+        if (r < total) {
+            int bit = (int)__fns(wbits, 0, (int)(r - wexc) + 1);
+            const Job& jb = jobs[wjob];
+            const SlabPtrs sp = slabs[jb.slab0 + wsl];
             int jj = (int)(wwidx / jb.nxw), tx = (int)(wwidx % jb.nxw);
-            int ii = tx * 32 + lane;
+            int ii = tx * 32 + bit;
             size_t idx = (size_t)jj * jb.nx + ii;
-            bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> lane) & 1u) : false;
+            bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> bit) & 1u) : false;
             float out = 0.0f;
             int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, __ldg(jb.xy + idx), vbit, out);
             if (flags & PF_DEFER) {
@@ -540,11 +568,9 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_job
                 deferred[slot] = d;
             } else {
                 if (flags & PF_WRITE) sp.r_arr[idx] = out;
-                newbit = (flags & PF_BIT) != 0;
+                if (flags & PF_BIT) atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
             }
         }
-        unsigned nb = __ballot_sync(0xffffffffu, newbit);
-        if (lane == 0 && nb) atomicOr(sp.new_pts + wwidx, (int)nb);
     }
 }
 
@@ -724,6 +750,19 @@ int wpsgpu_metgrid_enqueue_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, 
     return 0;
 }
 
+int wpsgpu_metgrid_enqueue_slabs(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, const wpsgpu_field_opts* fo,
+                                 const wpsgpu_slab* slabs, int32_t n)
+{
+    WPS_CHECK(h && src_proj && fo && (slabs || n == 0), -1, "wpsgpu_metgrid_enqueue_slabs: NULL argument");
+    WPS_CHECK(n >= 0, -1, "negative slab count");
+    const size_t mark = h->queue.size();
+    for (int32_t k = 0; k < n; ++k) {
+        int rc = wpsgpu_metgrid_enqueue_slab(h, src_proj, fo, slabs + k);
+        if (rc) { h->queue.resize(mark); return rc; }   // all or nothing
+    }
+    return 0;
+}
+
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float* ms, double* points)
 {
     WPS_CHECK(h && ms && points, -1, "NULL argument");
@@ -736,11 +775,258 @@ int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float* ms, double* points)
 int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float* ms3, double* points3)
 {
     WPS_CHECK(h && ms3 && points3, -1, "NULL argument");
-    WPS_CUDA(cudaEventSynchronize(h->ev_t[5]));
-    WPS_CUDA(cudaEventSynchronize(h->ev_t[7]));
-    for (int k = 0; k < 4; ++k) {
+    WPS_CUDA(cudaEventSynchronize(h->ev_t[11]));
+    for (int k = 0; k < 6; ++k) {
         WPS_CUDA(cudaEventElapsedTime(&ms3[k], h->ev_t[2 * k], h->ev_t[2 * k + 1]));
         points3[k] = h->last_pts3[k];
+    }
+    return 0;
+}
+
+// One pass over a subset of the job groups: stage inputs on s_in, compute on the handle's stream, copy results back
+// on s_out.  In device-pointer mode all three are the handle's stream and nothing is copied.
+struct Box { int fast, bx0, by0, bnx, bny, npack; };
+struct FlushShared {
+    std::vector<QueuedSlab>* queue;
+    std::vector<std::vector<int>>* groups;
+    std::vector<const float2*> job_xy;
+    std::vector<const float*> job_gauss;
+    std::vector<Box> box;
+    std::map<const void*, void*> staged;     // host pointer -> staged device copy (masks are shared by many slabs)
+    int max_depth = 0, max_span = 0;
+};
+
+static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gsel, cudaStream_t s_in, cudaStream_t s_out, bool last)
+{
+    std::vector<QueuedSlab>& queue = *fs.queue;
+    std::vector<std::vector<int>>& groups = *fs.groups;
+    const bool host = h->ptr_mode == WPSGPU_PTR_HOST;
+    const int njobs = (int)gsel.size();
+    int nq = 0;
+    for (int g : gsel) nq += (int)groups[g].size();
+    auto stage_shared = [&](const float* p, size_t bytes, const float** out) -> int {
+        if (!p) { *out = nullptr; return 0; }
+        if (!host) { *out = p; return 0; }
+        auto it = fs.staged.find(p);
+        if (it != fs.staged.end()) { *out = (const float*)it->second; return 0; }
+        void* d = h->arena.take(bytes);
+        WPS_CHECK(d != nullptr, -3, "device arena exhausted (%zu bytes requested)", bytes);
+        WPS_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s_in));
+        fs.staged[p] = d;
+        *out = (const float*)d;
+        return 0;
+    };
+    std::vector<Job> jobs(njobs);
+    std::vector<SlabPtrs> sp(nq);
+    struct OutRec { float* h_r; void* d_r; int* h_np; void* d_np; size_t rbytes, wbytes; };
+    std::vector<OutRec> outs;
+    std::vector<int> cls_jobs[2], cls_tile0[2];  // 0 = generic kernel, 1 = first-method kernels
+    std::vector<int> fast_word0;
+    long long fast_words = 0;
+    int tile_cursor[2] = { 0, 0 };
+    double cls_points[2] = { 0.0, 0.0 };
+    double fast16_points = 0.0, fast4_points = 0.0;
+    int slab_cursor = 0;
+    unsigned long long defer_cursor = 0;
+    bool any_search = false;
+    for (int j = 0; j < njobs; ++j) {
+        const int g = gsel[j];
+        const QueuedSlab& q0 = queue[groups[g][0]];
+        const DstGrid& dg = h->grids[q0.s.grid_id];
+        Job& jb = jobs[j];
+        memset(&jb, 0, sizeof(Job));
+        jb.xy = fs.job_xy[g]; jb.xlat = dg.d_xlat; jb.xlon = dg.d_xlon;
+        jb.landmask = q0.s.use_landmask ? dg.d_landmask : nullptr;
+        jb.sm1 = dg.sm1; jb.em1 = dg.em1; jb.sm2 = dg.sm2; jb.em2 = dg.em2;
+        jb.nx = dg.nx(); jb.ny = dg.ny(); jb.nxw = (jb.nx + 31) / 32;
+        jb.sd1 = h->sd1; jb.ed1 = h->ed1; jb.sd2 = h->sd2; jb.ed2 = h->ed2;
+        // process_width, process_domain_module.F:2270-2278
+        if (q0.s.process_bdy_width == 0) jb.pw = std::max(h->ed1 - h->sd1 + 1, h->ed2 - h->sd2 + 1);
+        else { jb.pw = q0.s.process_bdy_width; if (q0.s.field_stagger != WPSGPU_M) jb.pw += 2; }
+        jb.proj = to_dev(q0.proj, fs.job_gauss[g]);
+        jb.minx = q0.s.minx; jb.maxx = q0.s.maxx; jb.miny = q0.s.miny; jb.maxy = q0.s.maxy; jb.bdr = q0.s.bdr;
+        size_t sbytes = (size_t)(jb.maxx - jb.minx + 1) * (jb.maxy - jb.miny + 1) * sizeof(float);
+        for (int m = 0; m < 3; ++m) {
+            WPS_TRY(stage_shared(q0.s.mask[m], sbytes, &jb.mask[m]));
+            jb.mask_val[m] = q0.fo.mask_val[m];
+            jb.mask_rel[m] = rel_code(q0.fo.mask_rel[m]);
+        }
+        memcpy(jb.ops, q0.fo.ops, sizeof(jb.ops));
+        memcpy(jb.opts, q0.fo.opts, sizeof(jb.opts));
+        jb.ops[WPSGPU_MAX_OPS - 1] = 0;
+        jb.msg = q0.fo.missing_value; jb.fill = q0.fo.fill_missing; jb.masked = q0.fo.masked;
+        jb.nslab = (int)groups[g].size(); jb.slab0 = slab_cursor;
+        jb.tiles_x = (jb.nx + TILE_X - 1) / TILE_X; jb.tiles_y = (jb.ny + TILE_Y - 1) / TILE_Y;
+        const Box& bx = fs.box[g];
+        const int cls = bx.fast ? 1 : 0;
+        jb.tile0 = tile_cursor[cls];
+        cls_jobs[cls].push_back(j);
+        cls_tile0[cls].push_back(tile_cursor[cls]);
+        tile_cursor[cls] += jb.tiles_x * jb.tiles_y;
+        cls_points[cls] += (double)dg.npts() * groups[g].size();
+        if (bx.fast == 1) fast16_points += (double)dg.npts() * groups[g].size();
+        if (bx.fast >= 2) fast4_points += (double)dg.npts() * groups[g].size();
+        if (cls == 1) { fast_word0.push_back((int)fast_words); fast_words += (long long)jb.ny * jb.nxw * groups[g].size(); }
+        jb.f_negzero = -0.0f; jb.f_one = 1.0f;
+        jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
+        if (jb.fast == 1) {
+            size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
+            jb.rec = (const float4*)h->arena.take(cells * 6 * sizeof(float4));
+            jb.cf = (const unsigned char*)h->arena.take(cells);
+            WPS_CHECK(jb.rec && jb.cf, -3, "device arena exhausted (packed records)");
+        }
+        bool has_search = false;
+        for (int k = 0; k < WPSGPU_MAX_OPS && jb.ops[k]; ++k) if (jb.ops[k] == WPSGPU_SEARCH) has_search = true;
+        jb.defer_base = defer_cursor;
+        if (has_search) { defer_cursor += (unsigned long long)dg.npts() * groups[g].size(); any_search = true; }
+        size_t rbytes = dg.npts() * sizeof(float), wbytes = (size_t)jb.ny * jb.nxw * sizeof(int);
+        for (int a : groups[g]) {
+            const wpsgpu_slab& s = queue[a].s;
+            SlabPtrs& p = sp[slab_cursor++];
+            p.slow = nullptr; p.pad_ = nullptr;
+            if (jb.fast) { p.slow = (int*)h->arena.take(wbytes); WPS_CHECK(p.slow != nullptr, -3, "device arena exhausted (slow bitmaps)"); }
+            WPS_TRY(stage_shared(s.slab, sbytes, &p.src));
+            if (host) {
+                void* d_r = h->arena.take(rbytes); void* d_np = h->arena.take(wbytes); void* d_v = nullptr;
+                WPS_CHECK(d_r && d_np, -3, "device arena exhausted (outputs)");
+                if (s.valid_mask) {  // r_arr carries lower-priority data only where valid bits are set
+                    d_v = h->arena.take(wbytes);
+                    WPS_CHECK(d_v != nullptr, -3, "device arena exhausted (valid mask)");
+                    WPS_CUDA(cudaMemcpyAsync(d_r, s.r_arr, rbytes, cudaMemcpyHostToDevice, s_in));
+                    WPS_CUDA(cudaMemcpyAsync(d_v, s.valid_mask, wbytes, cudaMemcpyHostToDevice, s_in));
+                }
+                p.r_arr = (float*)d_r; p.valid = (const int*)d_v; p.new_pts = (int*)d_np;
+                OutRec o; o.h_r = s.r_arr; o.d_r = d_r; o.h_np = s.new_pts; o.d_np = d_np; o.rbytes = rbytes; o.wbytes = wbytes;
+                outs.push_back(o);
+            } else {
+                p.r_arr = s.r_arr; p.valid = s.valid_mask; p.new_pts = s.new_pts;
+            }
+        }
+    }
+    Job* d_jobs = (Job*)h->arena.take(sizeof(Job) * njobs);
+    SlabPtrs* d_sp = (SlabPtrs*)h->arena.take(sizeof(SlabPtrs) * nq);
+    int* d_cls = (int*)h->arena.take(sizeof(int) * 5 * (njobs + 1));
+    WPS_CHECK(d_jobs && d_sp && d_cls, -3, "device arena exhausted (tables)");
+    WPS_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(Job) * njobs, cudaMemcpyHostToDevice, s_in));
+    WPS_CUDA(cudaMemcpyAsync(d_sp, sp.data(), sizeof(SlabPtrs) * nq, cudaMemcpyHostToDevice, s_in));
+    int* d_cls_jobs[2]; int* d_cls_tile0[2];
+    for (int c = 0; c < 2; ++c) {
+        d_cls_jobs[c] = d_cls + (2 * c) * (njobs + 1);
+        d_cls_tile0[c] = d_cls + (2 * c + 1) * (njobs + 1);
+        if (!cls_jobs[c].empty()) {
+            WPS_CUDA(cudaMemcpyAsync(d_cls_jobs[c], cls_jobs[c].data(), sizeof(int) * cls_jobs[c].size(), cudaMemcpyHostToDevice, s_in));
+            WPS_CUDA(cudaMemcpyAsync(d_cls_tile0[c], cls_tile0[c].data(), sizeof(int) * cls_tile0[c].size(), cudaMemcpyHostToDevice, s_in));
+        }
+    }
+    int* d_fast_word0 = d_cls + 4 * (njobs + 1);
+    WPS_CHECK(fast_words < 2000000000LL, -3, "too many output words in one flush");
+    if (!fast_word0.empty()) WPS_CUDA(cudaMemcpyAsync(d_fast_word0, fast_word0.data(), sizeof(int) * fast_word0.size(), cudaMemcpyHostToDevice, s_in));
+    Deferred *d_def = nullptr, *d_def2 = nullptr;
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(h->d_counters);
+    if (any_search) {
+        d_def = (Deferred*)h->arena.take(sizeof(Deferred) * defer_cursor);
+        d_def2 = (Deferred*)h->arena.take(sizeof(Deferred) * defer_cursor);
+        WPS_CHECK(d_def && d_def2, -3, "device arena exhausted (deferred lists)");
+    }
+    // inputs staged on s_in must be complete before the compute stream touches them
+    if (s_in != h->stream) {
+        WPS_CUDA(cudaEventRecord(h->ev_copy, s_in));
+        WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+    }
+    if (any_search) WPS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), h->stream));
+
+    // ---- launches ----
+    dim3 block(TILE_X, TILE_Y);
+    WPS_CUDA(cudaEventRecord(h->ev_t[0], h->stream));
+    for (int j : cls_jobs[1]) {
+        const Job& jb = jobs[j];
+        if (jb.fast != 1) continue;
+        k_pack16<<<dim3((jb.bnx * jb.bny + 255) / 256, jb.npack), 256, 0, h->stream>>>(d_jobs, j, d_sp);
+        h->launches++;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
+    WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
+    for (int j : cls_jobs[1]) {
+        if (jobs[j].fast != 1) continue;
+        FastParams fp;
+        fp.jb = jobs[j];
+        for (int k = 0; k < fp.jb.nslab; ++k) {
+            const SlabPtrs& p = sp[fp.jb.slab0 + k];
+            fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
+        }
+        k_metgrid_fast16<<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
+        h->launches++;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
+    WPS_CUDA(cudaEventRecord(h->ev_t[6], h->stream));
+    for (int j : cls_jobs[1]) {
+        if (jobs[j].fast < 2) continue;
+        Fast4Params fp;
+        fp.jb = jobs[j];
+        for (int k = 0; k < fp.jb.nslab; ++k) {
+            const SlabPtrs& p = sp[fp.jb.slab0 + k];
+            fp.src[k] = p.src; fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
+        }
+        if (jobs[j].fast == 2) k_metgrid_fast4<WPSGPU_FOUR_POINT><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
+        else k_metgrid_fast4<WPSGPU_N_NEIGHBOR><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
+        h->launches++;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[7], h->stream));
+    WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
+    if (tile_cursor[1] > 0) {
+        k_metgrid_slowbits<<<(unsigned)((fast_words + 127) / 128), 128, 0, h->stream>>>(d_jobs, d_cls_jobs[1], d_fast_word0, (int)cls_jobs[1].size(), d_sp, d_def, d_cnt, fast_words);
+        h->launches++;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[9], h->stream));
+    WPS_CUDA(cudaEventRecord(h->ev_t[4], h->stream));
+    if (tile_cursor[0] > 0) {
+        k_metgrid_interp<<<tile_cursor[0], block, 0, h->stream>>>(d_jobs, d_cls_jobs[0], d_cls_tile0[0], (int)cls_jobs[0].size(), d_sp, d_def, d_cnt);
+        h->launches++;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[5], h->stream));
+    WPS_CUDA(cudaGetLastError());
+    if (last) {
+        h->last_pts3[0] = fast16_points; h->last_pts3[1] = fast16_points; h->last_pts3[2] = cls_points[0]; h->last_pts3[3] = fast4_points;
+        h->last_pts3[4] = cls_points[1]; h->last_pts3[5] = (double)defer_cursor;
+        // the dominant kernel for the roofline line: whichever main kernel produced more outputs
+        int dom = fast16_points >= cls_points[0] ? 1 : 2;
+        h->ev_k0 = h->ev_t[2 * dom]; h->ev_k1 = h->ev_t[2 * dom + 1];
+        h->last_points = dom == 1 ? fast16_points : cls_points[0];
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[10], h->stream));
+    if (any_search) {
+        int sblocks = h->sm_count * 8;
+        k_metgrid_search<<<sblocks, 256, 0, h->stream>>>(d_jobs, njobs, d_sp, d_def, d_cnt, d_def2, d_cnt + 1);
+        h->launches++;
+        WPS_CUDA(cudaGetLastError());
+        // literal fallback: few threads, big per-thread scratch
+        int R = std::min(std::max(fs.max_depth, 1), std::max(fs.max_span, 1));
+        size_t vis_words = ((size_t)(2 * R + 1) * (2 * R + 1) + 31) / 32;
+        int qcap = 8 * R + 64;
+        size_t words_per_thread = ((vis_words + 1) & ~size_t(1)) + (size_t)qcap * sizeof(QNode) / sizeof(unsigned);
+        int lit_threads = 256;
+        size_t bytes = words_per_thread * sizeof(unsigned) * lit_threads;
+        if (bytes > h->search_scratch_bytes) {
+            WPS_CUDA(cudaStreamSynchronize(h->stream));
+            if (h->d_search_scratch) cudaFree(h->d_search_scratch);
+            WPS_CUDA(cudaMalloc(&h->d_search_scratch, bytes));
+            h->search_scratch_bytes = bytes;
+        }
+        k_metgrid_search_literal<<<lit_threads / 64, 64, 0, h->stream>>>(d_jobs, njobs, d_sp, d_def2, d_cnt + 1,
+                                                                      (unsigned*)h->d_search_scratch, words_per_thread, R, qcap);
+        h->launches++;
+        WPS_CUDA(cudaGetLastError());
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[11], h->stream));
+    if (host) {
+        if (s_out != h->stream) {
+            WPS_CUDA(cudaEventRecord(h->ev_done, h->stream));
+            WPS_CUDA(cudaStreamWaitEvent(s_out, h->ev_done, 0));
+        }
+        for (const OutRec& o : outs) {
+            WPS_CUDA(cudaMemcpyAsync(o.h_r, o.d_r, o.rbytes, cudaMemcpyDeviceToHost, s_out));
+            WPS_CUDA(cudaMemcpyAsync(o.h_np, o.d_np, o.wbytes, cudaMemcpyDeviceToHost, s_out));
+        }
     }
     return 0;
 }
@@ -756,18 +1042,21 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     const int nq = (int)queue.size();
 
     // ---- group slabs into jobs (stable: first-appearance order) ----
+    // host-pointer mode keeps the groups short so that copies and kernels of neighbouring groups overlap
+    const int group_cap = host ? 16 : FAST_MAX_SLABS;
     std::vector<std::vector<int>> groups;
     for (int a = 0; a < nq; ++a) {
         bool placed = false;
         for (size_t g = 0; g < groups.size() && !placed; ++g)
-            if ((int)groups[g].size() < FAST_MAX_SLABS && same_group(queue[groups[g][0]], queue[a])) { groups[g].push_back(a); placed = true; }
+            if ((int)groups[g].size() < group_cap && same_group(queue[groups[g][0]], queue[a])) { groups[g].push_back(a); placed = true; }
         if (!placed) groups.push_back(std::vector<int>(1, a));
     }
     const int njobs = (int)groups.size();
+    FlushShared fs;
+    fs.queue = &queue; fs.groups = &groups;
+    fs.job_xy.resize(njobs); fs.job_gauss.assign(njobs, nullptr); fs.box.resize(njobs);
 
     // ---- coordinate cache: (rx, ry) of every destination point per (grid, source projection), computed once ----
-    std::vector<const float2*> job_xy(njobs);
-    std::vector<const float*> job_gauss(njobs, nullptr);
     std::vector<int> job_bbox(4 * njobs, 0);
     for (int g = 0; g < njobs; ++g) {
         const QueuedSlab& q0 = queue[groups[g][0]];
@@ -798,19 +1087,17 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
             if (it != h->coord_cache.end()) { cudaFree(it->second.d_xy); if (it->second.d_gauss) cudaFree(it->second.d_gauss); h->coord_cache.erase(it); }
             it = h->coord_cache.insert(std::make_pair(key, e)).first;
         }
-        job_xy[g] = it->second.d_xy;
-        job_gauss[g] = it->second.d_gauss;
+        fs.job_xy[g] = it->second.d_xy;
+        fs.job_gauss[g] = it->second.d_gauss;
         memcpy(&job_bbox[4 * g], it->second.bbox, 4 * sizeof(int));
     }
 
     // ---- classify jobs and size the arena ----
-    // fast16: chain starts with sixteen_pt, no interp mask on the path every point takes, and the source-cell
-    // bounding box is small against the destination grid (source coarser than the domain).
-    struct Box { int fast, bx0, by0, bnx, bny, npack; };
-    std::vector<Box> box(njobs);
-    size_t need = (size_t)njobs * (sizeof(Job) + 64) + (size_t)nq * sizeof(SlabPtrs) + (1 << 20);
+    // first-method kernels: chain starts with sixteen_pt / four_pt / nearest_neighbor (the latter two only when the
+    // landmask logic selects a single interp mask, i.e. not masked=both); sixteen_pt additionally needs the
+    // source-cell bounding box to be small against the destination grid (source coarser than the domain).
+    size_t need = (size_t)njobs * (sizeof(Job) + 256) + (size_t)nq * sizeof(SlabPtrs) + (1 << 20);
     size_t defer_entries = 0;
-    int max_depth = 0, max_span = 0;
     std::map<const void*, size_t> uniq_in;  // host source/mask pointers staged once
     for (int g = 0; g < njobs; ++g) {
         const QueuedSlab& q0 = queue[groups[g][0]];
@@ -818,17 +1105,16 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         size_t sbytes = (size_t)(q0.s.maxx - q0.s.minx + 1) * (q0.s.maxy - q0.s.miny + 1) * sizeof(float);
         bool has_search = false;
         for (int k = 0; k < WPSGPU_MAX_OPS && q0.fo.ops[k]; ++k)
-            if (q0.fo.ops[k] == WPSGPU_SEARCH) { has_search = true; max_depth = std::max(max_depth, q0.fo.opts[k]); }
+            if (q0.fo.ops[k] == WPSGPU_SEARCH) { has_search = true; fs.max_depth = std::max(fs.max_depth, q0.fo.opts[k]); }
         if (has_search) {
             defer_entries += dg.npts() * groups[g].size();
-            max_span = std::max(max_span, std::max(q0.s.maxx - q0.s.minx, q0.s.maxy - q0.s.miny));
+            fs.max_span = std::max(fs.max_span, std::max(q0.s.maxx - q0.s.minx, q0.s.maxy - q0.s.miny));
         }
-        Box& b = box[g];
+        Box& b = fs.box[g];
         b.fast = 0; b.bx0 = b.by0 = b.bnx = b.bny = b.npack = 0;
         const int* bb = &job_bbox[4 * g];
-        // eligible for the first-method kernels unless masked=both (two interp masks chosen per point by the landmask)
         bool simple_mask = !(q0.s.use_landmask && q0.fo.masked == WPSGPU_MASKED_BOTH);
-        if (simple_mask && !h->disable_fast) {
+        if (!h->disable_fast && (simple_mask || q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT)) {
             if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
                 long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);
                 long y0 = std::max<long>(q0.s.miny, (long)bb[2] - 2), y1 = std::min<long>(q0.s.maxy, (long)bb[3] + 4);
@@ -851,219 +1137,40 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         }
     }
     for (auto& kv : uniq_in) need += kv.second + 256;
-    need += 2 * (defer_entries * sizeof(Deferred) + 256);
+    need += 2 * (defer_entries * sizeof(Deferred) + 256) + (size_t)njobs * 4096;
     h->arena.reset();
     WPS_TRY(h->arena.reserve(need, h->stream));
 
-    // ---- stage inputs, build tables ----
-    std::map<const void*, void*> staged;
-    auto stage_shared = [&](const float* p, size_t bytes, const float** out) -> int {
-        if (!p) { *out = nullptr; return 0; }
-        if (!host) { *out = p; return 0; }
-        auto it = staged.find(p);
-        if (it != staged.end()) { *out = (const float*)it->second; return 0; }
-        void* d;
-        WPS_TRY(stage_in(h, p, bytes, &d));
-        staged[p] = d;
-        *out = (const float*)d;
-        return 0;
-    };
-    std::vector<Job> jobs(njobs);
-    std::vector<SlabPtrs> sp(nq);
-    struct OutRec { float* h_r; void* d_r; int* h_np; void* d_np; size_t rbytes, wbytes; };
-    std::vector<OutRec> outs;
-    std::vector<int> cls_jobs[2], cls_tile0[2];  // 0 = generic kernel, 1 = packed sixteen_pt kernel
-    std::vector<int> fast_word0;
-    long long fast_words = 0;
-    int tile_cursor[2] = { 0, 0 };
-    double cls_points[2] = { 0.0, 0.0 };
-    double fast16_points = 0.0, fast4_points = 0.0;
-    int slab_cursor = 0;
-    unsigned long long defer_cursor = 0;
-    bool any_search = false;
+    if (!host) {
+        std::vector<int> all(njobs);
+        for (int g = 0; g < njobs; ++g) all[g] = g;
+        return run_groups(h, fs, all, h->stream, h->stream, true);
+    }
+    // Host-pointer mode: pipeline the job groups through three streams so that the H2D copies of group k+1, the kernels of
+    // group k and the D2H copies of group k-1 overlap (PCIe is full duplex and is the end-to-end limiter).
+    if (!h->s_in) {
+        WPS_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+        WPS_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+        WPS_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+        WPS_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    }
+    // everything previously enqueued on the handle's stream (set_grid copies, earlier calls) precedes the new copies
+    WPS_CUDA(cudaEventRecord(h->ev_done, h->stream));
+    WPS_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
+    const int chunk_slabs = 12;
+    std::vector<int> sel;
+    int count = 0;
     for (int g = 0; g < njobs; ++g) {
-        const QueuedSlab& q0 = queue[groups[g][0]];
-        const DstGrid& dg = h->grids[q0.s.grid_id];
-        Job& jb = jobs[g];
-        memset(&jb, 0, sizeof(Job));
-        jb.xy = job_xy[g]; jb.xlat = dg.d_xlat; jb.xlon = dg.d_xlon;
-        jb.landmask = q0.s.use_landmask ? dg.d_landmask : nullptr;
-        jb.sm1 = dg.sm1; jb.em1 = dg.em1; jb.sm2 = dg.sm2; jb.em2 = dg.em2;
-        jb.nx = dg.nx(); jb.ny = dg.ny(); jb.nxw = (jb.nx + 31) / 32;
-        jb.sd1 = h->sd1; jb.ed1 = h->ed1; jb.sd2 = h->sd2; jb.ed2 = h->ed2;
-        // process_width, process_domain_module.F:2270-2278
-        if (q0.s.process_bdy_width == 0) jb.pw = std::max(h->ed1 - h->sd1 + 1, h->ed2 - h->sd2 + 1);
-        else { jb.pw = q0.s.process_bdy_width; if (q0.s.field_stagger != WPSGPU_M) jb.pw += 2; }
-        jb.proj = to_dev(q0.proj, job_gauss[g]);
-        jb.minx = q0.s.minx; jb.maxx = q0.s.maxx; jb.miny = q0.s.miny; jb.maxy = q0.s.maxy; jb.bdr = q0.s.bdr;
-        size_t sbytes = (size_t)(jb.maxx - jb.minx + 1) * (jb.maxy - jb.miny + 1) * sizeof(float);
-        for (int m = 0; m < 3; ++m) {
-            WPS_TRY(stage_shared(q0.s.mask[m], sbytes, &jb.mask[m]));
-            jb.mask_val[m] = q0.fo.mask_val[m];
-            jb.mask_rel[m] = rel_code(q0.fo.mask_rel[m]);
-        }
-        memcpy(jb.ops, q0.fo.ops, sizeof(jb.ops));
-        memcpy(jb.opts, q0.fo.opts, sizeof(jb.opts));
-        jb.ops[WPSGPU_MAX_OPS - 1] = 0;
-        jb.msg = q0.fo.missing_value; jb.fill = q0.fo.fill_missing; jb.masked = q0.fo.masked;
-        jb.nslab = (int)groups[g].size(); jb.slab0 = slab_cursor;
-        jb.tiles_x = (jb.nx + TILE_X - 1) / TILE_X; jb.tiles_y = (jb.ny + TILE_Y - 1) / TILE_Y;
-        const int cls = box[g].fast ? 1 : 0;
-        jb.tile0 = tile_cursor[cls];
-        cls_jobs[cls].push_back(g);
-        cls_tile0[cls].push_back(tile_cursor[cls]);
-        tile_cursor[cls] += jb.tiles_x * jb.tiles_y;
-        cls_points[cls] += (double)dg.npts() * groups[g].size();
-        if (box[g].fast == 1) fast16_points += (double)dg.npts() * groups[g].size();
-        if (box[g].fast >= 2) fast4_points += (double)dg.npts() * groups[g].size();
-        if (cls == 1) { fast_word0.push_back((int)fast_words); fast_words += (long long)jb.ny * jb.nxw * groups[g].size(); }
-        jb.f_negzero = -0.0f; jb.f_one = 1.0f;
-        jb.fast = box[g].fast; jb.bx0 = box[g].bx0; jb.by0 = box[g].by0; jb.bnx = box[g].bnx; jb.bny = box[g].bny; jb.npack = box[g].npack;
-        if (jb.fast == 1) {
-            size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
-            jb.rec = (const float4*)h->arena.take(cells * 6 * sizeof(float4));
-            jb.cf = (const unsigned char*)h->arena.take(cells);
-            WPS_CHECK(jb.rec && jb.cf, -3, "device arena exhausted (packed records)");
-        }
-        bool has_search = false;
-        for (int k = 0; k < WPSGPU_MAX_OPS && jb.ops[k]; ++k) if (jb.ops[k] == WPSGPU_SEARCH) has_search = true;
-        jb.defer_base = defer_cursor;
-        if (has_search) { defer_cursor += (unsigned long long)dg.npts() * groups[g].size(); any_search = true; }
-        size_t rbytes = dg.npts() * sizeof(float), wbytes = (size_t)jb.ny * jb.nxw * sizeof(int);
-        for (int a : groups[g]) {
-            const wpsgpu_slab& s = queue[a].s;
-            SlabPtrs& p = sp[slab_cursor++];
-            p.slow = nullptr; p.pad_ = nullptr;
-            if (jb.fast) { p.slow = (int*)h->arena.take(wbytes); WPS_CHECK(p.slow != nullptr, -3, "device arena exhausted (slow bitmaps)"); }
-            WPS_TRY(stage_shared(s.slab, sbytes, &p.src));
-            if (host) {
-                void* d_r; void* d_np; void* d_v = nullptr;
-                if (s.valid_mask) {  // r_arr carries lower-priority data only where valid bits are set
-                    WPS_TRY(stage_in(h, s.r_arr, rbytes, &d_r));
-                    WPS_TRY(stage_in(h, s.valid_mask, wbytes, &d_v));
-                } else WPS_TRY(alloc_out(h, s.r_arr, rbytes, &d_r));
-                WPS_TRY(alloc_out(h, s.new_pts, wbytes, &d_np));
-                p.r_arr = (float*)d_r; p.valid = (const int*)d_v; p.new_pts = (int*)d_np;
-                OutRec o; o.h_r = s.r_arr; o.d_r = d_r; o.h_np = s.new_pts; o.d_np = d_np; o.rbytes = rbytes; o.wbytes = wbytes;
-                outs.push_back(o);
-            } else {
-                p.r_arr = s.r_arr; p.valid = s.valid_mask; p.new_pts = s.new_pts;
-            }
+        sel.push_back(g);
+        count += (int)groups[g].size();
+        if (count >= chunk_slabs || g == njobs - 1) {
+            WPS_TRY(run_groups(h, fs, sel, h->s_in, h->s_out, g == njobs - 1));
+            sel.clear();
+            count = 0;
         }
     }
-    Job* d_jobs = (Job*)h->arena.take(sizeof(Job) * njobs);
-    SlabPtrs* d_sp = (SlabPtrs*)h->arena.take(sizeof(SlabPtrs) * nq);
-    int* d_cls = (int*)h->arena.take(sizeof(int) * 5 * (njobs + 1));
-    WPS_CHECK(d_jobs && d_sp && d_cls, -3, "device arena exhausted (tables)");
-    WPS_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(Job) * njobs, cudaMemcpyHostToDevice, h->stream));
-    WPS_CUDA(cudaMemcpyAsync(d_sp, sp.data(), sizeof(SlabPtrs) * nq, cudaMemcpyHostToDevice, h->stream));
-    int* d_cls_jobs[2]; int* d_cls_tile0[2];
-    for (int c = 0; c < 2; ++c) {
-        d_cls_jobs[c] = d_cls + (2 * c) * (njobs + 1);
-        d_cls_tile0[c] = d_cls + (2 * c + 1) * (njobs + 1);
-        if (!cls_jobs[c].empty()) {
-            WPS_CUDA(cudaMemcpyAsync(d_cls_jobs[c], cls_jobs[c].data(), sizeof(int) * cls_jobs[c].size(), cudaMemcpyHostToDevice, h->stream));
-            WPS_CUDA(cudaMemcpyAsync(d_cls_tile0[c], cls_tile0[c].data(), sizeof(int) * cls_tile0[c].size(), cudaMemcpyHostToDevice, h->stream));
-        }
-    }
-    int* d_fast_word0 = d_cls + 4 * (njobs + 1);
-    WPS_CHECK(fast_words < 2000000000LL, -3, "too many output words in one flush");
-    if (!fast_word0.empty()) WPS_CUDA(cudaMemcpyAsync(d_fast_word0, fast_word0.data(), sizeof(int) * fast_word0.size(), cudaMemcpyHostToDevice, h->stream));
-    Deferred *d_def = nullptr, *d_def2 = nullptr;
-    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(h->d_counters);
-    if (any_search) {
-        d_def = (Deferred*)h->arena.take(sizeof(Deferred) * defer_cursor);
-        d_def2 = (Deferred*)h->arena.take(sizeof(Deferred) * defer_cursor);
-        WPS_CHECK(d_def && d_def2, -3, "device arena exhausted (deferred lists)");
-        WPS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), h->stream));
-    }
-
-    // ---- launches ----
-    dim3 block(TILE_X, TILE_Y);
-    WPS_CUDA(cudaEventRecord(h->ev_t[0], h->stream));
-    for (int g : cls_jobs[1]) {
-        const Job& jb = jobs[g];
-        if (jb.fast != 1) continue;
-        k_pack16<<<dim3((jb.bnx * jb.bny + 255) / 256, jb.npack), 256, 0, h->stream>>>(d_jobs, g, d_sp);
-        h->launches++;
-    }
-    WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
-    WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
-    for (int g : cls_jobs[1]) {
-        if (jobs[g].fast != 1) continue;
-        FastParams fp;
-        fp.jb = jobs[g];
-        for (int k = 0; k < fp.jb.nslab; ++k) {
-            const SlabPtrs& p = sp[fp.jb.slab0 + k];
-            fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
-        }
-        k_metgrid_fast16<<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
-        h->launches++;
-    }
-    WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
-    WPS_CUDA(cudaEventRecord(h->ev_t[6], h->stream));
-    for (int g : cls_jobs[1]) {
-        if (jobs[g].fast < 2) continue;
-        Fast4Params fp;
-        fp.jb = jobs[g];
-        for (int k = 0; k < fp.jb.nslab; ++k) {
-            const SlabPtrs& p = sp[fp.jb.slab0 + k];
-            fp.src[k] = p.src; fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
-        }
-        if (jobs[g].fast == 2) k_metgrid_fast4<WPSGPU_FOUR_POINT><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
-        else k_metgrid_fast4<WPSGPU_N_NEIGHBOR><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
-        h->launches++;
-    }
-    WPS_CUDA(cudaEventRecord(h->ev_t[7], h->stream));
-    if (tile_cursor[1] > 0) {
-        k_metgrid_slowbits<<<(unsigned)((fast_words + 127) / 128), 128, 0, h->stream>>>(d_jobs, d_cls_jobs[1], d_fast_word0, (int)cls_jobs[1].size(), d_sp, d_def, d_cnt, fast_words);
-        h->launches++;
-    }
-    WPS_CUDA(cudaEventRecord(h->ev_t[4], h->stream));
-    if (tile_cursor[0] > 0) {
-        k_metgrid_interp<<<tile_cursor[0], block, 0, h->stream>>>(d_jobs, d_cls_jobs[0], d_cls_tile0[0], (int)cls_jobs[0].size(), d_sp, d_def, d_cnt);
-        h->launches++;
-    }
-    WPS_CUDA(cudaEventRecord(h->ev_t[5], h->stream));
-    WPS_CUDA(cudaGetLastError());
-    h->last_pts3[0] = fast16_points; h->last_pts3[1] = fast16_points; h->last_pts3[2] = cls_points[0]; h->last_pts3[3] = fast4_points;
-    // the dominant kernel for the roofline line: whichever main kernel produced more outputs
-    {
-        int dom = fast16_points >= cls_points[0] ? 1 : 2;
-        cudaEvent_t t0 = h->ev_t[2 * dom], t1 = h->ev_t[2 * dom + 1];
-        h->ev_k0 = t0; h->ev_k1 = t1;
-        h->last_points = dom == 1 ? fast16_points : cls_points[0];
-    }
-    if (any_search) {
-        int sblocks = h->sm_count * 8;
-        k_metgrid_search<<<sblocks, 256, 0, h->stream>>>(d_jobs, njobs, d_sp, d_def, d_cnt, d_def2, d_cnt + 1);
-        h->launches++;
-        WPS_CUDA(cudaGetLastError());
-        // literal fallback: few threads, big per-thread scratch
-        int R = std::min(std::max(max_depth, 1), std::max(max_span, 1));
-        size_t vis_words = ((size_t)(2 * R + 1) * (2 * R + 1) + 31) / 32;
-        int qcap = 8 * R + 64;
-        size_t words_per_thread = ((vis_words + 1) & ~size_t(1)) + (size_t)qcap * sizeof(QNode) / sizeof(unsigned);
-        int lit_threads = 256;
-        size_t bytes = words_per_thread * sizeof(unsigned) * lit_threads;
-        if (bytes > h->search_scratch_bytes) {
-            WPS_CUDA(cudaStreamSynchronize(h->stream));
-            if (h->d_search_scratch) cudaFree(h->d_search_scratch);
-            WPS_CUDA(cudaMalloc(&h->d_search_scratch, bytes));
-            h->search_scratch_bytes = bytes;
-        }
-        k_metgrid_search_literal<<<lit_threads / 64, 64, 0, h->stream>>>(d_jobs, njobs, d_sp, d_def2, d_cnt + 1,
-                                                                      (unsigned*)h->d_search_scratch, words_per_thread, R, qcap);
-        h->launches++;
-        WPS_CUDA(cudaGetLastError());
-    }
-    if (host) {
-        for (const OutRec& o : outs) {
-            WPS_TRY(copy_out(h, o.h_r, o.d_r, o.rbytes));
-            WPS_TRY(copy_out(h, o.h_np, o.d_np, o.wbytes));
-        }
-        WPS_CUDA(cudaStreamSynchronize(h->stream));
-    }
+    WPS_CUDA(cudaStreamSynchronize(h->s_out));
+    WPS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
