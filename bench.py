@@ -316,7 +316,7 @@ def run_b200(args, rank, world, local_rank):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "kernel": "k_metgrid_fast16" if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
                              "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
-                             "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5]},
+                             "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
                              "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},

@@ -152,10 +152,10 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h);
 /* Device time (CUDA events on the handle's stream) of the dominant kernel of the last flush and the number of
  * (slab x destination point) outputs it produced -- for roofline reporting only. */
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);
-/* Same, broken down (arrays of 6): [0] packing pre-pass, [1] packed sixteen_pt kernel, [2] generic kernel,
+/* Same, broken down (arrays of 7): [0] packing pre-pass, [1] packed sixteen_pt kernel, [2] generic kernel,
  * [3] four_pt / nearest_neighbor first-method kernels, [4] slow-bitmap pass (points the first-method kernels handed
- * back to the full fallback chain), [5] deferred search passes. */
-int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms6, double *points6);
+ * back to the full fallback chain), [5] deferred search passes, [6] first launch to last kernel of the flush. */
+int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms7, double *points7);
 /* Testing aid: disable!=0 routes every job through the generic kernel (used to test both kernels against the oracle). */
 int wpsgpu_debug_disable_fast(wpsgpu_handle_t h, int disable);
 /* The average_gcell branch (:2331-2478) with metgrid's accum_continuous (:3347-3717); dom_proj is the

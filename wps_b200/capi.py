@@ -294,8 +294,8 @@ class Handle:
         return ms.value, pts.value
 
     def metgrid_last_timings(self):
-        ms = (C.c_float * 6)()
-        pts = (C.c_double * 6)()
+        ms = (C.c_float * 7)()
+        pts = (C.c_double * 7)()
         check(lib().wpsgpu_metgrid_last_timings(self._h, ms, pts))
         return list(ms), list(pts)
 

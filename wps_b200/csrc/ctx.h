@@ -46,6 +46,14 @@ struct Arena {
         off = a + bytes;
         return base + a;
     }
+    // continue the previous block without alignment padding (lets neighbouring host arrays be copied in one piece)
+    void* take_tail(size_t bytes)
+    {
+        if (off + bytes > cap) return nullptr;
+        off += bytes;
+        return base + off - bytes;
+    }
+    char* tail() const { return base + off; }
     void reset() { off = 0; }
     void release();
 };

@@ -1,5 +1,6 @@
 // metgrid.cu -- batched replacement of metgrid's interp_met_field (process_domain_module.F:2205-2669):
 // coordinate cache, one launch over (destination tile x slab group), deferred search passes.
+#include <chrono>
 #include <algorithm>
 #include <climits>
 #include "ctx.h"
@@ -207,11 +208,12 @@ __global__ void k_xy_bbox(const float2* __restrict__ xy, int64_t n, int* __restr
 // sub-terms of oned (:1370): t1=0.5*(c-a), t2=0.5*(c+a)-b, t3=0.5*(b-d), t4=0.5*(b+d)-c, evaluated in the
 // reference's operation order.  cf bit lv says the whole 4x4 stencil anchored at (i,jj) has no missing value
 // and takes oned's general branch in the x direction (b*c /= 0 and a*d /= 0 in all four rows).
-__global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, int job_idx, const SlabPtrs* __restrict__ slabs)
+// One launch covers every packed job of the flush: blockIdx.z picks the job, blockIdx.y the pack of 4 levels.
+__global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, const int* __restrict__ pack_jobs, const SlabPtrs* __restrict__ slabs)
 {
-    const Job& jb = jobs[job_idx];
+    const Job& jb = jobs[pack_jobs[blockIdx.z]];
     int cell = blockIdx.x * blockDim.x + threadIdx.x, pack = blockIdx.y;
-    if (cell >= jb.bnx * jb.bny) return;
+    if (pack >= jb.npack || cell >= jb.bnx * jb.bny) return;
     int ci = cell % jb.bnx, cj = cell / jb.bnx;
     int i = jb.bx0 + ci, jj = jb.by0 + cj;
     const int sx = jb.minx, ex = jb.maxx, sy = jb.miny, ey = jb.maxy, snx = ex - sx + 1;
@@ -653,6 +655,15 @@ static std::string cache_key(int grid_id, const wpsgpu_proj& p)
     return k;
 }
 
+// tuning knobs of the host-pointer pipeline (slabs per job group / per pipeline stage)
+static int env_int(const char* name, int dflt, int lo, int hi)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
 static int rel_code(char c) { return c == '<' ? REL_LT : (c == '>' ? REL_GT : REL_EQ); }
 
 static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
@@ -780,6 +791,8 @@ int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float* ms3, double* points3)
         WPS_CUDA(cudaEventElapsedTime(&ms3[k], h->ev_t[2 * k], h->ev_t[2 * k + 1]));
         points3[k] = h->last_pts3[k];
     }
+    WPS_CUDA(cudaEventElapsedTime(&ms3[6], h->ev_t[0], h->ev_t[11]));   // first launch to last kernel of the flush
+    points3[6] = h->last_pts3[4] + h->last_pts3[2];
     return 0;
 }
 
@@ -804,22 +817,38 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     const int njobs = (int)gsel.size();
     int nq = 0;
     for (int g : gsel) nq += (int)groups[g].size();
+    // Host-pointer mode moves data in as few, as large copies as possible: arrays that follow one another in host memory
+    // (the levels of a 3-d field) are placed back to back on the device and travel as one piece -- with copies running in
+    // both directions, slab-sized pieces reach 37 GB/s per direction on this platform and 60+ MB pieces 49 GB/s
+    // (tools/pcie_bw.py).
+    struct CopyRun { const char* h; char* d; size_t bytes; };
+    std::vector<CopyRun> in_runs, out_r_runs, out_np_runs;
+    auto take_run = [&](std::vector<CopyRun>& runs, const void* hp, size_t bytes) -> void* {
+        if (!runs.empty()) {
+            CopyRun& r = runs.back();
+            if (r.h + r.bytes == (const char*)hp && r.d + r.bytes == h->arena.tail()) {
+                void* d = h->arena.take_tail(bytes);
+                if (d) r.bytes += bytes;
+                return d;
+            }
+        }
+        void* d = h->arena.take(bytes);
+        if (d) { CopyRun r; r.h = (const char*)hp; r.d = (char*)d; r.bytes = bytes; runs.push_back(r); }
+        return d;
+    };
     auto stage_shared = [&](const float* p, size_t bytes, const float** out) -> int {
         if (!p) { *out = nullptr; return 0; }
         if (!host) { *out = p; return 0; }
         auto it = fs.staged.find(p);
         if (it != fs.staged.end()) { *out = (const float*)it->second; return 0; }
-        void* d = h->arena.take(bytes);
+        void* d = take_run(in_runs, p, bytes);
         WPS_CHECK(d != nullptr, -3, "device arena exhausted (%zu bytes requested)", bytes);
-        WPS_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s_in));
         fs.staged[p] = d;
         *out = (const float*)d;
         return 0;
     };
     std::vector<Job> jobs(njobs);
     std::vector<SlabPtrs> sp(nq);
-    struct OutRec { float* h_r; void* d_r; int* h_np; void* d_np; size_t rbytes, wbytes; };
-    std::vector<OutRec> outs;
     std::vector<int> cls_jobs[2], cls_tile0[2];  // 0 = generic kernel, 1 = first-method kernels
     std::vector<int> fast_word0;
     long long fast_words = 0;
@@ -880,32 +909,51 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         jb.defer_base = defer_cursor;
         if (has_search) { defer_cursor += (unsigned long long)dg.npts() * groups[g].size(); any_search = true; }
         size_t rbytes = dg.npts() * sizeof(float), wbytes = (size_t)jb.ny * jb.nxw * sizeof(int);
-        for (int a : groups[g]) {
-            const wpsgpu_slab& s = queue[a].s;
-            SlabPtrs& p = sp[slab_cursor++];
-            p.slow = nullptr; p.pad_ = nullptr;
-            if (jb.fast) { p.slow = (int*)h->arena.take(wbytes); WPS_CHECK(p.slow != nullptr, -3, "device arena exhausted (slow bitmaps)"); }
-            WPS_TRY(stage_shared(s.slab, sbytes, &p.src));
-            if (host) {
-                void* d_r = h->arena.take(rbytes); void* d_np = h->arena.take(wbytes); void* d_v = nullptr;
-                WPS_CHECK(d_r && d_np, -3, "device arena exhausted (outputs)");
-                if (s.valid_mask) {  // r_arr carries lower-priority data only where valid bits are set
-                    d_v = h->arena.take(wbytes);
-                    WPS_CHECK(d_v != nullptr, -3, "device arena exhausted (valid mask)");
-                    WPS_CUDA(cudaMemcpyAsync(d_r, s.r_arr, rbytes, cudaMemcpyHostToDevice, s_in));
-                    WPS_CUDA(cudaMemcpyAsync(d_v, s.valid_mask, wbytes, cudaMemcpyHostToDevice, s_in));
-                }
-                p.r_arr = (float*)d_r; p.valid = (const int*)d_v; p.new_pts = (int*)d_np;
-                OutRec o; o.h_r = s.r_arr; o.d_r = d_r; o.h_np = s.new_pts; o.d_np = d_np; o.rbytes = rbytes; o.wbytes = wbytes;
-                outs.push_back(o);
-            } else {
-                p.r_arr = s.r_arr; p.valid = s.valid_mask; p.new_pts = s.new_pts;
+        const std::vector<int>& grp = groups[g];
+        const int ns = (int)grp.size(), s0 = slab_cursor;
+        slab_cursor += ns;
+        // one pass per kind of array, so that the arrays of neighbouring levels end up next to each other
+        for (int k = 0; k < ns; ++k) {
+            SlabPtrs& p = sp[s0 + k];
+            p.slow = nullptr; p.pad_ = nullptr; p.valid = nullptr;
+            WPS_TRY(stage_shared(queue[grp[k]].s.slab, sbytes, &p.src));
+        }
+        if (jb.fast)
+            for (int k = 0; k < ns; ++k) {
+                sp[s0 + k].slow = (int*)h->arena.take(wbytes);
+                WPS_CHECK(sp[s0 + k].slow != nullptr, -3, "device arena exhausted (slow bitmaps)");
+            }
+        if (host) {
+            for (int k = 0; k < ns; ++k) {
+                const wpsgpu_slab& s = queue[grp[k]].s;
+                sp[s0 + k].r_arr = (float*)take_run(out_r_runs, s.r_arr, rbytes);
+                WPS_CHECK(sp[s0 + k].r_arr != nullptr, -3, "device arena exhausted (outputs)");
+            }
+            for (int k = 0; k < ns; ++k) {
+                const wpsgpu_slab& s = queue[grp[k]].s;
+                sp[s0 + k].new_pts = (int*)take_run(out_np_runs, s.new_pts, wbytes);
+                WPS_CHECK(sp[s0 + k].new_pts != nullptr, -3, "device arena exhausted (outputs)");
+            }
+            for (int k = 0; k < ns; ++k) {
+                const wpsgpu_slab& s = queue[grp[k]].s;
+                if (!s.valid_mask) continue;   // r_arr carries lower-priority data only where valid bits are set
+                void* d_v = h->arena.take(wbytes);
+                WPS_CHECK(d_v != nullptr, -3, "device arena exhausted (valid mask)");
+                WPS_CUDA(cudaMemcpyAsync(sp[s0 + k].r_arr, s.r_arr, rbytes, cudaMemcpyHostToDevice, s_in));
+                WPS_CUDA(cudaMemcpyAsync(d_v, s.valid_mask, wbytes, cudaMemcpyHostToDevice, s_in));
+                sp[s0 + k].valid = (const int*)d_v;
+            }
+        } else {
+            for (int k = 0; k < ns; ++k) {
+                const wpsgpu_slab& s = queue[grp[k]].s;
+                sp[s0 + k].r_arr = s.r_arr; sp[s0 + k].valid = s.valid_mask; sp[s0 + k].new_pts = s.new_pts;
             }
         }
     }
+    for (const CopyRun& r : in_runs) WPS_CUDA(cudaMemcpyAsync(r.d, r.h, r.bytes, cudaMemcpyHostToDevice, s_in));
     Job* d_jobs = (Job*)h->arena.take(sizeof(Job) * njobs);
     SlabPtrs* d_sp = (SlabPtrs*)h->arena.take(sizeof(SlabPtrs) * nq);
-    int* d_cls = (int*)h->arena.take(sizeof(int) * 5 * (njobs + 1));
+    int* d_cls = (int*)h->arena.take(sizeof(int) * 6 * (njobs + 1));
     WPS_CHECK(d_jobs && d_sp && d_cls, -3, "device arena exhausted (tables)");
     WPS_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(Job) * njobs, cudaMemcpyHostToDevice, s_in));
     WPS_CUDA(cudaMemcpyAsync(d_sp, sp.data(), sizeof(SlabPtrs) * nq, cudaMemcpyHostToDevice, s_in));
@@ -919,6 +967,17 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         }
     }
     int* d_fast_word0 = d_cls + 4 * (njobs + 1);
+    int* d_pack_jobs = d_cls + 5 * (njobs + 1);
+    std::vector<int> pack_jobs;
+    int pack_cells = 0, pack_max = 0;
+    for (int j : cls_jobs[1])
+        if (jobs[j].fast == 1) {
+            pack_jobs.push_back(j);
+            pack_cells = std::max(pack_cells, jobs[j].bnx * jobs[j].bny);
+            pack_max = std::max(pack_max, jobs[j].npack);
+        }
+    WPS_CHECK(pack_jobs.size() < 65536, -3, "too many packed jobs in one flush");
+    if (!pack_jobs.empty()) WPS_CUDA(cudaMemcpyAsync(d_pack_jobs, pack_jobs.data(), sizeof(int) * pack_jobs.size(), cudaMemcpyHostToDevice, s_in));
     WPS_CHECK(fast_words < 2000000000LL, -3, "too many output words in one flush");
     if (!fast_word0.empty()) WPS_CUDA(cudaMemcpyAsync(d_fast_word0, fast_word0.data(), sizeof(int) * fast_word0.size(), cudaMemcpyHostToDevice, s_in));
     Deferred *d_def = nullptr, *d_def2 = nullptr;
@@ -938,10 +997,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     // ---- launches ----
     dim3 block(TILE_X, TILE_Y);
     WPS_CUDA(cudaEventRecord(h->ev_t[0], h->stream));
-    for (int j : cls_jobs[1]) {
-        const Job& jb = jobs[j];
-        if (jb.fast != 1) continue;
-        k_pack16<<<dim3((jb.bnx * jb.bny + 255) / 256, jb.npack), 256, 0, h->stream>>>(d_jobs, j, d_sp);
+    if (!pack_jobs.empty()) {
+        k_pack16<<<dim3((pack_cells + 255) / 256, pack_max, (unsigned)pack_jobs.size()), 256, 0, h->stream>>>(d_jobs, d_pack_jobs, d_sp);
         h->launches++;
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
@@ -1023,10 +1080,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             WPS_CUDA(cudaEventRecord(h->ev_done, h->stream));
             WPS_CUDA(cudaStreamWaitEvent(s_out, h->ev_done, 0));
         }
-        for (const OutRec& o : outs) {
-            WPS_CUDA(cudaMemcpyAsync(o.h_r, o.d_r, o.rbytes, cudaMemcpyDeviceToHost, s_out));
-            WPS_CUDA(cudaMemcpyAsync(o.h_np, o.d_np, o.wbytes, cudaMemcpyDeviceToHost, s_out));
-        }
+        for (const CopyRun& r : out_r_runs) WPS_CUDA(cudaMemcpyAsync((void*)r.h, r.d, r.bytes, cudaMemcpyDeviceToHost, s_out));
+        for (const CopyRun& r : out_np_runs) WPS_CUDA(cudaMemcpyAsync((void*)r.h, r.d, r.bytes, cudaMemcpyDeviceToHost, s_out));
     }
     return 0;
 }
@@ -1043,7 +1098,7 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
 
     // ---- group slabs into jobs (stable: first-appearance order) ----
     // host-pointer mode keeps the groups short so that copies and kernels of neighbouring groups overlap
-    const int group_cap = host ? 16 : FAST_MAX_SLABS;
+    const int group_cap = host ? env_int("WPSGPU_PIPE_GROUP", 16, 1, FAST_MAX_SLABS) : FAST_MAX_SLABS;
     std::vector<std::vector<int>> groups;
     for (int a = 0; a < nq; ++a) {
         bool placed = false;
@@ -1157,7 +1212,14 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     // everything previously enqueued on the handle's stream (set_grid copies, earlier calls) precedes the new copies
     WPS_CUDA(cudaEventRecord(h->ev_done, h->stream));
     WPS_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
-    const int chunk_slabs = 12;
+    const bool trace = env_int("WPSGPU_PIPE_TRACE", 0, 0, 1) != 0;   // print where the pipeline's time goes
+    cudaEvent_t tr[4] = { nullptr, nullptr, nullptr, nullptr };
+    const auto host_t0 = std::chrono::steady_clock::now();
+    if (trace) {
+        for (int k = 0; k < 4; ++k) WPS_CUDA(cudaEventCreate(&tr[k]));
+        WPS_CUDA(cudaEventRecord(tr[0], h->s_in));
+    }
+    const int chunk_slabs = env_int("WPSGPU_PIPE_CHUNK", 12, 1, 1 << 20);
     std::vector<int> sel;
     int count = 0;
     for (int g = 0; g < njobs; ++g) {
@@ -1169,8 +1231,20 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
             count = 0;
         }
     }
+    const double issue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+    if (trace) {
+        WPS_CUDA(cudaEventRecord(tr[1], h->s_in));
+        WPS_CUDA(cudaEventRecord(tr[2], h->stream));
+        WPS_CUDA(cudaEventRecord(tr[3], h->s_out));
+    }
     WPS_CUDA(cudaStreamSynchronize(h->s_out));
     WPS_CUDA(cudaStreamSynchronize(h->stream));
+    if (trace) {
+        float a = 0.0f, b = 0.0f, c = 0.0f;
+        cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[0], tr[2]); cudaEventElapsedTime(&c, tr[0], tr[3]);
+        fprintf(stderr, "[wpsgpu] pipeline: %d groups, host issue %.2f ms, H2D done %.2f ms, kernels done %.2f ms, D2H done %.2f ms\n", njobs, issue_ms, a, b, c);
+        for (int k = 0; k < 4; ++k) cudaEventDestroy(tr[k]);
+    }
     return 0;
 }
 
