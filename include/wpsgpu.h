@@ -159,7 +159,13 @@ int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms7, double *points7);
 /* Testing aid: disable!=0 routes every job through the generic kernel (used to test both kernels against the oracle). */
 int wpsgpu_debug_disable_fast(wpsgpu_handle_t h, int disable);
 /* The average_gcell branch (:2331-2478) with metgrid's accum_continuous (:3347-3717); dom_proj is the
- * projection set_domain_projection built (llxy_module.F:191).  Executes immediately. */
+ * projection set_domain_projection built (llxy_module.F:191).  The caller decides per slab whether the branch
+ * applies (do_gcell_interp, :1198-1220).  Cell sums are accumulated in binary64 and rounded once (the reference adds
+ * in binary32 in quadtree order), so cell averages agree to ~1e-7 relative rather than bit for bit; everything else
+ * (which cells receive data, the fallback chain for the others, new_pts) is exact.
+ * enqueue_gcell_slab queues the call for the next wpsgpu_metgrid_flush; gcell_slab queues it and flushes. */
+int wpsgpu_metgrid_enqueue_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj *src_proj, const wpsgpu_proj *dom_proj,
+                                      const wpsgpu_field_opts *fo, const wpsgpu_slab *slab);
 int wpsgpu_metgrid_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj *src_proj, const wpsgpu_proj *dom_proj,
                               const wpsgpu_field_opts *fo, const wpsgpu_slab *slab);
 

@@ -326,3 +326,60 @@ def test_enqueue_slabs_batched_entry(orc, handle):
         handle.metgrid_enqueue_slabs(gsrc, fo_g, bad)
     handle.metgrid_flush()
     assert (r[0] == -7.0).all()
+
+
+GCELL_RTOL = 1e-6   # cell averages: binary64 sums rounded once vs the reference's binary32 running sum (north_star tolerance)
+
+
+@pytest.mark.parametrize("case", ["plain", "missing+mask", "mask<", "landmask", "valid+bdy"])
+def test_average_gcell_branch(orc, handle, case):
+    """average_gcell branch of interp_met_field (process_domain_module.F:2331-2478 + accum_continuous :3347-3717): a
+    regional 0.1-degree source over part of a 60-km Lambert domain -- cells covered by source pixels get the cell average,
+    the others fall through to the interpolation chain."""
+    from wps_b200 import capi
+    nx, ny = 48, 40
+    orc.set_transc_mode(1)
+    odom, gdom = conus_like(nx, ny, 60000.0, truelat1=30.0, truelat2=60.0, stand_lon=-98.0, ref_lat=34.83, ref_lon=-81.03)
+    xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, nx, ny, orc.M)
+    snx, sny = 300, 250
+    osrc, gsrc = latlon_source(snx, sny, -0.1, 0.1, 50.0, -110.0)
+    rng = np.random.default_rng(11)
+    jj, ii = np.mgrid[0:sny, 0:snx]
+    slab = (280.0 + 10.0 * np.sin(ii / 17.0) * np.cos(jj / 13.0) + rng.uniform(-0.5, 0.5, (sny, snx))).astype(np.float32)
+    kw = dict(mask=None, landmask=None, process_bdy_width=0, r_arr=None, valid_mask=None)
+    msg, fill, masked, mval, rel = np.float32(-1e30), np.float32(0.0), -2.0, 1e20, " "
+    if case != "plain":
+        slab[rng.random(slab.shape) < 0.1] = msg
+    if case in ("missing+mask", "mask<"):
+        kw["mask"] = (np.sin(ii / 9.0) + np.cos(jj / 7.0) > 0.2).astype(np.float32)
+        mval, rel = (1.0, " ") if case == "missing+mask" else (0.5, "<")
+    if case == "landmask":
+        kw["landmask"] = (rng.random((ny, nx)) < 0.7).astype(np.float32)
+        masked, fill = 0.0, np.float32(-5.0)
+    if case == "valid+bdy":
+        kw["r_arr"] = rng.uniform(200, 300, (ny, nx)).astype(np.float32)
+        kw["valid_mask"] = bool_to_bits(rng.random((ny, nx)) < 0.5)
+        kw["process_bdy_width"] = 6
+        fill = np.float32(1e20)
+    chain = "average_gcell(4.0)+four_pt+average_4pt"
+    fo_o = orc.field_opts(chain, msg, fill, masked, (mval, 1e20, 1e20), rel + "  ")
+    fo_g = capi.field_opts(chain, msg, fill, masked, (mval, 1e20, 1e20), rel + "  ")
+    r_ref, np_ref = orc.interp_met_field_gcell(osrc, odom, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), slab, 1, 1, 0,
+                                               mask=kw["mask"], landmask=kw["landmask"], process_bdy_width=kw["process_bdy_width"],
+                                               r_arr=None if kw["r_arr"] is None else kw["r_arr"].copy(), valid_mask=kw["valid_mask"])
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    if kw["landmask"] is not None:
+        handle.metgrid_set_landmask(0, kw["landmask"])
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    r = np.zeros((ny, nx), np.float32) if kw["r_arr"] is None else kw["r_arr"].copy()
+    npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+    handle.metgrid_enqueue_gcell_slab(gsrc, gdom, fo_g, slab, 1, 1, 0, 0, capi.M, r, npw, valid_mask=kw["valid_mask"],
+                                      mask=kw["mask"], use_landmask=kw["landmask"] is not None,
+                                      process_bdy_width=kw["process_bdy_width"])
+    handle.metgrid_flush()
+    assert (npw == np_ref).all(), "new_pts differ: %d words" % (npw != np_ref).sum()
+    assert np.isfinite(r).all()
+    np.testing.assert_allclose(r, r_ref, rtol=GCELL_RTOL, atol=0.0)
+    # the branch did something: a good share of the cells are averages, and some cells fell through to the chain
+    covered = bits_to_bool(npw, nx).mean()
+    assert 0.2 < covered <= 1.0

@@ -284,6 +284,13 @@ class Handle:
         s.new_pts = ptr(new_pts)
         check(lib().wpsgpu_metgrid_enqueue_slab(self._h, C.byref(proj), C.byref(fo), C.byref(s)))
 
+    def metgrid_enqueue_gcell_slab(self, proj, dom_proj, fo, slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts,
+                                   valid_mask=None, mask=None, use_landmask=False, process_bdy_width=0):
+        """average_gcell branch of interp_met_field (process_domain_module.F:2331-2478); results after metgrid_flush."""
+        s = self.slab_desc(slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts, valid_mask=valid_mask,
+                           masks=(mask, None, None), use_landmask=use_landmask, process_bdy_width=process_bdy_width)
+        check(lib().wpsgpu_metgrid_enqueue_gcell_slab(self._h, C.byref(proj), C.byref(dom_proj), C.byref(fo), C.byref(s)))
+
     def metgrid_flush(self):
         check(lib().wpsgpu_metgrid_flush(self._h))
 

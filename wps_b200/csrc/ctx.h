@@ -80,6 +80,8 @@ struct QueuedSlab {
     wpsgpu_proj proj;
     wpsgpu_field_opts fo;
     wpsgpu_slab s;
+    bool gcell = false;      // average_gcell branch: cell averages first, the chain for cells no source pixel reached
+    wpsgpu_proj dom_proj;    // projection of the destination domain (gcell only)
 };
 
 struct GeoState;  // geogrid.cu

@@ -557,12 +557,4 @@ int wpsgpu_geogrid_field_finish(wpsgpu_handle_t h, int32_t* processed_domain_out
     return 0;
 }
 
-int wpsgpu_metgrid_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, const wpsgpu_proj* dom_proj,
-                              const wpsgpu_field_opts* fo, const wpsgpu_slab* slab)
-{
-    (void)src_proj; (void)dom_proj; (void)fo; (void)slab;
-    WPS_CHECK(h != nullptr, -1, "NULL handle");
-    WPS_CHECK(false, -40, "wpsgpu_metgrid_gcell_slab: metgrid average_gcell (process_domain_module.F:2331-2478) is not implemented yet");
-}
-
 }  // extern "C"

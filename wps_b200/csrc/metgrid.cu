@@ -34,6 +34,7 @@ struct Job {
     const float4* rec;           // [npack][bny][bnx][6] = {b, c, t1, t2, t3, t4} x 4 packed levels
     const unsigned char* cf;     // [npack][bny][bnx] bit lv = 4x4 stencil anchored here is "clean" for level lv
     float f_negzero, f_one;      // -0.0f and 1.0f as run-time values (see mul2/add2 in the packed kernel)
+    int gcell;                   // average_gcell branch (:2331-2478): masked=both is not special there
 };
 
 struct SlabPtrs {
@@ -42,7 +43,7 @@ struct SlabPtrs {
     const int* valid;
     int* new_pts;
     int* slow;      // packed sixteen_pt path: bit set = this (slab, point) must go through the generic operators
-    int* pad_;
+    const int* decided;  // average_gcell: bit set = r_arr already holds the cell average (:2393-2400)
 };
 
 
@@ -105,7 +106,7 @@ __device__ __forceinline__ int process_point(const Job& jb, const float* __restr
     const bool has_lm = jb.landmask != nullptr;
     if (has_lm) {
         lm = __ldg(jb.landmask + idx);
-        if (jb.masked == WPSGPU_MASKED_BOTH) {
+        if (jb.masked == WPSGPU_MASKED_BOTH && !jb.gcell) {
             if (lm == 0.0f) sel = 1;        // water point: interp_land_mask
             else if (lm == 1.0f) sel = 2;   // land point: interp_water_mask
             else do_interp = false;         // reference leaves `temp` stale here; we define it as missing_value
@@ -170,7 +171,8 @@ k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs,
         if (active) {
             bool vbit = false;
             if (sp.valid) vbit = (__ldg(sp.valid + widx) >> threadIdx.x) & 1;
-            flags = process_point<0>(jb, sp.src, i, j, idx, xy, vbit, out);
+            if (sp.decided && ((__ldg(sp.decided + widx) >> threadIdx.x) & 1)) flags = PF_BIT;   // cell average already stored
+            else flags = process_point<0>(jb, sp.src, i, j, idx, xy, vbit, out);
             if (flags & PF_DEFER) {
                 unsigned long long slot = atomicAdd(defer_count, 1ull);
                 Deferred d; d.slab = jb.slab0 + sl; d.idx = (int)idx;
@@ -182,6 +184,86 @@ k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs,
     }
 }
 
+
+// ---- average_gcell (process_domain_module.F:2331-2478, accum_continuous :3347-3717) ------------------
+// where_maps_to of every source cell: xytoll with the source projection, lltoxy with the domain's, the (unit)
+// sub-grid scaling of :3448-3449, the inside test and nint (:3441-3461).
+#define GC_OUTSIDE 100000000  // OUTSIDE_DOMAIN, misc_definitions_module.F:18
+__global__ void k_gc_wm(DevProj src, DevProj dom, int minx, int miny, int snx, int sny, int sm1, int em1, int sm2, int em2,
+                        int2* __restrict__ wm)
+{
+    int ti = blockIdx.x * blockDim.x + threadIdx.x, tj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ti >= snx || tj >= sny) return;
+    float lat, lon, rx, ry;
+    xytoll(src, (float)(minx + ti), (float)(miny + tj), lat, lon, WPSGPU_M);
+    lltoxy(dom, lat, lon, rx, ry, WPSGPU_M);
+    rx = (rx - 0.5f) * 1.0f + 0.5f;
+    ry = (ry - 0.5f) * 1.0f + 0.5f;
+    int2 w;
+    if ((float)sm1 <= rx && rx <= (float)em1 && (float)sm2 <= ry && ry <= (float)em2) { w.x = f_nint(rx); w.y = f_nint(ry); }
+    else { w.x = GC_OUTSIDE; w.y = 0; }
+    wm[(size_t)tj * snx + ti] = w;
+}
+
+// One thread per source cell of the block [minx+bdr, maxx-bdr] x [miny, maxy] (:2351-2375): walk the quadtree of
+// process_continuous_block top-down (:3519-3525 four-corner shortcut, :3597 2x2 leaf) to find the domain cell this
+// source cell is credited to, then add its value unless it is missing or masked (:3542-3592).  The reference sums in
+// binary32 in traversal order; here the sum is accumulated in binary64 (order-independent to ~1e-16) and rounded once.
+__global__ void k_gc_accum(const int2* __restrict__ wm, const float* __restrict__ slab, const float* __restrict__ mask,
+                           int rel, float maskval, float msg, int minx, int maxx, int miny, int maxy, int bdr,
+                           int sm1, int sm2, int nx, double* __restrict__ sum, int* __restrict__ cnt)
+{
+    const int I0 = minx + bdr, I1 = maxx - bdr, J0 = miny, J1 = maxy, snx = maxx - minx + 1;
+    int pi = I0 + blockIdx.x * blockDim.x + threadIdx.x, pj = J0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (pi > I1 || pj > J1) return;
+    auto W = [&](int i, int j) { return wm[(size_t)(j - miny) * snx + (i - minx)]; };
+    int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
+    int2 dest;
+    for (;;) {
+        int2 a = W(min_i, min_j), b = W(min_i, max_j), c = W(max_i, max_j), d = W(max_i, min_j);
+        if (a.x == b.x && a.x == c.x && a.x == d.x && a.y == b.y && a.y == c.y && a.y == d.y && a.x != GC_OUTSIDE) { dest = a; break; }
+        if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = W(pi, pj); break; }
+        int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
+        if (pi <= ci) max_i = ci; else min_i = ci + 1;
+        if (pj <= cj) max_j = cj; else min_j = cj + 1;
+    }
+    if (dest.x == GC_OUTSIDE) return;
+    size_t o = (size_t)(pj - miny) * snx + (pi - minx);
+    float v = __ldg(slab + o);
+    if (v == msg) return;
+    if (mask) {
+        float m = __ldg(mask + o);
+        bool usable = rel == REL_LT ? (m >= maskval) : (rel == REL_GT ? (m <= maskval) : (m != maskval));
+        if (!usable) return;
+    }
+    size_t cell = (size_t)(dest.y - sm2) * nx + (dest.x - sm1);
+    atomicAdd(sum + cell, (double)v);
+    atomicAdd(cnt + cell, 1);
+}
+
+// Cells that received data: r_arr = sum / count (:2393-2400, :2443-2450) unless the point is in the
+// process_bdy_width interior or masked by the landmask -- those and the empty cells are left to the chain.
+__global__ void k_gc_apply(const Job* __restrict__ jobs, int job, const SlabPtrs* __restrict__ slabs,
+                           const double* __restrict__ sum, const int* __restrict__ cnt, int* __restrict__ decided)
+{
+    const Job& jb = jobs[job];
+    const SlabPtrs sp = slabs[jb.slab0];
+    int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y;
+    bool dec = false;
+    if (ii < jb.nx) {
+        size_t idx = (size_t)jj * jb.nx + ii;
+        int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
+        bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+        bool lm_masked = jb.landmask != nullptr && __ldg(jb.landmask + idx) == jb.masked;
+        int c = cnt[idx];
+        if (!in_fill && !lm_masked && c > 0) {
+            sp.r_arr[idx] = (float)sum[idx] / (float)c;
+            dec = true;
+        }
+    }
+    unsigned word = __ballot_sync(0xffffffffu, dec);
+    if ((threadIdx.x & 31) == 0 && ii < jb.nxw * 32) decided[(size_t)jj * jb.nxw + (ii >> 5)] = (int)word;
+}
 
 // ---- source-cell bounding box of a destination grid (once per cached coordinate set) -----------------
 __global__ void k_xy_bbox(const float2* __restrict__ xy, int64_t n, int* __restrict__ bbox)
@@ -668,6 +750,7 @@ static int rel_code(char c) { return c == '<' ? REL_LT : (c == '>' ? REL_GT : RE
 
 static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
 {
+    if (a.gcell || b.gcell) return false;   // average_gcell slabs carry their own accumulation buffers
     if (memcmp(&a.proj, &b.proj, offsetof(wpsgpu_proj, gauss_lat)) != 0) return false;
     if (memcmp(a.fo.ops, b.fo.ops, sizeof(a.fo.ops)) || memcmp(a.fo.opts, b.fo.opts, sizeof(a.fo.opts))) return false;
     if (memcmp(&a.fo.missing_value, &b.fo.missing_value, sizeof(float)) || memcmp(&a.fo.fill_missing, &b.fo.fill_missing, sizeof(float)) ||
@@ -761,6 +844,24 @@ int wpsgpu_metgrid_enqueue_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, 
     return 0;
 }
 
+int wpsgpu_metgrid_enqueue_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, const wpsgpu_proj* dom_proj,
+                                      const wpsgpu_field_opts* fo, const wpsgpu_slab* slab)
+{
+    WPS_CHECK(h && dom_proj, -1, "wpsgpu_metgrid_enqueue_gcell_slab: NULL argument");
+    WPS_CHECK(dom_proj->init, -1, "domain projection not initialised");
+    WPS_TRY(wpsgpu_metgrid_enqueue_slab(h, src_proj, fo, slab));
+    h->queue.back().gcell = true;
+    h->queue.back().dom_proj = *dom_proj;
+    return 0;
+}
+
+int wpsgpu_metgrid_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, const wpsgpu_proj* dom_proj,
+                              const wpsgpu_field_opts* fo, const wpsgpu_slab* slab)
+{
+    WPS_TRY(wpsgpu_metgrid_enqueue_gcell_slab(h, src_proj, dom_proj, fo, slab));
+    return wpsgpu_metgrid_flush(h);
+}
+
 int wpsgpu_metgrid_enqueue_slabs(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, const wpsgpu_field_opts* fo,
                                  const wpsgpu_slab* slabs, int32_t n)
 {
@@ -848,6 +949,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         return 0;
     };
     std::vector<Job> jobs(njobs);
+    std::vector<int*> gc_decided(njobs, nullptr);
     std::vector<SlabPtrs> sp(nq);
     std::vector<int> cls_jobs[2], cls_tile0[2];  // 0 = generic kernel, 1 = first-method kernels
     std::vector<int> fast_word0;
@@ -897,6 +999,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         if (bx.fast >= 2) fast4_points += (double)dg.npts() * groups[g].size();
         if (cls == 1) { fast_word0.push_back((int)fast_words); fast_words += (long long)jb.ny * jb.nxw * groups[g].size(); }
         jb.f_negzero = -0.0f; jb.f_one = 1.0f;
+        jb.gcell = q0.gcell ? 1 : 0;
         jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
         if (jb.fast == 1) {
             size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
@@ -915,8 +1018,13 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         // one pass per kind of array, so that the arrays of neighbouring levels end up next to each other
         for (int k = 0; k < ns; ++k) {
             SlabPtrs& p = sp[s0 + k];
-            p.slow = nullptr; p.pad_ = nullptr; p.valid = nullptr;
+            p.slow = nullptr; p.decided = nullptr; p.valid = nullptr;
             WPS_TRY(stage_shared(queue[grp[k]].s.slab, sbytes, &p.src));
+        }
+        if (jb.gcell) {
+            gc_decided[j] = (int*)h->arena.take(wbytes);
+            WPS_CHECK(gc_decided[j] != nullptr, -3, "device arena exhausted (average_gcell bits)");
+            sp[s0].decided = gc_decided[j];
         }
         if (jb.fast)
             for (int k = 0; k < ns; ++k) {
@@ -993,6 +1101,33 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
     }
     if (any_search) WPS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), h->stream));
+
+    // ---- average_gcell pre-pass: cell averages into r_arr + "decided" bits, one slab per job ----
+    for (int j = 0; j < njobs; ++j) {
+        if (!jobs[j].gcell) continue;
+        const Job& jb = jobs[j];
+        const QueuedSlab& q0 = queue[groups[gsel[j]][0]];
+        const int snx = jb.maxx - jb.minx + 1, sny = jb.maxy - jb.miny + 1;
+        const size_t npts = (size_t)jb.nx * jb.ny;
+        int2* d_wm = (int2*)h->arena.take(sizeof(int2) * (size_t)snx * sny);
+        double* d_sum = (double*)h->arena.take(sizeof(double) * npts);
+        int* d_gcnt = (int*)h->arena.take(sizeof(int) * npts);
+        WPS_CHECK(d_wm && d_sum && d_gcnt, -3, "device arena exhausted (average_gcell buffers)");
+        WPS_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double) * npts, h->stream));
+        WPS_CUDA(cudaMemsetAsync(d_gcnt, 0, sizeof(int) * npts, h->stream));
+        const float* d_gauss_dom = nullptr;
+        if (q0.dom_proj.code == WPSGPU_PROJ_GAUSS) WPS_TRY(upload_gauss(h, q0.dom_proj, &d_gauss_dom));
+        DevProj dom = to_dev(q0.dom_proj, d_gauss_dom);
+        dim3 b2(32, 8);
+        k_gc_wm<<<dim3((snx + 31) / 32, (sny + 7) / 8), b2, 0, h->stream>>>(jb.proj, dom, jb.minx, jb.miny, snx, sny, jb.sm1, jb.em1, jb.sm2, jb.em2, d_wm);
+        const int bw = jb.maxx - jb.minx + 1 - 2 * jb.bdr;
+        if (bw > 0)
+            k_gc_accum<<<dim3((bw + 31) / 32, (sny + 7) / 8), b2, 0, h->stream>>>(d_wm, sp[jb.slab0].src, jb.mask[0], jb.mask_rel[0], jb.mask_val[0], jb.msg,
+                                                                                 jb.minx, jb.maxx, jb.miny, jb.maxy, jb.bdr, jb.sm1, jb.sm2, jb.nx, d_sum, d_gcnt);
+        k_gc_apply<<<dim3(jb.nxw, jb.ny), 32, 0, h->stream>>>(d_jobs, j, d_sp, d_sum, d_gcnt, gc_decided[j]);
+        h->launches += 3;
+        WPS_CUDA(cudaGetLastError());
+    }
 
     // ---- launches ----
     dim3 block(TILE_X, TILE_Y);
@@ -1169,7 +1304,10 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         b.fast = 0; b.bx0 = b.by0 = b.bnx = b.bny = b.npack = 0;
         const int* bb = &job_bbox[4 * g];
         bool simple_mask = !(q0.s.use_landmask && q0.fo.masked == WPSGPU_MASKED_BOTH);
-        if (!h->disable_fast && (simple_mask || q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT)) {
+        if (q0.gcell) {   // where_maps_to, sums, counts, decided bits
+            need += (size_t)(q0.s.maxx - q0.s.minx + 1) * (q0.s.maxy - q0.s.miny + 1) * sizeof(int2) + dg.npts() * (sizeof(double) + sizeof(int)) +
+                    (size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 2048;
+        } else if (!h->disable_fast && (simple_mask || q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT)) {
             if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
                 long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);
                 long y0 = std::max<long>(q0.s.miny, (long)bb[2] - 2), y1 = std::min<long>(q0.s.maxy, (long)bb[3] + 4);

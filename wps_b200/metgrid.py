@@ -62,7 +62,7 @@ class MetgridDomain:
     """One model domain: its staggered lat/lon arrays (from geo_em), LANDMASK and the device handle."""
 
     def __init__(self, handle: capi.Handle, xlat, xlon, xlat_u, xlon_u, xlat_v, xlon_v, landmask, domain=None,
-                 mem_start=(1, 1), process_bdy_width=0, dom_dx=None, dom_dy=None):
+                 mem_start=(1, 1), process_bdy_width=0, dom_dx=None, dom_dy=None, dom_proj=None):
         self.h = handle
         self.grids = {capi.M: (xlat, xlon), capi.U: (xlat_u, xlon_u), capi.V: (xlat_v, xlon_v)}
         self.landmask = landmask
@@ -71,6 +71,7 @@ class MetgridDomain:
         self.domain = domain or (mem_start[0], mem_start[0] + nx - 1, mem_start[1], mem_start[1] + ny - 1)
         self.process_bdy_width = process_bdy_width
         self.dom_dx, self.dom_dy = dom_dx, dom_dy
+        self.dom_proj = dom_proj     # set_domain_projection's projection; needed by the average_gcell branch only
         for st, (la, lo) in self.grids.items():
             handle.metgrid_set_grid(GRID_OF_STAGGER[st], la, lo, mem_start[0], mem_start[1])
         if landmask is not None:
@@ -100,9 +101,9 @@ class MetgridDomain:
             slab, minx, bdr = halo_slab(fg)
             proj = source_projection(fg)
             _, _, has_gcell, thr = capi.parse_interp_option(e.interp_method)
-            if has_gcell and self._do_gcell(fg, thr):
-                raise NotImplementedError("average_gcell for metgrid sources finer than the domain "
-                                          "(process_domain_module.F:2331-2478) is not ported yet")
+            do_gcell = has_gcell and self._do_gcell(fg, thr)
+            if do_gcell and self.dom_proj is None:
+                raise ValueError("average_gcell applies to %s but MetgridDomain was built without dom_proj" % name)
             stag = e.output_stagger if e.output_stagger in (capi.U, capi.V) else capi.M
             xlat, _ = self.grids[stag]
             gy, gx = xlat.shape
@@ -117,10 +118,17 @@ class MetgridDomain:
             fld.modified_mask = np.zeros((gy, capi.nwords(gx)), np.int32)
             m = [masks.get(nm + ".mask") if nm != " " else None for nm in (e.interp_mask, e.interp_land_mask, e.interp_water_mask)]
             fresh = getattr(fld, "_fresh", False)
-            self.h.metgrid_enqueue_slab(proj, e.field_opts(), slab, minx, 1, bdr, GRID_OF_STAGGER[stag], stag, fld.r_arr,
-                                        fld.modified_mask, valid_mask=None if fresh else fld.valid_mask, masks=tuple(m),
-                                        use_landmask=(stag == capi.M and self.landmask is not None),
-                                        process_bdy_width=self.process_bdy_width)
+            if do_gcell:
+                self.h.metgrid_enqueue_gcell_slab(proj, self.dom_proj, e.field_opts(), slab, minx, 1, bdr, GRID_OF_STAGGER[stag],
+                                                  stag, fld.r_arr, fld.modified_mask,
+                                                  valid_mask=None if fresh else fld.valid_mask, mask=m[0],
+                                                  use_landmask=(stag == capi.M and self.landmask is not None),
+                                                  process_bdy_width=self.process_bdy_width)
+            else:
+                self.h.metgrid_enqueue_slab(proj, e.field_opts(), slab, minx, 1, bdr, GRID_OF_STAGGER[stag], stag, fld.r_arr,
+                                            fld.modified_mask, valid_mask=None if fresh else fld.valid_mask, masks=tuple(m),
+                                            use_landmask=(stag == capi.M and self.landmask is not None),
+                                            process_bdy_width=self.process_bdy_width)
             fld._fresh = False
             keep.append((slab, m))
             queued.append((key, fld))
