@@ -200,6 +200,62 @@ def enqueue_all(h, w, descs):
     h.metgrid_flush()
 
 
+def geogrid_arm(h, torch, dev, config, steps):
+    """geogrid reported additionally as source pixels/s.  Config-3 shape: a 30-arc-second, 21-category,
+    1-byte land-use dataset in 1200x1200 tiles (raw bytes resident in HBM) accumulated onto the 3-km CONUS patch
+    (+-3 halo) with calc_field's categorical path: decode, where_maps_to, quadtree credit, per-tile merge, per-point
+    fallback, finish.  One step = one whole field (all tiles)."""
+    from wps_b200 import capi, synth
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = config["dom"]
+    dom = synth.lambert_domain(nx, ny, dx, tl1, tl2, slon, rlat, rlon)
+    gx, gy, ncat, tn = nx + 6, ny + 6, 21, 1200
+    xlat = torch.empty((gy, gx), dtype=torch.float32, device=dev)
+    xlon = torch.empty_like(xlat)
+    h.xytoll_grid(dom, capi.M, -2, -2, gx, gy, out=(xlat, xlon))
+    h.synchronize()
+    dxdeg, klat, klon = 0.00833333, -89.99583, -179.99583
+    src = capi.push_source_projection(capi.PROJ_LATLON, dlat=dxdeg, dlon=dxdeg, known_x=1.0, known_y=1.0, known_lat=klat,
+                                      known_lon=klon)
+    lat0, lat1 = float(xlat.min()) - 0.1, float(xlat.max()) + 0.1
+    lon0, lon1 = float(xlon.min()) - 0.1, float(xlon.max()) + 0.1
+    ix0, ix1 = int(np.floor((lon0 - klon) / dxdeg)) + 1, int(np.ceil((lon1 - klon) / dxdeg)) + 1
+    iy0, iy1 = int(np.floor((lat0 - klat) / dxdeg)) + 1, int(np.ceil((lat1 - klat) / dxdeg)) + 1
+    tiles = []
+    for ty in range(tn * ((iy0 - 1) // tn) + 1, iy1 + 1, tn):
+        for tx in range(tn * ((ix0 - 1) // tn) + 1, ix1 + 1, tn):
+            j = torch.arange(ty, ty + tn, device=dev)[:, None]
+            i = torch.arange(tx, tx + tn, device=dev)[None, :]
+            cat = (((i // 7) * 31 + (j // 5) * 17) % ncat + 1).to(torch.uint8).contiguous()
+            tiles.append((tx, ty, cat))
+    field = torch.zeros((ncat, gy, gx), dtype=torch.float32, device=dev)
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+
+    def one_field():
+        h.geogrid_field_begin(dom, capi.M, xlat, xlon, -2, -2, 1, field)
+        h.geogrid_level_begin(src, 1, capi.CATEGORICAL, "nearest_neighbor", msg_val=255.0)
+        for tx, ty, cat in tiles:
+            h.geogrid_add_tile_raw(cat, (1, tn, tn), 1, 0, 0, 1, tx, ty, 1, 0)
+        h.geogrid_level_end()
+        return h.geogrid_field_finish()
+
+    one_field()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = h.launch_count
+    ev0.record(stream)
+    for _ in range(steps):
+        one_field()
+    ev1.record(stream)
+    h.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    pixels = len(tiles) * tn * tn
+    frac_sum = float(field.sum(dim=0).mean())
+    return {"metric": "geogrid source pixels/s (categorical accumulation, config-3 land use)", "value": pixels / (ms / 1e3),
+            "unit": "pixels/s", "ms_per_field": ms, "tiles": len(tiles), "tile": "1200x1200x1B", "pixels_per_field": pixels,
+            "dest": "%dx%dx%d categories" % (gx, gy, ncat), "gpu_launches_per_field": (h.launch_count - l0) // steps,
+            "alg_bytes_per_pixel": 1.0 + 4.0 * ncat * gx * gy / pixels, "mean_fraction_sum": frac_sum}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -298,6 +354,9 @@ def run_b200(args, rank, world, local_rank):
         e2e_value = world * pts / float(t.item())
         hh.close()
 
+    geo = None
+    if rank == 0 and not args.no_geogrid:
+        geo = geogrid_arm(h, torch, dev, config, 3)
     if rank == 0:
         peaks = {}
         try:
@@ -321,6 +380,8 @@ def run_b200(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": sampler.result()}
+        if geo is not None:
+            line["geogrid"] = geo
         if world == 1 and not args.no_cpu:
             pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 3)
             line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}
@@ -337,6 +398,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-geogrid", action="store_true", help="skip the additional geogrid source-pixels/s measurement")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

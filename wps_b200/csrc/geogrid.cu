@@ -2,6 +2,7 @@
 // reference's quadtree "four corners agree" rule (proc_point_module.F:218-458,553-779), per-point fallback
 // (get_point, :788-855), post-processing, and the raw tile decode of read_geogrid.c.
 #include <algorithm>
+#include <climits>
 #include "ctx.h"
 #include "interp.cuh"
 
@@ -27,6 +28,10 @@ struct GeoState {
     void* d_raw = nullptr; size_t raw_cap = 0;
     Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
     void* d_lit = nullptr; size_t lit_bytes = 0;
+    // buffers kept across fields (grow-only): a geogrid run processes dozens of fields on the same patch
+    size_t cap_count = 0, cap_acc_cnt = 0, cap_acc_sum = 0, cap_touched = 0, cap_bits = 0, cap_xy = 0, cap_def = 0, cap_blk = 0;
+    float4* d_blk_xy = nullptr;       // per 256-point block: min/max of src_xy (lets the per-tile point pass skip far blocks)
+    int* d_tbbox = nullptr;           // destination rows/columns credited by the current tile: {jmin, imin, jmax, imax}
     const float* d_gauss_src = nullptr; const float* d_gauss_dom = nullptr;
     bool own_field = false, own_ll = false;
     bool has_search = false; int max_depth = 0;
@@ -41,6 +46,7 @@ struct GeoK {  // kernel-side view
     float* field; float* count; const float* landmask;
     int* processed; int* level;
     int* acc_cnt; double* acc_sum; int* touched; unsigned long long* invalid;
+    int* tbbox; const float4* blk_xy;
     // current tile
     const float* tile; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny;
     int2* wm;
@@ -50,61 +56,115 @@ struct GeoK {  // kernel-side view
 __device__ __forceinline__ bool bit_test(const int* w, int nxw, int ii, int jj) { return (w[(size_t)jj * nxw + (ii >> 5)] >> (ii & 31)) & 1; }
 __device__ __forceinline__ void bit_set_atomic(int* w, int nxw, int ii, int jj) { atomicOr(w + (size_t)jj * nxw + (ii >> 5), (int)(1u << (ii & 31))); }
 
-// where_maps_to for every pixel of the tile (proc_point_module.F:245-310)
-__global__ void k_geo_wm(GeoK g)
+// where_maps_to for every pixel of the tile (proc_point_module.F:245-310).  One block covers WM_T x WM_T pixels.
+// For a regular lat-lon source read onto a Lambert or polar-stereographic domain the projection separates into a
+// per-row term (latitude) and a per-column term (longitude): those 2*WM_T evaluations are shared by the WM_T^2
+// pixels of the block through shared memory -- same expressions as llij_lc / llij_ps, so the same bits.
+constexpr int WM_T = 64;
+__global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 {
-    int ti = blockIdx.x * blockDim.x + threadIdx.x, tj = blockIdx.y * blockDim.y + threadIdx.y;
-    if (ti >= g.tnx || tj >= g.tny) return;
-    float lat, lon, rx, ry;
-    xytoll(g.src, (float)(g.smx + ti), (float)(g.smy + tj), lat, lon, WPSGPU_M);
-    lltoxy(g.dom, lat, lon, rx, ry, g.istagger);
-    rx = (rx - 0.5f) * g.sr_x + 0.5f;
-    ry = (ry - 0.5f) * g.sr_y + 0.5f;
-    int2 w;
-    if ((float)g.start_i <= rx && rx <= (float)g.end_i && (float)g.start_j <= ry && ry <= (float)g.end_j) { w.x = f_nint(rx); w.y = f_nint(ry); }
-    else { w.x = GEO_OUTSIDE; w.y = 0; }
-    g.wm[(size_t)tj * g.tnx + ti] = w;
+    __shared__ float s_rm[WM_T], s_sin[WM_T], s_cos[WM_T], s_lat[WM_T], s_lon[WM_T];
+    const int ti0 = blockIdx.x * WM_T, tj0 = blockIdx.y * WM_T, t = threadIdx.x;
+    const bool separable = g.src.code == WPSGPU_PROJ_LATLON && (g.dom.code == WPSGPU_PROJ_LC || g.dom.code == WPSGPU_PROJ_PS);
+    if (separable) {
+        if (t < WM_T) {   // row terms: ijll_latlon gives lat from j alone
+            float lat, lon;
+            xytoll(g.src, (float)(g.smx + ti0), (float)(g.smy + tj0 + t), lat, lon, WPSGPU_M);
+            s_lat[t] = lat;
+            s_rm[t] = g.dom.code == WPSGPU_PROJ_LC ? llij_lc_rm(lat, g.dom) : llij_ps_rm(lat, g.dom);
+        } else if (t < 2 * WM_T) {   // column terms: lon from i alone
+            int c = t - WM_T;
+            float lat, lon, sn, cs;
+            xytoll(g.src, (float)(g.smx + ti0 + c), (float)(g.smy + tj0), lat, lon, WPSGPU_M);
+            if (g.dom.code == WPSGPU_PROJ_LC) llij_lc_sc(lon, g.dom, sn, cs); else llij_ps_sc(lon, g.dom, sn, cs);
+            s_lon[c] = lon; s_sin[c] = sn; s_cos[c] = cs;
+        }
+        __syncthreads();
+    }
+    for (int e = t; e < WM_T * WM_T; e += 256) {
+        int li = e % WM_T, lj = e / WM_T, ti = ti0 + li, tj = tj0 + lj;
+        if (ti >= g.tnx || tj >= g.tny) continue;
+        float rx, ry;
+        if (separable) {
+            if (g.dom.code == WPSGPU_PROJ_LC) llij_lc_combine(s_rm[lj], s_sin[li], s_cos[li], g.dom, rx, ry);
+            else llij_ps_combine(s_rm[lj], s_sin[li], s_cos[li], g.dom, rx, ry);
+            if (g.istagger == WPSGPU_U) rx = rx + 0.5f;
+            else if (g.istagger == WPSGPU_V) ry = ry + 0.5f;
+            else if (g.istagger == WPSGPU_CORNER) { rx = rx + 0.5f; ry = ry + 0.5f; }
+        } else {
+            float lat, lon;
+            xytoll(g.src, (float)(g.smx + ti), (float)(g.smy + tj), lat, lon, WPSGPU_M);
+            lltoxy(g.dom, lat, lon, rx, ry, g.istagger);
+        }
+        rx = (rx - 0.5f) * g.sr_x + 0.5f;
+        ry = (ry - 0.5f) * g.sr_y + 0.5f;
+        int2 w;
+        if ((float)g.start_i <= rx && rx <= (float)g.end_i && (float)g.start_j <= ry && ry <= (float)g.end_j) { w.x = f_nint(rx); w.y = f_nint(ry); }
+        else { w.x = GEO_OUTSIDE; w.y = 0; }
+        g.wm[(size_t)tj * g.tnx + ti] = w;
+    }
 }
 
 // Quadtree emulation: walk the block hierarchy of process_*_block top-down for this pixel and credit the
 // first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
-__global__ void k_geo_accum(GeoK g)
+__global__ void __launch_bounds__(256) k_geo_accum(GeoK g)
 {
+    __shared__ int s_bb[4];   // {jmin, imin, jmax, imax} of the cells this block credits
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid == 0) { s_bb[0] = INT_MAX; s_bb[1] = INT_MAX; s_bb[2] = INT_MIN; s_bb[3] = INT_MIN; }
+    __syncthreads();
     int I0 = g.smx + g.bdr, I1 = g.sMx - g.bdr, J0 = g.smy + g.bdr, J1 = g.sMy - g.bdr;
     int pi = I0 + blockIdx.x * blockDim.x + threadIdx.x, pj = J0 + blockIdx.y * blockDim.y + threadIdx.y;
-    if (pi > I1 || pj > J1) return;
-    auto W = [&](int i, int j) { return g.wm[(size_t)(j - g.smy) * g.tnx + (i - g.smx)]; };
-    int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
-    int2 dest;
-    for (;;) {
-        int2 a = W(min_i, min_j), b = W(min_i, max_j), c = W(max_i, max_j), d = W(max_i, min_j);
-        if (a.x == b.x && a.x == c.x && a.x == d.x && a.y == b.y && a.y == c.y && a.y == d.y && a.x != GEO_OUTSIDE) { dest = a; break; }
-        if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = W(pi, pj); break; }
-        int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
-        if (pi <= ci) max_i = ci; else min_i = ci + 1;
-        if (pj <= cj) max_j = cj; else min_j = cj + 1;
-    }
-    if (dest.x == GEO_OUTSIDE) return;
-    int ii = dest.x - g.start_i, jj = dest.y - g.start_j;
-    if (bit_test(g.processed, g.nxw, ii, jj)) return;
-    size_t cell = (size_t)jj * g.nx + ii;
-    g.touched[cell] = 1;
-    size_t tn2 = (size_t)g.tnx * g.tny, toff = (size_t)(pj - g.smy) * g.tnx + (pi - g.smx);
-    if (g.itype == WPSGPU_CATEGORICAL) {
-        float v = g.tile[toff];
-        if (v != g.msg_val) {
-            int cat = (int)v;
-            if (cat >= g.start_k && cat <= g.end_k) atomicAdd(g.acc_cnt + (size_t)(cat - g.start_k) * g.npts + cell, 1);
-            else atomicAdd(g.invalid, 1ull);
+    bool credit = pi <= I1 && pj <= J1;
+    int ii = 0, jj = 0;
+    if (credit) {
+        auto W = [&](int i, int j) { return g.wm[(size_t)(j - g.smy) * g.tnx + (i - g.smx)]; };
+        int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
+        int2 dest;
+        for (;;) {
+            int2 a = W(min_i, min_j), b = W(min_i, max_j), c = W(max_i, max_j), d = W(max_i, min_j);
+            if (a.x == b.x && a.x == c.x && a.x == d.x && a.y == b.y && a.y == c.y && a.y == d.y && a.x != GEO_OUTSIDE) { dest = a; break; }
+            if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = W(pi, pj); break; }
+            int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
+            if (pi <= ci) max_i = ci; else min_i = ci + 1;
+            if (pj <= cj) max_j = cj; else min_j = cj + 1;
         }
-    } else {
-        for (int k = g.smz; k <= g.sMz; ++k) {
-            float v = g.tile[(size_t)(k - g.smz) * tn2 + toff];
+        credit = dest.x != GEO_OUTSIDE;
+        if (credit) {
+            ii = dest.x - g.start_i; jj = dest.y - g.start_j;
+            credit = !bit_test(g.processed, g.nxw, ii, jj);
+        }
+    }
+    if (credit) {
+        size_t cell = (size_t)jj * g.nx + ii;
+        g.touched[cell] = 1;
+        atomicMin(&s_bb[0], jj); atomicMin(&s_bb[1], ii); atomicMax(&s_bb[2], jj); atomicMax(&s_bb[3], ii);
+        size_t tn2 = (size_t)g.tnx * g.tny, toff = (size_t)(pj - g.smy) * g.tnx + (pi - g.smx);
+        if (g.itype == WPSGPU_CATEGORICAL) {
+            float v = g.tile[toff];
             if (v != g.msg_val) {
-                atomicAdd(g.acc_sum + (size_t)(k - g.start_k) * g.npts + cell, (double)v);
-                atomicAdd(g.acc_cnt + (size_t)(k - g.start_k) * g.npts + cell, 1);
+                int cat = (int)v;
+                if (cat >= g.start_k && cat <= g.end_k) atomicAdd(g.acc_cnt + (size_t)(cat - g.start_k) * g.npts + cell, 1);
+                else atomicAdd(g.invalid, 1ull);
+            }
+        } else {
+            for (int k = g.smz; k <= g.sMz; ++k) {
+                float v = g.tile[(size_t)(k - g.smz) * tn2 + toff];
+                if (v != g.msg_val) {
+                    atomicAdd(g.acc_sum + (size_t)(k - g.start_k) * g.npts + cell, (double)v);
+                    atomicAdd(g.acc_cnt + (size_t)(k - g.start_k) * g.npts + cell, 1);
+                }
             }
         }
+    }
+    // rows / columns this tile reaches (k_geo_merge skips the rest of the domain): one update per block, and only
+    // when it would change the running range
+    __syncthreads();
+    if (tid < 4 && s_bb[0] != INT_MAX) {
+        int v = s_bb[tid];
+        int cur = __ldcg(g.tbbox + tid);
+        if (tid < 2) { if (v < cur) atomicMin(g.tbbox + tid, v); }
+        else if (v > cur) atomicMax(g.tbbox + tid, v);
     }
 }
 
@@ -112,33 +172,64 @@ __global__ void k_geo_accum(GeoK g)
 // (proc_point_module.F:326-346) and, for ilevel>1 categorical data, the half-area rule (:165-202).
 __global__ void k_geo_merge(GeoK g, int ilevel, float src_area, float dom_area)
 {
+    const bool all_cells = ilevel > 1 && g.itype == WPSGPU_CATEGORICAL;   // the half-area rule looks at every cell
+    if (!all_cells) {
+        size_t c0 = (size_t)blockIdx.x * blockDim.x, c1 = min(c0 + blockDim.x - 1, g.npts - 1);
+        int r0 = (int)(c0 / g.nx), r1 = (int)(c1 / g.nx);
+        if (r1 < g.tbbox[0] || r0 > g.tbbox[2]) return;   // no cell of this block was reached by the tile
+    }
     size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= g.npts) return;
     int ii = (int)(cell % g.nx), jj = (int)(cell / g.nx);
+    if (!all_cells && (ii < g.tbbox[1] || ii > g.tbbox[3])) return;
     if (g.touched[cell]) {
         g.touched[cell] = 0;
         bool isnew = bit_test(g.level, g.nxw, ii, jj);
         bool any = false;
+        // loads of a chunk of levels are issued together before the stores (the arrays may alias as far as the
+        // compiler knows, so a load-store-load sequence would pay one memory latency per level)
+        constexpr int CH = 8;
         if (g.itype == WPSGPU_CATEGORICAL) {
-            for (int k = 0; k < g.nk; ++k) {
-                size_t o = (size_t)k * g.npts + cell;
-                int c = g.acc_cnt[o];
-                g.acc_cnt[o] = 0;
-                float base = isnew ? g.field[o] : 0.0f;
-                g.field[o] = base + (float)c;
-                any |= c > 0;
+            for (int k0 = 0; k0 < g.nk; k0 += CH) {
+                int c[CH]; float f[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    size_t o = (size_t)(k0 + u) * g.npts + cell;
+                    bool in = k0 + u < g.nk;
+                    c[u] = in ? g.acc_cnt[o] : 0;
+                    f[u] = (in && isnew) ? g.field[o] : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    if (k0 + u >= g.nk) break;
+                    size_t o = (size_t)(k0 + u) * g.npts + cell;
+                    if (c[u] != 0) g.acc_cnt[o] = 0;
+                    g.field[o] = f[u] + (float)c[u];
+                    any |= c[u] > 0;
+                }
             }
         } else {
             int k0 = g.smz - g.start_k, k1 = g.sMz - g.start_k;
-            for (int k = k0; k <= k1; ++k) {
-                size_t o = (size_t)k * g.npts + cell;
-                int c = g.acc_cnt[o];
-                double s = g.acc_sum[o];
-                g.acc_cnt[o] = 0; g.acc_sum[o] = 0.0;
-                float base = isnew ? g.field[o] : 0.0f;
-                g.field[o] = base + (float)s;
-                g.count[o] = g.count[o] + (float)c;
-                any |= c > 0;
+            for (int kk = k0; kk <= k1; kk += CH) {
+                int c[CH]; double sm[CH]; float f[CH], n[CH];
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    size_t o = (size_t)(kk + u) * g.npts + cell;
+                    bool in = kk + u <= k1;
+                    c[u] = in ? g.acc_cnt[o] : 0;
+                    sm[u] = in ? g.acc_sum[o] : 0.0;
+                    f[u] = (in && isnew) ? g.field[o] : 0.0f;
+                    n[u] = in ? g.count[o] : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    if (kk + u > k1) break;
+                    size_t o = (size_t)(kk + u) * g.npts + cell;
+                    g.acc_cnt[o] = 0; g.acc_sum[o] = 0.0;
+                    g.field[o] = f[u] + (float)sm[u];
+                    g.count[o] = n[u] + (float)c[u];
+                    any |= c[u] > 0;
+                }
             }
         }
         if (any) bit_set_atomic(g.level, g.nxw, ii, jj);
@@ -157,14 +248,37 @@ __global__ void k_geo_merge(GeoK g, int ilevel, float src_area, float dom_area)
 }
 
 // source-grid coordinates of every destination point (get_point / is_point_in_tile, :811-823,911-921)
-__global__ void k_geo_src_xy(DevProj src, const float* __restrict__ xlat, const float* __restrict__ xlon, size_t n, float2* __restrict__ xy)
+// Also records, per block of 256 points, the range of those coordinates: a tile's point pass can then drop whole
+// blocks whose points all lie outside the tile with one 16-byte load.
+__global__ void __launch_bounds__(256)
+k_geo_src_xy(DevProj src, const float* __restrict__ xlat, const float* __restrict__ xlon, size_t n, float2* __restrict__ xy,
+             float4* __restrict__ blk_xy)
 {
+    __shared__ float s_red[4][8];
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    float rlat = xlat[p], rlon = xlon[p], rx, ry;
-    if (rlon >= 180.0f) rlon = rlon - 360.0f;
-    lltoxy(src, rlat, rlon, rx, ry, WPSGPU_M);
-    xy[p] = make_float2(rx, ry);
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    if (p < n) {
+        float rlat = xlat[p], rlon = xlon[p], rx, ry;
+        if (rlon >= 180.0f) rlon = rlon - 360.0f;
+        lltoxy(src, rlat, rlon, rx, ry, WPSGPU_M);
+        xy[p] = make_float2(rx, ry);
+        // NaN coordinates fail every in-tile test, so they may be left out of the range (fminf/fmaxf drop them)
+        xmin = xmax = rx; ymin = ymax = ry;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off)); xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, off));
+        ymin = fminf(ymin, __shfl_xor_sync(0xffffffffu, ymin, off)); ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
+    }
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_red[0][w] = xmin; s_red[1][w] = xmax; s_red[2][w] = ymin; s_red[3][w] = ymax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            xmin = fminf(xmin, s_red[0][k]); xmax = fmaxf(xmax, s_red[1][k]); ymin = fminf(ymin, s_red[2][k]); ymax = fmaxf(ymax, s_red[3][k]);
+        }
+        // an all-NaN / empty block keeps (+inf, -inf) and is skipped by every tile; a NaN seen first is replaced by fminf/fmaxf
+        blk_xy[blockIdx.x] = make_float4(xmin, xmax, ymin, ymax);
+    }
 }
 
 // inner loop of calc_field for one destination point (process_tile_module.F:1408-1519)
@@ -231,8 +345,14 @@ __device__ __forceinline__ bool geo_point(const GeoK& g, const float2* __restric
     return false;
 }
 
-__global__ void k_geo_points(GeoK g, const float2* __restrict__ src_xy, Deferred* def, unsigned long long* def_cnt)
+__global__ void __launch_bounds__(256)
+k_geo_points(GeoK g, const float2* __restrict__ src_xy, Deferred* def, unsigned long long* def_cnt)
 {
+    {   // is_point_in_tile is monotone in each coordinate: if it fails for the block's extreme coordinates it fails for all
+        float4 b = g.blk_xy[blockIdx.x];   // {xmin, xmax, ymin, ymax}
+        if (!(g.smx + g.bdr <= f_floor(b.y + 0.5f) && f_ceiling(b.x - 0.5f) <= g.sMx - g.bdr &&
+              g.smy + g.bdr <= f_floor(b.w + 0.5f) && f_ceiling(b.z - 0.5f) <= g.sMy - g.bdr)) return;
+    }
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= g.npts) return;
     if (geo_point<0>(g, src_xy, p, nullptr)) {
@@ -337,6 +457,7 @@ static GeoK make_k(wpsgpu_ctx* h)
     g.sr_x = (float)s->l.sr_x; g.sr_y = (float)s->l.sr_y; g.msg_val = s->l.msg_val; g.msg_fill_val = s->l.msg_fill_val; g.mask_val = s->l.mask_val;
     g.field = s->d_field; g.count = s->d_count; g.landmask = s->d_landmask; g.processed = s->d_processed; g.level = s->d_level;
     g.acc_cnt = s->d_acc_cnt; g.acc_sum = s->d_acc_sum; g.touched = s->d_touched; g.invalid = s->d_invalid;
+    g.tbbox = s->d_tbbox; g.blk_xy = s->d_blk_xy;
     memcpy(g.ops, s->l.ops, sizeof(g.ops)); memcpy(g.opts, s->l.opts, sizeof(g.opts));
     g.ops[WPSGPU_MAX_OPS - 1] = 0;
     return g;
@@ -346,12 +467,23 @@ static void geo_free_field(GeoState* s)
 {
     if (s->own_field && s->d_field) cudaFree(s->d_field);
     if (s->own_ll) { if (s->d_xlat) cudaFree(s->d_xlat); if (s->d_xlon) cudaFree(s->d_xlon); if (s->d_landmask) cudaFree(s->d_landmask); }
-    void* ptrs[] = { s->d_count, s->d_processed, s->d_level, s->d_src_xy, s->d_acc_cnt, s->d_acc_sum, s->d_touched, s->d_def, s->d_def2 };
-    for (void* p : ptrs) if (p) cudaFree(p);
-    s->d_field = s->d_xlat = s->d_xlon = s->d_landmask = s->d_count = nullptr;
-    s->d_processed = s->d_level = nullptr; s->d_src_xy = nullptr; s->d_acc_cnt = nullptr; s->d_acc_sum = nullptr; s->d_touched = nullptr;
-    s->d_def = s->d_def2 = nullptr;
+    s->d_field = s->d_xlat = s->d_xlon = s->d_landmask = nullptr;
+    s->own_field = s->own_ll = false;
     s->field_open = s->level_open = false;
+}
+
+// grow-only scratch; `zero` buffers are cleared when (re)allocated and are returned to all-zero by the kernels that
+// consume them (k_geo_merge clears what k_geo_accum wrote), so they are not cleared again per field
+static int geo_buf(void** p, size_t* cap, size_t bytes, bool zero, cudaStream_t st)
+{
+    if (bytes <= *cap) return 0;
+    WPS_CUDA(cudaStreamSynchronize(st));
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    WPS_CUDA(cudaMalloc(p, bytes));
+    *cap = bytes;
+    if (zero) WPS_CUDA(cudaMemsetAsync(*p, 0, bytes, st));
+    return 0;
 }
 
 }  // namespace wps
@@ -370,6 +502,9 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
     if (s->d_raw) cudaFree(s->d_raw);
     if (s->d_lit) cudaFree(s->d_lit);
     if (s->d_invalid) cudaFree(s->d_invalid);
+    void* ptrs[] = { s->d_count, s->d_processed, s->d_level, s->d_src_xy, s->d_acc_cnt, s->d_acc_sum, s->d_touched, s->d_def, s->d_def2,
+                     s->d_blk_xy, s->d_tbbox };
+    for (void* p : ptrs) if (p) cudaFree(p);
     delete s;
     h->geo = nullptr;
 }
@@ -400,18 +535,23 @@ int wpsgpu_geogrid_field_begin(wpsgpu_handle_t h, const wpsgpu_geo_field* f)
         s->d_field = f->field; s->own_field = false;
         s->d_xlat = const_cast<float*>(f->xlat); s->d_xlon = const_cast<float*>(f->xlon); s->d_landmask = const_cast<float*>(f->landmask); s->own_ll = false;
     }
-    WPS_CUDA(cudaMalloc((void**)&s->d_processed, wb)); WPS_CUDA(cudaMalloc((void**)&s->d_level, wb));
+    const size_t nblk = (s->npts + 255) / 256;
+    {   // d_processed and d_level share one capacity counter: allocate both whenever it grows
+        size_t cap = s->cap_bits;
+        WPS_TRY(geo_buf((void**)&s->d_processed, &cap, wb, false, h->stream));
+        WPS_TRY(geo_buf((void**)&s->d_level, &s->cap_bits, wb, false, h->stream));
+    }
     WPS_CUDA(cudaMemsetAsync(s->d_processed, 0, wb, h->stream));  // bitarray_create at ilevel==1 (:1257)
-    WPS_CUDA(cudaMalloc((void**)&s->d_src_xy, s->npts * sizeof(float2)));
-    WPS_CUDA(cudaMalloc((void**)&s->d_count, b3));
-    WPS_CUDA(cudaMalloc((void**)&s->d_acc_cnt, (size_t)s->nk * s->npts * sizeof(int)));
-    WPS_CUDA(cudaMalloc((void**)&s->d_acc_sum, (size_t)s->nk * s->npts * sizeof(double)));
-    WPS_CUDA(cudaMalloc((void**)&s->d_touched, s->npts * sizeof(int)));
-    WPS_CUDA(cudaMalloc((void**)&s->d_def, s->npts * sizeof(Deferred)));
-    WPS_CUDA(cudaMalloc((void**)&s->d_def2, s->npts * sizeof(Deferred)));
-    WPS_CUDA(cudaMemsetAsync(s->d_acc_cnt, 0, (size_t)s->nk * s->npts * sizeof(int), h->stream));
-    WPS_CUDA(cudaMemsetAsync(s->d_acc_sum, 0, (size_t)s->nk * s->npts * sizeof(double), h->stream));
-    WPS_CUDA(cudaMemsetAsync(s->d_touched, 0, s->npts * sizeof(int), h->stream));
+    WPS_TRY(geo_buf((void**)&s->d_src_xy, &s->cap_xy, s->npts * sizeof(float2), false, h->stream));
+    WPS_TRY(geo_buf((void**)&s->d_blk_xy, &s->cap_blk, nblk * sizeof(float4), false, h->stream));
+    WPS_TRY(geo_buf((void**)&s->d_acc_cnt, &s->cap_acc_cnt, (size_t)s->nk * s->npts * sizeof(int), true, h->stream));
+    WPS_TRY(geo_buf((void**)&s->d_touched, &s->cap_touched, s->npts * sizeof(int), true, h->stream));
+    {
+        size_t cap = s->cap_def;
+        WPS_TRY(geo_buf((void**)&s->d_def, &cap, s->npts * sizeof(Deferred), false, h->stream));
+        WPS_TRY(geo_buf((void**)&s->d_def2, &s->cap_def, s->npts * sizeof(Deferred), false, h->stream));
+    }
+    if (!s->d_tbbox) WPS_CUDA(cudaMalloc((void**)&s->d_tbbox, 4 * sizeof(int)));
     WPS_CUDA(cudaMemsetAsync(s->d_invalid, 0, 4 * sizeof(unsigned long long), h->stream));
     if (host) WPS_CUDA(cudaStreamSynchronize(h->stream));
     s->field_open = true;
@@ -428,11 +568,15 @@ int wpsgpu_geogrid_level_begin(wpsgpu_handle_t h, const wpsgpu_geo_level* l)
     s->l = *l;
     size_t wb = (size_t)s->ny * s->nxw * sizeof(int);
     WPS_CUDA(cudaMemsetAsync(s->d_level, 0, wb, h->stream));     // bitarray_create(level_domain) (:1345)
-    if (l->itype == WPSGPU_SP_CONTINUOUS) WPS_CUDA(cudaMemsetAsync(s->d_count, 0, s->npts * s->nk * sizeof(float), h->stream));  // data_count = 0. (:1316)
+    if (l->itype == WPSGPU_SP_CONTINUOUS) {
+        WPS_TRY(geo_buf((void**)&s->d_count, &s->cap_count, s->npts * s->nk * sizeof(float), false, h->stream));
+        WPS_TRY(geo_buf((void**)&s->d_acc_sum, &s->cap_acc_sum, s->npts * s->nk * sizeof(double), true, h->stream));
+        WPS_CUDA(cudaMemsetAsync(s->d_count, 0, s->npts * s->nk * sizeof(float), h->stream));  // data_count = 0. (:1316)
+    }
     s->has_search = false; s->max_depth = 0;
     for (int k = 0; k < WPSGPU_MAX_OPS && l->ops[k]; ++k) if (l->ops[k] == WPSGPU_SEARCH) { s->has_search = true; s->max_depth = std::max(s->max_depth, l->opts[k]); }
     GeoK g = make_k(h);
-    k_geo_src_xy<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g.src, s->d_xlat, s->d_xlon, s->npts, s->d_src_xy);
+    k_geo_src_xy<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g.src, s->d_xlat, s->d_xlon, s->npts, s->d_src_xy, s->d_blk_xy);
     h->launches++;
     WPS_CUDA(cudaGetLastError());
     s->level_open = true;
@@ -451,7 +595,10 @@ static int geo_process_tile(wpsgpu_ctx* h, int smx, int sMx, int smy, int sMy, i
     if (s->l.itype == WPSGPU_CATEGORICAL || s->l.itype == WPSGPU_SP_CONTINUOUS) {
         WPS_TRY(geo_grow((void**)&s->d_wm, &s->wm_cap, (size_t)tnx * tny * sizeof(int2), h->stream));
         g.wm = s->d_wm;
-        k_geo_wm<<<dim3((tnx + 31) / 32, (tny + 7) / 8), b, 0, h->stream>>>(g);
+        // {jmin, imin} = 0x7f7f7f7f, {jmax, imax} = 0x80808080 (very negative)
+        WPS_CUDA(cudaMemsetAsync(s->d_tbbox, 0x7f, 2 * sizeof(int), h->stream));
+        WPS_CUDA(cudaMemsetAsync(s->d_tbbox + 2, 0x80, 2 * sizeof(int), h->stream));
+        k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, h->stream>>>(g);
         int inx = tnx - 2 * bdr, iny = tny - 2 * bdr;
         if (inx > 0 && iny > 0) k_geo_accum<<<dim3((inx + 31) / 32, (iny + 7) / 8), b, 0, h->stream>>>(g);
         // areas of the half-area rule (proc_point_module.F:178-197)

@@ -121,33 +121,62 @@ WPS_HD void llij_latlon(float lat, float lon, const DevProj& p, float& io, float
     if (i >= (float)p.nxmax + 0.5f) i = i - (float)(p.nxmax - p.nxmin + 1);
     io = i; jo = j;
 }
-// llij_lc, :1236-1290
-WPS_HD void llij_lc(float lat, float lon, const DevProj& p, float& io, float& jo)
+// llij_lc, :1236-1290.  Split into its latitude-only and longitude-only terms so that kernels walking a regular
+// lat-lon source grid can evaluate each once per row / column (same operations, same order, same bits).
+WPS_HD float llij_lc_rm(float lat, const DevProj& p)
+{
+    float tl1r = p.truelat1 * WPS_RAD_PER_DEG;
+    float ctl1r = t_cos(tl1r);
+    return p.rebydx * ctl1r / p.cone *
+           t_pow(t_tan((90.0f * p.hemi - lat) * WPS_RAD_PER_DEG / 2.0f) /
+                     t_tan((90.0f * p.hemi - p.truelat1) * WPS_RAD_PER_DEG / 2.0f),
+                 p.cone);
+}
+WPS_HD void llij_lc_sc(float lon, const DevProj& p, float& s, float& c)
 {
     float deltalon = lon - p.stdlon;
     if (deltalon > 180.0f) deltalon = deltalon - 360.0f;
     if (deltalon < -180.0f) deltalon = deltalon + 360.0f;
-    float tl1r = p.truelat1 * WPS_RAD_PER_DEG;
-    float ctl1r = t_cos(tl1r);
-    float rm = p.rebydx * ctl1r / p.cone *
-               t_pow(t_tan((90.0f * p.hemi - lat) * WPS_RAD_PER_DEG / 2.0f) /
-                         t_tan((90.0f * p.hemi - p.truelat1) * WPS_RAD_PER_DEG / 2.0f),
-                     p.cone);
     float arg = p.cone * (deltalon * WPS_RAD_PER_DEG);
-    float i = p.polei + p.hemi * rm * t_sin(arg);
-    float j = p.polej - rm * t_cos(arg);
+    s = t_sin(arg); c = t_cos(arg);
+}
+WPS_HD void llij_lc_combine(float rm, float s, float c, const DevProj& p, float& io, float& jo)
+{
+    float i = p.polei + p.hemi * rm * s;
+    float j = p.polej - rm * c;
     io = p.hemi * i; jo = p.hemi * j;
 }
-// llij_ps, :718-760
-WPS_HD void llij_ps(float lat, float lon, const DevProj& p, float& i, float& j)
+WPS_HD void llij_lc(float lat, float lon, const DevProj& p, float& io, float& jo)
 {
-    float reflon = p.stdlon + 90.0f;
+    float s, c;
+    float rm = llij_lc_rm(lat, p);
+    llij_lc_sc(lon, p, s, c);
+    llij_lc_combine(rm, s, c, p, io, jo);
+}
+// llij_ps, :718-760 (same split)
+WPS_HD float llij_ps_rm(float lat, const DevProj& p)
+{
     float scale_top = 1.0f + p.hemi * t_sin(p.truelat1 * WPS_RAD_PER_DEG);
     float ala = lat * WPS_RAD_PER_DEG;
-    float rm = p.rebydx * t_cos(ala) * scale_top / (1.0f + p.hemi * t_sin(ala));
+    return p.rebydx * t_cos(ala) * scale_top / (1.0f + p.hemi * t_sin(ala));
+}
+WPS_HD void llij_ps_sc(float lon, const DevProj& p, float& s, float& c)
+{
+    float reflon = p.stdlon + 90.0f;
     float alo = (lon - reflon) * WPS_RAD_PER_DEG;
-    i = p.polei + rm * t_cos(alo);
-    j = p.polej + p.hemi * rm * t_sin(alo);
+    s = t_sin(alo); c = t_cos(alo);
+}
+WPS_HD void llij_ps_combine(float rm, float s, float c, const DevProj& p, float& i, float& j)
+{
+    i = p.polei + rm * c;
+    j = p.polej + p.hemi * rm * s;
+}
+WPS_HD void llij_ps(float lat, float lon, const DevProj& p, float& i, float& j)
+{
+    float s, c;
+    float rm = llij_ps_rm(lat, p);
+    llij_ps_sc(lon, p, s, c);
+    llij_ps_combine(rm, s, c, p, i, j);
 }
 // llij_merc, :1320-1341
 WPS_HD void llij_merc(float lat, float lon, const DevProj& p, float& i, float& j)
