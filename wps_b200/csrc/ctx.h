@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <deque>
 #include <map>
 #include <string>
 #include <vector>
@@ -77,11 +78,11 @@ struct CoordCacheEntry {
 };
 
 struct QueuedSlab {
-    wpsgpu_proj proj;
+    const wpsgpu_proj* proj;      // interned in wpsgpu_ctx::proj_pool (the descriptor carries an 8 KB Gaussian table)
     wpsgpu_field_opts fo;
     wpsgpu_slab s;
-    bool gcell = false;      // average_gcell branch: cell averages first, the chain for cells no source pixel reached
-    wpsgpu_proj dom_proj;    // projection of the destination domain (gcell only)
+    bool gcell = false;           // average_gcell branch: cell averages first, the chain for cells no source pixel reached
+    const wpsgpu_proj* dom_proj = nullptr;   // projection of the destination domain (gcell only), interned
 };
 
 struct GeoState;  // geogrid.cu
@@ -101,6 +102,7 @@ struct wpsgpu_ctx {
     uint64_t grid_version_counter = 0;
     std::map<std::string, wps::CoordCacheEntry> coord_cache;
     std::vector<wps::QueuedSlab> queue;
+    std::deque<wpsgpu_proj> proj_pool;   // projections referenced by the queue; cleared when a flush has consumed it
     wps::GeoState* geo = nullptr;
     // small persistent device scratch (counters etc.)
     int* d_counters = nullptr;

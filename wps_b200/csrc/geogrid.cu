@@ -31,6 +31,7 @@ struct GeoState {
     // buffers kept across fields (grow-only): a geogrid run processes dozens of fields on the same patch
     size_t cap_count = 0, cap_acc_cnt = 0, cap_acc_sum = 0, cap_touched = 0, cap_bits = 0, cap_xy = 0, cap_def = 0, cap_blk = 0;
     float4* d_blk_xy = nullptr;       // per 256-point block: min/max of src_xy (lets the per-tile point pass skip far blocks)
+    int* d_cand = nullptr; size_t cap_cand = 0;   // points of the current tile that need the interpolation chain
     int* d_tbbox = nullptr;           // destination rows/columns credited by the current tile: {jmin, imin, jmax, imax}
     const float* d_gauss_src = nullptr; const float* d_gauss_dom = nullptr;
     bool own_field = false, own_ll = false;
@@ -345,8 +346,11 @@ __device__ __forceinline__ bool geo_point(const GeoK& g, const float2* __restric
     return false;
 }
 
+// The per-point pass of a tile in two steps.  k_geo_select (few registers, one thread per domain point, whole blocks
+// dropped by their coordinate range) lists the points that lie in the tile and have no value yet; k_geo_points then
+// runs the interpolation chain (a 220-register kernel) over that usually short list.
 __global__ void __launch_bounds__(256)
-k_geo_points(GeoK g, const float2* __restrict__ src_xy, Deferred* def, unsigned long long* def_cnt)
+k_geo_select(GeoK g, const float2* __restrict__ src_xy, int* __restrict__ cand, unsigned long long* __restrict__ cand_cnt)
 {
     {   // is_point_in_tile is monotone in each coordinate: if it fails for the block's extreme coordinates it fails for all
         float4 b = g.blk_xy[blockIdx.x];   // {xmin, xmax, ymin, ymax}
@@ -355,10 +359,27 @@ k_geo_points(GeoK g, const float2* __restrict__ src_xy, Deferred* def, unsigned 
     }
     size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= g.npts) return;
-    if (geo_point<0>(g, src_xy, p, nullptr)) {
-        unsigned long long slot = atomicAdd(def_cnt, 1ull);
-        Deferred d; d.slab = 0; d.idx = (int)p;
-        def[slot] = d;
+    int ii = (int)(p % g.nx), jj = (int)(p / g.nx);
+    float2 xy = src_xy[p];
+    if (!(g.smx + g.bdr <= f_floor(xy.x + 0.5f) && f_ceiling(xy.x - 0.5f) <= g.sMx - g.bdr &&
+          g.smy + g.bdr <= f_floor(xy.y + 0.5f) && f_ceiling(xy.y - 0.5f) <= g.sMy - g.bdr)) return;
+    if (bit_test(g.level, g.nxw, ii, jj)) return;
+    if (bit_test(g.processed, g.nxw, ii, jj)) { bit_set_atomic(g.level, g.nxw, ii, jj); return; }
+    cand[atomicAdd(cand_cnt, 1ull)] = (int)p;
+}
+
+__global__ void __launch_bounds__(256)
+k_geo_points(GeoK g, const float2* __restrict__ src_xy, const int* __restrict__ cand, const unsigned long long* __restrict__ cand_cnt,
+             Deferred* def, unsigned long long* def_cnt)
+{
+    const unsigned long long n = *cand_cnt;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x) {
+        size_t p = (size_t)cand[e];
+        if (geo_point<0>(g, src_xy, p, nullptr)) {
+            unsigned long long slot = atomicAdd(def_cnt, 1ull);
+            Deferred d; d.slab = 0; d.idx = (int)p;
+            def[slot] = d;
+        }
     }
 }
 __global__ void k_geo_points_warp(GeoK g, const float2* __restrict__ src_xy, const Deferred* def, const unsigned long long* def_cnt,
@@ -503,7 +524,7 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
     if (s->d_lit) cudaFree(s->d_lit);
     if (s->d_invalid) cudaFree(s->d_invalid);
     void* ptrs[] = { s->d_count, s->d_processed, s->d_level, s->d_src_xy, s->d_acc_cnt, s->d_acc_sum, s->d_touched, s->d_def, s->d_def2,
-                     s->d_blk_xy, s->d_tbbox };
+                     s->d_blk_xy, s->d_tbbox, s->d_cand };
     for (void* p : ptrs) if (p) cudaFree(p);
     delete s;
     h->geo = nullptr;
@@ -551,6 +572,7 @@ int wpsgpu_geogrid_field_begin(wpsgpu_handle_t h, const wpsgpu_geo_field* f)
         WPS_TRY(geo_buf((void**)&s->d_def, &cap, s->npts * sizeof(Deferred), false, h->stream));
         WPS_TRY(geo_buf((void**)&s->d_def2, &s->cap_def, s->npts * sizeof(Deferred), false, h->stream));
     }
+    WPS_TRY(geo_buf((void**)&s->d_cand, &s->cap_cand, s->npts * sizeof(int), false, h->stream));
     if (!s->d_tbbox) WPS_CUDA(cudaMalloc((void**)&s->d_tbbox, 4 * sizeof(int)));
     WPS_CUDA(cudaMemsetAsync(s->d_invalid, 0, 4 * sizeof(unsigned long long), h->stream));
     if (host) WPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -609,10 +631,11 @@ static int geo_process_tile(wpsgpu_ctx* h, int smx, int sMx, int smy, int sMy, i
         h->launches += 3;
         WPS_CUDA(cudaGetLastError());
     }
-    unsigned long long* cnt = s->d_invalid + 1;
-    WPS_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), h->stream));
-    k_geo_points<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->d_src_xy, s->d_def, cnt);
-    h->launches++;
+    unsigned long long* cnt = s->d_invalid + 1;   // [0] deferred to the warp pass, [1] to the literal pass, [2] candidates
+    WPS_CUDA(cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned long long), h->stream));
+    k_geo_select<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->d_src_xy, s->d_cand, cnt + 2);
+    k_geo_points<<<h->sm_count * 2, 256, 0, h->stream>>>(g, s->d_src_xy, s->d_cand, cnt + 2, s->d_def, cnt);
+    h->launches += 2;
     if (s->has_search) {
         k_geo_points_warp<<<h->sm_count * 8, 256, 0, h->stream>>>(g, s->d_src_xy, s->d_def, cnt, s->d_def2, cnt + 1);
         int R = std::min(std::max(s->max_depth, 1), std::max(std::max(tnx, tny), 1));

@@ -746,12 +746,23 @@ static int env_int(const char* name, int dflt, int lo, int hi)
     return x < lo ? lo : (x > hi ? hi : x);
 }
 
+// Projection descriptors are interned per flush: callers pass the same one for every slab of a file.
+static const wpsgpu_proj* intern_proj(wpsgpu_ctx* h, const wpsgpu_proj* p)
+{
+    const size_t head = offsetof(wpsgpu_proj, gauss_lat);
+    for (auto it = h->proj_pool.rbegin(); it != h->proj_pool.rend(); ++it)
+        if (memcmp(&*it, p, head) == 0 && (p->code != WPSGPU_PROJ_GAUSS || memcmp(it->gauss_lat, p->gauss_lat, sizeof(p->gauss_lat)) == 0))
+            return &*it;
+    h->proj_pool.push_back(*p);
+    return &h->proj_pool.back();
+}
+
 static int rel_code(char c) { return c == '<' ? REL_LT : (c == '>' ? REL_GT : REL_EQ); }
 
 static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
 {
     if (a.gcell || b.gcell) return false;   // average_gcell slabs carry their own accumulation buffers
-    if (memcmp(&a.proj, &b.proj, offsetof(wpsgpu_proj, gauss_lat)) != 0) return false;
+    if (a.proj != b.proj && memcmp(a.proj, b.proj, offsetof(wpsgpu_proj, gauss_lat)) != 0) return false;
     if (memcmp(a.fo.ops, b.fo.ops, sizeof(a.fo.ops)) || memcmp(a.fo.opts, b.fo.opts, sizeof(a.fo.opts))) return false;
     if (memcmp(&a.fo.missing_value, &b.fo.missing_value, sizeof(float)) || memcmp(&a.fo.fill_missing, &b.fo.fill_missing, sizeof(float)) ||
         memcmp(&a.fo.masked, &b.fo.masked, sizeof(float)) || memcmp(a.fo.mask_val, b.fo.mask_val, sizeof(a.fo.mask_val)) ||
@@ -839,7 +850,7 @@ int wpsgpu_metgrid_enqueue_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, 
     WPS_CHECK(slab->maxx >= slab->minx && slab->maxy >= slab->miny, -1, "empty source slab");
     WPS_CHECK(!slab->use_landmask || h->grids[slab->grid_id].d_landmask, -1, "use_landmask set but no landmask given for grid %d", slab->grid_id);
     QueuedSlab q;
-    q.proj = *src_proj; q.fo = *fo; q.s = *slab;
+    q.proj = intern_proj(h, src_proj); q.fo = *fo; q.s = *slab;
     h->queue.push_back(q);
     return 0;
 }
@@ -851,7 +862,7 @@ int wpsgpu_metgrid_enqueue_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_
     WPS_CHECK(dom_proj->init, -1, "domain projection not initialised");
     WPS_TRY(wpsgpu_metgrid_enqueue_slab(h, src_proj, fo, slab));
     h->queue.back().gcell = true;
-    h->queue.back().dom_proj = *dom_proj;
+    h->queue.back().dom_proj = intern_proj(h, dom_proj);
     return 0;
 }
 
@@ -907,6 +918,7 @@ struct FlushShared {
     std::vector<const float*> job_gauss;
     std::vector<Box> box;
     std::map<const void*, void*> staged;     // host pointer -> staged device copy (masks are shared by many slabs)
+    std::vector<char> tab;                   // host image of a pass's tables
     int max_depth = 0, max_span = 0;
 };
 
@@ -974,7 +986,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         // process_width, process_domain_module.F:2270-2278
         if (q0.s.process_bdy_width == 0) jb.pw = std::max(h->ed1 - h->sd1 + 1, h->ed2 - h->sd2 + 1);
         else { jb.pw = q0.s.process_bdy_width; if (q0.s.field_stagger != WPSGPU_M) jb.pw += 2; }
-        jb.proj = to_dev(q0.proj, fs.job_gauss[g]);
+        jb.proj = to_dev(*q0.proj, fs.job_gauss[g]);
         jb.minx = q0.s.minx; jb.maxx = q0.s.maxx; jb.miny = q0.s.miny; jb.maxy = q0.s.maxy; jb.bdr = q0.s.bdr;
         size_t sbytes = (size_t)(jb.maxx - jb.minx + 1) * (jb.maxy - jb.miny + 1) * sizeof(float);
         for (int m = 0; m < 3; ++m) {
@@ -1059,23 +1071,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         }
     }
     for (const CopyRun& r : in_runs) WPS_CUDA(cudaMemcpyAsync(r.d, r.h, r.bytes, cudaMemcpyHostToDevice, s_in));
-    Job* d_jobs = (Job*)h->arena.take(sizeof(Job) * njobs);
-    SlabPtrs* d_sp = (SlabPtrs*)h->arena.take(sizeof(SlabPtrs) * nq);
-    int* d_cls = (int*)h->arena.take(sizeof(int) * 6 * (njobs + 1));
-    WPS_CHECK(d_jobs && d_sp && d_cls, -3, "device arena exhausted (tables)");
-    WPS_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(Job) * njobs, cudaMemcpyHostToDevice, s_in));
-    WPS_CUDA(cudaMemcpyAsync(d_sp, sp.data(), sizeof(SlabPtrs) * nq, cudaMemcpyHostToDevice, s_in));
-    int* d_cls_jobs[2]; int* d_cls_tile0[2];
-    for (int c = 0; c < 2; ++c) {
-        d_cls_jobs[c] = d_cls + (2 * c) * (njobs + 1);
-        d_cls_tile0[c] = d_cls + (2 * c + 1) * (njobs + 1);
-        if (!cls_jobs[c].empty()) {
-            WPS_CUDA(cudaMemcpyAsync(d_cls_jobs[c], cls_jobs[c].data(), sizeof(int) * cls_jobs[c].size(), cudaMemcpyHostToDevice, s_in));
-            WPS_CUDA(cudaMemcpyAsync(d_cls_tile0[c], cls_tile0[c].data(), sizeof(int) * cls_tile0[c].size(), cudaMemcpyHostToDevice, s_in));
-        }
-    }
-    int* d_fast_word0 = d_cls + 4 * (njobs + 1);
-    int* d_pack_jobs = d_cls + 5 * (njobs + 1);
+    // All tables of this pass travel in ONE copy: [jobs | slab pointers | six int lists of njobs+1 entries]
     std::vector<int> pack_jobs;
     int pack_cells = 0, pack_max = 0;
     for (int j : cls_jobs[1])
@@ -1085,9 +1081,30 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             pack_max = std::max(pack_max, jobs[j].npack);
         }
     WPS_CHECK(pack_jobs.size() < 65536, -3, "too many packed jobs in one flush");
-    if (!pack_jobs.empty()) WPS_CUDA(cudaMemcpyAsync(d_pack_jobs, pack_jobs.data(), sizeof(int) * pack_jobs.size(), cudaMemcpyHostToDevice, s_in));
     WPS_CHECK(fast_words < 2000000000LL, -3, "too many output words in one flush");
-    if (!fast_word0.empty()) WPS_CUDA(cudaMemcpyAsync(d_fast_word0, fast_word0.data(), sizeof(int) * fast_word0.size(), cudaMemcpyHostToDevice, s_in));
+    const size_t off_sp = (sizeof(Job) * njobs + 255) & ~size_t(255);
+    const size_t off_cls = (off_sp + sizeof(SlabPtrs) * nq + 255) & ~size_t(255);
+    const size_t tab_bytes = off_cls + sizeof(int) * 6 * (njobs + 1);
+    std::vector<char>& tab = fs.tab;
+    tab.assign(tab_bytes, 0);
+    memcpy(tab.data(), jobs.data(), sizeof(Job) * njobs);
+    memcpy(tab.data() + off_sp, sp.data(), sizeof(SlabPtrs) * nq);
+    {
+        int* cls = reinterpret_cast<int*>(tab.data() + off_cls);
+        const std::vector<int>* lists[6] = { &cls_jobs[0], &cls_tile0[0], &cls_jobs[1], &cls_tile0[1], &fast_word0, &pack_jobs };
+        for (int c = 0; c < 6; ++c)
+            if (!lists[c]->empty()) memcpy(cls + (size_t)c * (njobs + 1), lists[c]->data(), sizeof(int) * lists[c]->size());
+    }
+    char* d_tab = (char*)h->arena.take(tab_bytes);
+    WPS_CHECK(d_tab != nullptr, -3, "device arena exhausted (tables)");
+    WPS_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab_bytes, cudaMemcpyHostToDevice, s_in));   // pageable source: staged before the call returns
+    Job* d_jobs = (Job*)d_tab;
+    SlabPtrs* d_sp = (SlabPtrs*)(d_tab + off_sp);
+    int* d_cls = (int*)(d_tab + off_cls);
+    int* d_cls_jobs[2] = { d_cls, d_cls + 2 * (njobs + 1) };
+    int* d_cls_tile0[2] = { d_cls + (njobs + 1), d_cls + 3 * (njobs + 1) };
+    int* d_fast_word0 = d_cls + 4 * (njobs + 1);
+    int* d_pack_jobs = d_cls + 5 * (njobs + 1);
     Deferred *d_def = nullptr, *d_def2 = nullptr;
     unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(h->d_counters);
     if (any_search) {
@@ -1116,8 +1133,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         WPS_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double) * npts, h->stream));
         WPS_CUDA(cudaMemsetAsync(d_gcnt, 0, sizeof(int) * npts, h->stream));
         const float* d_gauss_dom = nullptr;
-        if (q0.dom_proj.code == WPSGPU_PROJ_GAUSS) WPS_TRY(upload_gauss(h, q0.dom_proj, &d_gauss_dom));
-        DevProj dom = to_dev(q0.dom_proj, d_gauss_dom);
+        if (q0.dom_proj->code == WPSGPU_PROJ_GAUSS) WPS_TRY(upload_gauss(h, *q0.dom_proj, &d_gauss_dom));
+        DevProj dom = to_dev(*q0.dom_proj, d_gauss_dom);
         dim3 b2(32, 8);
         k_gc_wm<<<dim3((snx + 31) / 32, (sny + 7) / 8), b2, 0, h->stream>>>(jb.proj, dom, jb.minx, jb.miny, snx, sny, jb.sm1, jb.em1, jb.sm2, jb.em2, d_wm);
         const int bw = jb.maxx - jb.minx + 1 - 2 * jb.bdr;
@@ -1228,6 +1245,8 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     WPS_CUDA(cudaSetDevice(h->device));
     std::vector<QueuedSlab> queue;
     queue.swap(h->queue);
+    h->queue.reserve(queue.size());
+    struct PoolClear { wpsgpu_ctx* h; ~PoolClear() { h->proj_pool.clear(); } } pool_clear{h};   // `queue` points into the pool
     const bool host = h->ptr_mode == WPSGPU_PTR_HOST;
     const int nq = (int)queue.size();
 
@@ -1251,18 +1270,18 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
     for (int g = 0; g < njobs; ++g) {
         const QueuedSlab& q0 = queue[groups[g][0]];
         const DstGrid& dg = h->grids[q0.s.grid_id];
-        std::string key = cache_key(q0.s.grid_id, q0.proj);
+        std::string key = cache_key(q0.s.grid_id, *q0.proj);
         auto it = h->coord_cache.find(key);
         if (it == h->coord_cache.end() || it->second.grid_version != dg.version) {
             CoordCacheEntry e;
             e.grid_version = dg.version;
             e.d_gauss = nullptr;
             WPS_CUDA(cudaMalloc((void**)&e.d_xy, dg.npts() * sizeof(float2)));
-            if (q0.proj.code == WPSGPU_PROJ_GAUSS) {
+            if (q0.proj->code == WPSGPU_PROJ_GAUSS) {
                 WPS_CUDA(cudaMalloc((void**)&e.d_gauss, sizeof(float) * WPSGPU_MAX_GAUSS));
-                WPS_CUDA(cudaMemcpyAsync(e.d_gauss, q0.proj.gauss_lat, sizeof(float) * WPSGPU_MAX_GAUSS, cudaMemcpyHostToDevice, h->stream));
+                WPS_CUDA(cudaMemcpyAsync(e.d_gauss, q0.proj->gauss_lat, sizeof(float) * WPSGPU_MAX_GAUSS, cudaMemcpyHostToDevice, h->stream));
             }
-            DevProj dp = to_dev(q0.proj, e.d_gauss);
+            DevProj dp = to_dev(*q0.proj, e.d_gauss);
             int64_t n = (int64_t)dg.npts();
             k_coord_cache<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dp, dg.d_xlat, dg.d_xlon, n, e.d_xy);
             // source-cell bounding box of this destination grid (read back once per cached coordinate set)
