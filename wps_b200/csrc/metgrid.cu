@@ -31,7 +31,7 @@ struct Job {
     unsigned long long defer_base;  // first slot of this job's deferred-entry region (jobs with SEARCH only)
     // packed sixteen_pt fast path (fast != 0): records over the source-cell bounding box of the destination grid
     int fast, bx0, by0, bnx, bny, npack;
-    const float4* rec;           // [npack][bny][bnx][6] = {b, c, t1, t2, t3, t4} x 4 packed levels
+    const float4* rec;           // [npack][bny][ceil(bnx/8)][6][8]: terms {b, c, t1, t2, t3, t4} of 8 cells, float4 = 4 packed levels
     const unsigned char* cf;     // [npack][bny][bnx] bit lv = 4x4 stencil anchored here is "clean" for level lv
     float f_negzero, f_one;      // -0.0f and 1.0f as run-time values (see mul2/add2 in the packed kernel)
     int gcell;                   // average_gcell branch (:2331-2478): masked=both is not special there
@@ -358,9 +358,13 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, co
         if (both && clean && cleanB) cfbits |= 16u << lv;
     }
     size_t o = ((size_t)pack * jb.bny + cj) * jb.bnx + ci;
-    float4* rec = const_cast<float4*>(jb.rec) + o * 6;
+    // layout [pack][row][group of 8 cells][term f][cell in group]: one 128-byte line holds one term of 8 neighbouring
+    // cells, so the two cells a quarter-warp of destination points typically spans are served by one L1 wavefront,
+    // and the six terms of a group are six consecutive lines
+    const int bnx8 = (jb.bnx + 7) >> 3;
+    float4* rec = const_cast<float4*>(jb.rec) + ((((size_t)pack * jb.bny + cj) * bnx8 + (ci >> 3)) * 6) * 8 + (ci & 7);
 #pragma unroll
-    for (int f = 0; f < 6; ++f) rec[f] = make_float4(out[f][0], out[f][1], out[f][2], out[f][3]);
+    for (int f = 0; f < 6; ++f) rec[f * 8] = make_float4(out[f][0], out[f][1], out[f][2], out[f][3]);
     const_cast<unsigned char*>(jb.cf)[o] = (unsigned char)cfbits;
 }
 
@@ -430,6 +434,8 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
     bool fastpt = false, fillpt = false;
     float x = 0.0f, y = 0.0f;
     int roff[4] = {0, 0, 0, 0}, cfoff = 0, cfshift = 0;
+    const int bnx8 = (jb.bnx + 7) >> 3;
+    const size_t rec_stride = (size_t)jb.bny * bnx8 * 48;   // float4 per pack
     if (active) {
         float2 xy = __ldg(jb.xy + idx);
         int di = jb.sm1 + ii, dj = jb.sm2 + jj;
@@ -456,7 +462,7 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
                 for (int l = 0; l < 4; ++l) {
                     int r = min(max(j + l - 1, jb.miny), jb.maxy) - jb.by0;
                     if (r < 0 || r >= jb.bny) fastpt = false;
-                    roff[l] = (r * jb.bnx + (i - jb.bx0)) * 6;
+                    roff[l] = ((r * bnx8 + ((i - jb.bx0) >> 3)) * 6) * 8 + ((i - jb.bx0) & 7);
                 }
                 cfoff = (j - jb.by0) * jb.bnx + (i - jb.bx0);
             }
@@ -475,13 +481,13 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             const float4* r = rec + roff[l];
-            float4 b = __ldg(r), c = __ldg(r + 1), t1 = __ldg(r + 2), t2 = __ldg(r + 3), t3 = __ldg(r + 4), t4 = __ldg(r + 5);
+            float4 b = __ldg(r), c = __ldg(r + 8), t1 = __ldg(r + 16), t2 = __ldg(r + 24), t3 = __ldg(r + 32), t4 = __ldg(r + 40);
             r01[l] = xpass2(make_float2(b.x, b.y), make_float2(c.x, c.y), make_float2(t1.x, t1.y), make_float2(t2.x, t2.y),
                             make_float2(t3.x, t3.y), make_float2(t4.x, t4.y), x2, omx2, k2);
             r23[l] = xpass2(make_float2(b.z, b.w), make_float2(c.z, c.w), make_float2(t1.z, t1.w), make_float2(t2.z, t2.w),
                             make_float2(t3.z, t3.w), make_float2(t4.z, t4.w), x2, omx2, k2);
         }
-        rec += pack_stride * 6;
+        rec += rec_stride;
         cf += pack_stride;
         float2 v01 = ypass2(r01[0], r01[1], r01[2], r01[3], y2, omy2, k2);
         float2 v23 = ypass2(r23[0], r23[1], r23[2], r23[3], y2, omy2, k2);
@@ -1015,7 +1021,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
         if (jb.fast == 1) {
             size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
-            jb.rec = (const float4*)h->arena.take(cells * 6 * sizeof(float4));
+            size_t cells8 = (size_t)jb.npack * ((jb.bnx + 7) / 8 * 8) * jb.bny;
+            jb.rec = (const float4*)h->arena.take(cells8 * 6 * sizeof(float4));
             jb.cf = (const unsigned char*)h->arena.take(cells);
             WPS_CHECK(jb.rec && jb.cf, -3, "device arena exhausted (packed records)");
         }
@@ -1333,7 +1340,7 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
                 if (x1 >= x0 && y1 >= y0 && (size_t)(x1 - x0 + 1) * (size_t)(y1 - y0 + 1) * 2 <= dg.npts()) {
                     b.fast = 1; b.bx0 = (int)x0; b.by0 = (int)y0; b.bnx = (int)(x1 - x0 + 1); b.bny = (int)(y1 - y0 + 1);
                     b.npack = ((int)groups[g].size() + 3) / 4;
-                    need += (size_t)b.npack * b.bnx * b.bny * (6 * sizeof(float4) + 1) + 1024;
+                    need += (size_t)b.npack * (b.bnx + 8) * b.bny * (6 * sizeof(float4) + 1) + 1024;
                 }
             } else if (q0.fo.ops[0] == WPSGPU_FOUR_POINT) b.fast = 2;
             else if (q0.fo.ops[0] == WPSGPU_N_NEIGHBOR) b.fast = 3;
