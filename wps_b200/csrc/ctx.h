@@ -116,6 +116,8 @@ struct wpsgpu_ctx {
     double last_points = 0.0;
     double last_pts3[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer pipeline
+    cudaStream_t s_side = nullptr;                  // slow-bitmap passes overlapping the first-method kernels
+    std::vector<cudaEvent_t> ev_pool;               // per-job fork events for s_side
     cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
     bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };
