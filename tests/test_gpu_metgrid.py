@@ -383,3 +383,70 @@ def test_average_gcell_branch(orc, handle, case):
     # the branch did something: a good share of the cells are averages, and some cells fell through to the chain
     covered = bits_to_bool(npw, nx).mean()
     assert 0.2 < covered <= 1.0
+
+
+def test_config2_full_size_windows_and_kernel_agreement(orc, handle):
+    """BASELINE config 2 at full size (GFS 0.25-degree 1440x721 -> 3-km CONUS Lambert 1799x1059), one slab of every
+    METGRID.TBL chain family: (1) the first-method kernels and the generic kernel -- two independent device paths --
+    must agree bit for bit over all 1.9 M points; (2) the oracle, evaluated on 48x40 windows spread over the domain
+    (corners, coast lines, interior), must match the device result bit for bit there."""
+    from wps_b200 import capi, synth
+    cfg = synth.CONFIGS["config2"]
+    sx, sy, dlat, dlon = cfg["src"]
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = cfg["dom"]
+    orc.set_transc_mode(1)
+    odom, gdom = conus_like(nx, ny, dx, truelat1=tl1, truelat2=tl2, stand_lon=slon, ref_lat=rlat, ref_lon=rlon)
+    xlat, xlon = handle.xytoll_grid(gdom, capi.M, 1, 1, nx, ny)
+    osrc, gsrc = latlon_source(sx, sy, dlat, dlon, 90.0, 0.0)
+    ls = synth.landsea_np(sx, sy)
+    lsh = synth.add_halo(ls)
+    lam = np.deg2rad(xlon) % (2 * np.pi)
+    landmask = (synth.landsea_fn(np, lam, np.deg2rad(xlat)) > synth.LAND_THRESHOLD).astype(np.float32)
+    cases = [  # chain, missing, fill, masked, mask triple, mask values, kind
+        (synth.C3D, 1e20, 0.0, -2.0, (None, None, None), (1e20, 1e20, 1e20), "smooth"),
+        (synth.C3D, 1e20, 0.0, -2.0, (None, None, None), (1e20, 1e20, 1e20), "wind"),
+        ("four_pt+average_4pt", 1e20, 1e20, -2.0, (None, None, None), (1e20, 1e20, 1e20), "smooth"),
+        ("nearest_neighbor", 1e20, -1.0, -2.0, (None, None, None), (1e20, 1e20, 1e20), "landsea"),
+        (synth.SOIL, -1e30, 285.0, 0.0, (lsh, None, None), (0.0, 1e20, 1e20), "land"),
+        (synth.SOIL, 1e20, 0.0, -1.0, (None, lsh, lsh), (1e20, 1.0, 0.0), "smooth"),
+    ]
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_landmask(0, landmask)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    slabs = [synth.add_halo(synth.slab_np(sx, sy, 7 + k, c[6], landsea=ls, missing=np.float32(c[1]))) for k, c in enumerate(cases)]
+    results = {}
+    for disable_fast in (False, True):
+        handle.debug_disable_fast(disable_fast)
+        outs = []
+        for c, slab in zip(cases, slabs):
+            fo = capi.field_opts(c[0], np.float32(c[1]), np.float32(c[2]), c[3], c[5])
+            r = np.zeros((ny, nx), np.float32)
+            npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+            handle.metgrid_enqueue_slab(gsrc, fo, slab, -2, 1, 3, 0, capi.M, r, npw, masks=c[4], use_landmask=True)
+            outs.append((r, npw))
+        handle.metgrid_flush()
+        results[disable_fast] = outs
+    handle.debug_disable_fast(False)
+    for k, ((r_f, n_f), (r_g, n_g)) in enumerate(zip(results[False], results[True])):
+        assert (n_f == n_g).all(), "case %d: new_pts differ between the two device paths" % k
+        assert_bitexact(r_f, r_g, "case %d: first-method kernels vs generic kernel, full size" % k)
+    # oracle on windows: corners, centre, and two windows on the synthetic coast line
+    coast = np.argwhere(np.abs(np.diff(landmask, axis=1)) > 0)
+    wins = [(1, 1), (nx - 47, 1), (1, ny - 39), (nx - 47, ny - 39), (nx // 2, ny // 2)]
+    for pick in (len(coast) // 3, 2 * len(coast) // 3):
+        cj, ci = coast[pick]
+        wins.append((int(min(max(ci - 20, 1), nx - 47)), int(min(max(cj - 20, 1), ny - 39))))
+    xlat_o, xlon_o = orc.get_lat_lon_fields(odom, 1, 1, nx, ny, orc.M)
+    assert_bitexact(xlat, xlat_o, "device xlat vs oracle")
+    assert_bitexact(xlon, xlon_o, "device xlon vs oracle")
+    for k, (c, slab) in enumerate(zip(cases, slabs)):
+        fo_o = orc.field_opts(c[0], np.float32(c[1]), np.float32(c[2]), c[3], c[5])
+        r_dev, n_dev = results[False][k]
+        bits_dev = bits_to_bool(n_dev, nx)
+        for (i0, j0) in wins:
+            i1, j1 = i0 + 47, j0 + 39
+            r_ref, n_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), slab, -2, 1, 3, mask=c[4][0],
+                                                land_mask=c[4][1], water_mask=c[4][2], landmask=landmask, sub=(i0, i1, j0, j1))
+            win = (slice(j0 - 1, j1), slice(i0 - 1, i1))
+            assert (bits_to_bool(n_ref, nx)[win] == bits_dev[win]).all(), "case %d window %s: new_pts" % (k, (i0, j0))
+            assert_bitexact(r_dev[win], r_ref[win], "case %d window %s" % (k, (i0, j0)))
