@@ -191,3 +191,51 @@ def test_raw_tile_decode(orc, handle):
             handle.geogrid_field_finish()
             res.append(field)
         assert_bitexact(res[0], res[1], "raw decode wordsize=%d signed=%d endian=%d row_order=%d" % (wordsize, signed, endian, row_order))
+
+
+@pytest.mark.parametrize("kind", ["categorical", "sp_continuous"])
+def test_patch_sharded_field_equals_whole_domain(orc, handle, kind):
+    """geogrid shards by destination patch (parallel_get_tile_dims) with the +-3 halo process_tile adds
+    and no exchange step.  Four patches, each fed only the tiles that overlap it, reproduce the whole-domain field on
+    their own window (halo included) -- which is what makes one-GPU-per-patch runs equal to a single-GPU run."""
+    from wps_b200 import capi
+    from wps_b200.shard import patch_bounds
+    orc.set_transc_mode(1)
+    nx, ny, dx, dxdeg = 60, 50, 9000.0, 0.00833333
+    odom, gdom = conus_like(nx, ny, dx, 30.0, 60.0, -98.0, 39.0, -105.0)
+    kw = dict(dlat=dxdeg, dlon=dxdeg, known_x=1.0, known_y=1.0, known_lat=-89.99583, known_lon=-179.99583)
+    gsrc = capi.push_source_projection(capi.PROJ_LATLON, **kw)
+    if kind == "categorical":
+        itype, chain, nk, bdr, tile_fn, tile_n = capi.CATEGORICAL, "nearest_neighbor", 21, 0, cat_tile, 120
+    else:
+        itype, chain, nk, bdr, tile_fn, tile_n = capi.SP_CONTINUOUS, "average_gcell(4.0)+four_pt+average_4pt", 1, 3, topo_tile, 120
+
+    def run(x0, x1, y0, y1):
+        gx, gy = x1 - x0 + 1 + 6, y1 - y0 + 1 + 6
+        xlat, xlon = orc.get_lat_lon_fields(odom, x0 - 3, y0 - 3, gx, gy, 1)
+        dom_ll = (float(xlat.min()) - 0.3, float(xlat.max()) + 0.3, float(xlon.min()) - 0.3, float(xlon.max()) + 0.3)
+        field = np.zeros((nk, gy, gx), np.float32)
+        handle.geogrid_field_begin(gdom, 1, xlat, xlon, x0 - 3, y0 - 3, 1, field, None)
+        handle.geogrid_level_begin(gsrc, 1, itype, chain, 1e20, 1e20, -1.0, None, 1, 1)
+        tiles = tiles_for(dom_ll, dxdeg, tile_n, bdr)
+        for (tx, ty) in tiles:
+            handle.geogrid_add_tile(tile_fn(tx, ty, tile_n + 2 * bdr, 1 if itype == capi.CATEGORICAL else nk), tx, ty, 1, bdr)
+        handle.geogrid_level_end()
+        handle.geogrid_field_finish()
+        return field, len(tiles)
+
+    whole, nt_whole = run(1, nx, 1, ny)
+    nts = []
+    for rank in range(4):
+        x0, x1, y0, y1 = patch_bounds(nx, ny, 4, rank)
+        part, nt = run(x0, x1, y0, y1)
+        nts.append(nt)
+        ref = whole[:, y0 - 1:y1 + 6, x0 - 1:x1 + 6]     # whole-domain array starts at (-2, -2): patch window incl. halo
+        # the outermost ring of any window only collects the source pixels on its inner half (the inside test of
+        # where_maps_to, proc_point_module.F:296-303), so it is compared on the inner 2 halo cells + the patch itself
+        part, ref = part[:, 1:-1, 1:-1], ref[:, 1:-1, 1:-1]
+        if kind == "categorical":
+            assert_bitexact(part, ref, "patch %d" % rank)
+        else:
+            np.testing.assert_allclose(part, ref, rtol=1e-6, atol=0.0)
+    assert min(nts) <= nt_whole

@@ -130,3 +130,55 @@ def test_sharded_run_gloo_world2(tmp_path):
                           "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK 15" in out.stdout
+
+
+def test_patch_decomposition_matches_rsl_rule():
+    """parallel_get_tile_dims / task_for_point (parallel_module.F:103-148, 218-267): hand-derived cases and the
+    partition property (every point owned exactly once, patches are rectangles)."""
+    from wps_b200.shard import _task_1d, patch_bounds, proc_grid
+    assert [proc_grid(n) for n in (1, 2, 3, 4, 6, 8, 12)] == [(1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (2, 4), (3, 4)]
+    # idim=10 over 3 tasks: rem=1 -> a=0, b=6: sizes 3,3,4 (the remainder goes to the tail when rem/2 == 0)
+    assert [_task_1d(i, 1, 10, 3) for i in range(1, 11)] == [0, 0, 0, 1, 1, 1, 2, 2, 2, 2]
+    # idim=11 over 4 tasks: rem=3 -> a=1*3=3, b=3+1*2=5: sizes 3,2,3,3
+    assert [_task_1d(i, 1, 11, 4) for i in range(1, 12)] == [0, 0, 0, 1, 1, 2, 2, 2, 3, 3, 3]
+    for (idim, jdim, n) in [(1799, 1059, 8), (101, 101, 6), (74, 61, 4), (10, 7, 3)]:
+        owner = np.zeros((jdim, idim), np.int32) - 1
+        for r in range(n):
+            x0, x1, y0, y1 = patch_bounds(idim, jdim, n, r)
+            assert (owner[y0 - 1:y1, x0 - 1:x1] == -1).all()
+            owner[y0 - 1:y1, x0 - 1:x1] = r
+        assert (owner >= 0).all()
+
+
+def test_patch_decomposition_gloo_world2(tmp_path):
+    """geogrid shards by destination patch: two gloo ranks take the patches of a 2-task run, accumulate a synthetic
+    categorical dataset onto their own patch with numpy, and the gathered result equals the single-task result."""
+    script = tmp_path / "p.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np, torch, torch.distributed as dist
+        from wps_b200.shard import patch_bounds
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        idim, jdim, ncat = 37, 29, 5
+        rng = np.random.default_rng(3)
+        # source pixels with a destination cell and a category each (what where_maps_to + the tile give)
+        px = rng.integers(1, idim + 1, 20000); py = rng.integers(1, jdim + 1, 20000); cat = rng.integers(0, ncat, 20000)
+        def accumulate(x0, x1, y0, y1):
+            f = np.zeros((ncat, jdim, idim), np.float32)
+            m = (px >= x0) & (px <= x1) & (py >= y0) & (py <= y1)
+            np.add.at(f, (cat[m], py[m] - 1, px[m] - 1), 1.0)
+            return f
+        x0, x1, y0, y1 = patch_bounds(idim, jdim, world, rank)
+        mine = torch.from_numpy(accumulate(x0, x1, y0, y1))
+        dist.all_reduce(mine)     # stands for gather_whole_field_r: patches are disjoint, so the sum is the gather
+        if rank == 0:
+            assert np.array_equal(mine.numpy(), accumulate(1, idim, 1, jdim))
+            print("OK", x0, x1, y0, y1)
+        dist.destroy_process_group()
+    """ % ROOT))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29613", str(script)], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "OK 1 37 1 14" in out.stdout

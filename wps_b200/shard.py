@@ -28,3 +28,48 @@ def shard_slabs(keys: Sequence[Tuple[str, int]], world: int, pairs=(("UU", "VV")
     for r in out:
         out[r].sort()
     return out
+
+
+# ---- geogrid: destination-patch decomposition (the reference's own MPI decomposition) ---------------------------
+def proc_grid(nprocs: int) -> Tuple[int, int]:
+    """(nproc_x, nproc_y) as square as possible, first minimum wins -- parallel_module.F:62-74."""
+    mini, npx, npy = 2 * nprocs, 1, nprocs
+    for m in range(1, nprocs + 1):
+        if nprocs % m == 0:
+            n = nprocs // m
+            if abs(m - n) < mini:
+                mini, npx, npy = abs(m - n), m, n
+    return npx, npy
+
+
+def _task_1d(p: int, ds: int, de: int, nproc: int) -> int:
+    """One direction of task_for_point (parallel_module.F:218-267, RSL_LITE's rule): the remainder rows are split
+    between the first rem/2 and the last rem - rem/2 tasks.  Fortran integer division == // for these non-negatives."""
+    i, ids, ide = p - 1, ds - 1, de - 1
+    idim = ide - ids + 1
+    i = min(max(i, ids), ide)
+    rem = idim % nproc
+    a = (rem // 2) * ((idim // nproc) + 1)
+    b = a + (nproc - rem) * (idim // nproc)
+    if i - ids < a:
+        return (i - ids) // ((idim // nproc) + 1)
+    if i - ids < b:
+        return (a // ((idim // nproc) + 1)) + (i - a - ids) // ((b - a) // (nproc - rem))
+    return (a // ((idim // nproc) + 1)) + (b - a - ids) // ((b - a) // (nproc - rem)) + (i - b - ids) // ((idim // nproc) + 1)
+
+
+def task_for_point(i: int, j: int, ids: int, ide: int, jds: int, jde: int, npx: int, npy: int) -> Tuple[int, int]:
+    return _task_1d(i, ids, ide, npx), _task_1d(j, jds, jde, npy)
+
+
+def patch_bounds(idim: int, jdim: int, nprocs: int, rank: int) -> Tuple[int, int, int, int]:
+    """(my_minx, my_maxx, my_miny, my_maxy), 1-based inclusive -- parallel_get_tile_dims, parallel_module.F:103-148.
+    rank -> (my_x, my_y) = (rank mod nproc_x, rank / nproc_x) (:78-79).  One rank = one GPU: every GPU accumulates the
+    source tiles overlapping its own patch (+ the caller's halo), no exchange step."""
+    npx, npy = proc_grid(nprocs)
+    my_x, my_y = rank % npx, rank // npx
+    xs = [i for i in range(1, idim + 1) if _task_1d(i, 1, idim, npx) == my_x]
+    ys = [j for j in range(1, jdim + 1) if _task_1d(j, 1, jdim, npy) == my_y]
+    if not xs or not ys:
+        return (-1, -1, -1, -1)
+    return xs[0], xs[-1], ys[0], ys[-1]
