@@ -169,6 +169,20 @@ int wpsgpu_metgrid_enqueue_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj *src_
 int wpsgpu_metgrid_gcell_slab(wpsgpu_handle_t h, const wpsgpu_proj *src_proj, const wpsgpu_proj *dom_proj,
                               const wpsgpu_field_opts *fo, const wpsgpu_slab *slab);
 
+/* fill_missing_levels, the vertical-interpolation loop (process_domain_module.F:2862-2921) over the nlev levels of
+ * one 3-d field: a point whose valid_mask bit is clear at level k receives the linear interpolation in `levels`
+ * between the nearest valid levels below and above in the list (storage_get_levels order), and its bit is set;
+ * levels filled earlier count as valid neighbours for later ones, as in the reference's k loop.
+ * levels, r_arr and valid_mask are HOST arrays of nlev entries; the arrays r_arr[k] / valid_mask[k] point to follow
+ * the handle's pointer mode (nx*ny floats, ny*ceil(nx/32) words). */
+int wpsgpu_fill_missing_levels(wpsgpu_handle_t h, int32_t nlev, const int32_t *levels, float *const *r_arr,
+                               int32_t *const *valid_mask, int32_t nx, int32_t ny);
+/* create_level (process_domain_module.F:3191-3332): a new level filled with a constant (src_* NULL; every valid bit
+ * set, :3263-3272) or copied from another field's level together with its valid bits (:3300-3312).  The storage
+ * lookups around it ("already exists; leaving it alone", source missing) stay with the caller. */
+int wpsgpu_create_level(wpsgpu_handle_t h, int32_t nx, int32_t ny, float fill_const, const float *src_r_arr,
+                        const int32_t *src_valid_mask, float *r_arr, int32_t *valid_mask);
+
 /* met_to_map / map_to_met -> metmap_xform (rotate_winds_module.F:23-387), C grid, nlev levels at once.
  * u(us1:ue1,us2:ue2,nlev), v(vs1:ve1,vs2:ve2,nlev) in place; masks are per-level bit arrays laid out
  * [nlev][ny][nwords].  idir=+1 map_to_met (proj = source projection), -1 met_to_map (proj = domain). */

@@ -426,3 +426,14 @@ def search_order(x0, y0, sx, ex, sy, ey, maxdepth, maxn=100000):
     ys = np.zeros(maxn, np.int32)
     n = lib().orc_search_order(int(x0), int(y0), int(sx), int(ex), int(sy), int(ey), int(maxdepth), iptr(xs), iptr(ys), maxn)
     return xs[:n], ys[:n]
+
+
+def fill_missing_levels(levels, r_arr, valid):
+    """fill_missing_levels vertical interpolation (process_domain_module.F:2862-2921); r_arr [nlev][ny][nx],
+    valid [nlev][ny][nxw]; returns updated copies."""
+    r = np.array(r_arr, np.float32, order="C")
+    v = np.array(valid, np.int32, order="C")
+    nlev, ny, nx = r.shape
+    lv = np.ascontiguousarray(levels, np.int32)
+    lib().orc_fill_missing_levels(int(nlev), lv.ctypes.data_as(C.c_void_p), fptr(r), iptr(v), int(nx), int(ny))
+    return r, v

@@ -312,3 +312,31 @@ void orc_metmap_xform(const orc_proj *proj, float *u, const int32_t *u_mask, flo
 #undef UU
 #undef VV
 }
+
+/* fill_missing_levels, the vertical-interpolation loop -- process_domain_module.F:2862-2921.  levels[] in the order
+ * storage_get_levels returns them; r_arr [nlev][ny][nx], valid [nlev][ny][nxw] (bit arrays), both updated in place. */
+void orc_fill_missing_levels(int nlev, const int32_t *levels, float *r_arr, int32_t *valid, int nx, int ny)
+{
+    int nxw = (nx + 31) / 32;
+    long np = (long)nx * ny, nw = (long)ny * nxw;
+    if (nlev <= 1) return;                                   /* "If this isn't a 3-d array, nothing to do" */
+    for (int k = 0; k < nlev; ++k) {
+        for (int jx = 1; jx <= ny; ++jx) {
+            for (int ix = 1; ix <= nx; ++ix) {
+                if (orc_bit_test(valid + k * nw, nxw, ix, jx)) continue;
+                int lower, upper;
+                for (lower = k - 1; lower >= 0; --lower)
+                    if (orc_bit_test(valid + lower * nw, nxw, ix, jx)) break;
+                for (upper = k + 1; upper < nlev; ++upper)
+                    if (orc_bit_test(valid + upper * nw, nxw, ix, jx)) break;
+                if (upper < nlev && lower >= 0) {
+                    long o = (long)(jx - 1) * nx + (ix - 1);
+                    float wl = (float)abs(levels[upper] - levels[k]) / (float)abs(levels[upper] - levels[lower]);
+                    float wu = (float)abs(levels[k] - levels[lower]) / (float)abs(levels[upper] - levels[lower]);
+                    r_arr[k * np + o] = wl * r_arr[lower * np + o] + wu * r_arr[upper * np + o];
+                    orc_bit_set(valid + k * nw, nxw, ix, jx);
+                }
+            }
+        }
+    }
+}

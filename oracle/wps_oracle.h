@@ -217,4 +217,7 @@ void orc_calc_dfdy(const float *src, float *dst, int si, int sj, int sk, int ei,
 #ifdef __cplusplus
 }
 #endif
+/* fill_missing_levels vertical interpolation, process_domain_module.F:2862-2921 */
+void orc_fill_missing_levels(int nlev, const int32_t *levels, float *r_arr, int32_t *valid, int nx, int ny);
+
 #endif

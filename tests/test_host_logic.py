@@ -182,3 +182,22 @@ def test_patch_decomposition_gloo_world2(tmp_path):
                           "--master-port", "29613", str(script)], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK 1 37 1 14" in out.stdout
+
+
+def test_fill_lev_table_options():
+    """fill_lev / level_template / derived / flag_in_output (interp_option_module.F:271-311, 428-475, 736-812)."""
+    from wps_b200.interp_option import get_constant_fill_lev, get_fill_src_level, read_interp_table
+    t = read_interp_table("""
+    ========================================
+    name=TT ; fill_lev=200100:TT(100000) ; fill_lev=all:const(5.5)
+    ========================================
+    name=PRESSURE ; derived=yes ; z_dim_name=num_metgrid_levels ; level_template=TT
+            fill_lev=all:PRES
+            fill_lev=all:vertical_index; flag_in_output=FLAG_P
+    ========================================
+    """)
+    assert t[0].fill_lev == [("200100", "TT(100000)"), ("all", "const(5.5)")] and not t[0].is_derived_field
+    assert t[1].fill_lev == [("all", "PRES"), ("all", "vertical_index")]
+    assert t[1].is_derived_field and t[1].level_template == "TT" and t[1].flag_in_output == "FLAG_P"
+    assert get_constant_fill_lev("const(5.5)") == (0, 5.5) and get_constant_fill_lev("PRES")[0] == 1
+    assert get_fill_src_level("TT(100000)") == ("TT", 100000) and get_fill_src_level("SOILHGT") == ("SOILHGT", 1)

@@ -190,3 +190,27 @@ def test_golden_regression(orc):
     for k in g.files:
         assert np.array_equal(g[k].view(np.int32) if g[k].dtype == np.float32 else g[k],
                               now[k].view(np.int32) if now[k].dtype == np.float32 else now[k]), k
+
+
+def test_fill_missing_levels_known_answers():
+    """process_domain_module.F:2862-2921 by hand: levels 100/200/400/800, one column each:
+    column 0: valid at 100 and 800 only -> 200 gets (600/700)*a + (100/700)*d; 400 then sees 200 as its lower
+    neighbour (it was just filled): (400/600)*v200 + (200/600)*d.  Column 1: nothing valid below 400 -> untouched.
+    Column 2: nothing valid above 200 -> untouched."""
+    from oracle import oracle as O
+    levels = [100, 200, 400, 800]
+    r = np.zeros((4, 1, 3), np.float32)
+    v = np.zeros((4, 1, 1), np.int32)
+    a, d = np.float32(10.0), np.float32(80.0)
+    r[0, 0, 0], r[3, 0, 0] = a, d
+    v[0, 0, 0] |= 1; v[3, 0, 0] |= 1
+    r[2, 0, 1], r[3, 0, 1] = 5.0, 6.0
+    v[2, 0, 0] |= 2; v[3, 0, 0] |= 2
+    r[0, 0, 2], r[1, 0, 2] = 7.0, 8.0
+    v[0, 0, 0] |= 4; v[1, 0, 0] |= 4
+    r2, v2 = O.fill_missing_levels(levels, r, v)
+    v200 = np.float32(600.0) / np.float32(700.0) * a + np.float32(100.0) / np.float32(700.0) * d
+    v400 = np.float32(400.0) / np.float32(600.0) * v200 + np.float32(200.0) / np.float32(600.0) * d
+    assert r2[1, 0, 0] == v200 and r2[2, 0, 0] == v400
+    assert [int(x) for x in v2[:, 0, 0]] == [1 | 4, 1 | 4, 1 | 2, 1 | 2]
+    assert r2[0, 0, 1] == 0.0 and r2[1, 0, 1] == 0.0 and r2[2, 0, 2] == 0.0 and r2[3, 0, 2] == 0.0

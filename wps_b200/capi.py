@@ -306,6 +306,23 @@ class Handle:
         check(lib().wpsgpu_metgrid_last_timings(self._h, ms, pts))
         return list(ms), list(pts)
 
+    def fill_missing_levels(self, levels, r_arrs, valid_masks):
+        """Vertical interpolation of fill_missing_levels (process_domain_module.F:2862-2921) over the levels of one
+        3-d field, in place.  r_arrs / valid_masks: sequences of per-level arrays [ny][nx] / [ny][nwords]."""
+        n = len(levels)
+        ny, nx = r_arrs[0].shape
+        lv = (C.c_int32 * n)(*[int(l) for l in levels])
+        pr = (C.c_void_p * n)(*[ptr(a) for a in r_arrs])
+        pv = (C.c_void_p * n)(*[ptr(a) for a in valid_masks])
+        check(lib().wpsgpu_fill_missing_levels(self._h, n, lv, pr, pv, int(nx), int(ny)))
+
+    def create_level(self, r_arr, valid_mask, fill_const=None, src=None, src_valid=None):
+        """create_level (process_domain_module.F:3191-3332): constant fill, or copy of (src, src_valid)."""
+        ny, nx = r_arr.shape
+        check(lib().wpsgpu_create_level(self._h, int(nx), int(ny), C.c_float(0.0 if fill_const is None else fill_const),
+                                        C.c_void_p(ptr(src)), C.c_void_p(ptr(src_valid)), C.c_void_p(ptr(r_arr)),
+                                        C.c_void_p(ptr(valid_mask))))
+
     def debug_disable_fast(self, disable=True):
         check(lib().wpsgpu_debug_disable_fast(self._h, int(disable)))
 

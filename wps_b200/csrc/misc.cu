@@ -1,4 +1,5 @@
 // misc.cu -- wind rotation, smoothers, fractions/dominant/landmask and the elementwise geometry outputs.
+#include <vector>
 #include "ctx.h"
 
 namespace wps {
@@ -279,6 +280,59 @@ __global__ void k_dfd(int dir, const float* __restrict__ src, float* __restrict_
 
 using namespace wps;
 
+
+// ---- fill_missing_levels / create_level (process_domain_module.F:2748-2933, 3191-3332) -------------------------
+// One thread per (ix, jx) column, levels walked in storage order exactly like the reference's k loop: a level filled
+// at step k is a valid "lower" neighbour for the levels after it.  A warp owns one word of each level's valid_mask,
+// so the updated word is assembled with a ballot and stored by lane 0.
+struct VFillArgs { float* const* r; int* const* v; const int* lev; int nlev, nx, ny, nxw; };
+
+__global__ void __launch_bounds__(256) k_fill_missing_levels(VFillArgs a)
+{
+    const int ix = blockIdx.x * 32 + threadIdx.x, jx = blockIdx.y * 8 + threadIdx.y;
+    if (jx >= a.ny) return;                       // whole warps only: threadIdx.y selects the warp
+    const bool in = ix < a.nx;
+    const size_t o = (size_t)jx * a.nx + ix, w = (size_t)jx * a.nxw + blockIdx.x;
+    const unsigned lane_bit = 1u << threadIdx.x;
+    int lower = -1;                               // last level below k whose bit is set for this column
+    int upper = -1;                               // first level above k whose bit is set (searched lazily)
+    for (int k = 0; k < a.nlev; ++k) {
+        unsigned word = (unsigned)a.v[k][w];
+        bool valid = (word & lane_bit) != 0;
+        bool fill = false;
+        if (in && !valid) {
+            if (upper <= k) {
+                for (upper = k + 1; upper < a.nlev; ++upper)
+                    if (((unsigned)a.v[upper][w]) & lane_bit) break;
+            }
+            if (upper < a.nlev && lower >= 0) {
+                const int lu = a.lev[upper], lk = a.lev[k], ll = a.lev[lower];
+                float wl = (float)abs(lu - lk) / (float)abs(lu - ll);
+                float wu = (float)abs(lk - ll) / (float)abs(lu - ll);
+                a.r[k][o] = wl * a.r[lower][o] + wu * a.r[upper][o];
+                fill = true;
+            }
+        }
+        unsigned add = __ballot_sync(0xffffffffu, fill);
+        if (threadIdx.x == 0 && add) a.v[k][w] = (int)(word | add);
+        if (valid || fill) lower = k;
+    }
+}
+
+__global__ void k_create_level(float value, const float* __restrict__ src, const int* __restrict__ src_valid,
+                               float* __restrict__ r, int* __restrict__ valid, int nx, int ny, int nxw)
+{
+    const int ix = blockIdx.x * 32 + threadIdx.x, jx = blockIdx.y * blockDim.y + threadIdx.y;
+    if (jx >= ny) return;
+    if (ix < nx) r[(size_t)jx * nx + ix] = src ? src[(size_t)jx * nx + ix] : value;
+    if (threadIdx.x == 0) {
+        size_t w = (size_t)jx * nxw + blockIdx.x;
+        int rest = nx - blockIdx.x * 32;
+        unsigned full = rest >= 32 ? 0xffffffffu : ((1u << rest) - 1u);   // bitarray_set for i = 1..nx only
+        valid[w] = src_valid ? (int)((unsigned)src_valid[w] & full) : (int)full;
+    }
+}
+
 static int begin_call(wpsgpu_ctx* h, size_t host_bytes)
 {
     WPS_CHECK(h != nullptr, -1, "NULL handle");
@@ -296,6 +350,72 @@ static int end_call(wpsgpu_ctx* h)
 static int stage_inout(wpsgpu_ctx* h, void* p, size_t bytes, void** d) { return stage_in(h, p, bytes, d); }
 
 extern "C" {
+
+int wpsgpu_fill_missing_levels(wpsgpu_handle_t h, int32_t nlev, const int32_t* levels, float* const* r_arr,
+                               int32_t* const* valid_mask, int32_t nx, int32_t ny)
+{
+    WPS_CHECK(h && levels && r_arr && valid_mask, -1, "wpsgpu_fill_missing_levels: NULL argument");
+    WPS_CHECK(nlev >= 0 && nx > 0 && ny > 0, -1, "wpsgpu_fill_missing_levels: bad dimensions");
+    if (nlev <= 1) return 0;   // "If this isn't a 3-d array, nothing to do" (:2870)
+    const int nxw = (nx + 31) / 32;
+    const size_t rb = sizeof(float) * (size_t)nx * ny, vb = sizeof(int) * (size_t)ny * nxw;
+    WPS_TRY(begin_call(h, (rb + vb + 512) * nlev + 65536));
+    if (h->ptr_mode == WPSGPU_PTR_DEVICE) WPS_TRY(h->arena.reserve((size_t)nlev * 32 + (1 << 20), h->stream));
+    std::vector<float*> dr(nlev);
+    std::vector<int*> dv(nlev);
+    for (int k = 0; k < nlev; ++k) {
+        WPS_CHECK(r_arr[k] && valid_mask[k], -1, "wpsgpu_fill_missing_levels: NULL level array");
+        void *a, *b;
+        WPS_TRY(stage_inout(h, r_arr[k], rb, &a));
+        WPS_TRY(stage_inout(h, valid_mask[k], vb, &b));
+        dr[k] = (float*)a; dv[k] = (int*)b;
+    }
+    // pointer and level tables (always host arrays of the ABI) go up through the arena
+    float** d_r = (float**)h->arena.take(sizeof(float*) * nlev);
+    int** d_v = (int**)h->arena.take(sizeof(int*) * nlev);
+    int* d_lev = (int*)h->arena.take(sizeof(int) * nlev);
+    WPS_CHECK(d_r && d_v && d_lev, -3, "device arena exhausted");
+    WPS_CUDA(cudaMemcpyAsync(d_r, dr.data(), sizeof(float*) * nlev, cudaMemcpyHostToDevice, h->stream));
+    WPS_CUDA(cudaMemcpyAsync(d_v, dv.data(), sizeof(int*) * nlev, cudaMemcpyHostToDevice, h->stream));
+    WPS_CUDA(cudaMemcpyAsync(d_lev, levels, sizeof(int) * nlev, cudaMemcpyHostToDevice, h->stream));
+    VFillArgs a;
+    a.r = d_r; a.v = d_v; a.lev = d_lev; a.nlev = nlev; a.nx = nx; a.ny = ny; a.nxw = nxw;
+    k_fill_missing_levels<<<dim3(nxw, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(a);
+    h->launches++;
+    WPS_CUDA(cudaGetLastError());
+    if (h->ptr_mode == WPSGPU_PTR_HOST)
+        for (int k = 0; k < nlev; ++k) {
+            WPS_CUDA(cudaMemcpyAsync(r_arr[k], dr[k], rb, cudaMemcpyDeviceToHost, h->stream));
+            WPS_CUDA(cudaMemcpyAsync(valid_mask[k], dv[k], vb, cudaMemcpyDeviceToHost, h->stream));
+        }
+    return end_call(h);
+}
+
+int wpsgpu_create_level(wpsgpu_handle_t h, int32_t nx, int32_t ny, float fill_const, const float* src_r_arr,
+                        const int32_t* src_valid_mask, float* r_arr, int32_t* valid_mask)
+{
+    WPS_CHECK(h && r_arr && valid_mask, -1, "wpsgpu_create_level: NULL argument");
+    WPS_CHECK((src_r_arr == nullptr) == (src_valid_mask == nullptr), -1,
+              "wpsgpu_create_level: source array and source valid_mask must be given together");
+    WPS_CHECK(nx > 0 && ny > 0, -1, "wpsgpu_create_level: bad dimensions");
+    const int nxw = (nx + 31) / 32;
+    const size_t rb = sizeof(float) * (size_t)nx * ny, vb = sizeof(int) * (size_t)ny * nxw;
+    WPS_TRY(begin_call(h, 2 * (rb + vb) + 8192));
+    void *ds = nullptr, *dsv = nullptr, *dr = r_arr, *dv = valid_mask;
+    if (src_r_arr) { WPS_TRY(stage_in(h, src_r_arr, rb, &ds)); WPS_TRY(stage_in(h, src_valid_mask, vb, &dsv)); }
+    if (h->ptr_mode == WPSGPU_PTR_HOST) {
+        dr = h->arena.take(rb); dv = h->arena.take(vb);
+        WPS_CHECK(dr && dv, -3, "device arena exhausted");
+    }
+    k_create_level<<<dim3(nxw, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(fill_const, (const float*)ds, (const int*)dsv, (float*)dr, (int*)dv, nx, ny, nxw);
+    h->launches++;
+    WPS_CUDA(cudaGetLastError());
+    if (h->ptr_mode == WPSGPU_PTR_HOST) {
+        WPS_CUDA(cudaMemcpyAsync(r_arr, dr, rb, cudaMemcpyDeviceToHost, h->stream));
+        WPS_CUDA(cudaMemcpyAsync(valid_mask, dv, vb, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return end_call(h);
+}
 
 int wpsgpu_rotate_winds(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj, float* u, const int32_t* u_mask,
                         float* v, const int32_t* v_mask, int us1, int us2, int ue1, int ue2,

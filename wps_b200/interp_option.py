@@ -34,6 +34,10 @@ class TableEntry:
     is_v_field: bool = False
     output_name: str = " "
     from_input: str = "*"
+    fill_lev: List = field(default_factory=list)     # [(level string | 'all', fill string)] in table order (:459-475)
+    level_template: str = " "
+    is_derived_field: bool = False
+    flag_in_output: str = " "
     other: Dict[str, str] = field(default_factory=dict)
 
     def field_opts(self):
@@ -116,6 +120,15 @@ def read_interp_table(text: str, gridtype: str = "C") -> List[TableEntry]:
                 cur.fill_missing = float(val.replace("E", "e").replace("D", "e"))
             elif key == "missing_value":
                 cur.missing_value = float(val.replace("E", "e").replace("D", "e"))
+            elif key == "fill_lev":          # fill_lev = [level:]spec ; no level means 'all' (:459-475)
+                c = val.find(":")
+                cur.fill_lev.append(("all", val) if c < 0 else (val[:c], val[c + 1:]))
+            elif key == "level_template":
+                cur.level_template = val
+            elif key == "derived":
+                cur.is_derived_field = bool(val) and val in "yes"
+            elif key == "flag_in_output":
+                cur.flag_in_output = val
             else:
                 cur.other.setdefault(key, val)
     if nparams > 0:
@@ -137,3 +150,22 @@ def find_entry(entries: List[TableEntry], fieldname: str, input_name: str) -> in
                 idxt = i
                 found = True
     return idxt
+
+
+def get_constant_fill_lev(fill_opt: str):
+    """-> (istatus, value): 'const(v)' specifications (interp_option_module.F:736-772); istatus 0 = is a constant."""
+    i = fill_opt.find("const")
+    if i < 0:
+        return 1, NAN
+    p1, p2 = fill_opt.find("(", i), fill_opt.find(")", i)
+    if p1 >= 0 and p2 >= 0:
+        return 0, float(fill_opt[p1 + 1:p2].replace("D", "e"))
+    return 0, NAN
+
+
+def get_fill_src_level(fill_opt: str):
+    """'FIELD(level)' -> (FIELD, level); a bare 'FIELD' means level 1 (interp_option_module.F:780-812)."""
+    p1, p2 = fill_opt.find("("), fill_opt.find(")")
+    if p1 >= 0 and p2 >= 0:
+        return fill_opt[:p1], int(fill_opt[p1 + 1:p2])
+    return fill_opt, 1

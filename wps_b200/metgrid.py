@@ -138,6 +138,91 @@ class MetgridDomain:
             fld.valid_mask |= fld.modified_mask
         return storage
 
+    # ---- fill_missing_levels / fill_field / create_level (process_domain_module.F:2748-2933, 3037-3332) ----------
+    def _dims(self, stagger):
+        st = stagger if stagger in (capi.U, capi.V) else capi.M
+        return self.grids[st][0].shape
+
+    def create_level(self, storage, name, stagger, rlevel, fill_const=None, src=None):
+        """create_level: no-op when (name, level) exists; constant fill, or a copy of src = (field, level) with its
+        valid bits; a missing source only logs in the reference (:3322-3325)."""
+        key = (name, int(np.rint(rlevel)))
+        if key in storage:
+            return False
+        gy, gx = self._dims(stagger)
+        new = FgInput(name, key[1], stagger, np.zeros((gy, gx), np.float32), np.zeros((gy, capi.nwords(gx)), np.int32),
+                      np.zeros((gy, capi.nwords(gx)), np.int32))
+        if src is None:
+            self.h.create_level(new.r_arr, new.valid_mask, fill_const=fill_const)
+        else:
+            skey = (src[0], int(np.rint(src[1])))
+            if skey not in storage:
+                return False
+            sf = storage[skey]
+            if sf.r_arr.shape != new.r_arr.shape:
+                raise ValueError("Dimensions for %s do not match those of %s. This is probably because the staggerings "
+                                 "of the fields do not match." % (src[0], name))
+            self.h.create_level(new.r_arr, new.valid_mask, src=sf.r_arr, src_valid=sf.valid_mask)
+        storage[key] = new
+        return True
+
+    @staticmethod
+    def _levels_of(storage, name):
+        """storage_get_levels: ascending vertical_level for time-dependent data (secondary_cmp, datatype_module.F:124)."""
+        return sorted(l for (n, l) in storage if n == name)
+
+    def fill_field(self, storage, name, entry, stagger, all_level_list=None):
+        """fill_field (:3037-3177): walk the entry's fill_lev list in table order."""
+        from .interp_option import get_constant_fill_lev, get_fill_src_level
+        filled_all = False
+        for lev_s, spec in entry.fill_lev:
+            if lev_s == "all":
+                if filled_all:
+                    continue
+                filled_all = True
+                ist, const = get_constant_fill_lev(spec)
+                if ist == 0 or spec == "vertical_index":
+                    levels = all_level_list if all_level_list is not None else self._levels_of(storage, entry.level_template)
+                    for l in levels:
+                        self.create_level(storage, name, stagger, float(l), fill_const=const if ist == 0 else float(l))
+                else:
+                    levels = all_level_list if all_level_list is not None else self._levels_of(storage, spec)
+                    if all_level_list is None and not levels:
+                        filled_all = False
+                    for l in levels:
+                        self.create_level(storage, name, stagger, float(l), src=(spec, float(l)))
+            else:
+                rlevel = float(lev_s)
+                ist, const = get_constant_fill_lev(spec)
+                if ist == 0:
+                    self.create_level(storage, name, stagger, rlevel, fill_const=const)
+                else:
+                    self.create_level(storage, name, stagger, rlevel, src=get_fill_src_level(spec))
+
+    def create_derived_fields(self, storage, table):
+        """create_derived_fields (:2939-3029): entries with derived=yes are built from their fill_lev rules."""
+        for e in table[:-1]:
+            if e.is_derived_field:
+                self.fill_field(storage, e.fieldname, e, e.output_stagger)
+
+    def fill_missing_levels(self, storage, table):
+        """fill_missing_levels (:2748-2933): union of the levels of all 3-d fields (201300 excluded), fill_field for
+        every stored field that has a table entry, then the vertical interpolation on device per 3-d field."""
+        names = list(dict.fromkeys(n for (n, _) in storage))[::-1]      # head insertion puts the newest name first
+        union = sorted({l for (n, l) in storage if l != 201300})
+        if not union:
+            return
+        for n in names:
+            e = next((t for t in table[:-1] if t.fieldname == n), None)
+            if e is not None:
+                stag = next(f.stagger for (nn, _), f in storage.items() if nn == n)
+                self.fill_field(storage, n, e, stag, all_level_list=union)
+        for n in list(dict.fromkeys(nn for (nn, _) in storage))[::-1]:
+            levels = self._levels_of(storage, n)
+            if len(levels) > 1:
+                flds = [storage[(n, l)] for l in levels]
+                self.h.fill_missing_levels(levels, [f.r_arr for f in flds], [f.valid_mask for f in flds])
+
     def _renamed(self, name, table, input_name):
         idx = find_entry(table, name, input_name)
         if table[idx].output_name != " ":
