@@ -200,6 +200,45 @@ def enqueue_all(h, w, descs):
     h.metgrid_flush()
 
 
+def vertical_fill_arm(h, torch, dev, config, steps):
+    """SURVEY 8(f) row 1 beside the headline: fill_missing_levels' vertical interpolation over one config-2 3-d field
+    (35 levels x 1799 x 1059, 30 % of the points missing at random) resident in HBM."""
+    nx, ny = config["dom"][0], config["dom"][1]
+    nlev = config["nlev"] + 1
+    from wps_b200 import capi
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    levels = [1000 + 2900 * k for k in range(nlev)]
+    r0 = torch.rand((nlev, ny, nx), device=dev, generator=g) * 100.0 + 200.0
+    miss = torch.rand((nlev, ny, nx), device=dev, generator=g) < 0.3
+    nw = capi.nwords(nx)
+    pad = torch.zeros((nlev, ny, nw * 32), dtype=torch.bool, device=dev)
+    pad[:, :, :nx] = ~miss
+    weights = (2 ** torch.arange(32, device=dev, dtype=torch.int64))
+    v0 = (pad.view(nlev, ny, nw, 32).to(torch.int64) * weights).sum(-1)
+    v0 = torch.where(v0 >= 2 ** 31, v0 - 2 ** 32, v0).to(torch.int32).contiguous()
+    r, v = r0.clone(), v0.clone()
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for it in range(steps + 1):
+        r.copy_(r0); v.copy_(v0)
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        h.fill_missing_levels(levels, [r[k] for k in range(nlev)], [v[k] for k in range(nlev)])
+        ev1.record(stream)
+        h.synchronize()
+        if it > 0:
+            ms.append(ev0.elapsed_time(ev1))
+    filled = int(((v != v0).sum()).item())   # words that changed (diagnostic only)
+    nmiss = int(miss[1:-1].sum().item())
+    t = float(np.mean(ms))
+    alg = nlev * ny * nw * 4 + 12.0 * nmiss   # every valid word once + (2 reads + 1 write) per interpolated point
+    return {"metric": "fill_missing_levels points/s (level x point)", "value": nlev * nx * ny / (t / 1e3), "unit": "points/s",
+            "ms": t, "levels": nlev, "missing_points": nmiss, "changed_words": filled,
+            "alg_GBps": alg / (t * 1e-3) / 1e9}
+
+
 def geogrid_arm(h, torch, dev, config, steps):
     """geogrid reported additionally as source pixels/s.  Config-3 shape: a 30-arc-second, 21-category,
     1-byte land-use dataset in 1200x1200 tiles (raw bytes resident in HBM) accumulated onto the 3-km CONUS patch
@@ -354,9 +393,10 @@ def run_b200(args, rank, world, local_rank):
         e2e_value = world * pts / float(t.item())
         hh.close()
 
-    geo = None
+    geo, vfill = None, None
     if rank == 0 and not args.no_geogrid:
         geo = geogrid_arm(h, torch, dev, config, 3)
+        vfill = vertical_fill_arm(h, torch, dev, config, 3)
     if rank == 0:
         peaks = {}
         try:
@@ -382,6 +422,7 @@ def run_b200(args, rank, world, local_rank):
                 "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": sampler.result()}
         if geo is not None:
             line["geogrid"] = geo
+            line["vertical_fill"] = vfill
         if world == 1 and not args.no_cpu:
             pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 3)
             line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}
