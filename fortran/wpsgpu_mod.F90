@@ -90,6 +90,37 @@ module wpsgpu_mod
          type(wpsgpu_field_opts) :: fo
          type(wpsgpu_slab) :: slab
       end function
+      integer(c_int) function wpsgpu_metgrid_enqueue_slabs(handle, proj, fo, slabs, n) bind(C, name='wpsgpu_metgrid_enqueue_slabs')
+         import :: c_int, c_int32_t, c_ptr, wpsgpu_proj, wpsgpu_field_opts, wpsgpu_slab
+         type(c_ptr), value :: handle
+         type(wpsgpu_proj) :: proj
+         type(wpsgpu_field_opts) :: fo
+         type(wpsgpu_slab) :: slabs(*)
+         integer(c_int32_t), value :: n
+      end function
+      integer(c_int) function wpsgpu_metgrid_enqueue_gcell_slab(handle, proj, dom_proj, fo, slab) &
+                        bind(C, name='wpsgpu_metgrid_enqueue_gcell_slab')
+         import :: c_int, c_ptr, wpsgpu_proj, wpsgpu_field_opts, wpsgpu_slab
+         type(c_ptr), value :: handle
+         type(wpsgpu_proj) :: proj, dom_proj
+         type(wpsgpu_field_opts) :: fo
+         type(wpsgpu_slab) :: slab
+      end function
+      integer(c_int) function wpsgpu_fill_missing_levels(handle, nlev, levels, r_arr, valid_mask, nx, ny) &
+                        bind(C, name='wpsgpu_fill_missing_levels')
+         import :: c_int, c_int32_t, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int32_t), value :: nlev, nx, ny
+         integer(c_int32_t) :: levels(*)
+         type(c_ptr) :: r_arr(*), valid_mask(*)       ! c_loc of each level's r_arr / valid_mask%iarray
+      end function
+      integer(c_int) function wpsgpu_create_level(handle, nx, ny, fill_const, src_r_arr, src_valid_mask, r_arr, valid_mask) &
+                        bind(C, name='wpsgpu_create_level')
+         import :: c_int, c_int32_t, c_ptr, c_float
+         type(c_ptr), value :: handle, src_r_arr, src_valid_mask, r_arr, valid_mask
+         integer(c_int32_t), value :: nx, ny
+         real(c_float), value :: fill_const
+      end function
       integer(c_int) function wpsgpu_metgrid_flush(handle) bind(C, name='wpsgpu_metgrid_flush')
          import :: c_int, c_ptr
          type(c_ptr), value :: handle
