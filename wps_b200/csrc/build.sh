@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -ftz=false -prec-div=true -prec-sqrt=true -Xcompiler -fPIC,-ffp-contract=off,-O2"
+FLAGS="$EXTRA_NVCC_FLAGS -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -ftz=false -prec-div=true -prec-sqrt=true -Xcompiler -fPIC,-ffp-contract=off,-O2"
 mkdir -p build
 pids=()
 for f in api metgrid geogrid misc; do

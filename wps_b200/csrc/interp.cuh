@@ -336,9 +336,10 @@ static __device__ float literal_search(const Src& s, float xx, float yy, int max
 struct LitScratch { unsigned* visited; int R; QNode* q; int qcap; };
 template <int MODE>
 __device__ __forceinline__ int interp_sequence(const Src& s, const int* __restrict__ ops, const int* __restrict__ opts,
-                                               float xx, float yy, float& r, const LitScratch* ls = nullptr)
+                                               float xx, float yy, float& r, const LitScratch* ls = nullptr, int first = 0)
 {
-    for (int idx = 0; idx < WPSGPU_MAX_OPS; ++idx) {
+    // `first` > 0: the caller already knows that methods 0..first-1 hand over to their successor at this point
+    for (int idx = first; idx < WPSGPU_MAX_OPS; ++idx) {
         int op = ops[idx];
         if (op == 0) break;
         int st;

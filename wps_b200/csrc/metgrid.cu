@@ -64,7 +64,7 @@ enum { PF_WRITE = 1, PF_BIT = 2, PF_DEFER = 4 };
 
 template <int MODE>
 __device__ __forceinline__ int interp_to_latlon(const Job& jb, const float* __restrict__ src, int sel, bool use_mask,
-                                                float2 xy, float rlat, float rlon, float& r, const LitScratch* ls)
+                                                float2 xy, float rlat, float rlon, float& r, const LitScratch* ls, int first = 0)
 {
     // interp_to_latlon, process_domain_module.F:2594-2669
     Src s;
@@ -75,7 +75,7 @@ __device__ __forceinline__ int interp_to_latlon(const Job& jb, const float* __re
     int st = ST_FINAL_MSG;
     r = jb.msg;
     if (xy.x >= lo && xy.x <= hi) {
-        st = interp_sequence<MODE>(s, jb.ops, jb.opts, xy.x, xy.y, r, ls);
+        st = interp_sequence<MODE>(s, jb.ops, jb.opts, xy.x, xy.y, r, ls, first);   // `first` applies to this position only
         if (st == ST_DEFER) return ST_DEFER;
     }
     if (r == jb.msg) {
@@ -93,7 +93,7 @@ __device__ __forceinline__ int interp_to_latlon(const Job& jb, const float* __re
 
 template <int MODE>
 __device__ __forceinline__ int process_point(const Job& jb, const float* __restrict__ src, int i, int j, size_t idx,
-                                             float2 xy, bool valid_bit, float& out, const LitScratch* ls = nullptr)
+                                             float2 xy, bool valid_bit, float& out, const LitScratch* ls = nullptr, int first = 0)
 {
     const int pw = jb.pw;
     if (abs(i - jb.sd1) >= pw && abs(i - jb.ed1) >= pw && abs(j - jb.sd2) >= pw && abs(j - jb.ed2) >= pw) {
@@ -117,7 +117,7 @@ __device__ __forceinline__ int process_point(const Job& jb, const float* __restr
         float rlat = 0.0f, rlon = 0.0f;
         rlon = __ldg(jb.xlon + idx);
         if (rlon < 0.0f) rlat = __ldg(jb.xlat + idx);
-        int st = interp_to_latlon<MODE>(jb, src, sel, jb.mask[sel] != nullptr, xy, rlat, rlon, temp, ls);
+        int st = interp_to_latlon<MODE>(jb, src, sel, jb.mask[sel] != nullptr, xy, rlat, rlon, temp, ls, first);
         if (st == ST_DEFER) return PF_DEFER;
     }
     int flags = 0;
@@ -133,7 +133,7 @@ __device__ __forceinline__ int process_point(const Job& jb, const float* __restr
 
 // ---- main batched kernel -------------------------------------------------------------------------
 // grid.x = sum over jobs of tiles; block = 32x8 destination points; each thread walks the job's slabs.
-__global__ void __launch_bounds__(TILE_X * TILE_Y, 2)
+__global__ void __launch_bounds__(TILE_X * TILE_Y, 4)
 k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_tile0, int ncls,
                  const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count)
 {
@@ -333,12 +333,13 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, co
         // bits 4-7) per destination point (:2495-2513), so both variants of the flag are kept
         const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
         const int selA = both ? 1 : 0;
-        bool clean = true, cleanA = true, cleanB = true;
+        bool clean = true, cleanA = true, cleanB = true, nomsg = true;
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
             int r = min(max(jj + l - 1, sy), ey);
             float w[4];
             row4(r, w);
+            nomsg = nomsg && w[0] != msg && w[1] != msg && w[2] != msg && w[3] != msg;
             clean = clean && w[0] != msg && w[1] != msg && w[2] != msg && w[3] != msg && (w[1] * w[2] != 0.0f) && (w[0] * w[3] != 0.0f);
             // interp_mask: any unusable cell in the stencil sends sixteen_pt to the next method (:1244-1270)
             auto mask_row = [&](int sel, bool& c) {
@@ -356,6 +357,9 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, co
         }
         if (clean && cleanA) cfbits |= 1u << lv;
         if (both && clean && cleanB) cfbits |= 16u << lv;
+        // single-mask jobs: bits 4-7 say "the stencil holds a missing or masked value", i.e. sixteen_pt is certain to
+        // hand over to the next method (:1244-1270) -- the slow-bitmap pass then starts the chain at the second method
+        if (!both && !(nomsg && cleanA)) cfbits |= 16u << lv;
     }
     size_t o = ((size_t)pack * jb.bny + cj) * jb.bnx + ci;
     // layout [pack][row][group of 8 cells][term f][cell in group]: one 128-byte line holds one term of 8 neighbouring
@@ -597,7 +601,10 @@ k_metgrid_fast4(const __grid_constant__ Fast4Params P)
 
 // Points the packed kernel could not take (missing values in the stencil, points on a node or near the array edge,
 // process_bdy_width interior): full generic operator chain, one thread per flagged word.
-__global__ void __launch_bounds__(128, 4)
+#ifndef SLOW_MINBLOCKS
+#define SLOW_MINBLOCKS 8   // 64 registers: measured 0.31 / 0.24 / 0.22 / 0.22 / 0.26 ms at 4 / 6 / 8 / 10 / 12 CTAs per SM
+#endif
+__global__ void __launch_bounds__(128, SLOW_MINBLOCKS)
 k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_word0, int ncls,
                    const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count,
                    long long w_begin, long long total_words)
@@ -651,7 +658,23 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_job
             size_t idx = (size_t)jj * jb.nx + ii;
             bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> bit) & 1u) : false;
             float out = 0.0f;
-            int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, __ldg(jb.xy + idx), vbit, out);
+            const float2 pxy = __ldg(jb.xy + idx);
+            int first = 0;
+            if (jb.fast == 1 && !(jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH)) {
+                // same cell arithmetic as sixteen_pt (interp_module.F:1211-1225); off a node and inside the record box
+                // the pre-pass has recorded whether the 4x4 stencil holds a missing / masked value
+                float xx = pxy.x, yy = pxy.y;
+                if (fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f && (int)xx >= jb.minx && (int)xx <= jb.maxx && (int)yy >= jb.miny && (int)yy <= jb.maxy) {
+                    int ci = (int)(xx + 0.00001f), cj = (int)(yy + 0.00001f);
+                    float fx = xx - (float)ci, fy = yy - (float)cj;
+                    ci -= jb.bx0; cj -= jb.by0;
+                    if ((fabsf(fx) > 0.0001f || fabsf(fy) > 0.0001f) && ci >= 0 && ci < jb.bnx && cj >= 0 && cj < jb.bny) {
+                        unsigned cfb = __ldg(jb.cf + ((size_t)(wsl >> 2) * jb.bny + cj) * jb.bnx + ci);
+                        if ((cfb >> (4 + (wsl & 3))) & 1u) first = 1;
+                    }
+                }
+            }
+            int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, pxy, vbit, out, nullptr, first);
             if (flags & PF_DEFER) {
                 unsigned long long slot = atomicAdd(defer_count, 1ull);
                 Deferred d; d.slab = jb.slab0 + wsl; d.idx = (int)idx;
@@ -684,7 +707,7 @@ __device__ __forceinline__ void finish_point(const Job& jb, const SlabPtrs& sp, 
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_metgrid_search(const Job* __restrict__ jobs, int njobs, const SlabPtrs* __restrict__ slabs,
                  const Deferred* __restrict__ deferred, const unsigned long long* __restrict__ defer_count,
                  Deferred* __restrict__ deferred2, unsigned long long* __restrict__ defer2_count)
