@@ -305,6 +305,28 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, co
     float out[6][4];
     unsigned cfbits = 0;
     const float msg = jb.msg;
+    // masked=both: the landmask picks interp_land_mask (water points, bits 0-3) or interp_water_mask (land points,
+    // bits 4-7) per destination point (:2495-2513), so both variants of the flag are kept
+    const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
+    const int selA = both ? 1 : 0;
+    // interp_mask: any unusable cell in the stencil sends sixteen_pt to the next method (:1244-1270); level-independent
+    bool cleanA = true, cleanB = true;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+        int r = min(max(jj + l - 1, sy), ey);
+        auto mask_row = [&](int sel, bool& c) {
+            if (!jb.mask[sel]) return;
+            const float* mp = jb.mask[sel] + (size_t)(r - sy) * snx;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float m = __ldg(mp + col[k]);
+                bool out_ = jb.mask_rel[sel] == REL_GT ? (m > jb.mask_val[sel]) : (jb.mask_rel[sel] == REL_LT ? (m < jb.mask_val[sel]) : (m == jb.mask_val[sel]));
+                c = c && !out_;
+            }
+        };
+        mask_row(selA, cleanA);
+        if (both) mask_row(2, cleanB);
+    }
 #pragma unroll
     for (int lv = 0; lv < 4; ++lv) {
         int sl = pack * 4 + lv;
@@ -312,49 +334,30 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, co
         for (int f = 0; f < 6; ++f) out[f][lv] = 0.0f;
         if (sl >= jb.nslab) continue;
         const float* __restrict__ src = slabs[jb.slab0 + sl].src;
-        auto row4 = [&](int r, float* v) {
+        bool clean = true, nomsg = true;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            int r = min(max(jj + l - 1, sy), ey);
             const float* p = src + (size_t)(r - sy) * snx;
+            float w[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float t = __ldg(p + col[k]);
                 if (t == 0.0f && msg != 0.0f) t = 1.0e-20f;
-                v[k] = t;
+                w[k] = t;
             }
-        };
-        float v[4];
-        row4(jj, v);
-        out[0][lv] = v[1];
-        out[1][lv] = v[2];
-        out[2][lv] = 0.5f * (v[2] - v[0]);
-        out[3][lv] = 0.5f * (v[2] + v[0]) - v[1];
-        out[4][lv] = 0.5f * (v[1] - v[3]);
-        out[5][lv] = 0.5f * (v[1] + v[3]) - v[2];
-        // masked=both: the landmask picks interp_land_mask (water points, bits 0-3) or interp_water_mask (land points,
-        // bits 4-7) per destination point (:2495-2513), so both variants of the flag are kept
-        const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
-        const int selA = both ? 1 : 0;
-        bool clean = true, cleanA = true, cleanB = true, nomsg = true;
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            int r = min(max(jj + l - 1, sy), ey);
-            float w[4];
-            row4(r, w);
             nomsg = nomsg && w[0] != msg && w[1] != msg && w[2] != msg && w[3] != msg;
-            clean = clean && w[0] != msg && w[1] != msg && w[2] != msg && w[3] != msg && (w[1] * w[2] != 0.0f) && (w[0] * w[3] != 0.0f);
-            // interp_mask: any unusable cell in the stencil sends sixteen_pt to the next method (:1244-1270)
-            auto mask_row = [&](int sel, bool& c) {
-                if (!jb.mask[sel]) return;
-                const float* mp = jb.mask[sel] + (size_t)(r - sy) * snx;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float m = __ldg(mp + col[k]);
-                    bool out_ = jb.mask_rel[sel] == REL_GT ? (m > jb.mask_val[sel]) : (jb.mask_rel[sel] == REL_LT ? (m < jb.mask_val[sel]) : (m == jb.mask_val[sel]));
-                    c = c && !out_;
-                }
-            };
-            mask_row(selA, cleanA);
-            if (both) mask_row(2, cleanB);
+            clean = clean && (w[1] * w[2] != 0.0f) && (w[0] * w[3] != 0.0f);
+            if (l == 1) {   // the cell's own row: jj lies inside the array, so row 1 of the stencil is never clamped
+                out[0][lv] = w[1];
+                out[1][lv] = w[2];
+                out[2][lv] = 0.5f * (w[2] - w[0]);
+                out[3][lv] = 0.5f * (w[2] + w[0]) - w[1];
+                out[4][lv] = 0.5f * (w[1] - w[3]);
+                out[5][lv] = 0.5f * (w[1] + w[3]) - w[2];
+            }
         }
+        clean = clean && nomsg;
         if (clean && cleanA) cfbits |= 1u << lv;
         if (both && clean && cleanB) cfbits |= 16u << lv;
         // single-mask jobs: bits 4-7 say "the stencil holds a missing or masked value", i.e. sixteen_pt is certain to
