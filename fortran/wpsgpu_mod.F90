@@ -134,6 +134,15 @@ module wpsgpu_mod
          real(c_float) :: u(*), v(*), xlon_u(*), xlon_v(*)
          integer(c_int32_t) :: u_mask(*), v_mask(*)
       end function
+      integer(c_int) function wpsgpu_rotate_winds_ll(handle, idir, proj, u, u_mask, v, v_mask, us1, us2, ue1, ue2, &
+                        vs1, vs2, ve1, ve2, xlon_u, xlon_v, xlat_u, xlat_v, nlev) bind(C, name='wpsgpu_rotate_winds_ll')
+         import :: c_int, c_ptr, c_float, c_int32_t, wpsgpu_proj
+         type(c_ptr), value :: handle
+         integer(c_int), value :: idir, us1, us2, ue1, ue2, vs1, vs2, ve1, ve2, nlev
+         type(wpsgpu_proj) :: proj
+         real(c_float) :: u(*), v(*), xlon_u(*), xlon_v(*), xlat_u(*), xlat_v(*)   ! latitudes: PROJ_CASSINI branches
+         integer(c_int32_t) :: u_mask(*), v_mask(*)
+      end function
       integer(c_int) function wpsgpu_smooth(handle, opt, npass, array, sx, ex, sy, ey, sz, ez) bind(C, name='wpsgpu_smooth')
          import :: c_int, c_ptr, c_float
          type(c_ptr), value :: handle

@@ -189,6 +189,13 @@ int wpsgpu_create_level(wpsgpu_handle_t h, int32_t nx, int32_t ny, float fill_co
 int wpsgpu_rotate_winds(wpsgpu_handle_t h, int idir, const wpsgpu_proj *proj, float *u, const int32_t *u_mask,
                         float *v, const int32_t *v_mask, int us1, int us2, int ue1, int ue2,
                         int vs1, int vs2, int ve1, int ve2, const float *xlon_u, const float *xlon_v, int nlev);
+/* Same with the latitudes of the U and V points, which the PROJ_CASSINI branches read (rotate_winds_module.F:174-222,
+ * :281-329: idir=+1 differentiates ij_to_latlon of `proj` at y +- 0.1, idir=-1 differentiates xlat/xlon along j).
+ * xlat_u / xlat_v may be NULL for Lambert conformal and polar stereographic. */
+int wpsgpu_rotate_winds_ll(wpsgpu_handle_t h, int idir, const wpsgpu_proj *proj, float *u, const int32_t *u_mask,
+                           float *v, const int32_t *v_mask, int us1, int us2, int ue1, int ue2,
+                           int vs1, int vs2, int ve1, int ve2, const float *xlon_u, const float *xlon_v,
+                           const float *xlat_u, const float *xlat_v, int nlev);
 
 /* ---- geogrid: calc_field (process_tile_module.F:1208-1681) ---- */
 typedef struct wpsgpu_geo_field {

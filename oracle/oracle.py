@@ -253,12 +253,21 @@ def interp_met_field_gcell(src, dom, fo, ifieldstagger, xlat, xlon, sm1, sm2, sd
     return r_arr, new_pts
 
 
-def metmap_xform(proj, u, u_mask, v, v_mask, xlon_u, xlon_v, idir, us=(1, 1), vs=(1, 1)):
-    """metmap_xform (rotate_winds_module.F:85); u [uny][unx], v [vny][vnx]; in place on copies."""
+def metmap_xform(proj, u, u_mask, v, v_mask, xlon_u, xlon_v, idir, us=(1, 1), vs=(1, 1), xlat_u=None, xlat_v=None):
+    """metmap_xform (rotate_winds_module.F:85); u [uny][unx], v [vny][vnx]; in place on copies.
+    xlat_u / xlat_v are needed for PROJ_CASSINI only (:174-222, :281-329)."""
     u = np.array(u, np.float32, order="C")
     v = np.array(v, np.float32, order="C")
     uny, unx = u.shape
     vny, vnx = v.shape
+    if xlat_u is not None:
+        lib().orc_metmap_xform_ll(C.byref(proj), fptr(u), iptr(np.ascontiguousarray(u_mask, np.int32)), fptr(v),
+                                  iptr(np.ascontiguousarray(v_mask, np.int32)), us[0], us[1], us[0] + unx - 1,
+                                  us[1] + uny - 1, vs[0], vs[1], vs[0] + vnx - 1, vs[1] + vny - 1,
+                                  fptr(np.ascontiguousarray(xlon_u, np.float32)), fptr(np.ascontiguousarray(xlon_v, np.float32)),
+                                  fptr(np.ascontiguousarray(xlat_u, np.float32)), fptr(np.ascontiguousarray(xlat_v, np.float32)),
+                                  int(idir))
+        return u, v
     lib().orc_metmap_xform(C.byref(proj), fptr(u), iptr(np.ascontiguousarray(u_mask, np.int32)), fptr(v),
                            iptr(np.ascontiguousarray(v_mask, np.int32)), us[0], us[1], us[0] + unx - 1,
                            us[1] + uny - 1, vs[0], vs[1], vs[0] + vnx - 1, vs[1] + vny - 1,

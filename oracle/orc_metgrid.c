@@ -232,12 +232,47 @@ void orc_interp_met_field_gcell(orc_proj *src, orc_proj *dom, const orc_field_op
     free(cur); free(cnt);
 }
 
-/* rotate_winds_module.F:85-387, C grid.  Cassini branches (:174-222,:281-329) are not restated. */
+/* Cassini rotation angle, rotate_winds_module.F:174-222 (U) and :281-329 (V): same formulas on the array passed in.
+ * idir == 1: finite difference of ij_to_latlon(SOURCE_PROJ) at y +- 0.1; idir == -1: finite difference of the
+ * domain's own lat/lon arrays along j (one-sided on the first/last row). */
+static float cassini_alpha(const orc_proj *proj, int idir, const float *xlat, const float *xlon,
+                           int s1, int s2, int e2, int nx, int i, int j)
+{
+#define LL(a, ii, jj) (a)[(long)((jj) - s2) * nx + ((ii) - s1)]
+    if (idir == 1) {
+        float x, y, latp, lonp, latm, lonm;
+        orc_latlon_to_ij(proj, LL(xlat, i, j), LL(xlon, i, j), &x, &y);
+        orc_ij_to_latlon(proj, x, y + 0.1f, &latp, &lonp);
+        orc_ij_to_latlon(proj, x, y - 0.1f, &latm, &lonm);
+        float diff_lon = lonp - lonm;
+        if (diff_lon > 180.0f) diff_lon = diff_lon - 360.0f; else if (diff_lon < -180.0f) diff_lon = diff_lon + 360.0f;
+        float diff_lat = latp - latm;
+        return -o_atan2(-o_cos(LL(xlat, i, j) * ORC_RAD_PER_DEG) * diff_lon * ORC_RAD_PER_DEG, diff_lat * ORC_RAD_PER_DEG);
+    }
+    int ja, jb;   /* :190-222: last row looks back, first row looks ahead, interior rows are centred */
+    if (j == e2) { ja = j; jb = j - 1; } else if (j == s2) { ja = j + 1; jb = j; } else { ja = j + 1; jb = j - 1; }
+    float diff = LL(xlon, i, ja) - LL(xlon, i, jb);
+    if (diff > 180.0f) diff = diff - 360.0f; else if (diff < -180.0f) diff = diff + 360.0f;
+    return o_atan2(-o_cos(LL(xlat, i, j) * ORC_RAD_PER_DEG) * diff * ORC_RAD_PER_DEG, (LL(xlat, i, ja) - LL(xlat, i, jb)) * ORC_RAD_PER_DEG);
+#undef LL
+}
+
+/* rotate_winds_module.F:85-387, C grid.  xlat_u / xlat_v are only read for PROJ_CASSINI (may be NULL otherwise). */
+void orc_metmap_xform_ll(const orc_proj *proj, float *u, const int32_t *u_mask, float *v, const int32_t *v_mask,
+                         int us1, int us2, int ue1, int ue2, int vs1, int vs2, int ve1, int ve2,
+                         const float *xlon_u, const float *xlon_v, const float *xlat_u, const float *xlat_v, int idir);
 void orc_metmap_xform(const orc_proj *proj, float *u, const int32_t *u_mask, float *v, const int32_t *v_mask,
                       int us1, int us2, int ue1, int ue2, int vs1, int vs2, int ve1, int ve2,
                       const float *xlon_u, const float *xlon_v, int idir)
 {
+    orc_metmap_xform_ll(proj, u, u_mask, v, v_mask, us1, us2, ue1, ue2, vs1, vs2, ve1, ve2, xlon_u, xlon_v, NULL, NULL, idir);
+}
+void orc_metmap_xform_ll(const orc_proj *proj, float *u, const int32_t *u_mask, float *v, const int32_t *v_mask,
+                         int us1, int us2, int ue1, int ue2, int vs1, int vs2, int ve1, int ve2,
+                         const float *xlon_u, const float *xlon_v, const float *xlat_u, const float *xlat_v, int idir)
+{
     if (!(proj->code == ORC_PROJ_LC || proj->code == ORC_PROJ_PS || proj->code == ORC_PROJ_CASSINI)) return;
+    if (proj->code == ORC_PROJ_CASSINI && (!xlat_u || !xlat_v)) return;
     int unx = ue1 - us1 + 1, uny = ue2 - us2 + 1, vnx = ve1 - vs1 + 1, vny = ve2 - vs2 + 1;
     int unxw = (unx + 31) / 32, vnxw = (vnx + 31) / 32;
 #define UU(a, i, j) (a)[(long)((j) - us2) * unx + ((i) - us1)]
@@ -257,6 +292,7 @@ void orc_metmap_xform(const orc_proj *proj, float *u, const int32_t *u_mask, flo
         if (diff > 180.0f) diff = diff - 360.0f; else if (diff < -180.0f) diff = diff + 360.0f;
         float alpha;
         if (proj->code == ORC_PROJ_LC) alpha = diff * proj->cone * ORC_RAD_PER_DEG * proj->hemi;
+        else if (proj->code == ORC_PROJ_CASSINI) alpha = cassini_alpha(proj, idir, xlat_u, xlon_u, us1, us2, ue2, unx, i, j);
         else alpha = diff * ORC_RAD_PER_DEG * proj->hemi;
         float v_weight = 0.0f, v_map = 0.0f;
         if (orc_bit_test(u_mask, unxw, i - us1 + 1, j - us2 + 1)) {
@@ -284,6 +320,7 @@ void orc_metmap_xform(const orc_proj *proj, float *u, const int32_t *u_mask, flo
         if (diff > 180.0f) diff = diff - 360.0f; else if (diff < -180.0f) diff = diff + 360.0f;
         float alpha;
         if (proj->code == ORC_PROJ_LC) alpha = diff * proj->cone * ORC_RAD_PER_DEG * proj->hemi;
+        else if (proj->code == ORC_PROJ_CASSINI) alpha = cassini_alpha(proj, idir, xlat_v, xlon_v, vs1, vs2, ve2, vnx, i, j);
         else alpha = diff * ORC_RAD_PER_DEG * proj->hemi;
         float u_weight = 0.0f, u_map = 0.0f;
         if (orc_bit_test(v_mask, vnxw, i - vs1 + 1, j - vs2 + 1)) {

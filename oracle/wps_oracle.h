@@ -156,6 +156,9 @@ void orc_interp_met_field_gcell(orc_proj *src, orc_proj *dom, const orc_field_op
                                 const float *mask, const float *landmask, int process_bdy_width,
                                 float *r_arr, const int32_t *valid_mask, int32_t *new_pts);
 /* metmap_xform, rotate_winds_module.F:85-387 (C grid; LC / PS / "plain" alpha only, no Cassini) */
+void orc_metmap_xform_ll(const orc_proj *proj, float *u, const int32_t *u_mask, float *v, const int32_t *v_mask,
+                         int us1, int us2, int ue1, int ue2, int vs1, int vs2, int ve1, int ve2,
+                         const float *xlon_u, const float *xlon_v, const float *xlat_u, const float *xlat_v, int idir);
 void orc_metmap_xform(const orc_proj *proj, float *u, const int32_t *u_mask, float *v, const int32_t *v_mask,
                       int us1, int us2, int ue1, int ue2, int vs1, int vs2, int ve1, int ve2,
                       const float *xlon_u, const float *xlon_v, int idir);

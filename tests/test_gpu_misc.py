@@ -146,3 +146,37 @@ def test_geometry_outputs(orc, handle):
     for m in (mf, None):
         assert_bitexact(handle.dfdx(hgt, 1, 30000., m), orc.calc_dfd("x", hgt, 1, m, 30000.), "dfdx")
         assert_bitexact(handle.dfdy(hgt, 1, 30000., m), orc.calc_dfd("y", hgt, 1, m, 30000.), "dfdy")
+
+
+@pytest.mark.parametrize("idir", [1, -1])
+def test_rotate_winds_cassini(orc, handle, idir):
+    """PROJ_CASSINI branches of metmap_xform (rotate_winds_module.F:174-222, 281-329): the rotation angle comes from
+    finite differences (of ij_to_latlon at y +- 0.1 for map_to_met, of the domain's lat/lon arrays along j for
+    met_to_map) instead of the standard-longitude formula; needs xlat_u / xlat_v besides xlon."""
+    from wps_b200 import capi
+    rng = np.random.default_rng(3)
+    kw = dict(latinc=0.5, loninc=0.5, lat1=10., lon1=-20., lat0=60., lon0=-140., knowni=1., knownj=1., stdlon=-140., dx=55000., dy=55000.)
+    orc.set_transc_mode(1)
+    po, pg = orc.map_set(orc.PROJ_CASSINI, **kw), capi.map_set(capi.PROJ_CASSINI, **kw)
+    nx, ny, nlev = 47, 39, 3
+    xlat_u, xlon_u = orc.get_lat_lon_fields(po, 1, 1, nx + 1, ny, orc.U)
+    xlat_v, xlon_v = orc.get_lat_lon_fields(po, 1, 1, nx, ny + 1, orc.V)
+    u = rng.uniform(-30, 30, (nlev, ny, nx + 1)).astype(np.float32)
+    v = rng.uniform(-30, 30, (nlev, ny + 1, nx)).astype(np.float32)
+    um = np.stack([bool_to_bits(rng.random((ny, nx + 1)) < p) for p in (1.0, 0.8, 0.5)])
+    vm = np.stack([bool_to_bits(rng.random((ny + 1, nx)) < p) for p in (1.0, 0.9, 0.5)])
+    ug, vg = u.copy(), v.copy()
+    handle.rotate_winds(idir, pg, ug, um, vg, vm, xlon_u, xlon_v, xlat_u=xlat_u, xlat_v=xlat_v)
+    changed = 0
+    for l in range(nlev):
+        uo, vo = orc.metmap_xform(po, u[l], um[l], v[l], vm[l], xlon_u, xlon_v, idir, xlat_u=xlat_u, xlat_v=xlat_v)
+        d = max(ulp_diff(ug[l], uo).max(), ulp_diff(vg[l], vo).max())
+        frac = max((ulp_diff(ug[l], uo) > 0).mean(), (ulp_diff(vg[l], vo) > 0).mean())
+        # every transcendental is FP64-then-round on both sides; the rotated-pole transform feeding alpha (idir=+1) may
+        # flip a last bit in rare double-rounding cases, which cos/sin(alpha) carry into the result
+        assert d <= 2 and frac < 2e-3, (idir, l, d, frac)
+        changed += int((uo != u[l]).sum())
+    assert changed > 0
+    # without the latitudes the Cassini rotation is refused loudly
+    with pytest.raises(capi.WpsGpuError):
+        handle.rotate_winds(idir, pg, u.copy(), um, v.copy(), vm, xlon_u, xlon_v)

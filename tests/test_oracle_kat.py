@@ -214,3 +214,24 @@ def test_fill_missing_levels_known_answers():
     assert r2[1, 0, 0] == v200 and r2[2, 0, 0] == v400
     assert [int(x) for x in v2[:, 0, 0]] == [1 | 4, 1 | 4, 1 | 2, 1 | 2]
     assert r2[0, 0, 1] == 0.0 and r2[1, 0, 1] == 0.0 and r2[2, 0, 2] == 0.0 and r2[3, 0, 2] == 0.0
+
+
+def test_cassini_rotation_unrotated_pole_is_identity():
+    """rotate_winds_module.F:190-222 by hand: with the computational pole at the geographic pole (lat0 = 90) the
+    domain's longitudes do not change along j, so diff = 0, alpha = atan2(-0, dlat) = -0 and u_new = cos(0)*u +
+    sin(-0)*v/w = u exactly (likewise v)."""
+    from oracle import oracle as O
+    O.set_transc_mode(1)
+    p = O.map_set(O.PROJ_CASSINI, latinc=0.5, loninc=0.5, lat1=10., lon1=-20., lat0=90., lon0=0., knowni=1., knownj=1.,
+                  stdlon=0., dx=55000., dy=55000.)
+    nx, ny = 12, 9
+    xlat_u, xlon_u = O.get_lat_lon_fields(p, 1, 1, nx + 1, ny, O.U)
+    xlat_v, xlon_v = O.get_lat_lon_fields(p, 1, 1, nx, ny + 1, O.V)
+    assert np.ptp(xlon_u, axis=0).max() == 0.0
+    rng = np.random.default_rng(0)
+    u = rng.uniform(-20, 20, (ny, nx + 1)).astype(np.float32)
+    v = rng.uniform(-20, 20, (ny + 1, nx)).astype(np.float32)
+    full_u = np.full((ny, (nx + 1 + 31) // 32), -1, np.int32)
+    full_v = np.full((ny + 1, (nx + 31) // 32), -1, np.int32)
+    uo, vo = O.metmap_xform(p, u, full_u, v, full_v, xlon_u, xlon_v, -1, xlat_u=xlat_u, xlat_v=xlat_v)
+    assert np.array_equal(uo, u) and np.array_equal(vo, v)

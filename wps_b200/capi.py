@@ -326,14 +326,15 @@ class Handle:
     def debug_disable_fast(self, disable=True):
         check(lib().wpsgpu_debug_disable_fast(self._h, int(disable)))
 
-    def rotate_winds(self, idir, proj, u, u_mask, v, v_mask, xlon_u, xlon_v, us=(1, 1), vs=(1, 1)):
-        """u [nlev][uny][unx], v [nlev][vny][vnx] rotated in place (metmap_xform)."""
+    def rotate_winds(self, idir, proj, u, u_mask, v, v_mask, xlon_u, xlon_v, us=(1, 1), vs=(1, 1), xlat_u=None, xlat_v=None):
+        """u [nlev][uny][unx], v [nlev][vny][vnx] rotated in place (metmap_xform); xlat_u / xlat_v for PROJ_CASSINI."""
         nlev, uny, unx = u.shape
         _, vny, vnx = v.shape
-        check(lib().wpsgpu_rotate_winds(self._h, int(idir), C.byref(proj), C.c_void_p(ptr(u)), C.c_void_p(ptr(u_mask)),
-                                        C.c_void_p(ptr(v)), C.c_void_p(ptr(v_mask)), us[0], us[1], us[0] + unx - 1,
-                                        us[1] + uny - 1, vs[0], vs[1], vs[0] + vnx - 1, vs[1] + vny - 1,
-                                        C.c_void_p(ptr(xlon_u)), C.c_void_p(ptr(xlon_v)), int(nlev)))
+        check(lib().wpsgpu_rotate_winds_ll(self._h, int(idir), C.byref(proj), C.c_void_p(ptr(u)), C.c_void_p(ptr(u_mask)),
+                                           C.c_void_p(ptr(v)), C.c_void_p(ptr(v_mask)), us[0], us[1], us[0] + unx - 1,
+                                           us[1] + uny - 1, vs[0], vs[1], vs[0] + vnx - 1, vs[1] + vny - 1,
+                                           C.c_void_p(ptr(xlon_u)), C.c_void_p(ptr(xlon_v)), C.c_void_p(ptr(xlat_u)),
+                                           C.c_void_p(ptr(xlat_v)), int(nlev)))
 
     # ---- geogrid ----
     def geogrid_field_begin(self, dom_proj, istagger, xlat, xlon, start_i, start_j, start_k, field, landmask=None):

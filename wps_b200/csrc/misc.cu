@@ -6,7 +6,9 @@ namespace wps {
 
 // ---- metmap_xform (rotate_winds_module.F:85-387), C grid, LC / PS (Cassini branches not ported) ----
 struct RotArgs {
-    const float *u, *v, *xlon_u, *xlon_v;
+    const float *u, *v, *xlon_u, *xlon_v, *xlat_u, *xlat_v;
+    int is_cassini;
+    DevProj proj;
     const int *u_mask, *v_mask;
     float *u_new, *v_new;
     int us1, us2, ue1, ue2, vs1, vs2, ve1, ve2, unx, uny, vnx, vny, unxw, vnxw;
@@ -15,11 +17,34 @@ struct RotArgs {
     int do_last_col_u, do_last_row_u, do_last_col_v, do_last_row_v;
 };
 
-__device__ __forceinline__ float rot_alpha(const RotArgs& a, float xlon)
+// rotation angle of one point; (ii, jj) 0-based in the nx x ny array the point belongs to (rotate_winds_module.F:161-226)
+__device__ __forceinline__ float rot_alpha(const RotArgs& a, const float* __restrict__ xlat, const float* __restrict__ xlon,
+                                           int nx, int ny, int ii, int jj)
 {
-    float diff = (float)a.idir * (xlon - a.stdlon);
+    const size_t o = (size_t)jj * nx + ii;
+    float diff = (float)a.idir * (xlon[o] - a.stdlon);
     if (diff > 180.0f) diff = diff - 360.0f; else if (diff < -180.0f) diff = diff + 360.0f;
-    return a.is_lc ? (diff * a.cone * WPS_RAD_PER_DEG * a.hemi) : (diff * WPS_RAD_PER_DEG * a.hemi);
+    if (a.is_lc) return diff * a.cone * WPS_RAD_PER_DEG * a.hemi;
+    if (a.is_cassini) {
+        if (a.idir == 1) {   // :174-189: finite difference of the source projection along its own y axis
+            float x, y, latp, lonp, latm, lonm;
+            latlon_to_ij(a.proj, xlat[o], xlon[o], x, y);
+            ij_to_latlon(a.proj, x, y + 0.1f, latp, lonp);
+            ij_to_latlon(a.proj, x, y - 0.1f, latm, lonm);
+            float diff_lon = lonp - lonm;
+            if (diff_lon > 180.0f) diff_lon = diff_lon - 360.0f; else if (diff_lon < -180.0f) diff_lon = diff_lon + 360.0f;
+            float diff_lat = latp - latm;
+            return -t_atan2(-t_cos(xlat[o] * WPS_RAD_PER_DEG) * diff_lon * WPS_RAD_PER_DEG, diff_lat * WPS_RAD_PER_DEG);
+        }
+        // :190-222: difference of the domain's lat/lon along j, one-sided on the first and last rows
+        int ja, jb;
+        if (jj == ny - 1) { ja = jj; jb = jj - 1; } else if (jj == 0) { ja = jj + 1; jb = jj; } else { ja = jj + 1; jb = jj - 1; }
+        const size_t oa = (size_t)ja * nx + ii, ob = (size_t)jb * nx + ii;
+        float d = xlon[oa] - xlon[ob];
+        if (d > 180.0f) d = d - 360.0f; else if (d < -180.0f) d = d + 360.0f;
+        return t_atan2(-t_cos(xlat[o] * WPS_RAD_PER_DEG) * d * WPS_RAD_PER_DEG, (xlat[oa] - xlat[ob]) * WPS_RAD_PER_DEG);
+    }
+    return diff * WPS_RAD_PER_DEG * a.hemi;
 }
 
 __global__ void k_rotate_u(RotArgs a, int nlev)
@@ -36,7 +61,7 @@ __global__ void k_rotate_u(RotArgs a, int nlev)
     size_t o = (size_t)jj * a.unx + ii;
     float uold = u[o], res = uold;
     if (ubit(i, j)) {
-        float alpha = rot_alpha(a, a.xlon_u[o]);
+        float alpha = rot_alpha(a, a.xlat_u, a.xlon_u, a.unx, a.uny, ii, jj);
         float v_weight, v_map;
         if (i == a.us1) {
             if (j == a.ue2 && a.do_last_row_u) { v_weight = vmul(i, j); v_map = V(i, j) * vmul(i, j); }
@@ -70,7 +95,7 @@ __global__ void k_rotate_v(RotArgs a, int nlev)
     size_t o = (size_t)jj * a.vnx + ii;
     float vold = v[o], res = vold;
     if (vbit(i, j)) {
-        float alpha = rot_alpha(a, a.xlon_v[o]);
+        float alpha = rot_alpha(a, a.xlat_v, a.xlon_v, a.vnx, a.vny, ii, jj);
         float u_weight, u_map;
         if (j == a.vs2) {
             if (i == a.ve1 && a.do_last_col_v) { u_weight = umul(i, j); u_map = U(i, j) * umul(i, j); }
@@ -421,16 +446,28 @@ int wpsgpu_rotate_winds(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj, fl
                         float* v, const int32_t* v_mask, int us1, int us2, int ue1, int ue2,
                         int vs1, int vs2, int ve1, int ve2, const float* xlon_u, const float* xlon_v, int nlev)
 {
+    return wpsgpu_rotate_winds_ll(h, idir, proj, u, u_mask, v, v_mask, us1, us2, ue1, ue2, vs1, vs2, ve1, ve2, xlon_u, xlon_v,
+                                  nullptr, nullptr, nlev);
+}
+
+int wpsgpu_rotate_winds_ll(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj, float* u, const int32_t* u_mask,
+                           float* v, const int32_t* v_mask, int us1, int us2, int ue1, int ue2,
+                           int vs1, int vs2, int ve1, int ve2, const float* xlon_u, const float* xlon_v,
+                           const float* xlat_u, const float* xlat_v, int nlev)
+{
     WPS_CHECK(h && proj && u && v && u_mask && v_mask && xlon_u && xlon_v, -1, "wpsgpu_rotate_winds: NULL argument");
     WPS_CHECK(proj->init, -1, "In metmap_xform(), uninitialized proj_info structure.");
-    WPS_CHECK(proj->code != WPSGPU_PROJ_CASSINI, -30, "wpsgpu_rotate_winds: Cassini wind rotation is not ported");
-    if (!(proj->code == WPSGPU_PROJ_LC || proj->code == WPSGPU_PROJ_PS)) return 0;  // only LC / PS rotate (:112-114)
+    WPS_CHECK(proj->code != WPSGPU_PROJ_CASSINI || (xlat_u && xlat_v), -30,
+              "wpsgpu_rotate_winds: Cassini wind rotation needs xlat_u / xlat_v (use wpsgpu_rotate_winds_ll)");
+    if (!(proj->code == WPSGPU_PROJ_LC || proj->code == WPSGPU_PROJ_PS || proj->code == WPSGPU_PROJ_CASSINI)) return 0;  // :112-114
+    WPS_CHECK(proj->code != WPSGPU_PROJ_CASSINI || idir == 1 || (ue2 > us2 && ve2 > vs2), -1,
+              "wpsgpu_rotate_winds: Cassini met_to_map needs at least two rows");
     RotArgs a;
     a.unx = ue1 - us1 + 1; a.uny = ue2 - us2 + 1; a.vnx = ve1 - vs1 + 1; a.vny = ve2 - vs2 + 1;
     a.unxw = (a.unx + 31) / 32; a.vnxw = (a.vnx + 31) / 32;
     size_t ub = sizeof(float) * a.unx * a.uny, vb = sizeof(float) * a.vnx * a.vny;
     size_t umb = sizeof(int) * a.uny * a.unxw, vmb = sizeof(int) * a.vny * a.vnxw;
-    WPS_TRY(begin_call(h, 2 * (ub + vb) * nlev + (umb + vmb) * nlev + ub + vb + 8192));
+    WPS_TRY(begin_call(h, 2 * (ub + vb) * nlev + (umb + vmb) * nlev + 2 * (ub + vb) + 8192));
     if (h->ptr_mode == WPSGPU_PTR_DEVICE) WPS_TRY(h->arena.reserve((ub + vb) * nlev + (1 << 20), h->stream));
     void *du, *dv, *dum, *dvm, *dxu, *dxv;
     WPS_TRY(stage_inout(h, u, ub * nlev, &du));
@@ -439,6 +476,11 @@ int wpsgpu_rotate_winds(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj, fl
     WPS_TRY(stage_in(h, v_mask, vmb * nlev, &dvm));
     WPS_TRY(stage_in(h, xlon_u, ub, &dxu));
     WPS_TRY(stage_in(h, xlon_v, vb, &dxv));
+    void *dlu = nullptr, *dlv = nullptr;
+    if (proj->code == WPSGPU_PROJ_CASSINI) { WPS_TRY(stage_in(h, xlat_u, ub, &dlu)); WPS_TRY(stage_in(h, xlat_v, vb, &dlv)); }
+    a.xlat_u = (const float*)dlu; a.xlat_v = (const float*)dlv;
+    a.is_cassini = proj->code == WPSGPU_PROJ_CASSINI;
+    a.proj = to_dev(*proj, nullptr);
     a.u_new = (float*)h->arena.take(ub * nlev);
     a.v_new = (float*)h->arena.take(vb * nlev);
     WPS_CHECK(a.u_new && a.v_new, -3, "device arena exhausted");

@@ -250,7 +250,8 @@ class MetgridDomain:
         pick = (lambda f: f.modified_mask) if only_modified else (lambda f: f.valid_mask)
         um = np.stack([pick(storage[(u_name, l)]) for l in levels])
         vm = np.stack([pick(storage[(v_name, l)]) for l in levels])
-        self.h.rotate_winds(idir, proj, u, um, v, vm, self.grids[capi.U][1], self.grids[capi.V][1], us=self.sm, vs=self.sm)
+        self.h.rotate_winds(idir, proj, u, um, v, vm, self.grids[capi.U][1], self.grids[capi.V][1], us=self.sm, vs=self.sm,
+                            xlat_u=self.grids[capi.U][0], xlat_v=self.grids[capi.V][0])
         for k, l in enumerate(levels):
             storage[(u_name, l)].r_arr[:] = u[k]
             storage[(v_name, l)].r_arr[:] = v[k]
