@@ -404,6 +404,13 @@ def run_b200(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None   # DRAM bytes of the dominant kernel's launches in one step, from the committed ncu capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_fast16_traffic.json")))
+            if p3[1] >= p3[2] and abs(tj["kernel_points"] - kp) < 0.01 * kp:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except Exception:
+            pass
         kms_avg = float(np.mean(kms))
         achieved = ALG_BYTES_PER_POINT * kp / (kms_avg * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -413,7 +420,8 @@ def run_b200(args, rank, world, local_rank):
                            "points_per_step_per_gpu": pts, "l2": "inputs (792 MB of source slabs) and outputs (1.45 GB) per step exceed the 126 MB L2",
                            "sharding": "one FILE time per GPU per step (field x level x time shard, no collective)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "k_metgrid_fast16" if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
+                             "traffic": traffic, "traffic_unit": "bytes per step (all launches of the kernel), ncu dram read+write; algorithmic = %d" % int(ALG_BYTES_PER_POINT * kp),
+                             "kernel": "k_metgrid_fast16" if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
                              "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
                              "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
                              "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
