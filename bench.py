@@ -105,7 +105,7 @@ def run_reference(args, rank):
         cpu_arm(config, 2, nprocs)
     times, pts = [], 0
     for _ in range(args.steps):
-        pps, dt, p, nprocs, desc = cpu_arm(config, 16, nprocs, 3)
+        pps, dt, p, nprocs, desc = cpu_arm(config, 16, nprocs, 8)
         times.append(dt)
         pts = p
     ms = 1e3 * float(np.mean(times))
@@ -432,7 +432,7 @@ def run_b200(args, rank, world, local_rank):
             line["geogrid"] = geo
             line["vertical_fill"] = vfill
         if world == 1 and not args.no_cpu:
-            pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 3)
+            pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 8)
             line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}
         print(json.dumps(line))
     h.close()
