@@ -31,6 +31,7 @@ module wpsgpu_mod
       type(c_ptr) :: mask(3)
       integer(c_int32_t) :: grid_id, field_stagger, use_landmask, process_bdy_width
       type(c_ptr) :: r_arr, valid_mask, new_pts
+      integer(c_int32_t) :: raw_nx = 0, raw_big_endian = 0   ! raw-record ingest: slab = fg_data%slab as read, see wpsgpu.h
    end type wpsgpu_slab
 
    interface

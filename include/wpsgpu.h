@@ -138,6 +138,13 @@ typedef struct wpsgpu_slab {
     float *r_arr;                   /* field%r_arr(sm1:em1,sm2:em2), inout */
     const int32_t *valid_mask;      /* field%valid_mask words, NULL = freshly created (all clear) */
     int32_t *new_pts;               /* field%modified_mask words, out (caller passes a zeroed array) */
+    /* Raw-record ingest (read_met_module.F:375-386 + halo_slab, process_domain_module.F:1119-1140), optional:
+     * raw_nx > 0 says `slab` is not the halo'd array but the record's slab(1:raw_nx, miny:maxy) exactly as it sits in
+     * the intermediate file -- 4-byte words, big-endian when raw_big_endian != 0.  The library byte-swaps it on the
+     * device and builds slab(minx:maxx) with bdr = (maxx-minx+1-raw_nx)/2 wrap-around columns on each side (bdr may
+     * be 0 for regional data), so the host neither converts nor copies the slab.  raw_nx == 0: `slab` is ready. */
+    int32_t raw_nx;
+    int32_t raw_big_endian;
 } wpsgpu_slab;
 
 /* Queue one interp_met_field call (non-average_gcell branch, :2483-2581). */

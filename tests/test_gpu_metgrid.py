@@ -450,3 +450,47 @@ def test_config2_full_size_windows_and_kernel_agreement(orc, handle):
             win = (slice(j0 - 1, j1), slice(i0 - 1, i1))
             assert (bits_to_bool(n_ref, nx)[win] == bits_dev[win]).all(), "case %d window %s: new_pts" % (k, (i0, j0))
             assert_bitexact(r_dev[win], r_ref[win], "case %d window %s" % (k, (i0, j0)))
+
+
+@pytest.mark.parametrize("big_endian", [True, False])
+def test_raw_record_ingest(orc, handle, big_endian):
+    """the slab is handed over exactly as it sits in the intermediate file (big-endian 4-byte words,
+    no halo); the library byte-swaps it and builds halo_slab (process_domain_module.F:1119-1140) on the device.  Result
+    must equal both the oracle and the path that gets a ready, host-built halo'd slab -- for a global source (bdr 3),
+    a regional one (bdr 0), and when the same record is queued twice."""
+    from wps_b200 import capi
+    xlat, xlon = make_domain(orc, handle, nx=75, ny=58)
+    ny, nx = xlat.shape
+    osrc, gsrc = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    chain = "sixteen_pt+four_pt+average_4pt"
+    fo_o, fo_g = orc.field_opts(chain, 1e20, 0.0, -2.0), capi.field_opts(chain, 1e20, 0.0, -2.0)
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    nlev = 5
+    recs = [synth_field(360, 181, 900 + s, kind="wind" if s % 2 else "smooth", zeros=0.002) for s in range(nlev)]
+    raw = np.stack(recs).astype(">f4" if big_endian else "<f4")        # contiguous, byte order as in the file
+    assert raw.dtype.byteorder == (">" if big_endian else "=") or not big_endian
+    raw_words = raw.view(np.float32)                                     # same bytes, no conversion
+    r = np.zeros((nlev + 1, ny, nx), np.float32)
+    npw = np.zeros((nlev + 1, ny, capi.nwords(nx)), np.int32)
+    for l in range(nlev):
+        handle.metgrid_enqueue_slab(gsrc, fo_g, raw_words[l], -2, 1, 3, 0, capi.M, r[l], npw[l], raw_big_endian=big_endian)
+    handle.metgrid_enqueue_slab(gsrc, fo_g, raw_words[2], -2, 1, 3, 0, capi.M, r[nlev], npw[nlev], raw_big_endian=big_endian)
+    handle.metgrid_flush()
+    orc.set_transc_mode(1)
+    for l in range(nlev):
+        r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), halo(recs[l]), -2, 1, 3)
+        assert (npw[l] == np_ref).all()
+        assert_bitexact(r[l], r_ref, "raw record, level %d" % l)
+    assert_bitexact(r[nlev], r[2], "record queued twice")
+    # regional source, no halo: only the byte order changes
+    reg_o, reg_g = latlon_source(120, 90, -0.25, 0.25, 50.0, -110.0)
+    rec = synth_field(120, 90, 77)
+    rr = np.zeros((ny, nx), np.float32)
+    nn = np.zeros((ny, capi.nwords(nx)), np.int32)
+    rec_raw = rec.astype(">f4" if big_endian else "<f4").view(np.float32)
+    handle.metgrid_enqueue_slab(reg_g, fo_g, rec_raw, 1, 1, 0, 0, capi.M, rr, nn, raw_big_endian=big_endian)
+    handle.metgrid_flush()
+    r_ref, np_ref = orc.interp_met_field(reg_o, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), rec, 1, 1, 0)
+    assert (nn == np_ref).all()
+    assert_bitexact(rr, r_ref, "regional raw record")

@@ -53,7 +53,8 @@ class Slab(C.Structure):
     _fields_ = [("slab", C.c_void_p), ("minx", C.c_int32), ("maxx", C.c_int32), ("miny", C.c_int32),
                 ("maxy", C.c_int32), ("bdr", C.c_int32), ("mask", C.c_void_p * 3), ("grid_id", C.c_int32),
                 ("field_stagger", C.c_int32), ("use_landmask", C.c_int32), ("process_bdy_width", C.c_int32),
-                ("r_arr", C.c_void_p), ("valid_mask", C.c_void_p), ("new_pts", C.c_void_p)]
+                ("r_arr", C.c_void_p), ("valid_mask", C.c_void_p), ("new_pts", C.c_void_p),
+                ("raw_nx", C.c_int32), ("raw_big_endian", C.c_int32)]
 
 
 class GeoField(C.Structure):
@@ -245,11 +246,17 @@ class Handle:
 
     @staticmethod
     def slab_desc(slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts, valid_mask=None,
-                  masks=(None, None, None), use_landmask=False, process_bdy_width=0, out=None):
-        """Fill a wpsgpu_slab descriptor (a caller that re-uses its buffers can build these once)."""
+                  masks=(None, None, None), use_landmask=False, process_bdy_width=0, out=None, raw_big_endian=None):
+        """Fill a wpsgpu_slab descriptor (a caller that re-uses its buffers can build these once).
+        raw_big_endian not None: `slab` is the record's [ny][nx] array as stored in the file (4-byte words, big-endian
+        if True) and the library adds the `bdr` wrap-around columns itself; minx then still names the halo'd bound."""
         sny, snx = slab.shape
         s = Slab() if out is None else out
         s.slab = ptr(slab)
+        s.raw_nx, s.raw_big_endian = 0, 0
+        if raw_big_endian is not None:
+            s.raw_nx, s.raw_big_endian = int(snx), int(bool(raw_big_endian))
+            snx = snx + 2 * int(bdr)
         s.minx, s.maxx, s.miny, s.maxy, s.bdr = int(minx), int(minx + snx - 1), int(miny), int(miny + sny - 1), int(bdr)
         for i in range(3):
             s.mask[i] = ptr(masks[i])
@@ -268,20 +275,10 @@ class Handle:
         check(lib().wpsgpu_metgrid_enqueue_slabs(self._h, C.byref(proj), C.byref(fo), descs, n))
 
     def metgrid_enqueue_slab(self, proj, fo, slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts,
-                             valid_mask=None, masks=(None, None, None), use_landmask=False, process_bdy_width=0):
-        sny, snx = slab.shape
-        s = Slab()
-        s.slab = ptr(slab)
-        s.minx, s.maxx, s.miny, s.maxy, s.bdr = int(minx), int(minx + snx - 1), int(miny), int(miny + sny - 1), int(bdr)
-        for i in range(3):
-            s.mask[i] = ptr(masks[i])
-        s.grid_id = int(grid_id)
-        s.field_stagger = int(field_stagger)
-        s.use_landmask = int(bool(use_landmask))
-        s.process_bdy_width = int(process_bdy_width)
-        s.r_arr = ptr(r_arr)
-        s.valid_mask = ptr(valid_mask)
-        s.new_pts = ptr(new_pts)
+                             valid_mask=None, masks=(None, None, None), use_landmask=False, process_bdy_width=0,
+                             raw_big_endian=None):
+        s = self.slab_desc(slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts, valid_mask=valid_mask, masks=masks,
+                           use_landmask=use_landmask, process_bdy_width=process_bdy_width, raw_big_endian=raw_big_endian)
         check(lib().wpsgpu_metgrid_enqueue_slab(self._h, C.byref(proj), C.byref(fo), C.byref(s)))
 
     def metgrid_enqueue_gcell_slab(self, proj, dom_proj, fo, slab, minx, miny, bdr, grid_id, field_stagger, r_arr, new_pts,

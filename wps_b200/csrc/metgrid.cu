@@ -58,6 +58,23 @@ __global__ void k_coord_cache(DevProj p, const float* __restrict__ xlat, const f
     xy[k] = make_float2(x, y);
 }
 
+// ---- raw intermediate-file records -> halo'd source slabs (read_met_module.F:375-386, process_domain_module.F:1119-1140)
+struct DecodeTask { const unsigned* raw; float* out; int raw_nx, ny, bdr, big_endian; };
+
+__global__ void __launch_bounds__(256) k_decode_records(const DecodeTask* __restrict__ tasks)
+{
+    const DecodeTask t = tasks[blockIdx.y];
+    const int snx = t.raw_nx + 2 * t.bdr;
+    const size_t n = (size_t)snx * t.ny;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        int i = (int)(e % snx) - t.bdr, j = (int)(e / snx);          // i: 0-based column of the record, halo columns outside
+        if (i < 0) i += t.raw_nx; else if (i >= t.raw_nx) i -= t.raw_nx;   // halo_slab(1-bdr:0) = slab(nx-bdr+1:nx), (nx+1:nx+bdr) = slab(1:bdr)
+        unsigned w = __ldg(t.raw + (size_t)j * t.raw_nx + i);
+        if (t.big_endian) w = __byte_perm(w, 0, 0x0123);
+        t.out[e] = __uint_as_float(w);
+    }
+}
+
 // ---- per-point logic of interp_met_field (non-gcell branch, :2487-2579) ------------------------
 // out flags
 enum { PF_WRITE = 1, PF_BIT = 2, PF_DEFER = 4 };
@@ -880,6 +897,11 @@ int wpsgpu_metgrid_enqueue_slab(wpsgpu_handle_t h, const wpsgpu_proj* src_proj, 
     WPS_CHECK(h->domain_set, -1, "wpsgpu_metgrid_set_domain has not been called");
     WPS_CHECK(slab->slab && slab->r_arr && slab->new_pts, -1, "slab, r_arr and new_pts must be non-NULL");
     WPS_CHECK(slab->maxx >= slab->minx && slab->maxy >= slab->miny, -1, "empty source slab");
+    if (slab->raw_nx != 0) {
+        const int halo2 = slab->maxx - slab->minx + 1 - slab->raw_nx;
+        WPS_CHECK(slab->raw_nx > 0 && halo2 >= 0 && halo2 % 2 == 0 && halo2 / 2 <= slab->raw_nx, -1,
+                  "raw record of %d columns does not fit slab bounds %d..%d", slab->raw_nx, slab->minx, slab->maxx);
+    }
     WPS_CHECK(!slab->use_landmask || h->grids[slab->grid_id].d_landmask, -1, "use_landmask set but no landmask given for grid %d", slab->grid_id);
     QueuedSlab q;
     q.proj = intern_proj(h, src_proj); q.fo = *fo; q.s = *slab;
@@ -992,6 +1014,10 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         *out = (const float*)d;
         return 0;
     };
+    std::vector<DecodeTask> decode_tasks;     // raw records of this pass
+    std::vector<int> decode_slots;            // their slab-table slots
+    std::vector<const void*> decode_hosts;
+    std::vector<std::pair<int, const void*>> decode_pending;
     std::vector<Job> jobs(njobs);
     std::vector<int*> gc_decided(njobs, nullptr);
     std::vector<SlabPtrs> sp(nq);
@@ -1064,7 +1090,24 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         for (int k = 0; k < ns; ++k) {
             SlabPtrs& p = sp[s0 + k];
             p.slow = nullptr; p.decided = nullptr; p.valid = nullptr;
-            WPS_TRY(stage_shared(queue[grp[k]].s.slab, sbytes, &p.src));
+            const wpsgpu_slab& s = queue[grp[k]].s;
+            if (s.raw_nx == 0) { WPS_TRY(stage_shared(s.slab, sbytes, &p.src)); continue; }
+            // raw record: bring the bytes over (host mode) and let k_decode_records build the slab
+            auto it = fs.staged.find(s.slab);
+            if (it != fs.staged.end()) {   // the same record queued again: share the decoded slab
+                if (it->second) p.src = (const float*)it->second; else decode_pending.push_back(std::make_pair(s0 + k, (const void*)s.slab));
+                continue;
+            }
+            const size_t rawbytes = (size_t)s.raw_nx * (jb.maxy - jb.miny + 1) * sizeof(float);
+            const void* d_raw = s.slab;
+            if (host) { d_raw = take_run(in_runs, s.slab, rawbytes); WPS_CHECK(d_raw != nullptr, -3, "device arena exhausted (raw records)"); }
+            DecodeTask t;
+            t.raw = (const unsigned*)d_raw; t.raw_nx = s.raw_nx; t.ny = jb.maxy - jb.miny + 1;
+            t.bdr = (jb.maxx - jb.minx + 1 - s.raw_nx) / 2; t.big_endian = s.raw_big_endian;
+            decode_tasks.push_back(t);
+            decode_slots.push_back(s0 + k);
+            fs.staged[s.slab] = nullptr;   // filled in once the decoded slabs are placed (below)
+            decode_hosts.push_back(s.slab);
         }
         if (jb.gcell) {
             gc_decided[j] = (int*)h->arena.take(wbytes);
@@ -1103,6 +1146,18 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             }
         }
     }
+    // decoded slabs are placed after the raw bytes so that the raw records of neighbouring levels stay adjacent
+    size_t decode_max = 0;
+    for (size_t k = 0; k < decode_tasks.size(); ++k) {
+        DecodeTask& t = decode_tasks[k];
+        const size_t n = (size_t)(t.raw_nx + 2 * t.bdr) * t.ny;
+        t.out = (float*)h->arena.take(n * sizeof(float));
+        WPS_CHECK(t.out != nullptr, -3, "device arena exhausted (decoded slabs)");
+        sp[decode_slots[k]].src = t.out;
+        fs.staged[decode_hosts[k]] = t.out;
+        decode_max = std::max(decode_max, n);
+    }
+    for (const auto& pr : decode_pending) sp[pr.first].src = (const float*)fs.staged[pr.second];
     for (const CopyRun& r : in_runs) WPS_CUDA(cudaMemcpyAsync(r.d, r.h, r.bytes, cudaMemcpyHostToDevice, s_in));
     // All tables of this pass travel in ONE copy: [jobs | slab pointers | six int lists of njobs+1 entries]
     std::vector<int> pack_jobs;
@@ -1117,7 +1172,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     WPS_CHECK(fast_words < 2000000000LL, -3, "too many output words in one flush");
     const size_t off_sp = (sizeof(Job) * njobs + 255) & ~size_t(255);
     const size_t off_cls = (off_sp + sizeof(SlabPtrs) * nq + 255) & ~size_t(255);
-    const size_t tab_bytes = off_cls + sizeof(int) * 6 * (njobs + 1);
+    const size_t off_dec = (off_cls + sizeof(int) * 6 * (njobs + 1) + 255) & ~size_t(255);
+    const size_t tab_bytes = off_dec + sizeof(DecodeTask) * decode_tasks.size();
     std::vector<char>& tab = fs.tab;
     tab.assign(tab_bytes, 0);
     memcpy(tab.data(), jobs.data(), sizeof(Job) * njobs);
@@ -1128,6 +1184,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         for (int c = 0; c < 6; ++c)
             if (!lists[c]->empty()) memcpy(cls + (size_t)c * (njobs + 1), lists[c]->data(), sizeof(int) * lists[c]->size());
     }
+    if (!decode_tasks.empty()) memcpy(tab.data() + off_dec, decode_tasks.data(), sizeof(DecodeTask) * decode_tasks.size());
     char* d_tab = (char*)h->arena.take(tab_bytes);
     WPS_CHECK(d_tab != nullptr, -3, "device arena exhausted (tables)");
     WPS_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab_bytes, cudaMemcpyHostToDevice, s_in));   // pageable source: staged before the call returns
@@ -1151,6 +1208,14 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
     }
     if (any_search) WPS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), h->stream));
+
+    // ---- raw records -> halo'd slabs (one launch for all records of this pass) ----
+    if (!decode_tasks.empty()) {
+        unsigned gx = (unsigned)std::min<size_t>((decode_max + 255) / 256, 4096);
+        k_decode_records<<<dim3(gx, (unsigned)decode_tasks.size()), 256, 0, h->stream>>>((const DecodeTask*)(d_tab + off_dec));
+        h->launches++;
+        WPS_CUDA(cudaGetLastError());
+    }
 
     // ---- average_gcell pre-pass: cell averages into r_arr + "decided" bits, one slab per job ----
     for (int j = 0; j < njobs; ++j) {
@@ -1408,13 +1473,16 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         if (host) {
             for (int m = 0; m < 3; ++m) if (q0.s.mask[m]) uniq_in[q0.s.mask[m]] = sbytes;
             for (int a : groups[g]) {
-                uniq_in[queue[a].s.slab] = sbytes;
+                uniq_in[queue[a].s.slab] = queue[a].s.raw_nx > 0 ? (size_t)queue[a].s.raw_nx * (q0.s.maxy - q0.s.miny + 1) * sizeof(float) : sbytes;
                 need += dg.npts() * sizeof(float) + 256;                                     // r_arr
                 need += 2 * ((size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 256);  // valid + new_pts
             }
         }
     }
     for (auto& kv : uniq_in) need += kv.second + 256;
+    for (int a = 0; a < nq; ++a)   // decoded copies of raw records (both pointer modes) + their task entries
+        if (queue[a].s.raw_nx > 0)
+            need += (size_t)(queue[a].s.maxx - queue[a].s.minx + 1) * (queue[a].s.maxy - queue[a].s.miny + 1) * sizeof(float) + 256 + sizeof(DecodeTask);
     need += 2 * (defer_entries * sizeof(Deferred) + 256) + (size_t)njobs * 4096;
     h->arena.reset();
     WPS_TRY(h->arena.reserve(need, h->stream));
