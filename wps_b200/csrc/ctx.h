@@ -111,7 +111,6 @@ struct wpsgpu_ctx {
     size_t search_scratch_bytes = 0;
     // CUDA events bracketing the dominant kernel of the last metgrid flush (roofline measurement)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // aliases into ev_t[] of the dominant kernel
-    cudaEvent_t ev_dummy0 = nullptr, ev_dummy1 = nullptr;
     cudaEvent_t ev_t[12] = {};  // pack / fast16 / generic / fast4 / slow-bitmap / search brackets
     double last_points = 0.0;
     double last_pts3[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };

@@ -48,6 +48,7 @@ struct GeoK {  // kernel-side view
     int* processed; int* level;
     int* acc_cnt; double* acc_sum; int* touched; unsigned long long* invalid;
     int* tbbox; const float4* blk_xy;
+    unsigned long long* counters;   // [0] deferred to the warp pass, [1] to the literal pass, [2] candidates of the point pass
     // current tile
     const float* tile; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny;
     int2* wm;
@@ -66,6 +67,10 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 {
     __shared__ float s_rm[WM_T], s_sin[WM_T], s_cos[WM_T], s_lat[WM_T], s_lon[WM_T];
     const int ti0 = blockIdx.x * WM_T, tj0 = blockIdx.y * WM_T, t = threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {   // per-tile state consumed by the kernels that follow in the stream
+        g.tbbox[0] = INT_MAX; g.tbbox[1] = INT_MAX; g.tbbox[2] = INT_MIN; g.tbbox[3] = INT_MIN;
+        g.counters[0] = 0ull; g.counters[1] = 0ull; g.counters[2] = 0ull;
+    }
     const bool separable = g.src.code == WPSGPU_PROJ_LATLON && (g.dom.code == WPSGPU_PROJ_LC || g.dom.code == WPSGPU_PROJ_PS);
     if (separable) {
         if (t < WM_T) {   // row terms: ijll_latlon gives lat from j alone
@@ -123,8 +128,13 @@ __global__ void __launch_bounds__(256) k_geo_accum(GeoK g)
         int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
         int2 dest;
         for (;;) {
-            int2 a = W(min_i, min_j), b = W(min_i, max_j), c = W(max_i, max_j), d = W(max_i, min_j);
-            if (a.x == b.x && a.x == c.x && a.x == d.x && a.y == b.y && a.y == c.y && a.y == d.y && a.x != GEO_OUTSIDE) { dest = a; break; }
+            // four corners agree?  The diagonal pair is compared first: on the upper levels it already differs and
+            // the other two corners need not be fetched.
+            int2 a = W(min_i, min_j), c = W(max_i, max_j);
+            if (a.x == c.x && a.y == c.y && a.x != GEO_OUTSIDE) {
+                int2 b = W(min_i, max_j), d = W(max_i, min_j);
+                if (a.x == b.x && a.x == d.x && a.y == b.y && a.y == d.y) { dest = a; break; }
+            }
             if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = W(pi, pj); break; }
             int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
             if (pi <= ci) max_i = ci; else min_i = ci + 1;
@@ -139,15 +149,26 @@ __global__ void __launch_bounds__(256) k_geo_accum(GeoK g)
     if (credit) {
         size_t cell = (size_t)jj * g.nx + ii;
         g.touched[cell] = 1;
-        atomicMin(&s_bb[0], jj); atomicMin(&s_bb[1], ii); atomicMax(&s_bb[2], jj); atomicMax(&s_bb[3], ii);
+        {   // one shared-memory update per group of lanes that arrive here together
+            const unsigned act = __activemask();
+            const int jmn = __reduce_min_sync(act, jj), imn = __reduce_min_sync(act, ii);
+            const int jmx = __reduce_max_sync(act, jj), imx = __reduce_max_sync(act, ii);
+            if ((threadIdx.x & 31) == (unsigned)(__ffs(act) - 1)) {
+                atomicMin(&s_bb[0], jmn); atomicMin(&s_bb[1], imn); atomicMax(&s_bb[2], jmx); atomicMax(&s_bb[3], imx);
+            }
+        }
         size_t tn2 = (size_t)g.tnx * g.tny, toff = (size_t)(pj - g.smy) * g.tnx + (pi - g.smx);
         if (g.itype == WPSGPU_CATEGORICAL) {
             float v = g.tile[toff];
-            if (v != g.msg_val) {
-                int cat = (int)v;
-                if (cat >= g.start_k && cat <= g.end_k) atomicAdd(g.acc_cnt + (size_t)(cat - g.start_k) * g.npts + cell, 1);
-                else atomicAdd(g.invalid, 1ull);
-            }
+            int cat = (int)v;
+            const bool has = v != g.msg_val, ok = has && cat >= g.start_k && cat <= g.end_k;
+            if (has && !ok) atomicAdd(g.invalid, 1ull);
+            // neighbouring pixels mostly fall into the same cell with the same category: one atomic per distinct
+            // (category, cell) among the lanes that arrive here together, carrying their count
+            const unsigned lane = threadIdx.x & 31;
+            unsigned long long key = ok ? ((unsigned long long)(cat - g.start_k) * g.npts + cell) : (~0ull - lane);
+            unsigned peers = __match_any_sync(__activemask(), key);
+            if (ok && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(g.acc_cnt + key, __popc(peers));
         } else {
             for (int k = g.smz; k <= g.sMz; ++k) {
                 float v = g.tile[(size_t)(k - g.smz) * tn2 + toff];
@@ -171,81 +192,104 @@ __global__ void __launch_bounds__(256) k_geo_accum(GeoK g)
 
 // Fold the tile's accumulation into field / data_count with the reference's first-touch semantics
 // (proc_point_module.F:326-346) and, for ilevel>1 categorical data, the half-area rule (:165-202).
-__global__ void k_geo_merge(GeoK g, int ilevel, float src_area, float dom_area)
+// The same launch then lists the points of this tile that still have no value (is_point_in_tile, :911-929, and the
+// level / processed tests of calc_field, :1410-1420) for the interpolation-chain kernel: a cell's level bit is only
+// changed by its own thread here, so the decision uses the thread's own view of it.
+__global__ void __launch_bounds__(256)
+k_geo_merge_select(GeoK g, int ilevel, float src_area, float dom_area, int do_merge, const float2* __restrict__ src_xy,
+                   int* __restrict__ cand, unsigned long long* __restrict__ cand_cnt)
 {
     const bool all_cells = ilevel > 1 && g.itype == WPSGPU_CATEGORICAL;   // the half-area rule looks at every cell
-    if (!all_cells) {
+    bool blk_merge = do_merge != 0;
+    if (blk_merge && !all_cells) {
         size_t c0 = (size_t)blockIdx.x * blockDim.x, c1 = min(c0 + blockDim.x - 1, g.npts - 1);
         int r0 = (int)(c0 / g.nx), r1 = (int)(c1 / g.nx);
-        if (r1 < g.tbbox[0] || r0 > g.tbbox[2]) return;   // no cell of this block was reached by the tile
+        if (r1 < g.tbbox[0] || r0 > g.tbbox[2]) blk_merge = false;   // no cell of this block was reached by the tile
     }
+    bool blk_select;
+    {   // is_point_in_tile is monotone in each coordinate: if it fails for the block's extreme coordinates it fails for all
+        float4 b = g.blk_xy[blockIdx.x];   // {xmin, xmax, ymin, ymax}
+        blk_select = g.smx + g.bdr <= f_floor(b.y + 0.5f) && f_ceiling(b.x - 0.5f) <= g.sMx - g.bdr &&
+                     g.smy + g.bdr <= f_floor(b.w + 0.5f) && f_ceiling(b.z - 0.5f) <= g.sMy - g.bdr;
+    }
+    if (!blk_merge && !blk_select) return;
     size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= g.npts) return;
     int ii = (int)(cell % g.nx), jj = (int)(cell / g.nx);
-    if (!all_cells && (ii < g.tbbox[1] || ii > g.tbbox[3])) return;
-    if (g.touched[cell]) {
-        g.touched[cell] = 0;
-        bool isnew = bit_test(g.level, g.nxw, ii, jj);
-        bool any = false;
-        // loads of a chunk of levels are issued together before the stores (the arrays may alias as far as the
-        // compiler knows, so a load-store-load sequence would pay one memory latency per level)
-        constexpr int CH = 8;
-        if (g.itype == WPSGPU_CATEGORICAL) {
-            for (int k0 = 0; k0 < g.nk; k0 += CH) {
-                int c[CH]; float f[CH];
+    bool levbit = bit_test(g.level, g.nxw, ii, jj);
+    if (blk_merge && (all_cells || (ii >= g.tbbox[1] && ii <= g.tbbox[3]))) {
+        if (g.touched[cell]) {
+            g.touched[cell] = 0;
+            bool isnew = levbit;
+            bool any = false;
+            // loads of a chunk of levels are issued together before the stores (the arrays may alias as far as the
+            // compiler knows, so a load-store-load sequence would pay one memory latency per level)
+            constexpr int CH = 8;
+            if (g.itype == WPSGPU_CATEGORICAL) {
+                for (int k0 = 0; k0 < g.nk; k0 += CH) {
+                    int c[CH]; float f[CH];
 #pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    size_t o = (size_t)(k0 + u) * g.npts + cell;
-                    bool in = k0 + u < g.nk;
-                    c[u] = in ? g.acc_cnt[o] : 0;
-                    f[u] = (in && isnew) ? g.field[o] : 0.0f;
+                    for (int u = 0; u < CH; ++u) {
+                        size_t o = (size_t)(k0 + u) * g.npts + cell;
+                        bool in = k0 + u < g.nk;
+                        c[u] = in ? g.acc_cnt[o] : 0;
+                        f[u] = (in && isnew) ? g.field[o] : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) {
+                        if (k0 + u >= g.nk) break;
+                        size_t o = (size_t)(k0 + u) * g.npts + cell;
+                        if (c[u] != 0) g.acc_cnt[o] = 0;
+                        g.field[o] = f[u] + (float)c[u];
+                        any |= c[u] > 0;
+                    }
                 }
+            } else {
+                int k0 = g.smz - g.start_k, k1 = g.sMz - g.start_k;
+                for (int kk = k0; kk <= k1; kk += CH) {
+                    int c[CH]; double sm[CH]; float f[CH], n[CH];
 #pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    if (k0 + u >= g.nk) break;
-                    size_t o = (size_t)(k0 + u) * g.npts + cell;
-                    if (c[u] != 0) g.acc_cnt[o] = 0;
-                    g.field[o] = f[u] + (float)c[u];
-                    any |= c[u] > 0;
+                    for (int u = 0; u < CH; ++u) {
+                        size_t o = (size_t)(kk + u) * g.npts + cell;
+                        bool in = kk + u <= k1;
+                        c[u] = in ? g.acc_cnt[o] : 0;
+                        sm[u] = in ? g.acc_sum[o] : 0.0;
+                        f[u] = (in && isnew) ? g.field[o] : 0.0f;
+                        n[u] = in ? g.count[o] : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) {
+                        if (kk + u > k1) break;
+                        size_t o = (size_t)(kk + u) * g.npts + cell;
+                        g.acc_cnt[o] = 0; g.acc_sum[o] = 0.0;
+                        g.field[o] = f[u] + (float)sm[u];
+                        g.count[o] = n[u] + (float)c[u];
+                        any |= c[u] > 0;
+                    }
                 }
             }
-        } else {
-            int k0 = g.smz - g.start_k, k1 = g.sMz - g.start_k;
-            for (int kk = k0; kk <= k1; kk += CH) {
-                int c[CH]; double sm[CH]; float f[CH], n[CH];
-#pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    size_t o = (size_t)(kk + u) * g.npts + cell;
-                    bool in = kk + u <= k1;
-                    c[u] = in ? g.acc_cnt[o] : 0;
-                    sm[u] = in ? g.acc_sum[o] : 0.0;
-                    f[u] = (in && isnew) ? g.field[o] : 0.0f;
-                    n[u] = in ? g.count[o] : 0.0f;
-                }
-#pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    if (kk + u > k1) break;
-                    size_t o = (size_t)(kk + u) * g.npts + cell;
-                    g.acc_cnt[o] = 0; g.acc_sum[o] = 0.0;
-                    g.field[o] = f[u] + (float)sm[u];
-                    g.count[o] = n[u] + (float)c[u];
-                    any |= c[u] > 0;
+            if (any) { bit_set_atomic(g.level, g.nxw, ii, jj); levbit = true; }
+        }
+        if (all_cells) {
+            if (levbit && !bit_test(g.processed, g.nxw, ii, jj)) {
+                float rarea = 0.0f;
+                for (int k = 0; k < g.nk; ++k) rarea = rarea + g.field[(size_t)k * g.npts + cell];
+                rarea = rarea * src_area;
+                if (dom_area > 2.0f * rarea) {
+                    for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + cell] = 0.0f;
+                    atomicAnd(g.level + (size_t)jj * g.nxw + (ii >> 5), (int)~(1u << (ii & 31)));
+                    levbit = false;
                 }
             }
         }
-        if (any) bit_set_atomic(g.level, g.nxw, ii, jj);
     }
-    if (ilevel > 1 && g.itype == WPSGPU_CATEGORICAL) {
-        if (bit_test(g.level, g.nxw, ii, jj) && !bit_test(g.processed, g.nxw, ii, jj)) {
-            float rarea = 0.0f;
-            for (int k = 0; k < g.nk; ++k) rarea = rarea + g.field[(size_t)k * g.npts + cell];
-            rarea = rarea * src_area;
-            if (dom_area > 2.0f * rarea) {
-                for (int k = 0; k < g.nk; ++k) g.field[(size_t)k * g.npts + cell] = 0.0f;
-                atomicAnd(g.level + (size_t)jj * g.nxw + (ii >> 5), (int)~(1u << (ii & 31)));
-            }
-        }
-    }
+    if (!blk_select) return;
+    float2 xy = src_xy[cell];
+    if (!(g.smx + g.bdr <= f_floor(xy.x + 0.5f) && f_ceiling(xy.x - 0.5f) <= g.sMx - g.bdr &&
+          g.smy + g.bdr <= f_floor(xy.y + 0.5f) && f_ceiling(xy.y - 0.5f) <= g.sMy - g.bdr)) return;
+    if (levbit) return;
+    if (bit_test(g.processed, g.nxw, ii, jj)) { bit_set_atomic(g.level, g.nxw, ii, jj); return; }
+    cand[atomicAdd(cand_cnt, 1ull)] = (int)cell;
 }
 
 // source-grid coordinates of every destination point (get_point / is_point_in_tile, :811-823,911-921)
@@ -346,28 +390,8 @@ __device__ __forceinline__ bool geo_point(const GeoK& g, const float2* __restric
     return false;
 }
 
-// The per-point pass of a tile in two steps.  k_geo_select (few registers, one thread per domain point, whole blocks
-// dropped by their coordinate range) lists the points that lie in the tile and have no value yet; k_geo_points then
-// runs the interpolation chain (a 220-register kernel) over that usually short list.
-__global__ void __launch_bounds__(256)
-k_geo_select(GeoK g, const float2* __restrict__ src_xy, int* __restrict__ cand, unsigned long long* __restrict__ cand_cnt)
-{
-    {   // is_point_in_tile is monotone in each coordinate: if it fails for the block's extreme coordinates it fails for all
-        float4 b = g.blk_xy[blockIdx.x];   // {xmin, xmax, ymin, ymax}
-        if (!(g.smx + g.bdr <= f_floor(b.y + 0.5f) && f_ceiling(b.x - 0.5f) <= g.sMx - g.bdr &&
-              g.smy + g.bdr <= f_floor(b.w + 0.5f) && f_ceiling(b.z - 0.5f) <= g.sMy - g.bdr)) return;
-    }
-    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= g.npts) return;
-    int ii = (int)(p % g.nx), jj = (int)(p / g.nx);
-    float2 xy = src_xy[p];
-    if (!(g.smx + g.bdr <= f_floor(xy.x + 0.5f) && f_ceiling(xy.x - 0.5f) <= g.sMx - g.bdr &&
-          g.smy + g.bdr <= f_floor(xy.y + 0.5f) && f_ceiling(xy.y - 0.5f) <= g.sMy - g.bdr)) return;
-    if (bit_test(g.level, g.nxw, ii, jj)) return;
-    if (bit_test(g.processed, g.nxw, ii, jj)) { bit_set_atomic(g.level, g.nxw, ii, jj); return; }
-    cand[atomicAdd(cand_cnt, 1ull)] = (int)p;
-}
-
+// The per-point pass of a tile: k_geo_merge_select has listed the points that lie in the tile and have no value yet;
+// k_geo_points runs the interpolation chain (a 220-register kernel) over that usually short list.
 __global__ void __launch_bounds__(256)
 k_geo_points(GeoK g, const float2* __restrict__ src_xy, const int* __restrict__ cand, const unsigned long long* __restrict__ cand_cnt,
              Deferred* def, unsigned long long* def_cnt)
@@ -478,7 +502,7 @@ static GeoK make_k(wpsgpu_ctx* h)
     g.sr_x = (float)s->l.sr_x; g.sr_y = (float)s->l.sr_y; g.msg_val = s->l.msg_val; g.msg_fill_val = s->l.msg_fill_val; g.mask_val = s->l.mask_val;
     g.field = s->d_field; g.count = s->d_count; g.landmask = s->d_landmask; g.processed = s->d_processed; g.level = s->d_level;
     g.acc_cnt = s->d_acc_cnt; g.acc_sum = s->d_acc_sum; g.touched = s->d_touched; g.invalid = s->d_invalid;
-    g.tbbox = s->d_tbbox; g.blk_xy = s->d_blk_xy;
+    g.tbbox = s->d_tbbox; g.blk_xy = s->d_blk_xy; g.counters = s->d_invalid + 1;
     memcpy(g.ops, s->l.ops, sizeof(g.ops)); memcpy(g.opts, s->l.opts, sizeof(g.opts));
     g.ops[WPSGPU_MAX_OPS - 1] = 0;
     return g;
@@ -617,9 +641,6 @@ static int geo_process_tile(wpsgpu_ctx* h, int smx, int sMx, int smy, int sMy, i
     if (s->l.itype == WPSGPU_CATEGORICAL || s->l.itype == WPSGPU_SP_CONTINUOUS) {
         WPS_TRY(geo_grow((void**)&s->d_wm, &s->wm_cap, (size_t)tnx * tny * sizeof(int2), h->stream));
         g.wm = s->d_wm;
-        // {jmin, imin} = 0x7f7f7f7f, {jmax, imax} = 0x80808080 (very negative)
-        WPS_CUDA(cudaMemsetAsync(s->d_tbbox, 0x7f, 2 * sizeof(int), h->stream));
-        WPS_CUDA(cudaMemsetAsync(s->d_tbbox + 2, 0x80, 2 * sizeof(int), h->stream));
         k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, h->stream>>>(g);
         int inx = tnx - 2 * bdr, iny = tny - 2 * bdr;
         if (inx > 0 && iny > 0) k_geo_accum<<<dim3((inx + 31) / 32, (iny + 7) / 8), b, 0, h->stream>>>(g);
@@ -627,15 +648,17 @@ static int geo_process_tile(wpsgpu_ctx* h, int smx, int sMx, int smy, int sMy, i
         const wpsgpu_proj &sp = s->l.src_proj, &dp = s->f.dom_proj;
         float sa = (sp.dx < 0.0f) ? (sp.latinc * 111000.0f) * (sp.latinc * 111000.0f) : sp.dx * sp.dx;
         float da = (dp.dx < 0.0f) ? (dp.latinc * 111000.0f) * (dp.latinc * 111000.0f) : dp.dx * dp.dx;
-        k_geo_merge<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->l.ilevel, sa, da);
+        k_geo_merge_select<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->l.ilevel, sa, da, 1, s->d_src_xy, s->d_cand, g.counters + 2);
         h->launches += 3;
         WPS_CUDA(cudaGetLastError());
+    } else {   // point-wise types: no accumulation, only the point pass
+        WPS_CUDA(cudaMemsetAsync(g.counters, 0, 3 * sizeof(unsigned long long), h->stream));
+        k_geo_merge_select<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->l.ilevel, 0.0f, 0.0f, 0, s->d_src_xy, s->d_cand, g.counters + 2);
+        h->launches++;
     }
-    unsigned long long* cnt = s->d_invalid + 1;   // [0] deferred to the warp pass, [1] to the literal pass, [2] candidates
-    WPS_CUDA(cudaMemsetAsync(cnt, 0, 3 * sizeof(unsigned long long), h->stream));
-    k_geo_select<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->d_src_xy, s->d_cand, cnt + 2);
+    unsigned long long* cnt = g.counters;
     k_geo_points<<<h->sm_count * 2, 256, 0, h->stream>>>(g, s->d_src_xy, s->d_cand, cnt + 2, s->d_def, cnt);
-    h->launches += 2;
+    h->launches++;
     if (s->has_search) {
         k_geo_points_warp<<<h->sm_count * 8, 256, 0, h->stream>>>(g, s->d_src_xy, s->d_def, cnt, s->d_def2, cnt + 1);
         int R = std::min(std::max(s->max_depth, 1), std::max(std::max(tnx, tny), 1));
