@@ -447,6 +447,10 @@ def run_b200(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 8)
             line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}
+            # also the single-thread figure, on the first slabs of the same sample
+            pps1, dt1, _, _, desc1 = cpu_arm(config, 2, 1, 1)
+            line["cpu_baseline"]["single_thread"] = {"value": pps1, "unit": "points/s", "cores": 1, "seconds": dt1,
+                                                     "sample": "2 TT slabs (sixteen_pt chain) on the full grid, one process"}
         print(json.dumps(line))
     h.close()
     if world > 1:
