@@ -494,3 +494,48 @@ def test_raw_record_ingest(orc, handle, big_endian):
     r_ref, np_ref = orc.interp_met_field(reg_o, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), rec, 1, 1, 0)
     assert (nn == np_ref).all()
     assert_bitexact(rr, r_ref, "regional raw record")
+
+
+@pytest.mark.parametrize("nx,ny", [(1, 1), (3, 2), (33, 1), (1, 40), (32, 8), (65, 9)])
+def test_tiny_and_ragged_domains(orc, handle, nx, ny):
+    """Destination grids smaller than one 32x8 tile, single rows / columns, exact tile multiples and one-past: every
+    chain family, both device paths (run_case checks the first-method kernels and the generic kernel)."""
+    xlat, xlon = make_domain(orc, handle, nx=nx, ny=ny, dx=45000.0)
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    ls = halo(landsea(360, 181))
+    slabs = [halo(synth_field(360, 181, 300 + s, missing=np.float32(-1e30), frac_missing=0.1, zeros=0.01)) for s in range(3)]
+    for chain in ("sixteen_pt+four_pt+average_4pt", "four_pt+average_4pt", "nearest_neighbor",
+                  "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search"):
+        run_case(orc, handle, xlat, xlon, slabs, src, chain, missing=np.float32(-1e30), fill=1.0,
+                 mask_val=(0.0, 1e20, 1e20), masks=(ls, None, None))
+
+
+def test_empty_flush_and_error_paths(handle):
+    """Nothing queued -> flush is a no-op; bad descriptors are refused with a message and queue nothing."""
+    from wps_b200 import capi
+    handle.metgrid_flush()
+    xlat = np.zeros((4, 5), np.float32) + 35.0
+    xlon = np.zeros((4, 5), np.float32) - 100.0
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_domain(1, 5, 1, 4)
+    src = capi.push_source_projection(capi.PROJ_LATLON, dlat=-1.0, dlon=1.0, known_x=1.0, known_y=1.0, known_lat=90.0,
+                                      known_lon=0.0, earth_radius=6371229.0)
+    fo = capi.field_opts("four_pt", 1e20, 0.0, -2.0)
+    slab = np.zeros((181, 366), np.float32)
+    r = np.zeros((4, 5), np.float32)
+    npw = np.zeros((4, 1), np.int32)
+    with pytest.raises(capi.WpsGpuError, match="grid 3 not set|destination grid"):
+        handle.metgrid_enqueue_slab(src, fo, slab, -2, 1, 3, 3, capi.M, r, npw)
+    with pytest.raises(capi.WpsGpuError, match="landmask"):
+        handle.metgrid_enqueue_slab(src, fo, slab, -2, 1, 3, 0, capi.M, r, npw, use_landmask=True)
+    with pytest.raises(capi.WpsGpuError, match="raw record"):
+        _bad_raw(handle, src, fo, slab, r, npw)
+    handle.metgrid_flush()
+    assert (r == 0).all()
+
+
+def _bad_raw(handle, src, fo, slab, r, npw):
+    from wps_b200 import capi
+    s = capi.Handle.slab_desc(slab, -2, 1, 3, 0, capi.M, r, npw)
+    s.raw_nx = 361          # 366 - 361 = 5 halo columns in total: not an even split
+    capi.check(capi.lib().wpsgpu_metgrid_enqueue_slab(handle._h, capi.C.byref(src), capi.C.byref(fo), capi.C.byref(s)))
