@@ -539,3 +539,64 @@ def _bad_raw(handle, src, fo, slab, r, npw):
     s = capi.Handle.slab_desc(slab, -2, 1, 3, 0, capi.M, r, npw)
     s.raw_nx = 361          # 366 - 361 = 5 halo columns in total: not an even split
     capi.check(capi.lib().wpsgpu_metgrid_enqueue_slab(handle._h, capi.C.byref(src), capi.C.byref(fo), capi.C.byref(s)))
+
+
+def test_config1_whole_step_every_slab(orc, handle):
+    """BASELINE configs[0] (the CPU-runnable case): one whole FILE time of the GFS-shaped table -- every field, level,
+    stagger, mask and landmask combination of the default METGRID.TBL chains (163 slabs at 32 levels) -- in ONE flush
+    through the batched entry point, each slab bit-exact against the oracle."""
+    from wps_b200 import capi, synth
+    cfg = synth.CONFIGS["config1"]
+    sx, sy, dlat, dlon = cfg["src"]
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = cfg["dom"]
+    orc.set_transc_mode(1)
+    odom, gdom = conus_like(nx, ny, dx, truelat1=tl1, truelat2=tl2, stand_lon=slon, ref_lat=rlat, ref_lon=rlon)
+    osrc, gsrc = latlon_source(sx, sy, dlat, dlon, 90.0, 0.0)
+    grids = {capi.M: orc.get_lat_lon_fields(odom, 1, 1, nx, ny, orc.M), capi.U: orc.get_lat_lon_fields(odom, 1, 1, nx + 1, ny, orc.U),
+             capi.V: orc.get_lat_lon_fields(odom, 1, 1, nx, ny + 1, orc.V)}
+    gid = {capi.M: 0, capi.U: 1, capi.V: 2}
+    for st, (la, lo) in grids.items():
+        handle.metgrid_set_grid(gid[st], la, lo, 1, 1)
+    lam = np.deg2rad(grids[capi.M][1]) % (2 * np.pi)
+    landmask = (synth.landsea_fn(np, lam, np.deg2rad(grids[capi.M][0])) > synth.LAND_THRESHOLD).astype(np.float32)
+    handle.metgrid_set_landmask(0, landmask)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    ls = synth.landsea_np(sx, sy)
+    lsh = synth.add_halo(ls)
+    table = synth.gfs_slab_table(cfg["nlev"])
+    work, seed = [], 0
+    for e in table:
+        gy, gx = grids[e["stagger"]][0].shape
+        masks, mv = (None, None, None), (1e20, 1e20, 1e20)
+        if e["mask"] is not None:
+            if e["mask"][0] == "mask":
+                masks, mv = (lsh, None, None), (e["mask"][1], 1e20, 1e20)
+            else:
+                masks, mv = (None, lsh, lsh), (1e20, e["mask"][1], e["mask"][2])
+        fo_g = capi.field_opts(e["chain"], np.float32(e["missing"]), np.float32(e["fill"]), e["masked"], mv)
+        fo_o = orc.field_opts(e["chain"], np.float32(e["missing"]), np.float32(e["fill"]), e["masked"], mv)
+        n = e["nlev"]
+        slabs = np.stack([synth.add_halo(synth.slab_np(sx, sy, seed + l, e["kind"], ls, np.float32(e["missing"]))) for l in range(n)])
+        r = np.zeros((n, gy, gx), np.float32)
+        npw = np.zeros((n, gy, capi.nwords(gx)), np.int32)
+        descs = (capi.Slab * n)()
+        use_lm = e["stagger"] == capi.M
+        for l in range(n):
+            capi.Handle.slab_desc(slabs[l], -2, 1, 3, gid[e["stagger"]], e["stagger"], r[l], npw[l], masks=masks,
+                                  use_landmask=use_lm, out=descs[l])
+        handle.metgrid_enqueue_slabs(gsrc, fo_g, descs)
+        work.append((e, fo_o, slabs, masks, r, npw, descs, use_lm))
+        seed += n
+    handle.metgrid_flush()
+    total = 0
+    for e, fo_o, slabs, masks, r, npw, _, use_lm in work:
+        xlat, xlon = grids[e["stagger"]]
+        gy, gx = xlat.shape
+        for l in range(slabs.shape[0]):
+            r_ref, np_ref = orc.interp_met_field(osrc, fo_o, e["stagger"], xlat, xlon, 1, 1, (1, nx, 1, ny), slabs[l], -2, 1, 3,
+                                                 mask=masks[0], land_mask=masks[1], water_mask=masks[2],
+                                                 landmask=landmask if use_lm else None)
+            assert (npw[l] == np_ref).all(), "%s level %d: new_pts" % (e["field"], l)
+            assert_bitexact(r[l], r_ref, "%s level %d" % (e["field"], l))
+            total += 1
+    assert total == synth.n_slabs(table)
