@@ -1,0 +1,106 @@
+"""GPU parity in DEVICE-pointer mode (wpsgpu_set_pointer_mode / Handle(dev, PTR_DEVICE)): the mode bench.py times.
+Inputs and outputs are torch tensors resident in HBM; results must equal the oracle (and hence the host-pointer mode)."""
+import numpy as np
+import pytest
+
+from tests.util import assert_bitexact, bool_to_bits, conus_like, halo, landsea, latlon_source, synth_field
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def dhandle():
+    from wps_b200 import capi
+    h = capi.Handle(0, capi.PTR_DEVICE)
+    yield h
+    h.close()
+
+
+def test_metgrid_137_levels_device_resident(orc, dhandle):
+    """Config-5 shape in small: 137 levels of one field (three job groups of at most 64 slabs in device mode) plus a
+    masked soil chain with deferred searches, all device-resident, one flush; oracle on a spread of levels."""
+    import torch
+    from wps_b200 import capi
+    dev = torch.device("cuda", 0)
+    nx, ny, nlev = 150, 110, 137
+    orc.set_transc_mode(1)
+    odom, gdom = conus_like(nx, ny, 12000.0, truelat1=30.0, truelat2=60.0, stand_lon=-98.0, ref_lat=34.83, ref_lon=-81.03)
+    xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, nx, ny, orc.M)
+    osrc, gsrc = latlon_source(720, 361, -0.5, 0.5, 90.0, 0.0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_xlat, d_xlon = t(xlat), t(xlon)
+    rng = np.random.default_rng(9)
+    landmask = (rng.random((ny, nx)) < 0.6).astype(np.float32)
+    d_lm = t(landmask)
+    dhandle.metgrid_set_grid(0, d_xlat, d_xlon, 1, 1)
+    dhandle.metgrid_set_landmask(0, d_lm)
+    dhandle.metgrid_set_domain(1, nx, 1, ny)
+    slabs = np.stack([halo(synth_field(720, 361, 2000 + s, kind="wind" if s % 3 else "smooth", zeros=0.002)) for s in range(nlev)])
+    d_slabs = t(slabs)
+    d_r = torch.zeros((nlev, ny, nx), dtype=torch.float32, device=dev)
+    d_np = torch.zeros((nlev, ny, capi.nwords(nx)), dtype=torch.int32, device=dev)
+    chain = "sixteen_pt+four_pt+average_4pt"
+    fo_g, fo_o = capi.field_opts(chain, 1e20, 0.0, -2.0), orc.field_opts(chain, 1e20, 0.0, -2.0)
+    descs = (capi.Slab * nlev)()
+    for l in range(nlev):
+        capi.Handle.slab_desc(d_slabs[l], -2, 1, 3, 0, capi.M, d_r[l], d_np[l], out=descs[l])
+    dhandle.metgrid_enqueue_slabs(gsrc, fo_g, descs)
+    # masked soil field: missing over water, interp_mask = LANDSEA(0), masked = water, search at the end of the chain
+    ls = landsea(720, 361)
+    soil = synth_field(720, 361, 3000)
+    soil[ls == 0] = np.float32(-1e30)
+    d_soil, d_mask = t(halo(soil)), t(halo(ls))
+    d_rs = torch.zeros((ny, nx), dtype=torch.float32, device=dev)
+    d_ns = torch.zeros((ny, capi.nwords(nx)), dtype=torch.int32, device=dev)
+    schain = "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search"
+    fs_g = capi.field_opts(schain, np.float32(-1e30), 285.0, 0.0, (0.0, 1e20, 1e20))
+    fs_o = orc.field_opts(schain, np.float32(-1e30), 285.0, 0.0, (0.0, 1e20, 1e20))
+    dhandle.metgrid_enqueue_slab(gsrc, fs_g, d_soil, -2, 1, 3, 0, capi.M, d_rs, d_ns, masks=(d_mask, None, None), use_landmask=True)
+    dhandle.metgrid_flush()
+    dhandle.synchronize()
+    r, npw = d_r.cpu().numpy(), d_np.cpu().numpy()
+    for l in (0, 1, 63, 64, 65, 127, 128, 136):
+        r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), slabs[l], -2, 1, 3)
+        assert (npw[l] == np_ref).all(), "level %d" % l
+        assert_bitexact(r[l], r_ref, "level %d" % l)
+    r_ref, np_ref = orc.interp_met_field(osrc, fs_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), halo(soil), -2, 1, 3, mask=halo(ls),
+                                         landmask=landmask)
+    assert (d_ns.cpu().numpy() == np_ref).all()
+    assert_bitexact(d_rs.cpu().numpy(), r_ref, "masked soil chain, device mode")
+
+
+def test_vertical_fill_and_raw_records_device_resident(orc, dhandle):
+    """fill_missing_levels and the raw-record ingest with every array in HBM (pointer tables stay host arrays)."""
+    import torch
+    from wps_b200 import capi
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(12)
+    nx, ny, nlev = 90, 37, 10
+    levels = [1000 * (k + 1) for k in range(nlev)]
+    r = rng.uniform(0, 1, (nlev, ny, nx)).astype(np.float32)
+    v = np.stack([bool_to_bits(rng.random((ny, nx)) < 0.55) for _ in range(nlev)])
+    r_ref, v_ref = orc.fill_missing_levels(levels, r, v)
+    d_r, d_v = torch.from_numpy(r).to(dev), torch.from_numpy(v).to(dev)
+    dhandle.fill_missing_levels(levels, [d_r[k] for k in range(nlev)], [d_v[k] for k in range(nlev)])
+    dhandle.synchronize()
+    assert (d_v.cpu().numpy() == v_ref).all()
+    assert_bitexact(d_r.cpu().numpy(), r_ref, "fill_missing_levels, device mode")
+    # raw big-endian record resident on the device
+    gx, gy = 61, 47
+    orc.set_transc_mode(1)
+    odom, _ = conus_like(gx, gy, 30000.0, truelat1=30.0, truelat2=60.0, stand_lon=-98.0, ref_lat=34.83, ref_lon=-81.03)
+    xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, gx, gy, orc.M)
+    osrc, gsrc = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    rec = synth_field(360, 181, 5)
+    d_raw = torch.from_numpy(rec.astype(">f4").view(np.float32).copy()).to(dev)
+    d_out = torch.zeros((gy, gx), dtype=torch.float32, device=dev)
+    d_bits = torch.zeros((gy, capi.nwords(gx)), dtype=torch.int32, device=dev)
+    dhandle.metgrid_set_grid(0, torch.from_numpy(xlat).to(dev), torch.from_numpy(xlon).to(dev), 1, 1)
+    dhandle.metgrid_set_domain(1, gx, 1, gy)
+    fo_g, fo_o = capi.field_opts("sixteen_pt+four_pt+average_4pt", 1e20, 0.0, -2.0), orc.field_opts("sixteen_pt+four_pt+average_4pt", 1e20, 0.0, -2.0)
+    dhandle.metgrid_enqueue_slab(gsrc, fo_g, d_raw, -2, 1, 3, 0, capi.M, d_out, d_bits, raw_big_endian=True)
+    dhandle.metgrid_flush()
+    dhandle.synchronize()
+    r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, gx, 1, gy), halo(rec), -2, 1, 3)
+    assert (d_bits.cpu().numpy() == np_ref).all()
+    assert_bitexact(d_out.cpu().numpy(), r_ref, "raw record, device mode")
