@@ -126,6 +126,14 @@ module wpsgpu_mod
          import :: c_int, c_ptr
          type(c_ptr), value :: handle
       end function
+      integer(c_int) function wpsgpu_metgrid_flush_async(handle) bind(C, name='wpsgpu_metgrid_flush_async')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+      end function
+      integer(c_int) function wpsgpu_synchronize(handle) bind(C, name='wpsgpu_synchronize')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+      end function
       integer(c_int) function wpsgpu_rotate_winds(handle, idir, proj, u, u_mask, v, v_mask, us1, us2, ue1, ue2, &
                         vs1, vs2, ve1, ve2, xlon_u, xlon_v, nlev) bind(C, name='wpsgpu_rotate_winds')
          import :: c_int, c_ptr, c_float, c_int32_t, wpsgpu_proj

@@ -156,6 +156,11 @@ int wpsgpu_metgrid_enqueue_slabs(wpsgpu_handle_t h, const wpsgpu_proj *src_proj,
                                  const wpsgpu_slab *slabs, int32_t n);
 /* Execute everything queued as ONE batched launch over field x level (x time) and fill r_arr / new_pts. */
 int wpsgpu_metgrid_flush(wpsgpu_handle_t h);
+/* Same without waiting for the device: returns once everything is queued.  The caller's input and output arrays must
+ * stay allocated and untouched until wpsgpu_synchronize(h) returns (then r_arr / new_pts are complete); with pinned
+ * host buffers the host is free to read and decode the next file meanwhile.  Further calls on the handle are ordered
+ * behind the pending copies automatically. */
+int wpsgpu_metgrid_flush_async(wpsgpu_handle_t h);
 /* Device time (CUDA events on the handle's stream) of the dominant kernel of the last flush and the number of
  * (slab x destination point) outputs it produced -- for roofline reporting only. */
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);

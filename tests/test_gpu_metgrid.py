@@ -524,8 +524,8 @@ def test_empty_flush_and_error_paths(handle):
     slab = np.zeros((181, 366), np.float32)
     r = np.zeros((4, 5), np.float32)
     npw = np.zeros((4, 1), np.int32)
-    with pytest.raises(capi.WpsGpuError, match="grid 3 not set|destination grid"):
-        handle.metgrid_enqueue_slab(src, fo, slab, -2, 1, 3, 3, capi.M, r, npw)
+    with pytest.raises(capi.WpsGpuError, match="destination grid 7 not set"):
+        handle.metgrid_enqueue_slab(src, fo, slab, -2, 1, 3, 7, capi.M, r, npw)
     with pytest.raises(capi.WpsGpuError, match="landmask"):
         handle.metgrid_enqueue_slab(src, fo, slab, -2, 1, 3, 0, capi.M, r, npw, use_landmask=True)
     with pytest.raises(capi.WpsGpuError, match="raw record"):
@@ -600,3 +600,35 @@ def test_config1_whole_step_every_slab(orc, handle):
             assert_bitexact(r[l], r_ref, "%s level %d" % (e["field"], l))
             total += 1
     assert total == synth.n_slabs(table)
+
+
+def test_flush_async_then_synchronize(orc, handle):
+    """wpsgpu_metgrid_flush_async: two flushes queued back to back without waiting (the second re-uses the arena behind
+    the first one's copies), another arena user in between, then one wpsgpu_synchronize -- results as from the blocking flush."""
+    from wps_b200 import capi
+    xlat, xlon = make_domain(orc, handle, nx=88, ny=61)
+    ny, nx = xlat.shape
+    osrc, gsrc = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    chain = "sixteen_pt+four_pt+average_4pt"
+    fo_o, fo_g = orc.field_opts(chain, 1e20, 0.0, -2.0), capi.field_opts(chain, 1e20, 0.0, -2.0)
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    slabs = [halo(synth_field(360, 181, 1200 + s)) for s in range(6)]
+    r = np.zeros((6, ny, nx), np.float32)
+    npw = np.zeros((6, ny, capi.nwords(nx)), np.int32)
+    for l in range(3):
+        handle.metgrid_enqueue_slab(gsrc, fo_g, slabs[l], -2, 1, 3, 0, capi.M, r[l], npw[l])
+    handle.metgrid_flush(wait=False)
+    for l in range(3, 6):
+        handle.metgrid_enqueue_slab(gsrc, fo_g, slabs[l], -2, 1, 3, 0, capi.M, r[l], npw[l])
+    handle.metgrid_flush(wait=False)
+    lvl = np.zeros((ny, nx), np.float32)
+    vm = np.zeros((ny, capi.nwords(nx)), np.int32)
+    handle.create_level(lvl, vm, fill_const=3.0)     # takes the arena while copies may be pending
+    handle.synchronize()
+    orc.set_transc_mode(1)
+    for l in range(6):
+        r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), slabs[l], -2, 1, 3)
+        assert (npw[l] == np_ref).all()
+        assert_bitexact(r[l], r_ref, "async flush, slab %d" % l)
+    assert (lvl == 3.0).all()

@@ -288,8 +288,9 @@ class Handle:
                            masks=(mask, None, None), use_landmask=use_landmask, process_bdy_width=process_bdy_width)
         check(lib().wpsgpu_metgrid_enqueue_gcell_slab(self._h, C.byref(proj), C.byref(dom_proj), C.byref(fo), C.byref(s)))
 
-    def metgrid_flush(self):
-        check(lib().wpsgpu_metgrid_flush(self._h))
+    def metgrid_flush(self, wait=True):
+        """wait=False: wpsgpu_metgrid_flush_async -- results are complete after synchronize()."""
+        check(lib().wpsgpu_metgrid_flush(self._h) if wait else lib().wpsgpu_metgrid_flush_async(self._h))
 
     def metgrid_last_kernel(self):
         ms = C.c_float()

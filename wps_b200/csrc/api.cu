@@ -57,6 +57,15 @@ int copy_out(wpsgpu_ctx* h, void* user_ptr, const void* dptr, size_t bytes)
     WPS_CUDA(cudaMemcpyAsync(user_ptr, dptr, bytes, cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
+int arena_begin(wpsgpu_ctx* h)
+{
+    if (h->async_pending) {
+        WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));
+        h->async_pending = false;
+    }
+    return 0;
+}
+
 int upload_gauss(wpsgpu_ctx* h, const wpsgpu_proj& p, const float** d_gauss)
 {
     *d_gauss = nullptr;
@@ -382,6 +391,7 @@ int wpsgpu_destroy(wpsgpu_handle_t h)
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
+    if (h->ev_out_done) cudaEventDestroy(h->ev_out_done);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -398,7 +408,12 @@ int wpsgpu_set_pointer_mode(wpsgpu_handle_t h, int mode)
 int wpsgpu_synchronize(wpsgpu_handle_t h)
 {
     WPS_CHECK(h != nullptr, -1, "NULL handle");
+    WPS_CUDA(cudaSetDevice(h->device));
+    if (h->s_in) WPS_CUDA(cudaStreamSynchronize(h->s_in));
     WPS_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->s_side) WPS_CUDA(cudaStreamSynchronize(h->s_side));
+    if (h->s_out) WPS_CUDA(cudaStreamSynchronize(h->s_out));
+    h->async_pending = false;
     return 0;
 }
 

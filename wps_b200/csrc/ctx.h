@@ -117,7 +117,8 @@ struct wpsgpu_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer pipeline
     cudaStream_t s_side = nullptr;                  // slow-bitmap passes overlapping the first-method kernels
     std::vector<cudaEvent_t> ev_pool;               // per-job fork events for s_side
-    cudaEvent_t ev_copy = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_done = nullptr, ev_out_done = nullptr;
+    bool async_pending = false;                     // wpsgpu_metgrid_flush_async: D2H copies may still read the arena
     bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };
 
@@ -128,4 +129,5 @@ int stage_in(wpsgpu_ctx* h, const void* p, size_t bytes, void** dptr);
 int alloc_out(wpsgpu_ctx* h, void* user_ptr, size_t bytes, void** dptr);
 int copy_out(wpsgpu_ctx* h, void* user_ptr, const void* dptr, size_t bytes);
 int upload_gauss(wpsgpu_ctx* h, const wpsgpu_proj& p, const float** d_gauss);
+int arena_begin(wpsgpu_ctx* h);   // call before re-using the arena: orders the handle's stream behind a pending async flush
 }  // namespace wps

@@ -1369,11 +1369,16 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     return 0;
 }
 
-int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
+static int flush_impl(wpsgpu_ctx* h, bool wait);
+int wpsgpu_metgrid_flush(wpsgpu_handle_t h) { return flush_impl(h, true); }
+int wpsgpu_metgrid_flush_async(wpsgpu_handle_t h) { return flush_impl(h, false); }
+
+static int flush_impl(wpsgpu_ctx* h, bool wait)
 {
     WPS_CHECK(h != nullptr, -1, "NULL handle");
     if (h->queue.empty()) return 0;
     WPS_CUDA(cudaSetDevice(h->device));
+    WPS_TRY(arena_begin(h));   // an earlier asynchronous flush may still be copying results out of the arena
     std::vector<QueuedSlab> queue;
     queue.swap(h->queue);
     h->queue.reserve(queue.size());
@@ -1499,6 +1504,7 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         WPS_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
         WPS_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
         WPS_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+        WPS_CUDA(cudaEventCreateWithFlags(&h->ev_out_done, cudaEventDisableTiming));
     }
     // everything previously enqueued on the handle's stream (set_grid copies, earlier calls) precedes the new copies
     WPS_CUDA(cudaEventRecord(h->ev_done, h->stream));
@@ -1528,8 +1534,13 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h)
         WPS_CUDA(cudaEventRecord(tr[2], h->stream));
         WPS_CUDA(cudaEventRecord(tr[3], h->s_out));
     }
-    WPS_CUDA(cudaStreamSynchronize(h->s_out));
-    WPS_CUDA(cudaStreamSynchronize(h->stream));
+    if (wait || trace) {
+        WPS_CUDA(cudaStreamSynchronize(h->s_out));
+        WPS_CUDA(cudaStreamSynchronize(h->stream));
+    } else {   // results are complete after wpsgpu_synchronize; later work on the handle is ordered behind the copies
+        WPS_CUDA(cudaEventRecord(h->ev_out_done, h->s_out));
+        h->async_pending = true;
+    }
     if (trace) {
         float a = 0.0f, b = 0.0f, c = 0.0f;
         cudaEventElapsedTime(&a, tr[0], tr[1]); cudaEventElapsedTime(&b, tr[0], tr[2]); cudaEventElapsedTime(&c, tr[0], tr[3]);

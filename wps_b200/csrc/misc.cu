@@ -362,6 +362,7 @@ static int begin_call(wpsgpu_ctx* h, size_t host_bytes)
 {
     WPS_CHECK(h != nullptr, -1, "NULL handle");
     WPS_CUDA(cudaSetDevice(h->device));
+    WPS_TRY(arena_begin(h));
     h->arena.reset();
     return h->arena.reserve((h->ptr_mode == WPSGPU_PTR_HOST ? host_bytes : 0) + (1 << 20), h->stream);
 }
