@@ -297,10 +297,29 @@ def geogrid_arm(h, torch, dev, config, steps):
             "alg_bytes_per_pixel": 1.0 + 4.0 * ncat * gx * gy / pixels, "mean_fraction_sum": frac_sum}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs next to that GPU, so that the
+    host<->device copies of the e2e leg do not cross the socket interconnect.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "cpus %d-%d (%d)" % (allowed[0], allowed[-1], len(allowed))
+    except Exception as e:   # affinity is an optimisation only
+        return "unchanged (%s)" % type(e).__name__
+    return "unchanged"
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from wps_b200 import capi, synth
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "unchanged (single process)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -440,7 +459,7 @@ def run_b200(args, rank, world, local_rank):
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3,
                         "raw_record_ms_per_step": None if e2e_raw_s is None else e2e_raw_s * 1e3},
-                "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": sampler.result()}
+                "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "cpu_affinity": affinity, "clocks": sampler.result()}
         if geo is not None:
             line["geogrid"] = geo
             line["vertical_fill"] = vfill
