@@ -291,10 +291,42 @@ def geogrid_arm(h, torch, dev, config, steps):
     ms = ev0.elapsed_time(ev1) / steps
     pixels = len(tiles) * tn * tn
     frac_sum = float(field.sum(dim=0).mean())
+    launches_per_field = (h.launch_count - l0) // steps
+    # HGT_M on the same patch: 30-arc-second topography, 2-byte signed big-endian tiles with tile_bdr=3.  At 3 km the
+    # average_gcell condition of calc_field (:1306-1317) fails, so every point takes four_pt+average_4pt (get_point).
+    bdr = 3
+    ttiles = []
+    for tx, ty, _ in tiles:
+        j = torch.arange(ty - bdr, ty + tn + bdr, device=dev, dtype=torch.float32)[:, None]
+        i = torch.arange(tx - bdr, tx + tn + bdr, device=dev, dtype=torch.float32)[None, :]
+        hgt = (1500.0 + 1200.0 * torch.sin(i / 370.0) * torch.cos(j / 530.0)).round().to(torch.int16)
+        be = torch.stack([(hgt >> 8).to(torch.uint8), (hgt & 255).to(torch.uint8)], dim=-1).contiguous()   # big-endian bytes
+        ttiles.append((tx - bdr, ty - bdr, be))
+    hfield = torch.zeros((1, gy, gx), dtype=torch.float32, device=dev)
+
+    def one_topo():
+        h.geogrid_field_begin(dom, capi.M, xlat, xlon, -2, -2, 1, hfield)
+        h.geogrid_level_begin(src, 1, capi.CONTINUOUS, "four_pt+average_4pt", msg_val=-32768.0)
+        for tx, ty, be in ttiles:
+            h.geogrid_add_tile_raw(be, (1, tn + 2 * bdr, tn + 2 * bdr), 2, 1, 0, 1, tx, ty, 1, bdr)
+        h.geogrid_level_end()
+        return h.geogrid_field_finish()
+
+    one_topo()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(steps):
+        one_topo()
+    ev1.record(stream)
+    h.synchronize()
+    topo_ms = ev0.elapsed_time(ev1) / steps
+    topo_mean = float(hfield.mean())
     return {"metric": "geogrid source pixels/s (categorical accumulation, config-3 land use)", "value": pixels / (ms / 1e3),
             "unit": "pixels/s", "ms_per_field": ms, "tiles": len(tiles), "tile": "1200x1200x1B", "pixels_per_field": pixels,
-            "dest": "%dx%dx%d categories" % (gx, gy, ncat), "gpu_launches_per_field": (h.launch_count - l0) // steps,
-            "alg_bytes_per_pixel": 1.0 + 4.0 * ncat * gx * gy / pixels, "mean_fraction_sum": frac_sum}
+            "dest": "%dx%dx%d categories" % (gx, gy, ncat), "gpu_launches_per_field": launches_per_field,
+            "alg_bytes_per_pixel": 1.0 + 4.0 * ncat * gx * gy / pixels, "mean_fraction_sum": frac_sum,
+            "topo_four_pt": {"ms_per_field": topo_ms, "points_per_s": gx * gy / (topo_ms / 1e3), "tile": "1206x1206x2B signed, tile_bdr 3",
+                             "pixels_per_s": len(ttiles) * (tn + 2 * bdr) ** 2 / (topo_ms / 1e3), "mean_height": topo_mean}}
 
 
 def bind_to_gpu_numa_node(local_rank):
