@@ -20,6 +20,23 @@ def test_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_host_library_exports_and_fails_without_device(tmp_path):
+    """libwpshost.so (C++ host side, include/wpshost.h) loads, exports its interface and reports the missing device."""
+    import torch
+    from wps_b200 import capi, hostlib
+    lib = hostlib.lib()
+    hdr = open(os.path.join(ROOT, "include", "wpshost.h")).read()
+    names = sorted(set(re.findall(r"\b(wpshost_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 10
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    if not torch.cuda.is_available():
+        z = np.zeros((3, 4), np.float32)
+        with pytest.raises(capi.WpsGpuError):
+            hostlib.HostDomain(0, z, z, np.zeros((3, 5), np.float32), np.zeros((3, 5), np.float32), np.zeros((4, 4), np.float32),
+                               np.zeros((4, 4), np.float32))
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     from wps_b200 import capi

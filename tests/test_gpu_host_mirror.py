@@ -86,3 +86,58 @@ def test_record_loop_matches_oracle(orc, handle, tmp_path):
     uo, vo = orc.metmap_xform(odom, u0, storage[("UU", 85000)].modified_mask, v0, storage[("VV", 85000)].modified_mask, g[2][1], g[3][1], -1)
     from tests.util import ulp_diff
     assert ulp_diff(storage[("UU", 85000)].r_arr, uo).max() <= 1 and ulp_diff(storage[("VV", 85000)].r_arr, vo).max() <= 1
+
+
+def test_cpp_host_side_matches_python_mirror(orc, handle, tmp_path):
+    """include/wpshost.h: the C++ restatement of the host side (METGRID.TBL parser, intermediate-file reader, record
+    loop with storage / mask carry-over, fill_missing_levels) drives the same C ABI -- handing the records over in file
+    byte order -- and must reproduce the Python mirror (itself checked against the oracle above) bit for bit."""
+    from wps_b200 import hostlib
+    from wps_b200.interp_option import read_interp_table
+    from wps_b200.metgrid import MetgridDomain
+    orc.set_transc_mode(1)
+    nx, ny = 64, 52
+    odom, gdom = conus_like(nx, ny, 40000.0, 30.0, 60.0, -98.0, 36.0, -92.0)
+    g = {1: orc.get_lat_lon_fields(odom, 1, 1, nx, ny, orc.M), 2: orc.get_lat_lon_fields(odom, 1, 1, nx + 1, ny, orc.U),
+         3: orc.get_lat_lon_fields(odom, 1, 1, nx, ny + 1, orc.V)}
+    rng = np.random.default_rng(1)
+    landmask = (rng.random((ny, nx)) < 0.6).astype(np.float32)
+    tbl = TBL + """
+    name=GHT ; interp_option=four_pt+average_4pt ; fill_lev=200100:PSFC(200100)
+    ========================================
+    name=PRES ; derived=yes ; fill_lev=all:vertical_index ; level_template=TT
+    ========================================
+    """
+    table = read_interp_table(tbl)
+    fields = [("LANDSEA", 200100.0, "landsea"), ("T", 85000.0, "smooth"), ("T", 50000.0, "smooth"), ("T", 30000.0, "smooth"),
+              ("UU", 85000.0, "wind"), ("VV", 85000.0, "wind"), ("ST000010", 200100.0, "land"), ("SKINTEMP", 200100.0, "smooth"),
+              ("PSFC", 200100.0, "smooth"), ("HGT", 85000.0, "smooth"), ("HGT", 30000.0, "smooth")]
+    recs = make_file(tmp_path, "FILE:2026-10-19_00", fields, 10)
+    recs2 = make_file(tmp_path, "SST:2026-10-19_00", [("T", 50000.0, "smooth")], 99)
+    # make the second source partial: re-write its file with missing values over half the globe
+    from wps_b200.intermediate import write_records
+    recs2[0].slab[:, :180] = 1e20
+    write_records(str(tmp_path / "SST:2026-10-19_00"), recs2)
+    # ---- Python mirror
+    dom = MetgridDomain(handle, g[1][0], g[1][1], g[2][0], g[2][1], g[3][0], g[3][1], landmask)
+    storage = dom.process_intermediate_fields(recs, table, "FILE")
+    dom.process_intermediate_fields(recs2, table, "SST", storage)
+    dom.create_derived_fields(storage, table)
+    dom.fill_missing_levels(storage, table)
+    # ---- C++ host side on the same files
+    hd = hostlib.HostDomain(0, g[1][0], g[1][1], g[2][0], g[2][1], g[3][0], g[3][1], landmask)
+    try:
+        assert hd.set_table(tbl) == len(table)
+        assert hd.process_file(str(tmp_path / "FILE:2026-10-19_00"), "FILE") == len(fields)
+        assert hd.process_file(str(tmp_path / "SST:2026-10-19_00"), "SST") == 1
+        hd.create_derived_fields()
+        hd.fill_missing_levels()
+        got = {(n, l) for (n, l, _, _, _) in hd.fields()}
+        assert got == set(storage.keys()), (sorted(got ^ set(storage.keys())))
+        assert ("GHT", 200100) in got and ("PRES", 50000) in got and ("TT", 200100) not in got
+        for (name, level), f in storage.items():
+            r, v = hd.get_field(name, level)
+            assert (v == f.valid_mask).all(), (name, level)
+            assert_bitexact(r, f.r_arr, "C++ host side %s %d" % (name, level))
+    finally:
+        hd.close()

@@ -16,3 +16,6 @@ done
 for p in "${pids[@]}"; do wait $p; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o ../libwpsgpu.so build/api.o build/metgrid.o build/geogrid.o build/misc.o -lcudart
 echo "built $(cd .. && pwd)/libwpsgpu.so"
+# C++ host side above the C ABI (include/wpshost.h): links against libwpsgpu.so next to it
+g++ -O2 -std=c++17 -fPIC -shared -Wall -Wextra -ffp-contract=off -o ../libwpshost.so host/wpshost.cpp -L.. -lwpsgpu -Wl,-rpath,'$ORIGIN'
+echo "built $(cd .. && pwd)/libwpshost.so"
