@@ -410,7 +410,7 @@ def run_b200(args, rank, world, local_rank):
     value = world * pts / (ms_per_step / 1e3)
 
     # ---- e2e: host buffers in pinned memory through the C ABI (H2D + kernels + D2H inside the timed region) ----
-    e2e_value, e2e_s, h2d, d2h, e2e_raw_s = None, 0.0, 0, 0, None
+    e2e_value, e2e_s, h2d, d2h, e2e_raw_s, host_input_bytes = None, 0.0, 0, 0, None, 0
     if not args.no_e2e:
         hh = capi.Handle(local_rank, capi.PTR_HOST)
         for gid, (xlat, xlon) in w["grids"].items():
@@ -437,11 +437,17 @@ def run_b200(args, rank, world, local_rank):
         hdescs = slab_descs(capi, w, host)
         enqueue_all(hh, w, hdescs)  # warm-up (arena allocation, coordinate cache)
         barrier()
+        b0 = hh.metgrid_copy_bytes()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             enqueue_all(hh, w, hdescs)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
+        b1 = hh.metgrid_copy_bytes()
+        # bytes the library actually moved (chains without `search` only transfer the part of the slab they can touch);
+        # host_input_bytes_per_step is the size of the input arrays handed over
+        host_input_bytes = h2d
+        h2d, d2h = (b1[0] - b0[0]) // e2e_steps, (b1[1] - b0[1]) // e2e_steps
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -489,7 +495,7 @@ def run_b200(args, rank, world, local_rank):
                              "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
                              "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_s * 1e3,
+                        "ms_per_step": e2e_s * 1e3, "host_input_bytes_per_step": host_input_bytes,
                         "raw_record_ms_per_step": None if e2e_raw_s is None else e2e_raw_s * 1e3},
                 "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "cpu_affinity": affinity, "clocks": sampler.result()}
         if geo is not None:

@@ -161,6 +161,10 @@ int wpsgpu_metgrid_flush(wpsgpu_handle_t h);
  * host buffers the host is free to read and decode the next file meanwhile.  Further calls on the handle are ordered
  * behind the pending copies automatically. */
 int wpsgpu_metgrid_flush_async(wpsgpu_handle_t h);
+/* Bytes the host-pointer mode has moved over PCIe for metgrid flushes since the handle was created (slabs, masks,
+ * carried-over fields in; r_arr and new_pts out; the small job tables are not counted).  Chains without `search` only
+ * need the rectangle of the source slab their destination grid can touch, so h2d is usually far below the slab sizes. */
+int wpsgpu_metgrid_copy_bytes(wpsgpu_handle_t h, int64_t *h2d, int64_t *d2h);
 /* Device time (CUDA events on the handle's stream) of the dominant kernel of the last flush and the number of
  * (slab x destination point) outputs it produced -- for roofline reporting only. */
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);

@@ -292,6 +292,11 @@ class Handle:
         """wait=False: wpsgpu_metgrid_flush_async -- results are complete after synchronize()."""
         check(lib().wpsgpu_metgrid_flush(self._h) if wait else lib().wpsgpu_metgrid_flush_async(self._h))
 
+    def metgrid_copy_bytes(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().wpsgpu_metgrid_copy_bytes(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def metgrid_last_kernel(self):
         ms = C.c_float()
         pts = C.c_double()

@@ -74,6 +74,7 @@ struct CoordCacheEntry {
     uint64_t grid_version;
     float2* d_xy;  // (rx, ry) of lltoxy(xlat, xlon) with the source projection, M stagger
     int bbox[4];   // min/max of floor(rx), floor(ry) over the destination grid (source-cell bounding box)
+    int rbbox[4];  // the same including the lon+360 retry position of interp_to_latlon (:2640-2660) for points with lon < 0
     float* d_gauss; // device copy of the Gaussian latitude table (PROJ_GAUSS sources), else nullptr
 };
 
@@ -118,6 +119,7 @@ struct wpsgpu_ctx {
     cudaStream_t s_side = nullptr;                  // slow-bitmap passes overlapping the first-method kernels
     std::vector<cudaEvent_t> ev_pool;               // per-job fork events for s_side
     cudaEvent_t ev_copy = nullptr, ev_done = nullptr, ev_out_done = nullptr;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;           // bytes moved by the host-pointer paths of the metgrid flush
     bool async_pending = false;                     // wpsgpu_metgrid_flush_async: D2H copies may still read the arena
     bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };

@@ -59,14 +59,15 @@ __global__ void k_coord_cache(DevProj p, const float* __restrict__ xlat, const f
 }
 
 // ---- raw intermediate-file records -> halo'd source slabs (read_met_module.F:375-386, process_domain_module.F:1119-1140)
-struct DecodeTask { const unsigned* raw; float* out; int raw_nx, ny, bdr, big_endian; };
+struct DecodeTask { const unsigned* raw; float* out; int raw_nx, ny, bdr, big_endian, row0, nrows; };   // rows [row0, row0+nrows) only
 
 __global__ void __launch_bounds__(256) k_decode_records(const DecodeTask* __restrict__ tasks)
 {
     const DecodeTask t = tasks[blockIdx.y];
     const int snx = t.raw_nx + 2 * t.bdr;
-    const size_t n = (size_t)snx * t.ny;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = (size_t)snx * t.nrows, e0 = (size_t)snx * t.row0;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = e0 + k;
         int i = (int)(e % snx) - t.bdr, j = (int)(e / snx);          // i: 0-based column of the record, halo columns outside
         if (i < 0) i += t.raw_nx; else if (i >= t.raw_nx) i -= t.raw_nx;   // halo_slab(1-bdr:0) = slab(nx-bdr+1:nx), (nx+1:nx+bdr) = slab(1:bdr)
         unsigned w = __ldg(t.raw + (size_t)j * t.raw_nx + i);
@@ -291,6 +292,29 @@ __global__ void k_xy_bbox(const float2* __restrict__ xy, int64_t n, int* __restr
         if (fabsf(p.x) < 1.0e9f && fabsf(p.y) < 1.0e9f) {
             int fi = (int)floorf(p.x), fj = (int)floorf(p.y);
             imin = min(imin, fi); imax = max(imax, fi); jmin = min(jmin, fj); jmax = max(jmax, fj);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, off)); imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, off));
+        jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, off)); jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, off));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(bbox + 0, imin); atomicMax(bbox + 1, imax); atomicMin(bbox + 2, jmin); atomicMax(bbox + 3, jmax); }
+}
+
+// interp_to_latlon tries (lat, lon + 360) when the first position gave nothing and lon < 0 (:2640-2660): the source
+// cells that second position can touch, so that partial source transfers cover them too.
+__global__ void k_xy_bbox_retry(DevProj p, const float* __restrict__ xlat, const float* __restrict__ xlon, int64_t n, int* __restrict__ bbox)
+{
+    int imin = INT_MAX, imax = INT_MIN, jmin = INT_MAX, jmax = INT_MIN;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        float lon = xlon[k];
+        if (lon < 0.0f) {
+            float rx, ry;
+            lltoxy(p, xlat[k], lon + 360.0f, rx, ry, WPSGPU_M);
+            if (fabsf(rx) < 1.0e9f && fabsf(ry) < 1.0e9f) {
+                int fi = (int)floorf(rx), fj = (int)floorf(ry);
+                imin = min(imin, fi); imax = max(imax, fi); jmin = min(jmin, fj); jmax = max(jmax, fj);
+            }
         }
     }
     for (int off = 16; off > 0; off >>= 1) {
@@ -940,6 +964,14 @@ int wpsgpu_metgrid_enqueue_slabs(wpsgpu_handle_t h, const wpsgpu_proj* src_proj,
     return 0;
 }
 
+int wpsgpu_metgrid_copy_bytes(wpsgpu_handle_t h, int64_t* h2d, int64_t* d2h)
+{
+    WPS_CHECK(h != nullptr, -1, "NULL handle");
+    if (h2d) *h2d = h->h2d_bytes;
+    if (d2h) *d2h = h->d2h_bytes;
+    return 0;
+}
+
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float* ms, double* points)
 {
     WPS_CHECK(h && ms && points, -1, "NULL argument");
@@ -973,6 +1005,8 @@ struct FlushShared {
     std::vector<Box> box;
     std::map<const void*, void*> staged;     // host pointer -> staged device copy (masks are shared by many slabs)
     std::vector<char> tab;                   // host image of a pass's tables
+    struct Sub { bool on; int x0, x1, y0, y1; };   // source columns / rows a group can touch (host mode, chains without search)
+    std::vector<Sub> sub;
     int max_depth = 0, max_span = 0;
 };
 
@@ -981,6 +1015,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     std::vector<QueuedSlab>& queue = *fs.queue;
     std::vector<std::vector<int>>& groups = *fs.groups;
     const bool host = h->ptr_mode == WPSGPU_PTR_HOST;
+    const bool poison = env_int("WPSGPU_POISON", 0, 0, 1) != 0;
     const int njobs = (int)gsel.size();
     int nq = 0;
     for (int g : gsel) nq += (int)groups[g].size();
@@ -1091,6 +1126,21 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             SlabPtrs& p = sp[s0 + k];
             p.slow = nullptr; p.decided = nullptr; p.valid = nullptr;
             const wpsgpu_slab& s = queue[grp[k]].s;
+            if (s.raw_nx == 0 && host && fs.sub[g].on && fs.staged.find(s.slab) == fs.staged.end()) {
+                // full-size device slab (indexing unchanged), but only the rectangle the chain can touch is transferred
+                const FlushShared::Sub& sb = fs.sub[g];
+                float* d = (float*)h->arena.take(sbytes);
+                WPS_CHECK(d != nullptr, -3, "device arena exhausted (source slab)");
+                if (poison) WPS_CUDA(cudaMemsetAsync(d, 0xff, sbytes, s_in));   // testing aid: stray reads see NaN
+                const size_t pitch = (size_t)(jb.maxx - jb.minx + 1) * sizeof(float);
+                const size_t off = (size_t)(sb.y0 - jb.miny) * (jb.maxx - jb.minx + 1) + (sb.x0 - jb.minx);
+                const size_t wbytes_row = (size_t)(sb.x1 - sb.x0 + 1) * sizeof(float), rows = (size_t)(sb.y1 - sb.y0 + 1);
+                WPS_CUDA(cudaMemcpy2DAsync(d + off, pitch, s.slab + off, pitch, wbytes_row, rows, cudaMemcpyHostToDevice, s_in));
+                h->h2d_bytes += (int64_t)(wbytes_row * rows);
+                fs.staged[s.slab] = d;
+                p.src = d;
+                continue;
+            }
             if (s.raw_nx == 0) { WPS_TRY(stage_shared(s.slab, sbytes, &p.src)); continue; }
             // raw record: bring the bytes over (host mode) and let k_decode_records build the slab
             auto it = fs.staged.find(s.slab);
@@ -1100,10 +1150,21 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             }
             const size_t rawbytes = (size_t)s.raw_nx * (jb.maxy - jb.miny + 1) * sizeof(float);
             const void* d_raw = s.slab;
-            if (host) { d_raw = take_run(in_runs, s.slab, rawbytes); WPS_CHECK(d_raw != nullptr, -3, "device arena exhausted (raw records)"); }
             DecodeTask t;
-            t.raw = (const unsigned*)d_raw; t.raw_nx = s.raw_nx; t.ny = jb.maxy - jb.miny + 1;
+            t.raw_nx = s.raw_nx; t.ny = jb.maxy - jb.miny + 1;
             t.bdr = (jb.maxx - jb.minx + 1 - s.raw_nx) / 2; t.big_endian = s.raw_big_endian;
+            t.row0 = 0; t.nrows = t.ny;
+            if (host && fs.sub[g].on) {
+                // only the rows the chain can touch (whole rows: the halo columns wrap around to the other end of the record)
+                t.row0 = fs.sub[g].y0 - jb.miny; t.nrows = fs.sub[g].y1 - fs.sub[g].y0 + 1;
+                char* d = (char*)h->arena.take(rawbytes);
+                WPS_CHECK(d != nullptr, -3, "device arena exhausted (raw records)");
+                const size_t off = (size_t)t.row0 * s.raw_nx * sizeof(float), len = (size_t)t.nrows * s.raw_nx * sizeof(float);
+                WPS_CUDA(cudaMemcpyAsync(d + off, reinterpret_cast<const char*>(s.slab) + off, len, cudaMemcpyHostToDevice, s_in));
+                h->h2d_bytes += (int64_t)len;
+                d_raw = d;
+            } else if (host) { d_raw = take_run(in_runs, s.slab, rawbytes); WPS_CHECK(d_raw != nullptr, -3, "device arena exhausted (raw records)"); }
+            t.raw = (const unsigned*)d_raw;
             decode_tasks.push_back(t);
             decode_slots.push_back(s0 + k);
             fs.staged[s.slab] = nullptr;   // filled in once the decoded slabs are placed (below)
@@ -1137,6 +1198,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
                 WPS_CHECK(d_v != nullptr, -3, "device arena exhausted (valid mask)");
                 WPS_CUDA(cudaMemcpyAsync(sp[s0 + k].r_arr, s.r_arr, rbytes, cudaMemcpyHostToDevice, s_in));
                 WPS_CUDA(cudaMemcpyAsync(d_v, s.valid_mask, wbytes, cudaMemcpyHostToDevice, s_in));
+                h->h2d_bytes += (int64_t)(rbytes + wbytes);
                 sp[s0 + k].valid = (const int*)d_v;
             }
         } else {
@@ -1153,12 +1215,13 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         const size_t n = (size_t)(t.raw_nx + 2 * t.bdr) * t.ny;
         t.out = (float*)h->arena.take(n * sizeof(float));
         WPS_CHECK(t.out != nullptr, -3, "device arena exhausted (decoded slabs)");
+        if (poison && t.nrows < t.ny) WPS_CUDA(cudaMemsetAsync(t.out, 0xff, n * sizeof(float), h->stream));
         sp[decode_slots[k]].src = t.out;
         fs.staged[decode_hosts[k]] = t.out;
         decode_max = std::max(decode_max, n);
     }
     for (const auto& pr : decode_pending) sp[pr.first].src = (const float*)fs.staged[pr.second];
-    for (const CopyRun& r : in_runs) WPS_CUDA(cudaMemcpyAsync(r.d, r.h, r.bytes, cudaMemcpyHostToDevice, s_in));
+    for (const CopyRun& r : in_runs) { WPS_CUDA(cudaMemcpyAsync(r.d, r.h, r.bytes, cudaMemcpyHostToDevice, s_in)); h->h2d_bytes += (int64_t)r.bytes; }
     // All tables of this pass travel in ONE copy: [jobs | slab pointers | six int lists of njobs+1 entries]
     std::vector<int> pack_jobs;
     int pack_cells = 0, pack_max = 0;
@@ -1363,8 +1426,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             WPS_CUDA(cudaEventRecord(h->ev_done, h->stream));
             WPS_CUDA(cudaStreamWaitEvent(s_out, h->ev_done, 0));
         }
-        for (const CopyRun& r : out_r_runs) WPS_CUDA(cudaMemcpyAsync((void*)r.h, r.d, r.bytes, cudaMemcpyDeviceToHost, s_out));
-        for (const CopyRun& r : out_np_runs) WPS_CUDA(cudaMemcpyAsync((void*)r.h, r.d, r.bytes, cudaMemcpyDeviceToHost, s_out));
+        for (const CopyRun& r : out_r_runs) { WPS_CUDA(cudaMemcpyAsync((void*)r.h, r.d, r.bytes, cudaMemcpyDeviceToHost, s_out)); h->d2h_bytes += (int64_t)r.bytes; }
+        for (const CopyRun& r : out_np_runs) { WPS_CUDA(cudaMemcpyAsync((void*)r.h, r.d, r.bytes, cudaMemcpyDeviceToHost, s_out)); h->d2h_bytes += (int64_t)r.bytes; }
     }
     return 0;
 }
@@ -1402,7 +1465,7 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
     fs.job_xy.resize(njobs); fs.job_gauss.assign(njobs, nullptr); fs.box.resize(njobs);
 
     // ---- coordinate cache: (rx, ry) of every destination point per (grid, source projection), computed once ----
-    std::vector<int> job_bbox(4 * njobs, 0);
+    std::vector<int> job_bbox(4 * njobs, 0), job_rbbox(4 * njobs, 0);
     for (int g = 0; g < njobs; ++g) {
         const QueuedSlab& q0 = queue[groups[g][0]];
         const DstGrid& dg = h->grids[q0.s.grid_id];
@@ -1425,9 +1488,11 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
             int* d_bbox = h->d_counters + 8;
             WPS_CUDA(cudaMemcpyAsync(d_bbox, init_bbox, sizeof(init_bbox), cudaMemcpyHostToDevice, h->stream));
             k_xy_bbox<<<h->sm_count * 4, 256, 0, h->stream>>>(e.d_xy, n, d_bbox);
-            h->launches += 2;
-            WPS_CUDA(cudaGetLastError());
             WPS_CUDA(cudaMemcpyAsync(e.bbox, d_bbox, sizeof(init_bbox), cudaMemcpyDeviceToHost, h->stream));
+            k_xy_bbox_retry<<<h->sm_count * 4, 256, 0, h->stream>>>(dp, dg.d_xlat, dg.d_xlon, n, d_bbox);   // grows the same box
+            h->launches += 3;
+            WPS_CUDA(cudaGetLastError());
+            WPS_CUDA(cudaMemcpyAsync(e.rbbox, d_bbox, sizeof(init_bbox), cudaMemcpyDeviceToHost, h->stream));
             WPS_CUDA(cudaStreamSynchronize(h->stream));
             if (it != h->coord_cache.end()) { cudaFree(it->second.d_xy); if (it->second.d_gauss) cudaFree(it->second.d_gauss); h->coord_cache.erase(it); }
             it = h->coord_cache.insert(std::make_pair(key, e)).first;
@@ -1435,12 +1500,15 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         fs.job_xy[g] = it->second.d_xy;
         fs.job_gauss[g] = it->second.d_gauss;
         memcpy(&job_bbox[4 * g], it->second.bbox, 4 * sizeof(int));
+        memcpy(&job_rbbox[4 * g], it->second.rbbox, 4 * sizeof(int));
     }
 
     // ---- classify jobs and size the arena ----
     // first-method kernels: chain starts with sixteen_pt / four_pt / nearest_neighbor (the latter two only when the
     // landmask logic selects a single interp mask, i.e. not masked=both); sixteen_pt additionally needs the
     // source-cell bounding box to be small against the destination grid (source coarser than the domain).
+    const bool subrect_enabled = env_int("WPSGPU_SUBRECT", 1, 0, 1) != 0;
+    fs.sub.resize(njobs);
     size_t need = (size_t)njobs * (sizeof(Job) + 256) + (size_t)nq * sizeof(SlabPtrs) + (1 << 20);
     size_t defer_entries = 0;
     std::map<const void*, size_t> uniq_in;  // host source/mask pointers staged once
@@ -1454,6 +1522,24 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         if (has_search) {
             defer_entries += dg.npts() * groups[g].size();
             fs.max_span = std::max(fs.max_span, std::max(q0.s.maxx - q0.s.minx, q0.s.maxy - q0.s.miny));
+        }
+        // Host-pointer mode: a chain without `search` reads the source within 2 cells of the cell a destination point
+        // (or its lon+360 retry position) falls into, and the packed pre-pass within 6 cells of the bounding box; only
+        // that rectangle (+8 cells) of the slab has to cross PCIe.  `search` can walk anywhere, average_gcell visits
+        // every source cell: those slabs are copied whole.
+        FlushShared::Sub& sb = fs.sub[g];
+        sb.on = false;
+        if (host && !has_search && !q0.gcell && subrect_enabled) {
+            const int* rb = &job_rbbox[4 * g];
+            if (rb[0] <= rb[1] && rb[2] <= rb[3]) {
+                const int margin = 8;
+                long x0 = std::max<long>(q0.s.minx, (long)rb[0] - margin), x1 = std::min<long>(q0.s.maxx, (long)rb[1] + margin);
+                long y0 = std::max<long>(q0.s.miny, (long)rb[2] - margin), y1 = std::min<long>(q0.s.maxy, (long)rb[3] + margin);
+                const double full = (double)(q0.s.maxx - q0.s.minx + 1) * (q0.s.maxy - q0.s.miny + 1);
+                if (x1 >= x0 && y1 >= y0 && (double)(x1 - x0 + 1) * (double)(y1 - y0 + 1) < 0.7 * full) {
+                    sb.on = true; sb.x0 = (int)x0; sb.x1 = (int)x1; sb.y0 = (int)y0; sb.y1 = (int)y1;
+                }
+            }
         }
         Box& b = fs.box[g];
         b.fast = 0; b.bx0 = b.by0 = b.bnx = b.bny = b.npack = 0;
