@@ -632,3 +632,35 @@ def test_flush_async_then_synchronize(orc, handle):
         assert (npw[l] == np_ref).all()
         assert_bitexact(r[l], r_ref, "async flush, slab %d" % l)
     assert (lvl == 3.0).all()
+
+
+def test_same_slab_for_two_grids_partial_transfers(orc, handle, monkeypatch):
+    """One host slab queued for two destination grids whose source footprints are far apart: host-pointer mode stages
+    only a rectangle per use, so the second use must not inherit the first one's (too small) staged copy.  Run with
+    the untransferred part poisoned (WPSGPU_POISON) so that a stray read cannot go unnoticed."""
+    from wps_b200 import capi
+    monkeypatch.setenv("WPSGPU_POISON", "1")
+    orc.set_transc_mode(1)
+    osrc, gsrc = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    slab = halo(synth_field(360, 181, 4242))
+    chain = "sixteen_pt+four_pt+average_4pt"
+    fo_o, fo_g = orc.field_opts(chain, 1e20, 0.0, -2.0), capi.field_opts(chain, 1e20, 0.0, -2.0)
+    doms = []
+    for gid, (ref_lat, ref_lon) in enumerate([(40.0, -120.0), (25.0, 100.0)]):      # North America / South-East Asia
+        odom, _ = conus_like(40, 30, 30000.0, truelat1=30.0, truelat2=60.0, stand_lon=ref_lon, ref_lat=ref_lat, ref_lon=ref_lon)
+        xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, 40, 30, orc.M)
+        handle.metgrid_set_grid(gid, xlat, xlon, 1, 1)
+        doms.append((xlat, xlon))
+    handle.metgrid_set_domain(1, 40, 1, 30)
+    outs = []
+    for gid in (0, 1):
+        r = np.zeros((30, 40), np.float32)
+        npw = np.zeros((30, capi.nwords(40)), np.int32)
+        handle.metgrid_enqueue_slab(gsrc, fo_g, slab, -2, 1, 3, gid, capi.M, r, npw)
+        outs.append((r, npw))
+    handle.metgrid_flush()
+    for gid, (xlat, xlon) in enumerate(doms):
+        r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, 40, 1, 30), slab, -2, 1, 3)
+        assert np.isfinite(outs[gid][0]).all()
+        assert (outs[gid][1] == np_ref).all()
+        assert_bitexact(outs[gid][0], r_ref, "grid %d" % gid)

@@ -1007,6 +1007,16 @@ struct FlushShared {
     std::vector<char> tab;                   // host image of a pass's tables
     struct Sub { bool on; int x0, x1, y0, y1; };   // source columns / rows a group can touch (host mode, chains without search)
     std::vector<Sub> sub;
+    std::map<const void*, Sub> staged_sub;   // rectangle (rows for raw records) present in a partially staged slab
+    // a slab staged before can be shared if it is complete or holds at least the rectangle wanted now
+    bool reusable(const void* p, const Sub& want) const
+    {
+        if (staged.find(p) == staged.end()) return false;
+        auto it = staged_sub.find(p);
+        if (it == staged_sub.end()) return true;
+        const Sub& have = it->second;
+        return want.on && have.x0 <= want.x0 && have.x1 >= want.x1 && have.y0 <= want.y0 && have.y1 >= want.y1;
+    }
     int max_depth = 0, max_span = 0;
 };
 
@@ -1126,6 +1136,10 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             SlabPtrs& p = sp[s0 + k];
             p.slow = nullptr; p.decided = nullptr; p.valid = nullptr;
             const wpsgpu_slab& s = queue[grp[k]].s;
+            if (host && fs.staged.count(s.slab) && !fs.reusable(s.slab, fs.sub[g])) {   // staged for another grid with a smaller rectangle
+                fs.staged.erase(s.slab);
+                fs.staged_sub.erase(s.slab);
+            }
             if (s.raw_nx == 0 && host && fs.sub[g].on && fs.staged.find(s.slab) == fs.staged.end()) {
                 // full-size device slab (indexing unchanged), but only the rectangle the chain can touch is transferred
                 const FlushShared::Sub& sb = fs.sub[g];
@@ -1138,6 +1152,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
                 WPS_CUDA(cudaMemcpy2DAsync(d + off, pitch, s.slab + off, pitch, wbytes_row, rows, cudaMemcpyHostToDevice, s_in));
                 h->h2d_bytes += (int64_t)(wbytes_row * rows);
                 fs.staged[s.slab] = d;
+                fs.staged_sub[s.slab] = sb;
                 p.src = d;
                 continue;
             }
@@ -1157,6 +1172,9 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             if (host && fs.sub[g].on) {
                 // only the rows the chain can touch (whole rows: the halo columns wrap around to the other end of the record)
                 t.row0 = fs.sub[g].y0 - jb.miny; t.nrows = fs.sub[g].y1 - fs.sub[g].y0 + 1;
+                FlushShared::Sub rows = fs.sub[g];
+                rows.x0 = jb.minx; rows.x1 = jb.maxx;          // whole rows are decoded
+                fs.staged_sub[s.slab] = rows;
                 char* d = (char*)h->arena.take(rawbytes);
                 WPS_CHECK(d != nullptr, -3, "device arena exhausted (raw records)");
                 const size_t off = (size_t)t.row0 * s.raw_nx * sizeof(float), len = (size_t)t.nrows * s.raw_nx * sizeof(float);
