@@ -25,6 +25,11 @@ METRIC = "metgrid output points/s (field*level*pt)"
 WORKLOAD = "config2: GFS 0.25deg 1440x721 x (34 isobaric + sfc) levels, default METGRID.TBL.ARW chains -> 3-km CONUS Lambert 1799x1059; 1 step = 1 time (190 slabs)"
 
 
+# WPSGPU_CELL16=0 selects the older point-major packed kernel (A/B measurements)
+CELL16 = os.environ.get("WPSGPU_CELL16", "1") != "0"
+K16 = "k_metgrid_cell16+k_cell16_words" if CELL16 else "k_metgrid_fast16"
+
+
 def env_int(k, d):
     return int(os.environ.get(k, d))
 
@@ -475,7 +480,7 @@ def run_b200(args, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None   # DRAM bytes of the dominant kernel's launches in one step, from the committed ncu capture
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_fast16_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_cell16_traffic.json" if CELL16 else "r01_fast16_traffic.json")))
             if p3[1] >= p3[2] and abs(tj["kernel_points"] - kp) < 0.01 * kp:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
@@ -490,9 +495,9 @@ def run_b200(args, rank, world, local_rank):
                            "sharding": "one FILE time per GPU per step (field x level x time shard, no collective)"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_unit": "bytes per step (all launches of the kernel), ncu dram read+write; algorithmic = %d" % int(ALG_BYTES_PER_POINT * kp),
-                             "kernel": "k_metgrid_fast16" if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
+                             "kernel": K16 if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
                              "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
-                             "breakdown_ms": {"k_pack16": t3[0], "k_metgrid_fast16": t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
+                             "breakdown_ms": {"k_pack16": t3[0], K16: t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
                              "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "host_input_bytes_per_step": host_input_bytes,

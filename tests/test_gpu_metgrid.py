@@ -44,9 +44,12 @@ def run_case(orc, handle, xlat, xlon, slabs, src, chain, sm=(1, 1), sd=None, bdr
     refs = [orc.interp_met_field(osrc, fo_o, fstag, xlat, xlon, sm[0], sm[1], sd, slab, minx, miny, bdr, mask=masks[0],
                                  land_mask=masks[1], water_mask=masks[2], landmask=landmask, process_bdy_width=pbw,
                                  r_arr=None if r0 is None else r0.copy(), valid_mask=valid) for slab in slabs]
-    # both device paths against the oracle: the packed sixteen_pt kernel (when eligible) and the generic kernel
-    for disable_fast in (False, True):
+    # all device paths against the oracle: the cell-major and the point-major packed sixteen_pt kernels (when eligible)
+    # and the generic kernel
+    import os
+    for disable_fast, cell16 in ((False, "1"), (False, "0"), (True, "1")):
         handle.debug_disable_fast(disable_fast)
+        os.environ["WPSGPU_CELL16"] = cell16
         outs = []
         for slab in slabs:
             r = np.zeros((ny, nx), np.float32) if r0 is None else r0.copy()
@@ -57,9 +60,10 @@ def run_case(orc, handle, xlat, xlon, slabs, src, chain, sm=(1, 1), sd=None, bdr
         handle.metgrid_flush()
         for (r_ref, np_ref), (r, npw) in zip(refs, outs):
             assert (npw == np_ref).all(), "new_pts bits differ for chain %s (fast disabled=%s): %d words" % (
-                chain, disable_fast, (npw != np_ref).sum())
-            assert_bitexact(r, r_ref, "r_arr chain=%s fast_disabled=%s" % (chain, disable_fast))
+                chain + " cell16=" + cell16, disable_fast, (npw != np_ref).sum())
+            assert_bitexact(r, r_ref, "r_arr chain=%s fast_disabled=%s cell16=%s" % (chain, disable_fast, cell16))
     handle.debug_disable_fast(False)
+    os.environ.pop("WPSGPU_CELL16", None)
     return outs
 
 
@@ -264,6 +268,24 @@ def test_packed_many_levels(orc, handle, missing):
     run_case(orc, handle, xlat, xlon, slabs[:5], src, "sixteen_pt+four_pt+wt_average_4pt+search", missing=np.float32(missing), fill=0.0)
 
 
+@pytest.mark.parametrize("nlev", [1, 2, 3, 9, 16, 20, 35, 40, 64])
+def test_cell_major_level_counts(orc, handle, nlev):
+    """Every lane shape of the cell-major kernel (level pairs per warp 1 ... 32, partial last chunk, odd level counts):
+    a few levels carry missing values and exact zeros so that ok bits differ between the lanes of a warp."""
+    xlat, xlon = make_domain(orc, handle, nx=97, ny=61, dx=9000.0)
+    src = latlon_source(720, 361, -0.5, 0.5, 90.0, 0.0)
+    slabs = []
+    for s in range(nlev):
+        f = synth_field(720, 361, 300 + s, kind="wind" if s % 2 else "smooth", zeros=0.01 if s % 5 == 0 else 0.0)
+        if s % 7 == 3:
+            f[np.random.default_rng(s).random(f.shape) < 0.02] = np.float32(1e20)
+        slabs.append(halo(f))
+    lm = (np.random.default_rng(5).random(xlat.shape) < 0.6).astype(np.float32)
+    run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+average_4pt", fill=0.0)
+    if nlev in (3, 35):
+        run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+average_4pt", fill=-7.0, landmask=lm, masked=1.0, pbw=9)
+
+
 def test_against_committed_golden_vectors(handle):
     """GPU vs tests/golden/metgrid_small.npz (committed fixtures generated by tests/golden/make_golden.py)."""
     import os
@@ -415,8 +437,10 @@ def test_config2_full_size_windows_and_kernel_agreement(orc, handle):
     handle.metgrid_set_domain(1, nx, 1, ny)
     slabs = [synth.add_halo(synth.slab_np(sx, sy, 7 + k, c[6], landsea=ls, missing=np.float32(c[1]))) for k, c in enumerate(cases)]
     results = {}
-    for disable_fast in (False, True):
-        handle.debug_disable_fast(disable_fast)
+    import os
+    for disable_fast in (False, True, "point-major"):
+        handle.debug_disable_fast(disable_fast is True)
+        os.environ["WPSGPU_CELL16"] = "0" if disable_fast == "point-major" else "1"
         outs = []
         for c, slab in zip(cases, slabs):
             fo = capi.field_opts(c[0], np.float32(c[1]), np.float32(c[2]), c[3], c[5])
@@ -427,9 +451,12 @@ def test_config2_full_size_windows_and_kernel_agreement(orc, handle):
         handle.metgrid_flush()
         results[disable_fast] = outs
     handle.debug_disable_fast(False)
-    for k, ((r_f, n_f), (r_g, n_g)) in enumerate(zip(results[False], results[True])):
+    os.environ.pop("WPSGPU_CELL16", None)
+    for k, ((r_f, n_f), (r_g, n_g), (r_p, n_p)) in enumerate(zip(results[False], results[True], results["point-major"])):
         assert (n_f == n_g).all(), "case %d: new_pts differ between the two device paths" % k
         assert_bitexact(r_f, r_g, "case %d: first-method kernels vs generic kernel, full size" % k)
+        assert (n_p == n_g).all(), "case %d: new_pts differ between the point-major packed kernel and the generic kernel" % k
+        assert_bitexact(r_p, r_g, "case %d: point-major packed kernel vs generic kernel, full size" % k)
     # oracle on windows: corners, centre, and two windows on the synthetic coast line
     coast = np.argwhere(np.abs(np.diff(landmask, axis=1)) > 0)
     wins = [(1, 1), (nx - 47, 1), (1, ny - 39), (nx - 47, ny - 39), (nx // 2, ny // 2)]

@@ -377,7 +377,7 @@ int wpsgpu_destroy(wpsgpu_handle_t h)
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (auto& kv : h->coord_cache) { cudaFree(kv.second.d_xy); if (kv.second.d_gauss) cudaFree(kv.second.d_gauss); }
+    for (auto& kv : h->coord_cache) wps::free_coord_entry(kv.second);
     for (auto& g : h->grids)
         if (g.own) { cudaFree(g.d_xlat); cudaFree(g.d_xlon); if (g.d_landmask) cudaFree(g.d_landmask); }
     wpsgpu_geo_free(h);
