@@ -25,9 +25,9 @@ METRIC = "metgrid output points/s (field*level*pt)"
 WORKLOAD = "config2: GFS 0.25deg 1440x721 x (34 isobaric + sfc) levels, default METGRID.TBL.ARW chains -> 3-km CONUS Lambert 1799x1059; 1 step = 1 time (190 slabs)"
 
 
-# WPSGPU_CELL16=0 selects the older point-major packed kernel (A/B measurements)
-CELL16 = os.environ.get("WPSGPU_CELL16", "1") != "0"
-K16 = "k_metgrid_cell16+k_cell16_words" if CELL16 else "k_metgrid_fast16"
+# WPSGPU_TILE16=1 selects the experimental tile-major sixteen_pt kernel (A/B measurements; slower on this workload)
+TILE16 = os.environ.get("WPSGPU_TILE16", "0") == "1"
+K16 = "k_metgrid_tile16" if TILE16 else "k_metgrid_fast16"
 
 
 def env_int(k, d):
@@ -480,7 +480,7 @@ def run_b200(args, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None   # DRAM bytes of the dominant kernel's launches in one step, from the committed ncu capture
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_cell16_traffic.json" if CELL16 else "r01_fast16_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_tile16_traffic.json" if TILE16 else "r01_fast16_traffic.json")))
             if p3[1] >= p3[2] and abs(tj["kernel_points"] - kp) < 0.01 * kp:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:

@@ -44,12 +44,12 @@ def run_case(orc, handle, xlat, xlon, slabs, src, chain, sm=(1, 1), sd=None, bdr
     refs = [orc.interp_met_field(osrc, fo_o, fstag, xlat, xlon, sm[0], sm[1], sd, slab, minx, miny, bdr, mask=masks[0],
                                  land_mask=masks[1], water_mask=masks[2], landmask=landmask, process_bdy_width=pbw,
                                  r_arr=None if r0 is None else r0.copy(), valid_mask=valid) for slab in slabs]
-    # all device paths against the oracle: the cell-major and the point-major packed sixteen_pt kernels (when eligible)
+    # all device paths against the oracle: the tile-major and the point-major packed sixteen_pt kernels (when eligible)
     # and the generic kernel
     import os
-    for disable_fast, cell16 in ((False, "1"), (False, "0"), (True, "1")):
+    for disable_fast, tile16 in ((False, "1"), (False, "0"), (True, "1")):
         handle.debug_disable_fast(disable_fast)
-        os.environ["WPSGPU_CELL16"] = cell16
+        os.environ["WPSGPU_TILE16"] = tile16
         outs = []
         for slab in slabs:
             r = np.zeros((ny, nx), np.float32) if r0 is None else r0.copy()
@@ -60,10 +60,10 @@ def run_case(orc, handle, xlat, xlon, slabs, src, chain, sm=(1, 1), sd=None, bdr
         handle.metgrid_flush()
         for (r_ref, np_ref), (r, npw) in zip(refs, outs):
             assert (npw == np_ref).all(), "new_pts bits differ for chain %s (fast disabled=%s): %d words" % (
-                chain + " cell16=" + cell16, disable_fast, (npw != np_ref).sum())
-            assert_bitexact(r, r_ref, "r_arr chain=%s fast_disabled=%s cell16=%s" % (chain, disable_fast, cell16))
+                chain + " tile16=" + tile16, disable_fast, (npw != np_ref).sum())
+            assert_bitexact(r, r_ref, "r_arr chain=%s fast_disabled=%s tile16=%s" % (chain, disable_fast, tile16))
     handle.debug_disable_fast(False)
-    os.environ.pop("WPSGPU_CELL16", None)
+    os.environ.pop("WPSGPU_TILE16", None)
     return outs
 
 
@@ -269,8 +269,8 @@ def test_packed_many_levels(orc, handle, missing):
 
 
 @pytest.mark.parametrize("nlev", [1, 2, 3, 9, 16, 20, 35, 40, 64])
-def test_cell_major_level_counts(orc, handle, nlev):
-    """Every lane shape of the cell-major kernel (level pairs per warp 1 ... 32, partial last chunk, odd level counts):
+def test_tile_major_level_counts(orc, handle, nlev):
+    """Every lane shape of the tile-major kernel (level pairs per warp 1 ... 32, partial last chunk, odd level counts):
     a few levels carry missing values and exact zeros so that ok bits differ between the lanes of a warp."""
     xlat, xlon = make_domain(orc, handle, nx=97, ny=61, dx=9000.0)
     src = latlon_source(720, 361, -0.5, 0.5, 90.0, 0.0)
@@ -440,7 +440,7 @@ def test_config2_full_size_windows_and_kernel_agreement(orc, handle):
     import os
     for disable_fast in (False, True, "point-major"):
         handle.debug_disable_fast(disable_fast is True)
-        os.environ["WPSGPU_CELL16"] = "0" if disable_fast == "point-major" else "1"
+        os.environ["WPSGPU_TILE16"] = "0" if disable_fast == "point-major" else "1"
         outs = []
         for c, slab in zip(cases, slabs):
             fo = capi.field_opts(c[0], np.float32(c[1]), np.float32(c[2]), c[3], c[5])
@@ -451,7 +451,7 @@ def test_config2_full_size_windows_and_kernel_agreement(orc, handle):
         handle.metgrid_flush()
         results[disable_fast] = outs
     handle.debug_disable_fast(False)
-    os.environ.pop("WPSGPU_CELL16", None)
+    os.environ.pop("WPSGPU_TILE16", None)
     for k, ((r_f, n_f), (r_g, n_g), (r_p, n_p)) in enumerate(zip(results[False], results[True], results["point-major"])):
         assert (n_f == n_g).all(), "case %d: new_pts differ between the two device paths" % k
         assert_bitexact(r_f, r_g, "case %d: first-method kernels vs generic kernel, full size" % k)

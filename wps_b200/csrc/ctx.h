@@ -70,20 +70,20 @@ struct DstGrid {
     size_t npts() const { return (size_t)nx() * ny(); }
 };
 
-// Destination points sorted by the source cell they fall into (cell-major sixteen_pt kernel): built once per cached
-// coordinate set and source-array extent, metgrid.cu build_cell_index
-struct CellIndex {
-    int dims[8];        // minx, maxx, miny, maxy, bx0, by0, bnx, bny it was built for
-    int* d_sidx;        // [npts] point index, sorted by (cell, index); points the packed path cannot take come last
-    int* d_pos;         // [npts] inverse permutation
-    int* d_cell_start;  // [bnx*bny + 1] first sorted position of each cell; the last entry is n_fast
+// Destination points sorted by (destination tile of 32 x th points, source cell) for the tile-major sixteen_pt
+// kernel: built once per cached coordinate set, source-array extent and tile height, metgrid.cu get_tile_index
+struct TileIndex {
+    int dims[9];        // minx, maxx, miny, maxy, bx0, by0, bnx, bny, th it was built for
+    int* d_sidx;        // [n_fast] point index, sorted by (tile, cell, index); points the packed path cannot take are left out
     float2* d_sxy;      // [n_fast] (rx, ry) in sorted order
-    int n_fast, n_cells_used;
+    int2* d_seg;        // [nseg + 1] (first sorted position, cell) of each run of points sharing tile and cell; sentinel (n_fast, 0)
+    int* d_tile_seg;    // [ntiles + 1] first segment of each tile
+    int n_fast, nseg, ntiles;
 };
 
 struct CoordCacheEntry {
     uint64_t grid_version;
-    std::vector<CellIndex> cidx;
+    std::vector<TileIndex> tidx;
     float2* d_xy;  // (rx, ry) of lltoxy(xlat, xlon) with the source projection, M stagger
     int bbox[4];   // min/max of floor(rx), floor(ry) over the destination grid (source-cell bounding box)
     int rbbox[4];  // the same including the lon+360 retry position of interp_to_latlon (:2640-2660) for points with lon < 0
@@ -94,8 +94,8 @@ inline void free_coord_entry(CoordCacheEntry& e)
 {
     cudaFree(e.d_xy);
     if (e.d_gauss) cudaFree(e.d_gauss);
-    for (CellIndex& c : e.cidx) { cudaFree(c.d_sidx); cudaFree(c.d_pos); cudaFree(c.d_cell_start); cudaFree(c.d_sxy); }
-    e.cidx.clear();
+    for (TileIndex& c : e.tidx) { cudaFree(c.d_sidx); cudaFree(c.d_sxy); cudaFree(c.d_seg); cudaFree(c.d_tile_seg); }
+    e.tidx.clear();
 }
 
 struct QueuedSlab {

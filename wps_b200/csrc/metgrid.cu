@@ -36,7 +36,7 @@ struct Job {
     const unsigned char* cf;     // [npack][bny][bnx] bit lv = 4x4 stencil anchored here is "clean" for level lv
     float f_negzero, f_one;      // -0.0f and 1.0f as run-time values (see mul2/add2 in the packed kernel)
     int gcell;                   // average_gcell branch (:2331-2478): masked=both is not special there
-    int cellmajor;               // rec is laid out for k_metgrid_cell16: [bny][bnx][2*npack level pairs][6] float2
+    int cellmajor;               // rec is laid out for k_metgrid_tile16: [bny][bnx][2*npack level pairs][6] float2
 };
 
 struct SlabPtrs {
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, co
     // cells, so the two cells a quarter-warp of destination points typically spans are served by one L1 wavefront,
     // and the six terms of a group are six consecutive lines
     if (jb.cellmajor) {
-        // cell-major kernel: the six terms of one level PAIR are 48 contiguous bytes, the pairs of a cell follow one another
+        // tile-major kernel: the six terms of one level PAIR are 48 contiguous bytes, the pairs of a cell follow one another
         // (a warp whose lanes are level pairs reads a cell's record with three coalesced 16-byte loads per stencil row)
         float4* rec = const_cast<float4*>(jb.rec) + (((size_t)cj * jb.bnx + ci) * (2 * jb.npack) + 2 * pack) * 3;
 #pragma unroll
@@ -576,60 +576,62 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
     }
 }
 
-// ---- cell-major sixteen_pt kernel ---------------------------------------------------------------------------------
-// The packed kernel above re-loads the 24 record terms (96 B) for every point-level; what limits it is the L1 return
-// path, not arithmetic.  Here the roles are swapped: a warp owns ONE source cell and a chunk of the job's levels, its
-// lanes are level PAIRS (f32x2), and the cell's record -- 4 stencil rows x 6 terms per level -- is loaded ONCE into
-// registers and reused for every destination point that falls into the cell (about 70 for a 0.25-degree source under a
-// 3-km grid).  The points of a cell come from the cell index (destination points sorted by source cell, cached with the
-// coordinates); their fractional offsets are warp-uniform and broadcast from shared memory.  With LV < 32 level pairs
-// per chunk the warp works on PT = 32/LV points at once.  Results are staged in shared memory [point][level] and
-// written out with lanes = points (runs of consecutive x inside the cell), so that stores stay sector-coalesced.
+// ---- tile-major sixteen_pt kernel ---------------------------------------------------------------------------------
+// The point-major kernel above re-loads the 24 record terms (96 B) for every point-level; what limits it is the L1
+// return path, not arithmetic.  Here the lanes of a warp are level PAIRS (f32x2) x a few point slots, and the record of
+// a source cell -- 4 stencil rows x 6 terms per level -- is held in REGISTERS while the warp walks through every
+// destination point of its tile that falls into that cell.  A warp owns a destination tile of 32 x TH points and a
+// chunk of 2*LV levels.  The tile index (points sorted by (tile, source cell), cached with the coordinates) gives the
+// tile's points as "segments", one per source cell it overlaps; the record of the next segment is fetched into shared
+// memory with cp.async while the current one is being used, the point table of the next batch is fetched one batch ahead.
+// Results are staged in shared memory [point of the tile][level]; the write-out has lanes = 32 consecutive x, so every
+// store is a full 128-byte line and the new_pts / slow words come from ballots, as in the point-major kernel.
+// (A first version sorted by source cell only and wrote each cell's runs of ~7 points: those partial 32-byte sectors
+// doubled the DRAM traffic -- L2 read-modify-write -- and it ended up slower than the point-major kernel.)
 // Arithmetic is the same xpass2 / ypass2 sequence as above: bit-identical results.
-// Per (point, level) "ok" bits go to okw[plane][sorted position]; k_cell16_words turns them into the new_pts / slow
-// bitmap words (32 consecutive x) and applies the level-independent fill rules.
-struct Cell16Params {
+struct Tile16Params {
     Job jb;
-    const int* sidx;         // CellIndex: point index, (rx, ry) and -- gathered per flush -- landmask in sorted order
+    const int* sidx;         // TileIndex: point index, (rx, ry) and -- gathered per flush -- landmask in sorted order
     const float2* sxy;
     const float* slm;
-    const int* cell_start;
-    unsigned* okw;           // [nchunks * H][okw_stride]
-    int okw_stride, nchunks;
+    const int2* seg;         // [nseg + 1] (first sorted position, source cell) of each segment; sentinel at the end
+    const int* tile_seg;     // [ntiles + 1] first segment of each tile
+    int nchunks;
     float* r_arr[FAST_MAX_SLABS];
+    int* new_pts[FAST_MAX_SLABS];
+    int* slow[FAST_MAX_SLABS];
 };
 
-constexpr int CELL_G = 4;    // consecutive cells per warp: their points are one contiguous run of the sorted list
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
 
-template <int LV>
+template <int LV, int TH>
 __global__ void __launch_bounds__(32, 16)
-k_metgrid_cell16(const __grid_constant__ Cell16Params P)
+k_metgrid_tile16(const __grid_constant__ Tile16Params P)
 {
     constexpr int PT = 32 / LV;                 // points in flight per warp
     constexpr int NL = 2 * LV;                  // levels per chunk
     constexpr int LS = NL + 1;                  // odd row stride of the staging tile: conflict-free for lanes = points
-    constexpr int PB = LV > 16 ? 32 : 64;       // points per batch
-    constexpr int NQ = PB / 32;                 // table entries a lane prefetches
+    constexpr int TP = 32 * TH;                 // points per tile
+    constexpr int PB = 32;                      // points per batch
     constexpr int PBX = PB + 2 * PT;            // table rows incl. the look-ahead of the pipelined loop
-    constexpr int H = LV > 16 ? 2 : 1;          // ok words per (chunk, point)
     __shared__ float4 s_x[PBX], s_y[PBX];       // {x, x, 1-x, 1-x}, {y, y, 1-y, 1-y}
-    __shared__ int s_meta[PBX];                 // point index | shift code << 29 (0: flag bits 0-3, 1: bits 4-7, 2: not a packed point)
-    __shared__ unsigned s_ok[(PB + PT) * H];
-    __shared__ float s_stg[(PB + PT) * LS];
+    __shared__ int s_meta[PBX];                 // point of the tile | shift code << 29 (0: flag bits 0-3, 1: bits 4-7, 2: not a packed point)
+    __shared__ unsigned s_ok[TP + 1];           // per point: ok bits of the even levels (low half) and odd levels (high half); [TP] = dump row
+    __shared__ float s_stg[(TP + 1) * LS];
+    __shared__ float4 s_rec[2][12 * LV];        // record of the current / next segment: [stencil row * 3 + k][level pair]
 
     const Job& jb = P.jb;
-    const int lane = threadIdx.x, chunk = blockIdx.y;
-    const int ncells = jb.bnx * jb.bny, c0 = blockIdx.x * CELL_G;
-    // first sorted position of the group's cells (lane g holds cell c0+g; lane CELL_G the end of the group)
-    const int cs = __ldg(P.cell_start + min(c0 + min(lane, CELL_G), ncells));
-    const int k_last = __shfl_sync(0xffffffffu, cs, CELL_G);
-    int kb = __shfl_sync(0xffffffffu, cs, 0);
-    if (k_last <= kb) return;
+    const int lane = threadIdx.x, chunk = blockIdx.y, tile = blockIdx.x;
+    const int tx = tile % jb.tiles_x, ty = tile / jb.tiles_x;
     const bool act = lane < LV * PT;
     const int pslot = act ? lane / LV : 0, lv = act ? lane % LV : 0;   // idle lanes shadow lane 0 (identical values, no ok bits)
-    const int nslab = jb.nslab, nx = jb.nx;
+    const int nslab = jb.nslab, nx = jb.nx, ny = jb.ny;
     const float msg = jb.msg;
-    const int npairs = 2 * jb.npack;
+    const int ncells = jb.bnx * jb.bny, npairs = 2 * jb.npack;
     const int gl = min(chunk * LV + lv, npairs - 1);   // level pair of this lane (clamped: lanes past the last pair idle)
     const int lvbit = (gl & 1) * 2;
     F2K k2;
@@ -637,189 +639,173 @@ k_metgrid_cell16(const __grid_constant__ Cell16Params P)
     const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
     const float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
 
-    // raw table entries of the coming batch, fetched one batch ahead (lanes = points)
-    int f_idx[NQ]; float2 f_xy[NQ]; float f_lm[NQ];
-    auto prefetch = [&](int k0) {
-#pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-            const int k = min(k0 + u * 32 + lane, k_last - 1);
-            f_idx[u] = __ldg(P.sidx + k);
-            f_xy[u] = __ldg(P.sxy + k);
-            f_lm[u] = P.slm != nullptr ? __ldg(P.slm + k) : 0.0f;
-        }
-    };
-    prefetch(kb);
+    for (int q = lane; q < TP + 1; q += 32) s_ok[q] = 0u;
 
-    float2 rb[4], rc[4], rt1[4], rt2[4], rt3[4], rt4[4];
-    unsigned cfbyte = 0;
-    int g = -1, cell_end = kb;
-    while (true) {
-        if (kb >= cell_end) {
-            // next non-empty cell of the group: its record, stencil rows j-1 .. j+2 (clamped like sixteen_pt, interp_module.F:1227-1241)
-            do { ++g; cell_end = __shfl_sync(0xffffffffu, cs, g + 1); } while (cell_end <= kb);
-            const int cell = c0 + g, ci = cell % jb.bnx, cj = cell / jb.bnx, j = jb.by0 + cj;
+    const int s_begin = __ldg(P.tile_seg + tile), s_end = __ldg(P.tile_seg + tile + 1);
+    if (s_end > s_begin) {
+        const int k_last = __ldg(&P.seg[s_end].x);   // end of the tile's run of the sorted list
+        // raw table entries of the coming batch, fetched one batch ahead (lanes = points)
+        int f_idx; float2 f_xy; float f_lm;
+        auto prefetch = [&](int k0) {
+            const int k = min(k0 + lane, k_last - 1);
+            f_idx = __ldg(P.sidx + k);
+            f_xy = __ldg(P.sxy + k);
+            f_lm = P.slm != nullptr ? __ldg(P.slm + k) : 0.0f;
+        };
+        // record of a cell -> shared memory (lanes of point slot 0, one level pair each), stencil rows j-1 .. j+2
+        // clamped like sixteen_pt (interp_module.F:1227-1241)
+        auto fetch_record = [&](int cell, int buf) {
+            if (lane < LV) {
+                const int ci = cell % jb.bnx, cj = cell / jb.bnx, j = jb.by0 + cj;
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    int r = min(max(j + l - 1, jb.miny), jb.maxy) - jb.by0;
+                    r = min(max(r, 0), jb.bny - 1);
+                    const float4* rp = jb.rec + (((size_t)r * jb.bnx + ci) * npairs + gl) * 3;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cp_async16(&s_rec[buf][(l * 3 + k) * LV + lv], rp + k);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto load_cf = [&](int cell) -> unsigned {
+            unsigned v;
+            // (volatile asm: a read-only load would be re-issued inside the point loop instead of being kept in a register)
+            asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(jb.cf + (size_t)(gl >> 1) * ncells + cell));
+            return v;
+        };
+
+        int2 sg = __ldg(P.seg + s_begin);          // (first position, cell) of the current segment
+        int kb = sg.x;
+        prefetch(kb);
+        fetch_record(sg.y, 0);
+        unsigned cf_next = load_cf(sg.y);
+        float2 rb[4], rc[4], rt1[4], rt2[4], rt3[4], rt4[4];
+        for (int s = s_begin; s < s_end; ++s) {
+            const int buf = (s - s_begin) & 1;
+            const int2 sgn = __ldg(P.seg + s + 1);  // next segment (or the sentinel)
+            const int seg_end = sgn.x;
+            // ---- this segment's record: shared memory -> registers; start fetching the next one ----
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
 #pragma unroll
             for (int l = 0; l < 4; ++l) {
-                int r = min(max(j + l - 1, jb.miny), jb.maxy) - jb.by0;
-                r = min(max(r, 0), jb.bny - 1);
-                const float4* rp = jb.rec + (((size_t)r * jb.bnx + ci) * npairs + gl) * 3;
-                float4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2);
+                const float4 q0 = s_rec[buf][(l * 3 + 0) * LV + lv], q1 = s_rec[buf][(l * 3 + 1) * LV + lv], q2 = s_rec[buf][(l * 3 + 2) * LV + lv];
                 rb[l] = make_float2(q0.x, q0.y); rc[l] = make_float2(q0.z, q0.w);
                 rt1[l] = make_float2(q1.x, q1.y); rt2[l] = make_float2(q1.z, q1.w);
                 rt3[l] = make_float2(q2.x, q2.y); rt4[l] = make_float2(q2.z, q2.w);
             }
-            // (volatile asm: a read-only load would be re-issued inside the point loop instead of being kept in a register)
-            asm volatile("ld.global.u8 %0, [%1];" : "=r"(cfbyte) : "l"(jb.cf + (size_t)(gl >> 1) * ncells + cell));
-            if (!act) cfbyte = 0u;
-        }
-        const int n = min(PB, cell_end - kb);
-        // ---- point table (lanes = points): level-independent part of interp_met_field's point logic (:2490-2541) ----
-#pragma unroll
-        for (int u = 0; u < NQ; ++u) {
-            const int q = u * 32 + lane;
-            const int idx = f_idx[u];
-            const float xx = f_xy[u].x, yy = f_xy[u].y, lm = f_lm[u];
-            const int ii = idx % nx, jj = idx / nx;
-            const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
-            const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
-            int code = 0;
-            bool valid = q < n && !in_fill;
-            if (both) { code = lm == 1.0f ? 1 : 0; valid = valid && (lm == 0.0f || lm == 1.0f); }
-            else if (jb.landmask != nullptr && lm == jb.masked) valid = false;
-            valid = valid && xx >= lo && xx <= hi;
-            const int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
-            float x = xx - (float)i, y = yy - (float)j;
-            if (!valid) { code = 2; x = 0.5f; y = 0.5f; }
-            s_x[q] = make_float4(x, x, 1.0f - x, 1.0f - x);
-            s_y[q] = make_float4(y, y, 1.0f - y, 1.0f - y);
-            s_meta[q] = idx | (code << 29);
-        }
-        if (lane < PT) {   // rows past the batch that the last loop iteration touches
-            s_x[PB + lane] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-            s_y[PB + lane] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-            s_meta[PB + lane] = 2 << 29;
-        }
-        __syncwarp();
-        const int kb_next = kb + n;
-        if (kb_next < k_last) prefetch(kb_next);
-        // ---- arithmetic (lanes = level pairs x point slots), table reads one iteration ahead ----
-        float4 X = s_x[pslot], Y = s_y[pslot];
-        int meta = s_meta[pslot];
+            const unsigned cfbyte = act ? cf_next : 0u;
+            if (s + 1 < s_end) { fetch_record(sgn.y, buf ^ 1); cf_next = load_cf(sgn.y); }
+            while (kb < seg_end) {
+                const int n = min(PB, seg_end - kb);
+                // ---- point table (lanes = points): level-independent part of interp_met_field's point logic (:2490-2541) ----
+                {
+                    const int idx = f_idx;
+                    const float xx = f_xy.x, yy = f_xy.y, lm = f_lm;
+                    const int ii = idx % nx, jj = idx / nx;
+                    const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
+                    const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+                    int code = 0;
+                    bool valid = lane < n && !in_fill;
+                    if (both) { code = lm == 1.0f ? 1 : 0; valid = valid && (lm == 0.0f || lm == 1.0f); }
+                    else if (jb.landmask != nullptr && lm == jb.masked) valid = false;
+                    valid = valid && xx >= lo && xx <= hi;
+                    const int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
+                    float x = xx - (float)i, y = yy - (float)j;
+                    int lp = (jj - ty * TH) * 32 + (ii - tx * 32);
+                    if (!valid) { code = 2; x = 0.5f; y = 0.5f; lp = TP; }   // results of such rows go to the dump row
+                    s_x[lane] = make_float4(x, x, 1.0f - x, 1.0f - x);
+                    s_y[lane] = make_float4(y, y, 1.0f - y, 1.0f - y);
+                    s_meta[lane] = lp | (code << 29);
+                }
+                if (lane < PT) {   // rows past the batch that the last loop iteration touches
+                    s_x[PB + lane] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                    s_y[PB + lane] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+                    s_meta[PB + lane] = TP | (2 << 29);
+                }
+                __syncwarp();
+                const int kb_next = kb + n;
+                if (kb_next < k_last) prefetch(kb_next);
+                // ---- arithmetic (lanes = level pairs x point slots), table reads one iteration ahead ----
+                float4 X = s_x[pslot], Y = s_y[pslot];
+                int meta = s_meta[pslot];
 #pragma unroll 2
-        for (int p0 = 0; p0 < n; p0 += PT) {
-            const int p = p0 + pslot;
-            const float4 Xn = s_x[p + PT], Yn = s_y[p + PT];
-            const int metan = s_meta[p + PT];
-            const int sh = (meta >> 29) * 4;
-            const float2 x2 = make_float2(X.x, X.y), omx2 = make_float2(X.z, X.w), y2 = make_float2(Y.x, Y.y), omy2 = make_float2(Y.z, Y.w);
-            float2 r[4];
+                for (int p0 = 0; p0 < n; p0 += PT) {
+                    const int p = p0 + pslot;
+                    const float4 Xn = s_x[p + PT], Yn = s_y[p + PT];
+                    const int metan = s_meta[p + PT];
+                    const int sh = (meta >> 29) * 4, lp = meta & 0x1fffffff;
+                    const float2 x2 = make_float2(X.x, X.y), omx2 = make_float2(X.z, X.w), y2 = make_float2(Y.x, Y.y), omy2 = make_float2(Y.z, Y.w);
+                    float2 r[4];
 #pragma unroll
-            for (int l = 0; l < 4; ++l) r[l] = xpass2(rb[l], rc[l], rt1[l], rt2[l], rt3[l], rt4[l], x2, omx2, k2);
-            float2 v = ypass2(r[0], r[1], r[2], r[3], y2, omy2, k2);
-            // oned's own guards in the y direction: general branch only when b*c /= 0 and a*d /= 0
-            const float2 bc = mul2(r[1], r[2], k2), ad = mul2(r[0], r[3], k2);
-            if (v.x == 1.0e-20f) v.x = 0.0f;
-            if (v.y == 1.0e-20f) v.y = 0.0f;
-            const unsigned cfb = (cfbyte >> sh) >> lvbit;   // sh = 8 (not a packed point, or a row past the batch): no bits
-            const bool ok0 = (cfb & 1u) && bc.x != 0.0f && ad.x != 0.0f && v.x != msg;
-            const bool ok1 = (cfb & 2u) && bc.y != 0.0f && ad.y != 0.0f && v.y != msg;
-            s_stg[p * LS + 2 * lv] = v.x; s_stg[p * LS + 2 * lv + 1] = v.y;
-            const unsigned w0 = __ballot_sync(0xffffffffu, ok0), w1 = __ballot_sync(0xffffffffu, ok1);
-            if (lv == 0) {
-                if (H == 2) { s_ok[2 * p] = w0; s_ok[2 * p + 1] = w1; }
-                else {
-                    const unsigned m = (1u << (LV & 31)) - 1u;
-                    s_ok[p] = ((w0 >> (pslot * LV)) & m) | (((w1 >> (pslot * LV)) & m) << 16);
+                    for (int l = 0; l < 4; ++l) r[l] = xpass2(rb[l], rc[l], rt1[l], rt2[l], rt3[l], rt4[l], x2, omx2, k2);
+                    float2 v = ypass2(r[0], r[1], r[2], r[3], y2, omy2, k2);
+                    // oned's own guards in the y direction: general branch only when b*c /= 0 and a*d /= 0
+                    const float2 bc = mul2(r[1], r[2], k2), ad = mul2(r[0], r[3], k2);
+                    if (v.x == 1.0e-20f) v.x = 0.0f;
+                    if (v.y == 1.0e-20f) v.y = 0.0f;
+                    const unsigned cfb = (cfbyte >> sh) >> lvbit;   // sh = 8 (not a packed point, or a row past the batch): no bits
+                    const bool ok0 = (cfb & 1u) && bc.x != 0.0f && ad.x != 0.0f && v.x != msg;
+                    const bool ok1 = (cfb & 2u) && bc.y != 0.0f && ad.y != 0.0f && v.y != msg;
+                    s_stg[lp * LS + 2 * lv] = v.x; s_stg[lp * LS + 2 * lv + 1] = v.y;
+                    const unsigned w0 = __ballot_sync(0xffffffffu, ok0), w1 = __ballot_sync(0xffffffffu, ok1);
+                    if (lv == 0) {
+                        const unsigned m = (1u << LV) - 1u;
+                        s_ok[lp] = ((w0 >> (pslot * LV)) & m) | (((w1 >> (pslot * LV)) & m) << 16);
+                    }
+                    X = Xn; Y = Yn; meta = metan;
                 }
+                __syncwarp();
+                kb = kb_next;
             }
-            X = Xn; Y = Yn; meta = metan;
+            sg = sgn;
         }
-        __syncwarp();
-        // ---- write-out (lanes = points: consecutive x inside the cell) ----
-        for (int p0 = 0; p0 < n; p0 += 32) {
-            const int p = p0 + lane;
-            if (p < n) {
-                const int idx = s_meta[p] & 0x1fffffff;
-                unsigned o0, o1;
-                if (H == 2) { o0 = s_ok[2 * p]; o1 = s_ok[2 * p + 1]; } else { o0 = s_ok[p] & 0xffffu; o1 = s_ok[p] >> 16; }
-                const size_t kpos = (size_t)(kb + p);
-                if (H == 2) { P.okw[(size_t)(2 * chunk) * P.okw_stride + kpos] = o0; P.okw[(size_t)(2 * chunk + 1) * P.okw_stride + kpos] = o1; }
-                else P.okw[(size_t)chunk * P.okw_stride + kpos] = o0 | (o1 << 16);
-                const float* st = s_stg + p * LS;
-#pragma unroll
-                for (int L = 0; L < NL; ++L) {
-                    const int sl = chunk * NL + L;
-                    if (sl < nslab && (((L & 1) ? o1 : o0) >> (L >> 1) & 1u)) P.r_arr[sl][idx] = st[L];
-                }
-            }
-        }
-        __syncwarp();
-        if (kb_next >= k_last) break;
-        kb = kb_next;
     }
-}
-
-// Bitmap words of the cell-major path: one warp per 32 consecutive x points.  ok bit of (point, level) from okw via the
-// inverse permutation; points outside the cell index have none.  The level-independent fill rules of interp_met_field
-// (process_bdy_width interior :2490-2495, landmask == masked :2527-2530) are applied here with coalesced stores.
-struct Words16Params {
-    Job jb;
-    const int* pos;
-    const unsigned* okw;
-    int okw_stride, nchunks, lv, n_fast;
-    float* r_arr[FAST_MAX_SLABS];
-    int* new_pts[FAST_MAX_SLABS];
-    int* slow[FAST_MAX_SLABS];
-};
-
-__global__ void __launch_bounds__(256)
-k_cell16_words(const __grid_constant__ Words16Params P)
-{
-    const Job& jb = P.jb;
-    const int nx = jb.nx, ny = jb.ny;
-    const int tx = blockIdx.x % jb.tiles_x, ty = blockIdx.x / jb.tiles_x;
-    const int ii = tx * TILE_X + threadIdx.x, jj = ty * TILE_Y + threadIdx.y;
-    if (jj >= ny) return;
+    __syncwarp();
+    // ---- write-out (lanes = 32 consecutive x): full lines, bitmap words by ballot; level-independent fill rules of
+    // interp_met_field (process_bdy_width interior :2490-2495, landmask == masked :2527-2530) ----
+    const int ii = tx * 32 + lane;
     const bool active = ii < nx;
-    const size_t idx = (size_t)jj * nx + min(ii, nx - 1);
-    const size_t widx = (size_t)jj * jb.nxw + tx;
-    const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
-    bool fillpt = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
-    if (jb.landmask != nullptr && jb.masked != WPSGPU_MASKED_BOTH) fillpt = fillpt || __ldg(jb.landmask + idx) == jb.masked;
-    fillpt = fillpt && active;
-    const int kpos = __ldg(P.pos + idx);
-    const bool fast = active && !fillpt && kpos < P.n_fast;
-    const int LV = P.lv, NL = 2 * LV, H = LV > 16 ? 2 : 1;
     const float fill = jb.fill;
-    for (int c = 0; c < P.nchunks; ++c) {
-        unsigned o0 = 0, o1 = 0;
-        if (fast) {
-            if (H == 2) { o0 = __ldg(P.okw + (size_t)(2 * c) * P.okw_stride + kpos); o1 = __ldg(P.okw + (size_t)(2 * c + 1) * P.okw_stride + kpos); }
-            else { unsigned w = __ldg(P.okw + (size_t)c * P.okw_stride + kpos); o0 = w & 0xffffu; o1 = w >> 16; }
-        }
+#pragma unroll 1
+    for (int row = 0; row < TH; ++row) {
+        const int jj = ty * TH + row;
+        if (jj >= ny) break;
+        const size_t idx = (size_t)jj * nx + min(ii, nx - 1);
+        const size_t widx = (size_t)jj * jb.nxw + tx;
+        const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
+        bool fillpt = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+        if (jb.landmask != nullptr && !both) fillpt = fillpt || __ldg(jb.landmask + idx) == jb.masked;
+        fillpt = fillpt && active;
+        const int lp = row * 32 + lane;
+        const unsigned okm = active ? s_ok[lp] : 0u;
+        const float* st = s_stg + lp * LS;
+#pragma unroll
         for (int L = 0; L < NL; ++L) {
-            const int sl = c * NL + L;
-            if (sl >= jb.nslab) break;
-            const bool ok = fillpt || ((((L & 1) ? o1 : o0) >> (L >> 1)) & 1u);
-            if (fillpt) P.r_arr[sl][idx] = fill;
+            const int sl = chunk * NL + L;
+            if (sl >= nslab) break;
+            const bool ok = fillpt || ((okm >> ((L & 1) * 16 + (L >> 1))) & 1u);
+            const float v = fillpt ? fill : st[L];
+            if (ok) P.r_arr[sl][idx] = v;
             const unsigned word = __ballot_sync(0xffffffffu, ok), sword = __ballot_sync(0xffffffffu, active && !ok);
-            if (threadIdx.x == 0) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
+            if (lane == 0) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
         }
     }
 }
 
-// ---- cell index: destination points sorted by source cell ---------------------------------------------------------
-// key = cell number inside the record box for points the packed path can take (the level- and job-independent part of
-// the old kernel's `fastpt` test: interior of the array by sixteen_pt's truncation test :1211, not on a node :1301,
-// stencil rows inside the box), ncells for every other point.
-__global__ void k_cell_keys(const float2* __restrict__ xy, int n, int minx, int maxx, int miny, int maxy, int bx0, int by0, int bnx, int bny,
-                            int* __restrict__ keys, int* __restrict__ vals)
+// ---- tile index: destination points sorted by (destination tile, source cell) ------------------------------------
+// key = tile * ncells + cell for points the packed path can take (the level- and job-independent part of the
+// point-major kernel's `fastpt` test: interior of the array by sixteen_pt's truncation test :1211, not on a node :1301,
+// stencil rows inside the box), the largest key for every other point.
+__global__ void k_tile_keys(const float2* __restrict__ xy, int n, int nx, int tiles_x, int th, int minx, int maxx, int miny, int maxy,
+                            int bx0, int by0, int bnx, int bny, unsigned long long nokey, unsigned long long* __restrict__ keys, int* __restrict__ vals)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float2 p = __ldg(xy + k);
     const float xx = p.x, yy = p.y;
-    int key = bnx * bny;
+    unsigned long long key = nokey;
     if (fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f && (int)xx >= minx && (int)xx <= maxx && (int)yy >= miny && (int)yy <= maxy) {
         const int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
         const float x = xx - (float)i, y = yy - (float)j;
@@ -830,23 +816,13 @@ __global__ void k_cell_keys(const float2* __restrict__ xy, int n, int minx, int 
                 int r = min(max(j + l - 1, miny), maxy) - by0;
                 if (r < 0 || r >= bny) okr = false;
             }
-            if (okr) key = (j - by0) * bnx + (i - bx0);
+            const int ii = k % nx, jj = k / nx;
+            const int tile = (jj / th) * tiles_x + ii / 32;
+            if (okr) key = (unsigned long long)tile * (unsigned long long)(bnx * bny) + (unsigned long long)((j - by0) * bnx + (i - bx0));
         }
     }
     keys[k] = key;
     vals[k] = k;
-}
-
-__global__ void k_cell_bounds(const int* __restrict__ skeys, int n, int ncells, int* __restrict__ cell_start)
-{
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > ncells) return;
-    int lo = 0, hi = n;   // first position whose key >= c
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (__ldg(skeys + mid) < c) lo = mid + 1; else hi = mid;
-    }
-    cell_start[c] = lo;
 }
 
 __global__ void k_cell_gather_xy(const int* __restrict__ sidx, const float2* __restrict__ xy, int n, float2* __restrict__ sxy)
@@ -859,12 +835,6 @@ __global__ void k_cell_gather_f(const int* __restrict__ sidx, const float* __res
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) out[k] = __ldg(a + __ldg(sidx + k));
-}
-
-__global__ void k_cell_pos(const int* __restrict__ sidx, int n, int* __restrict__ pos)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) pos[sidx[k]] = k;
 }
 
 // ---- four_pt / nearest_neighbor first-method kernel ------------------------------------------------------------
@@ -1155,84 +1125,108 @@ static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
 }
 
 
-// level pairs per warp of the cell-major kernel: cost model = chunks x (fixed work per cell and chunk + loop iterations),
-// with the fixed part (record loads, point table, write-out set-up) worth about six iterations
-static const int kCellLV[] = { 1, 2, 4, 6, 8, 10, 16, 32 };
-static void choose_cell_lv(int nslab, double pts_per_cell, int* lv, int* chunks)
+// Lane shape of the tile-major kernel: LV level pairs x 32/LV point slots per warp, tile height so that the staging tile
+// stays near 13 KB.  Score = lanes with real levels x how well a segment's points fill the point slots x share of the
+// per-segment set-up (worth about 1.5 loop iterations).
+static const int kTileLV[] = { 2, 4, 6, 8 };
+static int tile_th(int LV) { return LV == 2 ? 16 : (LV == 4 ? 12 : (LV == 6 ? 8 : 6)); }
+static void choose_tile_lv(int nslab, double pts_per_cell, int* lv, int* chunks)
 {
     const int npairs = (nslab + 1) / 2;
-    double best = 1e300;
-    for (int LV : kCellLV) {
-        const int PT = 32 / LV, ch = (npairs + LV - 1) / LV;
-        double cost = ch * (6.0 + ceil(pts_per_cell / PT));
-        if (cost < best - 1e-9 || (cost < best + 1e-9 && LV > *lv)) { best = cost; *lv = LV; *chunks = ch; }
+    const double cw = std::max(1.0, sqrt(pts_per_cell));
+    double best = -1.0;
+    for (int LV : kTileLV) {
+        const int PT = 32 / LV, ch = (npairs + LV - 1) / LV, TH = tile_th(LV);
+        const double ppv = 32.0 * TH / ((32.0 / cw + 1.0) * (TH / cw + 1.0));
+        const double util = (double)nslab / (ch * 2.0 * LV) * (LV * PT / 32.0);
+        const double score = util * ppv / (PT * ceil(ppv / PT)) * ppv / (ppv + 1.5 * PT);
+        if (score > best) { best = score; *lv = LV; *chunks = ch; }
     }
 }
 
-// Destination points sorted by source cell, cached with the coordinate set (CellIndex in ctx.h)
-static int get_cell_index(wpsgpu_ctx* h, CoordCacheEntry& e, int npts, const int dims[8], CellIndex* out)
+// Destination points sorted by (tile, source cell), cached with the coordinate set (TileIndex in ctx.h)
+static int get_tile_index(wpsgpu_ctx* h, CoordCacheEntry& e, int nx, int ny, const int dims[9], TileIndex* out)
 {
-    for (const CellIndex& c : e.cidx)
+    for (const TileIndex& c : e.tidx)
         if (!memcmp(c.dims, dims, sizeof(c.dims))) { *out = c; return 0; }
-    if (e.cidx.size() >= 4) {   // other source extents seen through the same projection: keep the cache small
+    if (e.tidx.size() >= 8) {   // other source extents seen through the same projection: keep the cache small
         WPS_CUDA(cudaStreamSynchronize(h->stream));
-        CellIndex& o = e.cidx.front();
-        cudaFree(o.d_sidx); cudaFree(o.d_pos); cudaFree(o.d_cell_start); cudaFree(o.d_sxy);
-        e.cidx.erase(e.cidx.begin());
+        TileIndex& o = e.tidx.front();
+        cudaFree(o.d_sidx); cudaFree(o.d_sxy); cudaFree(o.d_seg); cudaFree(o.d_tile_seg);
+        e.tidx.erase(e.tidx.begin());
     }
-    CellIndex c;
+    TileIndex c;
     memcpy(c.dims, dims, sizeof(c.dims));
-    const int ncells = dims[6] * dims[7];
-    int *d_keys = nullptr, *d_vals = nullptr, *d_skeys = nullptr;
+    const int npts = nx * ny, th = dims[8], ncells = dims[6] * dims[7];
+    const int tiles_x = (nx + 31) / 32, tiles_y = (ny + th - 1) / th;
+    c.ntiles = tiles_x * tiles_y;
+    const unsigned long long nokey = (unsigned long long)c.ntiles * (unsigned long long)ncells;
+    unsigned long long *d_keys = nullptr, *d_skeys = nullptr;
+    int *d_vals = nullptr, *d_svals = nullptr;
     void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
-    WPS_CUDA(cudaMalloc((void**)&d_keys, sizeof(int) * (size_t)npts));
+    WPS_CUDA(cudaMalloc((void**)&d_keys, sizeof(unsigned long long) * (size_t)npts));
+    WPS_CUDA(cudaMalloc((void**)&d_skeys, sizeof(unsigned long long) * (size_t)npts));
     WPS_CUDA(cudaMalloc((void**)&d_vals, sizeof(int) * (size_t)npts));
-    WPS_CUDA(cudaMalloc((void**)&d_skeys, sizeof(int) * (size_t)npts));
-    WPS_CUDA(cudaMalloc((void**)&c.d_sidx, sizeof(int) * (size_t)npts));
-    WPS_CUDA(cudaMalloc((void**)&c.d_pos, sizeof(int) * (size_t)npts));
-    WPS_CUDA(cudaMalloc((void**)&c.d_cell_start, sizeof(int) * (size_t)(ncells + 1)));
-    k_cell_keys<<<(npts + 255) / 256, 256, 0, h->stream>>>(e.d_xy, npts, dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], d_keys, d_vals);
+    WPS_CUDA(cudaMalloc((void**)&d_svals, sizeof(int) * (size_t)npts));
+    k_tile_keys<<<(npts + 255) / 256, 256, 0, h->stream>>>(e.d_xy, npts, nx, tiles_x, th, dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7],
+                                                           nokey, d_keys, d_vals);
     int bits = 1;
-    while ((1ll << bits) <= ncells) ++bits;
-    WPS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_skeys, d_vals, c.d_sidx, npts, 0, bits, h->stream));
+    while (bits < 64 && (1ull << bits) <= nokey) ++bits;
+    WPS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_skeys, d_vals, d_svals, npts, 0, bits, h->stream));
     WPS_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
-    WPS_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_skeys, d_vals, c.d_sidx, npts, 0, bits, h->stream));   // stable: index order inside a cell
-    k_cell_bounds<<<(ncells + 1 + 255) / 256, 256, 0, h->stream>>>(d_skeys, npts, ncells, c.d_cell_start);
-    k_cell_pos<<<(npts + 255) / 256, 256, 0, h->stream>>>(c.d_sidx, npts, c.d_pos);
-    h->launches += 3;
+    WPS_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_skeys, d_vals, d_svals, npts, 0, bits, h->stream));   // stable: index order inside a segment
+    h->launches += 2;
     WPS_CUDA(cudaGetLastError());
-    std::vector<int> starts((size_t)ncells + 1);
-    WPS_CUDA(cudaMemcpyAsync(starts.data(), c.d_cell_start, sizeof(int) * (size_t)(ncells + 1), cudaMemcpyDeviceToHost, h->stream));
+    // segments and the tiles' first segments: one linear pass on the host (once per coordinate set)
+    std::vector<unsigned long long> keys((size_t)npts);
+    WPS_CUDA(cudaMemcpyAsync(keys.data(), d_skeys, sizeof(unsigned long long) * (size_t)npts, cudaMemcpyDeviceToHost, h->stream));
     WPS_CUDA(cudaStreamSynchronize(h->stream));
-    c.n_fast = starts[ncells];
-    c.n_cells_used = 0;
-    for (int k = 0; k < ncells; ++k) c.n_cells_used += starts[k + 1] > starts[k];
-    WPS_CUDA(cudaMalloc((void**)&c.d_sxy, sizeof(float2) * (size_t)std::max(c.n_fast, 1)));
-    if (c.n_fast > 0) {
-        k_cell_gather_xy<<<(c.n_fast + 255) / 256, 256, 0, h->stream>>>(c.d_sidx, e.d_xy, c.n_fast, c.d_sxy);
+    std::vector<int2> seg;
+    std::vector<int> tile_seg((size_t)c.ntiles + 1, 0);
+    int n_fast = 0, next_tile = 0;
+    for (; n_fast < npts && keys[n_fast] < nokey; ++n_fast) {
+        if (n_fast == 0 || keys[n_fast] != keys[n_fast - 1]) {
+            const int tile = (int)(keys[n_fast] / (unsigned long long)ncells), cell = (int)(keys[n_fast] % (unsigned long long)ncells);
+            while (next_tile <= tile) tile_seg[next_tile++] = (int)seg.size();
+            seg.push_back(make_int2(n_fast, cell));
+        }
+    }
+    while (next_tile <= c.ntiles) tile_seg[next_tile++] = (int)seg.size();
+    c.n_fast = n_fast;
+    c.nseg = (int)seg.size();
+    seg.push_back(make_int2(n_fast, 0));
+    WPS_CUDA(cudaMalloc((void**)&c.d_sidx, sizeof(int) * (size_t)std::max(n_fast, 1)));
+    WPS_CUDA(cudaMalloc((void**)&c.d_sxy, sizeof(float2) * (size_t)std::max(n_fast, 1)));
+    WPS_CUDA(cudaMalloc((void**)&c.d_seg, sizeof(int2) * seg.size()));
+    WPS_CUDA(cudaMalloc((void**)&c.d_tile_seg, sizeof(int) * tile_seg.size()));
+    WPS_CUDA(cudaMemcpyAsync(c.d_seg, seg.data(), sizeof(int2) * seg.size(), cudaMemcpyHostToDevice, h->stream));
+    WPS_CUDA(cudaMemcpyAsync(c.d_tile_seg, tile_seg.data(), sizeof(int) * tile_seg.size(), cudaMemcpyHostToDevice, h->stream));
+    if (n_fast > 0) {
+        WPS_CUDA(cudaMemcpyAsync(c.d_sidx, d_svals, sizeof(int) * (size_t)n_fast, cudaMemcpyDeviceToDevice, h->stream));
+        k_cell_gather_xy<<<(n_fast + 255) / 256, 256, 0, h->stream>>>(c.d_sidx, e.d_xy, n_fast, c.d_sxy);
         h->launches++;
         WPS_CUDA(cudaGetLastError());
-        WPS_CUDA(cudaStreamSynchronize(h->stream));
     }
-    cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_skeys); cudaFree(d_tmp);
-    e.cidx.push_back(c);
+    WPS_CUDA(cudaStreamSynchronize(h->stream));   // seg / tile_seg are pageable host vectors
+    cudaFree(d_keys); cudaFree(d_skeys); cudaFree(d_vals); cudaFree(d_svals); cudaFree(d_tmp);
+    e.tidx.push_back(c);
     *out = c;
     return 0;
 }
 
-template <int LV>
-static int launch_cell16(const Cell16Params& cp, int ncells, cudaStream_t st)
+template <int LV, int TH>
+static int launch_tile16(const Tile16Params& tp, cudaStream_t st)
 {
     static bool carved = false;
     if (!carved) {
-        WPS_CUDA(cudaFuncSetAttribute(k_metgrid_cell16<LV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        WPS_CUDA(cudaFuncSetAttribute(k_metgrid_tile16<LV, TH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         carved = true;
     }
-    k_metgrid_cell16<LV><<<dim3((unsigned)((ncells + CELL_G - 1) / CELL_G), (unsigned)cp.nchunks), 32, 0, st>>>(cp);
+    const int tiles = tp.jb.tiles_x * ((tp.jb.ny + TH - 1) / TH);
+    k_metgrid_tile16<LV, TH><<<dim3((unsigned)tiles, (unsigned)tp.nchunks), 32, 0, st>>>(tp);
     return 0;
 }
-
 
 }  // namespace wps
 
@@ -1383,7 +1377,7 @@ int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float* ms3, double* points3)
 
 // One pass over a subset of the job groups: stage inputs on s_in, compute on the handle's stream, copy results back
 // on s_out.  In device-pointer mode all three are the handle's stream and nothing is copied.
-struct Box { int fast, bx0, by0, bnx, bny, npack; int cell_lv, cell_chunks; CellIndex cidx; };   // cell_lv > 0: cell-major kernel
+struct Box { int fast, bx0, by0, bnx, bny, npack; int tile_lv, tile_chunks; TileIndex tidx; };   // tile_lv > 0: tile-major kernel
 struct FlushShared {
     std::vector<QueuedSlab>* queue;
     std::vector<std::vector<int>>* groups;
@@ -1504,7 +1498,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         jb.f_negzero = -0.0f; jb.f_one = 1.0f;
         jb.gcell = q0.gcell ? 1 : 0;
         jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
-        jb.cellmajor = bx.fast == 1 && bx.cell_lv > 0;
+        jb.cellmajor = bx.fast == 1 && bx.tile_lv > 0;
         if (jb.fast == 1) {
             size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
             size_t cells8 = (size_t)jb.npack * ((jb.bnx + 7) / 8 * 8) * jb.bny;
@@ -1758,44 +1752,29 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
         }
         const Box& bx = fs.box[gsel[j]];
-        if (bx.cell_lv > 0) {
-            const int H = bx.cell_lv > 16 ? 2 : 1, stride = (bx.cidx.n_fast + 63) & ~63;
-            unsigned* okw = (unsigned*)h->arena.take(sizeof(unsigned) * (size_t)std::max(stride, 64) * bx.cell_chunks * H);
-            WPS_CHECK(okw != nullptr, -3, "device arena exhausted (cell-major ok words)");
-            Cell16Params cp;
-            cp.jb = fp.jb; cp.sidx = bx.cidx.d_sidx; cp.sxy = bx.cidx.d_sxy; cp.slm = nullptr;
-            cp.cell_start = bx.cidx.d_cell_start; cp.okw = okw; cp.okw_stride = stride; cp.nchunks = bx.cell_chunks;
-            if (fp.jb.landmask != nullptr && bx.cidx.n_fast > 0) {   // landmask in sorted order, gathered once per flush and index
-                auto key = std::make_pair((const void*)fp.jb.landmask, (const void*)bx.cidx.d_sidx);
+        if (bx.tile_lv > 0) {
+            Tile16Params tp;
+            tp.jb = fp.jb; tp.sidx = bx.tidx.d_sidx; tp.sxy = bx.tidx.d_sxy; tp.slm = nullptr;
+            tp.seg = bx.tidx.d_seg; tp.tile_seg = bx.tidx.d_tile_seg; tp.nchunks = bx.tile_chunks;
+            memcpy(tp.r_arr, fp.r_arr, sizeof(tp.r_arr)); memcpy(tp.new_pts, fp.new_pts, sizeof(tp.new_pts)); memcpy(tp.slow, fp.slow, sizeof(tp.slow));
+            if (fp.jb.landmask != nullptr && bx.tidx.n_fast > 0) {   // landmask in sorted order, gathered once per flush and index
+                auto key = std::make_pair((const void*)fp.jb.landmask, (const void*)bx.tidx.d_sidx);
                 auto it = fs.sorted_lm.find(key);
                 if (it == fs.sorted_lm.end()) {
-                    float* d = (float*)h->arena.take(sizeof(float) * (size_t)bx.cidx.n_fast);
+                    float* d = (float*)h->arena.take(sizeof(float) * (size_t)bx.tidx.n_fast);
                     WPS_CHECK(d != nullptr, -3, "device arena exhausted (sorted landmask)");
-                    k_cell_gather_f<<<(bx.cidx.n_fast + 255) / 256, 256, 0, h->stream>>>(bx.cidx.d_sidx, fp.jb.landmask, bx.cidx.n_fast, d);
+                    k_cell_gather_f<<<(bx.tidx.n_fast + 255) / 256, 256, 0, h->stream>>>(bx.tidx.d_sidx, fp.jb.landmask, bx.tidx.n_fast, d);
                     h->launches++;
                     it = fs.sorted_lm.insert(std::make_pair(key, d)).first;
                 }
-                cp.slm = it->second;
+                tp.slm = it->second;
             }
-            memcpy(cp.r_arr, fp.r_arr, sizeof(cp.r_arr));
-            const int ncells = bx.bnx * bx.bny;
-            if (bx.cidx.n_fast > 0) {
-                switch (bx.cell_lv) {
-                case 1: WPS_TRY(launch_cell16<1>(cp, ncells, h->stream)); break;
-                case 2: WPS_TRY(launch_cell16<2>(cp, ncells, h->stream)); break;
-                case 4: WPS_TRY(launch_cell16<4>(cp, ncells, h->stream)); break;
-                case 6: WPS_TRY(launch_cell16<6>(cp, ncells, h->stream)); break;
-                case 8: WPS_TRY(launch_cell16<8>(cp, ncells, h->stream)); break;
-                case 10: WPS_TRY(launch_cell16<10>(cp, ncells, h->stream)); break;
-                case 16: WPS_TRY(launch_cell16<16>(cp, ncells, h->stream)); break;
-                default: WPS_TRY(launch_cell16<32>(cp, ncells, h->stream)); break;
-                }
-                h->launches++;
+            switch (bx.tile_lv) {
+            case 2: WPS_TRY((launch_tile16<2, 16>(tp, h->stream))); break;
+            case 4: WPS_TRY((launch_tile16<4, 12>(tp, h->stream))); break;
+            case 6: WPS_TRY((launch_tile16<6, 8>(tp, h->stream))); break;
+            default: WPS_TRY((launch_tile16<8, 6>(tp, h->stream))); break;
             }
-            Words16Params wp;
-            wp.jb = fp.jb; wp.pos = bx.cidx.d_pos; wp.okw = okw; wp.okw_stride = stride; wp.nchunks = bx.cell_chunks; wp.lv = bx.cell_lv; wp.n_fast = bx.cidx.n_fast;
-            memcpy(wp.r_arr, fp.r_arr, sizeof(wp.r_arr)); memcpy(wp.new_pts, fp.new_pts, sizeof(wp.new_pts)); memcpy(wp.slow, fp.slow, sizeof(wp.slow));
-            k_cell16_words<<<fp.jb.tiles_x * fp.jb.tiles_y, dim3(TILE_X, TILE_Y), 0, h->stream>>>(wp);
             h->launches++;
         } else {
             k_metgrid_fast16<<<fp.jb.tiles_x * ((fp.jb.ny + F16_Y - 1) / F16_Y), dim3(TILE_X, F16_Y), 0, h->stream>>>(fp);
@@ -1959,7 +1938,7 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
     // landmask logic selects a single interp mask, i.e. not masked=both); sixteen_pt additionally needs the
     // source-cell bounding box to be small against the destination grid (source coarser than the domain).
     const bool subrect_enabled = env_int("WPSGPU_SUBRECT", 1, 0, 1) != 0;
-    const bool cell16_enabled = env_int("WPSGPU_CELL16", 1, 0, 1) != 0;   // 0: point-major packed kernel (k_metgrid_fast16)
+    const bool tile16_enabled = env_int("WPSGPU_TILE16", 0, 0, 1) != 0;   // 1: tile-major kernel (k_metgrid_tile16) instead of the point-major k_metgrid_fast16
     fs.sub.resize(njobs);
     size_t need = (size_t)njobs * (sizeof(Job) + 256) + (size_t)nq * sizeof(SlabPtrs) + (1 << 20);
     size_t defer_entries = 0;
@@ -1995,7 +1974,7 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         }
         Box& b = fs.box[g];
         b.fast = 0; b.bx0 = b.by0 = b.bnx = b.bny = b.npack = 0;
-        b.cell_lv = 0; b.cell_chunks = 0;
+        b.tile_lv = 0; b.tile_chunks = 0;
         const int* bb = &job_bbox[4 * g];
         bool simple_mask = !(q0.s.use_landmask && q0.fo.masked == WPSGPU_MASKED_BOTH);
         if (q0.gcell) {   // where_maps_to, sums, counts, decided bits
@@ -2009,12 +1988,12 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
                     b.fast = 1; b.bx0 = (int)x0; b.by0 = (int)y0; b.bnx = (int)(x1 - x0 + 1); b.bny = (int)(y1 - y0 + 1);
                     b.npack = ((int)groups[g].size() + 3) / 4;
                     need += (size_t)b.npack * (b.bnx + 8) * b.bny * (6 * sizeof(float4) + 1) + 1024;
-                    if (cell16_enabled && dg.npts() < (size_t(1) << 29)) {
-                        const int dims[8] = { q0.s.minx, q0.s.maxx, q0.s.miny, q0.s.maxy, b.bx0, b.by0, b.bnx, b.bny };
-                        WPS_TRY(get_cell_index(h, *job_entry[g], (int)dg.npts(), dims, &b.cidx));
-                        choose_cell_lv((int)groups[g].size(), (double)b.cidx.n_fast / std::max(b.cidx.n_cells_used, 1), &b.cell_lv, &b.cell_chunks);
-                        need += sizeof(unsigned) * ((size_t)b.cidx.n_fast + 128) * b.cell_chunks * 2 + 512;
-                        need += sizeof(float) * (size_t)b.cidx.n_fast + 512;   // sorted landmask
+                    if (tile16_enabled && dg.npts() < (size_t(1) << 29)) {
+                        const double ppc = 1.6 * (double)dg.npts() / ((double)b.bnx * b.bny);   // destination points per source cell, roughly
+                        choose_tile_lv((int)groups[g].size(), ppc, &b.tile_lv, &b.tile_chunks);
+                        const int dims[9] = { q0.s.minx, q0.s.maxx, q0.s.miny, q0.s.maxy, b.bx0, b.by0, b.bnx, b.bny, tile_th(b.tile_lv) };
+                        WPS_TRY(get_tile_index(h, *job_entry[g], dg.nx(), dg.ny(), dims, &b.tidx));
+                        need += sizeof(float) * (size_t)b.tidx.n_fast + 512;   // sorted landmask
                     }
                 }
             } else if (q0.fo.ops[0] == WPSGPU_FOUR_POINT) b.fast = 2;
