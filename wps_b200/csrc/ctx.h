@@ -75,7 +75,7 @@ struct DstGrid {
 struct TileIndex {
     int dims[9];        // minx, maxx, miny, maxy, bx0, by0, bnx, bny, th it was built for
     int* d_sidx;        // [n_fast] point index, sorted by (tile, cell, index); points the packed path cannot take are left out
-    float2* d_sxy;      // [n_fast] (rx, ry) in sorted order
+    float4* d_spt;      // [n_fast] {x, y offsets inside the source cell, rx, position inside the tile} in sorted order
     int2* d_seg;        // [nseg + 1] (first sorted position, cell) of each run of points sharing tile and cell; sentinel (n_fast, 0)
     int* d_tile_seg;    // [ntiles + 1] first segment of each tile
     int n_fast, nseg, ntiles;
@@ -94,7 +94,7 @@ inline void free_coord_entry(CoordCacheEntry& e)
 {
     cudaFree(e.d_xy);
     if (e.d_gauss) cudaFree(e.d_gauss);
-    for (TileIndex& c : e.tidx) { cudaFree(c.d_sidx); cudaFree(c.d_sxy); cudaFree(c.d_seg); cudaFree(c.d_tile_seg); }
+    for (TileIndex& c : e.tidx) { cudaFree(c.d_sidx); cudaFree(c.d_spt); cudaFree(c.d_seg); cudaFree(c.d_tile_seg); }
     e.tidx.clear();
 }
 

@@ -591,9 +591,8 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
 // Arithmetic is the same xpass2 / ypass2 sequence as above: bit-identical results.
 struct Tile16Params {
     Job jb;
-    const int* sidx;         // TileIndex: point index, (rx, ry) and -- gathered per flush -- landmask in sorted order
-    const float2* sxy;
-    const float* slm;
+    const float4* spt;       // TileIndex: per sorted point {x, y (offsets inside the source cell), rx, point of the tile as int bits}
+    const float* slm;        // landmask in sorted order, gathered per flush
     const int2* seg;         // [nseg + 1] (first sorted position, source cell) of each segment; sentinel at the end
     const int* tile_seg;     // [ntiles + 1] first segment of each tile
     int nchunks;
@@ -645,11 +644,10 @@ k_metgrid_tile16(const __grid_constant__ Tile16Params P)
     if (s_end > s_begin) {
         const int k_last = __ldg(&P.seg[s_end].x);   // end of the tile's run of the sorted list
         // raw table entries of the coming batch, fetched one batch ahead (lanes = points)
-        int f_idx; float2 f_xy; float f_lm;
+        float4 f_pt; float f_lm;
         auto prefetch = [&](int k0) {
             const int k = min(k0 + lane, k_last - 1);
-            f_idx = __ldg(P.sidx + k);
-            f_xy = __ldg(P.sxy + k);
+            f_pt = __ldg(P.spt + k);
             f_lm = P.slm != nullptr ? __ldg(P.slm + k) : 0.0f;
         };
         // record of a cell -> shared memory (lanes of point slot 0, one level pair each), stencil rows j-1 .. j+2
@@ -701,19 +699,16 @@ k_metgrid_tile16(const __grid_constant__ Tile16Params P)
                 const int n = min(PB, seg_end - kb);
                 // ---- point table (lanes = points): level-independent part of interp_met_field's point logic (:2490-2541) ----
                 {
-                    const int idx = f_idx;
-                    const float xx = f_xy.x, yy = f_xy.y, lm = f_lm;
-                    const int ii = idx % nx, jj = idx / nx;
-                    const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
+                    const float xx = f_pt.z, lm = f_lm;
+                    int lp = __float_as_int(f_pt.w);
+                    const int di = jb.sm1 + tx * 32 + (lp & 31), dj = jb.sm2 + ty * TH + (lp >> 5), pw = jb.pw;
                     const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
                     int code = 0;
                     bool valid = lane < n && !in_fill;
                     if (both) { code = lm == 1.0f ? 1 : 0; valid = valid && (lm == 0.0f || lm == 1.0f); }
                     else if (jb.landmask != nullptr && lm == jb.masked) valid = false;
                     valid = valid && xx >= lo && xx <= hi;
-                    const int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
-                    float x = xx - (float)i, y = yy - (float)j;
-                    int lp = (jj - ty * TH) * 32 + (ii - tx * 32);
+                    float x = f_pt.x, y = f_pt.y;
                     if (!valid) { code = 2; x = 0.5f; y = 0.5f; lp = TP; }   // results of such rows go to the dump row
                     s_x[lane] = make_float4(x, x, 1.0f - x, 1.0f - x);
                     s_y[lane] = make_float4(y, y, 1.0f - y, 1.0f - y);
@@ -765,32 +760,47 @@ k_metgrid_tile16(const __grid_constant__ Tile16Params P)
     __syncwarp();
     // ---- write-out (lanes = 32 consecutive x): full lines, bitmap words by ballot; level-independent fill rules of
     // interp_met_field (process_bdy_width interior :2490-2495, landmask == masked :2527-2530) ----
+    // Level-outer, row-inner: one base pointer per level; lane `row` collects the two bitmap words of row `row`, so the
+    // words of a level go out in one store each.
     const int ii = tx * 32 + lane;
     const bool active = ii < nx;
     const float fill = jb.fill;
-#pragma unroll 1
-    for (int row = 0; row < TH; ++row) {
-        const int jj = ty * TH + row;
-        if (jj >= ny) break;
-        const size_t idx = (size_t)jj * nx + min(ii, nx - 1);
-        const size_t widx = (size_t)jj * jb.nxw + tx;
-        const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
-        bool fillpt = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
-        if (jb.landmask != nullptr && !both) fillpt = fillpt || __ldg(jb.landmask + idx) == jb.masked;
-        fillpt = fillpt && active;
-        const int lp = row * 32 + lane;
-        const unsigned okm = active ? s_ok[lp] : 0u;
-        const float* st = s_stg + lp * LS;
+    const int j0 = ty * TH, rows = min(TH, ny - j0);
+    const size_t idx0 = (size_t)j0 * nx + min(ii, nx - 1);
+    unsigned fillbits = 0, actbits = 0, okm[TH];
 #pragma unroll
-        for (int L = 0; L < NL; ++L) {
-            const int sl = chunk * NL + L;
-            if (sl >= nslab) break;
-            const bool ok = fillpt || ((okm >> ((L & 1) * 16 + (L >> 1))) & 1u);
-            const float v = fillpt ? fill : st[L];
-            if (ok) P.r_arr[sl][idx] = v;
-            const unsigned word = __ballot_sync(0xffffffffu, ok), sword = __ballot_sync(0xffffffffu, active && !ok);
-            if (lane == 0) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
+    for (int row = 0; row < TH; ++row) {
+        const int rr = min(row, rows - 1);   // rows past the grid shadow the last one; their bits stay clear
+        const int di = jb.sm1 + ii, dj = jb.sm2 + j0 + rr, pw = jb.pw;
+        bool fillpt = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+        if (jb.landmask != nullptr && !both) fillpt = fillpt | (__ldg(jb.landmask + idx0 + (size_t)rr * nx) == jb.masked);
+        const bool on = active && row < rows;
+        fillbits |= (fillpt && on ? 1u : 0u) << row;
+        actbits |= (on ? 1u : 0u) << row;
+        okm[row] = on ? s_ok[row * 32 + lane] : 0u;
+    }
+    const size_t w0 = (size_t)(j0 + min(lane, rows - 1)) * jb.nxw + tx;
+    const float* stg = s_stg + lane * LS;
+#pragma unroll
+    for (int L = 0; L < NL; ++L) {
+        const int sl = chunk * NL + L;
+        if (sl >= nslab) break;
+        float* rp = P.r_arr[sl] + idx0;
+        unsigned myw = 0u, mys = 0u;
+#pragma unroll
+        for (int row = 0; row < TH; ++row) {
+            const float sv = stg[row * 32 * LS + L];
+            const unsigned fb = (fillbits >> row) & 1u;
+            const unsigned okb = fb | ((okm[row] >> ((L & 1) * 16 + (L >> 1))) & 1u);
+            const float v = fb ? fill : sv;
+            if (okb) *rp = v;
+            rp += nx;
+            const unsigned word = __ballot_sync(0xffffffffu, okb != 0u);
+            const unsigned sword = __ballot_sync(0xffffffffu, (((actbits >> row) & 1u) & ~okb) != 0u);
+            myw = lane == row ? word : myw;
+            mys = lane == row ? sword : mys;
         }
+        if (lane < rows) { P.new_pts[sl][w0] = (int)myw; P.slow[sl][w0] = (int)mys; }
     }
 }
 
@@ -825,10 +835,18 @@ __global__ void k_tile_keys(const float2* __restrict__ xy, int n, int nx, int ti
     vals[k] = k;
 }
 
-__global__ void k_cell_gather_xy(const int* __restrict__ sidx, const float2* __restrict__ xy, int n, float2* __restrict__ sxy)
+// per sorted point: offsets inside the source cell (sixteen_pt, interp_module.F:1216-1220), rx for the border test of
+// interp_to_latlon (:2620), and the point's position inside its tile
+__global__ void k_tile_gather_pt(const int* __restrict__ sidx, const float2* __restrict__ xy, int n, int nx, int th, float4* __restrict__ spt)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) sxy[k] = __ldg(xy + __ldg(sidx + k));
+    if (k >= n) return;
+    const int idx = __ldg(sidx + k);
+    const float2 p = __ldg(xy + idx);
+    const int i = (int)(p.x + 0.00001f), j = (int)(p.y + 0.00001f);
+    const int ii = idx % nx, jj = idx / nx;
+    const int lp = (jj % th) * 32 + (ii & 31);
+    spt[k] = make_float4(p.x - (float)i, p.y - (float)j, p.x, __int_as_float(lp));
 }
 
 __global__ void k_cell_gather_f(const int* __restrict__ sidx, const float* __restrict__ a, int n, float* __restrict__ out)
@@ -1152,7 +1170,7 @@ static int get_tile_index(wpsgpu_ctx* h, CoordCacheEntry& e, int nx, int ny, con
     if (e.tidx.size() >= 8) {   // other source extents seen through the same projection: keep the cache small
         WPS_CUDA(cudaStreamSynchronize(h->stream));
         TileIndex& o = e.tidx.front();
-        cudaFree(o.d_sidx); cudaFree(o.d_sxy); cudaFree(o.d_seg); cudaFree(o.d_tile_seg);
+        cudaFree(o.d_sidx); cudaFree(o.d_spt); cudaFree(o.d_seg); cudaFree(o.d_tile_seg);
         e.tidx.erase(e.tidx.begin());
     }
     TileIndex c;
@@ -1197,14 +1215,14 @@ static int get_tile_index(wpsgpu_ctx* h, CoordCacheEntry& e, int nx, int ny, con
     c.nseg = (int)seg.size();
     seg.push_back(make_int2(n_fast, 0));
     WPS_CUDA(cudaMalloc((void**)&c.d_sidx, sizeof(int) * (size_t)std::max(n_fast, 1)));
-    WPS_CUDA(cudaMalloc((void**)&c.d_sxy, sizeof(float2) * (size_t)std::max(n_fast, 1)));
+    WPS_CUDA(cudaMalloc((void**)&c.d_spt, sizeof(float4) * (size_t)std::max(n_fast, 1)));
     WPS_CUDA(cudaMalloc((void**)&c.d_seg, sizeof(int2) * seg.size()));
     WPS_CUDA(cudaMalloc((void**)&c.d_tile_seg, sizeof(int) * tile_seg.size()));
     WPS_CUDA(cudaMemcpyAsync(c.d_seg, seg.data(), sizeof(int2) * seg.size(), cudaMemcpyHostToDevice, h->stream));
     WPS_CUDA(cudaMemcpyAsync(c.d_tile_seg, tile_seg.data(), sizeof(int) * tile_seg.size(), cudaMemcpyHostToDevice, h->stream));
     if (n_fast > 0) {
         WPS_CUDA(cudaMemcpyAsync(c.d_sidx, d_svals, sizeof(int) * (size_t)n_fast, cudaMemcpyDeviceToDevice, h->stream));
-        k_cell_gather_xy<<<(n_fast + 255) / 256, 256, 0, h->stream>>>(c.d_sidx, e.d_xy, n_fast, c.d_sxy);
+        k_tile_gather_pt<<<(n_fast + 255) / 256, 256, 0, h->stream>>>(c.d_sidx, e.d_xy, n_fast, nx, th, c.d_spt);
         h->launches++;
         WPS_CUDA(cudaGetLastError());
     }
@@ -1754,7 +1772,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         const Box& bx = fs.box[gsel[j]];
         if (bx.tile_lv > 0) {
             Tile16Params tp;
-            tp.jb = fp.jb; tp.sidx = bx.tidx.d_sidx; tp.sxy = bx.tidx.d_sxy; tp.slm = nullptr;
+            tp.jb = fp.jb; tp.spt = bx.tidx.d_spt; tp.slm = nullptr;
             tp.seg = bx.tidx.d_seg; tp.tile_seg = bx.tidx.d_tile_seg; tp.nchunks = bx.tile_chunks;
             memcpy(tp.r_arr, fp.r_arr, sizeof(tp.r_arr)); memcpy(tp.new_pts, fp.new_pts, sizeof(tp.new_pts)); memcpy(tp.slow, fp.slow, sizeof(tp.slow));
             if (fp.jb.landmask != nullptr && bx.tidx.n_fast > 0) {   // landmask in sorted order, gathered once per flush and index
