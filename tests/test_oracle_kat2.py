@@ -1,0 +1,180 @@
+"""More hand-derived known answers that pin the CPU oracle (the reference ships no tests for this path):
+wind rotation, Coriolis, smoothers, land-use fractions / dominant category / landmask, categorical accumulation.
+Every expected value below is worked out by hand from the cited Fortran lines, not from running any code."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def full_bits(ny, nx):
+    return np.full((ny, (nx + 31) // 32), -1, np.int32)
+
+
+def cgrid(nx, ny, lon_u, lon_v):
+    """u (ny, nx+1) and v (ny+1, nx) longitudes of a C grid, constant per array"""
+    return np.full((ny, nx + 1), lon_u, np.float32), np.full((ny + 1, nx), lon_v, np.float32)
+
+
+def test_rotation_is_identity_on_the_standard_longitude():
+    """rotate_winds_module.F:163-173,257,362: xlon == stdlon gives diff = 0, alpha = 0, and
+    u_new = cos(0)*u + sin(0)*vbar = u, v_new = -sin(0)*ubar + cos(0)*v = v exactly, for LC and PS, both directions."""
+    O.set_transc_mode(1)
+    nx, ny = 7, 5
+    rng = np.random.default_rng(1)
+    u = rng.uniform(-30, 30, (ny, nx + 1)).astype(np.float32)
+    v = rng.uniform(-30, 30, (ny + 1, nx)).astype(np.float32)
+    xu, xv = cgrid(nx, ny, -98.0, -98.0)
+    for code, kw in ((O.PROJ_LC, dict(truelat1=30., truelat2=60.)), (O.PROJ_PS, dict(truelat1=60.))):
+        p = O.map_set(code, stdlon=-98., lat1=40., lon1=-98., knowni=4., knownj=3., dx=30000., **kw)
+        for idir in (1, -1):
+            uo, vo = O.metmap_xform(p, u, full_bits(ny, nx + 1), v, full_bits(ny + 1, nx), xu, xv, idir)
+            assert np.array_equal(uo, u) and np.array_equal(vo, v)
+
+
+@pytest.mark.parametrize("idir,eu,ev", [(1, 5.0, -3.0), (-1, -5.0, 3.0)])
+def test_polar_stereographic_quarter_turn(idir, eu, ev):
+    """PS, northern hemisphere: alpha = diff * rad_per_deg * hemi (:224).  90 degrees east of the standard longitude,
+    u = 3 and v = 5 everywhere, every mask bit set: vbar = 4*5/4 = 5, ubar = 3, so met_to_map (idir = 1) gives
+    u_new = cos(90)*3 + sin(90)*5 = 5, v_new = -sin(90)*3 + cos(90)*5 = -3; map_to_met (idir = -1) turns the other way."""
+    O.set_transc_mode(1)
+    nx, ny = 6, 6
+    p = O.map_set(O.PROJ_PS, truelat1=60., stdlon=-100., lat1=60., lon1=-100., knowni=3., knownj=3., dx=30000.)
+    assert p.hemi == 1.0
+    u = np.full((ny, nx + 1), 3.0, np.float32)
+    v = np.full((ny + 1, nx), 5.0, np.float32)
+    xu, xv = cgrid(nx, ny, -10.0, -10.0)
+    uo, vo = O.metmap_xform(p, u, full_bits(ny, nx + 1), v, full_bits(ny + 1, nx), xu, xv, idir)
+    assert np.allclose(uo, eu, rtol=0, atol=1e-6) and np.allclose(vo, ev, rtol=0, atol=1e-6)
+
+
+def test_lambert_rotation_uses_the_cone():
+    """LC with truelat1 = truelat2 = 30: cone = sin(30 deg) = 0.5 (module_map_utils.F:1146-1153).  60 degrees east of
+    stdlon: alpha = 60 * 0.5 = 30 degrees (:172).  u = 2, v = 4: u_new = cos30*2 + sin30*4 = 3.7320508,
+    v_new = -sin30*2 + cos30*4 = 2.4641016."""
+    O.set_transc_mode(1)
+    nx, ny = 5, 4
+    p = O.map_set(O.PROJ_LC, truelat1=30., truelat2=30., stdlon=-120., lat1=30., lon1=-120., knowni=3., knownj=2., dx=30000.)
+    assert abs(p.cone - 0.5) < 1e-6
+    u = np.full((ny, nx + 1), 2.0, np.float32)
+    v = np.full((ny + 1, nx), 4.0, np.float32)
+    xu, xv = cgrid(nx, ny, -60.0, -60.0)
+    uo, vo = O.metmap_xform(p, u, full_bits(ny, nx + 1), v, full_bits(ny + 1, nx), xu, xv, 1)
+    assert np.allclose(uo, 3.7320508, rtol=2e-6) and np.allclose(vo, 2.4641016, rtol=2e-6)
+
+
+def test_rotation_averages_only_the_valid_neighbours():
+    """:233-262: the V value at a U point is the mask-weighted mean of the four surrounding V points.  Interior U point
+    (i, j) = (3, 2) (1-based) sees v(2,2), v(2,3), v(3,2), v(3,3); with only v(2,2) = 1 and v(3,2) = 4 valid the mean is
+    2.5, so a quarter turn (PS, +90 degrees) gives u_new = 2.5.  A U point whose four V neighbours are all invalid keeps
+    its value (:259-261); a U point whose own mask bit is clear is copied (:263)."""
+    O.set_transc_mode(1)
+    nx, ny = 5, 4
+    p = O.map_set(O.PROJ_PS, truelat1=60., stdlon=-100., lat1=60., lon1=-100., knowni=3., knownj=3., dx=30000.)
+    u = np.full((ny, nx + 1), 7.0, np.float32)
+    v = np.zeros((ny + 1, nx), np.float32)
+    v[1, 1], v[2, 1], v[1, 2], v[2, 2] = 1.0, 2.0, 4.0, 8.0     # [j-1][i-1]: v(2,2), v(2,3), v(3,2), v(3,3)
+    vm = np.zeros((ny + 1, 1), np.int32)
+    vm[1, 0] = (1 << 1) | (1 << 2)                                # bits of v(2,2) and v(3,2)
+    um = full_bits(ny, nx + 1).copy()
+    um[3, 0] &= ~(1 << 4)                                         # u(5,4) not valid
+    xu, xv = cgrid(nx, ny, -10.0, -10.0)
+    uo, _ = O.metmap_xform(p, u, um, v, vm, xu, xv, 1)
+    assert abs(uo[1, 2] - 2.5) < 1e-6          # u(3,2)
+    assert uo[3, 0] == 7.0                     # u(1,4): no valid V neighbour
+    assert uo[3, 4] == 7.0                     # u(5,4): masked out, copied
+
+
+def test_coriolis_parameters():
+    """process_tile_module.F:1903-1904 with OMEGA_E = 7.292e-5 (constants_module.F:9): f = 2*OMEGA*sin(lat),
+    e = 2*OMEGA*cos(lat)."""
+    O.set_transc_mode(1)
+    f, e = O.get_coriolis(np.array([[0.0, 30.0, 90.0, -30.0]], np.float32))
+    assert np.allclose(f[0], [0.0, 7.292e-5, 1.4584e-4, -7.292e-5], rtol=2e-6, atol=1e-11)
+    assert np.allclose(e[0, :2], [1.4584e-4, 1.4584e-4 * 0.8660254], rtol=2e-6)
+
+
+def test_one_two_one_impulse_response():
+    """smooth_module.F:41-55: x sweep then y sweep with weights (0.25, 0.5, 0.25): an impulse of 16 becomes
+    [[1,2,1],[2,4,2],[1,2,1]] -- all intermediate values are dyadic, so the result is exact; a second pass gives the
+    5x5 binomial kernel 16 * outer(b, b) / 256 with b = (1,4,6,4,1)."""
+    a = np.zeros((9, 9), np.float32)
+    a[4, 4] = 16.0
+    s = O.smooth(a, 1, 1)
+    expect = np.zeros_like(a)
+    expect[3:6, 3:6] = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], np.float32)
+    assert np.array_equal(s, expect)
+    s2 = O.smooth(a, 2, 1)
+    b = np.array([1, 4, 6, 4, 1], np.float32)
+    expect2 = np.zeros_like(a)
+    expect2[2:7, 2:7] = np.outer(b, b) / 16.0
+    assert np.array_equal(s2, expect2)
+
+
+def test_smth_desmth_special_restores_overshoots():
+    """smooth_module.F:116-134: the desmoothing sweep has weights (-0.26, 1.52, -0.26), so a spike leaves negative
+    side lobes; :225-234: smth-desmth_special puts back the original value wherever the result is negative and the
+    original was not.  Everything else equals plain smth-desmth."""
+    a = np.zeros((11, 11), np.float32)
+    a[5, 5] = 100.0
+    plain = O.smooth(a, 1, 2)
+    special = O.smooth(a, 1, 3)
+    assert (plain < 0).any()
+    assert np.array_equal(special, np.where((plain < 0) & (a >= 0), a, plain))
+    # the weights of either sweep pair sum to one: a constant field comes back within rounding
+    c = np.full((8, 9), 250.0, np.float32)
+    assert np.allclose(O.smooth(c, 1, 2), c, rtol=1e-6)
+
+
+def test_fractions_dominant_category_and_landmask():
+    """process_tile_module.F:1035-1051 (fractions = counts / sum, all categories = msg_fill_val when nothing was counted),
+    :1123-1144 (dominant = FIRST strict maximum, msg_fill_val when no category is above zero), :570-596 (water mask:
+    land = 1 when the water fraction is < 0.5, -1 when the water category holds the fill value)."""
+    fillv = -999.0
+    counts = np.zeros((4, 1, 4), np.float32)                 # [category][j][i], categories 11..14
+    counts[:, 0, 0] = [3, 1, 0, 4]
+    counts[:, 0, 1] = [2, 2, 0, 0]                           # tie: the first one wins
+    counts[:, 0, 2] = [0, 0, 0, 0]                           # nothing counted
+    counts[:, 0, 3] = [1, 0, 0, 1]
+    fr = O.fractions(counts, fillv)
+    assert np.array_equal(fr[:, 0, 0], np.array([0.375, 0.125, 0.0, 0.5], np.float32))
+    assert np.array_equal(fr[:, 0, 1], np.array([0.5, 0.5, 0.0, 0.0], np.float32))
+    assert np.array_equal(fr[:, 0, 2], np.full(4, fillv, np.float32))
+    dom = O.dominant_category(fr, 11, fillv)
+    assert list(dom[0]) == [14.0, 11.0, fillv, 11.0]
+    lm = O.landmask_from_fractions(fr, 11, [14], True, fillv)   # category 14 is water
+    assert list(lm[0]) == [0.0, 1.0, -1.0, 0.0]                 # 0.5 is not < 0.5 -> water
+
+
+def test_accum_categorical_counts_on_aligned_grids():
+    """proc_point_module.F:245-372: a source pixel is credited to the destination cell nint(rx), nint(ry) of its centre
+    provided start_x <= rx <= end_x and start_y <= ry <= end_y as REALS (:253).  Destination = 1-degree lat-lon grid, cell
+    (1,1) centred on (10N, 20E), cells 1..3 in both directions; source = 0.25-degree pixels whose centres sit at +-0.125
+    and +-0.375 around the cell centres, so every cell has 4 x 4 pixel centres inside and none on an edge.  The real
+    compare drops pixels with rx < 1 or rx > 3 (likewise y), i.e. the outer half of the border cells: corner cells keep
+    2 x 2 pixels, edge cells 2 x 4, the centre cell all 16.  Category = 1 + (pixel column mod 2) splits each count evenly."""
+    O.set_transc_mode(1)
+    dom = O.map_set(O.PROJ_LATLON, latinc=1.0, loninc=1.0, lat1=10.0, lon1=20.0, knowni=1.0, knownj=1.0, stdlon=0.0)
+    src = O.push_source_projection(O.PROJ_LATLON, dlat=0.25, dlon=0.25, known_x=1.0, known_y=1.0, known_lat=9.625,
+                                   known_lon=19.625)
+    nx = ny = 3
+    tn = 12
+    tile = (1.0 + (np.arange(tn)[None, :] % 2) + np.zeros((tn, 1))).astype(np.float32)
+    dst = np.full((2, ny, nx), 77.0, np.float32)  # "uninitialised": first touch must zero it (:330-334)
+    processed = np.zeros((ny, 1), np.int32)
+    new_pts = np.zeros((ny, 1), np.int32)
+    ninv = O.accum_categorical(src, dom, O.M, tile, 1, 1, 0, dst, 1, 1, 1, processed, new_pts, 1, 0.0)
+    assert ninv == 0
+    per_cat = np.array([[2, 4, 2], [4, 8, 4], [2, 4, 2]], np.float32)
+    assert np.array_equal(dst, np.stack([per_cat, per_cat]))
+    assert all(int(w) & 0b111 == 0b111 for w in new_pts[:, 0])
+    # a category outside [start_z, end_z] is reported, not counted (:343-351); the cell is still zeroed at first touch
+    # (:330-334).  The 16 pixels of the centre cell carry category 9 here.
+    tile2 = tile.copy()
+    tile2[4:8, 4:8] = 9.0                         # the 16 pixels of the centre cell
+    dst2 = np.full((2, ny, nx), 77.0, np.float32)
+    processed[:] = 0
+    new_pts[:] = 0
+    ninv2 = O.accum_categorical(src, dom, O.M, tile2, 1, 1, 0, dst2, 1, 1, 1, processed, new_pts, 1, 0.0)
+    assert ninv2 == 16
+    assert dst2[0, 1, 1] == 0.0 and dst2[1, 1, 1] == 0.0 and dst2[0, 0, 0] == 2.0
