@@ -239,3 +239,22 @@ def test_patch_sharded_field_equals_whole_domain(orc, handle, kind):
         else:
             np.testing.assert_allclose(part, ref, rtol=1e-6, atol=0.0)
     assert min(nts) <= nt_whole
+
+
+@pytest.mark.parametrize("opt,npass", [(1, 2), (3, 1)])
+def test_patchwise_smoothing_on_device(orc, handle, opt, npass):
+    """a GPU that owns one destination patch smooths the patch extended by smoother_apron() cells and needs
+    no halo exchange: on the patch the result equals the whole-domain smoothing bit for bit (oracle = whole domain)."""
+    from wps_b200.shard import apron_window, patch_bounds, smoother_apron
+    idim, jdim, world = 97, 71, 4
+    a = np.random.default_rng(8).uniform(-50, 3000, (jdim, idim)).astype(np.float32)
+    whole = orc.smooth(a, npass, opt)
+    ap = smoother_apron(opt, npass)
+    out = np.full_like(a, np.nan)
+    for rank in range(world):
+        x0, x1, y0, y1 = patch_bounds(idim, jdim, world, rank)
+        ax0, ax1, ay0, ay1 = apron_window(x0, x1, y0, y1, idim, jdim, ap)
+        w = np.ascontiguousarray(a[ay0 - 1:ay1, ax0 - 1:ax1])
+        handle.smooth(w, opt, npass)
+        out[y0 - 1:y1, x0 - 1:x1] = w[y0 - ay0:y1 - ay0 + 1, x0 - ax0:x1 - ax0 + 1]
+    assert_bitexact(out, whole, "patch-wise smoothing opt=%d npass=%d" % (opt, npass))

@@ -201,3 +201,29 @@ def test_fill_lev_table_options():
     assert t[1].is_derived_field and t[1].level_template == "TT" and t[1].flag_in_output == "FLAG_P"
     assert get_constant_fill_lev("const(5.5)") == (0, 5.5) and get_constant_fill_lev("PRES")[0] == 1
     assert get_fill_src_level("TT(100000)") == ("TT", 100000) and get_fill_src_level("SOILHGT") == ("SOILHGT", 1)
+
+
+@pytest.mark.parametrize("opt,npass", [(1, 1), (1, 3), (2, 1), (3, 2)])
+def test_patchwise_smoothing_with_apron_equals_whole_domain(opt, npass):
+    """geogrid shards by destination patch; smoothing a patch extended by smoother_apron() cells gives, on
+    the patch, bit for bit what smoothing the whole domain gives (checked with the CPU oracle's smoothers; the GPU twin
+    is tests/test_gpu_geogrid.py::test_patchwise_smoothing_on_device)."""
+    from oracle import oracle as O
+    from wps_b200.shard import apron_window, patch_bounds, smoother_apron
+    idim, jdim, world = 61, 47, 4
+    a = np.random.default_rng(3).uniform(-50, 3000, (jdim, idim)).astype(np.float32)
+    whole = O.smooth(a, npass, opt)
+    ap = smoother_apron(opt, npass)
+    out = np.full_like(a, np.nan)
+    for rank in range(world):
+        x0, x1, y0, y1 = patch_bounds(idim, jdim, world, rank)
+        ax0, ax1, ay0, ay1 = apron_window(x0, x1, y0, y1, idim, jdim, ap)
+        s = O.smooth(a[ay0 - 1:ay1, ax0 - 1:ax1], npass, opt)
+        out[y0 - 1:y1, x0 - 1:x1] = s[y0 - ay0:y1 - ay0 + 1, x0 - ax0:x1 - ax0 + 1]
+    assert np.array_equal(out.view(np.int32), whole.view(np.int32))
+    # one cell less is not enough (the test would be vacuous otherwise)
+    if ap > 1:
+        x0, x1, y0, y1 = patch_bounds(idim, jdim, world, 0)
+        ax0, ax1, ay0, ay1 = apron_window(x0, x1, y0, y1, idim, jdim, ap - 1)
+        s = O.smooth(a[ay0 - 1:ay1, ax0 - 1:ax1], npass, opt)
+        assert not np.array_equal(s[y0 - ay0:y1 - ay0 + 1, x0 - ax0:x1 - ax0 + 1], whole[y0 - 1:y1, x0 - 1:x1])

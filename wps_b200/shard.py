@@ -73,3 +73,20 @@ def patch_bounds(idim: int, jdim: int, nprocs: int, rank: int) -> Tuple[int, int
     if not xs or not ys:
         return (-1, -1, -1, -1)
     return xs[0], xs[-1], ys[0], ys[-1]
+
+
+# ---- geogrid: smoothing a patch without an exchange step -----------------------------------------------------------
+def smoother_apron(smooth_option: int, npass: int) -> int:
+    """Cells a patch must be extended by so that smoothing the extended window reproduces, on the patch itself, the
+    result of smoothing the whole domain.  One 1-2-1 pass (smooth_module.F:41-55) reads one cell in every
+    direction and leaves the window's outermost ring unchanged, so after p passes the values within p cells of an
+    artificial window edge are off: an apron of npass cells for one_two_one (option 1), 2*npass for smth-desmth and
+    smth-desmth_special (options 2, 3: each pass is a smoothing and a desmoothing sweep pair, :92-134).  The reference's
+    MPI build gets the same effect with exchange_halo_r after every sweep pair."""
+    return int(npass) if smooth_option == 1 else 2 * int(npass)
+
+
+def apron_window(x0: int, x1: int, y0: int, y1: int, idim: int, jdim: int, apron: int) -> Tuple[int, int, int, int]:
+    """The patch (1-based inclusive bounds) extended by `apron` cells, clipped to the domain: at a true domain edge the
+    window's ring is the domain's ring, which the smoothers leave untouched anyway."""
+    return max(1, x0 - apron), min(idim, x1 + apron), max(1, y0 - apron), min(jdim, y1 + apron)
