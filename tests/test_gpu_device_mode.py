@@ -16,11 +16,14 @@ def dhandle():
     h.close()
 
 
-def test_metgrid_137_levels_device_resident(orc, dhandle):
-    """Config-5 shape in small: 137 levels of one field (three job groups of at most 64 slabs in device mode) plus a
+@pytest.mark.parametrize("tile16", ["0", "1"])
+def test_metgrid_137_levels_device_resident(orc, dhandle, tile16, monkeypatch):
+    """(tile16 = 1: the same through the opt-in tile-major sixteen_pt kernel, job groups of 64 + 64 + 9 levels.)
+    Config-5 shape in small: 137 levels of one field (three job groups of at most 64 slabs in device mode) plus a
     masked soil chain with deferred searches, all device-resident, one flush; oracle on a spread of levels."""
     import torch
     from wps_b200 import capi
+    monkeypatch.setenv("WPSGPU_TILE16", tile16)
     dev = torch.device("cuda", 0)
     nx, ny, nlev = 150, 110, 137
     orc.set_transc_mode(1)

@@ -1183,6 +1183,16 @@ static int get_tile_index(wpsgpu_ctx* h, CoordCacheEntry& e, int nx, int ny, con
     int *d_vals = nullptr, *d_svals = nullptr;
     void* d_tmp = nullptr;
     size_t tmp_bytes = 0;
+    c.d_sidx = nullptr; c.d_spt = nullptr; c.d_seg = nullptr; c.d_tile_seg = nullptr;
+    bool built = false;
+    struct Cleanup {   // temporaries always, the index arrays unless the build completed
+        unsigned long long **k, **sk; int **v, **sv; void** t; TileIndex* c; bool* built;
+        ~Cleanup()
+        {
+            cudaFree(*k); cudaFree(*sk); cudaFree(*v); cudaFree(*sv); cudaFree(*t);
+            if (!*built) { cudaFree(c->d_sidx); cudaFree(c->d_spt); cudaFree(c->d_seg); cudaFree(c->d_tile_seg); }
+        }
+    } cleanup{ &d_keys, &d_skeys, &d_vals, &d_svals, &d_tmp, &c, &built };
     WPS_CUDA(cudaMalloc((void**)&d_keys, sizeof(unsigned long long) * (size_t)npts));
     WPS_CUDA(cudaMalloc((void**)&d_skeys, sizeof(unsigned long long) * (size_t)npts));
     WPS_CUDA(cudaMalloc((void**)&d_vals, sizeof(int) * (size_t)npts));
@@ -1227,7 +1237,7 @@ static int get_tile_index(wpsgpu_ctx* h, CoordCacheEntry& e, int nx, int ny, con
         WPS_CUDA(cudaGetLastError());
     }
     WPS_CUDA(cudaStreamSynchronize(h->stream));   // seg / tile_seg are pageable host vectors
-    cudaFree(d_keys); cudaFree(d_skeys); cudaFree(d_vals); cudaFree(d_svals); cudaFree(d_tmp);
+    built = true;
     e.tidx.push_back(c);
     *out = c;
     return 0;
@@ -1236,11 +1246,8 @@ static int get_tile_index(wpsgpu_ctx* h, CoordCacheEntry& e, int nx, int ny, con
 template <int LV, int TH>
 static int launch_tile16(const Tile16Params& tp, cudaStream_t st)
 {
-    static bool carved = false;
-    if (!carved) {
-        WPS_CUDA(cudaFuncSetAttribute(k_metgrid_tile16<LV, TH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        carved = true;
-    }
+    // per device and context, so not cached in a static: a process may hold handles on several GPUs
+    WPS_CUDA(cudaFuncSetAttribute(k_metgrid_tile16<LV, TH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const int tiles = tp.jb.tiles_x * ((tp.jb.ny + TH - 1) / TH);
     k_metgrid_tile16<LV, TH><<<dim3((unsigned)tiles, (unsigned)tp.nchunks), 32, 0, st>>>(tp);
     return 0;
