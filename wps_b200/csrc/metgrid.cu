@@ -944,30 +944,20 @@ k_metgrid_fast4(const __grid_constant__ Fast4Params P)
 #define SLOW_MINBLOCKS 8   // 64 registers: measured 0.31 / 0.24 / 0.22 / 0.22 / 0.26 ms at 4 / 6 / 8 / 10 / 12 CTAs per SM
 #endif
 __global__ void __launch_bounds__(128, SLOW_MINBLOCKS)
-k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_word0, int ncls,
-                   const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count,
-                   long long w_begin, long long total_words)
+k_metgrid_slowbits(const Job* __restrict__ jobs, const int2* __restrict__ slow_slabs, int slab_begin,
+                   const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count)
 {
-    // each lane fetches one bitmap word (coalesced)
+    // blockIdx.y picks the slab (job, level) from the list of first-method slabs, blockIdx.x a run of 128 bitmap words
+    // of it: no per-thread search or division (a linear word index over all slabs cost a 64-bit division per thread,
+    // more than half of this kernel's time).  Each lane fetches one word (coalesced).
     const int lane = threadIdx.x & 31;
-    long long w = w_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;   // this launch covers words [w_begin, total_words)
+    const int2 js = __ldg(slow_slabs + slab_begin + blockIdx.y);
+    const int job = js.x, sl = js.y;
+    const int words_per_slab = jobs[job].ny * jobs[job].nxw;
+    const int widx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= (unsigned)words_per_slab) return;   // whole block past the end (grid sized for the largest slab)
     unsigned bits = 0;
-    int job = 0, sl = 0;
-    long long widx = 0;
-    if (w < total_words) {
-        int lo = 0, hi = ncls - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if ((long long)cls_word0[mid] <= w) lo = mid; else hi = mid - 1;
-        }
-        job = cls_jobs[lo];
-        const Job& jb = jobs[job];
-        long long rel = w - cls_word0[lo];
-        long long words_per_slab = (long long)jb.ny * jb.nxw;
-        sl = (int)(rel / words_per_slab);
-        widx = rel % words_per_slab;
-        bits = (unsigned)slabs[jb.slab0 + sl].slow[widx];
-    }
+    if (widx < words_per_slab) bits = (unsigned)slabs[jobs[job].slab0 + sl].slow[widx];
     // The flagged points of the warp's 32 words are ranked by an exclusive scan of the per-word popcounts and dealt
     // out 32 at a time, so every lane has a point to work on regardless of how the bits are spread over the words.
     unsigned cnt = __popc(bits), inc = cnt;
@@ -986,8 +976,8 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int* __restrict__ cls_job
             if (e <= r) pos += step;
         }
         unsigned wbits = __shfl_sync(0xffffffffu, bits, pos), wexc = __shfl_sync(0xffffffffu, exc, pos);
-        int wjob = __shfl_sync(0xffffffffu, job, pos), wsl = __shfl_sync(0xffffffffu, sl, pos);
-        long long wwidx = __shfl_sync(0xffffffffu, widx, pos);
+        const int wjob = job, wsl = sl;
+        const int wwidx = __shfl_sync(0xffffffffu, widx, pos);
         if (r < total) {
             int bit = (int)__fns(wbits, 0, (int)(r - wexc) + 1);
             const Job& jb = jobs[wjob];
@@ -1476,6 +1466,9 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     std::vector<int> cls_jobs[2], cls_tile0[2];  // 0 = generic kernel, 1 = first-method kernels
     std::vector<int> fast_word0;
     long long fast_words = 0;
+    std::vector<int2> slow_slabs;    // (job, level) of every first-method slab: the slow-bitmap pass takes one per blockIdx.y
+    std::vector<int> slow_first;     // first entry of each first-method job
+    int slow_max_words = 0;
     int tile_cursor[2] = { 0, 0 };
     double cls_points[2] = { 0.0, 0.0 };
     double fast16_points = 0.0, fast4_points = 0.0;
@@ -1519,7 +1512,12 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         cls_points[cls] += (double)dg.npts() * groups[g].size();
         if (bx.fast == 1) fast16_points += (double)dg.npts() * groups[g].size();
         if (bx.fast >= 2) fast4_points += (double)dg.npts() * groups[g].size();
-        if (cls == 1) { fast_word0.push_back((int)fast_words); fast_words += (long long)jb.ny * jb.nxw * groups[g].size(); }
+        if (cls == 1) {
+            fast_word0.push_back((int)fast_words); fast_words += (long long)jb.ny * jb.nxw * groups[g].size();
+            slow_first.push_back((int)slow_slabs.size());
+            for (int k = 0; k < (int)groups[g].size(); ++k) slow_slabs.push_back(make_int2(j, k));
+            slow_max_words = std::max(slow_max_words, jb.ny * jb.nxw);
+        }
         jb.f_negzero = -0.0f; jb.f_one = 1.0f;
         jb.gcell = q0.gcell ? 1 : 0;
         jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
@@ -1662,7 +1660,9 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     const size_t off_sp = (sizeof(Job) * njobs + 255) & ~size_t(255);
     const size_t off_cls = (off_sp + sizeof(SlabPtrs) * nq + 255) & ~size_t(255);
     const size_t off_dec = (off_cls + sizeof(int) * 6 * (njobs + 1) + 255) & ~size_t(255);
-    const size_t tab_bytes = off_dec + sizeof(DecodeTask) * decode_tasks.size();
+    const size_t off_slow = (off_dec + sizeof(DecodeTask) * decode_tasks.size() + 255) & ~size_t(255);
+    const size_t tab_bytes = off_slow + sizeof(int2) * slow_slabs.size();
+    WPS_CHECK(slow_slabs.size() < 65536, -3, "too many first-method slabs in one flush");
     std::vector<char>& tab = fs.tab;
     tab.assign(tab_bytes, 0);
     memcpy(tab.data(), jobs.data(), sizeof(Job) * njobs);
@@ -1674,6 +1674,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             if (!lists[c]->empty()) memcpy(cls + (size_t)c * (njobs + 1), lists[c]->data(), sizeof(int) * lists[c]->size());
     }
     if (!decode_tasks.empty()) memcpy(tab.data() + off_dec, decode_tasks.data(), sizeof(DecodeTask) * decode_tasks.size());
+    if (!slow_slabs.empty()) memcpy(tab.data() + off_slow, slow_slabs.data(), sizeof(int2) * slow_slabs.size());
     char* d_tab = (char*)h->arena.take(tab_bytes);
     WPS_CHECK(d_tab != nullptr, -3, "device arena exhausted (tables)");
     WPS_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab_bytes, cudaMemcpyHostToDevice, s_in));   // pageable source: staged before the call returns
@@ -1682,8 +1683,9 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     int* d_cls = (int*)(d_tab + off_cls);
     int* d_cls_jobs[2] = { d_cls, d_cls + 2 * (njobs + 1) };
     int* d_cls_tile0[2] = { d_cls + (njobs + 1), d_cls + 3 * (njobs + 1) };
-    int* d_fast_word0 = d_cls + 4 * (njobs + 1);
     int* d_pack_jobs = d_cls + 5 * (njobs + 1);
+    const int2* d_slow_slabs = (const int2*)(d_tab + off_slow);
+    const unsigned slow_gx = (unsigned)((slow_max_words + 127) / 128);
     Deferred *d_def = nullptr, *d_def2 = nullptr;
     unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(h->d_counters);
     if (any_search) {
@@ -1758,12 +1760,12 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     auto slow_pass = [&](int j) -> int {   // j = job index; its words are [fast_word0[k], fast_word0[k+1])
         if (!overlap) return 0;
         size_t k = std::find(cls_jobs[1].begin(), cls_jobs[1].end(), j) - cls_jobs[1].begin();
-        long long w0 = fast_word0[k], w1 = k + 1 < fast_word0.size() ? (long long)fast_word0[k + 1] : fast_words;
+        const int s0 = slow_first[k], s1 = k + 1 < slow_first.size() ? slow_first[k + 1] : (int)slow_slabs.size();
         WPS_CUDA(cudaEventRecord(h->ev_pool[k], h->stream));
         WPS_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_pool[k], 0));
         if (!side_used) WPS_CUDA(cudaEventRecord(h->ev_t[8], h->s_side));
         side_used = true;
-        k_metgrid_slowbits<<<(unsigned)((w1 - w0 + 127) / 128), 128, 0, h->s_side>>>(d_jobs, d_cls_jobs[1], d_fast_word0, (int)cls_jobs[1].size(), d_sp, d_def, d_cnt, w0, w1);
+        k_metgrid_slowbits<<<dim3(slow_gx, (unsigned)(s1 - s0)), 128, 0, h->s_side>>>(d_jobs, d_slow_slabs, s0, d_sp, d_def, d_cnt);
         h->launches++;
         return 0;
     };
@@ -1829,7 +1831,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     } else {
         WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
         if (tile_cursor[1] > 0) {
-            k_metgrid_slowbits<<<(unsigned)((fast_words + 127) / 128), 128, 0, h->stream>>>(d_jobs, d_cls_jobs[1], d_fast_word0, (int)cls_jobs[1].size(), d_sp, d_def, d_cnt, 0, fast_words);
+            k_metgrid_slowbits<<<dim3(slow_gx, (unsigned)slow_slabs.size()), 128, 0, h->stream>>>(d_jobs, d_slow_slabs, 0, d_sp, d_def, d_cnt);
             h->launches++;
         }
         WPS_CUDA(cudaEventRecord(h->ev_t[9], h->stream));
