@@ -1660,6 +1660,16 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     const size_t off_sp = (sizeof(Job) * njobs + 255) & ~size_t(255);
     const size_t off_cls = (off_sp + sizeof(SlabPtrs) * nq + 255) & ~size_t(255);
     const size_t off_dec = (off_cls + sizeof(int) * 6 * (njobs + 1) + 255) & ~size_t(255);
+    // slabs of masked / search chains carry nearly all the flagged points: their blocks go first, so that the long
+    // generic chains start early and the empty bitmaps of the 3-d fields are scanned in their shadow (a per-job
+    // launch on the side stream, WPSGPU_OVERLAP, keeps the job order)
+    if (env_int("WPSGPU_OVERLAP", 0, 0, 1) == 0)
+        std::stable_partition(slow_slabs.begin(), slow_slabs.end(), [&](const int2& e) {
+            const Job& jb = jobs[e.x];
+            bool heavy = jb.mask[0] || jb.mask[1] || jb.mask[2];
+            for (int k = 0; k < WPSGPU_MAX_OPS && jb.ops[k]; ++k) heavy = heavy || jb.ops[k] == WPSGPU_SEARCH;
+            return heavy;
+        });
     const size_t off_slow = (off_dec + sizeof(DecodeTask) * decode_tasks.size() + 255) & ~size_t(255);
     const size_t tab_bytes = off_slow + sizeof(int2) * slow_slabs.size();
     WPS_CHECK(slow_slabs.size() < 65536, -3, "too many first-method slabs in one flush");
