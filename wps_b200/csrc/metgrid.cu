@@ -943,21 +943,39 @@ k_metgrid_fast4(const __grid_constant__ Fast4Params P)
 #ifndef SLOW_MINBLOCKS
 #define SLOW_MINBLOCKS 8   // 64 registers: measured 0.31 / 0.24 / 0.22 / 0.22 / 0.26 ms at 4 / 6 / 8 / 10 / 12 CTAs per SM
 #endif
+// WPT = bitmap words per thread (rounds per block); 1 is what is launched.
+template <int WPT>
 __global__ void __launch_bounds__(128, SLOW_MINBLOCKS)
 k_metgrid_slowbits(const Job* __restrict__ jobs, const int2* __restrict__ slow_slabs, int slab_begin,
                    const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count)
 {
-    // blockIdx.y picks the slab (job, level) from the list of first-method slabs, blockIdx.x a run of 128 bitmap words
-    // of it: no per-thread search or division (a linear word index over all slabs cost a 64-bit division per thread,
-    // more than half of this kernel's time).  Each lane fetches one word (coalesced).
+    // blockIdx.y picks the slab (job, level) from the list of first-method slabs, blockIdx.x a run of WPT x 128 bitmap
+    // words of it: no per-thread search or division (a linear word index over all slabs cost a 64-bit division per
+    // thread).  Each lane fetches one word per round (coalesced); a round without a set bit in the block is skipped.
     const int lane = threadIdx.x & 31;
     const int2 js = __ldg(slow_slabs + slab_begin + blockIdx.y);
     const int job = js.x, sl = js.y;
     const int words_per_slab = jobs[job].ny * jobs[job].nxw;
-    const int widx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x * blockDim.x >= (unsigned)words_per_slab) return;   // whole block past the end (grid sized for the largest slab)
-    unsigned bits = 0;
-    if (widx < words_per_slab) bits = (unsigned)slabs[jobs[job].slab0 + sl].slow[widx];
+    if (blockIdx.x * blockDim.x * WPT >= (unsigned)words_per_slab) return;   // whole block past the end (grid sized for the largest slab)
+    __shared__ unsigned short s_queue[128 * 32];   // (word of the round << 6) | (bit << 1) | first
+    __shared__ int s_nq;
+    const Job& jb = jobs[job];
+    const SlabPtrs sp = slabs[jb.slab0 + sl];
+    const bool hint_ok = jb.fast == 1 && !(jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH);
+    const bool light_ok = hint_ok && jb.ops[1] == WPSGPU_FOUR_POINT;
+    auto word_at = [&](int k) -> unsigned {
+        const int w = (blockIdx.x * WPT + k) * blockDim.x + threadIdx.x;
+        return (k < WPT && w < words_per_slab) ? (unsigned)__ldg(sp.slow + w) : 0u;
+    };
+    unsigned bits_next = word_at(0);
+#pragma unroll 1
+    for (int k = 0; k < WPT; ++k) {
+    const unsigned bits = bits_next;
+    bits_next = word_at(k + 1);   // in flight while this round is examined
+    if (threadIdx.x == 0) s_nq = 0;
+    if (!__syncthreads_or(bits != 0u)) continue;
+    const int w_block = (blockIdx.x * WPT + k) * blockDim.x;
+    const int widx = w_block + threadIdx.x;
     // The flagged points of the warp's 32 words are ranked by an exclusive scan of the per-word popcounts and dealt
     // out 32 at a time, so every lane has a point to work on regardless of how the bits are spread over the words.
     unsigned cnt = __popc(bits), inc = cnt;
@@ -967,6 +985,10 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int2* __restrict__ slow_s
         if (lane >= off) inc += v;
     }
     const unsigned total = __shfl_sync(0xffffffffu, inc, 31), exc = inc - cnt;
+    // Two phases.  (1) Every flagged point whose stencil is known to hold a missing / masked value (so sixteen_pt hands
+    // over) and whose second method is four_pt tries just that operator -- four loads; two thirds of the coast-line
+    // points of the soil chains end here.  (2) The rest is queued in shared memory and worked off by the whole block
+    // with the full chain, so the 64-register generic code runs on dense warps instead of a few lanes per warp.
     for (unsigned base = 0; base < total; base += 32) {
         unsigned r = base + lane;
         int pos = 0;   // largest lane whose exclusive prefix is <= r: the word holding the r-th flagged point
@@ -976,20 +998,15 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int2* __restrict__ slow_s
             if (e <= r) pos += step;
         }
         unsigned wbits = __shfl_sync(0xffffffffu, bits, pos), wexc = __shfl_sync(0xffffffffu, exc, pos);
-        const int wjob = job, wsl = sl;
         const int wwidx = __shfl_sync(0xffffffffu, widx, pos);
         if (r < total) {
             int bit = (int)__fns(wbits, 0, (int)(r - wexc) + 1);
-            const Job& jb = jobs[wjob];
-            const SlabPtrs sp = slabs[jb.slab0 + wsl];
             int jj = (int)(wwidx / jb.nxw), tx = (int)(wwidx % jb.nxw);
             int ii = tx * 32 + bit;
             size_t idx = (size_t)jj * jb.nx + ii;
-            bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> bit) & 1u) : false;
-            float out = 0.0f;
             const float2 pxy = __ldg(jb.xy + idx);
             int first = 0;
-            if (jb.fast == 1 && !(jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH)) {
+            if (hint_ok) {
                 // same cell arithmetic as sixteen_pt (interp_module.F:1211-1225); off a node and inside the record box
                 // the pre-pass has recorded whether the 4x4 stencil holds a missing / masked value
                 float xx = pxy.x, yy = pxy.y;
@@ -998,21 +1015,58 @@ k_metgrid_slowbits(const Job* __restrict__ jobs, const int2* __restrict__ slow_s
                     float fx = xx - (float)ci, fy = yy - (float)cj;
                     ci -= jb.bx0; cj -= jb.by0;
                     if ((fabsf(fx) > 0.0001f || fabsf(fy) > 0.0001f) && ci >= 0 && ci < jb.bnx && cj >= 0 && cj < jb.bny) {
-                        unsigned cfb = __ldg(jb.cf + ((size_t)(wsl >> 2) * jb.bny + cj) * jb.bnx + ci);
-                        if ((cfb >> (4 + (wsl & 3))) & 1u) first = 1;
+                        unsigned cfb = __ldg(jb.cf + ((size_t)(sl >> 2) * jb.bny + cj) * jb.bnx + ci);
+                        if ((cfb >> (4 + (sl & 3))) & 1u) first = 1;
                     }
                 }
             }
-            int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, pxy, vbit, out, nullptr, first);
-            if (flags & PF_DEFER) {
-                unsigned long long slot = atomicAdd(defer_count, 1ull);
-                Deferred d; d.slab = jb.slab0 + wsl; d.idx = (int)idx;
-                deferred[slot] = d;
-            } else {
-                if (flags & PF_WRITE) sp.r_arr[idx] = out;
-                if (flags & PF_BIT) atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
+            bool done = false;
+            if (light_ok && first == 1) {
+                // what process_point / interp_to_latlon do for such a point (no fill rule applies to a flagged point of
+                // a job without masked=both; interp_sequence starts at method 1): the x-range test of :2620, four_pt,
+                // and "value /= missing_value => store + new bit" (:2558-2563)
+                const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
+                const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+                const bool lm_fill = jb.landmask != nullptr && __ldg(jb.landmask + idx) == jb.masked;
+                const float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
+                if (!in_fill && !lm_fill && pxy.x >= lo && pxy.x <= hi) {
+                    Src s4;
+                    s4.a = sp.src; s4.m = jb.mask[0];
+                    s4.sx = jb.minx; s4.ex = jb.maxx; s4.sy = jb.miny; s4.ey = jb.maxy; s4.nx = jb.maxx - jb.minx + 1;
+                    s4.msg = jb.msg; s4.maskval = jb.mask_val[0]; s4.rel = jb.mask_rel[0];
+                    float v4 = jb.msg;
+                    if (op_four_pt(s4, pxy.x, pxy.y, v4) == ST_VAL && v4 != jb.msg) {
+                        sp.r_arr[idx] = v4;
+                        atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
+                        done = true;
+                    }
+                }
             }
+            if (!done) s_queue[atomicAdd(&s_nq, 1)] = (unsigned short)(((wwidx - w_block) << 6) | (bit << 1) | first);
         }
+    }
+    __syncthreads();
+    const int nq = s_nq;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        const unsigned e = s_queue[q];
+        const int wwidx = w_block + (int)(e >> 6), bit = (int)((e >> 1) & 31u), first = (int)(e & 1u);
+        int jj = (int)(wwidx / jb.nxw), tx = (int)(wwidx % jb.nxw);
+        int ii = tx * 32 + bit;
+        size_t idx = (size_t)jj * jb.nx + ii;
+        bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> bit) & 1u) : false;
+        float out = 0.0f;
+        const float2 pxy = __ldg(jb.xy + idx);
+        int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, pxy, vbit, out, nullptr, first);
+        if (flags & PF_DEFER) {
+            unsigned long long slot = atomicAdd(defer_count, 1ull);
+            Deferred d; d.slab = jb.slab0 + sl; d.idx = (int)idx;
+            deferred[slot] = d;
+        } else {
+            if (flags & PF_WRITE) sp.r_arr[idx] = out;
+            if (flags & PF_BIT) atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
+        }
+    }
+    __syncthreads();   // the queue is reused by the next round
     }
 }
 
@@ -1664,12 +1718,12 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     // generic chains start early and the empty bitmaps of the 3-d fields are scanned in their shadow (a per-job
     // launch on the side stream, WPSGPU_OVERLAP, keeps the job order)
     if (env_int("WPSGPU_OVERLAP", 0, 0, 1) == 0)
-        std::stable_partition(slow_slabs.begin(), slow_slabs.end(), [&](const int2& e) {
+        (void)(std::stable_partition(slow_slabs.begin(), slow_slabs.end(), [&](const int2& e) {
             const Job& jb = jobs[e.x];
             bool heavy = jb.mask[0] || jb.mask[1] || jb.mask[2];
             for (int k = 0; k < WPSGPU_MAX_OPS && jb.ops[k]; ++k) heavy = heavy || jb.ops[k] == WPSGPU_SEARCH;
             return heavy;
-        });
+        }));
     const size_t off_slow = (off_dec + sizeof(DecodeTask) * decode_tasks.size() + 255) & ~size_t(255);
     const size_t tab_bytes = off_slow + sizeof(int2) * slow_slabs.size();
     WPS_CHECK(slow_slabs.size() < 65536, -3, "too many first-method slabs in one flush");
@@ -1775,7 +1829,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         WPS_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_pool[k], 0));
         if (!side_used) WPS_CUDA(cudaEventRecord(h->ev_t[8], h->s_side));
         side_used = true;
-        k_metgrid_slowbits<<<dim3(slow_gx, (unsigned)(s1 - s0)), 128, 0, h->s_side>>>(d_jobs, d_slow_slabs, s0, d_sp, d_def, d_cnt);
+        k_metgrid_slowbits<1><<<dim3(slow_gx, (unsigned)(s1 - s0)), 128, 0, h->s_side>>>(d_jobs, d_slow_slabs, s0, d_sp, d_def, d_cnt);
         h->launches++;
         return 0;
     };
@@ -1841,7 +1895,10 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     } else {
         WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
         if (tile_cursor[1] > 0) {
-            k_metgrid_slowbits<<<dim3(slow_gx, (unsigned)slow_slabs.size()), 128, 0, h->stream>>>(d_jobs, d_slow_slabs, 0, d_sp, d_def, d_cnt);
+            // one launch: the heavy slabs' blocks come first and the almost empty bitmaps of the other slabs are
+            // scanned in their shadow (a separate coarse-grained launch for the latter, 16 words per thread, was slower:
+            // 0.191 vs 0.160 ms, the two launches no longer overlap)
+            k_metgrid_slowbits<1><<<dim3(slow_gx, (unsigned)slow_slabs.size()), 128, 0, h->stream>>>(d_jobs, d_slow_slabs, 0, d_sp, d_def, d_cnt);
             h->launches++;
         }
         WPS_CUDA(cudaEventRecord(h->ev_t[9], h->stream));
