@@ -107,3 +107,58 @@ def test_vertical_fill_and_raw_records_device_resident(orc, dhandle):
     r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, gx, 1, gy), halo(rec), -2, 1, 3)
     assert (d_bits.cpu().numpy() == np_ref).all()
     assert_bitexact(d_out.cpu().numpy(), r_ref, "raw record, device mode")
+
+
+@pytest.mark.parametrize("kind", ["categorical", "continuous"])
+def test_geogrid_tiles_pipelined_in_device_mode(handle, dhandle, kind):
+    """Device-pointer mode stages tile k+1 (decode + where_maps_to) on a second stream while tile k is accumulated, merged
+    and point-filled (two buffer sets, geogrid.cu geo_tile_begin).  The field must equal, bit for bit, what the
+    host-pointer mode (one tile at a time on one stream; checked against the oracle in test_gpu_geogrid.py) produces from
+    the same tiles -- for a categorical field fed as raw bytes and a continuous one fed as float tiles with a border."""
+    import torch
+    from wps_b200 import capi
+    from tests.test_gpu_geogrid import cat_tile, tiles_for, topo_tile
+    dev = torch.device("cuda", 0)
+    nx, ny, dx, dxdeg = 90, 70, 9000.0, 0.00833333
+    _, gdom = conus_like(nx, ny, dx, 30.0, 60.0, -98.0, 39.0, -105.0)
+    gx, gy = nx + 6, ny + 6
+    xlat, xlon = handle.xytoll_grid(gdom, capi.M, -2, -2, gx, gy)
+    kw = dict(dlat=dxdeg, dlon=dxdeg, known_x=1.0, known_y=1.0, known_lat=-89.99583, known_lon=-179.99583)
+    gsrc = capi.push_source_projection(capi.PROJ_LATLON, **kw)
+    dom_ll = (float(xlat.min()) - 0.3, float(xlat.max()) + 0.3, float(xlon.min()) - 0.3, float(xlon.max()) + 0.3)
+    if kind == "categorical":
+        itype, chain, nk, bdr, tn, msg = capi.CATEGORICAL, "nearest_neighbor", 21, 0, 100, 255.0
+    else:
+        itype, chain, nk, bdr, tn, msg = capi.SP_CONTINUOUS, "average_gcell(4.0)+four_pt+average_4pt", 1, 3, 100, 1e20
+    tiles = tiles_for(dom_ll, dxdeg, tn, bdr)
+    assert len(tiles) >= 6
+    tsz = tn + 2 * bdr
+    data = [(cat_tile(tx, ty, tsz, 1) if kind == "categorical" else topo_tile(tx, ty, tsz, 1)) for tx, ty in tiles]
+    init = np.random.default_rng(4).uniform(-1, 1, (nk, gy, gx)).astype(np.float32)
+
+    # host-pointer mode, float tiles
+    f_host = init.copy()
+    handle.geogrid_field_begin(gdom, capi.M, xlat, xlon, -2, -2, 1, f_host, None)
+    handle.geogrid_level_begin(gsrc, 1, itype, chain, msg, 1e20, -1.0, None, 1, 1)
+    for (tx, ty), t in zip(tiles, data):
+        handle.geogrid_add_tile(t, tx, ty, 1, bdr)
+    handle.geogrid_level_end()
+    p_host = np.zeros((gy, capi.nwords(gx)), np.int32)
+    handle.geogrid_field_finish(p_host)
+
+    # device-pointer mode: raw bytes (categorical) / float tiles (continuous), everything resident in HBM
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_xlat, d_xlon, d_field = t(xlat), t(xlon), t(init)
+    d_tiles = [t(x[0].astype(np.uint8)) if kind == "categorical" else t(x) for x in data]
+    torch.cuda.synchronize()
+    dhandle.geogrid_field_begin(gdom, capi.M, d_xlat, d_xlon, -2, -2, 1, d_field)
+    dhandle.geogrid_level_begin(gsrc, 1, itype, chain, msg, 1e20, -1.0, None, 1, 1)
+    for (tx, ty), dt in zip(tiles, d_tiles):
+        if kind == "categorical":
+            dhandle.geogrid_add_tile_raw(dt, (1, tsz, tsz), 1, 0, 0, 1, tx, ty, 1, bdr)
+        else:
+            dhandle.geogrid_add_tile(dt, tx, ty, 1, bdr)
+    dhandle.geogrid_level_end()
+    dhandle.geogrid_field_finish()
+    dhandle.synchronize()
+    assert_bitexact(d_field.cpu().numpy(), f_host, "geogrid field, device mode (pipelined tiles) vs host mode, %s" % kind)

@@ -23,8 +23,14 @@ struct GeoState {
     double* d_acc_sum = nullptr;      // per-tile accumulation: sums (continuous)
     int* d_touched = nullptr;         // per-tile: cell was reached by a credit attempt
     unsigned long long* d_invalid = nullptr;
-    float* d_tile = nullptr; size_t tile_cap = 0;
-    int2* d_wm = nullptr; size_t wm_cap = 0;
+    // Two sets of tile / where_maps_to buffers: in device-pointer mode the decode and where_maps_to kernels of tile k+1
+    // run on s_pre while tile k is accumulated, merged and point-filled on the handle's stream.
+    float* d_tile[2] = { nullptr, nullptr }; size_t tile_cap[2] = { 0, 0 };
+    int2* d_wm[2] = { nullptr, nullptr }; size_t wm_cap[2] = { 0, 0 };
+    cudaStream_t s_pre = nullptr;
+    cudaEvent_t ev_pre[2] = { nullptr, nullptr }, ev_used[2] = { nullptr, nullptr };
+    bool used_rec[2] = { false, false };
+    int parity = 0;
     void* d_raw = nullptr; size_t raw_cap = 0;
     Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
     void* d_lit = nullptr; size_t lit_bytes = 0;
@@ -58,6 +64,14 @@ struct GeoK {  // kernel-side view
 __device__ __forceinline__ bool bit_test(const int* w, int nxw, int ii, int jj) { return (w[(size_t)jj * nxw + (ii >> 5)] >> (ii & 31)) & 1; }
 __device__ __forceinline__ void bit_set_atomic(int* w, int nxw, int ii, int jj) { atomicOr(w + (size_t)jj * nxw + (ii >> 5), (int)(1u << (ii & 31))); }
 
+// per-tile state consumed by the kernels that follow on the handle's stream (k_geo_wm of the NEXT tile may already be
+// running on the other stream, so it cannot do this)
+__global__ void k_geo_tile_reset(int* tbbox, unsigned long long* counters)
+{
+    tbbox[0] = INT_MAX; tbbox[1] = INT_MAX; tbbox[2] = INT_MIN; tbbox[3] = INT_MIN;
+    counters[0] = 0ull; counters[1] = 0ull; counters[2] = 0ull;
+}
+
 // where_maps_to for every pixel of the tile (proc_point_module.F:245-310).  One block covers WM_T x WM_T pixels.
 // For a regular lat-lon source read onto a Lambert or polar-stereographic domain the projection separates into a
 // per-row term (latitude) and a per-column term (longitude): those 2*WM_T evaluations are shared by the WM_T^2
@@ -67,10 +81,6 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 {
     __shared__ float s_rm[WM_T], s_sin[WM_T], s_cos[WM_T], s_lat[WM_T], s_lon[WM_T];
     const int ti0 = blockIdx.x * WM_T, tj0 = blockIdx.y * WM_T, t = threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {   // per-tile state consumed by the kernels that follow in the stream
-        g.tbbox[0] = INT_MAX; g.tbbox[1] = INT_MAX; g.tbbox[2] = INT_MIN; g.tbbox[3] = INT_MIN;
-        g.counters[0] = 0ull; g.counters[1] = 0ull; g.counters[2] = 0ull;
-    }
     const bool separable = g.src.code == WPSGPU_PROJ_LATLON && (g.dom.code == WPSGPU_PROJ_LC || g.dom.code == WPSGPU_PROJ_PS);
     if (separable) {
         if (t < WM_T) {   // row terms: ijll_latlon gives lat from j alone
@@ -542,8 +552,13 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
     if (!h->geo) return;
     GeoState* s = h->geo;
     geo_free_field(s);
-    if (s->d_tile) cudaFree(s->d_tile);
-    if (s->d_wm) cudaFree(s->d_wm);
+    for (int b = 0; b < 2; ++b) {
+        if (s->d_tile[b]) cudaFree(s->d_tile[b]);
+        if (s->d_wm[b]) cudaFree(s->d_wm[b]);
+        if (s->ev_pre[b]) cudaEventDestroy(s->ev_pre[b]);
+        if (s->ev_used[b]) cudaEventDestroy(s->ev_used[b]);
+    }
+    if (s->s_pre) cudaStreamDestroy(s->s_pre);
     if (s->d_raw) cudaFree(s->d_raw);
     if (s->d_lit) cudaFree(s->d_lit);
     if (s->d_invalid) cudaFree(s->d_invalid);
@@ -629,19 +644,56 @@ int wpsgpu_geogrid_level_begin(wpsgpu_handle_t h, const wpsgpu_geo_level* l)
     return 0;
 }
 
-static int geo_process_tile(wpsgpu_ctx* h, int smx, int sMx, int smy, int sMy, int smz, int sMz, int bdr)
+// Buffers and stream of the coming tile.  Device-pointer mode: alternate between the two buffer sets and stage on s_pre
+// (ordered behind the previous user of the set); host-pointer mode: set 0 on the handle's stream (the call synchronises).
+static int geo_tile_begin(wpsgpu_ctx* h, size_t tile_floats, int* set, cudaStream_t* pre)
+{
+    GeoState* s = h->geo;
+    const bool pipelined = h->ptr_mode != WPSGPU_PTR_HOST;
+    if (!pipelined) { *set = 0; *pre = h->stream; }
+    else {
+        if (!s->s_pre) {
+            WPS_CUDA(cudaStreamCreateWithFlags(&s->s_pre, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                WPS_CUDA(cudaEventCreateWithFlags(&s->ev_pre[b], cudaEventDisableTiming));
+                WPS_CUDA(cudaEventCreateWithFlags(&s->ev_used[b], cudaEventDisableTiming));
+            }
+        }
+        *set = s->parity; s->parity ^= 1; *pre = s->s_pre;
+        if (s->used_rec[*set]) WPS_CUDA(cudaStreamWaitEvent(s->s_pre, s->ev_used[*set], 0));
+    }
+    if (tile_floats * sizeof(float) > s->tile_cap[*set]) {
+        WPS_CUDA(cudaStreamSynchronize(h->stream));
+        WPS_TRY(geo_grow((void**)&s->d_tile[*set], &s->tile_cap[*set], tile_floats * sizeof(float), *pre));
+    }
+    return 0;
+}
+
+static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, int sMx, int smy, int sMy, int smz, int sMz, int bdr)
 {
     GeoState* s = h->geo;
     int tnx = sMx - smx + 1, tny = sMy - smy + 1;
     GeoK g = make_k(h);
-    g.tile = s->d_tile; g.smx = smx; g.sMx = sMx; g.smy = smy; g.sMy = sMy; g.smz = smz; g.sMz = sMz; g.bdr = bdr; g.tnx = tnx; g.tny = tny;
+    g.tile = s->d_tile[set]; g.smx = smx; g.sMx = sMx; g.smy = smy; g.sMy = sMy; g.smz = smz; g.sMz = sMz; g.bdr = bdr; g.tnx = tnx; g.tny = tny;
     if (s->l.itype != WPSGPU_CATEGORICAL)
         WPS_CHECK(smz >= s->f.start_k && sMz <= s->f.end_k, -1, "source levels %d..%d outside field levels %d..%d", smz, sMz, s->f.start_k, s->f.end_k);
     dim3 b(32, 8);
-    if (s->l.itype == WPSGPU_CATEGORICAL || s->l.itype == WPSGPU_SP_CONTINUOUS) {
-        WPS_TRY(geo_grow((void**)&s->d_wm, &s->wm_cap, (size_t)tnx * tny * sizeof(int2), h->stream));
-        g.wm = s->d_wm;
-        k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, h->stream>>>(g);
+    const bool accum = s->l.itype == WPSGPU_CATEGORICAL || s->l.itype == WPSGPU_SP_CONTINUOUS;
+    if (accum) {
+        if ((size_t)tnx * tny * sizeof(int2) > s->wm_cap[set]) {
+            WPS_CUDA(cudaStreamSynchronize(h->stream));
+            WPS_TRY(geo_grow((void**)&s->d_wm[set], &s->wm_cap[set], (size_t)tnx * tny * sizeof(int2), pre));
+        }
+        g.wm = s->d_wm[set];
+        k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, pre>>>(g);
+        h->launches++;
+    }
+    if (pre != h->stream) {   // the handle's stream takes over once the tile and its mapping are in place
+        WPS_CUDA(cudaEventRecord(s->ev_pre[set], pre));
+        WPS_CUDA(cudaStreamWaitEvent(h->stream, s->ev_pre[set], 0));
+    }
+    if (accum) {
+        k_geo_tile_reset<<<1, 1, 0, h->stream>>>(g.tbbox, g.counters);
         int inx = tnx - 2 * bdr, iny = tny - 2 * bdr;
         if (inx > 0 && iny > 0) k_geo_accum<<<dim3((inx + 31) / 32, (iny + 7) / 8), b, 0, h->stream>>>(g);
         // areas of the half-area rule (proc_point_module.F:178-197)
@@ -671,6 +723,7 @@ static int geo_process_tile(wpsgpu_ctx* h, int smx, int sMx, int smy, int sMy, i
         h->launches += 2;
     }
     WPS_CUDA(cudaGetLastError());
+    if (pre != h->stream) { WPS_CUDA(cudaEventRecord(s->ev_used[set], h->stream)); s->used_rec[set] = true; }
     return 0;
 }
 
@@ -682,10 +735,12 @@ int wpsgpu_geogrid_add_tile(wpsgpu_handle_t h, const float* tile, int src_min_x,
     GeoState* s = h->geo;
     size_t n = (size_t)(src_max_x - src_min_x + 1) * (src_max_y - src_min_y + 1) * (src_max_z - src_min_z + 1);
     WPS_CHECK(n > 0, -1, "empty tile");
-    WPS_TRY(geo_grow((void**)&s->d_tile, &s->tile_cap, n * sizeof(float), h->stream));
-    WPS_CUDA(cudaMemcpyAsync(s->d_tile, tile, n * sizeof(float),
-                             h->ptr_mode == WPSGPU_PTR_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
-    WPS_TRY(geo_process_tile(h, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
+    int set = 0;
+    cudaStream_t pre = h->stream;
+    WPS_TRY(geo_tile_begin(h, n, &set, &pre));
+    WPS_CUDA(cudaMemcpyAsync(s->d_tile[set], tile, n * sizeof(float),
+                             h->ptr_mode == WPSGPU_PTR_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, pre));
+    WPS_TRY(geo_process_tile(h, set, pre, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
     if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -701,17 +756,19 @@ int wpsgpu_geogrid_add_tile_raw(wpsgpu_handle_t h, const void* bytes, int wordsi
     int tnx = src_max_x - src_min_x + 1, tny = src_max_y - src_min_y + 1, tnz = src_max_z - src_min_z + 1;
     size_t n = (size_t)tnx * tny * tnz;
     WPS_CHECK(n > 0, -1, "empty tile");
-    WPS_TRY(geo_grow((void**)&s->d_tile, &s->tile_cap, n * sizeof(float), h->stream));
+    int set = 0;
+    cudaStream_t pre = h->stream;
+    WPS_TRY(geo_tile_begin(h, n, &set, &pre));
     const unsigned char* d_bytes = (const unsigned char*)bytes;
     if (h->ptr_mode == WPSGPU_PTR_HOST) {
         WPS_TRY(geo_grow(&s->d_raw, &s->raw_cap, n * wordsize, h->stream));
         WPS_CUDA(cudaMemcpyAsync(s->d_raw, bytes, n * wordsize, cudaMemcpyHostToDevice, h->stream));
         d_bytes = (const unsigned char*)s->d_raw;
     }
-    k_geo_decode<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_bytes, wordsize, is_signed, endian == 1, row_order == 2, tnx, tny, tnz, s->d_tile);
+    k_geo_decode<<<(unsigned)((n + 255) / 256), 256, 0, pre>>>(d_bytes, wordsize, is_signed, endian == 1, row_order == 2, tnx, tny, tnz, s->d_tile[set]);
     h->launches++;
     WPS_CUDA(cudaGetLastError());
-    WPS_TRY(geo_process_tile(h, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
+    WPS_TRY(geo_process_tile(h, set, pre, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
     if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
