@@ -258,3 +258,56 @@ def test_patchwise_smoothing_on_device(orc, handle, opt, npass):
         handle.smooth(w, opt, npass)
         out[y0 - 1:y1, x0 - 1:x1] = w[y0 - ay0:y1 - ay0 + 1, x0 - ax0:x1 - ax0 + 1]
     assert_bitexact(out, whole, "patch-wise smoothing opt=%d npass=%d" % (opt, npass))
+
+
+def test_against_committed_geogrid_golden_vectors(handle):
+    """tests/golden/geogrid_small.npz (oracle outputs, committed): land-use counts from four raw tiles, fractions /
+    dominant category / landmask, the continuous accumulation with its point fallback, three smoothers and a Lambert wind
+    rotation -- all through the C ABI, without the oracle at run time."""
+    import os
+    from wps_b200 import capi
+    from tests.golden import make_golden_geogrid as mg
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "geogrid_small.npz"))
+    xlat, xlon = g["xlat"], g["xlon"]
+    gy, gx = xlat.shape
+    dom = capi.map_set(capi.PROJ_LC, **mg.KW_DOM)
+    src = capi.push_source_projection(capi.PROJ_LATLON, **mg.KW_SRC)
+
+    def field(itype, chain, nk, bdr, tile_fn, raw):
+        f = np.zeros((nk, gy, gx), np.float32)
+        handle.geogrid_field_begin(dom, capi.M, xlat, xlon, -2, -2, 1, f, None)
+        handle.geogrid_level_begin(src, 1, itype, chain, 1e20, 1e20, -1.0, None, 1, 1)
+        for tx, ty in mg.tile_origins(xlat, xlon, bdr):
+            t = tile_fn(tx, ty, mg.TN + 2 * bdr)
+            if raw:
+                handle.geogrid_add_tile_raw(np.ascontiguousarray(t[0].astype(np.uint8)), t.shape, 1, 0, 0, 1, tx, ty, 1, bdr)
+            else:
+                handle.geogrid_add_tile(t, tx, ty, 1, bdr)
+        handle.geogrid_level_end()
+        handle.geogrid_field_finish(np.zeros((gy, capi.nwords(gx)), np.int32))
+        return f
+
+    counts = field(capi.CATEGORICAL, "nearest_neighbor", 21, 0, mg.cat_tile, True)
+    assert_bitexact(counts, g["landuse_counts"], "golden land-use counts")
+    fr = counts.copy()
+    lm = np.zeros((gy, gx), np.float32)
+    dc = np.zeros((gy, gx), np.float32)
+    handle.fractions_dominant(fr, 1, 1e20, (17, 21), True, lm, dc)
+    assert_bitexact(fr, g["landuse_fractions"], "golden fractions")
+    assert_bitexact(dc, g["landuse_dominant"], "golden dominant category (landmask-aware, :699-727)")
+    assert_bitexact(lm, g["landmask"], "golden landmask")
+    fr2, dc2 = counts.copy(), np.zeros((gy, gx), np.float32)
+    handle.fractions_dominant(fr2, 1, 1e20, (), True, None, dc2)
+    assert_bitexact(dc2, g["landuse_dominant_plain"], "golden dominant category (plain, :1123-1144)")
+    hgt = field(capi.SP_CONTINUOUS, "average_gcell(4.0)+four_pt+average_4pt", 1, 3, mg.topo_tile, False)
+    # cell sums are binary64 on the device (DESIGN sec. 8): the north-star tolerance for average_gcell, 1e-6 relative
+    assert np.allclose(hgt, g["hgt"], rtol=1e-6, atol=0.0), "golden HGT"
+    for name, opt, npass in (("hgt_121_2", 1, 2), ("hgt_smth_desmth_1", 2, 1), ("hgt_smth_desmth_special_2", 3, 2)):
+        a = np.ascontiguousarray(g["hgt"][0] - np.float32(1600.0))
+        handle.smooth(a, opt, npass)
+        assert_bitexact(a, g[name], "golden smoother " + name)
+    u, v = g["u"].copy()[None], g["v"].copy()[None]
+    um = np.full((u.shape[1], capi.nwords(u.shape[2])), -1, np.int32)
+    vm = np.full((v.shape[1], capi.nwords(v.shape[2])), -1, np.int32)
+    handle.rotate_winds(1, dom, u, um, v, vm, g["xlon_u"], g["xlon_v"])
+    assert ulp_diff(u[0], g["u_rot"]).max() <= 1 and ulp_diff(v[0], g["v_rot"]).max() <= 1, "golden wind rotation"

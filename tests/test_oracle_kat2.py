@@ -178,3 +178,16 @@ def test_accum_categorical_counts_on_aligned_grids():
     ninv2 = O.accum_categorical(src, dom, O.M, tile2, 1, 1, 0, dst2, 1, 1, 1, processed, new_pts, 1, 0.0)
     assert ninv2 == 16
     assert dst2[0, 1, 1] == 0.0 and dst2[1, 1, 1] == 0.0 and dst2[0, 0, 0] == 2.0
+
+
+def test_geogrid_golden_regression():
+    """the oracle still produces the committed geogrid fixtures (tests/golden/make_golden_geogrid.py)"""
+    import os
+    from tests.golden import make_golden_geogrid as mg
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "geogrid_small.npz"))
+    now = mg.build()
+    assert sorted(g.files) == sorted(now.keys())
+    for k in g.files:
+        a, b = g[k], now[k]
+        assert a.shape == b.shape, k
+        assert np.array_equal(a.view(np.int32) if a.dtype == np.float32 else a, b.view(np.int32) if b.dtype == np.float32 else b), k
