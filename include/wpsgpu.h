@@ -236,7 +236,10 @@ int wpsgpu_geogrid_level_begin(wpsgpu_handle_t h, const wpsgpu_geo_level *l);
  * src_min_y:src_max_y, src_min_z:src_max_z) in global source-index space, bdr = tile_bdr.  Runs
  * accum_categorical / accum_continuous (proc_point_module.F:100,473) and then the per-point fallback of
  * calc_field's inner loop (:1408-1519, get_point proc_point_module.F:788) for the destination points
- * inside the tile (is_point_in_tile, :894). */
+ * inside the tile (is_point_in_tile, :894).  The call returns once the tile has been read (host-pointer mode: copied
+ * to the device; device-pointer mode: the work is queued and the caller keeps the buffer alive until the level ends);
+ * the tile is staged on a second stream while the previous one is still being accumulated, so the host can fetch the
+ * next tile from disk meanwhile.  Results are complete after wpsgpu_geogrid_field_finish. */
 int wpsgpu_geogrid_add_tile(wpsgpu_handle_t h, const float *tile, int src_min_x, int src_max_x, int src_min_y,
                             int src_max_y, int src_min_z, int src_max_z, int bdr);
 /* Same, from the raw file bytes of read_geogrid.c:26-140 (decode + row flip on device):

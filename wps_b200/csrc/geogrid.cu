@@ -31,7 +31,8 @@ struct GeoState {
     cudaEvent_t ev_pre[2] = { nullptr, nullptr }, ev_used[2] = { nullptr, nullptr };
     bool used_rec[2] = { false, false };
     int parity = 0;
-    void* d_raw = nullptr; size_t raw_cap = 0;
+    void* d_raw[2] = { nullptr, nullptr }; size_t raw_cap[2] = { 0, 0 };   // host-pointer mode: the file bytes of a tile
+    cudaEvent_t ev_h2d = nullptr;    // host-pointer mode: the caller's tile buffer has been read
     Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
     void* d_lit = nullptr; size_t lit_bytes = 0;
     // buffers kept across fields (grow-only): a geogrid run processes dozens of fields on the same patch
@@ -559,7 +560,8 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
         if (s->ev_used[b]) cudaEventDestroy(s->ev_used[b]);
     }
     if (s->s_pre) cudaStreamDestroy(s->s_pre);
-    if (s->d_raw) cudaFree(s->d_raw);
+    for (int b = 0; b < 2; ++b) if (s->d_raw[b]) cudaFree(s->d_raw[b]);
+    if (s->ev_h2d) cudaEventDestroy(s->ev_h2d);
     if (s->d_lit) cudaFree(s->d_lit);
     if (s->d_invalid) cudaFree(s->d_invalid);
     void* ptrs[] = { s->d_count, s->d_processed, s->d_level, s->d_src_xy, s->d_acc_cnt, s->d_acc_sum, s->d_touched, s->d_def, s->d_def2,
@@ -644,28 +646,36 @@ int wpsgpu_geogrid_level_begin(wpsgpu_handle_t h, const wpsgpu_geo_level* l)
     return 0;
 }
 
-// Buffers and stream of the coming tile.  Device-pointer mode: alternate between the two buffer sets and stage on s_pre
-// (ordered behind the previous user of the set); host-pointer mode: set 0 on the handle's stream (the call synchronises).
+// Buffers and stream of the coming tile: alternate between the two buffer sets and stage on s_pre (ordered behind the
+// previous user of the set).  In host-pointer mode the call returns as soon as the caller's buffer has been read
+// (geo_tile_staged), so the host reads the next tile from disk while this one is processed; wpsgpu_geogrid_level_end /
+// field_finish run on the handle's stream behind every tile.
 static int geo_tile_begin(wpsgpu_ctx* h, size_t tile_floats, int* set, cudaStream_t* pre)
 {
     GeoState* s = h->geo;
-    const bool pipelined = h->ptr_mode != WPSGPU_PTR_HOST;
-    if (!pipelined) { *set = 0; *pre = h->stream; }
-    else {
-        if (!s->s_pre) {
-            WPS_CUDA(cudaStreamCreateWithFlags(&s->s_pre, cudaStreamNonBlocking));
-            for (int b = 0; b < 2; ++b) {
-                WPS_CUDA(cudaEventCreateWithFlags(&s->ev_pre[b], cudaEventDisableTiming));
-                WPS_CUDA(cudaEventCreateWithFlags(&s->ev_used[b], cudaEventDisableTiming));
-            }
+    if (!s->s_pre) {
+        WPS_CUDA(cudaStreamCreateWithFlags(&s->s_pre, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            WPS_CUDA(cudaEventCreateWithFlags(&s->ev_pre[b], cudaEventDisableTiming));
+            WPS_CUDA(cudaEventCreateWithFlags(&s->ev_used[b], cudaEventDisableTiming));
         }
-        *set = s->parity; s->parity ^= 1; *pre = s->s_pre;
-        if (s->used_rec[*set]) WPS_CUDA(cudaStreamWaitEvent(s->s_pre, s->ev_used[*set], 0));
+        WPS_CUDA(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming | cudaEventBlockingSync));
     }
+    *set = s->parity; s->parity ^= 1; *pre = s->s_pre;
+    if (s->used_rec[*set]) WPS_CUDA(cudaStreamWaitEvent(s->s_pre, s->ev_used[*set], 0));
     if (tile_floats * sizeof(float) > s->tile_cap[*set]) {
         WPS_CUDA(cudaStreamSynchronize(h->stream));
         WPS_TRY(geo_grow((void**)&s->d_tile[*set], &s->tile_cap[*set], tile_floats * sizeof(float), *pre));
     }
+    return 0;
+}
+
+// host-pointer mode: wait until the copy out of the caller's buffer is done (not for the kernels)
+static int geo_tile_staged(wpsgpu_ctx* h, cudaStream_t pre)
+{
+    if (h->ptr_mode != WPSGPU_PTR_HOST) return 0;
+    WPS_CUDA(cudaEventRecord(h->geo->ev_h2d, pre));
+    WPS_CUDA(cudaEventSynchronize(h->geo->ev_h2d));
     return 0;
 }
 
@@ -740,8 +750,8 @@ int wpsgpu_geogrid_add_tile(wpsgpu_handle_t h, const float* tile, int src_min_x,
     WPS_TRY(geo_tile_begin(h, n, &set, &pre));
     WPS_CUDA(cudaMemcpyAsync(s->d_tile[set], tile, n * sizeof(float),
                              h->ptr_mode == WPSGPU_PTR_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, pre));
+    WPS_TRY(geo_tile_staged(h, pre));
     WPS_TRY(geo_process_tile(h, set, pre, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
-    if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -761,15 +771,18 @@ int wpsgpu_geogrid_add_tile_raw(wpsgpu_handle_t h, const void* bytes, int wordsi
     WPS_TRY(geo_tile_begin(h, n, &set, &pre));
     const unsigned char* d_bytes = (const unsigned char*)bytes;
     if (h->ptr_mode == WPSGPU_PTR_HOST) {
-        WPS_TRY(geo_grow(&s->d_raw, &s->raw_cap, n * wordsize, h->stream));
-        WPS_CUDA(cudaMemcpyAsync(s->d_raw, bytes, n * wordsize, cudaMemcpyHostToDevice, h->stream));
-        d_bytes = (const unsigned char*)s->d_raw;
+        if (n * wordsize > s->raw_cap[set]) {
+            WPS_CUDA(cudaStreamSynchronize(h->stream));
+            WPS_TRY(geo_grow(&s->d_raw[set], &s->raw_cap[set], n * wordsize, pre));
+        }
+        WPS_CUDA(cudaMemcpyAsync(s->d_raw[set], bytes, n * wordsize, cudaMemcpyHostToDevice, pre));
+        WPS_TRY(geo_tile_staged(h, pre));
+        d_bytes = (const unsigned char*)s->d_raw[set];
     }
     k_geo_decode<<<(unsigned)((n + 255) / 256), 256, 0, pre>>>(d_bytes, wordsize, is_signed, endian == 1, row_order == 2, tnx, tny, tnz, s->d_tile[set]);
     h->launches++;
     WPS_CUDA(cudaGetLastError());
     WPS_TRY(geo_process_tile(h, set, pre, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
-    if (h->ptr_mode == WPSGPU_PTR_HOST) WPS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
