@@ -25,9 +25,10 @@ METRIC = "metgrid output points/s (field*level*pt)"
 WORKLOAD = "config2: GFS 0.25deg 1440x721 x (34 isobaric + sfc) levels, default METGRID.TBL.ARW chains -> 3-km CONUS Lambert 1799x1059; 1 step = 1 time (190 slabs)"
 
 
-# WPSGPU_TILE16=1 selects the experimental tile-major sixteen_pt kernel (A/B measurements; slower on this workload)
-TILE16 = os.environ.get("WPSGPU_TILE16", "0") == "1"
-K16 = "k_metgrid_tile16" if TILE16 else "k_metgrid_fast16"
+# Arithmetic of the sixteen_pt chains (wpsgpu_metgrid_set_precision): 1 = north_star tolerance (1e-5, strip kernel, the
+# headline), 0 = bit-exact (k_metgrid_fast16).  WPSGPU_PRECISION=0 times the exact mode for A/B lines.
+PRECISION = int(os.environ.get("WPSGPU_PRECISION", "1"))
+K16 = "k_metgrid_strip16" if PRECISION == 1 else "k_metgrid_fast16"
 
 
 def env_int(k, d):
@@ -363,6 +364,7 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     config = synth.CONFIGS["config2"]
     h = capi.Handle(local_rank, capi.PTR_DEVICE)
+    h.metgrid_set_precision(PRECISION)
     w = build_workload(h, torch, dev, config)
     nx, ny = w["nx"], w["ny"]
     for gid, (xlat, xlon) in w["grids"].items():
@@ -418,6 +420,7 @@ def run_b200(args, rank, world, local_rank):
     e2e_value, e2e_s, h2d, d2h, e2e_raw_s, host_input_bytes = None, 0.0, 0, 0, None, 0
     if not args.no_e2e:
         hh = capi.Handle(local_rank, capi.PTR_HOST)
+        hh.metgrid_set_precision(PRECISION)
         for gid, (xlat, xlon) in w["grids"].items():
             hh.metgrid_set_grid(gid, xlat.cpu().numpy(), xlon.cpu().numpy(), 1, 1)
         hh.metgrid_set_landmask(0, w["landmask"].cpu().numpy())
@@ -480,7 +483,7 @@ def run_b200(args, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None   # DRAM bytes of the dominant kernel's launches in one step, from the committed ncu capture
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_tile16_traffic.json" if TILE16 else "r01_fast16_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_fast16_traffic.json")))
             if p3[1] >= p3[2] and abs(tj["kernel_points"] - kp) < 0.01 * kp:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:

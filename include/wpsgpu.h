@@ -172,6 +172,17 @@ int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);
  * [3] four_pt / nearest_neighbor first-method kernels, [4] slow-bitmap pass (points the first-method kernels handed
  * back to the full fallback chain), [5] deferred search passes, [6] first launch to last kernel of the flush. */
 int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float *ms7, double *points7);
+/* Arithmetic of chains that start with sixteen_pt (interp_module.F:1179-1374).
+ * WPSGPU_PRECISION_EXACT (default): every operation of sixteen_pt / oned is rounded separately in the reference's
+ *   order -- results are bit-identical to a build of the Fortran without FMA contraction.
+ * WPSGPU_PRECISION_TOLERANCE: the general branch of oned is evaluated as a weighted sum of the 16 stencil values with
+ *   fused multiply-adds (weights are level-independent); results agree with the reference to a few ulp of the largest
+ *   stencil value (<= 1e-5 relative to it, the bound the project allows for sixteen_pt).  Points where the reference
+ *   leaves the general branch -- missing or masked stencil values, exact zeros among the row interpolants, values below
+ *   1e-21 in magnitude -- are detected conservatively and still take the exact code; all other operators, masks,
+ *   new_pts bits and fill rules are unchanged and exact.  About 3x the throughput of the exact mode. */
+enum { WPSGPU_PRECISION_EXACT = 0, WPSGPU_PRECISION_TOLERANCE = 1 };
+int wpsgpu_metgrid_set_precision(wpsgpu_handle_t h, int mode);
 /* Testing aid: disable!=0 routes every job through the generic kernel (used to test both kernels against the oracle). */
 int wpsgpu_debug_disable_fast(wpsgpu_handle_t h, int disable);
 /* The average_gcell branch (:2331-2478) with metgrid's accum_continuous (:3347-3717); dom_proj is the

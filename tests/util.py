@@ -85,3 +85,24 @@ def assert_bitexact(a, b, what=""):
         k = tuple(bad[0])
         raise AssertionError("%s: %d of %d values differ; first at %s: %r vs %r" %
                              (what, (~same).sum(), same.size, k, a[k], b[k]))
+
+
+def assert_sixteen_pt_tolerance(r, r_ref, scale, what="", rtol=1e-5):
+    """Tolerance mode of the device path (wpsgpu_metgrid_set_precision): north_star allows 1e-5 relative for
+    sixteen_pt.  `scale` is the largest magnitude among the usable source values: the reference's own evaluation of
+    the overlapping parabolas carries a rounding error of a few ulp of the stencil values, so a result that is small
+    only through cancellation cannot be pinned more tightly than rtol * scale.  Magnitudes below 1e-19 are the
+    reference's stand-ins for zero (interp_module.F:1255-1257, :1317) and compare equal to 0.
+    Returns (share of points within a pure relative 1e-5, largest error / scale)."""
+    a = np.ascontiguousarray(r).astype(np.float64)
+    b = np.ascontiguousarray(r_ref).astype(np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b)
+    tol = rtol * np.maximum(np.abs(b), scale) + 1e-19
+    bad = err > tol
+    if bad.any():
+        k = tuple(np.argwhere(bad)[0])
+        raise AssertionError("%s: %d of %d values outside %g * max(|ref|, %g); first at %s: %r vs %r" %
+                             (what, bad.sum(), bad.size, rtol, scale, k, r[k], r_ref[k]))
+    pure = err <= rtol * np.abs(b) + 1e-19
+    return float(pure.mean()), float((err / max(scale, 1e-30)).max())

@@ -21,6 +21,7 @@ CONTINUOUS, CATEGORICAL, SP_CONTINUOUS = 0, 1, 2
 PROJ_LATLON, PROJ_LC, PROJ_PS, PROJ_MERC, PROJ_GAUSS, PROJ_CYL, PROJ_CASSINI = 0, 1, 2, 3, 4, 5, 6
 PROJ_PS_WGS84, PROJ_ALBERS_NAD83, PROJ_ROTLL = 102, 105, 203
 PTR_HOST, PTR_DEVICE = 0, 1
+PRECISION_EXACT, PRECISION_TOLERANCE = 0, 1
 MAX_OPS = 16
 MAX_GAUSS = 2048
 
@@ -325,6 +326,10 @@ class Handle:
         check(lib().wpsgpu_create_level(self._h, int(nx), int(ny), C.c_float(0.0 if fill_const is None else fill_const),
                                         C.c_void_p(ptr(src)), C.c_void_p(ptr(src_valid)), C.c_void_p(ptr(r_arr)),
                                         C.c_void_p(ptr(valid_mask))))
+
+    def metgrid_set_precision(self, mode):
+        """PRECISION_EXACT (default, bit-identical sixteen_pt) or PRECISION_TOLERANCE (north_star's 1e-5, ~3x faster)."""
+        check(lib().wpsgpu_metgrid_set_precision(self._h, int(mode)))
 
     def debug_disable_fast(self, disable=True):
         check(lib().wpsgpu_debug_disable_fast(self._h, int(disable)))

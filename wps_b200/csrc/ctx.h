@@ -70,20 +70,8 @@ struct DstGrid {
     size_t npts() const { return (size_t)nx() * ny(); }
 };
 
-// Destination points sorted by (destination tile of 32 x th points, source cell) for the tile-major sixteen_pt
-// kernel: built once per cached coordinate set, source-array extent and tile height, metgrid.cu get_tile_index
-struct TileIndex {
-    int dims[9];        // minx, maxx, miny, maxy, bx0, by0, bnx, bny, th it was built for
-    int* d_sidx;        // [n_fast] point index, sorted by (tile, cell, index); points the packed path cannot take are left out
-    float4* d_spt;      // [n_fast] {x, y offsets inside the source cell, rx, position inside the tile} in sorted order
-    int2* d_seg;        // [nseg + 1] (first sorted position, cell) of each run of points sharing tile and cell; sentinel (n_fast, 0)
-    int* d_tile_seg;    // [ntiles + 1] first segment of each tile
-    int n_fast, nseg, ntiles;
-};
-
 struct CoordCacheEntry {
     uint64_t grid_version;
-    std::vector<TileIndex> tidx;
     float2* d_xy;  // (rx, ry) of lltoxy(xlat, xlon) with the source projection, M stagger
     int bbox[4];   // min/max of floor(rx), floor(ry) over the destination grid (source-cell bounding box)
     int rbbox[4];  // the same including the lon+360 retry position of interp_to_latlon (:2640-2660) for points with lon < 0
@@ -94,8 +82,6 @@ inline void free_coord_entry(CoordCacheEntry& e)
 {
     cudaFree(e.d_xy);
     if (e.d_gauss) cudaFree(e.d_gauss);
-    for (TileIndex& c : e.tidx) { cudaFree(c.d_sidx); cudaFree(c.d_spt); cudaFree(c.d_seg); cudaFree(c.d_tile_seg); }
-    e.tidx.clear();
 }
 
 struct QueuedSlab {
@@ -141,6 +127,7 @@ struct wpsgpu_ctx {
     cudaEvent_t ev_copy = nullptr, ev_done = nullptr, ev_out_done = nullptr;
     int64_t h2d_bytes = 0, d2h_bytes = 0;           // bytes moved by the host-pointer paths of the metgrid flush
     bool async_pending = false;                     // wpsgpu_metgrid_flush_async: D2H copies may still read the arena
+    int precision = WPSGPU_PRECISION_EXACT;   // wpsgpu_metgrid_set_precision
     bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };
 

@@ -5,7 +5,6 @@
 #include <climits>
 #include "ctx.h"
 #include "interp.cuh"
-#include <cub/device/device_radix_sort.cuh>
 
 namespace wps {
 
@@ -36,7 +35,11 @@ struct Job {
     const unsigned char* cf;     // [npack][bny][bnx] bit lv = 4x4 stencil anchored here is "clean" for level lv
     float f_negzero, f_one;      // -0.0f and 1.0f as run-time values (see mul2/add2 in the packed kernel)
     int gcell;                   // average_gcell branch (:2331-2478): masked=both is not special there
-    int cellmajor;               // rec is laid out for k_metgrid_tile16: [bny][bnx][2*npack level pairs][6] float2
+    // tolerance mode (strip != 0, strip16.cuh): rec holds the window records [npack][bny][bnx] float4 over cells
+    // (bx0 + c, by0 + r) -- not clipped to the source array, columns / rows clamped instead --, thr the guard
+    // thresholds (two sets for masked=both), cf the slow pass's hint bits; strip = destination points per thread
+    int strip;
+    const float4* thr;
 };
 
 struct SlabPtrs {
@@ -411,21 +414,10 @@ __global__ void __launch_bounds__(256) k_pack16(const Job* __restrict__ jobs, co
     // layout [pack][row][group of 8 cells][term f][cell in group]: one 128-byte line holds one term of 8 neighbouring
     // cells, so the two cells a quarter-warp of destination points typically spans are served by one L1 wavefront,
     // and the six terms of a group are six consecutive lines
-    if (jb.cellmajor) {
-        // tile-major kernel: the six terms of one level PAIR are 48 contiguous bytes, the pairs of a cell follow one another
-        // (a warp whose lanes are level pairs reads a cell's record with three coalesced 16-byte loads per stencil row)
-        float4* rec = const_cast<float4*>(jb.rec) + (((size_t)cj * jb.bnx + ci) * (2 * jb.npack) + 2 * pack) * 3;
+    const int bnx8 = (jb.bnx + 7) >> 3;
+    float4* rec = const_cast<float4*>(jb.rec) + ((((size_t)pack * jb.bny + cj) * bnx8 + (ci >> 3)) * 6) * 8 + (ci & 7);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int f = 0; f < 3; ++f)
-                rec[h * 3 + f] = make_float4(out[2 * f][2 * h], out[2 * f][2 * h + 1], out[2 * f + 1][2 * h], out[2 * f + 1][2 * h + 1]);
-    } else {
-        const int bnx8 = (jb.bnx + 7) >> 3;
-        float4* rec = const_cast<float4*>(jb.rec) + ((((size_t)pack * jb.bny + cj) * bnx8 + (ci >> 3)) * 6) * 8 + (ci & 7);
-#pragma unroll
-        for (int f = 0; f < 6; ++f) rec[f * 8] = make_float4(out[f][0], out[f][1], out[f][2], out[f][3]);
-    }
+    for (int f = 0; f < 6; ++f) rec[f * 8] = make_float4(out[f][0], out[f][1], out[f][2], out[f][3]);
     const_cast<unsigned char*>(jb.cf)[o] = (unsigned char)cfbits;
 }
 
@@ -574,285 +566,6 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
             if (wlead) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
         }
     }
-}
-
-// ---- tile-major sixteen_pt kernel ---------------------------------------------------------------------------------
-// The point-major kernel above re-loads the 24 record terms (96 B) for every point-level; what limits it is the L1
-// return path, not arithmetic.  Here the lanes of a warp are level PAIRS (f32x2) x a few point slots, and the record of
-// a source cell -- 4 stencil rows x 6 terms per level -- is held in REGISTERS while the warp walks through every
-// destination point of its tile that falls into that cell.  A warp owns a destination tile of 32 x TH points and a
-// chunk of 2*LV levels.  The tile index (points sorted by (tile, source cell), cached with the coordinates) gives the
-// tile's points as "segments", one per source cell it overlaps; the record of the next segment is fetched into shared
-// memory with cp.async while the current one is being used, the point table of the next batch is fetched one batch ahead.
-// Results are staged in shared memory [point of the tile][level]; the write-out has lanes = 32 consecutive x, so every
-// store is a full 128-byte line and the new_pts / slow words come from ballots, as in the point-major kernel.
-// (A first version sorted by source cell only and wrote each cell's runs of ~7 points: those partial 32-byte sectors
-// doubled the DRAM traffic -- L2 read-modify-write -- and it ended up slower than the point-major kernel.)
-// Arithmetic is the same xpass2 / ypass2 sequence as above: bit-identical results.
-struct Tile16Params {
-    Job jb;
-    const float4* spt;       // TileIndex: per sorted point {x, y (offsets inside the source cell), rx, point of the tile as int bits}
-    const float* slm;        // landmask in sorted order, gathered per flush
-    const int2* seg;         // [nseg + 1] (first sorted position, source cell) of each segment; sentinel at the end
-    const int* tile_seg;     // [ntiles + 1] first segment of each tile
-    int nchunks;
-    float* r_arr[FAST_MAX_SLABS];
-    int* new_pts[FAST_MAX_SLABS];
-    int* slow[FAST_MAX_SLABS];
-};
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-
-template <int LV, int TH>
-__global__ void __launch_bounds__(32, 16)
-k_metgrid_tile16(const __grid_constant__ Tile16Params P)
-{
-    constexpr int PT = 32 / LV;                 // points in flight per warp
-    constexpr int NL = 2 * LV;                  // levels per chunk
-    constexpr int LS = NL + 1;                  // odd row stride of the staging tile: conflict-free for lanes = points
-    constexpr int TP = 32 * TH;                 // points per tile
-    constexpr int PB = 32;                      // points per batch
-    constexpr int PBX = PB + 2 * PT;            // table rows incl. the look-ahead of the pipelined loop
-    __shared__ float4 s_x[PBX], s_y[PBX];       // {x, x, 1-x, 1-x}, {y, y, 1-y, 1-y}
-    __shared__ int s_meta[PBX];                 // point of the tile | shift code << 29 (0: flag bits 0-3, 1: bits 4-7, 2: not a packed point)
-    __shared__ unsigned s_ok[TP + 1];           // per point: ok bits of the even levels (low half) and odd levels (high half); [TP] = dump row
-    __shared__ float s_stg[(TP + 1) * LS];
-    __shared__ float4 s_rec[2][12 * LV];        // record of the current / next segment: [stencil row * 3 + k][level pair]
-
-    const Job& jb = P.jb;
-    const int lane = threadIdx.x, chunk = blockIdx.y, tile = blockIdx.x;
-    const int tx = tile % jb.tiles_x, ty = tile / jb.tiles_x;
-    const bool act = lane < LV * PT;
-    const int pslot = act ? lane / LV : 0, lv = act ? lane % LV : 0;   // idle lanes shadow lane 0 (identical values, no ok bits)
-    const int nslab = jb.nslab, nx = jb.nx, ny = jb.ny;
-    const float msg = jb.msg;
-    const int ncells = jb.bnx * jb.bny, npairs = 2 * jb.npack;
-    const int gl = min(chunk * LV + lv, npairs - 1);   // level pair of this lane (clamped: lanes past the last pair idle)
-    const int lvbit = (gl & 1) * 2;
-    F2K k2;
-    k2.nz = f2(jb.f_negzero); k2.one = f2(jb.f_one);
-    const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
-    const float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
-
-    for (int q = lane; q < TP + 1; q += 32) s_ok[q] = 0u;
-
-    const int s_begin = __ldg(P.tile_seg + tile), s_end = __ldg(P.tile_seg + tile + 1);
-    if (s_end > s_begin) {
-        const int k_last = __ldg(&P.seg[s_end].x);   // end of the tile's run of the sorted list
-        // raw table entries of the coming batch, fetched one batch ahead (lanes = points)
-        float4 f_pt; float f_lm;
-        auto prefetch = [&](int k0) {
-            const int k = min(k0 + lane, k_last - 1);
-            f_pt = __ldg(P.spt + k);
-            f_lm = P.slm != nullptr ? __ldg(P.slm + k) : 0.0f;
-        };
-        // record of a cell -> shared memory (lanes of point slot 0, one level pair each), stencil rows j-1 .. j+2
-        // clamped like sixteen_pt (interp_module.F:1227-1241)
-        auto fetch_record = [&](int cell, int buf) {
-            if (lane < LV) {
-                const int ci = cell % jb.bnx, cj = cell / jb.bnx, j = jb.by0 + cj;
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    int r = min(max(j + l - 1, jb.miny), jb.maxy) - jb.by0;
-                    r = min(max(r, 0), jb.bny - 1);
-                    const float4* rp = jb.rec + (((size_t)r * jb.bnx + ci) * npairs + gl) * 3;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) cp_async16(&s_rec[buf][(l * 3 + k) * LV + lv], rp + k);
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        auto load_cf = [&](int cell) -> unsigned {
-            unsigned v;
-            // (volatile asm: a read-only load would be re-issued inside the point loop instead of being kept in a register)
-            asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(jb.cf + (size_t)(gl >> 1) * ncells + cell));
-            return v;
-        };
-
-        int2 sg = __ldg(P.seg + s_begin);          // (first position, cell) of the current segment
-        int kb = sg.x;
-        prefetch(kb);
-        fetch_record(sg.y, 0);
-        unsigned cf_next = load_cf(sg.y);
-        float2 rb[4], rc[4], rt1[4], rt2[4], rt3[4], rt4[4];
-        for (int s = s_begin; s < s_end; ++s) {
-            const int buf = (s - s_begin) & 1;
-            const int2 sgn = __ldg(P.seg + s + 1);  // next segment (or the sentinel)
-            const int seg_end = sgn.x;
-            // ---- this segment's record: shared memory -> registers; start fetching the next one ----
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                const float4 q0 = s_rec[buf][(l * 3 + 0) * LV + lv], q1 = s_rec[buf][(l * 3 + 1) * LV + lv], q2 = s_rec[buf][(l * 3 + 2) * LV + lv];
-                rb[l] = make_float2(q0.x, q0.y); rc[l] = make_float2(q0.z, q0.w);
-                rt1[l] = make_float2(q1.x, q1.y); rt2[l] = make_float2(q1.z, q1.w);
-                rt3[l] = make_float2(q2.x, q2.y); rt4[l] = make_float2(q2.z, q2.w);
-            }
-            const unsigned cfbyte = act ? cf_next : 0u;
-            if (s + 1 < s_end) { fetch_record(sgn.y, buf ^ 1); cf_next = load_cf(sgn.y); }
-            while (kb < seg_end) {
-                const int n = min(PB, seg_end - kb);
-                // ---- point table (lanes = points): level-independent part of interp_met_field's point logic (:2490-2541) ----
-                {
-                    const float xx = f_pt.z, lm = f_lm;
-                    int lp = __float_as_int(f_pt.w);
-                    const int di = jb.sm1 + tx * 32 + (lp & 31), dj = jb.sm2 + ty * TH + (lp >> 5), pw = jb.pw;
-                    const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
-                    int code = 0;
-                    bool valid = lane < n && !in_fill;
-                    if (both) { code = lm == 1.0f ? 1 : 0; valid = valid && (lm == 0.0f || lm == 1.0f); }
-                    else if (jb.landmask != nullptr && lm == jb.masked) valid = false;
-                    valid = valid && xx >= lo && xx <= hi;
-                    float x = f_pt.x, y = f_pt.y;
-                    if (!valid) { code = 2; x = 0.5f; y = 0.5f; lp = TP; }   // results of such rows go to the dump row
-                    s_x[lane] = make_float4(x, x, 1.0f - x, 1.0f - x);
-                    s_y[lane] = make_float4(y, y, 1.0f - y, 1.0f - y);
-                    s_meta[lane] = lp | (code << 29);
-                }
-                if (lane < PT) {   // rows past the batch that the last loop iteration touches
-                    s_x[PB + lane] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-                    s_y[PB + lane] = make_float4(0.5f, 0.5f, 0.5f, 0.5f);
-                    s_meta[PB + lane] = TP | (2 << 29);
-                }
-                __syncwarp();
-                const int kb_next = kb + n;
-                if (kb_next < k_last) prefetch(kb_next);
-                // ---- arithmetic (lanes = level pairs x point slots), table reads one iteration ahead ----
-                float4 X = s_x[pslot], Y = s_y[pslot];
-                int meta = s_meta[pslot];
-#pragma unroll 2
-                for (int p0 = 0; p0 < n; p0 += PT) {
-                    const int p = p0 + pslot;
-                    const float4 Xn = s_x[p + PT], Yn = s_y[p + PT];
-                    const int metan = s_meta[p + PT];
-                    const int sh = (meta >> 29) * 4, lp = meta & 0x1fffffff;
-                    const float2 x2 = make_float2(X.x, X.y), omx2 = make_float2(X.z, X.w), y2 = make_float2(Y.x, Y.y), omy2 = make_float2(Y.z, Y.w);
-                    float2 r[4];
-#pragma unroll
-                    for (int l = 0; l < 4; ++l) r[l] = xpass2(rb[l], rc[l], rt1[l], rt2[l], rt3[l], rt4[l], x2, omx2, k2);
-                    float2 v = ypass2(r[0], r[1], r[2], r[3], y2, omy2, k2);
-                    // oned's own guards in the y direction: general branch only when b*c /= 0 and a*d /= 0
-                    const float2 bc = mul2(r[1], r[2], k2), ad = mul2(r[0], r[3], k2);
-                    if (v.x == 1.0e-20f) v.x = 0.0f;
-                    if (v.y == 1.0e-20f) v.y = 0.0f;
-                    const unsigned cfb = (cfbyte >> sh) >> lvbit;   // sh = 8 (not a packed point, or a row past the batch): no bits
-                    const bool ok0 = (cfb & 1u) && bc.x != 0.0f && ad.x != 0.0f && v.x != msg;
-                    const bool ok1 = (cfb & 2u) && bc.y != 0.0f && ad.y != 0.0f && v.y != msg;
-                    s_stg[lp * LS + 2 * lv] = v.x; s_stg[lp * LS + 2 * lv + 1] = v.y;
-                    const unsigned w0 = __ballot_sync(0xffffffffu, ok0), w1 = __ballot_sync(0xffffffffu, ok1);
-                    if (lv == 0) {
-                        const unsigned m = (1u << LV) - 1u;
-                        s_ok[lp] = ((w0 >> (pslot * LV)) & m) | (((w1 >> (pslot * LV)) & m) << 16);
-                    }
-                    X = Xn; Y = Yn; meta = metan;
-                }
-                __syncwarp();
-                kb = kb_next;
-            }
-            sg = sgn;
-        }
-    }
-    __syncwarp();
-    // ---- write-out (lanes = 32 consecutive x): full lines, bitmap words by ballot; level-independent fill rules of
-    // interp_met_field (process_bdy_width interior :2490-2495, landmask == masked :2527-2530) ----
-    // Level-outer, row-inner: one base pointer per level; lane `row` collects the two bitmap words of row `row`, so the
-    // words of a level go out in one store each.
-    const int ii = tx * 32 + lane;
-    const bool active = ii < nx;
-    const float fill = jb.fill;
-    const int j0 = ty * TH, rows = min(TH, ny - j0);
-    const size_t idx0 = (size_t)j0 * nx + min(ii, nx - 1);
-    unsigned fillbits = 0, actbits = 0, okm[TH];
-#pragma unroll
-    for (int row = 0; row < TH; ++row) {
-        const int rr = min(row, rows - 1);   // rows past the grid shadow the last one; their bits stay clear
-        const int di = jb.sm1 + ii, dj = jb.sm2 + j0 + rr, pw = jb.pw;
-        bool fillpt = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
-        if (jb.landmask != nullptr && !both) fillpt = fillpt | (__ldg(jb.landmask + idx0 + (size_t)rr * nx) == jb.masked);
-        const bool on = active && row < rows;
-        fillbits |= (fillpt && on ? 1u : 0u) << row;
-        actbits |= (on ? 1u : 0u) << row;
-        okm[row] = on ? s_ok[row * 32 + lane] : 0u;
-    }
-    const size_t w0 = (size_t)(j0 + min(lane, rows - 1)) * jb.nxw + tx;
-    const float* stg = s_stg + lane * LS;
-#pragma unroll
-    for (int L = 0; L < NL; ++L) {
-        const int sl = chunk * NL + L;
-        if (sl >= nslab) break;
-        float* rp = P.r_arr[sl] + idx0;
-        unsigned myw = 0u, mys = 0u;
-#pragma unroll
-        for (int row = 0; row < TH; ++row) {
-            const float sv = stg[row * 32 * LS + L];
-            const unsigned fb = (fillbits >> row) & 1u;
-            const unsigned okb = fb | ((okm[row] >> ((L & 1) * 16 + (L >> 1))) & 1u);
-            const float v = fb ? fill : sv;
-            if (okb) *rp = v;
-            rp += nx;
-            const unsigned word = __ballot_sync(0xffffffffu, okb != 0u);
-            const unsigned sword = __ballot_sync(0xffffffffu, (((actbits >> row) & 1u) & ~okb) != 0u);
-            myw = lane == row ? word : myw;
-            mys = lane == row ? sword : mys;
-        }
-        if (lane < rows) { P.new_pts[sl][w0] = (int)myw; P.slow[sl][w0] = (int)mys; }
-    }
-}
-
-// ---- tile index: destination points sorted by (destination tile, source cell) ------------------------------------
-// key = tile * ncells + cell for points the packed path can take (the level- and job-independent part of the
-// point-major kernel's `fastpt` test: interior of the array by sixteen_pt's truncation test :1211, not on a node :1301,
-// stencil rows inside the box), the largest key for every other point.
-__global__ void k_tile_keys(const float2* __restrict__ xy, int n, int nx, int tiles_x, int th, int minx, int maxx, int miny, int maxy,
-                            int bx0, int by0, int bnx, int bny, unsigned long long nokey, unsigned long long* __restrict__ keys, int* __restrict__ vals)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const float2 p = __ldg(xy + k);
-    const float xx = p.x, yy = p.y;
-    unsigned long long key = nokey;
-    if (fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f && (int)xx >= minx && (int)xx <= maxx && (int)yy >= miny && (int)yy <= maxy) {
-        const int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
-        const float x = xx - (float)i, y = yy - (float)j;
-        if ((fabsf(x) > 0.0001f || fabsf(y) > 0.0001f) && i >= bx0 && i < bx0 + bnx && j >= by0 && j < by0 + bny) {
-            bool okr = true;
-#pragma unroll
-            for (int l = 0; l < 4; ++l) {
-                int r = min(max(j + l - 1, miny), maxy) - by0;
-                if (r < 0 || r >= bny) okr = false;
-            }
-            const int ii = k % nx, jj = k / nx;
-            const int tile = (jj / th) * tiles_x + ii / 32;
-            if (okr) key = (unsigned long long)tile * (unsigned long long)(bnx * bny) + (unsigned long long)((j - by0) * bnx + (i - bx0));
-        }
-    }
-    keys[k] = key;
-    vals[k] = k;
-}
-
-// per sorted point: offsets inside the source cell (sixteen_pt, interp_module.F:1216-1220), rx for the border test of
-// interp_to_latlon (:2620), and the point's position inside its tile
-__global__ void k_tile_gather_pt(const int* __restrict__ sidx, const float2* __restrict__ xy, int n, int nx, int th, float4* __restrict__ spt)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int idx = __ldg(sidx + k);
-    const float2 p = __ldg(xy + idx);
-    const int i = (int)(p.x + 0.00001f), j = (int)(p.y + 0.00001f);
-    const int ii = idx % nx, jj = idx / nx;
-    const int lp = (jj % th) * 32 + (ii & 31);
-    spt[k] = make_float4(p.x - (float)i, p.y - (float)j, p.x, __int_as_float(lp));
-}
-
-__global__ void k_cell_gather_f(const int* __restrict__ sidx, const float* __restrict__ a, int n, float* __restrict__ out)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) out[k] = __ldg(a + __ldg(sidx + k));
 }
 
 // ---- four_pt / nearest_neighbor first-method kernel ------------------------------------------------------------
@@ -1140,6 +853,10 @@ k_metgrid_search_literal(const Job* __restrict__ jobs, int njobs, const SlabPtrs
     }
 }
 
+}  // namespace wps
+#include "strip16.cuh"
+namespace wps {
+
 // ---- host side ---------------------------------------------------------------------------------------
 static std::string cache_key(int grid_id, const wpsgpu_proj& p)
 {
@@ -1186,114 +903,69 @@ static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
            x.field_stagger == y.field_stagger && x.use_landmask == y.use_landmask && x.process_bdy_width == y.process_bdy_width;
 }
 
-
-// Lane shape of the tile-major kernel: LV level pairs x 32/LV point slots per warp, tile height so that the staging tile
-// stays near 13 KB.  Score = lanes with real levels x how well a segment's points fill the point slots x share of the
-// per-segment set-up (worth about 1.5 loop iterations).
-static const int kTileLV[] = { 2, 4, 6, 8 };
-static int tile_th(int LV) { return LV == 2 ? 16 : (LV == 4 ? 12 : (LV == 6 ? 8 : 6)); }
-static void choose_tile_lv(int nslab, double pts_per_cell, int* lv, int* chunks)
+// Tolerance-mode sixteen_pt jobs of one pass -> as few strip launches as the parameter block allows.
+template <int R, bool BOTH>
+static void launch_strip_kernel(const StripParams& sp, unsigned tiles, unsigned chunks, bool stage, cudaStream_t st)
 {
-    const int npairs = (nslab + 1) / 2;
-    const double cw = std::max(1.0, sqrt(pts_per_cell));
-    double best = -1.0;
-    for (int LV : kTileLV) {
-        const int PT = 32 / LV, ch = (npairs + LV - 1) / LV, TH = tile_th(LV);
-        const double ppv = 32.0 * TH / ((32.0 / cw + 1.0) * (TH / cw + 1.0));
-        const double util = (double)nslab / (ch * 2.0 * LV) * (LV * PT / 32.0);
-        const double score = util * ppv / (PT * ceil(ppv / PT)) * ppv / (ppv + 1.5 * PT);
-        if (score > best) { best = score; *lv = LV; *chunks = ch; }
-    }
+    if (stage && R > 1) k_metgrid_strip16<R, BOTH, (R > 1)><<<dim3(tiles, chunks), 32, 0, st>>>(sp);
+    else k_metgrid_strip16<R, BOTH, false><<<dim3(tiles, chunks), 32, 0, st>>>(sp);
 }
 
-// Destination points sorted by (tile, source cell), cached with the coordinate set (TileIndex in ctx.h)
-static int get_tile_index(wpsgpu_ctx* h, CoordCacheEntry& e, int nx, int ny, const int dims[9], TileIndex* out)
+static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std::vector<int>& sel, const std::vector<SlabPtrs>& sp,
+                         float* dump_r, int* dump_w)
 {
-    for (const TileIndex& c : e.tidx)
-        if (!memcmp(c.dims, dims, sizeof(c.dims))) { *out = c; return 0; }
-    if (e.tidx.size() >= 8) {   // other source extents seen through the same projection: keep the cache small
-        WPS_CUDA(cudaStreamSynchronize(h->stream));
-        TileIndex& o = e.tidx.front();
-        cudaFree(o.d_sidx); cudaFree(o.d_spt); cudaFree(o.d_seg); cudaFree(o.d_tile_seg);
-        e.tidx.erase(e.tidx.begin());
-    }
-    TileIndex c;
-    memcpy(c.dims, dims, sizeof(c.dims));
-    const int npts = nx * ny, th = dims[8], ncells = dims[6] * dims[7];
-    const int tiles_x = (nx + 31) / 32, tiles_y = (ny + th - 1) / th;
-    c.ntiles = tiles_x * tiles_y;
-    const unsigned long long nokey = (unsigned long long)c.ntiles * (unsigned long long)ncells;
-    unsigned long long *d_keys = nullptr, *d_skeys = nullptr;
-    int *d_vals = nullptr, *d_svals = nullptr;
-    void* d_tmp = nullptr;
-    size_t tmp_bytes = 0;
-    c.d_sidx = nullptr; c.d_spt = nullptr; c.d_seg = nullptr; c.d_tile_seg = nullptr;
-    bool built = false;
-    struct Cleanup {   // temporaries always, the index arrays unless the build completed
-        unsigned long long **k, **sk; int **v, **sv; void** t; TileIndex* c; bool* built;
-        ~Cleanup()
-        {
-            cudaFree(*k); cudaFree(*sk); cudaFree(*v); cudaFree(*sv); cudaFree(*t);
-            if (!*built) { cudaFree(c->d_sidx); cudaFree(c->d_spt); cudaFree(c->d_seg); cudaFree(c->d_tile_seg); }
+    constexpr int SW = 1;
+    const bool stage = env_int("WPSGPU_STRIP_STAGE", 1, 0, 1) != 0;   // 0: windows straight from global memory (A/B measurements)
+    const int chunk_packs = env_int("WPSGPU_STRIP_CHUNK", 8, 1, 64);
+    for (int R : { 4, 2, 1 })
+        for (int both = 0; both < 2; ++both) {
+            StripParams P;
+            int nj = 0, ns = 0, nc = 0;
+            unsigned tiles = 0;
+            auto fire = [&]() {
+                if (nc == 0) return;
+                if (R == 4) { if (both) launch_strip_kernel<4, true>(P, tiles, nc, stage, h->stream); else launch_strip_kernel<4, false>(P, tiles, nc, stage, h->stream); }
+                else if (R == 2) { if (both) launch_strip_kernel<2, true>(P, tiles, nc, stage, h->stream); else launch_strip_kernel<2, false>(P, tiles, nc, stage, h->stream); }
+                else { if (both) launch_strip_kernel<1, true>(P, tiles, nc, stage, h->stream); else launch_strip_kernel<1, false>(P, tiles, nc, stage, h->stream); }
+                h->launches++;
+                nj = ns = nc = 0; tiles = 0;
+            };
+            for (int j : sel) {
+                const Job& jb = jobs[j];
+                const bool jboth = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
+                if (jb.strip != R || (int)jboth != both) continue;
+                const int nchunk = (jb.npack + chunk_packs - 1) / chunk_packs;
+                const int nslot = jb.npack * 4;      // levels past the last one write to the dump area
+                if (nj + 1 > STRIP_MAX_JOBS || ns + nslot > STRIP_MAX_SLABS || nc + nchunk > STRIP_MAX_CHUNKS) fire();
+                WPS_CHECK(nslot <= STRIP_MAX_SLABS && nchunk <= STRIP_MAX_CHUNKS, -3, "sixteen_pt job too large for one strip launch");
+                StripJob& q = P.job[nj];
+                q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr;
+                q.TB = jboth ? jb.thr + (size_t)jb.npack * jb.bnx * jb.bny : jb.thr;
+                q.nx = jb.nx; q.ny = jb.ny; q.nxw = jb.nxw; q.sm1 = jb.sm1; q.sm2 = jb.sm2;
+                q.sd1 = jb.sd1; q.ed1 = jb.ed1; q.sd2 = jb.sd2; q.ed2 = jb.ed2; q.pw = jb.pw;
+                q.minx = jb.minx; q.maxx = jb.maxx; q.miny = jb.miny; q.maxy = jb.maxy; q.bdr = jb.bdr;
+                q.px0 = jb.bx0; q.py0 = jb.by0; q.pnx = jb.bnx; q.pny = jb.bny;
+                q.nslab = jb.nslab; q.slab0 = ns;
+                q.tiles_x = jb.tiles_x; q.ntiles = jb.tiles_x * ((jb.ny + R * SW - 1) / (R * SW));
+                q.both = jboth ? 1 : 0; q.has_lm = jb.landmask != nullptr ? 1 : 0;
+                q.msg = jb.msg; q.fill = jb.fill; q.masked = jb.masked;
+                for (int k = 0; k < jb.nslab; ++k) {
+                    const SlabPtrs& p = sp[jb.slab0 + k];
+                    P.r_arr[ns + k] = p.r_arr; P.new_pts[ns + k] = p.new_pts; P.slow[ns + k] = p.slow;
+                }
+                for (int k = jb.nslab; k < nslot; ++k) { P.r_arr[ns + k] = dump_r; P.new_pts[ns + k] = dump_w; P.slow[ns + k] = dump_w; }
+                // chunks of equal size (e.g. 9 packs -> 5 + 4, not 8 + 1)
+                const int per = (jb.npack + nchunk - 1) / nchunk;
+                for (int c = 0; c < nchunk; ++c) {
+                    StripChunk& ck = P.chunk[nc++];
+                    ck.job = (short)nj; ck.pack0 = (short)(c * per); ck.npk = (short)std::min(per, jb.npack - c * per); ck.pad = 0;
+                }
+                tiles = std::max(tiles, (unsigned)q.ntiles);
+                ns += nslot; nj++;
+            }
+            fire();
         }
-    } cleanup{ &d_keys, &d_skeys, &d_vals, &d_svals, &d_tmp, &c, &built };
-    WPS_CUDA(cudaMalloc((void**)&d_keys, sizeof(unsigned long long) * (size_t)npts));
-    WPS_CUDA(cudaMalloc((void**)&d_skeys, sizeof(unsigned long long) * (size_t)npts));
-    WPS_CUDA(cudaMalloc((void**)&d_vals, sizeof(int) * (size_t)npts));
-    WPS_CUDA(cudaMalloc((void**)&d_svals, sizeof(int) * (size_t)npts));
-    k_tile_keys<<<(npts + 255) / 256, 256, 0, h->stream>>>(e.d_xy, npts, nx, tiles_x, th, dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7],
-                                                           nokey, d_keys, d_vals);
-    int bits = 1;
-    while (bits < 64 && (1ull << bits) <= nokey) ++bits;
-    WPS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_skeys, d_vals, d_svals, npts, 0, bits, h->stream));
-    WPS_CUDA(cudaMalloc(&d_tmp, tmp_bytes + 256));
-    WPS_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_skeys, d_vals, d_svals, npts, 0, bits, h->stream));   // stable: index order inside a segment
-    h->launches += 2;
     WPS_CUDA(cudaGetLastError());
-    // segments and the tiles' first segments: one linear pass on the host (once per coordinate set)
-    std::vector<unsigned long long> keys((size_t)npts);
-    WPS_CUDA(cudaMemcpyAsync(keys.data(), d_skeys, sizeof(unsigned long long) * (size_t)npts, cudaMemcpyDeviceToHost, h->stream));
-    WPS_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<int2> seg;
-    std::vector<int> tile_seg((size_t)c.ntiles + 1, 0);
-    int n_fast = 0, next_tile = 0;
-    for (; n_fast < npts && keys[n_fast] < nokey; ++n_fast) {
-        if (n_fast == 0 || keys[n_fast] != keys[n_fast - 1]) {
-            const int tile = (int)(keys[n_fast] / (unsigned long long)ncells), cell = (int)(keys[n_fast] % (unsigned long long)ncells);
-            while (next_tile <= tile) tile_seg[next_tile++] = (int)seg.size();
-            seg.push_back(make_int2(n_fast, cell));
-        }
-    }
-    while (next_tile <= c.ntiles) tile_seg[next_tile++] = (int)seg.size();
-    c.n_fast = n_fast;
-    c.nseg = (int)seg.size();
-    seg.push_back(make_int2(n_fast, 0));
-    WPS_CUDA(cudaMalloc((void**)&c.d_sidx, sizeof(int) * (size_t)std::max(n_fast, 1)));
-    WPS_CUDA(cudaMalloc((void**)&c.d_spt, sizeof(float4) * (size_t)std::max(n_fast, 1)));
-    WPS_CUDA(cudaMalloc((void**)&c.d_seg, sizeof(int2) * seg.size()));
-    WPS_CUDA(cudaMalloc((void**)&c.d_tile_seg, sizeof(int) * tile_seg.size()));
-    WPS_CUDA(cudaMemcpyAsync(c.d_seg, seg.data(), sizeof(int2) * seg.size(), cudaMemcpyHostToDevice, h->stream));
-    WPS_CUDA(cudaMemcpyAsync(c.d_tile_seg, tile_seg.data(), sizeof(int) * tile_seg.size(), cudaMemcpyHostToDevice, h->stream));
-    if (n_fast > 0) {
-        WPS_CUDA(cudaMemcpyAsync(c.d_sidx, d_svals, sizeof(int) * (size_t)n_fast, cudaMemcpyDeviceToDevice, h->stream));
-        k_tile_gather_pt<<<(n_fast + 255) / 256, 256, 0, h->stream>>>(c.d_sidx, e.d_xy, n_fast, nx, th, c.d_spt);
-        h->launches++;
-        WPS_CUDA(cudaGetLastError());
-    }
-    WPS_CUDA(cudaStreamSynchronize(h->stream));   // seg / tile_seg are pageable host vectors
-    built = true;
-    e.tidx.push_back(c);
-    *out = c;
-    return 0;
-}
-
-template <int LV, int TH>
-static int launch_tile16(const Tile16Params& tp, cudaStream_t st)
-{
-    // per device and context, so not cached in a static: a process may hold handles on several GPUs
-    WPS_CUDA(cudaFuncSetAttribute(k_metgrid_tile16<LV, TH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    const int tiles = tp.jb.tiles_x * ((tp.jb.ny + TH - 1) / TH);
-    k_metgrid_tile16<LV, TH><<<dim3((unsigned)tiles, (unsigned)tp.nchunks), 32, 0, st>>>(tp);
     return 0;
 }
 
@@ -1446,7 +1118,7 @@ int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float* ms3, double* points3)
 
 // One pass over a subset of the job groups: stage inputs on s_in, compute on the handle's stream, copy results back
 // on s_out.  In device-pointer mode all three are the handle's stream and nothing is copied.
-struct Box { int fast, bx0, by0, bnx, bny, npack; int tile_lv, tile_chunks; TileIndex tidx; };   // tile_lv > 0: tile-major kernel
+struct Box { int fast, bx0, by0, bnx, bny, npack, strip; };   // strip > 0: tolerance-mode strip kernel with that many points per thread
 struct FlushShared {
     std::vector<QueuedSlab>* queue;
     std::vector<std::vector<int>>* groups;
@@ -1457,7 +1129,6 @@ struct FlushShared {
     std::vector<char> tab;                   // host image of a pass's tables
     struct Sub { bool on; int x0, x1, y0, y1; };   // source columns / rows a group can touch (host mode, chains without search)
     std::vector<Sub> sub;
-    std::map<std::pair<const void*, const void*>, float*> sorted_lm;   // (landmask, cell index) -> landmask gathered in sorted order (arena)
     std::map<const void*, Sub> staged_sub;   // rectangle (rows for raw records) present in a partially staged slab
     // a slab staged before can be shared if it is complete or holds at least the rectangle wanted now
     bool reusable(const void* p, const Sub& want) const
@@ -1575,8 +1246,15 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         jb.f_negzero = -0.0f; jb.f_one = 1.0f;
         jb.gcell = q0.gcell ? 1 : 0;
         jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
-        jb.cellmajor = bx.fast == 1 && bx.tile_lv > 0;
-        if (jb.fast == 1) {
+        jb.strip = bx.fast == 1 ? bx.strip : 0;
+        if (jb.fast == 1 && jb.strip > 0) {
+            const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
+            const size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
+            jb.rec = (const float4*)h->arena.take(cells * sizeof(float4));
+            jb.thr = (const float4*)h->arena.take(cells * sizeof(float4) * (both ? 2 : 1));
+            jb.cf = (const unsigned char*)h->arena.take(cells);
+            WPS_CHECK(jb.rec && jb.thr && jb.cf, -3, "device arena exhausted (window records)");
+        } else if (jb.fast == 1) {
             size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
             size_t cells8 = (size_t)jb.npack * ((jb.bnx + 7) / 8 * 8) * jb.bny;
             jb.rec = (const float4*)h->arena.take(cells8 * 6 * sizeof(float4));
@@ -1655,6 +1333,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         }
         if (jb.fast)
             for (int k = 0; k < ns; ++k) {
+                // strip jobs: the four levels of a pack are flagged together and share one bitmap
+                if (jb.strip > 0 && (k & 3)) { sp[s0 + k].slow = sp[s0 + (k & ~3)].slow; continue; }
                 sp[s0 + k].slow = (int*)h->arena.take(wbytes);
                 WPS_CHECK(sp[s0 + k].slow != nullptr, -3, "device arena exhausted (slow bitmaps)");
             }
@@ -1702,9 +1382,13 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     for (const CopyRun& r : in_runs) { WPS_CUDA(cudaMemcpyAsync(r.d, r.h, r.bytes, cudaMemcpyHostToDevice, s_in)); h->h2d_bytes += (int64_t)r.bytes; }
     // All tables of this pass travel in ONE copy: [jobs | slab pointers | six int lists of njobs+1 entries]
     std::vector<int> pack_jobs;
-    int pack_cells = 0, pack_max = 0;
+    std::vector<PackWinTask> win_tasks;     // (job, pack) of the tolerance-mode pre-pass
+    int pack_cells = 0, pack_max = 0, win_tiles = 0;
     for (int j : cls_jobs[1])
-        if (jobs[j].fast == 1) {
+        if (jobs[j].fast == 1 && jobs[j].strip > 0) {
+            for (int pk = 0; pk < jobs[j].npack; ++pk) { PackWinTask t; t.job = j; t.pack = pk; win_tasks.push_back(t); }
+            win_tiles = std::max(win_tiles, ((jobs[j].bnx + 15) / 16) * ((jobs[j].bny + 15) / 16));
+        } else if (jobs[j].fast == 1) {
             pack_jobs.push_back(j);
             pack_cells = std::max(pack_cells, jobs[j].bnx * jobs[j].bny);
             pack_max = std::max(pack_max, jobs[j].npack);
@@ -1725,7 +1409,9 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             return heavy;
         }));
     const size_t off_slow = (off_dec + sizeof(DecodeTask) * decode_tasks.size() + 255) & ~size_t(255);
-    const size_t tab_bytes = off_slow + sizeof(int2) * slow_slabs.size();
+    const size_t off_win = (off_slow + sizeof(int2) * slow_slabs.size() + 255) & ~size_t(255);
+    const size_t tab_bytes = off_win + sizeof(PackWinTask) * win_tasks.size();
+    WPS_CHECK(win_tasks.size() < 65536, -3, "too many window-record packs in one flush");
     WPS_CHECK(slow_slabs.size() < 65536, -3, "too many first-method slabs in one flush");
     std::vector<char>& tab = fs.tab;
     tab.assign(tab_bytes, 0);
@@ -1739,6 +1425,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     }
     if (!decode_tasks.empty()) memcpy(tab.data() + off_dec, decode_tasks.data(), sizeof(DecodeTask) * decode_tasks.size());
     if (!slow_slabs.empty()) memcpy(tab.data() + off_slow, slow_slabs.data(), sizeof(int2) * slow_slabs.size());
+    if (!win_tasks.empty()) memcpy(tab.data() + off_win, win_tasks.data(), sizeof(PackWinTask) * win_tasks.size());
     char* d_tab = (char*)h->arena.take(tab_bytes);
     WPS_CHECK(d_tab != nullptr, -3, "device arena exhausted (tables)");
     WPS_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab_bytes, cudaMemcpyHostToDevice, s_in));   // pageable source: staged before the call returns
@@ -1806,6 +1493,10 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         k_pack16<<<dim3((pack_cells + 255) / 256, pack_max, (unsigned)pack_jobs.size()), 256, 0, h->stream>>>(d_jobs, d_pack_jobs, d_sp);
         h->launches++;
     }
+    if (!win_tasks.empty()) {
+        k_pack_win<<<dim3((unsigned)win_tiles, (unsigned)win_tasks.size()), 256, 0, h->stream>>>(d_jobs, (const PackWinTask*)(d_tab + off_win), d_sp);
+        h->launches++;
+    }
     WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
     // Optional (WPSGPU_OVERLAP=1): the slow-bitmap pass of a job is latency-bound (scattered loads, 128 registers) while
     // the first-method kernels keep the L1 data pipe busy, so it can run on a side stream as soon as its job's kernel
@@ -1835,43 +1526,33 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     };
     WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
     for (int j : cls_jobs[1]) {
-        if (jobs[j].fast != 1) continue;
+        if (jobs[j].fast != 1 || jobs[j].strip > 0) continue;
         FastParams fp;
         fp.jb = jobs[j];
         for (int k = 0; k < fp.jb.nslab; ++k) {
             const SlabPtrs& p = sp[fp.jb.slab0 + k];
             fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
         }
-        const Box& bx = fs.box[gsel[j]];
-        if (bx.tile_lv > 0) {
-            Tile16Params tp;
-            tp.jb = fp.jb; tp.spt = bx.tidx.d_spt; tp.slm = nullptr;
-            tp.seg = bx.tidx.d_seg; tp.tile_seg = bx.tidx.d_tile_seg; tp.nchunks = bx.tile_chunks;
-            memcpy(tp.r_arr, fp.r_arr, sizeof(tp.r_arr)); memcpy(tp.new_pts, fp.new_pts, sizeof(tp.new_pts)); memcpy(tp.slow, fp.slow, sizeof(tp.slow));
-            if (fp.jb.landmask != nullptr && bx.tidx.n_fast > 0) {   // landmask in sorted order, gathered once per flush and index
-                auto key = std::make_pair((const void*)fp.jb.landmask, (const void*)bx.tidx.d_sidx);
-                auto it = fs.sorted_lm.find(key);
-                if (it == fs.sorted_lm.end()) {
-                    float* d = (float*)h->arena.take(sizeof(float) * (size_t)bx.tidx.n_fast);
-                    WPS_CHECK(d != nullptr, -3, "device arena exhausted (sorted landmask)");
-                    k_cell_gather_f<<<(bx.tidx.n_fast + 255) / 256, 256, 0, h->stream>>>(bx.tidx.d_sidx, fp.jb.landmask, bx.tidx.n_fast, d);
-                    h->launches++;
-                    it = fs.sorted_lm.insert(std::make_pair(key, d)).first;
-                }
-                tp.slm = it->second;
-            }
-            switch (bx.tile_lv) {
-            case 2: WPS_TRY((launch_tile16<2, 16>(tp, h->stream))); break;
-            case 4: WPS_TRY((launch_tile16<4, 12>(tp, h->stream))); break;
-            case 6: WPS_TRY((launch_tile16<6, 8>(tp, h->stream))); break;
-            default: WPS_TRY((launch_tile16<8, 6>(tp, h->stream))); break;
-            }
-            h->launches++;
-        } else {
-            k_metgrid_fast16<<<fp.jb.tiles_x * ((fp.jb.ny + F16_Y - 1) / F16_Y), dim3(TILE_X, F16_Y), 0, h->stream>>>(fp);
-            h->launches++;
-        }
+        k_metgrid_fast16<<<fp.jb.tiles_x * ((fp.jb.ny + F16_Y - 1) / F16_Y), dim3(TILE_X, F16_Y), 0, h->stream>>>(fp);
+        h->launches++;
         WPS_TRY(slow_pass(j));
+    }
+    {
+        // tolerance mode: ONE strip launch per (points per thread, masked=both or not) takes every sixteen_pt job of the
+        // pass, cut into chunks of up to 8 packs (32 levels) -- 1-level surface fields no longer cost a launch each
+        std::vector<int> sj;
+        for (int j : cls_jobs[1]) if (jobs[j].fast == 1 && jobs[j].strip > 0) sj.push_back(j);
+        float* dump_r = nullptr;
+        int* dump_w = nullptr;
+        if (!sj.empty()) {
+            size_t mp = 0, mw = 0;
+            for (int j : sj) { mp = std::max(mp, (size_t)jobs[j].nx * jobs[j].ny); mw = std::max(mw, (size_t)jobs[j].nxw * jobs[j].ny); }
+            dump_r = (float*)h->arena.take(mp * sizeof(float));
+            dump_w = (int*)h->arena.take(mw * sizeof(int));
+            WPS_CHECK(dump_r && dump_w, -3, "device arena exhausted (strip dump area)");
+        }
+        WPS_TRY(launch_strips(h, jobs, sj, sp, dump_r, dump_w));
+        if (overlap) for (int j : sj) WPS_TRY(slow_pass(j));
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
     WPS_CUDA(cudaEventRecord(h->ev_t[6], h->stream));
@@ -2032,7 +1713,6 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
     // landmask logic selects a single interp mask, i.e. not masked=both); sixteen_pt additionally needs the
     // source-cell bounding box to be small against the destination grid (source coarser than the domain).
     const bool subrect_enabled = env_int("WPSGPU_SUBRECT", 1, 0, 1) != 0;
-    const bool tile16_enabled = env_int("WPSGPU_TILE16", 0, 0, 1) != 0;   // 1: tile-major kernel (k_metgrid_tile16) instead of the point-major k_metgrid_fast16
     fs.sub.resize(njobs);
     size_t need = (size_t)njobs * (sizeof(Job) + 256) + (size_t)nq * sizeof(SlabPtrs) + (1 << 20);
     size_t defer_entries = 0;
@@ -2068,27 +1748,33 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         }
         Box& b = fs.box[g];
         b.fast = 0; b.bx0 = b.by0 = b.bnx = b.bny = b.npack = 0;
-        b.tile_lv = 0; b.tile_chunks = 0;
+        b.strip = 0;
         const int* bb = &job_bbox[4 * g];
         bool simple_mask = !(q0.s.use_landmask && q0.fo.masked == WPSGPU_MASKED_BOTH);
         if (q0.gcell) {   // where_maps_to, sums, counts, decided bits
             need += (size_t)(q0.s.maxx - q0.s.minx + 1) * (q0.s.maxy - q0.s.miny + 1) * sizeof(int2) + dg.npts() * (sizeof(double) + sizeof(int)) +
                     (size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 2048;
         } else if (!h->disable_fast && (simple_mask || q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT)) {
-            if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
+            if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3] && h->precision == WPSGPU_PRECISION_TOLERANCE &&
+                (size_t)(bb[1] - bb[0] + 7) * (size_t)(bb[3] - bb[2] + 7) * 2 <= dg.npts()) {
+                // window records over the source cells the grid's points fall into, +-2 / +4 for the 5 x 5 windows; not
+                // clipped to the source array (the pre-pass clamps columns and rows as interp_module.F:1227-1241 does)
+                b.fast = 1; b.bx0 = bb[0] - 2; b.by0 = bb[2] - 2; b.bnx = bb[1] - bb[0] + 7; b.bny = bb[3] - bb[2] + 7;
+                b.npack = ((int)groups[g].size() + 3) / 4;
+                // points per thread: a strip must stay within two source cells in each direction
+                const double ppc = sqrt((double)dg.npts() / ((double)(bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1)));
+                b.strip = ppc >= 5.0 ? 4 : (ppc >= 2.5 ? 2 : 1);
+                b.strip = env_int("WPSGPU_STRIP", b.strip, 1, 4) == 3 ? 2 : env_int("WPSGPU_STRIP", b.strip, 1, 4);
+                const bool both = q0.s.use_landmask && q0.fo.masked == WPSGPU_MASKED_BOTH;
+                need += (size_t)b.npack * b.bnx * b.bny * (sizeof(float4) * (both ? 3 : 2) + 1) + 1024;
+                need += dg.npts() * sizeof(float) + (size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 512;   // dump area (per pass at most once)
+            } else if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
                 long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);
                 long y0 = std::max<long>(q0.s.miny, (long)bb[2] - 2), y1 = std::min<long>(q0.s.maxy, (long)bb[3] + 4);
                 if (x1 >= x0 && y1 >= y0 && (size_t)(x1 - x0 + 1) * (size_t)(y1 - y0 + 1) * 2 <= dg.npts()) {
                     b.fast = 1; b.bx0 = (int)x0; b.by0 = (int)y0; b.bnx = (int)(x1 - x0 + 1); b.bny = (int)(y1 - y0 + 1);
                     b.npack = ((int)groups[g].size() + 3) / 4;
                     need += (size_t)b.npack * (b.bnx + 8) * b.bny * (6 * sizeof(float4) + 1) + 1024;
-                    if (tile16_enabled && dg.npts() < (size_t(1) << 29)) {
-                        const double ppc = 1.6 * (double)dg.npts() / ((double)b.bnx * b.bny);   // destination points per source cell, roughly
-                        choose_tile_lv((int)groups[g].size(), ppc, &b.tile_lv, &b.tile_chunks);
-                        const int dims[9] = { q0.s.minx, q0.s.maxx, q0.s.miny, q0.s.maxy, b.bx0, b.by0, b.bnx, b.bny, tile_th(b.tile_lv) };
-                        WPS_TRY(get_tile_index(h, *job_entry[g], dg.nx(), dg.ny(), dims, &b.tidx));
-                        need += sizeof(float) * (size_t)b.tidx.n_fast + 512;   // sorted landmask
-                    }
                 }
             } else if (q0.fo.ops[0] == WPSGPU_FOUR_POINT) b.fast = 2;
             else if (q0.fo.ops[0] == WPSGPU_N_NEIGHBOR) b.fast = 3;
@@ -2166,6 +1852,14 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         fprintf(stderr, "[wpsgpu] pipeline: %d groups, host issue %.2f ms, H2D done %.2f ms, kernels done %.2f ms, D2H done %.2f ms\n", njobs, issue_ms, a, b, c);
         for (int k = 0; k < 4; ++k) cudaEventDestroy(tr[k]);
     }
+    return 0;
+}
+
+int wpsgpu_metgrid_set_precision(wpsgpu_handle_t h, int mode)
+{
+    WPS_CHECK(h != nullptr, -1, "NULL handle");
+    WPS_CHECK(mode == WPSGPU_PRECISION_EXACT || mode == WPSGPU_PRECISION_TOLERANCE, -1, "unknown precision mode %d", mode);
+    h->precision = mode;
     return 0;
 }
 

@@ -1,0 +1,442 @@
+// strip16.cuh -- the tolerance-mode sixteen_pt path (WPSGPU_PRECISION_TOLERANCE): window records + strip kernel.
+// Included by metgrid.cu after Job / SlabPtrs.
+//
+// sixteen_pt (interp_module.F:1179-1374) is linear in the 16 stencil values whenever `oned` takes its general branch
+// in all five calls: oned(x,a,b,c,d) = wa(x)*a + wb(x)*b + wc(x)*c + wd(x)*d with
+//     wa = -u*u*x/2,  wb = u*(1-x*x) + x*u*(1+u)/2,  wc = u*x*(1+x)/2 + x*(1-u*u),  wd = -x*x*u/2,   u = 1-x
+// (expand :1370).  The weights are level-independent, so a destination point costs 4 x 4 + 4 fused multiply-adds per
+// level instead of the 67 separately rounded operations of the bit-exact kernel.  north_star allows 1e-5 relative
+// for sixteen_pt; results agree with the reference's nested evaluation to a few ulp of the largest stencil value.
+//
+// A thread owns a vertical STRIP of R destination points (same x, R consecutive y): with a source grid much coarser
+// than the domain their stencils overlap almost completely, so the thread loads ONE 5 x 5 window of source cells per
+// pack of four levels (float4 = 4 levels) and evaluates all R points from registers -- 25 vector loads serve 4*R
+// point-levels (k_metgrid_fast16: 24 per 4), which takes the kernel off the L1 return path.  A point whose cell is
+// (i0+di, j0+dj), di, dj in {0, 1}, relative to the window origin gets its four weights shifted by (di, dj) inside
+// five window weights (one of them 0).
+//
+// What the linear form cannot reproduce is decided per window by the pre-pass and per point-level by a guard:
+//  * a missing or interp-masked value, a NaN/Inf, or a value so small that `b*c`, `a*d` could underflow to 0 in the
+//    x direction (|v| < 1e-21) anywhere in the window  -> threshold +Inf, the points go to the exact slow path;
+//  * oned's guards in the y direction act on the four row interpolants: a row result within 2^-18 of the window's
+//    largest magnitude of zero (the reference's own value may then be exactly 0, or the products may underflow)
+//    -> slow path.  Everything else provably takes the general branch in the reference as well.
+// Zeros are replaced by 1.E-20 in the window records exactly as :1255-1257 does, and a result equal to 1.E-20 becomes 0
+// (:1317).
+#pragma once
+#include <type_traits>
+
+namespace wps {
+
+constexpr int STRIP_MAX_JOBS = 24;
+constexpr int STRIP_MAX_SLABS = 320;
+constexpr int STRIP_MAX_CHUNKS = 96;
+
+struct StripJob {
+    const float2* xy;
+    const float* landmask;
+    const float4* P;             // window records [npack][pny][pnx], float4 = 4 levels of source cell (px0 + c, py0 + r), clamped like :1227-1241
+    const float4* TA;            // guard thresholds per window ORIGIN cell, same index space; +Inf = window not clean
+    const float4* TB;            // masked=both: thresholds under interp_water_mask (land points); TA is interp_land_mask then
+    int nx, ny, nxw, sm1, sm2, sd1, ed1, sd2, ed2, pw;
+    int minx, maxx, miny, maxy, bdr;
+    int px0, py0, pnx, pny;
+    int nslab, slab0;            // slabs [slab0, slab0 + nslab) of the pointer tables below
+    int tiles_x, ntiles;
+    int both, has_lm;
+    float msg, fill, masked;
+};
+
+struct StripChunk { short job, pack0, npk, pad; };
+
+struct StripParams {
+    StripJob job[STRIP_MAX_JOBS];
+    StripChunk chunk[STRIP_MAX_CHUNKS];
+    float* r_arr[STRIP_MAX_SLABS];
+    int* new_pts[STRIP_MAX_SLABS];
+    int* slow[STRIP_MAX_SLABS];
+};
+
+// ---- pre-pass: window records, guard thresholds and the slow pass's hints ------------------------------------------------
+// One block = 16 x 16 cells of the window array of one (job, pack).  The 20 x 20 halo tile of the four levels goes
+// through shared memory once; every thread then writes its cell's record and derives the threshold of the 5 x 5 window
+// whose ORIGIN is that cell (cells c-1..c+3, r-1..r+3) and the hint bits of the 4 x 4 stencil anchored there.
+struct PackWinTask { int job, pack; };
+
+__global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, const PackWinTask* __restrict__ tasks,
+                                                  const SlabPtrs* __restrict__ slabs)
+{
+    const PackWinTask t = tasks[blockIdx.y];
+    const Job& jb = jobs[t.job];
+    const int pnx = jb.bnx, pny = jb.bny, ntx = (pnx + 15) >> 4;
+    const int bx = blockIdx.x % ntx, by = blockIdx.x / ntx;
+    if (by * 16 >= pny) return;
+    __shared__ float s_v[4][20][21];
+    __shared__ unsigned char s_m[20][20];     // bit 0: unusable under mask A, bit 1: under mask B
+    const int tid = threadIdx.x;
+    const int sx = jb.minx, ex = jb.maxx, sy = jb.miny, ey = jb.maxy, snx = ex - sx + 1;
+    const float msg = jb.msg;
+    const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
+    const int selA = both ? 1 : 0;
+    const float* src[4];
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) {
+        const int sl = t.pack * 4 + lv;
+        src[lv] = sl < jb.nslab ? slabs[jb.slab0 + sl].src : nullptr;
+    }
+    for (int e = tid; e < 400; e += 256) {
+        const int c = e % 20, r = e / 20;
+        const int gx = min(max(jb.bx0 + bx * 16 - 1 + c, sx), ex), gy = min(max(jb.by0 + by * 16 - 1 + r, sy), ey);
+        const size_t off = (size_t)(gy - sy) * snx + (gx - sx);
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {
+            float v = 0.0f;
+            if (src[lv]) {
+                v = __ldg(src[lv] + off);
+                if (v == 0.0f && msg != 0.0f) v = 1.0e-20f;     // interp_module.F:1255-1257
+            }
+            s_v[lv][r][c] = v;
+        }
+        unsigned m = 0;
+        auto unusable = [&](int sel) -> bool {
+            if (!jb.mask[sel]) return false;
+            const float mv = __ldg(jb.mask[sel] + off);
+            return jb.mask_rel[sel] == REL_GT ? (mv > jb.mask_val[sel]) : (jb.mask_rel[sel] == REL_LT ? (mv < jb.mask_val[sel]) : (mv == jb.mask_val[sel]));
+        };
+        if (unusable(selA)) m |= 1u;
+        if (both && unusable(2)) m |= 2u;
+        s_m[r][c] = (unsigned char)m;
+    }
+    __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4;
+    const int cx = bx * 16 + tx, cy = by * 16 + ty;
+    if (cx >= pnx || cy >= pny) return;
+    const int c0 = tx + 1, r0 = ty + 1;
+    const size_t o = ((size_t)t.pack * pny + cy) * pnx + cx;
+    const_cast<float4*>(jb.rec)[o] = make_float4(s_v[0][r0][c0], s_v[1][r0][c0], s_v[2][r0][c0], s_v[3][r0][c0]);
+    unsigned mwin = 0, mst = 0;
+#pragma unroll
+    for (int r = -1; r <= 3; ++r)
+#pragma unroll
+        for (int c = -1; c <= 3; ++c) {
+            const unsigned m = s_m[r0 + r][c0 + c];
+            mwin |= m;
+            if (r <= 2 && c <= 2) mst |= m;
+        }
+    float thrA[4], thrB[4];
+    unsigned cfbits = 0;
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) {
+        if (!src[lv]) { thrA[lv] = thrB[lv] = -1.0f; continue; }     // level beyond the job's last: records are 0, never flagged
+        float mx = 0.0f, mn = 3.0e38f;
+        bool bad = false, stmsg = false;
+#pragma unroll
+        for (int r = -1; r <= 3; ++r)
+#pragma unroll
+            for (int c = -1; c <= 3; ++c) {
+                const float v = s_v[lv][r0 + r][c0 + c], a = fabsf(v);
+                const bool ismsg = v == msg;
+                bad = bad || ismsg || !(a <= 3.0e38f);
+                if (r <= 2 && c <= 2) stmsg = stmsg || ismsg;
+                mx = fmaxf(mx, a); mn = fminf(mn, a);
+            }
+        const bool clean = !bad && mn >= 1.0e-21f;
+        const float thr = fmaxf(mx * 3.814697265625e-6f, 1.0e-21f);
+        const float inf = __int_as_float(0x7f800000);
+        thrA[lv] = (clean && !(mwin & 1u)) ? thr : inf;
+        thrB[lv] = (clean && !(mwin & 2u)) ? thr : inf;
+        // single-mask jobs: bit 4+lv = the 4 x 4 stencil anchored here holds a missing or masked value, so sixteen_pt is
+        // certain to hand over to the next method (:1244-1270) and the slow pass may start the chain there
+        if (!both && (stmsg || (mst & 1u))) cfbits |= 16u << lv;
+    }
+    const size_t tstride = (size_t)jb.npack * pny * pnx;     // TB follows TA
+    float4* T = const_cast<float4*>(jb.thr);
+    T[o] = make_float4(thrA[0], thrA[1], thrA[2], thrA[3]);
+    if (both) T[tstride + o] = make_float4(thrB[0], thrB[1], thrB[2], thrB[3]);
+    const_cast<unsigned char*>(jb.cf)[o] = (unsigned char)cfbits;
+}
+
+// ---- strip kernel --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
+// predicated stores: the compiler otherwise wraps every `if (ok) store` around a ballot in a branch + reconvergence pair
+__device__ __forceinline__ void st_f32_if(bool p, void* a, float v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.f32 [%1], %2; }" ::"r"((unsigned)p), "l"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_u32_if(bool p, void* a, unsigned v)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u32 [%1], %2; }" ::"r"((unsigned)p), "l"(a), "r"(v) : "memory");
+}
+
+// mbarrier + bulk-copy (TMA engine, SASS UBLKCP) primitives of the window ring
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Window ring of the staged variant: each warp (= block) copies the bounding box of its lanes' windows for pack p+2 into
+// shared memory with one bulk copy per box row while pack p is computed -- the north-star design ("each thread block
+// TMA-stages the compact source-grid bounding box its destination tile maps onto").  Box: up to 16 x 8 cells of 16 B.
+constexpr int SBW = 16, SBH = 8, SROW = SBW + 1, SNS = 3;     // row stride 17 cells: rows start in different banks
+
+// R points per thread, WIN = window edge (5 when R > 1: cells of a strip may differ by one in each direction; 4 for R = 1).
+// One warp per block.  STAGE: windows come from the shared-memory ring (bulk copies), else straight from L1/L2.
+template <int R, bool BOTH, bool STAGE>
+__global__ void __launch_bounds__(32, R == 4 ? 16 : 20)
+k_metgrid_strip16(const __grid_constant__ StripParams P)
+{
+    constexpr int WIN = R > 1 ? 5 : 4;
+    const StripChunk ch = P.chunk[blockIdx.y];
+    const StripJob& jb = P.job[ch.job];
+    if ((int)blockIdx.x >= jb.ntiles) return;
+    const int lane = threadIdx.x;
+    const int tx = blockIdx.x % jb.tiles_x, ty = blockIdx.x / jb.tiles_x;
+    const int nx = jb.nx, ny = jb.ny;
+    const int ii = tx * 32 + lane, jj0 = ty * R;
+    const float msg = jb.msg;
+
+    // ---- level-independent part: interp_met_field's point logic (:2490-2541) and sixteen_pt's cell arithmetic (:1211-1225)
+    bool fastpt[R], active[R];
+    int ci[R], cj[R];
+    float fx[R], fy[R];
+    int useB = 0;                                // bit p: point p takes the thresholds of interp_water_mask (masked=both, land point)
+    unsigned fillm = 0;                          // bit p: the point receives fill_missing (process_bdy_width interior, landmask == masked)
+    int i0 = INT_MAX, j0 = INT_MAX;
+    const float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+        const int jj = jj0 + p;
+        active[p] = ii < nx && jj < ny;
+        fastpt[p] = false; ci[p] = 0; cj[p] = 0; fx[p] = 0.0f; fy[p] = 0.0f;
+        if (!active[p]) continue;
+        const size_t idx = (size_t)jj * nx + ii;
+        const float2 xy = __ldg(jb.xy + idx);
+        const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
+        const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+        const float lm = jb.has_lm ? __ldg(jb.landmask + idx) : 0.0f;
+        bool lm_ok = true, fill = in_fill;
+        if (BOTH) {
+            if (lm == 1.0f) useB |= 1 << p;
+            lm_ok = lm == 0.0f || lm == 1.0f;
+        } else fill = fill || (jb.has_lm && lm == jb.masked);
+        if (fill) fillm |= 1u << p;
+        const float xx = xy.x, yy = xy.y;
+        if (!fill && lm_ok && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f &&
+            (int)xx >= jb.minx && (int)xx <= jb.maxx && (int)yy >= jb.miny && (int)yy <= jb.maxy) {
+            const int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
+            const float x = xx - (float)i, y = yy - (float)j;
+            // a window with origin (i, j) must lie inside the record array, whatever the other points of the strip do
+            if ((fabsf(x) > 0.0001f || fabsf(y) > 0.0001f) && i - 1 >= jb.px0 && i + WIN - 2 < jb.px0 + jb.pnx &&
+                j - 1 >= jb.py0 && j + WIN - 2 < jb.py0 + jb.pny) {
+                fastpt[p] = true; ci[p] = i; cj[p] = j; fx[p] = x; fy[p] = y;
+                i0 = min(i0, i); j0 = min(j0, j);
+            }
+        }
+    }
+    const bool anyfast = i0 != INT_MAX;
+    if (!anyfast) { i0 = jb.px0 + 1; j0 = jb.py0 + 1; }
+    // window weights: the point's four oned weights at offset (di, dj) inside the window, x weights duplicated for
+    // the packed level-pair arithmetic
+    float2 wx[R][WIN];
+    float wy[R][WIN];
+    unsigned fastm = 0;
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+        const int di = ci[p] - i0, dj = cj[p] - j0;
+        if (fastpt[p] && (di > WIN - 4 || dj > WIN - 4)) fastpt[p] = false;     // strip spans more than two cells: slow path
+        if (fastpt[p]) fastm |= 1u << p;
+        float w4x[4], w4y[4];
+        {
+            const float x = fx[p], u = 1.0f - x;
+            w4x[0] = -0.5f * u * u * x; w4x[3] = -0.5f * x * x * u;
+            w4x[1] = u * (1.0f - x * x) + 0.5f * x * u * (1.0f + u);
+            w4x[2] = 0.5f * u * x * (1.0f + x) + x * (1.0f - u * u);
+            const float y = fy[p], v = 1.0f - y;
+            w4y[0] = -0.5f * v * v * y; w4y[3] = -0.5f * y * y * v;
+            w4y[1] = v * (1.0f - y * y) + 0.5f * y * v * (1.0f + v);
+            w4y[2] = 0.5f * v * y * (1.0f + y) + y * (1.0f - v * v);
+        }
+        if (!fastpt[p]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { w4x[k] = 0.0f; w4y[k] = 0.0f; }
+        }
+        if (WIN == 5) {
+            const bool sx_ = fastpt[p] && di == 1, sy_ = fastpt[p] && dj == 1;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float a = k < 4 ? w4x[k] : 0.0f, b = k > 0 ? w4x[k - 1] : 0.0f;
+                const float c = k < 4 ? w4y[k] : 0.0f, d = k > 0 ? w4y[k - 1] : 0.0f;
+                const float wxv = sx_ ? b : a;
+                wx[p][k] = make_float2(wxv, wxv);
+                wy[p][k] = sy_ ? d : c;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { wx[p][k] = make_float2(w4x[k], w4x[k]); wy[p][k] = w4y[k]; }
+        }
+    }
+    const int pnx = jb.pnx;
+    const size_t pstride = (size_t)jb.pny * pnx;
+    const size_t toff = (size_t)(j0 - jb.py0) * pnx + (i0 - jb.px0);
+    const float4* __restrict__ Ta = jb.TA + (size_t)ch.pack0 * pstride + toff;
+    const float4* __restrict__ Tb = jb.TB + (size_t)ch.pack0 * pstride + toff;
+
+    // ---- window source: shared-memory ring fed by bulk copies, or global memory directly
+    __shared__ alignas(128) float4 s_win[STAGE ? SNS * SBH * SROW : 1];
+    __shared__ alignas(8) unsigned long long s_bar[STAGE ? SNS : 1];
+    bool staged = false;
+    int bi0 = 0, bj0 = 0, bw = 0, bh = 0;
+    if (STAGE) {
+        // bounding box of the warp's windows (lanes without a fast point do not count)
+        bi0 = __reduce_min_sync(0xffffffffu, anyfast ? i0 - 1 : INT_MAX);
+        bj0 = __reduce_min_sync(0xffffffffu, anyfast ? j0 - 1 : INT_MAX);
+        const int bi1 = __reduce_max_sync(0xffffffffu, anyfast ? i0 + WIN - 2 : INT_MIN);
+        const int bj1 = __reduce_max_sync(0xffffffffu, anyfast ? j0 + WIN - 2 : INT_MIN);
+        bw = bi1 - bi0 + 1; bh = bj1 - bj0 + 1;
+        staged = bi0 != INT_MAX && bw <= SBW && bh <= SBH;
+    }
+    const float4* __restrict__ Pw = jb.P + (size_t)ch.pack0 * pstride + (size_t)(j0 - 1 - jb.py0) * pnx + (i0 - 1 - jb.px0);
+    const float4* Pbox = jb.P + (size_t)ch.pack0 * pstride + (size_t)(bj0 - jb.py0 + (lane < bh ? lane : 0)) * pnx + (bi0 - jb.px0);
+    const unsigned bar0 = smem_u32(s_bar), win0 = smem_u32(s_win);
+    const float4* sw_ = s_win + (staged && anyfast ? (j0 - 1 - bj0) * SROW + (i0 - 1 - bi0) : 0);
+    auto issue = [&](int pk) {      // bulk copies of pack pk's box rows into stage pk % SNS
+        const int st = pk % SNS;
+        if (lane == 0) mbar_expect_tx(bar0 + 8 * st, (unsigned)(bw * bh * 16));
+        __syncwarp();
+        if (lane < bh) bulk_g2s(win0 + (unsigned)((st * SBH + lane) * SROW * 16), Pbox + (size_t)pk * pstride, (unsigned)(bw * 16), bar0 + 8 * st);
+    };
+    if (STAGE && staged) {
+        if (lane == 0) {
+#pragma unroll
+            for (int st = 0; st < SNS; ++st) mbar_init(bar0 + 8 * st, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        for (int pk = 0; pk < SNS - 1 && pk < ch.npk; ++pk) issue(pk);
+    }
+
+    // Output addressing: byte offsets of the strip's points / bitmap words, added to the per-level base pointers (warp-uniform,
+    // constant bank).  Levels past the job's last one have their pointers aimed at a dump area by the host, so the loop
+    // below has no level test at all; stores are predicated, not branched around.
+    unsigned actw[R];
+    unsigned poff[R], woffs[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+        actw[p] = __ballot_sync(0xffffffffu, active[p]);
+        poff[p] = (unsigned)(((size_t)(jj0 + p) * nx + ii) * sizeof(float));
+        woffs[p] = (unsigned)(((size_t)(jj0 + p) * jb.nxw + tx) * sizeof(int));
+    }
+    const unsigned rowsm = (1u << min(R, ny - jj0)) - 1u;     // rows of the strip that exist
+    const bool anyfill = __any_sync(0xffffffffu, fillm != 0u);
+    const float fillv = jb.fill;
+    float4 ta = __ldg(Ta);
+    float4 tb = ta;
+    if (BOTH) tb = __ldg(Tb);
+
+    const int npk = ch.npk;
+    const int slab00 = jb.slab0 + ch.pack0 * 4;
+    // the pack loop exists twice (windows from the ring / from global memory) so that neither carries the other's loads
+    auto packs = [&](auto direct_tag) {
+        constexpr bool DIRECT = decltype(direct_tag)::value;
+        for (int pk = 0; pk < npk; ++pk) {
+            const float4 cta = ta, ctb = tb;
+            if (pk + 1 < npk) {                      // thresholds of the next pack, one iteration ahead
+                Ta += pstride; Tb += pstride;
+                ta = __ldg(Ta);
+                if (BOTH) tb = __ldg(Tb);
+            }
+            if (!DIRECT) {
+                __syncwarp();                        // every lane has finished reading the stage that is refilled now
+                if (pk + SNS - 1 < npk) issue(pk + SNS - 1);
+                mbar_wait(bar0 + 8 * (pk % SNS), (unsigned)((pk / SNS) & 1));
+            }
+            const float4* __restrict__ sw = sw_ + (pk % SNS) * SBH * SROW;
+            float2 a01[R], a23[R];
+            bool g[R];                               // the guard holds for every row and level of point p so far
+#pragma unroll
+            for (int p = 0; p < R; ++p) { a01[p] = make_float2(0.0f, 0.0f); a23[p] = a01[p]; g[p] = (fastm >> p) & 1u; }
+#pragma unroll
+            for (int l = 0; l < WIN; ++l) {
+                float4 v[WIN];
+#pragma unroll
+                for (int k = 0; k < WIN; ++k) v[k] = DIRECT ? __ldg(Pw + l * pnx + k) : sw[l * SROW + k];
+#pragma unroll
+                for (int p = 0; p < R; ++p) {
+                    float2 r01 = __fmul2_rn(wx[p][0], lo2(v[0])), r23 = __fmul2_rn(wx[p][0], hi2(v[0]));
+#pragma unroll
+                    for (int k = 1; k < WIN; ++k) {
+                        r01 = __ffma2_rn(wx[p][k], lo2(v[k]), r01);
+                        r23 = __ffma2_rn(wx[p][k], hi2(v[k]), r23);
+                    }
+                    const float4 th = (BOTH && ((useB >> p) & 1)) ? ctb : cta;
+                    g[p] = g[p] && fabsf(r01.x) > th.x && fabsf(r01.y) > th.y && fabsf(r23.x) > th.z && fabsf(r23.y) > th.w;
+                    const float2 wyl = make_float2(wy[p][l], wy[p][l]);
+                    a01[p] = __ffma2_rn(wyl, r01, a01[p]);
+                    a23[p] = __ffma2_rn(wyl, r23, a23[p]);
+                }
+            }
+            if (DIRECT) Pw += pstride;
+            // ---- outputs.  The guard is joint over the pack's four levels: a point either delivers all of them or hands all
+            // of them to the slow pass, so one ballot and one slow word per point serve the pack (the four slabs share a bitmap).
+            const int sl0 = slab00 + pk * 4;
+            unsigned word[R];
+#pragma unroll
+            for (int p = 0; p < R; ++p) {
+                float r0 = a01[p].x, r1 = a01[p].y, r2 = a23[p].x, r3 = a23[p].y;
+                bool ok = g[p] && r0 != msg && r1 != msg && r2 != msg && r3 != msg;
+                r0 = r0 == 1.0e-20f ? 0.0f : r0; r1 = r1 == 1.0e-20f ? 0.0f : r1;     // :1317
+                r2 = r2 == 1.0e-20f ? 0.0f : r2; r3 = r3 == 1.0e-20f ? 0.0f : r3;
+                if (anyfill) {                       // warp-uniform: fill_missing points exist in this strip row group
+                    const bool f = (fillm >> p) & 1u;
+                    r0 = f ? fillv : r0; r1 = f ? fillv : r1; r2 = f ? fillv : r2; r3 = f ? fillv : r3;
+                    ok = ok || f;
+                }
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 0]) + poff[p], r0);
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 1]) + poff[p], r1);
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 2]) + poff[p], r2);
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 3]) + poff[p], r3);
+                word[p] = __ballot_sync(0xffffffffu, ok);
+            }
+            if (lane < R) {
+                // lane p writes the words of strip row p: new_pts of the four levels and the pack's slow word
+                unsigned w = word[0], a = actw[0], wo = woffs[0];
+#pragma unroll
+                for (int p = 1; p < R; ++p) if (lane == p) { w = word[p]; a = actw[p]; wo = woffs[p]; }
+                const bool rowok = (rowsm >> lane) & 1u;
+                st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 0]) + wo, w);
+                st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 1]) + wo, w);
+                st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 2]) + wo, w);
+                st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 3]) + wo, w);
+                st_u32_if(rowok, reinterpret_cast<char*>(P.slow[sl0]) + wo, a & ~w);
+            }
+        }
+    };
+    if (STAGE && staged) packs(std::false_type{});
+    else packs(std::true_type{});
+}
+
+}  // namespace wps
