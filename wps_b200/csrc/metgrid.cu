@@ -47,10 +47,29 @@ struct SlabPtrs {
     float* r_arr;
     const int* valid;
     int* new_pts;
-    int* slow;      // packed sixteen_pt path: bit set = this (slab, point) must go through the generic operators
     const int* decided;  // average_gcell: bit set = r_arr already holds the cell average (:2393-2400)
 };
 
+
+// Points a first-method kernel cannot finish (missing values in the stencil, coast lines, nodes, array edges) are
+// appended to a compact queue as (slab, point) and redone by k_metgrid_slowlist with the full chain.  cnt[0] = entries
+// requested, cnt[1] = overflow flag: when the queue is too small the whole pass is redone by the generic kernel instead.
+struct SlowQ { int2* q; unsigned* cnt; unsigned cap; };
+
+// sword: ballot of the lanes whose point is flagged (non-zero, warp-uniform); the point stands for nl consecutive slabs
+__device__ __forceinline__ void slowq_push(const SlowQ& Q, unsigned sword, int lane, int gslab, int nl, int idx)
+{
+    const unsigned n = __popc(sword);
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(Q.cnt, n * (unsigned)nl);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if ((sword >> lane) & 1u) {
+        const unsigned at = base + __popc(sword & ((1u << lane) - 1u)) * (unsigned)nl;
+        if (at + (unsigned)nl <= Q.cap) {
+            for (int lv = 0; lv < nl; ++lv) Q.q[at + lv] = make_int2(gslab + lv, idx);
+        } else Q.cnt[1] = 1u;
+    }
+}
 
 // ---- coordinate cache -------------------------------------------------------------------------
 __global__ void k_coord_cache(DevProj p, const float* __restrict__ xlat, const float* __restrict__ xlon, int64_t n,
@@ -157,13 +176,17 @@ __device__ __forceinline__ int process_point(const Job& jb, const float* __restr
 // ---- main batched kernel -------------------------------------------------------------------------
 // grid.x = sum over jobs of tiles; block = 32x8 destination points; each thread walks the job's slabs.
 __global__ void __launch_bounds__(TILE_X * TILE_Y, 4)
-k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_tile0, int ncls,
-                 const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count)
+k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs, const int* __restrict__ cls_tile0, int ncls, int ntiles,
+                 const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count,
+                 const unsigned* __restrict__ only_if)
 {
+    // only_if: the launch is the fallback for an overflowed slow queue and has nothing to do otherwise
+    if (only_if && *only_if == 0u) return;
     __shared__ Job jb;
     __shared__ int s_job, s_tile0;
+    for (int b = blockIdx.x; b < ntiles; b += gridDim.x) {
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        int lo = 0, hi = ncls - 1, b = blockIdx.x;
+        int lo = 0, hi = ncls - 1;
         while (lo < hi) {
             int mid = (lo + hi + 1) >> 1;
             if (cls_tile0[mid] <= b) lo = mid; else hi = mid - 1;
@@ -178,7 +201,7 @@ k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs,
         for (int w = tid; w < (int)(sizeof(Job) / sizeof(int)); w += TILE_X * TILE_Y) sdst[w] = gsrc[w];
     }
     __syncthreads();
-    int t = blockIdx.x - s_tile0;
+    int t = b - s_tile0;
     int tx = t % jb.tiles_x, ty = t / jb.tiles_x;
     int ii = tx * TILE_X + threadIdx.x, jj = ty * TILE_Y + threadIdx.y;  // 0-based within the grid
     bool active = ii < jb.nx && jj < jb.ny;
@@ -204,6 +227,8 @@ k_metgrid_interp(const Job* __restrict__ jobs, const int* __restrict__ cls_jobs,
         }
         unsigned word = __ballot_sync(0xffffffffu, (flags & PF_BIT) != 0);
         if (threadIdx.x == 0 && jj < jb.ny) sp.new_pts[widx] = (int)word;
+    }
+    __syncthreads();   // jb is overwritten by the next tile
     }
 }
 
@@ -467,7 +492,7 @@ struct FastParams {
     Job jb;
     float* r_arr[FAST_MAX_SLABS];
     int* new_pts[FAST_MAX_SLABS];
-    int* slow[FAST_MAX_SLABS];
+    SlowQ sq;
 };
 
 // One warp per CTA (32 x 1 destination points): a CTA's registers are released as soon as its single warp is done, which
@@ -563,7 +588,8 @@ k_metgrid_fast16(const __grid_constant__ FastParams P)
             if (fillpt) { r = jb.fill; ok = true; }
             if (ok) P.r_arr[sl][idx] = r;
             unsigned word = __ballot_sync(0xffffffffu, ok), sword = __ballot_sync(0xffffffffu, active && !ok);
-            if (wlead) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
+            if (wlead) P.new_pts[sl][widx] = (int)word;
+            if (sword) slowq_push(P.sq, sword, threadIdx.x, jb.slab0 + sl, 1, (int)idx);
         }
     }
 }
@@ -577,7 +603,7 @@ struct Fast4Params {
     const float* src[FAST_MAX_SLABS];
     float* r_arr[FAST_MAX_SLABS];
     int* new_pts[FAST_MAX_SLABS];
-    int* slow[FAST_MAX_SLABS];
+    SlowQ sq;
 };
 
 template <int OP>
@@ -647,143 +673,12 @@ k_metgrid_fast4(const __grid_constant__ Fast4Params P)
         if (fillpt) { r = jb.fill; ok = true; }
         if (ok) P.r_arr[sl][idx] = r;
         unsigned word = __ballot_sync(0xffffffffu, ok), sword = __ballot_sync(0xffffffffu, active && !ok);
-        if (wlead) { P.new_pts[sl][widx] = (int)word; P.slow[sl][widx] = (int)sword; }
+        if (wlead) P.new_pts[sl][widx] = (int)word;
+        if (sword) slowq_push(P.sq, sword, threadIdx.x, jb.slab0 + sl, 1, (int)idx);
     }
 }
 
-// Points the packed kernel could not take (missing values in the stencil, points on a node or near the array edge,
-// process_bdy_width interior): full generic operator chain, one thread per flagged word.
-#ifndef SLOW_MINBLOCKS
-#define SLOW_MINBLOCKS 8   // 64 registers: measured 0.31 / 0.24 / 0.22 / 0.22 / 0.26 ms at 4 / 6 / 8 / 10 / 12 CTAs per SM
-#endif
-// WPT = bitmap words per thread (rounds per block); 1 is what is launched.
-template <int WPT>
-__global__ void __launch_bounds__(128, SLOW_MINBLOCKS)
-k_metgrid_slowbits(const Job* __restrict__ jobs, const int2* __restrict__ slow_slabs, int slab_begin,
-                   const SlabPtrs* __restrict__ slabs, Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count)
-{
-    // blockIdx.y picks the slab (job, level) from the list of first-method slabs, blockIdx.x a run of WPT x 128 bitmap
-    // words of it: no per-thread search or division (a linear word index over all slabs cost a 64-bit division per
-    // thread).  Each lane fetches one word per round (coalesced); a round without a set bit in the block is skipped.
-    const int lane = threadIdx.x & 31;
-    const int2 js = __ldg(slow_slabs + slab_begin + blockIdx.y);
-    const int job = js.x, sl = js.y;
-    const int words_per_slab = jobs[job].ny * jobs[job].nxw;
-    if (blockIdx.x * blockDim.x * WPT >= (unsigned)words_per_slab) return;   // whole block past the end (grid sized for the largest slab)
-    __shared__ unsigned short s_queue[128 * 32];   // (word of the round << 6) | (bit << 1) | first
-    __shared__ int s_nq;
-    const Job& jb = jobs[job];
-    const SlabPtrs sp = slabs[jb.slab0 + sl];
-    const bool hint_ok = jb.fast == 1 && !(jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH);
-    const bool light_ok = hint_ok && jb.ops[1] == WPSGPU_FOUR_POINT;
-    auto word_at = [&](int k) -> unsigned {
-        const int w = (blockIdx.x * WPT + k) * blockDim.x + threadIdx.x;
-        return (k < WPT && w < words_per_slab) ? (unsigned)__ldg(sp.slow + w) : 0u;
-    };
-    unsigned bits_next = word_at(0);
-#pragma unroll 1
-    for (int k = 0; k < WPT; ++k) {
-    const unsigned bits = bits_next;
-    bits_next = word_at(k + 1);   // in flight while this round is examined
-    if (threadIdx.x == 0) s_nq = 0;
-    if (!__syncthreads_or(bits != 0u)) continue;
-    const int w_block = (blockIdx.x * WPT + k) * blockDim.x;
-    const int widx = w_block + threadIdx.x;
-    // The flagged points of the warp's 32 words are ranked by an exclusive scan of the per-word popcounts and dealt
-    // out 32 at a time, so every lane has a point to work on regardless of how the bits are spread over the words.
-    unsigned cnt = __popc(bits), inc = cnt;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        unsigned v = __shfl_up_sync(0xffffffffu, inc, off);
-        if (lane >= off) inc += v;
-    }
-    const unsigned total = __shfl_sync(0xffffffffu, inc, 31), exc = inc - cnt;
-    // Two phases.  (1) Every flagged point whose stencil is known to hold a missing / masked value (so sixteen_pt hands
-    // over) and whose second method is four_pt tries just that operator -- four loads; two thirds of the coast-line
-    // points of the soil chains end here.  (2) The rest is queued in shared memory and worked off by the whole block
-    // with the full chain, so the 64-register generic code runs on dense warps instead of a few lanes per warp.
-    for (unsigned base = 0; base < total; base += 32) {
-        unsigned r = base + lane;
-        int pos = 0;   // largest lane whose exclusive prefix is <= r: the word holding the r-th flagged point
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            unsigned e = __shfl_sync(0xffffffffu, exc, pos + step);
-            if (e <= r) pos += step;
-        }
-        unsigned wbits = __shfl_sync(0xffffffffu, bits, pos), wexc = __shfl_sync(0xffffffffu, exc, pos);
-        const int wwidx = __shfl_sync(0xffffffffu, widx, pos);
-        if (r < total) {
-            int bit = (int)__fns(wbits, 0, (int)(r - wexc) + 1);
-            int jj = (int)(wwidx / jb.nxw), tx = (int)(wwidx % jb.nxw);
-            int ii = tx * 32 + bit;
-            size_t idx = (size_t)jj * jb.nx + ii;
-            const float2 pxy = __ldg(jb.xy + idx);
-            int first = 0;
-            if (hint_ok) {
-                // same cell arithmetic as sixteen_pt (interp_module.F:1211-1225); off a node and inside the record box
-                // the pre-pass has recorded whether the 4x4 stencil holds a missing / masked value
-                float xx = pxy.x, yy = pxy.y;
-                if (fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f && (int)xx >= jb.minx && (int)xx <= jb.maxx && (int)yy >= jb.miny && (int)yy <= jb.maxy) {
-                    int ci = (int)(xx + 0.00001f), cj = (int)(yy + 0.00001f);
-                    float fx = xx - (float)ci, fy = yy - (float)cj;
-                    ci -= jb.bx0; cj -= jb.by0;
-                    if ((fabsf(fx) > 0.0001f || fabsf(fy) > 0.0001f) && ci >= 0 && ci < jb.bnx && cj >= 0 && cj < jb.bny) {
-                        unsigned cfb = __ldg(jb.cf + ((size_t)(sl >> 2) * jb.bny + cj) * jb.bnx + ci);
-                        if ((cfb >> (4 + (sl & 3))) & 1u) first = 1;
-                    }
-                }
-            }
-            bool done = false;
-            if (light_ok && first == 1) {
-                // what process_point / interp_to_latlon do for such a point (no fill rule applies to a flagged point of
-                // a job without masked=both; interp_sequence starts at method 1): the x-range test of :2620, four_pt,
-                // and "value /= missing_value => store + new bit" (:2558-2563)
-                const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
-                const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
-                const bool lm_fill = jb.landmask != nullptr && __ldg(jb.landmask + idx) == jb.masked;
-                const float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
-                if (!in_fill && !lm_fill && pxy.x >= lo && pxy.x <= hi) {
-                    Src s4;
-                    s4.a = sp.src; s4.m = jb.mask[0];
-                    s4.sx = jb.minx; s4.ex = jb.maxx; s4.sy = jb.miny; s4.ey = jb.maxy; s4.nx = jb.maxx - jb.minx + 1;
-                    s4.msg = jb.msg; s4.maskval = jb.mask_val[0]; s4.rel = jb.mask_rel[0];
-                    float v4 = jb.msg;
-                    if (op_four_pt(s4, pxy.x, pxy.y, v4) == ST_VAL && v4 != jb.msg) {
-                        sp.r_arr[idx] = v4;
-                        atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
-                        done = true;
-                    }
-                }
-            }
-            if (!done) s_queue[atomicAdd(&s_nq, 1)] = (unsigned short)(((wwidx - w_block) << 6) | (bit << 1) | first);
-        }
-    }
-    __syncthreads();
-    const int nq = s_nq;
-    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-        const unsigned e = s_queue[q];
-        const int wwidx = w_block + (int)(e >> 6), bit = (int)((e >> 1) & 31u), first = (int)(e & 1u);
-        int jj = (int)(wwidx / jb.nxw), tx = (int)(wwidx % jb.nxw);
-        int ii = tx * 32 + bit;
-        size_t idx = (size_t)jj * jb.nx + ii;
-        bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> bit) & 1u) : false;
-        float out = 0.0f;
-        const float2 pxy = __ldg(jb.xy + idx);
-        int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, idx, pxy, vbit, out, nullptr, first);
-        if (flags & PF_DEFER) {
-            unsigned long long slot = atomicAdd(defer_count, 1ull);
-            Deferred d; d.slab = jb.slab0 + sl; d.idx = (int)idx;
-            deferred[slot] = d;
-        } else {
-            if (flags & PF_WRITE) sp.r_arr[idx] = out;
-            if (flags & PF_BIT) atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
-        }
-    }
-    __syncthreads();   // the queue is reused by the next round
-    }
-}
-
-// ---- deferred passes: warp per point (closed-form search), then thread per point (literal) ---------
+// Points the first-method kernels could not take: full generic operator chain, one thread per queue entry.
 __device__ __forceinline__ int job_of_slab(const Job* jobs, int njobs, int slab)
 {
     int lo = 0, hi = njobs - 1;
@@ -794,6 +689,78 @@ __device__ __forceinline__ int job_of_slab(const Job* jobs, int njobs, int slab)
     return lo;
 }
 
+#ifndef SLOW_MINBLOCKS
+#define SLOW_MINBLOCKS 8   // 64 registers
+#endif
+__global__ void __launch_bounds__(128, SLOW_MINBLOCKS)
+k_metgrid_slowlist(const Job* __restrict__ jobs, int njobs, const SlabPtrs* __restrict__ slabs, SlowQ Q,
+                   Deferred* __restrict__ deferred, unsigned long long* __restrict__ defer_count)
+{
+    if (Q.cnt[1] != 0u) return;                  // overflowed: the generic kernel redoes the pass
+    const unsigned n = min(Q.cnt[0], Q.cap);
+    for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int2 en = Q.q[e];
+        const int slab = en.x, idx = en.y;
+        const Job& jb = jobs[job_of_slab(jobs, njobs, slab)];
+        const SlabPtrs sp = slabs[slab];
+        const int sl = slab - jb.slab0;
+        const int jj = idx / jb.nx, ii = idx - jj * jb.nx;
+        const int wwidx = jj * jb.nxw + (ii >> 5), bit = ii & 31;
+        const float2 pxy = __ldg(jb.xy + idx);
+        const bool hint_ok = jb.fast == 1 && !(jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH);
+        int first = 0;
+        if (hint_ok) {
+            // same cell arithmetic as sixteen_pt (interp_module.F:1211-1225); off a node and inside the record box
+            // the pre-pass has recorded whether the 4x4 stencil holds a missing / masked value
+            float xx = pxy.x, yy = pxy.y;
+            if (fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f && (int)xx >= jb.minx && (int)xx <= jb.maxx && (int)yy >= jb.miny && (int)yy <= jb.maxy) {
+                int ci = (int)(xx + 0.00001f), cj = (int)(yy + 0.00001f);
+                float fx = xx - (float)ci, fy = yy - (float)cj;
+                ci -= jb.bx0; cj -= jb.by0;
+                if ((fabsf(fx) > 0.0001f || fabsf(fy) > 0.0001f) && ci >= 0 && ci < jb.bnx && cj >= 0 && cj < jb.bny) {
+                    unsigned cfb = __ldg(jb.cf + ((size_t)(sl >> 2) * jb.bny + cj) * jb.bnx + ci);
+                    if ((cfb >> (4 + (sl & 3))) & 1u) first = 1;
+                }
+            }
+        }
+        bool done = false;
+        if (hint_ok && first == 1 && jb.ops[1] == WPSGPU_FOUR_POINT) {
+            // what process_point / interp_to_latlon do for such a point (no fill rule applies to a flagged point of
+            // a job without masked=both; interp_sequence starts at method 1): the x-range test of :2620, four_pt,
+            // and "value /= missing_value => store + new bit" (:2558-2563)
+            const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
+            const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+            const bool lm_fill = jb.landmask != nullptr && __ldg(jb.landmask + idx) == jb.masked;
+            const float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
+            if (!in_fill && !lm_fill && pxy.x >= lo && pxy.x <= hi) {
+                Src s4;
+                s4.a = sp.src; s4.m = jb.mask[0];
+                s4.sx = jb.minx; s4.ex = jb.maxx; s4.sy = jb.miny; s4.ey = jb.maxy; s4.nx = jb.maxx - jb.minx + 1;
+                s4.msg = jb.msg; s4.maskval = jb.mask_val[0]; s4.rel = jb.mask_rel[0];
+                float v4 = jb.msg;
+                if (op_four_pt(s4, pxy.x, pxy.y, v4) == ST_VAL && v4 != jb.msg) {
+                    sp.r_arr[idx] = v4;
+                    atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
+                    done = true;
+                }
+            }
+        }
+        if (done) continue;
+        bool vbit = sp.valid ? ((((unsigned)__ldg(sp.valid + wwidx)) >> bit) & 1u) : false;
+        float out = 0.0f;
+        int flags = process_point<0>(jb, sp.src, jb.sm1 + ii, jb.sm2 + jj, (size_t)idx, pxy, vbit, out, nullptr, first);
+        if (flags & PF_DEFER) {
+            unsigned long long slot = atomicAdd(defer_count, 1ull);
+            Deferred d; d.slab = slab; d.idx = idx;
+            deferred[slot] = d;
+        } else {
+            if (flags & PF_WRITE) sp.r_arr[idx] = out;
+            if (flags & PF_BIT) atomicOr(sp.new_pts + wwidx, (int)(1u << bit));
+        }
+    }
+}
+
+// ---- deferred passes: warp per point (closed-form search), then thread per point (literal) ---------
 __device__ __forceinline__ void finish_point(const Job& jb, const SlabPtrs& sp, int idx, int flags, float out)
 {
     if (flags & PF_WRITE) sp.r_arr[idx] = out;
@@ -912,14 +879,15 @@ static void launch_strip_kernel(const StripParams& sp, unsigned tiles, unsigned 
 }
 
 static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std::vector<int>& sel, const std::vector<SlabPtrs>& sp,
-                         float* dump_r, int* dump_w)
+                         float* dump_r, int* dump_w, const SlowQ& sq)
 {
     constexpr int SW = 1;
     const bool stage = env_int("WPSGPU_STRIP_STAGE", 1, 0, 1) != 0;   // 0: windows straight from global memory (A/B measurements)
-    const int chunk_packs = env_int("WPSGPU_STRIP_CHUNK", 8, 1, 64);
+    const int chunk_packs = env_int("WPSGPU_STRIP_CHUNK", 16, 1, 64);
     for (int R : { 4, 2, 1 })
         for (int both = 0; both < 2; ++both) {
             StripParams P;
+            P.sq = sq;
             int nj = 0, ns = 0, nc = 0;
             unsigned tiles = 0;
             auto fire = [&]() {
@@ -939,21 +907,20 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                 if (nj + 1 > STRIP_MAX_JOBS || ns + nslot > STRIP_MAX_SLABS || nc + nchunk > STRIP_MAX_CHUNKS) fire();
                 WPS_CHECK(nslot <= STRIP_MAX_SLABS && nchunk <= STRIP_MAX_CHUNKS, -3, "sixteen_pt job too large for one strip launch");
                 StripJob& q = P.job[nj];
-                q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr;
-                q.TB = jboth ? jb.thr + (size_t)jb.npack * jb.bnx * jb.bny : jb.thr;
+                q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cf;
                 q.nx = jb.nx; q.ny = jb.ny; q.nxw = jb.nxw; q.sm1 = jb.sm1; q.sm2 = jb.sm2;
                 q.sd1 = jb.sd1; q.ed1 = jb.ed1; q.sd2 = jb.sd2; q.ed2 = jb.ed2; q.pw = jb.pw;
                 q.minx = jb.minx; q.maxx = jb.maxx; q.miny = jb.miny; q.maxy = jb.maxy; q.bdr = jb.bdr;
                 q.px0 = jb.bx0; q.py0 = jb.by0; q.pnx = jb.bnx; q.pny = jb.bny;
-                q.nslab = jb.nslab; q.slab0 = ns;
+                q.nslab = jb.nslab; q.slab0 = ns; q.gslab0 = jb.slab0;
                 q.tiles_x = jb.tiles_x; q.ntiles = jb.tiles_x * ((jb.ny + R * SW - 1) / (R * SW));
                 q.both = jboth ? 1 : 0; q.has_lm = jb.landmask != nullptr ? 1 : 0;
                 q.msg = jb.msg; q.fill = jb.fill; q.masked = jb.masked;
                 for (int k = 0; k < jb.nslab; ++k) {
                     const SlabPtrs& p = sp[jb.slab0 + k];
-                    P.r_arr[ns + k] = p.r_arr; P.new_pts[ns + k] = p.new_pts; P.slow[ns + k] = p.slow;
+                    P.r_arr[ns + k] = p.r_arr; P.new_pts[ns + k] = p.new_pts;
                 }
-                for (int k = jb.nslab; k < nslot; ++k) { P.r_arr[ns + k] = dump_r; P.new_pts[ns + k] = dump_w; P.slow[ns + k] = dump_w; }
+                for (int k = jb.nslab; k < nslot; ++k) { P.r_arr[ns + k] = dump_r; P.new_pts[ns + k] = dump_w; }
                 // chunks of equal size (e.g. 9 packs -> 5 + 4, not 8 + 1)
                 const int per = (jb.npack + nchunk - 1) / nchunk;
                 for (int c = 0; c < nchunk; ++c) {
@@ -1189,11 +1156,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     std::vector<int*> gc_decided(njobs, nullptr);
     std::vector<SlabPtrs> sp(nq);
     std::vector<int> cls_jobs[2], cls_tile0[2];  // 0 = generic kernel, 1 = first-method kernels
-    std::vector<int> fast_word0;
-    long long fast_words = 0;
-    std::vector<int2> slow_slabs;    // (job, level) of every first-method slab: the slow-bitmap pass takes one per blockIdx.y
-    std::vector<int> slow_first;     // first entry of each first-method job
-    int slow_max_words = 0;
+    double fast_pairs = 0.0;          // (slab, point) pairs of the first-method jobs: sizes the slow queue
     int tile_cursor[2] = { 0, 0 };
     double cls_points[2] = { 0.0, 0.0 };
     double fast16_points = 0.0, fast4_points = 0.0;
@@ -1237,21 +1200,15 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         cls_points[cls] += (double)dg.npts() * groups[g].size();
         if (bx.fast == 1) fast16_points += (double)dg.npts() * groups[g].size();
         if (bx.fast >= 2) fast4_points += (double)dg.npts() * groups[g].size();
-        if (cls == 1) {
-            fast_word0.push_back((int)fast_words); fast_words += (long long)jb.ny * jb.nxw * groups[g].size();
-            slow_first.push_back((int)slow_slabs.size());
-            for (int k = 0; k < (int)groups[g].size(); ++k) slow_slabs.push_back(make_int2(j, k));
-            slow_max_words = std::max(slow_max_words, jb.ny * jb.nxw);
-        }
+        if (cls == 1) fast_pairs += (double)dg.npts() * groups[g].size();
         jb.f_negzero = -0.0f; jb.f_one = 1.0f;
         jb.gcell = q0.gcell ? 1 : 0;
         jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
         jb.strip = bx.fast == 1 ? bx.strip : 0;
         if (jb.fast == 1 && jb.strip > 0) {
-            const bool both = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
             const size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
             jb.rec = (const float4*)h->arena.take(cells * sizeof(float4));
-            jb.thr = (const float4*)h->arena.take(cells * sizeof(float4) * (both ? 2 : 1));
+            jb.thr = (const float4*)h->arena.take(cells * sizeof(float4));
             jb.cf = (const unsigned char*)h->arena.take(cells);
             WPS_CHECK(jb.rec && jb.thr && jb.cf, -3, "device arena exhausted (window records)");
         } else if (jb.fast == 1) {
@@ -1272,7 +1229,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         // one pass per kind of array, so that the arrays of neighbouring levels end up next to each other
         for (int k = 0; k < ns; ++k) {
             SlabPtrs& p = sp[s0 + k];
-            p.slow = nullptr; p.decided = nullptr; p.valid = nullptr;
+            p.decided = nullptr; p.valid = nullptr;
             const wpsgpu_slab& s = queue[grp[k]].s;
             if (host && fs.staged.count(s.slab) && !fs.reusable(s.slab, fs.sub[g])) {   // staged for another grid with a smaller rectangle
                 fs.staged.erase(s.slab);
@@ -1331,13 +1288,6 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             WPS_CHECK(gc_decided[j] != nullptr, -3, "device arena exhausted (average_gcell bits)");
             sp[s0].decided = gc_decided[j];
         }
-        if (jb.fast)
-            for (int k = 0; k < ns; ++k) {
-                // strip jobs: the four levels of a pack are flagged together and share one bitmap
-                if (jb.strip > 0 && (k & 3)) { sp[s0 + k].slow = sp[s0 + (k & ~3)].slow; continue; }
-                sp[s0 + k].slow = (int*)h->arena.take(wbytes);
-                WPS_CHECK(sp[s0 + k].slow != nullptr, -3, "device arena exhausted (slow bitmaps)");
-            }
         if (host) {
             for (int k = 0; k < ns; ++k) {
                 const wpsgpu_slab& s = queue[grp[k]].s;
@@ -1394,37 +1344,24 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             pack_max = std::max(pack_max, jobs[j].npack);
         }
     WPS_CHECK(pack_jobs.size() < 65536, -3, "too many packed jobs in one flush");
-    WPS_CHECK(fast_words < 2000000000LL, -3, "too many output words in one flush");
     const size_t off_sp = (sizeof(Job) * njobs + 255) & ~size_t(255);
     const size_t off_cls = (off_sp + sizeof(SlabPtrs) * nq + 255) & ~size_t(255);
     const size_t off_dec = (off_cls + sizeof(int) * 6 * (njobs + 1) + 255) & ~size_t(255);
-    // slabs of masked / search chains carry nearly all the flagged points: their blocks go first, so that the long
-    // generic chains start early and the empty bitmaps of the 3-d fields are scanned in their shadow (a per-job
-    // launch on the side stream, WPSGPU_OVERLAP, keeps the job order)
-    if (env_int("WPSGPU_OVERLAP", 0, 0, 1) == 0)
-        (void)(std::stable_partition(slow_slabs.begin(), slow_slabs.end(), [&](const int2& e) {
-            const Job& jb = jobs[e.x];
-            bool heavy = jb.mask[0] || jb.mask[1] || jb.mask[2];
-            for (int k = 0; k < WPSGPU_MAX_OPS && jb.ops[k]; ++k) heavy = heavy || jb.ops[k] == WPSGPU_SEARCH;
-            return heavy;
-        }));
-    const size_t off_slow = (off_dec + sizeof(DecodeTask) * decode_tasks.size() + 255) & ~size_t(255);
-    const size_t off_win = (off_slow + sizeof(int2) * slow_slabs.size() + 255) & ~size_t(255);
+    const size_t off_win = (off_dec + sizeof(DecodeTask) * decode_tasks.size() + 255) & ~size_t(255);
     const size_t tab_bytes = off_win + sizeof(PackWinTask) * win_tasks.size();
     WPS_CHECK(win_tasks.size() < 65536, -3, "too many window-record packs in one flush");
-    WPS_CHECK(slow_slabs.size() < 65536, -3, "too many first-method slabs in one flush");
     std::vector<char>& tab = fs.tab;
     tab.assign(tab_bytes, 0);
     memcpy(tab.data(), jobs.data(), sizeof(Job) * njobs);
     memcpy(tab.data() + off_sp, sp.data(), sizeof(SlabPtrs) * nq);
     {
         int* cls = reinterpret_cast<int*>(tab.data() + off_cls);
-        const std::vector<int>* lists[6] = { &cls_jobs[0], &cls_tile0[0], &cls_jobs[1], &cls_tile0[1], &fast_word0, &pack_jobs };
+        const std::vector<int> unused;
+        const std::vector<int>* lists[6] = { &cls_jobs[0], &cls_tile0[0], &cls_jobs[1], &cls_tile0[1], &unused, &pack_jobs };
         for (int c = 0; c < 6; ++c)
             if (!lists[c]->empty()) memcpy(cls + (size_t)c * (njobs + 1), lists[c]->data(), sizeof(int) * lists[c]->size());
     }
     if (!decode_tasks.empty()) memcpy(tab.data() + off_dec, decode_tasks.data(), sizeof(DecodeTask) * decode_tasks.size());
-    if (!slow_slabs.empty()) memcpy(tab.data() + off_slow, slow_slabs.data(), sizeof(int2) * slow_slabs.size());
     if (!win_tasks.empty()) memcpy(tab.data() + off_win, win_tasks.data(), sizeof(PackWinTask) * win_tasks.size());
     char* d_tab = (char*)h->arena.take(tab_bytes);
     WPS_CHECK(d_tab != nullptr, -3, "device arena exhausted (tables)");
@@ -1435,8 +1372,15 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
     int* d_cls_jobs[2] = { d_cls, d_cls + 2 * (njobs + 1) };
     int* d_cls_tile0[2] = { d_cls + (njobs + 1), d_cls + 3 * (njobs + 1) };
     int* d_pack_jobs = d_cls + 5 * (njobs + 1);
-    const int2* d_slow_slabs = (const int2*)(d_tab + off_slow);
-    const unsigned slow_gx = (unsigned)((slow_max_words + 127) / 128);
+    // slow queue: room for 1/32 of the first-method outputs + 1 M entries (a whole all-missing slab fits); beyond that
+    // the pass falls back to the generic kernel
+    SlowQ sq;
+    sq.q = nullptr; sq.cnt = reinterpret_cast<unsigned*>(h->d_counters + 16); sq.cap = 0;
+    if (tile_cursor[1] > 0) {
+        sq.cap = (unsigned)std::min(fast_pairs, fast_pairs / 32.0 + 1048576.0);
+        sq.q = (int2*)h->arena.take(sizeof(int2) * (size_t)sq.cap);
+        WPS_CHECK(sq.q != nullptr, -3, "device arena exhausted (slow queue)");
+    }
     Deferred *d_def = nullptr, *d_def2 = nullptr;
     unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(h->d_counters);
     if (any_search) {
@@ -1450,6 +1394,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
     }
     if (any_search) WPS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (tile_cursor[1] > 0) WPS_CUDA(cudaMemsetAsync(sq.cnt, 0, 2 * sizeof(unsigned), h->stream));
 
     // ---- raw records -> halo'd slabs (one launch for all records of this pass) ----
     if (!decode_tasks.empty()) {
@@ -1498,32 +1443,6 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         h->launches++;
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
-    // Optional (WPSGPU_OVERLAP=1): the slow-bitmap pass of a job is latency-bound (scattered loads, 128 registers) while
-    // the first-method kernels keep the L1 data pipe busy, so it can run on a side stream as soon as its job's kernel
-    // has finished, overlapping the next job's kernel.  Measured: step 2.18 -> 2.12 ms, with the packed kernel's own
-    // bracket growing from 1.59 to 1.75 ms under the interference; off by default to keep per-kernel timings clean.
-    const bool overlap = env_int("WPSGPU_OVERLAP", 0, 0, 1) != 0 && cls_jobs[1].size() > 1;
-    if (overlap) {
-        if (!h->s_side) WPS_CUDA(cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
-        while (h->ev_pool.size() < cls_jobs[1].size() + 1) {
-            cudaEvent_t e;
-            WPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            h->ev_pool.push_back(e);
-        }
-    }
-    bool side_used = false;
-    auto slow_pass = [&](int j) -> int {   // j = job index; its words are [fast_word0[k], fast_word0[k+1])
-        if (!overlap) return 0;
-        size_t k = std::find(cls_jobs[1].begin(), cls_jobs[1].end(), j) - cls_jobs[1].begin();
-        const int s0 = slow_first[k], s1 = k + 1 < slow_first.size() ? slow_first[k + 1] : (int)slow_slabs.size();
-        WPS_CUDA(cudaEventRecord(h->ev_pool[k], h->stream));
-        WPS_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_pool[k], 0));
-        if (!side_used) WPS_CUDA(cudaEventRecord(h->ev_t[8], h->s_side));
-        side_used = true;
-        k_metgrid_slowbits<1><<<dim3(slow_gx, (unsigned)(s1 - s0)), 128, 0, h->s_side>>>(d_jobs, d_slow_slabs, s0, d_sp, d_def, d_cnt);
-        h->launches++;
-        return 0;
-    };
     WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
     for (int j : cls_jobs[1]) {
         if (jobs[j].fast != 1 || jobs[j].strip > 0) continue;
@@ -1531,11 +1450,11 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         fp.jb = jobs[j];
         for (int k = 0; k < fp.jb.nslab; ++k) {
             const SlabPtrs& p = sp[fp.jb.slab0 + k];
-            fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
+            fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts;
         }
+        fp.sq = sq;
         k_metgrid_fast16<<<fp.jb.tiles_x * ((fp.jb.ny + F16_Y - 1) / F16_Y), dim3(TILE_X, F16_Y), 0, h->stream>>>(fp);
         h->launches++;
-        WPS_TRY(slow_pass(j));
     }
     {
         // tolerance mode: ONE strip launch per (points per thread, masked=both or not) takes every sixteen_pt job of the
@@ -1551,8 +1470,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             dump_w = (int*)h->arena.take(mw * sizeof(int));
             WPS_CHECK(dump_r && dump_w, -3, "device arena exhausted (strip dump area)");
         }
-        WPS_TRY(launch_strips(h, jobs, sj, sp, dump_r, dump_w));
-        if (overlap) for (int j : sj) WPS_TRY(slow_pass(j));
+        WPS_TRY(launch_strips(h, jobs, sj, sp, dump_r, dump_w, sq));
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
     WPS_CUDA(cudaEventRecord(h->ev_t[6], h->stream));
@@ -1562,31 +1480,32 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         fp.jb = jobs[j];
         for (int k = 0; k < fp.jb.nslab; ++k) {
             const SlabPtrs& p = sp[fp.jb.slab0 + k];
-            fp.src[k] = p.src; fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts; fp.slow[k] = p.slow;
+            fp.src[k] = p.src; fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts;
         }
+        fp.sq = sq;
         if (jobs[j].fast == 2) k_metgrid_fast4<WPSGPU_FOUR_POINT><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
         else k_metgrid_fast4<WPSGPU_N_NEIGHBOR><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
         h->launches++;
-        WPS_TRY(slow_pass(j));
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[7], h->stream));
-    if (overlap && side_used) {   // join: everything after this point on the main stream sees the slow passes' results
-        WPS_CUDA(cudaEventRecord(h->ev_t[9], h->s_side));
-        WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_t[9], 0));
-    } else {
-        WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
-        if (tile_cursor[1] > 0) {
-            // one launch: the heavy slabs' blocks come first and the almost empty bitmaps of the other slabs are
-            // scanned in their shadow (a separate coarse-grained launch for the latter, 16 words per thread, was slower:
-            // 0.191 vs 0.160 ms, the two launches no longer overlap)
-            k_metgrid_slowbits<1><<<dim3(slow_gx, (unsigned)slow_slabs.size()), 128, 0, h->stream>>>(d_jobs, d_slow_slabs, 0, d_sp, d_def, d_cnt);
-            h->launches++;
-        }
-        WPS_CUDA(cudaEventRecord(h->ev_t[9], h->stream));
+    WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
+    if (tile_cursor[1] > 0) {
+        k_metgrid_slowlist<<<h->sm_count * SLOW_MINBLOCKS, 128, 0, h->stream>>>(d_jobs, njobs, d_sp, sq, d_def, d_cnt);
+        // queue overflow (cnt[1] set by a producer): the generic kernel redoes every first-method job of the pass
+        k_metgrid_interp<<<std::min(tile_cursor[1], h->sm_count * 8), block, 0, h->stream>>>(d_jobs, d_cls_jobs[1], d_cls_tile0[1], (int)cls_jobs[1].size(),
+                                                                                          tile_cursor[1], d_sp, d_def, d_cnt, sq.cnt + 1);
+        h->launches += 2;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[9], h->stream));
+    if (env_int("WPSGPU_DEBUG_SLOW", 0, 0, 1) && tile_cursor[1] > 0) {   // diagnostic: size of the slow queue
+        unsigned c[2] = { 0, 0 };
+        WPS_CUDA(cudaStreamSynchronize(h->stream));
+        WPS_CUDA(cudaMemcpy(c, sq.cnt, sizeof(c), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[wpsgpu] slow queue: %u entries of %.0f first-method outputs (capacity %u, overflow %u)\n", c[0], fast_pairs, sq.cap, c[1]);
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[4], h->stream));
     if (tile_cursor[0] > 0) {
-        k_metgrid_interp<<<tile_cursor[0], block, 0, h->stream>>>(d_jobs, d_cls_jobs[0], d_cls_tile0[0], (int)cls_jobs[0].size(), d_sp, d_def, d_cnt);
+        k_metgrid_interp<<<tile_cursor[0], block, 0, h->stream>>>(d_jobs, d_cls_jobs[0], d_cls_tile0[0], (int)cls_jobs[0].size(), tile_cursor[0], d_sp, d_def, d_cnt, nullptr);
         h->launches++;
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[5], h->stream));
@@ -1765,8 +1684,7 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
                 const double ppc = sqrt((double)dg.npts() / ((double)(bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1)));
                 b.strip = ppc >= 5.0 ? 4 : (ppc >= 2.5 ? 2 : 1);
                 b.strip = env_int("WPSGPU_STRIP", b.strip, 1, 4) == 3 ? 2 : env_int("WPSGPU_STRIP", b.strip, 1, 4);
-                const bool both = q0.s.use_landmask && q0.fo.masked == WPSGPU_MASKED_BOTH;
-                need += (size_t)b.npack * b.bnx * b.bny * (sizeof(float4) * (both ? 3 : 2) + 1) + 1024;
+                need += (size_t)b.npack * b.bnx * b.bny * (sizeof(float4) * 2 + 1) + 1024;
                 need += dg.npts() * sizeof(float) + (size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 512;   // dump area (per pass at most once)
             } else if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
                 long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);
@@ -1778,7 +1696,7 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
                 }
             } else if (q0.fo.ops[0] == WPSGPU_FOUR_POINT) b.fast = 2;
             else if (q0.fo.ops[0] == WPSGPU_N_NEIGHBOR) b.fast = 3;
-            if (b.fast) need += groups[g].size() * ((size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 256);  // slow bitmaps
+            if (b.fast) need += (size_t)((double)groups[g].size() * dg.npts() / 32.0) * sizeof(int2) + 256;  // share of the slow queue
         }
         if (host) {
             for (int m = 0; m < 3; ++m) if (q0.s.mask[m]) uniq_in[q0.s.mask[m]] = sbytes;
@@ -1794,6 +1712,19 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         if (queue[a].s.raw_nx > 0)
             need += (size_t)(queue[a].s.maxx - queue[a].s.minx + 1) * (queue[a].s.maxy - queue[a].s.miny + 1) * sizeof(float) + 256 + sizeof(DecodeTask);
     need += 2 * (defer_entries * sizeof(Deferred) + 256) + (size_t)njobs * 4096;
+    const int chunk_slabs = env_int("WPSGPU_PIPE_CHUNK", 12, 1, 1 << 20);
+    {
+        // the slow queue's fixed 1 M entries, once per pass (host-pointer mode runs the groups in several passes)
+        int npass = 1;
+        if (host) {
+            npass = 0;
+            for (int g = 0, count = 0; g < njobs; ++g) {
+                count += (int)groups[g].size();
+                if (count >= chunk_slabs || g == njobs - 1) { ++npass; count = 0; }
+            }
+        }
+        need += (size_t)npass * ((size_t(1) << 23) + 4096);
+    }
     h->arena.reset();
     WPS_TRY(h->arena.reserve(need, h->stream));
 
@@ -1821,7 +1752,6 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         for (int k = 0; k < 4; ++k) WPS_CUDA(cudaEventCreate(&tr[k]));
         WPS_CUDA(cudaEventRecord(tr[0], h->s_in));
     }
-    const int chunk_slabs = env_int("WPSGPU_PIPE_CHUNK", 12, 1, 1 << 20);
     std::vector<int> sel;
     int count = 0;
     for (int g = 0; g < njobs; ++g) {

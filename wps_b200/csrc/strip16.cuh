@@ -36,12 +36,12 @@ struct StripJob {
     const float2* xy;
     const float* landmask;
     const float4* P;             // window records [npack][pny][pnx], float4 = 4 levels of source cell (px0 + c, py0 + r), clamped like :1227-1241
-    const float4* TA;            // guard thresholds per window ORIGIN cell, same index space; +Inf = window not clean
-    const float4* TB;            // masked=both: thresholds under interp_water_mask (land points); TA is interp_land_mask then
+    const float4* TA;            // guard thresholds per window ORIGIN cell, same index space
+    const unsigned char* cf;     // per (pack, cell): clean bits of the 4 x 4 stencil anchored at the cell (k_pack_win)
     int nx, ny, nxw, sm1, sm2, sd1, ed1, sd2, ed2, pw;
     int minx, maxx, miny, maxy, bdr;
     int px0, py0, pnx, pny;
-    int nslab, slab0;            // slabs [slab0, slab0 + nslab) of the pointer tables below
+    int nslab, slab0, gslab0;    // slabs [slab0, slab0 + nslab) of the pointer tables below; gslab0 = first slab in the pass's slab table
     int tiles_x, ntiles;
     int both, has_lm;
     float msg, fill, masked;
@@ -54,7 +54,7 @@ struct StripParams {
     StripChunk chunk[STRIP_MAX_CHUNKS];
     float* r_arr[STRIP_MAX_SLABS];
     int* new_pts[STRIP_MAX_SLABS];
-    int* slow[STRIP_MAX_SLABS];
+    SlowQ sq;
 };
 
 // ---- pre-pass: window records, guard thresholds and the slow pass's hints ------------------------------------------------
@@ -113,46 +113,56 @@ __global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, 
     if (cx >= pnx || cy >= pny) return;
     const int c0 = tx + 1, r0 = ty + 1;
     const size_t o = ((size_t)t.pack * pny + cy) * pnx + cx;
-    const_cast<float4*>(jb.rec)[o] = make_float4(s_v[0][r0][c0], s_v[1][r0][c0], s_v[2][r0][c0], s_v[3][r0][c0]);
-    unsigned mwin = 0, mst = 0;
+    {
+        // a non-finite value, or a missing value of huge magnitude, meets zero weights in the neighbouring stencils of a
+        // window: 0 there keeps those sums finite (its own stencils are flagged and never use the record)
+        float q[4];
 #pragma unroll
-    for (int r = -1; r <= 3; ++r)
+        for (int lv = 0; lv < 4; ++lv) { const float v = s_v[lv][r0][c0]; q[lv] = (fabsf(v) <= 3.0e38f && v != msg) ? v : 0.0f; }
+        const_cast<float4*>(jb.rec)[o] = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    // cf byte of the cell = flags of the 4 x 4 stencil anchored at it (cells c-1..c+2, r-1..r+2), per level lv:
+    //   bit lv      stencil is clean under mask A: no missing / masked / non-finite value, every |v| >= 1e-21
+    //   bit 4 + lv  single-mask jobs: the stencil holds a missing or masked value, so sixteen_pt is certain to hand over
+    //               to the next method (:1244-1270) and the slow pass may start the chain there;
+    //               masked=both jobs: stencil is clean under mask B (interp_water_mask, land points)
+    // threshold of the 5 x 5 window whose origin is the cell: 2^-18 of the largest usable magnitude in it (an upper bound
+    // for every stencil inside the window), at least 1e-21
+    unsigned mstA = 0, mstB = 0;
 #pragma unroll
-        for (int c = -1; c <= 3; ++c) {
+    for (int r = -1; r <= 2; ++r)
+#pragma unroll
+        for (int c = -1; c <= 2; ++c) {
             const unsigned m = s_m[r0 + r][c0 + c];
-            mwin |= m;
-            if (r <= 2 && c <= 2) mst |= m;
+            mstA |= m & 1u; mstB |= (m >> 1) & 1u;
         }
-    float thrA[4], thrB[4];
+    float thr[4];
     unsigned cfbits = 0;
 #pragma unroll
     for (int lv = 0; lv < 4; ++lv) {
-        if (!src[lv]) { thrA[lv] = thrB[lv] = -1.0f; continue; }     // level beyond the job's last: records are 0, never flagged
+        if (!src[lv]) { thr[lv] = -1.0f; cfbits |= 0x11u << lv; continue; }     // level beyond the job's last: records are 0, never flagged
         float mx = 0.0f, mn = 3.0e38f;
-        bool bad = false, stmsg = false;
+        bool stmsg = false, stbad = false;
 #pragma unroll
         for (int r = -1; r <= 3; ++r)
 #pragma unroll
             for (int c = -1; c <= 3; ++c) {
                 const float v = s_v[lv][r0 + r][c0 + c], a = fabsf(v);
-                const bool ismsg = v == msg;
-                bad = bad || ismsg || !(a <= 3.0e38f);
-                if (r <= 2 && c <= 2) stmsg = stmsg || ismsg;
-                mx = fmaxf(mx, a); mn = fminf(mn, a);
+                const bool ismsg = v == msg, fin = a <= 3.0e38f;
+                if (fin && !ismsg) mx = fmaxf(mx, a);
+                if (r <= 2 && c <= 2) {
+                    stmsg = stmsg || ismsg;
+                    stbad = stbad || !fin;
+                    mn = fminf(mn, a);
+                }
             }
-        const bool clean = !bad && mn >= 1.0e-21f;
-        const float thr = fmaxf(mx * 3.814697265625e-6f, 1.0e-21f);
-        const float inf = __int_as_float(0x7f800000);
-        thrA[lv] = (clean && !(mwin & 1u)) ? thr : inf;
-        thrB[lv] = (clean && !(mwin & 2u)) ? thr : inf;
-        // single-mask jobs: bit 4+lv = the 4 x 4 stencil anchored here holds a missing or masked value, so sixteen_pt is
-        // certain to hand over to the next method (:1244-1270) and the slow pass may start the chain there
-        if (!both && (stmsg || (mst & 1u))) cfbits |= 16u << lv;
+        const bool clean = !stmsg && !stbad && mn >= 1.0e-21f;
+        thr[lv] = fmaxf(mx * 3.814697265625e-6f, 1.0e-21f);
+        if (clean && !mstA) cfbits |= 1u << lv;
+        if (both) { if (clean && !mstB) cfbits |= 16u << lv; }
+        else if (stmsg || mstA) cfbits |= 16u << lv;
     }
-    const size_t tstride = (size_t)jb.npack * pny * pnx;     // TB follows TA
-    float4* T = const_cast<float4*>(jb.thr);
-    T[o] = make_float4(thrA[0], thrA[1], thrA[2], thrA[3]);
-    if (both) T[tstride + o] = make_float4(thrB[0], thrB[1], thrB[2], thrB[3]);
+    const_cast<float4*>(jb.thr)[o] = make_float4(thr[0], thr[1], thr[2], thr[3]);
     const_cast<unsigned char*>(jb.cf)[o] = (unsigned char)cfbits;
 }
 
@@ -194,7 +204,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
@@ -227,25 +237,34 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     unsigned fillm = 0;                          // bit p: the point receives fill_missing (process_bdy_width interior, landmask == masked)
     int i0 = INT_MAX, j0 = INT_MAX;
     const float lo = (float)(jb.minx + jb.bdr) - 0.5f, hi = (float)(jb.maxx - jb.bdr) + 0.5f;
+    // all loads of the strip first (rows / columns past the grid re-read its last point), then the logic
+    float2 xyv[R];
+    float lmv[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+        const size_t idx = (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1);
+        xyv[p] = __ldg(jb.xy + idx);
+        lmv[p] = jb.has_lm ? __ldg(jb.landmask + idx) : 0.0f;
+    }
+    const int pw = jb.pw, di = jb.sm1 + ii;
+    const bool fill_i = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw;
 #pragma unroll
     for (int p = 0; p < R; ++p) {
         const int jj = jj0 + p;
         active[p] = ii < nx && jj < ny;
         fastpt[p] = false; ci[p] = 0; cj[p] = 0; fx[p] = 0.0f; fy[p] = 0.0f;
-        if (!active[p]) continue;
-        const size_t idx = (size_t)jj * nx + ii;
-        const float2 xy = __ldg(jb.xy + idx);
-        const int di = jb.sm1 + ii, dj = jb.sm2 + jj, pw = jb.pw;
-        const bool in_fill = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
-        const float lm = jb.has_lm ? __ldg(jb.landmask + idx) : 0.0f;
+        const int dj = jb.sm2 + jj;
+        const bool in_fill = fill_i && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw;
+        const float lm = lmv[p];
         bool lm_ok = true, fill = in_fill;
         if (BOTH) {
             if (lm == 1.0f) useB |= 1 << p;
             lm_ok = lm == 0.0f || lm == 1.0f;
         } else fill = fill || (jb.has_lm && lm == jb.masked);
+        fill = fill && active[p];
         if (fill) fillm |= 1u << p;
-        const float xx = xy.x, yy = xy.y;
-        if (!fill && lm_ok && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f &&
+        const float xx = xyv[p].x, yy = xyv[p].y;
+        if (active[p] && !fill && lm_ok && xx >= lo && xx <= hi && fabsf(xx) < 1.0e9f && fabsf(yy) < 1.0e9f &&
             (int)xx >= jb.minx && (int)xx <= jb.maxx && (int)yy >= jb.miny && (int)yy <= jb.maxy) {
             const int i = (int)(xx + 0.00001f), j = (int)(yy + 0.00001f);
             const float x = xx - (float)i, y = yy - (float)j;
@@ -303,7 +322,14 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     const size_t pstride = (size_t)jb.pny * pnx;
     const size_t toff = (size_t)(j0 - jb.py0) * pnx + (i0 - jb.px0);
     const float4* __restrict__ Ta = jb.TA + (size_t)ch.pack0 * pstride + toff;
-    const float4* __restrict__ Tb = jb.TB + (size_t)ch.pack0 * pstride + toff;
+    const unsigned char* __restrict__ cfp = jb.cf + (size_t)ch.pack0 * pstride;
+    // the points' own cells in the flag array, relative to the window origin cell: bit p of cdx / cdy = the cell is one
+    // column / row further (points that are not fast read the origin's flags and ignore them)
+    const unsigned cfo0 = (unsigned)toff;
+    unsigned cdx = 0, cdy = 0;
+#pragma unroll
+    for (int p = 0; p < R; ++p) if (fastpt[p]) { cdx |= (unsigned)(ci[p] - i0) << p; cdy |= (unsigned)(cj[p] - j0) << p; }
+    auto cfo = [&](int p) -> unsigned { return cfo0 + ((cdx >> p) & 1u) + ((cdy >> p) & 1u) * (unsigned)pnx; };
 
     // ---- window source: shared-memory ring fed by bulk copies, or global memory directly
     __shared__ alignas(128) float4 s_win[STAGE ? SNS * SBH * SROW : 1];
@@ -342,20 +368,16 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     // Output addressing: byte offsets of the strip's points / bitmap words, added to the per-level base pointers (warp-uniform,
     // constant bank).  Levels past the job's last one have their pointers aimed at a dump area by the host, so the loop
     // below has no level test at all; stores are predicated, not branched around.
-    unsigned actw[R];
-    unsigned poff[R], woffs[R];
-#pragma unroll
-    for (int p = 0; p < R; ++p) {
-        actw[p] = __ballot_sync(0xffffffffu, active[p]);
-        poff[p] = (unsigned)(((size_t)(jj0 + p) * nx + ii) * sizeof(float));
-        woffs[p] = (unsigned)(((size_t)(jj0 + p) * jb.nxw + tx) * sizeof(int));
-    }
+    const unsigned colw = __ballot_sync(0xffffffffu, ii < nx);   // lanes inside the grid
     const unsigned rowsm = (1u << min(R, ny - jj0)) - 1u;     // rows of the strip that exist
+    const unsigned poff0 = (unsigned)(((size_t)jj0 * nx + ii) * sizeof(float)), prow = (unsigned)(nx * sizeof(float));
+    const unsigned woff0 = (unsigned)(((size_t)jj0 * jb.nxw + tx) * sizeof(int)), wrow = (unsigned)(jb.nxw * sizeof(int));
     const bool anyfill = __any_sync(0xffffffffu, fillm != 0u);
     const float fillv = jb.fill;
     float4 ta = __ldg(Ta);
-    float4 tb = ta;
-    if (BOTH) tb = __ldg(Tb);
+    unsigned cfv = 0;                            // byte p: flags of point p's stencil for the pack
+#pragma unroll
+    for (int p = 0; p < R; ++p) cfv |= (unsigned)__ldg(cfp + cfo(p)) << (8 * p);
 
     const int npk = ch.npk;
     const int slab00 = jb.slab0 + ch.pack0 * 4;
@@ -363,11 +385,14 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     auto packs = [&](auto direct_tag) {
         constexpr bool DIRECT = decltype(direct_tag)::value;
         for (int pk = 0; pk < npk; ++pk) {
-            const float4 cta = ta, ctb = tb;
-            if (pk + 1 < npk) {                      // thresholds of the next pack, one iteration ahead
-                Ta += pstride; Tb += pstride;
+            const float4 cta = ta;
+            const unsigned ccf = cfv;
+            if (pk + 1 < npk) {                      // thresholds and stencil flags of the next pack, one iteration ahead
+                Ta += pstride; cfp += pstride;
                 ta = __ldg(Ta);
-                if (BOTH) tb = __ldg(Tb);
+                cfv = 0;
+#pragma unroll
+                for (int p = 0; p < R; ++p) cfv |= (unsigned)__ldg(cfp + cfo(p)) << (8 * p);
             }
             if (!DIRECT) {
                 __syncwarp();                        // every lane has finished reading the stage that is refilled now
@@ -378,7 +403,12 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
             float2 a01[R], a23[R];
             bool g[R];                               // the guard holds for every row and level of point p so far
 #pragma unroll
-            for (int p = 0; p < R; ++p) { a01[p] = make_float2(0.0f, 0.0f); a23[p] = a01[p]; g[p] = (fastm >> p) & 1u; }
+            for (int p = 0; p < R; ++p) {
+                a01[p] = make_float2(0.0f, 0.0f); a23[p] = a01[p];
+                // the stencil must be clean for all four levels (under the mask the landmask selects, masked=both)
+                const unsigned need = (BOTH && ((useB >> p) & 1)) ? 0xf0u : 0x0fu;
+                g[p] = ((fastm >> p) & 1u) && ((ccf >> (8 * p)) & need) == need;
+            }
 #pragma unroll
             for (int l = 0; l < WIN; ++l) {
                 float4 v[WIN];
@@ -392,8 +422,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                         r01 = __ffma2_rn(wx[p][k], lo2(v[k]), r01);
                         r23 = __ffma2_rn(wx[p][k], hi2(v[k]), r23);
                     }
-                    const float4 th = (BOTH && ((useB >> p) & 1)) ? ctb : cta;
-                    g[p] = g[p] && fabsf(r01.x) > th.x && fabsf(r01.y) > th.y && fabsf(r23.x) > th.z && fabsf(r23.y) > th.w;
+                    g[p] = g[p] && fabsf(r01.x) > cta.x && fabsf(r01.y) > cta.y && fabsf(r23.x) > cta.z && fabsf(r23.y) > cta.w;
                     const float2 wyl = make_float2(wy[p][l], wy[p][l]);
                     a01[p] = __ffma2_rn(wyl, r01, a01[p]);
                     a23[p] = __ffma2_rn(wyl, r23, a23[p]);
@@ -415,23 +444,38 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                     r0 = f ? fillv : r0; r1 = f ? fillv : r1; r2 = f ? fillv : r2; r3 = f ? fillv : r3;
                     ok = ok || f;
                 }
-                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 0]) + poff[p], r0);
-                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 1]) + poff[p], r1);
-                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 2]) + poff[p], r2);
-                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 3]) + poff[p], r3);
+                // (level base + p rows) is warp-uniform arithmetic; the lane adds its own offset
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 0]) + (size_t)p * prow + poff0, r0);
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 1]) + (size_t)p * prow + poff0, r1);
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 2]) + (size_t)p * prow + poff0, r2);
+                st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 3]) + (size_t)p * prow + poff0, r3);
                 word[p] = __ballot_sync(0xffffffffu, ok);
             }
-            if (lane < R) {
-                // lane p writes the words of strip row p: new_pts of the four levels and the pack's slow word
-                unsigned w = word[0], a = actw[0], wo = woffs[0];
+            {
+                // flagged points (rare): one warp-uniform test per pack, the queue code stays out of the way
+                unsigned any = 0;
 #pragma unroll
-                for (int p = 1; p < R; ++p) if (lane == p) { w = word[p]; a = actw[p]; wo = woffs[p]; }
+                for (int p = 0; p < R; ++p) any |= (((rowsm >> p) & 1u) ? colw : 0u) & ~word[p];
+                if (any) {
+                    const int nl = min(4, jb.nslab - (ch.pack0 + pk) * 4);
+#pragma unroll 1
+                    for (int p = 0; p < R; ++p) {
+                        const unsigned sword = (((rowsm >> p) & 1u) ? colw : 0u) & ~word[p];
+                        if (sword) slowq_push(P.sq, sword, lane, jb.gslab0 + (ch.pack0 + pk) * 4, nl, (int)((poff0 >> 2) + p * nx));
+                    }
+                }
+            }
+            if (lane < R) {
+                // lane p writes the new_pts words of strip row p for the four levels
+                unsigned w = word[0];
+#pragma unroll
+                for (int p = 1; p < R; ++p) if (lane == p) w = word[p];
+                const unsigned wo = woff0 + (unsigned)lane * wrow;
                 const bool rowok = (rowsm >> lane) & 1u;
                 st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 0]) + wo, w);
                 st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 1]) + wo, w);
                 st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 2]) + wo, w);
                 st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 3]) + wo, w);
-                st_u32_if(rowok, reinterpret_cast<char*>(P.slow[sl0]) + wo, a & ~w);
             }
         }
     };
