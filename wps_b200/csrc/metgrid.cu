@@ -40,6 +40,7 @@ struct Job {
     // thresholds (two sets for masked=both), cf the slow pass's hint bits; strip = destination points per thread
     int strip;
     const float4* thr;
+    const unsigned* cfw;         // strip jobs: flag words (byte 0 = the cell's own stencil, like cf)
 };
 
 struct SlabPtrs {
@@ -718,7 +719,8 @@ k_metgrid_slowlist(const Job* __restrict__ jobs, int njobs, const SlabPtrs* __re
                 float fx = xx - (float)ci, fy = yy - (float)cj;
                 ci -= jb.bx0; cj -= jb.by0;
                 if ((fabsf(fx) > 0.0001f || fabsf(fy) > 0.0001f) && ci >= 0 && ci < jb.bnx && cj >= 0 && cj < jb.bny) {
-                    unsigned cfb = __ldg(jb.cf + ((size_t)(sl >> 2) * jb.bny + cj) * jb.bnx + ci);
+                    const size_t co = ((size_t)(sl >> 2) * jb.bny + cj) * jb.bnx + ci;
+                    unsigned cfb = jb.strip > 0 ? (__ldg(jb.cfw + co) & 0xffu) : (unsigned)__ldg(jb.cf + co);
                     if ((cfb >> (4 + (sl & 3))) & 1u) first = 1;
                 }
             }
@@ -907,7 +909,7 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                 if (nj + 1 > STRIP_MAX_JOBS || ns + nslot > STRIP_MAX_SLABS || nc + nchunk > STRIP_MAX_CHUNKS) fire();
                 WPS_CHECK(nslot <= STRIP_MAX_SLABS && nchunk <= STRIP_MAX_CHUNKS, -3, "sixteen_pt job too large for one strip launch");
                 StripJob& q = P.job[nj];
-                q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cf;
+                q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cfw;
                 q.nx = jb.nx; q.ny = jb.ny; q.nxw = jb.nxw; q.sm1 = jb.sm1; q.sm2 = jb.sm2;
                 q.sd1 = jb.sd1; q.ed1 = jb.ed1; q.sd2 = jb.sd2; q.ed2 = jb.ed2; q.pw = jb.pw;
                 q.minx = jb.minx; q.maxx = jb.maxx; q.miny = jb.miny; q.maxy = jb.maxy; q.bdr = jb.bdr;
@@ -1209,8 +1211,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
             const size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
             jb.rec = (const float4*)h->arena.take(cells * sizeof(float4));
             jb.thr = (const float4*)h->arena.take(cells * sizeof(float4));
-            jb.cf = (const unsigned char*)h->arena.take(cells);
-            WPS_CHECK(jb.rec && jb.thr && jb.cf, -3, "device arena exhausted (window records)");
+            jb.cfw = (const unsigned*)h->arena.take(cells * sizeof(unsigned));
+            WPS_CHECK(jb.rec && jb.thr && jb.cfw, -3, "device arena exhausted (window records)");
         } else if (jb.fast == 1) {
             size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
             size_t cells8 = (size_t)jb.npack * ((jb.bnx + 7) / 8 * 8) * jb.bny;
@@ -1684,7 +1686,7 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
                 const double ppc = sqrt((double)dg.npts() / ((double)(bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1)));
                 b.strip = ppc >= 5.0 ? 4 : (ppc >= 2.5 ? 2 : 1);
                 b.strip = env_int("WPSGPU_STRIP", b.strip, 1, 4) == 3 ? 2 : env_int("WPSGPU_STRIP", b.strip, 1, 4);
-                need += (size_t)b.npack * b.bnx * b.bny * (sizeof(float4) * 2 + 1) + 1024;
+                need += (size_t)b.npack * b.bnx * b.bny * (sizeof(float4) * 2 + sizeof(unsigned)) + 1024;
                 need += dg.npts() * sizeof(float) + (size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 512;   // dump area (per pass at most once)
             } else if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
                 long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);

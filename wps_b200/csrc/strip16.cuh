@@ -37,7 +37,7 @@ struct StripJob {
     const float* landmask;
     const float4* P;             // window records [npack][pny][pnx], float4 = 4 levels of source cell (px0 + c, py0 + r), clamped like :1227-1241
     const float4* TA;            // guard thresholds per window ORIGIN cell, same index space
-    const unsigned char* cf;     // per (pack, cell): clean bits of the 4 x 4 stencil anchored at the cell (k_pack_win)
+    const unsigned* cf;          // per (pack, cell): flag bytes of the four stencils a strip with this window origin can use (k_pack_win)
     int nx, ny, nxw, sm1, sm2, sd1, ed1, sd2, ed2, pw;
     int minx, maxx, miny, maxy, bdr;
     int px0, py0, pnx, pny;
@@ -71,8 +71,11 @@ __global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, 
     const int pnx = jb.bnx, pny = jb.bny, ntx = (pnx + 15) >> 4;
     const int bx = blockIdx.x % ntx, by = blockIdx.x / ntx;
     if (by * 16 >= pny) return;
-    __shared__ float s_v[4][20][21];
-    __shared__ unsigned char s_m[20][20];     // bit 0: unusable under mask A, bit 1: under mask B
+    // tile of 20 x 20 cells: the block's 16 x 16 cells with one cell of halo to the left / top and three to the right / bottom
+    __shared__ float s_v[4][20][21];           // record values (zeros replaced, unusable values 0)
+    __shared__ float s_a[4][20][21];           // usable magnitude per level (0 where missing / non-finite); later its 5-wide row maximum
+    __shared__ unsigned short s_f[20][20];     // per cell: bit lv = missing value, bit 4+lv = unusable for sixteen_pt, bit 8 / 9 = masked under A / B
+    __shared__ unsigned short s_h[20][20];     // OR of s_f over the four cells c .. c+3 of the row
     const int tid = threadIdx.x;
     const int sx = jb.minx, ex = jb.maxx, sy = jb.miny, ey = jb.maxy, snx = ex - sx + 1;
     const float msg = jb.msg;
@@ -86,84 +89,100 @@ __global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, 
     }
     for (int e = tid; e < 400; e += 256) {
         const int c = e % 20, r = e / 20;
-        const int gx = min(max(jb.bx0 + bx * 16 - 1 + c, sx), ex), gy = min(max(jb.by0 + by * 16 - 1 + r, sy), ey);
+        const int gx = min(max(jb.bx0 + bx * 16 - 1 + c, sx), ex), gy = min(max(jb.by0 + by * 16 - 1 + r, sy), ey);   // clamped like :1227-1241
         const size_t off = (size_t)(gy - sy) * snx + (gx - sx);
+        unsigned f = 0;
 #pragma unroll
         for (int lv = 0; lv < 4; ++lv) {
-            float v = 0.0f;
+            float v = 0.0f, a = 0.0f;
             if (src[lv]) {
                 v = __ldg(src[lv] + off);
                 if (v == 0.0f && msg != 0.0f) v = 1.0e-20f;     // interp_module.F:1255-1257
+                a = fabsf(v);
+                const bool ismsg = v == msg, fin = a <= 3.0e38f;
+                if (ismsg) f |= 1u << lv;
+                if (ismsg || !fin || !(a >= 1.0e-21f)) f |= 16u << lv;
+                // a non-finite or missing value meets zero weights in the neighbouring stencils of a window: 0 keeps those
+                // sums finite (its own stencils are flagged and never use the record)
+                if (ismsg || !fin) { v = 0.0f; a = 0.0f; }
             }
             s_v[lv][r][c] = v;
+            s_a[lv][r][c] = a;
         }
-        unsigned m = 0;
         auto unusable = [&](int sel) -> bool {
             if (!jb.mask[sel]) return false;
             const float mv = __ldg(jb.mask[sel] + off);
             return jb.mask_rel[sel] == REL_GT ? (mv > jb.mask_val[sel]) : (jb.mask_rel[sel] == REL_LT ? (mv < jb.mask_val[sel]) : (mv == jb.mask_val[sel]));
         };
-        if (unusable(selA)) m |= 1u;
-        if (both && unusable(2)) m |= 2u;
-        s_m[r][c] = (unsigned char)m;
+        if (unusable(selA)) f |= 256u;
+        if (both && unusable(2)) f |= 512u;
+        s_f[r][c] = (unsigned short)f;
+    }
+    __syncthreads();
+    // row pass: flags of the 4 cells c .. c+3 and the largest usable magnitude of the 5 cells c .. c+4 (clipped to the tile)
+    float hm[2][4];
+    unsigned hf[2];
+    for (int e = tid, k = 0; e < 400; e += 256, ++k) {
+        const int c = e % 20, r = e / 20;
+        unsigned f = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) if (c + d < 20) f |= s_f[r][c + d];
+        hf[k] = f;
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) {
+            float m = 0.0f;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) if (c + d < 20) m = fmaxf(m, s_a[lv][r][c + d]);
+            hm[k][lv] = m;
+        }
+    }
+    __syncthreads();
+    for (int e = tid, k = 0; e < 400; e += 256, ++k) {
+        const int c = e % 20, r = e / 20;
+        s_h[r][c] = (unsigned short)hf[k];
+#pragma unroll
+        for (int lv = 0; lv < 4; ++lv) s_a[lv][r][c] = hm[k][lv];
     }
     __syncthreads();
     const int tx = tid & 15, ty = tid >> 4;
     const int cx = bx * 16 + tx, cy = by * 16 + ty;
     if (cx >= pnx || cy >= pny) return;
-    const int c0 = tx + 1, r0 = ty + 1;
+    const int c0 = tx + 1, r0 = ty + 1;        // the thread's cell in the tile
     const size_t o = ((size_t)t.pack * pny + cy) * pnx + cx;
-    {
-        // a non-finite value, or a missing value of huge magnitude, meets zero weights in the neighbouring stencils of a
-        // window: 0 there keeps those sums finite (its own stencils are flagged and never use the record)
-        float q[4];
-#pragma unroll
-        for (int lv = 0; lv < 4; ++lv) { const float v = s_v[lv][r0][c0]; q[lv] = (fabsf(v) <= 3.0e38f && v != msg) ? v : 0.0f; }
-        const_cast<float4*>(jb.rec)[o] = make_float4(q[0], q[1], q[2], q[3]);
-    }
-    // cf byte of the cell = flags of the 4 x 4 stencil anchored at it (cells c-1..c+2, r-1..r+2), per level lv:
+    const_cast<float4*>(jb.rec)[o] = make_float4(s_v[0][r0][c0], s_v[1][r0][c0], s_v[2][r0][c0], s_v[3][r0][c0]);
+    // Flag byte of the 4 x 4 stencil anchored at a cell (cells c-1..c+2, r-1..r+2), per level lv:
     //   bit lv      stencil is clean under mask A: no missing / masked / non-finite value, every |v| >= 1e-21
     //   bit 4 + lv  single-mask jobs: the stencil holds a missing or masked value, so sixteen_pt is certain to hand over
     //               to the next method (:1244-1270) and the slow pass may start the chain there;
     //               masked=both jobs: stencil is clean under mask B (interp_water_mask, land points)
+    // The cell's flag WORD holds the bytes of the stencils anchored at (c, r), (c+1, r), (c, r+1), (c+1, r+1): the four
+    // cells the points of a strip whose window origin is (c, r) can fall into -- one load per thread and pack.
+    unsigned present = 0;
+#pragma unroll
+    for (int lv = 0; lv < 4; ++lv) if (src[lv]) present |= 1u << lv;
+    auto stencil_byte = [&](int ax, int ay) -> unsigned {
+        unsigned f = 0;
+#pragma unroll
+        for (int r = -1; r <= 2; ++r) f |= s_h[r0 + ay + r][c0 + ax - 1];
+        const unsigned anymsg = f & 15u, bad = (f >> 4) & 15u, mA = (f >> 8) & 1u, mB = (f >> 9) & 1u;
+        unsigned bits = mA ? 0u : (~bad & 15u);
+        if (both) bits |= mB ? 0u : ((~bad & 15u) << 4);
+        else bits |= (mA ? 15u : anymsg) << 4;
+        // levels beyond the job's last: records are 0, never flagged
+        return (bits & (present | (present << 4))) | ((~present & 15u) * 0x11u);
+    };
     // threshold of the 5 x 5 window whose origin is the cell: 2^-18 of the largest usable magnitude in it (an upper bound
     // for every stencil inside the window), at least 1e-21
-    unsigned mstA = 0, mstB = 0;
-#pragma unroll
-    for (int r = -1; r <= 2; ++r)
-#pragma unroll
-        for (int c = -1; c <= 2; ++c) {
-            const unsigned m = s_m[r0 + r][c0 + c];
-            mstA |= m & 1u; mstB |= (m >> 1) & 1u;
-        }
     float thr[4];
-    unsigned cfbits = 0;
 #pragma unroll
     for (int lv = 0; lv < 4; ++lv) {
-        if (!src[lv]) { thr[lv] = -1.0f; cfbits |= 0x11u << lv; continue; }     // level beyond the job's last: records are 0, never flagged
-        float mx = 0.0f, mn = 3.0e38f;
-        bool stmsg = false, stbad = false;
+        float mx = 0.0f;
 #pragma unroll
-        for (int r = -1; r <= 3; ++r)
-#pragma unroll
-            for (int c = -1; c <= 3; ++c) {
-                const float v = s_v[lv][r0 + r][c0 + c], a = fabsf(v);
-                const bool ismsg = v == msg, fin = a <= 3.0e38f;
-                if (fin && !ismsg) mx = fmaxf(mx, a);
-                if (r <= 2 && c <= 2) {
-                    stmsg = stmsg || ismsg;
-                    stbad = stbad || !fin;
-                    mn = fminf(mn, a);
-                }
-            }
-        const bool clean = !stmsg && !stbad && mn >= 1.0e-21f;
-        thr[lv] = fmaxf(mx * 3.814697265625e-6f, 1.0e-21f);
-        if (clean && !mstA) cfbits |= 1u << lv;
-        if (both) { if (clean && !mstB) cfbits |= 16u << lv; }
-        else if (stmsg || mstA) cfbits |= 16u << lv;
+        for (int r = -1; r <= 3; ++r) mx = fmaxf(mx, s_a[lv][r0 + r][c0 - 1]);
+        thr[lv] = src[lv] ? fmaxf(mx * 3.814697265625e-6f, 1.0e-21f) : -1.0f;
     }
     const_cast<float4*>(jb.thr)[o] = make_float4(thr[0], thr[1], thr[2], thr[3]);
-    const_cast<unsigned char*>(jb.cf)[o] = (unsigned char)cfbits;
+    const_cast<unsigned*>(jb.cfw)[o] = stencil_byte(0, 0) | (stencil_byte(1, 0) << 8) | (stencil_byte(0, 1) << 16) | (stencil_byte(1, 1) << 24);
 }
 
 // ---- strip kernel --------------------------------------------------------------------------------------------------------
@@ -282,6 +301,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     // the packed level-pair arithmetic
     float2 wx[R][WIN];
     float wy[R][WIN];
+    __shared__ float4 s_wy[R == 4 ? WIN * 32 : 1];    // R = 4: the y weights live in shared memory (20 registers less)
     unsigned fastm = 0;
 #pragma unroll
     for (int p = 0; p < R; ++p) {
@@ -318,18 +338,25 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
             for (int k = 0; k < 4; ++k) { wx[p][k] = make_float2(w4x[k], w4x[k]); wy[p][k] = w4y[k]; }
         }
     }
+    if (R == 4) {
+#pragma unroll
+        for (int l = 0; l < WIN; ++l) s_wy[l * 32 + lane] = make_float4(wy[0][l], wy[1 % R][l], wy[2 % R][l], wy[3 % R][l]);
+        __syncwarp();
+    }
     const int pnx = jb.pnx;
     const size_t pstride = (size_t)jb.pny * pnx;
     const size_t toff = (size_t)(j0 - jb.py0) * pnx + (i0 - jb.px0);
     const float4* __restrict__ Ta = jb.TA + (size_t)ch.pack0 * pstride + toff;
-    const unsigned char* __restrict__ cfp = jb.cf + (size_t)ch.pack0 * pstride;
-    // the points' own cells in the flag array, relative to the window origin cell: bit p of cdx / cdy = the cell is one
-    // column / row further (points that are not fast read the origin's flags and ignore them)
-    const unsigned cfo0 = (unsigned)toff;
-    unsigned cdx = 0, cdy = 0;
+    const unsigned* __restrict__ cfp = jb.cf + (size_t)ch.pack0 * pstride + toff;
+    // byte of the flag word that belongs to point p: cell (i0 + dx, j0 + dy) -> byte dx + 2 dy
+    unsigned cfsh = 0;                           // 5 bits per point: shift of its byte, +4 when mask B applies (masked=both, land point)
 #pragma unroll
-    for (int p = 0; p < R; ++p) if (fastpt[p]) { cdx |= (unsigned)(ci[p] - i0) << p; cdy |= (unsigned)(cj[p] - j0) << p; }
-    auto cfo = [&](int p) -> unsigned { return cfo0 + ((cdx >> p) & 1u) + ((cdy >> p) & 1u) * (unsigned)pnx; };
+    for (int p = 0; p < R; ++p) {
+        unsigned sh = 0;
+        if (fastpt[p]) sh = 8u * (unsigned)((ci[p] - i0) + 2 * (cj[p] - j0));
+        if (BOTH && ((useB >> p) & 1)) sh += 4u;
+        cfsh |= sh << (5 * p);
+    }
 
     // ---- window source: shared-memory ring fed by bulk copies, or global memory directly
     __shared__ alignas(128) float4 s_win[STAGE ? SNS * SBH * SROW : 1];
@@ -375,9 +402,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     const bool anyfill = __any_sync(0xffffffffu, fillm != 0u);
     const float fillv = jb.fill;
     float4 ta = __ldg(Ta);
-    unsigned cfv = 0;                            // byte p: flags of point p's stencil for the pack
-#pragma unroll
-    for (int p = 0; p < R; ++p) cfv |= (unsigned)__ldg(cfp + cfo(p)) << (8 * p);
+    unsigned cfv = __ldg(cfp);                   // flag word of the window origin for the pack
 
     const int npk = ch.npk;
     const int slab00 = jb.slab0 + ch.pack0 * 4;
@@ -390,9 +415,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
             if (pk + 1 < npk) {                      // thresholds and stencil flags of the next pack, one iteration ahead
                 Ta += pstride; cfp += pstride;
                 ta = __ldg(Ta);
-                cfv = 0;
-#pragma unroll
-                for (int p = 0; p < R; ++p) cfv |= (unsigned)__ldg(cfp + cfo(p)) << (8 * p);
+                cfv = __ldg(cfp);
             }
             if (!DIRECT) {
                 __syncwarp();                        // every lane has finished reading the stage that is refilled now
@@ -405,15 +428,22 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
 #pragma unroll
             for (int p = 0; p < R; ++p) {
                 a01[p] = make_float2(0.0f, 0.0f); a23[p] = a01[p];
-                // the stencil must be clean for all four levels (under the mask the landmask selects, masked=both)
-                const unsigned need = (BOTH && ((useB >> p) & 1)) ? 0xf0u : 0x0fu;
-                g[p] = ((fastm >> p) & 1u) && ((ccf >> (8 * p)) & need) == need;
+                // the point's stencil must be clean for all four levels (under the mask the landmask selects, masked=both)
+                g[p] = ((fastm >> p) & 1u) && ((ccf >> ((cfsh >> (5 * p)) & 31u)) & 0xfu) == 0xfu;
             }
 #pragma unroll
             for (int l = 0; l < WIN; ++l) {
                 float4 v[WIN];
 #pragma unroll
                 for (int k = 0; k < WIN; ++k) v[k] = DIRECT ? __ldg(Pw + l * pnx + k) : sw[l * SROW + k];
+                float wyr[R];
+                if (R == 4) {
+                    const float4 w4 = s_wy[l * 32 + lane];
+                    wyr[0] = w4.x; wyr[1 % R] = w4.y; wyr[2 % R] = w4.z; wyr[3 % R] = w4.w;
+                } else {
+#pragma unroll
+                    for (int p = 0; p < R; ++p) wyr[p] = wy[p][l];
+                }
 #pragma unroll
                 for (int p = 0; p < R; ++p) {
                     float2 r01 = __fmul2_rn(wx[p][0], lo2(v[0])), r23 = __fmul2_rn(wx[p][0], hi2(v[0]));
@@ -423,7 +453,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                         r23 = __ffma2_rn(wx[p][k], hi2(v[k]), r23);
                     }
                     g[p] = g[p] && fabsf(r01.x) > cta.x && fabsf(r01.y) > cta.y && fabsf(r23.x) > cta.z && fabsf(r23.y) > cta.w;
-                    const float2 wyl = make_float2(wy[p][l], wy[p][l]);
+                    const float2 wyl = make_float2(wyr[p], wyr[p]);
                     a01[p] = __ffma2_rn(wyl, r01, a01[p]);
                     a23[p] = __ffma2_rn(wyl, r23, a23[p]);
                 }
