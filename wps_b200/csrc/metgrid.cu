@@ -873,67 +873,104 @@ static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
 }
 
 // Tolerance-mode sixteen_pt jobs of one pass -> as few strip launches as the parameter block allows.
-template <int R, bool BOTH>
-static void launch_strip_kernel(const StripParams& sp, unsigned tiles, unsigned chunks, bool stage, cudaStream_t st)
+template <int R>
+static void launch_strip_kernel(const StripParams& sp, unsigned tiles, unsigned nwork, bool stage, cudaStream_t st)
 {
-    if (stage && R > 1) k_metgrid_strip16<R, BOTH, (R > 1)><<<dim3(tiles, chunks), 32, 0, st>>>(sp);
-    else k_metgrid_strip16<R, BOTH, false><<<dim3(tiles, chunks), 32, 0, st>>>(sp);
+    if (stage && R > 1) k_metgrid_strip16<R, (R > 1)><<<dim3(tiles, nwork), 32, 0, st>>>(sp);
+    else k_metgrid_strip16<R, false><<<dim3(tiles, nwork), 32, 0, st>>>(sp);
 }
 
 static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std::vector<int>& sel, const std::vector<SlabPtrs>& sp,
                          float* dump_r, int* dump_w, const SlowQ& sq)
 {
-    constexpr int SW = 1;
     const bool stage = env_int("WPSGPU_STRIP_STAGE", 1, 0, 1) != 0;   // 0: windows straight from global memory (A/B measurements)
-    const int chunk_packs = env_int("WPSGPU_STRIP_CHUNK", 16, 1, 64);
-    for (int R : { 4, 2, 1 })
-        for (int both = 0; both < 2; ++both) {
+    const int work_packs = env_int("WPSGPU_STRIP_CHUNK", 16, 1, 64);    // packs per block
+    // jobs that share the destination grid, the cached coordinates and the record-array geometry form a class: a block
+    // does the level-independent set-up once for all of them
+    auto same_geometry = [](const Job& a, const Job& b) {
+        return a.xy == b.xy && a.nx == b.nx && a.ny == b.ny && a.sm1 == b.sm1 && a.sm2 == b.sm2 && a.bx0 == b.bx0 && a.by0 == b.by0 &&
+               a.bnx == b.bnx && a.bny == b.bny && a.minx == b.minx && a.maxx == b.maxx && a.miny == b.miny && a.maxy == b.maxy && a.bdr == b.bdr;
+    };
+    for (int R : { 4, 2, 1 }) {
+        std::vector<int> todo;
+        for (int j : sel) if (jobs[j].strip == R) todo.push_back(j);
+        while (!todo.empty()) {
+            // one launch: classes are taken whole as long as the parameter block has room
             StripParams P;
             P.sq = sq;
-            int nj = 0, ns = 0, nc = 0;
+            int nj = 0, ns = 0, nseg = 0, nwork = 0;
             unsigned tiles = 0;
-            auto fire = [&]() {
-                if (nc == 0) return;
-                if (R == 4) { if (both) launch_strip_kernel<4, true>(P, tiles, nc, stage, h->stream); else launch_strip_kernel<4, false>(P, tiles, nc, stage, h->stream); }
-                else if (R == 2) { if (both) launch_strip_kernel<2, true>(P, tiles, nc, stage, h->stream); else launch_strip_kernel<2, false>(P, tiles, nc, stage, h->stream); }
-                else { if (both) launch_strip_kernel<1, true>(P, tiles, nc, stage, h->stream); else launch_strip_kernel<1, false>(P, tiles, nc, stage, h->stream); }
-                h->launches++;
-                nj = ns = nc = 0; tiles = 0;
-            };
-            for (int j : sel) {
-                const Job& jb = jobs[j];
-                const bool jboth = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
-                if (jb.strip != R || (int)jboth != both) continue;
-                const int nchunk = (jb.npack + chunk_packs - 1) / chunk_packs;
-                const int nslot = jb.npack * 4;      // levels past the last one write to the dump area
-                if (nj + 1 > STRIP_MAX_JOBS || ns + nslot > STRIP_MAX_SLABS || nc + nchunk > STRIP_MAX_CHUNKS) fire();
-                WPS_CHECK(nslot <= STRIP_MAX_SLABS && nchunk <= STRIP_MAX_CHUNKS, -3, "sixteen_pt job too large for one strip launch");
-                StripJob& q = P.job[nj];
-                q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cfw;
-                q.nx = jb.nx; q.ny = jb.ny; q.nxw = jb.nxw; q.sm1 = jb.sm1; q.sm2 = jb.sm2;
-                q.sd1 = jb.sd1; q.ed1 = jb.ed1; q.sd2 = jb.sd2; q.ed2 = jb.ed2; q.pw = jb.pw;
-                q.minx = jb.minx; q.maxx = jb.maxx; q.miny = jb.miny; q.maxy = jb.maxy; q.bdr = jb.bdr;
-                q.px0 = jb.bx0; q.py0 = jb.by0; q.pnx = jb.bnx; q.pny = jb.bny;
-                q.nslab = jb.nslab; q.slab0 = ns; q.gslab0 = jb.slab0;
-                q.tiles_x = jb.tiles_x; q.ntiles = jb.tiles_x * ((jb.ny + R * SW - 1) / (R * SW));
-                q.both = jboth ? 1 : 0; q.has_lm = jb.landmask != nullptr ? 1 : 0;
-                q.msg = jb.msg; q.fill = jb.fill; q.masked = jb.masked;
-                for (int k = 0; k < jb.nslab; ++k) {
-                    const SlabPtrs& p = sp[jb.slab0 + k];
-                    P.r_arr[ns + k] = p.r_arr; P.new_pts[ns + k] = p.new_pts;
+            std::vector<int> rest;
+            std::vector<char> taken(todo.size(), 0);
+            bool full = false;
+            for (size_t a = 0; a < todo.size() && !full; ++a) {
+                if (taken[a]) continue;
+                // the class of todo[a]
+                std::vector<int> cls;
+                for (size_t b = a; b < todo.size(); ++b)
+                    if (!taken[b] && same_geometry(jobs[todo[a]], jobs[todo[b]])) cls.push_back((int)b);
+                int c_slots = 0, c_packs = 0;
+                for (int b : cls) { c_slots += jobs[todo[b]].npack * 4; c_packs += jobs[todo[b]].npack; }
+                const int c_work = (c_packs + work_packs - 1) / work_packs;
+                const int c_seg = (int)cls.size() + c_work;       // upper bound: every cut adds a segment
+                WPS_CHECK((int)cls.size() <= STRIP_MAX_JOBS && c_slots <= STRIP_MAX_SLABS && c_seg <= STRIP_MAX_SEGS && c_work <= STRIP_MAX_WORK, -3,
+                          "sixteen_pt jobs of one grid too large for one strip launch");
+                if (nj + (int)cls.size() > STRIP_MAX_JOBS || ns + c_slots > STRIP_MAX_SLABS || nseg + c_seg > STRIP_MAX_SEGS || nwork + c_work > STRIP_MAX_WORK) {
+                    full = true;
+                    break;
                 }
-                for (int k = jb.nslab; k < nslot; ++k) { P.r_arr[ns + k] = dump_r; P.new_pts[ns + k] = dump_w; }
-                // chunks of equal size (e.g. 9 packs -> 5 + 4, not 8 + 1)
-                const int per = (jb.npack + nchunk - 1) / nchunk;
-                for (int c = 0; c < nchunk; ++c) {
-                    StripChunk& ck = P.chunk[nc++];
-                    ck.job = (short)nj; ck.pack0 = (short)(c * per); ck.npk = (short)std::min(per, jb.npack - c * per); ck.pad = 0;
+                // work items of equal size (e.g. 29 packs -> 15 + 14), cut across the class's jobs
+                const int per = (c_packs + c_work - 1) / c_work;
+                int in_work = 0;
+                P.work[nwork].seg0 = (short)nseg; P.work[nwork].nseg = 0;
+                for (int b : cls) {
+                    taken[b] = 1;
+                    const Job& jb = jobs[todo[b]];
+                    const bool jboth = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
+                    const int nslot = jb.npack * 4;          // levels past the last one write to the dump area
+                    StripJob& q = P.job[nj];
+                    q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cfw;
+                    q.nx = jb.nx; q.ny = jb.ny; q.nxw = jb.nxw; q.sm1 = jb.sm1; q.sm2 = jb.sm2;
+                    q.sd1 = jb.sd1; q.ed1 = jb.ed1; q.sd2 = jb.sd2; q.ed2 = jb.ed2; q.pw = jb.pw;
+                    q.minx = jb.minx; q.maxx = jb.maxx; q.miny = jb.miny; q.maxy = jb.maxy; q.bdr = jb.bdr;
+                    q.px0 = jb.bx0; q.py0 = jb.by0; q.pnx = jb.bnx; q.pny = jb.bny;
+                    q.nslab = jb.nslab; q.slab0 = ns; q.gslab0 = jb.slab0;
+                    q.tiles_x = jb.tiles_x; q.ntiles = jb.tiles_x * ((jb.ny + R - 1) / R);
+                    q.both = jboth ? 1 : 0; q.has_lm = jb.landmask != nullptr ? 1 : 0;
+                    q.msg = jb.msg; q.fill = jb.fill; q.masked = jb.masked;
+                    for (int k = 0; k < jb.nslab; ++k) {
+                        const SlabPtrs& p = sp[jb.slab0 + k];
+                        P.r_arr[ns + k] = p.r_arr; P.new_pts[ns + k] = p.new_pts;
+                    }
+                    for (int k = jb.nslab; k < nslot; ++k) { P.r_arr[ns + k] = dump_r; P.new_pts[ns + k] = dump_w; }
+                    for (int pk = 0; pk < jb.npack;) {
+                        if (in_work == per) {                 // next block
+                            ++nwork;
+                            P.work[nwork].seg0 = (short)nseg; P.work[nwork].nseg = 0;
+                            in_work = 0;
+                        }
+                        const int n = std::min(per - in_work, jb.npack - pk);
+                        StripSeg& sgm = P.seg[nseg++];
+                        sgm.job = (short)nj; sgm.pack0 = (short)pk; sgm.npk = (short)n; sgm.pad = 0;
+                        P.work[nwork].nseg++;
+                        in_work += n; pk += n;
+                    }
+                    tiles = std::max(tiles, (unsigned)q.ntiles);
+                    ns += nslot; nj++;
                 }
-                tiles = std::max(tiles, (unsigned)q.ntiles);
-                ns += nslot; nj++;
+                ++nwork;
             }
-            fire();
+            for (size_t a = 0; a < todo.size(); ++a) if (!taken[a]) rest.push_back(todo[a]);
+            if (nwork > 0) {
+                if (R == 4) launch_strip_kernel<4>(P, tiles, nwork, stage, h->stream);
+                else if (R == 2) launch_strip_kernel<2>(P, tiles, nwork, stage, h->stream);
+                else launch_strip_kernel<1>(P, tiles, nwork, stage, h->stream);
+                h->launches++;
+            }
+            WPS_CHECK(rest.size() < todo.size(), -3, "strip launch made no progress");
+            todo.swap(rest);
         }
+    }
     WPS_CUDA(cudaGetLastError());
     return 0;
 }
