@@ -62,42 +62,58 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_sample(config, nslab=16):
-    """Bounded sample of the step for the CPU arm: slab mix proportional to the step's chain mix."""
+def step_config(config, pts):
+    """The `config` object of the JSON line: identical for the device arm and the reference arm."""
     from wps_b200 import synth
-    sx, sy, dlat, dlon = config["src"]
-    ls = synth.landsea_np(sx, sy)
+    return {"workload": WORKLOAD, "slabs_per_step": synth.n_slabs(synth.gfs_slab_table(config["nlev"])), "points_per_step_per_gpu": pts,
+            "l2": "inputs (792 MB of source slabs) and outputs (1.45 GB) per step exceed the 126 MB L2",
+            "sharding": "one FILE time per GPU per step (field x level x time shard, no collective)",
+            "inputs": "synth.gfs_step_numpy(config2): the same 190 slabs, masks and values in both arms"}
+
+
+def cpu_step(config):
+    """The whole step as the list of interp_met_field calls the CPU arm makes: every slab of synth.gfs_step_numpy."""
+    from wps_b200 import synth
+    ls, fields = synth.gfs_step_numpy(config)
     lsh = synth.add_halo(ls)
-    picks = [("TT", synth.C3D, 1, 1e20, 0.0, None, "smooth")] * 5 + [("UU", synth.C3D, 2, 1e20, 0.0, None, "wind")] * 4 + \
-            [("VV", synth.C3D, 3, 1e20, 0.0, None, "wind")] * 4 + [("PSFC", "four_pt+average_4pt", 1, 1e20, 1e20, None, "smooth")] + \
-            [("ST000010", synth.SOIL, 1, -1e30, 285.0, lsh, "land")] * 2
-    picks = picks[:nslab]
-    sample = []
-    for k, (name, chain, stag, msg, fill, mask, kind) in enumerate(picks):
-        slab = synth.add_halo(synth.slab_np(sx, sy, 1000 + k, kind, ls, np.float32(msg)))
-        sample.append(dict(name=name, chain=chain, stagger=stag, missing=msg, fill=fill,
-                           masked=0.0 if mask is not None else -2.0,   # soil fields: masked=water, interp_mask=LANDSEA(0)
-                           mask_val=(0.0, 1e20, 1e20) if mask is not None else (1e20, 1e20, 1e20), mask=mask,
-                           land_mask=None, water_mask=None, use_landmask=(stag == 1), slab=slab))
-    return sample
+    calls = []
+    for f in fields:
+        e = f["e"]
+        mask, lmask, wmask, mv = None, None, None, (1e20, 1e20, 1e20)
+        if e["mask"] is not None:
+            if e["mask"][0] == "mask":
+                mask, mv = lsh, (e["mask"][1], 1e20, 1e20)
+            else:
+                lmask, wmask, mv = lsh, lsh, (1e20, e["mask"][1], e["mask"][2])
+        for k in range(e["nlev"]):
+            calls.append(dict(name=e["field"], chain=e["chain"], stagger=e["stagger"], missing=e["missing"], fill=e["fill"],
+                              masked=e["masked"], mask_val=mv, mask=mask, land_mask=lmask, water_mask=wmask,
+                              use_landmask=(e["stagger"] == 1), slab=f["slabs"][k]))
+    return calls
 
 
-def cpu_arm(config, nslab, nprocs, repeats=1):
+_CPU = {}
+
+
+def cpu_arm(config, nprocs, calls=None):
+    """One step (all 190 slabs) through the oracle restatement of interp_met_field on `nprocs` host processes."""
     from oracle import oracle as O, cpu_bench
     from wps_b200 import synth
     sx, sy, dlat, dlon = config["src"]
     nx, ny, dx, tl1, tl2, slon, rlat, rlon = config["dom"]
     O.set_transc_mode(0)
-    dom = O.map_set(O.PROJ_LC, truelat1=tl1, truelat2=tl2, stdlon=slon, lat1=rlat, lon1=rlon, knowni=(nx + 1) / 2.0,
-                    knownj=(ny + 1) / 2.0, dx=dx)
-    grids = {1: O.get_lat_lon_fields(dom, 1, 1, nx, ny, O.M), 2: O.get_lat_lon_fields(dom, 1, 1, nx + 1, ny, O.U),
-             3: O.get_lat_lon_fields(dom, 1, 1, nx, ny + 1, O.V)}
+    if "grids" not in _CPU:
+        dom = O.map_set(O.PROJ_LC, truelat1=tl1, truelat2=tl2, stdlon=slon, lat1=rlat, lon1=rlon, knowni=(nx + 1) / 2.0,
+                        knownj=(ny + 1) / 2.0, dx=dx)
+        _CPU["grids"] = {1: O.get_lat_lon_fields(dom, 1, 1, nx, ny, O.M), 2: O.get_lat_lon_fields(dom, 1, 1, nx + 1, ny, O.U),
+                         3: O.get_lat_lon_fields(dom, 1, 1, nx, ny + 1, O.V)}
+        lam = np.deg2rad(_CPU["grids"][1][1]) % (2 * np.pi)
+        _CPU["landmask"] = (synth.landsea_fn(np, lam, np.deg2rad(_CPU["grids"][1][0])) > synth.LAND_THRESHOLD).astype(np.float32)
+        _CPU["calls"] = cpu_step(config)
+    calls = calls if calls is not None else _CPU["calls"]
     src_kw = dict(dlat=dlat, dlon=dlon, known_x=1.0, known_y=1.0, known_lat=90.0, known_lon=0.0, earth_radius=6371229.0)
-    sample = cpu_sample(config, nslab)
-    lam = np.deg2rad(grids[1][1]) % (2 * np.pi)
-    landmask = (synth.landsea_fn(np, lam, np.deg2rad(grids[1][0])) > synth.LAND_THRESHOLD).astype(np.float32)
-    pps, dt, pts, nprocs = cpu_bench.run(src_kw, grids, landmask, (1, nx, 1, ny), sample, nprocs, repeats)
-    desc = "%d slabs of the step (TT/UU/VV sixteen_pt chain x13, PSFC four_pt, 2 masked soil search chains) on the full 1799x1059 grid, %d-process patch decomposition" % (len(sample) * repeats, nprocs)
+    pps, dt, pts, nprocs = cpu_bench.run(src_kw, _CPU["grids"], _CPU["landmask"], (1, nx, 1, ny), calls, nprocs, 1)
+    desc = "%d slabs (the whole step of synth.gfs_step_numpy: same table, masks and values as the device arm) on the full 1799x1059 grid, %d-process patch decomposition as in the dmpar build" % (len(calls), nprocs)
     return pps, dt, pts, nprocs, desc
 
 
@@ -108,17 +124,17 @@ def run_reference(args, rank):
     config = synth.CONFIGS["config2"]
     nprocs = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
-        cpu_arm(config, 2, nprocs)
+        cpu_arm(config, nprocs)
     times, pts = [], 0
     for _ in range(args.steps):
-        pps, dt, p, nprocs, desc = cpu_arm(config, 16, nprocs, 8)
+        pps, dt, p, nprocs, desc = cpu_arm(config, nprocs)
         times.append(dt)
         pts = p
     ms = 1e3 * float(np.mean(times))
     value = pts / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "step_sample": desc},
+            "dtype": "f32", "data": "synthetic", "config": step_config(config, pts),
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -142,34 +158,16 @@ def build_workload(h, torch, dev, config, device_mode=True):
     lam = torch.deg2rad(grids[0][1]) % (2 * np.pi)
     phi = torch.deg2rad(grids[0][0])
     landmask = (synth.landsea_fn(torch, lam, phi) > synth.LAND_THRESHOLD).float().contiguous()
-    table = synth.gfs_slab_table(config["nlev"])
-    g = torch.Generator(device=dev)
-    g.manual_seed(20261019)
-    lam_s = torch.linspace(0, 2 * np.pi, sx + 1, device=dev)[:-1][None, :]
-    phi_s = torch.linspace(np.pi / 2, -np.pi / 2, sy, device=dev)[:, None]
-    ls = (synth.landsea_fn(torch, lam_s, phi_s) > synth.LAND_THRESHOLD).float()
+    ls_np, fields = synth.gfs_step_numpy(config)
+    ls = torch.from_numpy(ls_np).to(dev)
     lsh = synth.add_halo(ls)
     plan = []
-    seed = 0
-    for e in table:
+    for f in fields:
+        e = f["e"]
         gid = {capi.M: 0, capi.U: 1, capi.V: 2}[e["stagger"]]
         gy, gx = grids[gid][0].shape
         n = e["nlev"]
-        if e["kind"] == "landsea":
-            slabs = ls[None].repeat(n, 1, 1)
-        elif e["kind"] == "wind":
-            ph = torch.arange(n, device=dev, dtype=torch.float32)[:, None, None] * 0.1
-            slabs = 12.0 * torch.sin(3 * lam_s[None] + ph) * torch.cos(2 * phi_s[None]) + (torch.rand((n, sy, sx), device=dev, generator=g) - 0.5) * 0.024
-        else:
-            lev = torch.arange(n, device=dev, dtype=torch.float32)[:, None, None] * 0.5
-            slabs = 280.0 + 30.0 * torch.sin(3 * lam_s[None]) * torch.cos(2 * phi_s[None]) + lev + (torch.rand((n, sy, sx), device=dev, generator=g) - 0.5) * 0.06
-        slabs = slabs.float()
-        slabs[torch.rand((n, sy, sx), device=dev, generator=g) < 0.001] = 0.0
-        if e["kind"] == "land":
-            slabs[:, ls == 0] = e["missing"]
-        elif e["kind"] == "water":
-            slabs[:, ls == 1] = e["missing"]
-        slabs = synth.add_halo(slabs)
+        slabs = torch.from_numpy(f["slabs"]).to(dev)
         masks, mv = (None, None, None), (1e20, 1e20, 1e20)
         if e["mask"] is not None:
             if e["mask"][0] == "mask":
@@ -181,7 +179,6 @@ def build_workload(h, torch, dev, config, device_mode=True):
         npw = torch.zeros((n, gy, capi.nwords(gx)), dtype=torch.int32, device=dev)
         plan.append(dict(e=e, gid=gid, fo=fo, slabs=slabs, masks=masks, r=r, npw=npw,
                          use_landmask=(e["stagger"] == capi.M)))
-        seed += n
     return dict(dom=dom, src=src, grids=grids, landmask=landmask, plan=plan, nx=nx, ny=ny)
 
 
@@ -493,9 +490,7 @@ def run_b200(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "slabs_per_step": len([0 for p in w["plan"] for _ in range(p["slabs"].shape[0])]),
-                           "points_per_step_per_gpu": pts, "l2": "inputs (792 MB of source slabs) and outputs (1.45 GB) per step exceed the 126 MB L2",
-                           "sharding": "one FILE time per GPU per step (field x level x time shard, no collective)"},
+                "config": dict(step_config(config, pts), precision="tolerance (sixteen_pt <= 1e-5, north_star)" if PRECISION == 1 else "exact (bit-identical sixteen_pt)"),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_unit": "bytes per step (all launches of the kernel), ncu dram read+write; algorithmic = %d" % int(ALG_BYTES_PER_POINT * kp),
                              "kernel": K16 if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
@@ -510,12 +505,12 @@ def run_b200(args, rank, world, local_rank):
             line["geogrid"] = geo
             line["vertical_fill"] = vfill
         if world == 1 and not args.no_cpu:
-            pps, dt, cpts, nprocs, desc = cpu_arm(config, 16, os.cpu_count() or 1, 8)
+            pps, dt, cpts, nprocs, desc = cpu_arm(config, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}
-            # also the single-thread figure, on the first slabs of the same sample
-            pps1, dt1, _, _, desc1 = cpu_arm(config, 2, 1, 1)
+            # also the single-thread figure, on the first two slabs of the same step
+            pps1, dt1, _, _, _ = cpu_arm(config, 1, calls=_CPU["calls"][:2])
             line["cpu_baseline"]["single_thread"] = {"value": pps1, "unit": "points/s", "cores": 1, "seconds": dt1,
-                                                     "sample": "2 TT slabs (sixteen_pt chain) on the full grid, one process"}
+                                                     "sample": "the first 2 TT slabs of the step (sixteen_pt chain) on the full grid, one process"}
         print(json.dumps(line))
     h.close()
     if world > 1:

@@ -192,23 +192,27 @@ static float search_extrap(const ictx *c, float xx, float yy, int izz, int idx)
     int nx = c->ex - c->sx + 1, ny = c->ey - c->sy + 1;
     if (o_nint(xx) < c->sx || o_nint(xx) > c->ex || o_nint(yy) < c->sy || o_nint(yy) > c->ey) return c->msgval;
     int maxdepth = c->opts[idx - 2];
-    unsigned char *b = (unsigned char *)calloc((size_t)nx * (size_t)ny, 1);
+    /* bitarray_create (interp_module.F:490, bitarray_module.F:25-50): one BIT per source cell */
+    const size_t nwords = ((size_t)nx * (size_t)ny + 31) / 32;
+    unsigned *b = (unsigned *)calloc(nwords, sizeof(unsigned));
     long cap = 1024, head = 0, tail = 0;
     qd *q = (qd *)malloc(sizeof(qd) * (size_t)cap);
 #define QPUSH(v) do { if (tail == cap) { cap *= 2; q = (qd *)realloc(q, sizeof(qd) * (size_t)cap); } q[tail++] = (v); } while (0)
-#define BT(i, j) b[(long)((j) - c->sy) * nx + ((i) - c->sx)]
+#define BPOS(i, j) ((size_t)((j) - c->sy) * (size_t)nx + (size_t)((i) - c->sx))
+#define BT(i, j) ((b[BPOS(i, j) >> 5] >> (BPOS(i, j) & 31)) & 1u)
+#define BSET(i, j) (b[BPOS(i, j) >> 5] |= 1u << (BPOS(i, j) & 31))
     int found_valid = 0, i = 0, j = 0;
     qd d; d.x = o_nint(xx); d.y = o_nint(yy); d.depth = 0;
-    QPUSH(d); BT(d.x, d.y) = 1;
+    QPUSH(d); BSET(d.x, d.y);
     while (head < tail && !found_valid) {
         d = q[head++];
         i = d.x; j = d.y;
         if (A3(c, i, j, izz) != c->msgval && mask_valid(c, i, j)) found_valid = 1;
         /* neighbours are pushed even when this node is valid; d.depth accumulates across siblings */
-        if (i - 1 >= c->sx && !BT(i - 1, j) && d.depth < maxdepth) { d.x = i - 1; d.y = j; d.depth = d.depth + 1; QPUSH(d); BT(i - 1, j) = 1; }
-        if (i + 1 <= c->ex && !BT(i + 1, j) && d.depth < maxdepth) { d.x = i + 1; d.y = j; d.depth = d.depth + 1; QPUSH(d); BT(i + 1, j) = 1; }
-        if (j - 1 >= c->sy && !BT(i, j - 1) && d.depth < maxdepth) { d.x = i; d.y = j - 1; d.depth = d.depth + 1; QPUSH(d); BT(i, j - 1) = 1; }
-        if (j + 1 <= c->ey && !BT(i, j + 1) && d.depth < maxdepth) { d.x = i; d.y = j + 1; d.depth = d.depth + 1; QPUSH(d); BT(i, j + 1) = 1; }
+        if (i - 1 >= c->sx && !BT(i - 1, j) && d.depth < maxdepth) { d.x = i - 1; d.y = j; d.depth = d.depth + 1; QPUSH(d); BSET(i - 1, j); }
+        if (i + 1 <= c->ex && !BT(i + 1, j) && d.depth < maxdepth) { d.x = i + 1; d.y = j; d.depth = d.depth + 1; QPUSH(d); BSET(i + 1, j); }
+        if (j - 1 >= c->sy && !BT(i, j - 1) && d.depth < maxdepth) { d.x = i; d.y = j - 1; d.depth = d.depth + 1; QPUSH(d); BSET(i, j - 1); }
+        if (j + 1 <= c->ey && !BT(i, j + 1) && d.depth < maxdepth) { d.x = i; d.y = j + 1; d.depth = d.depth + 1; QPUSH(d); BSET(i, j + 1); }
     }
     float r;
     if (found_valid) {
@@ -226,6 +230,8 @@ static float search_extrap(const ictx *c, float xx, float yy, int izz, int idx)
     return r;
 #undef QPUSH
 #undef BT
+#undef BSET
+#undef BPOS
 }
 
 /* pop order of the BFS (ignores data); used to test the closed-form ring order of SURVEY 8(a8) */

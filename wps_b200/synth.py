@@ -77,6 +77,27 @@ def slab_np(nx, ny, seed, kind, landsea=None, missing=1e20):
     return f
 
 
+def gfs_step_numpy(config, seed0=20261019):
+    """The slabs of one FILE time of `config` as numpy arrays -- the SAME table, masks and values for the device arm and the
+    CPU reference arm of bench.py.  -> (landsea, [dict(e=table entry, slabs=[nlev][sy][sx + 6] halo'd float32)])"""
+    sx, sy, _, _ = config["src"]
+    key = (sx, sy, config["nlev"], seed0)
+    if key in _STEP_CACHE:
+        return _STEP_CACHE[key]
+    ls = landsea_np(sx, sy)
+    out, seed = [], seed0
+    for e in gfs_slab_table(config["nlev"]):
+        lev = [add_halo(slab_np(sx, sy, seed + k, e["kind"], ls, np.float32(e["missing"]))) for k in range(e["nlev"])]
+        seed += e["nlev"]
+        out.append(dict(e=e, slabs=np.stack(lev)))
+    _STEP_CACHE.clear()          # one step at a time: 0.8 GB for config 2
+    _STEP_CACHE[key] = (ls, out)
+    return ls, out
+
+
+_STEP_CACHE = {}
+
+
 def add_halo(slab, bdr=3):
     """halo_slab of process_domain_module.F:1121-1135 (global lat-lon source); works for numpy and torch."""
     nx = slab.shape[-1]
@@ -96,4 +117,13 @@ CONFIGS = {
     "config1": dict(src=(360, 181, -1.0, 1.0), nlev=32, dom=(100, 100, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)),
     # BASELINE.json configs[1]: GFS 0.25 deg, 34 levels -> 3-km CONUS Lambert 1799x1059 (HRRR-like)
     "config2": dict(src=(1440, 721, -0.25, 0.25), nlev=34, dom=(1799, 1059, 3000.0, 38.5, 38.5, -97.5, 38.5, -97.5)),
+    # BASELINE.json configs[2]: geogrid 30-arc-second topography + 21-category land use -> the same 3-km CONUS domain, smth-desmth
+    "config3": dict(dom=(1799, 1059, 3000.0, 38.5, 38.5, -97.5, 38.5, -97.5), dx_deg=0.00833333, known_lat=-89.99583, known_lon=-179.99583,
+                    tile=1200, ncat=21, smooth_passes=1),
+    # BASELINE.json configs[3]: 3-domain nest 27/9/3 km (parent_grid_ratio 3, namelist.wps-style i/j_parent_start), masked SST / soil
+    # fields, Lambert-grid source winds rotated to earth-relative and back (map_to_met + met_to_map)
+    "config4": dict(src=(720, 361, -0.5, 0.5), nlev=8, dom=(150, 130, 27000.0, 30.0, 60.0, -98.0, 38.0, -98.0),
+                    nests=[(1, 1, 1, 150, 130), (1, 3, (40, 35), 160, 151), (2, 3, (50, 45), 172, 163)]),   # (parent, ratio, (i, j)_parent_start, e_we, e_sn)
+    # BASELINE.json configs[4]: ERA5-shaped 0.25 deg, 137 model levels -> 1-km 4000x4000 Lambert, sharded field x level
+    "config5": dict(src=(1440, 721, -0.25, 0.25), nlev=137, dom=(4000, 4000, 1000.0, 38.5, 38.5, -97.5, 38.5, -97.5)),
 }
