@@ -86,6 +86,18 @@ int64_t wpsgpu_launch_count(wpsgpu_handle_t h);
 /* ---- projections ---- */
 /* map_set (module_map_utils.F:243-567) */
 int wpsgpu_map_set(int proj_code, const wpsgpu_map_args *args, wpsgpu_proj *out);
+/* compute_nest_locations + find_known_latlon (geogrid/src/llxy_module.F:331-593): the projection of every domain of a nested
+ * configuration.  `coarse` holds the map_set arguments of domain 1 exactly as :343-438 passes them (known_lat/known_lon as
+ * lat1/lon1, known_x/known_y as knowni/knownj, dxkm as dx).  The arrays have n_domains entries
+ * (entry 0 = domain 1): parent_id (1-based), parent_grid_ratio, i_parent_start / j_parent_start (gridinfo_module.F:581
+ * parent_ll_x/y), ixdim = e_we - s_we + 1 and jydim = e_sn - s_sn + 1 (:461-462).  out[k] receives proj_stack(k + 1): nests
+ * are located through their centre point (ixdim/2, jydim/2) mapped up the parent chain, grid distances divided by the ratios.
+ * Host-only: no device work.  Lambert conformal, polar stereographic (both), Mercator and Albers; the reference's own
+ * PROJ_LATLON branch omits map_set's mandatory knowni/knownj and stops in MAP_INIT, Cassini / rotated lat-lon are not built. */
+int wpsgpu_compute_nest_locations(int iproj, const wpsgpu_map_args *coarse, int n_domains, const int32_t *parent_id,
+                                  const int32_t *parent_grid_ratio, const int32_t *i_parent_start,
+                                  const int32_t *j_parent_start, const int32_t *ixdim, const int32_t *jydim,
+                                  wpsgpu_proj *out);
 /* push_source_projection (llxy_module.F:39-165); cassini[6] = {pole_lat,pole_lon,centerlat,centerlon,
  * centeri,centerj} or NULL; earth_radius NULL = absent */
 int wpsgpu_push_source_projection(int iproj, float stand_lon, float truelat1, float truelat2, float dxkm,

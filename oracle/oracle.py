@@ -101,6 +101,24 @@ def map_set(code, **kw):
     return p
 
 
+def compute_nest_locations(iproj, nests, **coarse_kw):
+    """compute_nest_locations (llxy_module.F:331-593); same arguments as wps_b200.capi.compute_nest_locations."""
+    a = MapArgs()
+    present = 0
+    for k, v in coarse_kw.items():
+        key = "lambda_" if k == "lambda" else k
+        present |= 1 << _A[key]
+        setattr(a, key, v)
+    a.present = present
+    n = len(nests)
+    arr = lambda col: (C.c_int * n)(*[int(t[col]) for t in nests])
+    out = (Proj * n)()
+    rc = lib().orc_compute_nest_locations(int(iproj), C.byref(a), n, arr(0), arr(1), arr(2), arr(3), arr(4), arr(5), out)
+    if rc != 0:
+        raise ValueError("compute_nest_locations error %d" % rc)
+    return [out[k] for k in range(n)]
+
+
 def push_source_projection(iproj, stand_lon=0., truelat1=0., truelat2=0., dxkm=0., dykm=0., dlat=0., dlon=0.,
                            known_x=1., known_y=1., known_lat=0., known_lon=0., pole_lat=None, pole_lon=None,
                            centerlat=None, centerlon=None, centeri=None, centerj=None, earth_radius=None):

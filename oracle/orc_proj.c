@@ -762,3 +762,47 @@ int orc_push_source_projection(orc_proj *p, int iproj, float stand_lon, float tr
     }
     return orc_map_set(iproj, p, &a);
 }
+
+
+/* find_known_latlon (llxy_module.F:550-593), recursive exactly like the reference: returns the coarse-domain lat/lon of
+ * point (rx, ry) of domain n (1-based) and the grid distances divided by the ratios on the way back up. */
+static void find_known_latlon(const orc_proj *coarse, const orc_map_args *ca, int n, float rx, float ry, const int *parent_id,
+                              const int *ratio, const int *ips, const int *jps, float *rlat, float *rlon, float *dx, float *dy,
+                              float *dlat, float *dlon)
+{
+    if (n == 1) {
+        *dx = (ca->present & (1u << 6)) ? ca->dx : 0.0f;
+        *dy = (ca->present & (1u << 7)) ? ca->dy : 0.0f;
+        *dlat = (ca->present & (1u << 8)) ? ca->latinc : 0.0f;
+        *dlon = (ca->present & (1u << 9)) ? ca->loninc : 0.0f;
+        orc_ij_to_latlon(coarse, rx, ry, rlat, rlon);
+        return;
+    }
+    float r = (float)ratio[n - 1];
+    float xp = (rx - ((r + 1.0f) / 2.0f)) / r + (float)ips[n - 1];
+    float yp = (ry - ((r + 1.0f) / 2.0f)) / r + (float)jps[n - 1];
+    find_known_latlon(coarse, ca, parent_id[n - 1], xp, yp, parent_id, ratio, ips, jps, rlat, rlon, dx, dy, dlat, dlon);
+    *dx = *dx / r; *dy = *dy / r; *dlat = *dlat / r; *dlon = *dlon / r;
+}
+
+/* compute_nest_locations (llxy_module.F:331-531) for the projections with a dx (LC, PS, PS_WGS84, MERC, ALBERS) */
+int orc_compute_nest_locations(int iproj, const orc_map_args *coarse, int n_domains, const int *parent_id, const int *ratio,
+                               const int *ips, const int *jps, const int *ixdim, const int *jydim, orc_proj *out)
+{
+    orc_map_init(&out[0]);
+    int rc = orc_map_set(iproj, &out[0], coarse);
+    if (rc) return rc;
+    for (int i = 2; i <= n_domains; ++i) {
+        float kx = (float)ixdim[i - 1] / 2.0f, ky = (float)jydim[i - 1] / 2.0f, klat, klon, dx, dy, dlat, dlon;
+        find_known_latlon(&out[0], coarse, i, kx, ky, parent_id, ratio, ips, jps, &klat, &klon, &dx, &dy, &dlat, &dlon);
+        orc_map_args a = *coarse;
+        a.present |= (1u << 0) | (1u << 1);
+        a.lat1 = klat; a.lon1 = klon;
+        a.present |= (1u << 4) | (1u << 5) | (1u << 6); a.knowni = kx; a.knownj = ky; a.dx = dx;
+        (void)dy; (void)dlat; (void)dlon;
+        orc_map_init(&out[i - 1]);
+        rc = orc_map_set(iproj, &out[i - 1], &a);
+        if (rc) return rc;
+    }
+    return 0;
+}

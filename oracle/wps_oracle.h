@@ -92,6 +92,9 @@ void orc_xytoll_array(orc_proj *p, long n, const float *x, const float *y, float
 void orc_rotate_coords(float ilat, float ilon, float *olat, float *olon, float lat_np, float lon_np,
                        float lon_0, int direction);
 void orc_lc_cone(float truelat1, float truelat2, float *cone);
+/* compute_nest_locations + find_known_latlon (llxy_module.F:331-593); arrays of n_domains entries, entry 0 = domain 1 */
+int orc_compute_nest_locations(int iproj, const orc_map_args *coarse, int n_domains, const int *parent_id, const int *ratio,
+                               const int *ips, const int *jps, const int *ixdim, const int *jydim, orc_proj *out);
 /* push_source_projection (llxy_module.F:39-165) */
 int orc_push_source_projection(orc_proj *p, int iproj, float stand_lon, float truelat1, float truelat2,
                                float dxkm, float dykm, float dlat, float dlon, float known_x, float known_y,

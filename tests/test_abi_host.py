@@ -110,6 +110,37 @@ def test_map_set_matches_oracle_bit_for_bit(orc, name, kw):
         assert np.array_equal(np.array(po.gauss_lat[:94], np.float32), np.array(pg.gauss_lat[:94], np.float32))
 
 
+NEST_FIELDS = ("lat1", "lon1", "dx", "stdlon", "truelat1", "truelat2", "hemi", "cone", "polei", "polej", "rsw", "rebydx", "knowni", "knownj",
+               "re_m", "latinc", "loninc")
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("PROJ_LC", dict(truelat1=30., truelat2=60., stdlon=-98., lat1=38.0, lon1=-98.0, knowni=75.0, knownj=65.0, dx=27000.)),
+    ("PROJ_PS", dict(truelat1=60., stdlon=-100., lat1=62.0, lon1=-100.0, knowni=75.0, knownj=65.0, dx=27000.)),
+    ("PROJ_MERC", dict(truelat1=10., lat1=5.0, lon1=120.0, knowni=75.0, knownj=65.0, dx=27000.)),
+])
+def test_compute_nest_locations_matches_oracle(orc, name, kw):
+    """compute_nest_locations / find_known_latlon (llxy_module.F:331-593) for a 27/9/3-km three-domain nest plus a second
+    nest on level 2: host arithmetic of the product vs the oracle's recursive restatement, bit for bit (transc mode 1)."""
+    from wps_b200 import capi
+    orc.set_transc_mode(1)
+    nests = [(1, 1, 1, 1, 150, 130), (1, 3, 40, 35, 160, 151), (2, 3, 50, 45, 172, 163), (1, 5, 90, 20, 101, 96)]
+    po = orc.compute_nest_locations(getattr(orc, name), nests, **kw)
+    pg = capi.compute_nest_locations(getattr(capi, name), nests, **kw)
+    for k, (a, b) in enumerate(zip(po, pg)):
+        for f in NEST_FIELDS:
+            x, y = np.float32(getattr(a, f)), np.float32(getattr(b, f))
+            assert x.tobytes() == y.tobytes(), (name, "domain %d" % (k + 1), f, x, y)
+    if True:
+        # known answers: grid distances divide by the ratios, the known point is the nest's centre (ixdim/2, jydim/2)
+        assert np.float32(pg[1].dx) == np.float32(27000.0 / 3) and np.float32(pg[3].dx) == np.float32(27000.0 / 5)
+        assert np.float32(pg[2].dx) == np.float32(np.float32(27000.0) / np.float32(3) / np.float32(3))
+        assert (pg[2].knowni, pg[2].knownj) == (86.0, 81.5)
+        # the centre of nest 2 seen from the coarse domain: (80 - 2) / 3 + 40, (75.5 - 2) / 3 + 35
+        lat, lon = orc.xytoll(po[0], np.array([(80.0 - 2.0) / 3.0 + 40.0], np.float32), np.array([(75.5 - 2.0) / 3.0 + 35.0], np.float32))
+        assert np.float32(pg[1].lat1) == np.float32(lat[0]) and np.float32(pg[1].lon1) == np.float32(lon[0])
+
+
 def test_map_set_rejects_what_the_reference_rejects(orc):
     from wps_b200 import capi
     with pytest.raises(capi.WpsGpuError):

@@ -703,3 +703,49 @@ def test_same_slab_for_two_grids_partial_transfers(orc, handle, monkeypatch):
         assert np.isfinite(outs[gid][0]).all()
         assert (outs[gid][1] == np_ref).all()
         assert_bitexact(outs[gid][0], r_ref, "grid %d" % gid)
+
+
+def test_mask_aliasing_a_partially_staged_slab(orc, handle, monkeypatch):
+    """Host-pointer mode, regional source: LANDSEA is queued first with nearest_neighbor (no `search`, so only the
+    rectangle its chain can touch crosses PCIe), then a masked soil field whose interp_mask is THE SAME host array
+    (the Python mirror aliases them, wps_b200/metgrid.py) and whose chain ends in `search`, which may read the mask
+    anywhere.  The mask must be staged in full; with WPSGPU_POISON a read of the untransferred part shows up as NaN."""
+    from wps_b200 import capi
+    monkeypatch.setenv("WPSGPU_POISON", "1")
+    xlat, xlon = make_domain(orc, handle, nx=61, ny=51, dx=30000.0)
+    ny, nx = xlat.shape
+    # regional 0.5-degree source 5N-75N, 160W-30W: the domain covers about a tenth of it
+    snx, sny = 261, 141
+    osrc, gsrc = latlon_source(snx, sny, 0.5, 0.5, 5.0, -160.0)
+    rng = np.random.default_rng(21)
+    lam = np.deg2rad(-160.0 + 0.5 * np.arange(snx))[None, :]
+    phi = np.deg2rad(5.0 + 0.5 * np.arange(sny))[:, None]
+    ls = ((np.sin(9 * lam) + np.cos(11 * phi)) > -0.3).astype(np.float32)     # islands and lakes a few cells across
+    soil = (280.0 + 10.0 * np.sin(3 * lam) * np.cos(2 * phi) + rng.uniform(-0.1, 0.1, (sny, snx))).astype(np.float32)
+    soil[ls == 0] = np.float32(-1e30)
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    lm = (rng.random((ny, nx)) < 0.7).astype(np.float32)
+    handle.metgrid_set_landmask(0, lm)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    cases = [("nearest_neighbor", ls, 1e20, -1.0, -2.0, (1e20, 1e20, 1e20), (None, None, None)),
+             ("sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search", soil, np.float32(-1e30), 285.0, 0.0, (0.0, 1e20, 1e20), (ls, None, None))]
+    for precision in (capi.PRECISION_EXACT, capi.PRECISION_TOLERANCE):
+        handle.metgrid_set_precision(precision)
+        outs = []
+        for chain, slab, msg, fill, masked, mv, masks in cases:
+            r = np.zeros((ny, nx), np.float32)
+            npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+            handle.metgrid_enqueue_slab(gsrc, capi.field_opts(chain, msg, fill, masked, mv), slab, 1, 1, 0, 0, capi.M, r, npw,
+                                        masks=masks, use_landmask=True)
+            outs.append((r, npw))
+        handle.metgrid_flush()
+        for (chain, slab, msg, fill, masked, mv, masks), (r, npw) in zip(cases, outs):
+            r_ref, np_ref = orc.interp_met_field(osrc, orc.field_opts(chain, msg, fill, masked, mv), 1, xlat, xlon, 1, 1, (1, nx, 1, ny),
+                                                 slab, 1, 1, 0, mask=masks[0], landmask=lm)
+            assert np.isfinite(r).all(), "chain %s read the poisoned part of a partially staged array" % chain
+            assert (npw == np_ref).all(), "new_pts, chain %s" % chain
+            if precision == capi.PRECISION_EXACT:
+                assert_bitexact(r, r_ref, "chain %s with the mask aliasing the LANDSEA slab" % chain)
+            else:
+                assert_sixteen_pt_tolerance(r, r_ref, 300.0, "chain %s, tolerance mode" % chain)
+    handle.metgrid_set_precision(capi.PRECISION_EXACT)

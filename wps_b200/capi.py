@@ -127,6 +127,22 @@ def map_set(code, **kw):
     return p
 
 
+def compute_nest_locations(iproj, nests, **coarse_kw):
+    """compute_nest_locations (llxy_module.F:331): nests = [(parent_id, parent_grid_ratio, i_parent_start, j_parent_start,
+    e_we, e_sn), ...] with entry 0 the coarse domain; coarse_kw = the map_set keywords of domain 1.  -> list of Proj."""
+    a = MapArgs()
+    present = 0
+    for k, v in coarse_kw.items():
+        present |= 1 << _A[k]
+        setattr(a, k, v)
+    a.present = present
+    n = len(nests)
+    arr = lambda col: (C.c_int32 * n)(*[int(t[col]) for t in nests])
+    out = (Proj * n)()
+    check(lib().wpsgpu_compute_nest_locations(int(iproj), C.byref(a), n, arr(0), arr(1), arr(2), arr(3), arr(4), arr(5), out))
+    return [out[k] for k in range(n)]
+
+
 def push_source_projection(iproj, stand_lon=0., truelat1=0., truelat2=0., dxkm=0., dykm=0., dlat=0., dlon=0.,
                            known_x=1., known_y=1., known_lat=0., known_lon=0., cassini=None, earth_radius=None):
     """push_source_projection (llxy_module.F:39)."""

@@ -426,6 +426,52 @@ int wpsgpu_map_set(int proj_code, const wpsgpu_map_args* args, wpsgpu_proj* out)
     return h_map_set(proj_code, *args, *out);
 }
 
+// compute_nest_locations + find_known_latlon, llxy_module.F:331-593.  Host arithmetic only (binary32, the reference's order).
+int wpsgpu_compute_nest_locations(int iproj, const wpsgpu_map_args* coarse, int n_domains, const int32_t* parent_id,
+                                  const int32_t* parent_grid_ratio, const int32_t* i_parent_start, const int32_t* j_parent_start,
+                                  const int32_t* ixdim, const int32_t* jydim, wpsgpu_proj* out)
+{
+    WPS_CHECK(coarse && parent_id && parent_grid_ratio && i_parent_start && j_parent_start && ixdim && jydim && out, -1,
+              "wpsgpu_compute_nest_locations: NULL argument");
+    WPS_CHECK(n_domains >= 1 && n_domains <= 21, -1, "n_domains %d out of range 1..21 (MAX_DOMAINS)", n_domains);
+    WPS_CHECK(iproj == WPSGPU_PROJ_LC || iproj == WPSGPU_PROJ_PS || iproj == WPSGPU_PROJ_PS_WGS84 || iproj == WPSGPU_PROJ_MERC ||
+              iproj == WPSGPU_PROJ_ALBERS_NAD83, -1,
+              "compute_nest_locations: projection %d is not supported for nesting here", iproj);
+    WPS_TRY(h_map_set(iproj, *coarse, out[0]));          // proj_stack(1), :343-438
+    const wps::DevProj d1 = wps::to_dev(out[0], out[0].gauss_lat);
+    for (int n = 2; n <= n_domains; ++n) {
+        WPS_CHECK(parent_id[n - 1] >= 1 && parent_id[n - 1] < n && parent_grid_ratio[n - 1] >= 1, -1,
+                  "domain %d: parent_id %d / parent_grid_ratio %d invalid", n, parent_id[n - 1], parent_grid_ratio[n - 1]);
+        // find_known_latlon (:550-593) for the nest's centre point, walked up to the coarse domain
+        float rx = (float)ixdim[n - 1] / 2.0f, ry = (float)jydim[n - 1] / 2.0f;
+        const float known_x = rx, known_y = ry;
+        float dx = (coarse->present & WPSGPU_A_DX) ? coarse->dx : 0.0f, dy = (coarse->present & WPSGPU_A_DY) ? coarse->dy : 0.0f;
+        float dlat = (coarse->present & WPSGPU_A_LATINC) ? coarse->latinc : 0.0f, dlon = (coarse->present & WPSGPU_A_LONINC) ? coarse->loninc : 0.0f;
+        // the recursion divides on the way back up, innermost ratio last: dx = ((dx / r_outer) ... / r_n)
+        int chain[32], nc = 0;
+        for (int k = n; k != 1; k = parent_id[k - 1]) {
+            const float r = (float)parent_grid_ratio[k - 1];
+            rx = (rx - ((r + 1.0f) / 2.0f)) / r + (float)i_parent_start[k - 1];
+            ry = (ry - ((r + 1.0f) / 2.0f)) / r + (float)j_parent_start[k - 1];
+            chain[nc++] = k;
+        }
+        for (int c = nc - 1; c >= 0; --c) {
+            const float r = (float)parent_grid_ratio[chain[c] - 1];
+            dx = dx / r; dy = dy / r; dlat = dlat / r; dlon = dlon / r;
+        }
+        float rlat, rlon;
+        wps::ij_to_latlon(d1, rx, ry, rlat, rlon);
+        wpsgpu_map_args a = *coarse;                     // truelat1/2, stdlon, ... as for the coarse domain (:451-532)
+        a.present |= WPSGPU_A_LAT1 | WPSGPU_A_LON1;
+        a.lat1 = rlat; a.lon1 = rlon;
+        a.present |= WPSGPU_A_KNOWNI | WPSGPU_A_KNOWNJ | WPSGPU_A_DX;
+        a.knowni = known_x; a.knownj = known_y; a.dx = dx;
+        (void)dy; (void)dlat; (void)dlon;
+        WPS_TRY(h_map_set(iproj, a, out[n - 1]));
+    }
+    return 0;
+}
+
 int wpsgpu_push_source_projection(int iproj, float stand_lon, float truelat1, float truelat2, float dxkm,
                                   float dykm, float dlat, float dlon, float known_x, float known_y,
                                   float known_lat, float known_lon, const float* cassini,

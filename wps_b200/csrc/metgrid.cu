@@ -1180,7 +1180,14 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         if (!p) { *out = nullptr; return 0; }
         if (!host) { *out = p; return 0; }
         auto it = fs.staged.find(p);
-        if (it != fs.staged.end()) { *out = (const float*)it->second; return 0; }
+        if (it != fs.staged.end()) {
+            // The same host array was staged before as a source slab.  A mask is read anywhere (search, average_gcell, the
+            // pre-passes), so a copy that only holds the rectangle one chain could touch is not good enough: stage it whole.
+            WPS_CHECK(it->second != nullptr, -1, "an interp mask aliases a raw (undecoded) record queued in the same flush");
+            if (fs.staged_sub.find(p) == fs.staged_sub.end()) { *out = (const float*)it->second; return 0; }
+            fs.staged.erase(it);
+            fs.staged_sub.erase(p);
+        }
         void* d = take_run(in_runs, p, bytes);
         WPS_CHECK(d != nullptr, -3, "device arena exhausted (%zu bytes requested)", bytes);
         fs.staged[p] = d;
@@ -1747,6 +1754,25 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
         }
     }
     for (auto& kv : uniq_in) need += kv.second + 256;
+    if (host) {
+        // a host array that several groups use (a slab shared by two grids, a slab that is also a mask) can be staged again
+        // in full when the first copy only held a rectangle: budget one more copy per additional user
+        std::map<const void*, int> users;
+        for (int g = 0; g < njobs; ++g) {
+            const QueuedSlab& q0 = queue[groups[g][0]];
+            std::vector<const void*> seen;
+            for (int m = 0; m < 3; ++m) if (q0.s.mask[m]) seen.push_back(q0.s.mask[m]);
+            for (int a : groups[g]) seen.push_back(queue[a].s.slab);
+            std::sort(seen.begin(), seen.end());
+            seen.erase(std::unique(seen.begin(), seen.end()), seen.end());
+            for (const void* p : seen) users[p]++;
+        }
+        for (auto& kv : users)
+            if (kv.second > 1) {
+                auto it = uniq_in.find(kv.first);
+                if (it != uniq_in.end()) need += (size_t)(kv.second - 1) * (it->second + 256);
+            }
+    }
     for (int a = 0; a < nq; ++a)   // decoded copies of raw records (both pointer modes) + their task entries
         if (queue[a].s.raw_nx > 0)
             need += (size_t)(queue[a].s.maxx - queue[a].s.minx + 1) * (queue[a].s.maxy - queue[a].s.miny + 1) * sizeof(float) + 256 + sizeof(DecodeTask);
