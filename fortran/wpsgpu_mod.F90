@@ -1,7 +1,8 @@
 !-----------------------------------------------------------------------------------------------
 ! wpsgpu_mod -- ISO_C_BINDING interfaces to libwpsgpu.so (include/wpsgpu.h) for the WPS host code.
-! Add this file to metgrid/src and geogrid/src, link with -lwpsgpu -lcudart.  (Not compiled in this
-! repository's image: it has no Fortran compiler.  See INTEGRATION.md.)
+! Add this file to metgrid/src and geogrid/src, link with -lwpsgpu -lcudart.  Every entry point of the header has an
+! interface here (tests/test_abi_host.py checks the two lists against each other and the derived types against the C
+! struct layouts).  Not compiled in this repository's image: it has no Fortran compiler.  See INTEGRATION.md.
 !-----------------------------------------------------------------------------------------------
 module wpsgpu_mod
 
@@ -33,6 +34,43 @@ module wpsgpu_mod
       type(c_ptr) :: r_arr, valid_mask, new_pts
       integer(c_int32_t) :: raw_nx = 0, raw_big_endian = 0   ! raw-record ingest: slab = fg_data%slab as read, see wpsgpu.h
    end type wpsgpu_slab
+
+   ! OPTIONAL arguments of map_set (module_map_utils.F:243-283): bit set in `present` = argument passed
+   integer(c_int32_t), parameter :: WPSGPU_A_LAT1 = 1, WPSGPU_A_LON1 = 2, WPSGPU_A_LAT0 = 4, WPSGPU_A_LON0 = 8, &
+      WPSGPU_A_KNOWNI = 16, WPSGPU_A_KNOWNJ = 32, WPSGPU_A_DX = 64, WPSGPU_A_DY = 128, WPSGPU_A_LATINC = 256, &
+      WPSGPU_A_LONINC = 512, WPSGPU_A_STDLON = 1024, WPSGPU_A_TRUELAT1 = 2048, WPSGPU_A_TRUELAT2 = 4096, &
+      WPSGPU_A_NLAT = 8192, WPSGPU_A_NXMIN = 131072, WPSGPU_A_NXMAX = 262144, WPSGPU_A_STAGGER = 524288, &
+      WPSGPU_A_R_EARTH = 4194304
+   integer(c_int), parameter :: WPSGPU_PRECISION_EXACT = 0, WPSGPU_PRECISION_TOLERANCE = 1
+   integer(c_int), parameter :: WPSGPU_PTR_HOST = 0, WPSGPU_PTR_DEVICE = 1
+   integer(c_int), parameter :: WPSGPU_CONTINUOUS = 0, WPSGPU_CATEGORICAL = 1, WPSGPU_SP_CONTINUOUS = 2
+
+   type, bind(C) :: wpsgpu_map_args
+      integer(c_int32_t) :: present      ! uint32_t in C: same size and representation
+      real(c_float) :: lat1, lon1, lat0, lon0, knowni, knownj, dx, dy, latinc, loninc, stdlon, truelat1, truelat2, r_earth
+      integer(c_int32_t) :: nlat, nxmin, nxmax, stagger
+   end type wpsgpu_map_args
+
+   ! calc_field's arguments (process_tile_module.F:1208-1260)
+   type, bind(C) :: wpsgpu_geo_field
+      type(wpsgpu_proj) :: dom_proj                   ! proj_stack(current_nest_number)
+      integer(c_int32_t) :: istagger
+      type(c_ptr) :: xlat, xlon                       ! c_loc(xlat_array), c_loc(xlon_array)
+      integer(c_int32_t) :: start_i, end_i, start_j, end_j, start_k, end_k
+      type(c_ptr) :: landmask                         ! c_null_ptr = optional landmask absent
+      type(c_ptr) :: field                            ! c_loc(field)
+   end type wpsgpu_geo_field
+
+   ! one priority level of a field (:1271-1345)
+   type, bind(C) :: wpsgpu_geo_level
+      type(wpsgpu_proj) :: src_proj
+      integer(c_int32_t) :: ilevel, itype
+      integer(c_int32_t) :: ops(WPSGPU_MAX_OPS), opts(WPSGPU_MAX_OPS)
+      real(c_float) :: msg_val, msg_fill_val, mask_val
+      integer(c_int32_t) :: has_scale
+      real(c_float) :: scale_factor
+      integer(c_int32_t) :: sr_x, sr_y
+   end type wpsgpu_geo_level
 
    interface
       integer(c_int) function wpsgpu_create(device_id, handle) bind(C, name='wpsgpu_create')
@@ -158,9 +196,183 @@ module wpsgpu_mod
          integer(c_int), value :: opt, npass, sx, ex, sy, ey, sz, ez
          real(c_float) :: array(*)
       end function
-      ! ... the geogrid entry points (wpsgpu_geogrid_*, wpsgpu_fractions_dominant, wpsgpu_xytoll_grid, wpsgpu_map_factor,
-      !     wpsgpu_coriolis, wpsgpu_rotang, wpsgpu_dfdx, wpsgpu_dfdy, wpsgpu_lltoxy, wpsgpu_xytoll) follow the same pattern;
-      !     their C prototypes are in include/wpsgpu.h.
+      integer(c_int) function wpsgpu_set_pointer_mode(handle, mode) bind(C, name='wpsgpu_set_pointer_mode')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: mode
+      end function
+      function wpsgpu_stream(handle) bind(C, name='wpsgpu_stream')
+         import :: c_ptr
+         type(c_ptr), value :: handle
+         type(c_ptr) :: wpsgpu_stream
+      end function
+      integer(c_int64_t) function wpsgpu_launch_count(handle) bind(C, name='wpsgpu_launch_count')
+         import :: c_int64_t, c_ptr
+         type(c_ptr), value :: handle
+      end function
+      integer(c_int) function wpsgpu_map_set(proj_code, args, proj) bind(C, name='wpsgpu_map_set')
+         import :: c_int, wpsgpu_map_args, wpsgpu_proj
+         integer(c_int), value :: proj_code
+         type(wpsgpu_map_args) :: args
+         type(wpsgpu_proj) :: proj
+      end function
+      integer(c_int) function wpsgpu_compute_nest_locations(iproj, coarse, n_domains, parent_id, parent_grid_ratio, &
+                        i_parent_start, j_parent_start, ixdim, jydim, projs) bind(C, name='wpsgpu_compute_nest_locations')
+         import :: c_int, c_int32_t, wpsgpu_map_args, wpsgpu_proj
+         integer(c_int), value :: iproj, n_domains
+         type(wpsgpu_map_args) :: coarse
+         integer(c_int32_t) :: parent_id(*), parent_grid_ratio(*), i_parent_start(*), j_parent_start(*), ixdim(*), jydim(*)
+         type(wpsgpu_proj) :: projs(*)                 ! proj_stack(1:n_domains)
+      end function
+      integer(c_int) function wpsgpu_lltoxy(handle, proj, stagger, lat, lon, n, x, y) bind(C, name='wpsgpu_lltoxy')
+         import :: c_int, c_int64_t, c_ptr, c_float, wpsgpu_proj
+         type(c_ptr), value :: handle
+         type(wpsgpu_proj) :: proj
+         integer(c_int), value :: stagger
+         integer(c_int64_t), value :: n
+         real(c_float) :: lat(*), lon(*), x(*), y(*)
+      end function
+      integer(c_int) function wpsgpu_xytoll(handle, proj, stagger, x, y, n, lat, lon) bind(C, name='wpsgpu_xytoll')
+         import :: c_int, c_int64_t, c_ptr, c_float, wpsgpu_proj
+         type(c_ptr), value :: handle
+         type(wpsgpu_proj) :: proj
+         integer(c_int), value :: stagger
+         integer(c_int64_t), value :: n
+         real(c_float) :: x(*), y(*), lat(*), lon(*)
+      end function
+      integer(c_int) function wpsgpu_metgrid_set_precision(handle, mode) bind(C, name='wpsgpu_metgrid_set_precision')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: mode
+      end function
+      integer(c_int) function wpsgpu_metgrid_copy_bytes(handle, h2d, d2h) bind(C, name='wpsgpu_metgrid_copy_bytes')
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int64_t) :: h2d, d2h
+      end function
+      integer(c_int) function wpsgpu_metgrid_last_kernel(handle, ms, points) bind(C, name='wpsgpu_metgrid_last_kernel')
+         import :: c_int, c_ptr, c_float, c_double
+         type(c_ptr), value :: handle
+         real(c_float) :: ms
+         real(c_double) :: points
+      end function
+      integer(c_int) function wpsgpu_metgrid_last_timings(handle, ms7, points7) bind(C, name='wpsgpu_metgrid_last_timings')
+         import :: c_int, c_ptr, c_float, c_double
+         type(c_ptr), value :: handle
+         real(c_float) :: ms7(7)
+         real(c_double) :: points7(7)
+      end function
+      integer(c_int) function wpsgpu_debug_disable_fast(handle, disable) bind(C, name='wpsgpu_debug_disable_fast')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: disable
+      end function
+      integer(c_int) function wpsgpu_metgrid_gcell_slab(handle, proj, dom_proj, fo, slab) bind(C, name='wpsgpu_metgrid_gcell_slab')
+         import :: c_int, c_ptr, wpsgpu_proj, wpsgpu_field_opts, wpsgpu_slab
+         type(c_ptr), value :: handle
+         type(wpsgpu_proj) :: proj, dom_proj
+         type(wpsgpu_field_opts) :: fo
+         type(wpsgpu_slab) :: slab
+      end function
+      ! ---- geogrid: calc_field (process_tile_module.F:1208-1681) ----
+      integer(c_int) function wpsgpu_geogrid_field_begin(handle, f) bind(C, name='wpsgpu_geogrid_field_begin')
+         import :: c_int, c_ptr, wpsgpu_geo_field
+         type(c_ptr), value :: handle
+         type(wpsgpu_geo_field) :: f
+      end function
+      integer(c_int) function wpsgpu_geogrid_level_begin(handle, l) bind(C, name='wpsgpu_geogrid_level_begin')
+         import :: c_int, c_ptr, wpsgpu_geo_level
+         type(c_ptr), value :: handle
+         type(wpsgpu_geo_level) :: l
+      end function
+      integer(c_int) function wpsgpu_geogrid_add_tile(handle, tile, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, &
+                        src_max_z, bdr) bind(C, name='wpsgpu_geogrid_add_tile')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle
+         real(c_float) :: tile(*)                      ! where_maps_to_tile%... as get_data_tile returns it
+         integer(c_int), value :: src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr
+      end function
+      integer(c_int) function wpsgpu_geogrid_add_tile_raw(handle, bytes, wordsize, is_signed, endian, row_order, src_min_x, &
+                        src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr) bind(C, name='wpsgpu_geogrid_add_tile_raw')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle, bytes            ! c_loc of the buffer the tile file was read into
+         integer(c_int), value :: wordsize, is_signed, endian, row_order
+         integer(c_int), value :: src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr
+      end function
+      integer(c_int) function wpsgpu_geogrid_decode_tile(handle, bytes, wordsize, is_signed, endian, row_order, nx, ny, nz, &
+                        scalefactor, rarray) bind(C, name='wpsgpu_geogrid_decode_tile')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle, bytes
+         integer(c_int), value :: wordsize, is_signed, endian, row_order, nx, ny, nz
+         real(c_float), value :: scalefactor
+         real(c_float) :: rarray(*)
+      end function
+      integer(c_int) function wpsgpu_geogrid_level_end(handle) bind(C, name='wpsgpu_geogrid_level_end')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+      end function
+      integer(c_int) function wpsgpu_geogrid_field_finish(handle, processed_domain, n_invalid_category) &
+                        bind(C, name='wpsgpu_geogrid_field_finish')
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: handle, processed_domain  ! c_loc(processed_domain%iarray) or c_null_ptr
+         integer(c_int64_t) :: n_invalid_category
+      end function
+      integer(c_int) function wpsgpu_fractions_dominant(handle, field, npts, min_cat, max_cat, msg_fill_val, lm_vals, n_lm, &
+                        is_water_mask, landmask_out, dominant_out) bind(C, name='wpsgpu_fractions_dominant')
+         import :: c_int, c_int32_t, c_int64_t, c_ptr, c_float
+         type(c_ptr), value :: handle, landmask_out, dominant_out   ! c_null_ptr = not wanted
+         real(c_float) :: field(*)
+         integer(c_int64_t), value :: npts
+         integer(c_int), value :: min_cat, max_cat, n_lm, is_water_mask
+         real(c_float), value :: msg_fill_val
+         integer(c_int32_t) :: lm_vals(*)
+      end function
+      integer(c_int) function wpsgpu_xytoll_grid(handle, dom, stagger, si, sj, ei, ej, sub_x, sub_y, xlat, xlon) &
+                        bind(C, name='wpsgpu_xytoll_grid')
+         import :: c_int, c_ptr, c_float, wpsgpu_proj
+         type(c_ptr), value :: handle
+         type(wpsgpu_proj) :: dom
+         integer(c_int), value :: stagger, si, sj, ei, ej
+         real(c_float), value :: sub_x, sub_y
+         real(c_float) :: xlat(*), xlon(*)
+      end function
+      integer(c_int) function wpsgpu_map_factor(handle, iproj, truelat1, truelat2, pole_lat, pole_lon, stand_lon, xlat, xlon, &
+                        npts, mapfac_x, mapfac_y) bind(C, name='wpsgpu_map_factor')
+         import :: c_int, c_int64_t, c_ptr, c_float
+         type(c_ptr), value :: handle
+         integer(c_int), value :: iproj
+         real(c_float), value :: truelat1, truelat2, pole_lat, pole_lon, stand_lon
+         integer(c_int64_t), value :: npts
+         real(c_float) :: xlat(*), xlon(*), mapfac_x(*), mapfac_y(*)
+      end function
+      integer(c_int) function wpsgpu_coriolis(handle, xlat, npts, f, e) bind(C, name='wpsgpu_coriolis')
+         import :: c_int, c_int64_t, c_ptr, c_float
+         type(c_ptr), value :: handle
+         integer(c_int64_t), value :: npts
+         real(c_float) :: xlat(*), f(*), e(*)
+      end function
+      integer(c_int) function wpsgpu_rotang(handle, iproj, truelat1, truelat2, stand_lon, xlat, xlon, si, sj, ei, ej, cosa, sina) &
+                        bind(C, name='wpsgpu_rotang')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle
+         integer(c_int), value :: iproj, si, sj, ei, ej
+         real(c_float), value :: truelat1, truelat2, stand_lon
+         real(c_float) :: xlat(*), xlon(*), cosa(*), sina(*)
+      end function
+      integer(c_int) function wpsgpu_dfdx(handle, src, dst, si, sj, sk, ei, ej, ek, sr_x, mapfac, dom_dx) bind(C, name='wpsgpu_dfdx')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle, mapfac            ! c_null_ptr = no map factor
+         integer(c_int), value :: si, sj, sk, ei, ej, ek, sr_x
+         real(c_float), value :: dom_dx
+         real(c_float) :: src(*), dst(*)
+      end function
+      integer(c_int) function wpsgpu_dfdy(handle, src, dst, si, sj, sk, ei, ej, ek, sr_y, mapfac, dom_dy) bind(C, name='wpsgpu_dfdy')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle, mapfac
+         integer(c_int), value :: si, sj, sk, ei, ej, ek, sr_y
+         real(c_float), value :: dom_dy
+         real(c_float) :: src(*), dst(*)
+      end function
    end interface
 
 contains

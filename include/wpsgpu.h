@@ -270,6 +270,12 @@ int wpsgpu_geogrid_add_tile(wpsgpu_handle_t h, const float *tile, int src_min_x,
 int wpsgpu_geogrid_add_tile_raw(wpsgpu_handle_t h, const void *bytes, int wordsize, int is_signed, int endian,
                                 int row_order, int src_min_x, int src_max_x, int src_min_y, int src_max_y,
                                 int src_min_z, int src_max_z, int bdr);
+/* read_geogrid (geogrid/src/read_geogrid.c:26-140) without the file access, plus the TOP_BOTTOM row flip of
+ * source_data_module.F:2887-2898: nx*ny*nz words of `wordsize` bytes -> rarray(nx,ny,nz) binary32, multiplied by
+ * scalefactor when it is not 1.  Reproduces the reference's sign rule as written (`ival > 2^(8w-1)`, so the most negative
+ * value of a signed word stays positive).  bytes / rarray follow the handle's pointer mode. */
+int wpsgpu_geogrid_decode_tile(wpsgpu_handle_t h, const void *bytes, int wordsize, int is_signed, int endian,
+                               int row_order, int nx, int ny, int nz, float scalefactor, float *rarray);
 /* post-processing of the level (:1580-1659) */
 int wpsgpu_geogrid_level_end(wpsgpu_handle_t h);
 /* copies field (and optionally the processed_domain words) back to the caller */

@@ -149,3 +149,61 @@ def test_map_set_rejects_what_the_reference_rejects(orc):
         capi.map_set(capi.PROJ_LC, truelat1=30., truelat2=60., stdlon=-98., lat1=94.83, lon1=-81.03, knowni=50.5, knownj=50.5, dx=3000.)
     with pytest.raises(capi.WpsGpuError):
         capi.map_set(capi.PROJ_ROTLL, lat1=1.0, lon1=1.0)
+
+
+def _header_entry_points():
+    import re
+    txt = open(os.path.join(ROOT, "include", "wpsgpu.h")).read()
+    return sorted(set(re.findall(r"^(?:int|int64_t|void \*|const char \*)\s*(wpsgpu_\w+)\s*\(", txt, re.M)))
+
+
+def test_fortran_module_binds_every_entry_point():
+    """fortran/wpsgpu_mod.F90 has a bind(C) interface for every function include/wpsgpu.h declares, and nothing else."""
+    import re
+    f90 = open(os.path.join(ROOT, "fortran", "wpsgpu_mod.F90")).read()
+    bound = sorted(set(re.findall(r"bind\(C,\s*name='(wpsgpu_\w+)'\)", f90)))
+    assert bound == _header_entry_points(), (sorted(set(_header_entry_points()) - set(bound)), sorted(set(bound) - set(_header_entry_points())))
+
+
+def _f90_type_members(name):
+    """member names of a bind(C) derived type of fortran/wpsgpu_mod.F90, in declaration order"""
+    import re
+    f90 = open(os.path.join(ROOT, "fortran", "wpsgpu_mod.F90")).read()
+    body = re.search(r"type, bind\(C\) :: %s\n(.*?)end type %s" % (name, name), f90, re.S).group(1)
+    body = re.sub(r"&\s*\n", " ", body)
+    out = []
+    for line in body.split("\n"):
+        line = line.split("!")[0]
+        if "::" not in line:
+            continue
+        for item in line.split("::")[1].split(","):
+            item = item.strip()
+            if item and not item[0].isdigit() and not item.endswith(")") or "(" in item:
+                out.append(re.sub(r"\(.*|\s*=.*", "", item).strip())
+    return [m for m in out if m]
+
+
+def test_struct_layouts_agree_between_c_ctypes_and_fortran(tmp_path):
+    """A C program that includes include/wpsgpu.h and is LINKED with -lwpsgpu prints sizeof / offsetof of every struct; the
+    ctypes mirrors of wps_b200/capi.py must have exactly those layouts, and the bind(C) derived types of the Fortran module
+    must list the same members in the same order (bind(C) then guarantees the same layout)."""
+    import json
+    import subprocess
+    from wps_b200 import capi
+    exe = str(tmp_path / "abi_layout")
+    libdir = os.path.join(ROOT, "wps_b200")
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_layout.c"),
+                           "-o", exe, "-L", libdir, "-lwpsgpu", "-L", cuda_lib, "-lcudart", "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib])
+    lay = json.loads(subprocess.check_output([exe]).decode())
+    assert lay["map_set_ok"] == 0 and lay["map_set_without_dx"] != 0 and lay["error_text_length"] > 0
+    assert abs(lay["cone"] - 0.715567) < 1e-5                   # cone factor of a 30 / 60 Lambert projection
+    pairs = {"wpsgpu_proj": capi.Proj, "wpsgpu_map_args": capi.MapArgs, "wpsgpu_field_opts": capi.FieldOpts, "wpsgpu_slab": capi.Slab,
+             "wpsgpu_geo_field": capi.GeoField, "wpsgpu_geo_level": capi.GeoLevel}
+    for cname, ct in pairs.items():
+        assert C.sizeof(ct) == lay["sizeof(%s)" % cname], cname
+        cfields = [k.split(".")[1] for k in lay if k.startswith(cname + ".")]
+        assert cfields == [f[0] for f in ct._fields_], cname
+        for fname in cfields:
+            assert getattr(ct, fname).offset == lay["%s.%s" % (cname, fname)], (cname, fname)
+        assert _f90_type_members(cname) == cfields, (cname, _f90_type_members(cname), cfields)

@@ -403,6 +403,16 @@ class Handle:
                                                 int(src_min_y), int(src_min_y + ny - 1), int(src_min_z),
                                                 int(src_min_z + nz - 1), int(bdr)))
 
+    def geogrid_decode_tile(self, raw, shape, wordsize, is_signed, endian, row_order=1, scalefactor=1.0, out=None):
+        """read_geogrid.c on the device: raw bytes -> float32 [nz][ny][nx]."""
+        nz, ny, nx = shape
+        if out is None:
+            out = np.empty((nz, ny, nx), np.float32)
+        check(lib().wpsgpu_geogrid_decode_tile(self._h, C.c_void_p(ptr(raw)), int(wordsize), int(is_signed), int(endian),
+                                               int(row_order), int(nx), int(ny), int(nz), C.c_float(scalefactor),
+                                               C.c_void_p(ptr(out))))
+        return out
+
     def geogrid_level_end(self):
         check(lib().wpsgpu_geogrid_level_end(self._h))
 

@@ -490,6 +490,12 @@ __global__ void k_geo_decode(const unsigned char* __restrict__ c, int wordsize, 
     out[(k * tny + jo) * tnx + i] = (float)ival;
 }
 
+__global__ void k_geo_scale(float* __restrict__ a, size_t n, float f)
+{
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) a[e] = a[e] * f;
+}
+
 static int geo_grow(void** p, size_t* cap, size_t bytes, cudaStream_t st)
 {
     if (bytes <= *cap) return 0;
@@ -783,6 +789,34 @@ int wpsgpu_geogrid_add_tile_raw(wpsgpu_handle_t h, const void* bytes, int wordsi
     h->launches++;
     WPS_CUDA(cudaGetLastError());
     WPS_TRY(geo_process_tile(h, set, pre, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr));
+    return 0;
+}
+
+int wpsgpu_geogrid_decode_tile(wpsgpu_handle_t h, const void* bytes, int wordsize, int is_signed, int endian, int row_order,
+                               int nx, int ny, int nz, float scalefactor, float* rarray)
+{
+    WPS_CHECK(h && bytes && rarray, -1, "wpsgpu_geogrid_decode_tile: NULL argument");
+    WPS_CHECK(wordsize >= 1 && wordsize <= 4, -1, "wordsize must be 1..4");
+    WPS_CHECK(nx > 0 && ny > 0 && nz > 0, -1, "empty tile");
+    WPS_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)nx * ny * nz;
+    WPS_TRY(arena_begin(h));
+    h->arena.reset();
+    WPS_TRY(h->arena.reserve(n * (wordsize + sizeof(float)) + 1024, h->stream));
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    WPS_TRY(stage_in(h, bytes, n * wordsize, &d_in));
+    WPS_TRY(alloc_out(h, rarray, n * sizeof(float), &d_out));
+    k_geo_decode<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((const unsigned char*)d_in, wordsize, is_signed, endian == 1, row_order == 2,
+                                                                    nx, ny, nz, (float*)d_out);
+    h->launches++;
+    if (scalefactor != 1.0f) {      // read_geogrid.c:133-137
+        k_geo_scale<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((float*)d_out, n, scalefactor);
+        h->launches++;
+    }
+    WPS_CUDA(cudaGetLastError());
+    WPS_TRY(copy_out(h, rarray, d_out, n * sizeof(float)));
+    WPS_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
