@@ -332,6 +332,246 @@ def geogrid_arm(h, torch, dev, config, steps):
                              "pixels_per_s": len(ttiles) * (tn + 2 * bdr) ** 2 / (topo_ms / 1e3), "mean_height": topo_mean}}
 
 
+
+def aux_kernels_arm(h, torch, dev, steps=5):
+    """The other hot-path subsystems north_star lists, timed alone on config-2 / config-3 sized arrays resident in HBM:
+    smooth_module (one smth-desmth_special pass and three 1-2-1 passes over HGT_M), rotate_winds (met_to_map, 35 levels of
+    U / V), fractions + dominant category + landmask (21 categories).  GB/s = algorithmic bytes / device time."""
+    from wps_b200 import capi, synth
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = synth.CONFIGS["config2"]["dom"]
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+
+    def timed(fn, prep=None):
+        ms = []
+        for it in range(steps + 1):
+            if prep:
+                prep()
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            fn()
+            ev1.record(stream)
+            h.synchronize()
+            if it > 0:
+                ms.append(ev0.elapsed_time(ev1))
+        return float(np.mean(ms))
+    out = {}
+    gx, gy = nx + 6, ny + 6
+    hgt0 = (torch.rand((1, gy, gx), device=dev, generator=g) * 3000.0 - 100.0).contiguous()
+    hgt = hgt0.clone()
+    n = gx * gy
+    t = timed(lambda: h.smooth(hgt, capi.SMTHDESMTH_SPECIAL, 1), lambda: hgt.copy_(hgt0))
+    # one pass: read + write by the fused kernel, then the scratch is copied back into the caller's array (device-pointer mode)
+    out["smth_desmth_special_1pass"] = {"ms": t, "points": n, "alg_bytes_per_point": 8.0, "GBps": 8.0 * n / (t * 1e-3) / 1e9,
+                                        "launches": "1 fused pass (tile + apron of 2 in shared memory) + 1 copy back"}
+    t = timed(lambda: h.smooth(hgt, capi.ONETWOONE, 3), lambda: hgt.copy_(hgt0))
+    out["one_two_one_3pass"] = {"ms": t, "points": n, "alg_bytes_per_point": 24.0, "GBps": 24.0 * n / (t * 1e-3) / 1e9,
+                                "launches": "3 fused passes, the last one in place"}
+    nlev = 35
+    dom = synth.lambert_domain(nx, ny, dx, tl1, tl2, slon, rlat, rlon)
+    xlat_u = torch.empty((ny, nx + 1), device=dev); xlon_u = torch.empty_like(xlat_u)
+    xlat_v = torch.empty((ny + 1, nx), device=dev); xlon_v = torch.empty_like(xlat_v)
+    h.xytoll_grid(dom, capi.U, 1, 1, nx + 1, ny, out=(xlat_u, xlon_u))
+    h.xytoll_grid(dom, capi.V, 1, 1, nx, ny + 1, out=(xlat_v, xlon_v))
+    u = (torch.rand((nlev, ny, nx + 1), device=dev, generator=g) * 40.0 - 20.0).contiguous()
+    v = (torch.rand((nlev, ny + 1, nx), device=dev, generator=g) * 40.0 - 20.0).contiguous()
+    um = torch.full((nlev, ny, capi.nwords(nx + 1)), -1, dtype=torch.int32, device=dev)
+    vm = torch.full((nlev, ny + 1, capi.nwords(nx)), -1, dtype=torch.int32, device=dev)
+    t = timed(lambda: h.rotate_winds(-1, dom, u, um, v, vm, xlon_u, xlon_v))
+    npt = u.numel() + v.numel()
+    # per output: own value (4 B) + four neighbours of the other component (mostly cached: ~4 B) + store (4 B)
+    out["rotate_winds_met_to_map"] = {"ms": t, "points": npt, "levels": nlev, "alg_bytes_per_point": 12.0, "GBps": 12.0 * npt / (t * 1e-3) / 1e9}
+    ncat = 21
+    cnt0 = torch.randint(0, 9, (ncat, gy, gx), device=dev, generator=g).float().contiguous()
+    cnt = cnt0.clone()
+    lm = torch.empty((gy, gx), device=dev); dm = torch.empty((gy, gx), device=dev)
+    t = timed(lambda: h.fractions_dominant(cnt, 1, 1e20, [17], True, lm, dm), lambda: cnt.copy_(cnt0))
+    out["fractions_dominant_landmask"] = {"ms": t, "points": n, "categories": ncat, "alg_bytes_per_point": 8.0 * ncat + 8.0,
+                                          "GBps": (8.0 * ncat + 8.0) * n / (t * 1e-3) / 1e9}
+    return out
+
+
+def config5_plan(capi, synth, config, rank, world):
+    """One time of an ERA5-shaped FILE: TT, QV, UU, VV on `nlev` model levels; the slabs of the step are sharded by level
+    (shard.shard_slabs keeps UU and VV of a level on the same rank) -> this rank's list of (field, level, stagger, kind)."""
+    from wps_b200 import shard
+    fields = (("TT", capi.M, "smooth"), ("QV", capi.M, "smooth"), ("UU", capi.U, "wind"), ("VV", capi.V, "wind"))
+    keys, meta = [], []
+    for f, st, kind in fields:
+        for l in range(config["nlev"]):
+            keys.append((f, l))
+            meta.append((f, l, st, kind))
+    mine = shard.shard_slabs(keys, world)[rank]
+    return [meta[i] for i in mine], len(keys)
+
+
+def run_config5(args, rank, world, local_rank):
+    """BASELINE configs[4]: 137 model levels -> 1-km 4000 x 4000, ONE time step sharded field x level over the GPUs (strong
+    scaling: total work fixed).  Device-timed (HBM-resident) and end to end with pinned host buffers."""
+    import torch
+    import torch.distributed as dist
+    from wps_b200 import capi, synth
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "unchanged (single process)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    config = synth.CONFIGS["config5"]
+    sx, sy, dlat, dlon = config["src"]
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = config["dom"]
+    mine, total_slabs = config5_plan(capi, synth, config, rank, world)
+    h = capi.Handle(local_rank, capi.PTR_DEVICE)
+    h.metgrid_set_precision(PRECISION)
+    dom = synth.lambert_domain(nx, ny, dx, tl1, tl2, slon, rlat, rlon)
+    src = capi.push_source_projection(capi.PROJ_LATLON, dlat=dlat, dlon=dlon, known_x=1.0, known_y=1.0, known_lat=90.0, known_lon=0.0,
+                                      earth_radius=6371229.0)
+    grids, gid_of = {}, {capi.M: 0, capi.U: 1, capi.V: 2}
+    for st, (gx, gy) in {capi.M: (nx, ny), capi.U: (nx + 1, ny), capi.V: (nx, ny + 1)}.items():
+        xlat = torch.empty((gy, gx), dtype=torch.float32, device=dev)
+        xlon = torch.empty_like(xlat)
+        h.xytoll_grid(dom, st, 1, 1, gx, gy, out=(xlat, xlon))
+        h.metgrid_set_grid(gid_of[st], xlat, xlon, 1, 1)
+        grids[st] = (gx, gy)
+    h.metgrid_set_domain(1, nx, 1, ny)
+    fo = capi.field_opts(synth.C3D, np.float32(1e20), np.float32(0.0), capi.NOT_MASKED, (1e20, 1e20, 1e20))
+    # this rank's slabs, grouped by field so that the levels of a field are enqueued together
+    by_field = {}
+    for f, l, st, kind in mine:
+        by_field.setdefault((f, st, kind), []).append(l)
+    plan, pts = [], 0
+    for (f, st, kind), levels in by_field.items():
+        gx, gy = grids[st]
+        slabs = torch.from_numpy(np.stack([synth.add_halo(synth.slab_np(sx, sy, 7000 + 1000 * gid_of[st] + 37 * len(f) + l, kind)) for l in levels])).to(dev)
+        r = torch.empty((len(levels), gy, gx), dtype=torch.float32, device=dev)
+        npw = torch.zeros((len(levels), gy, capi.nwords(gx)), dtype=torch.int32, device=dev)
+        arr = (capi.Slab * len(levels))()
+        for k in range(len(levels)):
+            capi.Handle.slab_desc(slabs[k], -2, 1, 3, gid_of[st], st, r[k], npw[k], out=arr[k])
+        plan.append(dict(field=f, st=st, slabs=slabs, r=r, npw=npw, arr=arr, n=len(levels)))
+        pts += len(levels) * gx * gy
+
+    def step(hd, pl):
+        for p in pl:
+            hd.metgrid_enqueue_slabs(src, fo, p["arr"], p["n"])
+        hd.metgrid_flush()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    for _ in range(max(args.warmup, 3)):
+        step(h, plan)
+    h.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = h.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step(h, plan)
+    ev1.record(stream)
+    h.synchronize()
+    barrier()
+    launches = h.launch_count - l0
+    kms = []
+    for _ in range(min(args.steps, 3)):
+        step(h, plan)
+        ms, kp = h.metgrid_last_kernel()
+        kms.append(ms)
+        t3, p3 = h.metgrid_last_timings()
+    sampler.stop_flag = True
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    tp = torch.tensor([float(pts)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+    ms_per_step = float(t.item()) / args.steps
+    total_pts = float(tp.item())
+    value = total_pts / (ms_per_step / 1e3)
+    # ---- e2e: pinned host buffers through the C ABI; host memory for at most E2E_CHUNK slabs is re-used chunk after chunk
+    # (every slab of the rank is still interpolated and copied back in every step)
+    e2e_value, e2e_ms, h2d, d2h = None, None, 0, 0
+    if not args.no_e2e:
+        chunk = env_int("WPSGPU_E2E_CHUNK", 48)
+        hh = capi.Handle(local_rank, capi.PTR_HOST)
+        hh.metgrid_set_precision(PRECISION)
+        for st, (gx, gy) in grids.items():
+            xlat = np.empty((gy, gx), np.float32); xlon = np.empty_like(xlat)
+            hh.xytoll_grid(dom, st, 1, 1, gx, gy, out=(xlat, xlon))
+            hh.metgrid_set_grid(gid_of[st], xlat, xlon, 1, 1)
+        hh.metgrid_set_domain(1, nx, 1, ny)
+        hplan = []
+        for p in plan:
+            gx, gy = grids[p["st"]]
+            nbuf = min(chunk, p["n"])
+            hs = p["slabs"].cpu().pin_memory()
+            hr = torch.empty((nbuf, gy, gx), dtype=torch.float32).pin_memory()
+            hn = torch.zeros((nbuf, gy, capi.nwords(gx)), dtype=torch.int32).pin_memory()
+            chunks = []
+            for c0 in range(0, p["n"], nbuf):
+                m = min(nbuf, p["n"] - c0)
+                arr = (capi.Slab * m)()
+                for k in range(m):
+                    capi.Handle.slab_desc(hs[c0 + k], -2, 1, 3, gid_of[p["st"]], p["st"], hr[k], hn[k], out=arr[k])
+                chunks.append((arr, m))
+            hplan.append((chunks, hs, hr, hn))
+
+        def host_step():
+            for chunks, _, _, _ in hplan:
+                for arr, m in chunks:
+                    hh.metgrid_enqueue_slabs(src, fo, arr, m)
+                    hh.metgrid_flush()
+        host_step()
+        barrier()
+        b0 = hh.metgrid_copy_bytes()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        b1 = hh.metgrid_copy_bytes()
+        h2d, d2h = (b1[0] - b0[0]) // e2e_steps, (b1[1] - b0[1]) // e2e_steps
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_ms = float(te.item()) * 1e3
+        e2e_value = total_pts / float(te.item())
+        hh.close()
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        kms_avg = float(np.mean(kms))
+        achieved = ALG_BYTES_PER_POINT * kp / (kms_avg * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "config5: ERA5-shaped 0.25deg 1440x721 x 137 model levels x (TT, QV, UU, VV) -> 1-km Lambert 4000x4000; 1 step = 1 time (%d slabs, %.3g points)" % (total_slabs, total_pts),
+                           "sharding": "the step's slabs by level over the GPUs (wps_b200/shard.py: UU and VV of a level on the same rank), no collective",
+                           "slabs_this_rank": len(mine), "points_per_step_total": total_pts,
+                           "l2": "outputs (%.1f GB on rank 0) exceed the 126 MB L2" % (pts * 4 / 1e9),
+                           "precision": "tolerance (sixteen_pt <= 1e-5, north_star)" if PRECISION == 1 else "exact (bit-identical sixteen_pt)"},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": K16, "kernel_ms": kms_avg, "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
+                             "breakdown_ms": {"k_pack_win": t3[0], K16: t3[1], "k_metgrid_slowlist": t3[4], "flush_first_to_last_kernel": t3[6]},
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)", "rank": 0},
+                "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                        "note": "per rank; host buffers of at most WPSGPU_E2E_CHUNK slabs per field are re-used chunk after chunk"},
+                "gpu_launches": int(launches), "cpu_affinity": affinity, "clocks": sampler.result()}
+        print(json.dumps(line))
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def bind_to_gpu_numa_node(local_rank):
     """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs next to that GPU, so that the
     host<->device copies of the e2e leg do not cross the socket interconnect.  Returns a short description."""
@@ -438,7 +678,7 @@ def run_b200(args, rank, world, local_rank):
                     h2d += m.numel() * 4
                     seen.add("mask")
             d2h += hr.numel() * 4 + hn.numel() * 4
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, args.steps)
         hdescs = slab_descs(capi, w, host)
         enqueue_all(hh, w, hdescs)  # warm-up (arena allocation, coordinate cache)
         barrier()
@@ -467,10 +707,11 @@ def run_b200(args, rank, world, local_rank):
         e2e_raw_s = (time.perf_counter() - t0) / e2e_steps
         hh.close()
 
-    geo, vfill = None, None
+    geo, vfill, aux = None, None, None
     if rank == 0 and not args.no_geogrid:
         geo = geogrid_arm(h, torch, dev, config, 3)
         vfill = vertical_fill_arm(h, torch, dev, config, 3)
+        aux = aux_kernels_arm(h, torch, dev)
     if rank == 0:
         peaks = {}
         try:
@@ -480,8 +721,10 @@ def run_b200(args, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None   # DRAM bytes of the dominant kernel's launches in one step, from the committed ncu capture
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_fast16_traffic.json")))
-            if p3[1] >= p3[2] and abs(tj["kernel_points"] - kp) < 0.01 * kp:
+            # written by tools/ncu_traffic.py from an ncu capture of this very command; only accepted for the kernel and the
+            # amount of work it was measured on
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_%s_traffic.json" % K16)))
+            if p3[1] >= p3[2] and tj["kernel"] == K16 and abs(tj["kernel_points"] - kp) < 0.01 * kp:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except Exception:
             pass
@@ -495,7 +738,7 @@ def run_b200(args, rank, world, local_rank):
                              "traffic": traffic, "traffic_unit": "bytes per step (all launches of the kernel), ncu dram read+write; algorithmic = %d" % int(ALG_BYTES_PER_POINT * kp),
                              "kernel": K16 if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
                              "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
-                             "breakdown_ms": {"k_pack16": t3[0], K16: t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowbits": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
+                             "breakdown_ms": {("k_pack_win" if PRECISION == 1 else "k_pack16"): t3[0], K16: t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowlist": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
                              "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "host_input_bytes_per_step": host_input_bytes,
@@ -504,6 +747,9 @@ def run_b200(args, rank, world, local_rank):
         if geo is not None:
             line["geogrid"] = geo
             line["vertical_fill"] = vfill
+            line["aux_kernels"] = aux
+            for k in aux.values():
+                k["frac_of_hbm_peak"] = k["GBps"] / peak
         if world == 1 and not args.no_cpu:
             pps, dt, cpts, nprocs, desc = cpu_arm(config, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": pps, "unit": "points/s", "cores": nprocs, "kind": "port", "sample": desc, "seconds": dt}
@@ -523,6 +769,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2 (default, the headline: one FILE time per GPU, weak scaling) or config5 (one 137-level time step sharded by level, strong scaling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-geogrid", action="store_true", help="skip the additional geogrid source-pixels/s measurement")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (profiling runs only)")
@@ -530,6 +778,8 @@ def main():
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.workload == "config5":
+        run_config5(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
 
