@@ -11,6 +11,7 @@ struct RotArgs {
     DevProj proj;
     const int *u_mask, *v_mask;
     float *u_new, *v_new;
+    const float2 *cs_u, *cs_v;     // (cos alpha, sin alpha) per U / V point
     int us1, us2, ue1, ue2, vs1, vs2, ve1, ve2, unx, uny, vnx, vny, unxw, vnxw;
     int idir, is_lc;
     float stdlon, cone, hemi;
@@ -47,12 +48,24 @@ __device__ __forceinline__ float rot_alpha(const RotArgs& a, const float* __rest
     return diff * WPS_RAD_PER_DEG * a.hemi;
 }
 
+// The rotation angle and its cosine / sine (binary64, rounded once) depend on the point only: evaluated once per call for
+// every U and V point (k_rot_angles) and shared by all levels instead of once per point and level.
+__global__ void k_rot_angles(RotArgs a, int is_v, float2* __restrict__ cs)
+{
+    const int nx = is_v ? a.vnx : a.unx, ny = is_v ? a.vny : a.uny;
+    int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ii >= nx || jj >= ny) return;
+    const float alpha = is_v ? rot_alpha(a, a.xlat_v, a.xlon_v, nx, ny, ii, jj) : rot_alpha(a, a.xlat_u, a.xlon_u, nx, ny, ii, jj);
+    cs[(size_t)jj * nx + ii] = make_float2(t_cos(alpha), t_sin(alpha));
+}
+
 __global__ void k_rotate_u(RotArgs a, int nlev)
 {
     int ii = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y * blockDim.y + threadIdx.y, lev = blockIdx.z;
     if (ii >= a.unx || jj >= a.uny) return;
     int i = a.us1 + ii, j = a.us2 + jj;
     size_t un = (size_t)a.unx * a.uny, vn = (size_t)a.vnx * a.vny;
+    {
     const float *u = a.u + lev * un, *v = a.v + lev * vn;
     const int *um = a.u_mask + (size_t)lev * a.uny * a.unxw, *vm = a.v_mask + (size_t)lev * a.vny * a.vnxw;
     auto ubit = [&](int x, int y) { int xi = x - a.us1, yi = y - a.us2; return (um[(size_t)yi * a.unxw + (xi >> 5)] >> (xi & 31)) & 1; };
@@ -61,7 +74,8 @@ __global__ void k_rotate_u(RotArgs a, int nlev)
     size_t o = (size_t)jj * a.unx + ii;
     float uold = u[o], res = uold;
     if (ubit(i, j)) {
-        float alpha = rot_alpha(a, a.xlat_u, a.xlon_u, a.unx, a.uny, ii, jj);
+        const float2 cs = __ldg(a.cs_u + o);
+        const float ca = cs.x, sa = cs.y;
         float v_weight, v_map;
         if (i == a.us1) {
             if (j == a.ue2 && a.do_last_row_u) { v_weight = vmul(i, j); v_map = V(i, j) * vmul(i, j); }
@@ -76,9 +90,10 @@ __global__ void k_rotate_u(RotArgs a, int nlev)
             v_weight = vmul(i - 1, j) + vmul(i - 1, j + 1) + vmul(i, j) + vmul(i, j + 1);
             v_map = V(i - 1, j) * vmul(i - 1, j) + V(i - 1, j + 1) * vmul(i - 1, j + 1) + V(i, j) * vmul(i, j) + V(i, j + 1) * vmul(i, j + 1);
         }
-        if (v_weight > 0.0f) res = t_cos(alpha) * uold + t_sin(alpha) * v_map / v_weight;
+        if (v_weight > 0.0f) res = ca * uold + sa * v_map / v_weight;
     }
     a.u_new[lev * un + o] = res;
+    }
 }
 
 __global__ void k_rotate_v(RotArgs a, int nlev)
@@ -87,6 +102,7 @@ __global__ void k_rotate_v(RotArgs a, int nlev)
     if (ii >= a.vnx || jj >= a.vny) return;
     int i = a.vs1 + ii, j = a.vs2 + jj;
     size_t un = (size_t)a.unx * a.uny, vn = (size_t)a.vnx * a.vny;
+    {
     const float *u = a.u + lev * un, *v = a.v + lev * vn;
     const int *um = a.u_mask + (size_t)lev * a.uny * a.unxw, *vm = a.v_mask + (size_t)lev * a.vny * a.vnxw;
     auto vbit = [&](int x, int y) { int xi = x - a.vs1, yi = y - a.vs2; return (vm[(size_t)yi * a.vnxw + (xi >> 5)] >> (xi & 31)) & 1; };
@@ -95,7 +111,8 @@ __global__ void k_rotate_v(RotArgs a, int nlev)
     size_t o = (size_t)jj * a.vnx + ii;
     float vold = v[o], res = vold;
     if (vbit(i, j)) {
-        float alpha = rot_alpha(a, a.xlat_v, a.xlon_v, a.vnx, a.vny, ii, jj);
+        const float2 cs = __ldg(a.cs_v + o);
+        const float ca = cs.x, sa = cs.y;
         float u_weight, u_map;
         if (j == a.vs2) {
             if (i == a.ve1 && a.do_last_col_v) { u_weight = umul(i, j); u_map = U(i, j) * umul(i, j); }
@@ -110,9 +127,10 @@ __global__ void k_rotate_v(RotArgs a, int nlev)
             u_weight = umul(i, j - 1) + umul(i, j) + umul(i + 1, j - 1) + umul(i + 1, j);
             u_map = U(i, j - 1) * umul(i, j - 1) + U(i, j) * umul(i, j) + U(i + 1, j - 1) * umul(i + 1, j - 1) + U(i + 1, j) * umul(i + 1, j);
         }
-        if (u_weight > 0.0f) res = -t_sin(alpha) * u_map / u_weight + t_cos(alpha) * vold;
+        if (u_weight > 0.0f) res = -sa * u_map / u_weight + ca * vold;
     }
     a.v_new[lev * vn + o] = res;
+    }
 }
 
 // ---- smoothers (smooth_module.F:20-239) -----------------------------------------------------------------
@@ -501,8 +519,8 @@ int wpsgpu_rotate_winds_ll(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj,
     a.unxw = (a.unx + 31) / 32; a.vnxw = (a.vnx + 31) / 32;
     size_t ub = sizeof(float) * a.unx * a.uny, vb = sizeof(float) * a.vnx * a.vny;
     size_t umb = sizeof(int) * a.uny * a.unxw, vmb = sizeof(int) * a.vny * a.vnxw;
-    WPS_TRY(begin_call(h, 2 * (ub + vb) * nlev + (umb + vmb) * nlev + 2 * (ub + vb) + 8192));
-    if (h->ptr_mode == WPSGPU_PTR_DEVICE) WPS_TRY(h->arena.reserve((ub + vb) * nlev + (1 << 20), h->stream));
+    WPS_TRY(begin_call(h, 2 * (ub + vb) * nlev + (umb + vmb) * nlev + 4 * (ub + vb) + 8192));
+    if (h->ptr_mode == WPSGPU_PTR_DEVICE) WPS_TRY(h->arena.reserve((ub + vb) * nlev + 2 * (ub + vb) + (1 << 20), h->stream));
     void *du, *dv, *dum, *dvm, *dxu, *dxv;
     WPS_TRY(stage_inout(h, u, ub * nlev, &du));
     WPS_TRY(stage_inout(h, v, vb * nlev, &dv));
@@ -515,9 +533,11 @@ int wpsgpu_rotate_winds_ll(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj,
     a.xlat_u = (const float*)dlu; a.xlat_v = (const float*)dlv;
     a.is_cassini = proj->code == WPSGPU_PROJ_CASSINI;
     a.proj = to_dev(*proj, nullptr);
+    // U is rotated into a scratch array (it reads the old V); V is then rotated IN PLACE -- it reads the old U, which is
+    // still untouched, and every V point is read only by the thread that overwrites it -- and U is copied back
     a.u_new = (float*)h->arena.take(ub * nlev);
-    a.v_new = (float*)h->arena.take(vb * nlev);
-    WPS_CHECK(a.u_new && a.v_new, -3, "device arena exhausted");
+    a.v_new = (float*)dv;
+    WPS_CHECK(a.u_new != nullptr, -3, "device arena exhausted");
     a.u = (const float*)du; a.v = (const float*)dv; a.u_mask = (const int*)dum; a.v_mask = (const int*)dvm;
     a.xlon_u = (const float*)dxu; a.xlon_v = (const float*)dxv;
     a.us1 = us1; a.us2 = us2; a.ue1 = ue1; a.ue2 = ue2; a.vs1 = vs1; a.vs2 = vs2; a.ve1 = ve1; a.ve2 = ve2;
@@ -525,14 +545,19 @@ int wpsgpu_rotate_winds_ll(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj,
     if (ue1 - us1 == ve1 - vs1) { a.do_last_col_u = 0; a.do_last_col_v = 1; } else { a.do_last_col_u = 1; a.do_last_col_v = 0; }
     if (ue2 - us2 == ve2 - vs2) { a.do_last_row_u = 1; a.do_last_row_v = 0; } else { a.do_last_row_u = 0; a.do_last_row_v = 1; }
     dim3 b(32, 8);
+    float2* cs_u = (float2*)h->arena.take(2 * ub);
+    float2* cs_v = (float2*)h->arena.take(2 * vb);
+    WPS_CHECK(cs_u && cs_v, -3, "device arena exhausted");
+    a.cs_u = cs_u; a.cs_v = cs_v;
+    k_rot_angles<<<dim3((a.unx + 31) / 32, (a.uny + 7) / 8), b, 0, h->stream>>>(a, 0, cs_u);
+    k_rot_angles<<<dim3((a.vnx + 31) / 32, (a.vny + 7) / 8), b, 0, h->stream>>>(a, 1, cs_v);
     k_rotate_u<<<dim3((a.unx + 31) / 32, (a.uny + 7) / 8, nlev), b, 0, h->stream>>>(a, nlev);
     k_rotate_v<<<dim3((a.vnx + 31) / 32, (a.vny + 7) / 8, nlev), b, 0, h->stream>>>(a, nlev);
-    h->launches += 2;
+    h->launches += 4;
     WPS_CUDA(cudaGetLastError());
     // "Copy rotated winds back into argument arrays" (:374-375)
     if (h->ptr_mode == WPSGPU_PTR_DEVICE) {
         WPS_CUDA(cudaMemcpyAsync(u, a.u_new, ub * nlev, cudaMemcpyDeviceToDevice, h->stream));
-        WPS_CUDA(cudaMemcpyAsync(v, a.v_new, vb * nlev, cudaMemcpyDeviceToDevice, h->stream));
     } else {
         WPS_CUDA(cudaMemcpyAsync(u, a.u_new, ub * nlev, cudaMemcpyDeviceToHost, h->stream));
         WPS_CUDA(cudaMemcpyAsync(v, a.v_new, vb * nlev, cudaMemcpyDeviceToHost, h->stream));
