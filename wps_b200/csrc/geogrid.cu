@@ -9,6 +9,7 @@
 namespace wps {
 
 #define GEO_OUTSIDE 100000000  // OUTSIDE_DOMAIN, misc_definitions_module.F:18
+constexpr int GEO_SETS = 10;   // staging buffer sets: one batch (GEO_NB = 8 tiles) + two tiles being staged for the next
 
 struct GeoState {
     bool field_open = false, level_open = false;
@@ -25,13 +26,18 @@ struct GeoState {
     unsigned long long* d_invalid = nullptr;
     // Two sets of tile / where_maps_to buffers: in device-pointer mode the decode and where_maps_to kernels of tile k+1
     // run on s_pre while tile k is accumulated, merged and point-filled on the handle's stream.
-    float* d_tile[2] = { nullptr, nullptr }; size_t tile_cap[2] = { 0, 0 };
-    int2* d_wm[2] = { nullptr, nullptr }; size_t wm_cap[2] = { 0, 0 };
+    // GEO_SETS sets of tile / where_maps_to buffers: the decode and where_maps_to kernels of the coming tiles run on s_pre
+    // while earlier tiles are accumulated, merged and point-filled on the handle's stream; a batch holds up to GEO_NB tiles.
+    float* d_tile[GEO_SETS] = {}; size_t tile_cap[GEO_SETS] = {};
+    int2* d_wm[GEO_SETS] = {}; size_t wm_cap[GEO_SETS] = {};
     cudaStream_t s_pre = nullptr;
-    cudaEvent_t ev_pre[2] = { nullptr, nullptr }, ev_used[2] = { nullptr, nullptr };
-    bool used_rec[2] = { false, false };
+    cudaEvent_t ev_pre[GEO_SETS] = {}, ev_used[GEO_SETS] = {};
+    bool used_rec[GEO_SETS] = {};
     int parity = 0;
-    void* d_raw[2] = { nullptr, nullptr }; size_t raw_cap[2] = { 0, 0 };   // host-pointer mode: the file bytes of a tile
+    void* d_raw[GEO_SETS] = {}; size_t raw_cap[GEO_SETS] = {};   // host-pointer mode: the file bytes of a tile
+    struct Pending { int set, smx, sMx, smy, sMy, smz, sMz, bdr; };
+    std::vector<Pending> pending;     // tiles staged (decoded, mapped) but not yet accumulated: the current batch
+    int* d_first_tile = nullptr; size_t cap_first = 0;
     cudaEvent_t ev_h2d = nullptr;    // host-pointer mode: the caller's tile buffer has been read
     Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
     void* d_lit = nullptr; size_t lit_bytes = 0;
@@ -124,8 +130,17 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 
 // Quadtree emulation: walk the block hierarchy of process_*_block top-down for this pixel and credit the
 // first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
-__global__ void __launch_bounds__(256) k_geo_accum(GeoK g)
+// Tile-specific part of the kernel arguments: a batch launch takes several of these (blockIdx.z picks one).
+struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; };
+constexpr int GEO_NB = 8;     // tiles per batch
+struct GeoBatch { GeoTile t[GEO_NB]; int n; };
+
+// order / first_tile: batch launches record, per destination cell, the first tile of the batch (in the caller's order) that
+// actually credited it -- the per-point pass needs to know whether a cell already held data when "its" tile was processed
+__device__ __forceinline__ void geo_accum_body(GeoK g, const GeoTile& t, int order, int* __restrict__ first_tile)
 {
+    g.tile = t.tile; g.wm = const_cast<int2*>(t.wm);
+    g.smx = t.smx; g.sMx = t.sMx; g.smy = t.smy; g.sMy = t.sMy; g.smz = t.smz; g.sMz = t.sMz; g.bdr = t.bdr; g.tnx = t.tnx; g.tny = t.tny;
     __shared__ int s_bb[4];   // {jmin, imin, jmax, imax} of the cells this block credits
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     if (tid == 0) { s_bb[0] = INT_MAX; s_bb[1] = INT_MAX; s_bb[2] = INT_MIN; s_bb[3] = INT_MIN; }
@@ -179,15 +194,21 @@ __global__ void __launch_bounds__(256) k_geo_accum(GeoK g)
             const unsigned lane = threadIdx.x & 31;
             unsigned long long key = ok ? ((unsigned long long)(cat - g.start_k) * g.npts + cell) : (~0ull - lane);
             unsigned peers = __match_any_sync(__activemask(), key);
-            if (ok && lane == (unsigned)(__ffs(peers) - 1)) atomicAdd(g.acc_cnt + key, __popc(peers));
+            if (ok && lane == (unsigned)(__ffs(peers) - 1)) {
+                atomicAdd(g.acc_cnt + key, __popc(peers));
+                if (first_tile && __ldcg(first_tile + cell) > order) atomicMin(first_tile + cell, order);
+            }
         } else {
+            bool any = false;
             for (int k = g.smz; k <= g.sMz; ++k) {
                 float v = g.tile[(size_t)(k - g.smz) * tn2 + toff];
                 if (v != g.msg_val) {
                     atomicAdd(g.acc_sum + (size_t)(k - g.start_k) * g.npts + cell, (double)v);
                     atomicAdd(g.acc_cnt + (size_t)(k - g.start_k) * g.npts + cell, 1);
+                    any = true;
                 }
             }
+            if (any && first_tile && __ldcg(first_tile + cell) > order) atomicMin(first_tile + cell, order);
         }
     }
     // rows / columns this tile reaches (k_geo_merge skips the rest of the domain): one update per block, and only
@@ -199,6 +220,111 @@ __global__ void __launch_bounds__(256) k_geo_accum(GeoK g)
         if (tid < 2) { if (v < cur) atomicMin(g.tbbox + tid, v); }
         else if (v > cur) atomicMax(g.tbbox + tid, v);
     }
+}
+
+__device__ __forceinline__ GeoTile tile_of(const GeoK& g)
+{
+    GeoTile t;
+    t.tile = g.tile; t.wm = g.wm; t.smx = g.smx; t.sMx = g.sMx; t.smy = g.smy; t.sMy = g.sMy; t.smz = g.smz; t.sMz = g.sMz;
+    t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny;
+    return t;
+}
+__global__ void __launch_bounds__(256) k_geo_accum(GeoK g) { geo_accum_body(g, tile_of(g), 0, nullptr); }
+// batch: blockIdx.z = tile of the batch; the grid covers the largest tile
+__global__ void __launch_bounds__(256) k_geo_accum_b(GeoK g, GeoBatch bt, int* __restrict__ first_tile)
+{
+    const GeoTile& t = bt.t[blockIdx.z];
+    const int inx = t.tnx - 2 * t.bdr, iny = t.tny - 2 * t.bdr;
+    if ((int)(blockIdx.x * blockDim.x) >= inx || (int)(blockIdx.y * blockDim.y) >= iny) return;
+    geo_accum_body(g, t, (int)blockIdx.z, first_tile);
+}
+
+// Batch selection of the per-point pass (before the batch's accumulations are merged): the point belongs to the tile that
+// contains it (is_point_in_tile, proc_point_module.F:911-929); it takes the interpolation chain if it holds no value of
+// this level yet and no tile that comes BEFORE its own in the batch credited its cell -- exactly the points the
+// sequential order (accumulate tile, merge, fill points, next tile) would hand to get_point.  A cell that a LATER tile
+// credits keeps its chain value and the merge adds to it, as in the reference.
+__global__ void __launch_bounds__(256)
+k_geo_select_b(GeoK g, GeoBatch bt, const float2* __restrict__ src_xy, const int* __restrict__ first_tile, int* __restrict__ cand,
+               unsigned long long* __restrict__ counters)
+{
+    {   // block-level rejection as in k_geo_merge_select: no tile of the batch can contain a point of this block
+        const float4 b = g.blk_xy[blockIdx.x];
+        bool any = false;
+        for (int z = 0; z < bt.n; ++z) {
+            const GeoTile& t = bt.t[z];
+            any = any || (t.smx + t.bdr <= f_floor(b.y + 0.5f) && f_ceiling(b.x - 0.5f) <= t.sMx - t.bdr &&
+                          t.smy + t.bdr <= f_floor(b.w + 0.5f) && f_ceiling(b.z - 0.5f) <= t.sMy - t.bdr);
+        }
+        if (!any) return;
+    }
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= g.npts) return;
+    const float2 xy = src_xy[cell];
+    int owner = -1;
+    for (int z = 0; z < bt.n && owner < 0; ++z) {
+        const GeoTile& t = bt.t[z];
+        if (t.smx + t.bdr <= f_floor(xy.x + 0.5f) && f_ceiling(xy.x - 0.5f) <= t.sMx - t.bdr &&
+            t.smy + t.bdr <= f_floor(xy.y + 0.5f) && f_ceiling(xy.y - 0.5f) <= t.sMy - t.bdr) owner = z;
+    }
+    if (owner < 0) return;
+    const int ii = (int)(cell % g.nx), jj = (int)(cell / g.nx);
+    if (bit_test(g.level, g.nxw, ii, jj)) return;
+    if (first_tile[cell] <= owner) return;          // its own tile or an earlier one gives the cell data: level bit set by then
+    if (bit_test(g.processed, g.nxw, ii, jj)) { bit_set_atomic(g.level, g.nxw, ii, jj); return; }
+    cand[(size_t)owner * g.npts + atomicAdd(counters + 3 * owner + 2, 1ull)] = (int)cell;
+}
+
+// Batch merge: k_geo_merge_select's first half for all tiles of the batch at once (runs after the batch's point pass, so a
+// cell the chain has just filled is "not new" and the accumulation is added to it).  ilevel == 1 or continuous data only:
+// the half-area rule of overlay levels needs the tile-by-tile order.
+__global__ void __launch_bounds__(256) k_geo_merge_b(GeoK g, int* __restrict__ first_tile, int k0, int k1)
+{
+    {
+        size_t c0 = (size_t)blockIdx.x * blockDim.x, c1 = min(c0 + blockDim.x - 1, g.npts - 1);
+        int r0 = (int)(c0 / g.nx), r1 = (int)(c1 / g.nx);
+        if (r1 < g.tbbox[0] || r0 > g.tbbox[2]) return;   // no cell of this block was reached by the batch
+    }
+    const size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= g.npts || !g.touched[cell]) return;
+    const int ii = (int)(cell % g.nx), jj = (int)(cell / g.nx);
+    g.touched[cell] = 0;
+    first_tile[cell] = INT_MAX;
+    const bool isnew = bit_test(g.level, g.nxw, ii, jj);
+    bool any = false;
+    constexpr int CH = 8;
+    if (g.itype == WPSGPU_CATEGORICAL) {
+        for (int k0 = 0; k0 < g.nk; k0 += CH) {
+            int c[CH]; float f[CH];
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                size_t o = (size_t)(k0 + u) * g.npts + cell;
+                bool in = k0 + u < g.nk;
+                c[u] = in ? g.acc_cnt[o] : 0;
+                f[u] = (in && isnew) ? g.field[o] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                if (k0 + u >= g.nk) break;
+                size_t o = (size_t)(k0 + u) * g.npts + cell;
+                if (c[u] != 0) g.acc_cnt[o] = 0;
+                g.field[o] = f[u] + (float)c[u];
+                any |= c[u] > 0;
+            }
+        }
+    } else {
+        for (int kk = k0; kk <= k1; ++kk) {      // the level range every tile of the batch carries (src_min_z .. src_max_z)
+            size_t o = (size_t)kk * g.npts + cell;
+            const int c = g.acc_cnt[o];
+            const double sm = g.acc_sum[o];
+            g.acc_cnt[o] = 0; g.acc_sum[o] = 0.0;
+            const float f = isnew ? g.field[o] : 0.0f, n = g.count[o];
+            g.field[o] = f + (float)sm;
+            g.count[o] = n + (float)c;
+            any |= c > 0;
+        }
+    }
+    if (any) bit_set_atomic(g.level, g.nxw, ii, jj);
 }
 
 // Fold the tile's accumulation into field / data_count with the reference's first-touch semantics
@@ -439,6 +565,62 @@ __global__ void k_geo_points_literal(GeoK g, const float2* __restrict__ src_xy, 
     for (unsigned long long e = tid; e < n; e += nth) geo_point<2>(g, src_xy, (size_t)def2[e].idx, &ls);
 }
 
+// Batch versions: one launch walks the candidate lists of every tile of the batch (tile z's list sits at cand + z * npts,
+// its length at counters[3 z + 2]); deferred searches carry the tile in Deferred::slab.
+__device__ __forceinline__ void apply_tile(GeoK& g, const GeoTile& t)
+{
+    g.tile = t.tile; g.wm = const_cast<int2*>(t.wm);
+    g.smx = t.smx; g.sMx = t.sMx; g.smy = t.smy; g.sMy = t.sMy; g.smz = t.smz; g.sMz = t.sMz; g.bdr = t.bdr; g.tnx = t.tnx; g.tny = t.tny;
+}
+__global__ void __launch_bounds__(256)
+k_geo_points_b(GeoK g, GeoBatch bt, const float2* __restrict__ src_xy, const int* __restrict__ cand, unsigned long long* counters,
+               Deferred* def)
+{
+    for (int z = 0; z < bt.n; ++z) {
+        const unsigned long long n = counters[3 * z + 2];
+        if (n == 0) continue;
+        apply_tile(g, bt.t[z]);
+        for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x) {
+            size_t p = (size_t)cand[(size_t)z * g.npts + e];
+            if (geo_point<0>(g, src_xy, p, nullptr)) {
+                unsigned long long slot = atomicAdd(counters, 1ull);
+                Deferred d; d.slab = z; d.idx = (int)p;
+                def[slot] = d;
+            }
+        }
+    }
+}
+__global__ void k_geo_points_warp_b(GeoK g, GeoBatch bt, const float2* __restrict__ src_xy, const Deferred* def, unsigned long long* counters,
+                                    Deferred* def2)
+{
+    unsigned long long n = counters[0];
+    unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long e = warp; e < n; e += nw) {
+        Deferred d = def[e];
+        apply_tile(g, bt.t[d.slab]);
+        bool again = geo_point<1>(g, src_xy, (size_t)d.idx, nullptr);
+        if (again && (threadIdx.x & 31) == 0) { unsigned long long slot = atomicAdd(counters + 1, 1ull); def2[slot] = d; }
+    }
+}
+__global__ void k_geo_points_literal_b(GeoK g, GeoBatch bt, const float2* __restrict__ src_xy, const Deferred* def2, const unsigned long long* counters,
+                                       unsigned* scratch, size_t words_per_thread, int R, int qcap)
+{
+    unsigned long long n = counters[1], tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned* mine = scratch + tid * words_per_thread;
+    size_t vis_words = ((size_t)(2 * R + 1) * (2 * R + 1) + 31) / 32;
+    LitScratch ls;
+    ls.visited = mine; ls.R = R; ls.q = reinterpret_cast<QNode*>(mine + ((vis_words + 1) & ~size_t(1))); ls.qcap = qcap;
+    for (unsigned long long e = tid; e < n; e += nth) {
+        apply_tile(g, bt.t[def2[e].slab]);
+        geo_point<2>(g, src_xy, (size_t)def2[e].idx, &ls);
+    }
+}
+__global__ void k_geo_batch_reset(int* tbbox, unsigned long long* counters)
+{
+    if (threadIdx.x == 0) { tbbox[0] = INT_MAX; tbbox[1] = INT_MAX; tbbox[2] = INT_MIN; tbbox[3] = INT_MIN; }
+    if (threadIdx.x < 3 * GEO_NB) counters[threadIdx.x] = 0ull;
+}
+
 // calc_field post-processing (process_tile_module.F:1580-1659)
 __global__ void k_geo_finish(GeoK g, int has_scale, float scale_factor)
 {
@@ -559,14 +741,15 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
     if (!h->geo) return;
     GeoState* s = h->geo;
     geo_free_field(s);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < GEO_SETS; ++b) {
         if (s->d_tile[b]) cudaFree(s->d_tile[b]);
         if (s->d_wm[b]) cudaFree(s->d_wm[b]);
         if (s->ev_pre[b]) cudaEventDestroy(s->ev_pre[b]);
         if (s->ev_used[b]) cudaEventDestroy(s->ev_used[b]);
     }
     if (s->s_pre) cudaStreamDestroy(s->s_pre);
-    for (int b = 0; b < 2; ++b) if (s->d_raw[b]) cudaFree(s->d_raw[b]);
+    for (int b = 0; b < GEO_SETS; ++b) if (s->d_raw[b]) cudaFree(s->d_raw[b]);
+    if (s->d_first_tile) cudaFree(s->d_first_tile);
     if (s->ev_h2d) cudaEventDestroy(s->ev_h2d);
     if (s->d_lit) cudaFree(s->d_lit);
     if (s->d_invalid) cudaFree(s->d_invalid);
@@ -582,7 +765,7 @@ int wpsgpu_geogrid_field_begin(wpsgpu_handle_t h, const wpsgpu_geo_field* f)
     WPS_CHECK(h && f && f->xlat && f->xlon && f->field, -1, "wpsgpu_geogrid_field_begin: NULL argument");
     WPS_CHECK(f->dom_proj.init, -1, "domain projection not initialised");
     WPS_CUDA(cudaSetDevice(h->device));
-    if (!h->geo) { h->geo = new GeoState(); WPS_CUDA(cudaMalloc((void**)&h->geo->d_invalid, 4 * sizeof(unsigned long long))); }
+    if (!h->geo) { h->geo = new GeoState(); WPS_CUDA(cudaMalloc((void**)&h->geo->d_invalid, (1 + 3 * GEO_NB) * sizeof(unsigned long long))); }
     GeoState* s = h->geo;
     WPS_CUDA(cudaStreamSynchronize(h->stream));
     geo_free_field(s);
@@ -619,9 +802,14 @@ int wpsgpu_geogrid_field_begin(wpsgpu_handle_t h, const wpsgpu_geo_field* f)
         WPS_TRY(geo_buf((void**)&s->d_def, &cap, s->npts * sizeof(Deferred), false, h->stream));
         WPS_TRY(geo_buf((void**)&s->d_def2, &s->cap_def, s->npts * sizeof(Deferred), false, h->stream));
     }
-    WPS_TRY(geo_buf((void**)&s->d_cand, &s->cap_cand, s->npts * sizeof(int), false, h->stream));
+    WPS_TRY(geo_buf((void**)&s->d_cand, &s->cap_cand, (size_t)GEO_NB * s->npts * sizeof(int), false, h->stream));
+    if (s->npts * sizeof(int) > s->cap_first) {
+        WPS_TRY(geo_buf((void**)&s->d_first_tile, &s->cap_first, s->npts * sizeof(int), false, h->stream));
+        WPS_CUDA(cudaMemsetAsync(s->d_first_tile, 0x7f, s->cap_first, h->stream));   // "no tile yet"; k_geo_merge_b restores it
+    }
+    s->pending.clear();
     if (!s->d_tbbox) WPS_CUDA(cudaMalloc((void**)&s->d_tbbox, 4 * sizeof(int)));
-    WPS_CUDA(cudaMemsetAsync(s->d_invalid, 0, 4 * sizeof(unsigned long long), h->stream));
+    WPS_CUDA(cudaMemsetAsync(s->d_invalid, 0, (1 + 3 * GEO_NB) * sizeof(unsigned long long), h->stream));
     if (host) WPS_CUDA(cudaStreamSynchronize(h->stream));
     s->field_open = true;
     return 0;
@@ -661,13 +849,13 @@ static int geo_tile_begin(wpsgpu_ctx* h, size_t tile_floats, int* set, cudaStrea
     GeoState* s = h->geo;
     if (!s->s_pre) {
         WPS_CUDA(cudaStreamCreateWithFlags(&s->s_pre, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < GEO_SETS; ++b) {
             WPS_CUDA(cudaEventCreateWithFlags(&s->ev_pre[b], cudaEventDisableTiming));
             WPS_CUDA(cudaEventCreateWithFlags(&s->ev_used[b], cudaEventDisableTiming));
         }
         WPS_CUDA(cudaEventCreateWithFlags(&s->ev_h2d, cudaEventDisableTiming | cudaEventBlockingSync));
     }
-    *set = s->parity; s->parity ^= 1; *pre = s->s_pre;
+    *set = s->parity; s->parity = (s->parity + 1) % GEO_SETS; *pre = s->s_pre;
     if (s->used_rec[*set]) WPS_CUDA(cudaStreamWaitEvent(s->s_pre, s->ev_used[*set], 0));
     if (tile_floats * sizeof(float) > s->tile_cap[*set]) {
         WPS_CUDA(cudaStreamSynchronize(h->stream));
@@ -682,6 +870,63 @@ static int geo_tile_staged(wpsgpu_ctx* h, cudaStream_t pre)
     if (h->ptr_mode != WPSGPU_PTR_HOST) return 0;
     WPS_CUDA(cudaEventRecord(h->geo->ev_h2d, pre));
     WPS_CUDA(cudaEventSynchronize(h->geo->ev_h2d));
+    return 0;
+}
+
+// Tiles of a level whose results do not depend on the tile-by-tile order beyond what k_geo_select_b reproduces are
+// accumulated GEO_NB at a time: one accumulate launch, one selection, one point pass and one merge per batch instead of per
+// tile.  Overlay levels of categorical data (half-area rule after every tile, proc_point_module.F:165-202) keep the
+// sequential path; WPSGPU_GEO_BATCH=0 forces it for everything (A/B measurements and the parity tests).
+static bool geo_batchable(const GeoState* s)
+{
+    static const bool enabled = !(getenv("WPSGPU_GEO_BATCH") && atoi(getenv("WPSGPU_GEO_BATCH")) == 0);
+    if (!enabled) return false;
+    if (s->l.itype == WPSGPU_SP_CONTINUOUS) return true;
+    return s->l.itype == WPSGPU_CATEGORICAL && s->l.ilevel == 1;
+}
+
+static int geo_flush_batch(wpsgpu_ctx* h)
+{
+    GeoState* s = h->geo;
+    if (s->pending.empty()) return 0;
+    GeoK g = make_k(h);
+    GeoBatch bt;
+    memset(&bt, 0, sizeof(bt));
+    bt.n = (int)s->pending.size();
+    int gx = 1, gy = 1, tmax = 1;
+    for (int z = 0; z < bt.n; ++z) {
+        const GeoState::Pending& p = s->pending[z];
+        GeoTile& t = bt.t[z];
+        t.tile = s->d_tile[p.set]; t.wm = s->d_wm[p.set];
+        t.smx = p.smx; t.sMx = p.sMx; t.smy = p.smy; t.sMy = p.sMy; t.smz = p.smz; t.sMz = p.sMz; t.bdr = p.bdr;
+        t.tnx = p.sMx - p.smx + 1; t.tny = p.sMy - p.smy + 1;
+        gx = std::max(gx, (t.tnx - 2 * p.bdr + 31) / 32); gy = std::max(gy, (t.tny - 2 * p.bdr + 7) / 8);
+        tmax = std::max(tmax, std::max(t.tnx, t.tny));
+        WPS_CUDA(cudaStreamWaitEvent(h->stream, s->ev_pre[p.set], 0));   // the tile and its mapping are in place
+    }
+    unsigned long long* cnt = g.counters;
+    k_geo_batch_reset<<<1, 32, 0, h->stream>>>(g.tbbox, cnt);
+    k_geo_accum_b<<<dim3(gx, gy, bt.n), dim3(32, 8), 0, h->stream>>>(g, bt, s->d_first_tile);
+    const unsigned nblk = (unsigned)((s->npts + 255) / 256);
+    k_geo_select_b<<<nblk, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_first_tile, s->d_cand, cnt);
+    k_geo_points_b<<<h->sm_count * 2, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_cand, cnt, s->d_def);
+    h->launches += 4;
+    if (s->has_search) {
+        k_geo_points_warp_b<<<h->sm_count * 8, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_def, cnt, s->d_def2);
+        int R = std::min(std::max(s->max_depth, 1), tmax);
+        size_t vis_words = ((size_t)(2 * R + 1) * (2 * R + 1) + 31) / 32;
+        int qcap = 8 * R + 64;
+        size_t wpt = ((vis_words + 1) & ~size_t(1)) + (size_t)qcap * sizeof(QNode) / sizeof(unsigned);
+        int lit_threads = 256;
+        WPS_TRY(geo_grow(&s->d_lit, &s->lit_bytes, wpt * sizeof(unsigned) * lit_threads, h->stream));
+        k_geo_points_literal_b<<<lit_threads / 64, 64, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_def2, cnt, (unsigned*)s->d_lit, wpt, R, qcap);
+        h->launches += 2;
+    }
+    k_geo_merge_b<<<nblk, 256, 0, h->stream>>>(g, s->d_first_tile, s->pending[0].smz - s->f.start_k, s->pending[0].sMz - s->f.start_k);
+    h->launches++;
+    WPS_CUDA(cudaGetLastError());
+    for (const GeoState::Pending& p : s->pending) { WPS_CUDA(cudaEventRecord(s->ev_used[p.set], h->stream)); s->used_rec[p.set] = true; }
+    s->pending.clear();
     return 0;
 }
 
@@ -704,6 +949,17 @@ static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, i
         k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, pre>>>(g);
         h->launches++;
     }
+    if (accum && geo_batchable(s) && pre != h->stream) {
+        // batch path: the tile waits, staged, until GEO_NB tiles have come together (or the level ends)
+        WPS_CUDA(cudaEventRecord(s->ev_pre[set], pre));
+        if (!s->pending.empty() && (s->pending[0].smz != smz || s->pending[0].sMz != sMz)) WPS_TRY(geo_flush_batch(h));
+        GeoState::Pending p;
+        p.set = set; p.smx = smx; p.sMx = sMx; p.smy = smy; p.sMy = sMy; p.smz = smz; p.sMz = sMz; p.bdr = bdr;
+        s->pending.push_back(p);
+        if ((int)s->pending.size() == GEO_NB) WPS_TRY(geo_flush_batch(h));
+        return 0;
+    }
+    WPS_TRY(geo_flush_batch(h));   // anything pending precedes a tile of the sequential path
     if (pre != h->stream) {   // the handle's stream takes over once the tile and its mapping are in place
         WPS_CUDA(cudaEventRecord(s->ev_pre[set], pre));
         WPS_CUDA(cudaStreamWaitEvent(h->stream, s->ev_pre[set], 0));
@@ -825,6 +1081,7 @@ int wpsgpu_geogrid_level_end(wpsgpu_handle_t h)
     WPS_CHECK(h && h->geo && h->geo->level_open, -1, "wpsgpu_geogrid_level_end: no level open");
     WPS_CUDA(cudaSetDevice(h->device));
     GeoState* s = h->geo;
+    WPS_TRY(geo_flush_batch(h));
     GeoK g = make_k(h);
     k_geo_finish<<<(unsigned)((s->npts + 255) / 256), 256, 0, h->stream>>>(g, s->l.has_scale, s->l.scale_factor);
     size_t nwords = (size_t)s->ny * s->nxw;
