@@ -386,7 +386,8 @@ int wpsgpu_destroy(wpsgpu_handle_t h)
     if (h->d_search_scratch) cudaFree(h->d_search_scratch);
     for (int k = 0; k < 12; ++k) if (h->ev_t[k]) cudaEventDestroy(h->ev_t[k]);
     if (h->s_side) cudaStreamDestroy(h->s_side);
-    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     if (h->ev_copy) cudaEventDestroy(h->ev_copy);

@@ -122,8 +122,8 @@ struct wpsgpu_ctx {
     double last_points = 0.0;
     double last_pts3[6] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
     cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the host-pointer pipeline
-    cudaStream_t s_side = nullptr;                  // slow-bitmap passes overlapping the first-method kernels
-    std::vector<cudaEvent_t> ev_pool;               // per-job fork events for s_side
+    cudaStream_t s_side = nullptr;                  // four_pt / nearest_neighbor first-method kernels beside the sixteen_pt kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_done = nullptr, ev_out_done = nullptr;
     int64_t h2d_bytes = 0, d2h_bytes = 0;           // bytes moved by the host-pointer paths of the metgrid flush
     bool async_pending = false;                     // wpsgpu_metgrid_flush_async: D2H copies may still read the arena

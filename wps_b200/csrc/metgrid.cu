@@ -884,7 +884,7 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                          float* dump_r, int* dump_w, const SlowQ& sq)
 {
     const bool stage = env_int("WPSGPU_STRIP_STAGE", 1, 0, 1) != 0;   // 0: windows straight from global memory (A/B measurements)
-    const int work_packs = env_int("WPSGPU_STRIP_CHUNK", 16, 1, 64);    // packs per block
+    const int work_packs = env_int("WPSGPU_STRIP_CHUNK", 32, 1, 64);    // packs per block
     // jobs that share the destination grid, the cached coordinates and the record-array geometry form a class: a block
     // does the level-independent set-up once for all of them
     auto same_geometry = [](const Job& a, const Job& b) {
@@ -1479,6 +1479,38 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
 
     // ---- launches ----
     dim3 block(TILE_X, TILE_Y);
+    // The four_pt / nearest_neighbor first-method jobs (a handful of 2-d fields, 20-40 us per launch, latency-bound) run on
+    // a side stream beside the sixteen_pt kernels instead of after them: they only share the slow queue (atomics).
+    const bool have16 = !pack_jobs.empty() || !win_tasks.empty();
+    bool have4 = false;
+    for (int j : cls_jobs[1]) have4 = have4 || jobs[j].fast >= 2;
+    const bool side = have16 && have4 && env_int("WPSGPU_SIDE_STREAM", 1, 0, 1) != 0;
+    cudaStream_t s4 = h->stream;
+    if (side) {
+        if (!h->s_side) {
+            WPS_CUDA(cudaStreamCreateWithFlags(&h->s_side, cudaStreamNonBlocking));
+            WPS_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            WPS_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        WPS_CUDA(cudaEventRecord(h->ev_fork, h->stream));      // inputs staged, tables uploaded, counters cleared
+        WPS_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_fork, 0));
+        s4 = h->s_side;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[6], s4));
+    for (int j : cls_jobs[1]) {
+        if (jobs[j].fast < 2) continue;
+        Fast4Params fp;
+        fp.jb = jobs[j];
+        for (int k = 0; k < fp.jb.nslab; ++k) {
+            const SlabPtrs& p = sp[fp.jb.slab0 + k];
+            fp.src[k] = p.src; fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts;
+        }
+        fp.sq = sq;
+        if (jobs[j].fast == 2) k_metgrid_fast4<WPSGPU_FOUR_POINT><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, s4>>>(fp);
+        else k_metgrid_fast4<WPSGPU_N_NEIGHBOR><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, s4>>>(fp);
+        h->launches++;
+    }
+    WPS_CUDA(cudaEventRecord(h->ev_t[7], s4));
     WPS_CUDA(cudaEventRecord(h->ev_t[0], h->stream));
     if (!pack_jobs.empty()) {
         k_pack16<<<dim3((pack_cells + 255) / 256, pack_max, (unsigned)pack_jobs.size()), 256, 0, h->stream>>>(d_jobs, d_pack_jobs, d_sp);
@@ -1519,21 +1551,10 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         WPS_TRY(launch_strips(h, jobs, sj, sp, dump_r, dump_w, sq));
     }
     WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
-    WPS_CUDA(cudaEventRecord(h->ev_t[6], h->stream));
-    for (int j : cls_jobs[1]) {
-        if (jobs[j].fast < 2) continue;
-        Fast4Params fp;
-        fp.jb = jobs[j];
-        for (int k = 0; k < fp.jb.nslab; ++k) {
-            const SlabPtrs& p = sp[fp.jb.slab0 + k];
-            fp.src[k] = p.src; fp.r_arr[k] = p.r_arr; fp.new_pts[k] = p.new_pts;
-        }
-        fp.sq = sq;
-        if (jobs[j].fast == 2) k_metgrid_fast4<WPSGPU_FOUR_POINT><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
-        else k_metgrid_fast4<WPSGPU_N_NEIGHBOR><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, h->stream>>>(fp);
-        h->launches++;
+    if (side) {   // join: the slow pass and everything after it see the side stream's results
+        WPS_CUDA(cudaEventRecord(h->ev_join, h->s_side));
+        WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[7], h->stream));
     WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
     if (tile_cursor[1] > 0) {
         k_metgrid_slowlist<<<h->sm_count * SLOW_MINBLOCKS, 128, 0, h->stream>>>(d_jobs, njobs, d_sp, sq, d_def, d_cnt);
