@@ -141,3 +141,35 @@ def test_cpp_host_side_matches_python_mirror(orc, handle, tmp_path):
             assert_bitexact(r, f.r_arr, "C++ host side %s %d" % (name, level))
     finally:
         hd.close()
+
+
+def test_two_records_of_one_field_level_in_a_file(orc, handle, tmp_path):
+    """two records of a file that resolve to the same (field, level).  The reference processes records one
+    after another and merges valid_mask after each (process_domain_module.F:1225-1365): the second interpolation sees the
+    first one's points as valid.  Both host mirrors flush before queueing the duplicate; the result must equal the
+    sequential oracle loop (first record partly missing, second record fills only what it has)."""
+    from wps_b200.interp_option import read_interp_table
+    from wps_b200.metgrid import MetgridDomain, halo_slab
+    orc.set_transc_mode(1)
+    nx, ny = 58, 47
+    odom, gdom = conus_like(nx, ny, 40000.0, 30.0, 60.0, -98.0, 36.0, -92.0)
+    g = {1: orc.get_lat_lon_fields(odom, 1, 1, nx, ny, orc.M), 2: orc.get_lat_lon_fields(odom, 1, 1, nx + 1, ny, orc.U),
+         3: orc.get_lat_lon_fields(odom, 1, 1, nx, ny + 1, orc.V)}
+    table = read_interp_table(TBL)
+    recs = make_file(tmp_path, "FILE:2026-10-19_00", [("T", 85000.0, "smooth"), ("T", 85000.0, "wind"), ("T", 70000.0, "smooth")], 300)
+    recs[0].slab[:, 200:300] = 1e20          # first record: a band of missing values over the domain's longitudes
+    recs[1].slab[:90, :] = 1e20              # second record: missing elsewhere
+    dom = MetgridDomain(handle, g[1][0], g[1][1], g[2][0], g[2][1], g[3][0], g[3][1], None)
+    storage = dom.process_intermediate_fields(recs, table, "FILE")
+    src = orc.push_source_projection(orc.PROJ_LATLON, dlat=-1.0, dlon=1.0, known_x=1.0, known_y=1.0, known_lat=90.0, known_lon=0.0,
+                                     earth_radius=np.float32(6371.229) * np.float32(1000.0))
+    fo = orc.field_opts("sixteen_pt+four_pt+average_4pt", np.float32(1e20), np.float32(0.0))
+    slab, minx, bdr = halo_slab(recs[0])
+    r1, n1 = orc.interp_met_field(src, fo, 1, g[1][0], g[1][1], 1, 1, (1, nx, 1, ny), slab, minx, 1, bdr)
+    slab, minx, bdr = halo_slab(recs[1])
+    r2, n2 = orc.interp_met_field(src, fo, 1, g[1][0], g[1][1], 1, 1, (1, nx, 1, ny), slab, minx, 1, bdr, r_arr=r1.copy(), valid_mask=n1)
+    got = storage[("TT", 85000)]
+    assert (got.modified_mask == n2).all()
+    assert (got.valid_mask == (n1 | n2)).all()
+    assert_bitexact(got.r_arr, r2, "second record of the same (field, level)")
+    assert (n1 != n2).any() and (bits_to_bool(n1, nx) & ~bits_to_bool(n2, nx)).any()

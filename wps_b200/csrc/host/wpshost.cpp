@@ -458,6 +458,14 @@ int wpshost_process_file(wpshost_domain_t d, const char* path, const char* input
         const int stag = (e.output_stagger == WPSGPU_U || e.output_stagger == WPSGPU_V) ? e.output_stagger : WPSGPU_M;
         const int level = (int)lroundf(r.xlvl);
         Field* fld = d->find(name, level);   // storage_query_field (:1225-1233): data and valid mask carry over
+        if (fld && std::find(queued.begin(), queued.end(), fld) != queued.end()) {
+            // a second record of the same (field, level) in this file: the reference has finished the first one --
+            // interpolation and bitarray_merge (:1225-1365) -- before it reads the second, so flush what is queued
+            GPU_TRY(wpsgpu_metgrid_flush(d->gpu));
+            for (Field* f : queued)
+                for (size_t w = 0; w < f->valid_mask.size(); ++w) f->valid_mask[w] |= f->modified_mask[w];
+            queued.clear();
+        }
         const bool fresh = fld == nullptr;
         if (!fld) fld = d->put(name, level, stag);
         std::fill(fld->modified_mask.begin(), fld->modified_mask.end(), 0);   // bitarray_create(field%modified_mask)

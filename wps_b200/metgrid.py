@@ -108,6 +108,14 @@ class MetgridDomain:
             xlat, _ = self.grids[stag]
             gy, gx = xlat.shape
             key = (name, int(np.rint(fg.xlvl)))
+            if any(k == key for k, _ in queued):
+                # a second record of the same (field, level) in this file: the reference has finished the first one --
+                # interpolation and bitarray_merge (:1225-1365) -- before it reads the second, so flush what is queued
+                self.h.metgrid_flush()
+                for _, f in queued:
+                    f.valid_mask |= f.modified_mask
+                queued.clear()
+                keep.clear()
             if key in storage:                       # storage_query_field found it (:1225-1233): carry data + valid mask over
                 fld = storage[key]
                 fld.modified_mask = None
