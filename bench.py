@@ -393,6 +393,86 @@ def aux_kernels_arm(h, torch, dev, steps=5):
     return out
 
 
+def config4_arm(h, torch, dev, steps=5):
+    """BASELINE configs[3]: 27 / 9 / 3-km nests (compute_nest_locations), Lambert-grid source (NAM-218-like, 614 x 428),
+    per nest TT / UU / VV x 8 levels + SST (masked land) + soil temperature (masked water, search) + SKINTEMP (masked=both),
+    ONE flush per nest, then map_to_met + met_to_map on the winds.  Device-resident; small domains: launch-latency bound."""
+    from wps_b200 import capi, synth
+    cfg = synth.CONFIGS["config4"]
+    nests = [(p, r, (ij if isinstance(ij, tuple) else (1, 1))[0], (ij if isinstance(ij, tuple) else (1, 1))[1], ewe, esn)
+             for (p, r, ij, ewe, esn) in cfg["nests"]]
+    nx1, ny1, dx, tl1, tl2, slon, rlat, rlon = cfg["dom"]
+    projs = capi.compute_nest_locations(capi.PROJ_LC, nests, truelat1=tl1, truelat2=tl2, stdlon=slon, lat1=rlat, lon1=rlon,
+                                        knowni=nx1 / 2.0, knownj=ny1 / 2.0, dx=dx)
+    snx, sny, nlev = 614, 428, cfg["nlev"]
+    src = capi.push_source_projection(capi.PROJ_LC, stand_lon=-95.0, truelat1=25.0, truelat2=25.0, dxkm=12190.58, dykm=12190.58,
+                                      known_x=1.0, known_y=1.0, known_lat=12.19, known_lon=-133.459)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    jj = torch.arange(sny, device=dev, dtype=torch.float32)[:, None]
+    ii = torch.arange(snx, device=dev, dtype=torch.float32)[None, :]
+    ls = ((torch.sin(ii / 23.0) + torch.cos(jj / 17.0)) > -0.2).float().contiguous()
+    tt = (285.0 + 8.0 * torch.sin(ii / 60.0) * torch.cos(jj / 45.0))[None].repeat(nlev, 1, 1).contiguous()
+    uu = (12.0 * torch.sin(ii / 70.0) * torch.cos(jj / 50.0))[None].repeat(nlev, 1, 1).contiguous()
+    sst = (290.0 + 6.0 * torch.cos(jj / 80.0) + 0.0 * ii).contiguous()
+    sst[ls == 1] = -1e30
+    soil = (280.0 + 5.0 * torch.sin(ii / 40.0) + 0.0 * jj).contiguous()
+    soil[ls == 0] = -1e30
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total_ms, total_pts, launches = 0.0, 0, 0
+    per_nest = []
+    for dom_id, (pg, nest) in enumerate(zip(projs, nests), start=1):
+        nx, ny = nest[4] - 1, nest[5] - 1
+        grids = {}
+        for gid, (st, gx, gy) in {0: (capi.M, nx, ny), 1: (capi.U, nx + 1, ny), 2: (capi.V, nx, ny + 1)}.items():
+            xlat = torch.empty((gy, gx), dtype=torch.float32, device=dev); xlon = torch.empty_like(xlat)
+            h.xytoll_grid(pg, st, 1, 1, gx, gy, out=(xlat, xlon))
+            h.metgrid_set_grid(gid, xlat, xlon, 1, 1)
+            grids[gid] = (xlat, xlon)
+        h.metgrid_set_domain(1, nx, 1, ny)
+        lm = ((torch.sin(grids[0][1] * 0.9) + torch.cos(grids[0][0] * 1.3)) > -0.3).float().contiguous()
+        h.metgrid_set_landmask(0, lm)
+        fields = [(tt, 0, capi.M, synth.C3D, 1e20, 0.0, -2.0, (None, None, None), (1e20, 1e20, 1e20), True),
+                  (uu, 1, capi.U, synth.C3D, 1e20, 0.0, -2.0, (None, None, None), (1e20, 1e20, 1e20), False),
+                  (uu, 2, capi.V, synth.C3D, 1e20, 0.0, -2.0, (None, None, None), (1e20, 1e20, 1e20), False),
+                  (sst[None], 0, capi.M, "sixteen_pt+four_pt+wt_average_4pt+search", -1e30, 0.0, 1.0, (ls, None, None), (1.0, 1e20, 1e20), True),
+                  (soil[None], 0, capi.M, synth.SOIL, -1e30, 285.0, 0.0, (ls, None, None), (0.0, 1e20, 1e20), True),
+                  (tt[:1], 0, capi.M, synth.SOIL, 1e20, 0.0, -1.0, (None, ls, ls), (1e20, 1.0, 0.0), True)]
+        plan, pts = [], 0
+        for slabs, gid, st, chain, msg, fill, masked, masks, mv, use_lm in fields:
+            gy, gx = grids[gid][0].shape
+            n = slabs.shape[0]
+            r = torch.zeros((n, gy, gx), dtype=torch.float32, device=dev)
+            npw = torch.zeros((n, gy, capi.nwords(gx)), dtype=torch.int32, device=dev)
+            arr = (capi.Slab * n)()
+            for k in range(n):
+                capi.Handle.slab_desc(slabs[k], 1, 1, 0, gid, st, r[k], npw[k], masks=masks, use_landmask=use_lm, out=arr[k])
+            plan.append((capi.field_opts(chain, np.float32(msg), np.float32(fill), masked, mv), arr, n, r, npw))
+            pts += n * gy * gx
+
+        def one():
+            for fo, arr, n, _, _ in plan:
+                h.metgrid_enqueue_slabs(src, fo, arr, n)
+            h.metgrid_flush()
+            h.rotate_winds(1, src, plan[1][3], plan[1][4], plan[2][3], plan[2][4], grids[1][1], grids[2][1])
+            h.rotate_winds(-1, pg, plan[1][3], plan[1][4], plan[2][3], plan[2][4], grids[1][1], grids[2][1])
+        one(); one()
+        torch.cuda.synchronize()
+        l0 = h.launch_count
+        ev0.record(stream)
+        for _ in range(steps):
+            one()
+        ev1.record(stream)
+        h.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+        per_nest.append({"domain": dom_id, "grid": "%dx%d" % (nx, ny), "ms": ms, "points": pts})
+        total_ms += ms; total_pts += pts; launches += (h.launch_count - l0) // steps
+    return {"metric": "metgrid output points/s, config 4 (three nests, one flush + wind rotations per nest)", "value": total_pts / (total_ms / 1e3),
+            "unit": "points/s", "ms_total": total_ms, "points": total_pts, "gpu_launches": launches, "per_nest": per_nest,
+            "note": "25-28 k points per nest and level: launch-latency bound, not a roofline case"}
+
+
 def config5_plan(capi, synth, config, rank, world):
     """One time of an ERA5-shaped FILE: TT, QV, UU, VV on `nlev` model levels; the slabs of the step are sharded by level
     (shard.shard_slabs keeps UU and VV of a level on the same rank) -> this rank's list of (field, level, stagger, kind)."""
@@ -707,11 +787,12 @@ def run_b200(args, rank, world, local_rank):
         e2e_raw_s = (time.perf_counter() - t0) / e2e_steps
         hh.close()
 
-    geo, vfill, aux = None, None, None
+    geo, vfill, aux, cfg4 = None, None, None, None
     if rank == 0 and not args.no_geogrid:
         geo = geogrid_arm(h, torch, dev, config, 3)
         vfill = vertical_fill_arm(h, torch, dev, config, 3)
         aux = aux_kernels_arm(h, torch, dev)
+        cfg4 = config4_arm(h, torch, dev)
     if rank == 0:
         peaks = {}
         try:
@@ -748,6 +829,7 @@ def run_b200(args, rank, world, local_rank):
             line["geogrid"] = geo
             line["vertical_fill"] = vfill
             line["aux_kernels"] = aux
+            line["config4"] = cfg4
             for k in aux.values():
                 k["frac_of_hbm_peak"] = k["GBps"] / peak
         if world == 1 and not args.no_cpu:
