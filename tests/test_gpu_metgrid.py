@@ -749,3 +749,45 @@ def test_mask_aliasing_a_partially_staged_slab(orc, handle, monkeypatch):
             else:
                 assert_sixteen_pt_tolerance(r, r_ref, 300.0, "chain %s, tolerance mode" % chain)
     handle.metgrid_set_precision(capi.PRECISION_EXACT)
+
+
+@pytest.mark.parametrize("tolerance", [False, True])
+def test_masked_both_with_landmask_outside_0_1(orc, handle, tolerance):
+    """Known divergence, pinned on the device: masked=both with a LANDMASK value that is neither 0 nor
+    1 leaves the reference's `temp` holding the PREVIOUS point's value (process_domain_module.F:2497-2526; uninitialised
+    for the first point).  The device defines such points as "no interpolated value": they receive fill_missing and
+    count as new when fill_missing is not NaN-like, exactly like a point whose chain found nothing.  Everywhere else
+    the result equals the oracle."""
+    from wps_b200 import capi
+    xlat, xlon = make_domain(orc, handle, nx=70, ny=41)
+    ny, nx = xlat.shape
+    osrc, gsrc = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    ls = halo(landsea(360, 181))
+    slab = halo(synth_field(360, 181, 31))
+    rng = np.random.default_rng(6)
+    lm = (rng.random((ny, nx)) < 0.6).astype(np.float32)
+    odd = rng.random((ny, nx)) < 0.05
+    lm_odd = lm.copy()
+    lm_odd[odd] = 0.5                            # e.g. a fractional LANDMASK handed over by mistake
+    chain = "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search"
+    fill = np.float32(-77.0)
+    fo_o = orc.field_opts(chain, 1e20, fill, -1.0, (1e20, 1.0, 0.0))
+    fo_g = capi.field_opts(chain, 1e20, fill, -1.0, (1e20, 1.0, 0.0))
+    handle.metgrid_set_precision(capi.PRECISION_TOLERANCE if tolerance else capi.PRECISION_EXACT)
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_landmask(0, lm_odd)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    r = np.zeros((ny, nx), np.float32)
+    npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+    handle.metgrid_enqueue_slab(gsrc, fo_g, slab, -2, 1, 3, 0, capi.M, r, npw, masks=(None, ls, ls), use_landmask=True)
+    handle.metgrid_flush()
+    handle.metgrid_set_precision(capi.PRECISION_EXACT)
+    # the oracle with a clean landmask gives the reference's values wherever the landmask is 0 or 1
+    r_ref, np_ref = orc.interp_met_field(osrc, fo_o, 1, xlat, xlon, 1, 1, (1, nx, 1, ny), slab, -2, 1, 3, land_mask=ls, water_mask=ls, landmask=lm)
+    bits, bits_ref = bits_to_bool(npw, nx), bits_to_bool(np_ref, nx)
+    assert (bits[~odd] == bits_ref[~odd]).all()
+    if tolerance:
+        assert_sixteen_pt_tolerance(r[~odd], r_ref[~odd], float(np.abs(slab).max()), "masked=both, clean landmask points")
+    else:
+        assert_bitexact(r[~odd], r_ref[~odd], "masked=both, clean landmask points")
+    assert (r[odd] == fill).all() and bits[odd].all(), "points with LANDMASK outside {0, 1} receive fill_missing and count as new"
