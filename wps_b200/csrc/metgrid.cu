@@ -874,16 +874,50 @@ static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
 
 // Tolerance-mode sixteen_pt jobs of one pass -> as few strip launches as the parameter block allows.
 template <int R>
-static void launch_strip_kernel(const StripParams& sp, unsigned tiles, unsigned nwork, bool stage, cudaStream_t st)
+static void launch_strip_kernel(const StripParams& sp, unsigned tiles, unsigned nwork, int stage, cudaStream_t st)
 {
-    if (stage && R > 1) k_metgrid_strip16<R, (R > 1)><<<dim3(tiles, nwork), 32, 0, st>>>(sp);
-    else k_metgrid_strip16<R, false><<<dim3(tiles, nwork), 32, 0, st>>>(sp);
+    if (stage == 2 && R > 1) k_metgrid_strip16<R, (R > 1 ? 2 : 0)><<<dim3(tiles, nwork), 32, 0, st>>>(sp);
+    else if (stage == 1 && R > 1) k_metgrid_strip16<R, (R > 1 ? 1 : 0)><<<dim3(tiles, nwork), 32, 0, st>>>(sp);
+    else k_metgrid_strip16<R, 0><<<dim3(tiles, nwork), 32, 0, st>>>(sp);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && p)
+            fn = (EncodeTiledFn)p;
+        else (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// The window records of a strip job, [npack][pny][pnx] float4, as the tensor the ring's tiled copies read: box = SBW cells x
+// SBH rows x 1 pack, cells past the array's edge arrive as zeros (they belong to no lane's window).
+static bool encode_window_tensor(CUtensorMap* tm, const Job& jb)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = { (cuuint64_t)jb.bnx * 4, (cuuint64_t)jb.bny, (cuuint64_t)jb.npack };
+    const cuuint64_t strides[2] = { (cuuint64_t)jb.bnx * 16, (cuuint64_t)jb.bnx * jb.bny * 16 };
+    const cuuint32_t box[3] = { SBW * 4, SBH, 1 }, estr[3] = { 1, 1, 1 };
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float4*>(jb.rec), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std::vector<int>& sel, const std::vector<SlabPtrs>& sp,
                          float* dump_r, int* dump_w, const SlowQ& sq)
 {
-    const bool stage = env_int("WPSGPU_STRIP_STAGE", 1, 0, 1) != 0;   // 0: windows straight from global memory (A/B measurements)
+    // 2: ring fed by one tiled tensor copy per pack, 1: by one bulk copy per box row, 0: windows straight from global memory
+    int stage = env_int("WPSGPU_STRIP_STAGE", 2, 0, 2);
+    if (stage == 2 && !tensor_map_encoder()) stage = 1;
     const int work_packs = env_int("WPSGPU_STRIP_CHUNK", 32, 1, 64);    // packs per block
     // jobs that share the destination grid, the cached coordinates and the record-array geometry form a class: a block
     // does the level-independent set-up once for all of them
@@ -940,9 +974,10 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                     q.msg = jb.msg; q.fill = jb.fill; q.masked = jb.masked;
                     for (int k = 0; k < jb.nslab; ++k) {
                         const SlabPtrs& p = sp[jb.slab0 + k];
-                        P.r_arr[ns + k] = p.r_arr; P.new_pts[ns + k] = p.new_pts;
+                        P.out[ns + k].r = p.r_arr; P.out[ns + k].w = p.new_pts;
                     }
-                    for (int k = jb.nslab; k < nslot; ++k) { P.r_arr[ns + k] = dump_r; P.new_pts[ns + k] = dump_w; }
+                    for (int k = jb.nslab; k < nslot; ++k) { P.out[ns + k].r = dump_r; P.out[ns + k].w = dump_w; }
+                    if (stage == 2 && R > 1) WPS_CHECK(encode_window_tensor(&P.tmap[nj], jb), -3, "cuTensorMapEncodeTiled failed for a window-record array");
                     for (int pk = 0; pk < jb.npack;) {
                         if (in_work == per) {                 // next block
                             ++nwork;
@@ -1741,8 +1776,9 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
             need += (size_t)(q0.s.maxx - q0.s.minx + 1) * (q0.s.maxy - q0.s.miny + 1) * sizeof(int2) + dg.npts() * (sizeof(double) + sizeof(int)) +
                     (size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 2048;
         } else if (!h->disable_fast && (simple_mask || q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT)) {
+            // (missing_value == 0 stays with the exact kernel: a weighted sum can be 0, and the strip kernel carries no such test)
             if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3] && h->precision == WPSGPU_PRECISION_TOLERANCE &&
-                (size_t)(bb[1] - bb[0] + 7) * (size_t)(bb[3] - bb[2] + 7) * 2 <= dg.npts()) {
+                q0.fo.missing_value != 0.0f && (size_t)(bb[1] - bb[0] + 7) * (size_t)(bb[3] - bb[2] + 7) * 2 <= dg.npts()) {
                 // window records over the source cells the grid's points fall into, +-2 / +4 for the 5 x 5 windows; not
                 // clipped to the source array (the pre-pass clamps columns and rows as interp_module.F:1227-1241 does)
                 b.fast = 1; b.bx0 = bb[0] - 2; b.by0 = bb[2] - 2; b.bnx = bb[1] - bb[0] + 7; b.bny = bb[3] - bb[2] + 7;

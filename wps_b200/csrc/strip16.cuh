@@ -24,6 +24,7 @@
 // Zeros are replaced by 1.E-20 in the window records exactly as :1255-1257 does, and a result equal to 1.E-20 becomes 0
 // (:1317).
 #pragma once
+#include <cuda.h>
 #include <type_traits>
 
 namespace wps {
@@ -48,6 +49,7 @@ struct StripJob {
     float msg, fill, masked;
 };
 
+struct StripOut { float* r; int* w; };                 // output plane and new_pts bitmap of one slab (level)
 struct StripSeg { short job, pack0, npk, pad; };       // consecutive packs of one job
 struct StripWork { short seg0, nseg; };                // what one block does: segments [seg0, seg0 + nseg), same geometry
 
@@ -55,9 +57,9 @@ struct StripParams {
     StripJob job[STRIP_MAX_JOBS];
     StripSeg seg[STRIP_MAX_SEGS];
     StripWork work[STRIP_MAX_WORK];
-    float* r_arr[STRIP_MAX_SLABS];
-    int* new_pts[STRIP_MAX_SLABS];
+    StripOut out[STRIP_MAX_SLABS];
     SlowQ sq;
+    alignas(64) CUtensorMap tmap[STRIP_MAX_JOBS];      // STAGE 2: the job's record array as a 3-d tensor (4 * pnx floats, pny, npack)
 };
 
 // ---- pre-pass: window records, guard thresholds and the slow pass's hints ------------------------------------------------
@@ -195,17 +197,22 @@ __global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, 
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
-// predicated stores: the compiler otherwise wraps every `if (ok) store` around a ballot in a branch + reconvergence pair
-__device__ __forceinline__ void st_f32_if(bool p, void* a, float v)
+// predicated stores: the compiler otherwise wraps every `if (ok) store` around a ballot in a branch + reconvergence pair.
+// One predicate serves the four levels of a point.
+__device__ __forceinline__ void st4_f32_if(bool p, float* a0, float* a1, float* a2, float* a3, float v0, float v1, float v2, float v3)
 {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.f32 [%1], %2; }" ::"r"((unsigned)p), "l"(a), "f"(v) : "memory");
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0;\n\t@q st.global.f32 [%1], %5;\n\t@q st.global.f32 [%2], %6;\n\t"
+                 "@q st.global.f32 [%3], %7;\n\t@q st.global.f32 [%4], %8; }"
+                 ::"r"((unsigned)p), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
 }
-__device__ __forceinline__ void st_u32_if(bool p, void* a, unsigned v)
+__device__ __forceinline__ void st4_u32_if(bool p, int* a0, int* a1, int* a2, int* a3, unsigned v)
 {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u32 [%1], %2; }" ::"r"((unsigned)p), "l"(a), "r"(v) : "memory");
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0;\n\t@q st.global.u32 [%1], %5;\n\t@q st.global.u32 [%2], %5;\n\t"
+                 "@q st.global.u32 [%3], %5;\n\t@q st.global.u32 [%4], %5; }"
+                 ::"r"((unsigned)p), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "r"(v) : "memory");
 }
 
-// mbarrier + bulk-copy (TMA engine, SASS UBLKCP) primitives of the window ring
+// mbarrier + bulk-copy (TMA engine; SASS UBLKCP / UTMALDG) primitives of the window ring
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
@@ -220,11 +227,11 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
+        "WAIT_LOOP_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
+        "@p bra WAIT_DONE_%=;\n"
+        "bra WAIT_LOOP_%=;\n"
+        "WAIT_DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar)
@@ -232,26 +239,52 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
     asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// one lane of the (converged) warp, known to the compiler as exactly one: the uniform-datapath copy below needs no lane loop
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0u;
+}
+// one tiled tensor copy: box (SBW cells x SBH rows x 1 pack) of the job's record array, out-of-range cells arrive as 0
+__device__ __forceinline__ void tma_g2s_3d(unsigned dst, const void* tmap, int c0, int c1, int c2, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
 
-// Window ring of the staged variant: each warp (= block) copies the bounding box of its lanes' windows for pack p+2 into
-// shared memory with one bulk copy per box row while pack p is computed -- the north-star design ("each thread block
-// TMA-stages the compact source-grid bounding box its destination tile maps onto").  Box: up to 16 x 8 cells of 16 B.
-constexpr int SBW = 16, SBH = 8, SROW = SBW + 1, SNS = 3;     // row stride 17 cells: rows start in different banks
+// Window ring of the staged variants: each warp (= block) copies the bounding box of its lanes' windows for pack p+2 into
+// shared memory while pack p is computed -- the north-star design ("each thread block TMA-stages the compact source-grid
+// bounding box its destination tile maps onto").  Box: up to 16 x 8 cells of 16 B.
+//   STAGE 1: one bulk copy per box row, issued by lanes 0..bh-1; row stride 17 cells (rows start in different banks)
+//   STAGE 2: ONE tiled tensor copy (cp.async.bulk.tensor.3d through a CUtensorMap of the job's record array), dense 16-cell rows
+constexpr int SBW = 16, SBH = 8, SNS = 3;
 
 #ifndef STRIP_MINB
 #define STRIP_MINB 16      // resident warps (= blocks) per SM the R = 4 kernel is compiled for: 128 registers (12: 0.921 ms, 20: 0.996 ms, 16: 0.907 ms)
 #endif
 
+// flagged points of a strip (rare): kept out of line so that the pack loop carries neither the queue code nor its registers
+__device__ __noinline__ void strip_slow_push(const SlowQ Q, unsigned s0, unsigned s1, unsigned s2, unsigned s3, int gslab, int nl, int idx0, int nx)
+{
+    const int lane = threadIdx.x;
+    if (s0) slowq_push(Q, s0, lane, gslab, nl, idx0);
+    if (s1) slowq_push(Q, s1, lane, gslab, nl, idx0 + nx);
+    if (s2) slowq_push(Q, s2, lane, gslab, nl, idx0 + 2 * nx);
+    if (s3) slowq_push(Q, s3, lane, gslab, nl, idx0 + 3 * nx);
+}
+
 // R points per thread, WIN = window edge (5 when R > 1: cells of a strip may differ by one in each direction; 4 for R = 1).
-// One warp per block.  STAGE: windows come from the shared-memory ring (bulk copies), else straight from L1/L2.
+// One warp per block.  STAGE: 0 = windows straight from L1/L2, 1 / 2 = from the shared-memory ring (see above).
 // A block works through a list of SEGMENTS (consecutive packs of one job); all jobs of the list share the destination grid,
 // the cached coordinates and the record-array geometry, so the level-independent set-up -- cells, weights, window box --
 // is done once per block and only the landmask / fill logic is redone per job.
-template <int R, bool STAGE>
+template <int R, int STAGE>
 __global__ void __launch_bounds__(32, R == 4 ? STRIP_MINB : 20)
 k_metgrid_strip16(const __grid_constant__ StripParams P)
 {
     constexpr int WIN = R > 1 ? 5 : 4;
+    constexpr int SROW = STAGE == 2 ? SBW : SBW + 1;     // cells per ring row
     const StripWork wk = P.work[blockIdx.y];
     const StripJob& gj = P.job[P.seg[wk.seg0].job];      // geometry: identical for every job of the work item
     if ((int)blockIdx.x >= gj.ntiles) return;
@@ -293,12 +326,12 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     float wy[R][WIN];
     __shared__ float4 s_wy[R == 4 ? WIN * 32 : 1];
     unsigned geom = 0;                           // bit p: geo[p]
-    unsigned cfsh0 = 0;                          // 5 bits per point: shift of the point's byte in the flag word, 8 * (dx + 2 dy)
+    unsigned csel0 = 0;                          // nibble p: byte of the flag word that belongs to point p's cell, dx + 2 dy
 #pragma unroll
     for (int p = 0; p < R; ++p) {
         const int di = ci[p] - i0, dj = cj[p] - j0;
         if (geo[p] && (di > WIN - 4 || dj > WIN - 4)) geo[p] = false;     // strip spans more than two cells: slow path
-        if (geo[p]) { geom |= 1u << p; cfsh0 |= (8u * (unsigned)(di + 2 * dj)) << (5 * p); }
+        if (geo[p]) { geom |= 1u << p; csel0 |= (unsigned)(di + 2 * dj) << (4 * p); }
         float w4x[4], w4y[4];
         {
             const float x = fx[p], u = 1.0f - x;
@@ -339,13 +372,14 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     const size_t toff = (size_t)(j0 - gj.py0) * pnx + (i0 - gj.px0);                   // window origin cell: thresholds, flag words
     const size_t woff = (size_t)(j0 - 1 - gj.py0) * pnx + (i0 - 1 - gj.px0);           // window's first cell: records
 
-    // ---- window source: shared-memory ring fed by bulk copies, or global memory directly
+    // ---- window source: shared-memory ring fed by the TMA engine, or global memory directly
     __shared__ alignas(128) float4 s_win[STAGE ? SNS * SBH * SROW : 1];
     __shared__ alignas(8) unsigned long long s_bar[STAGE ? SNS : 1];
+    constexpr unsigned STG_BYTES = SBH * SROW * 16;
     bool staged = false;
-    int bw = 0, bh = 0;
+    int bw = 0, bh = 0, bc0 = 0, bc1 = 0;
     size_t boff = 0;
-    const float4* sw_ = s_win;
+    unsigned sw_off = 0;                         // byte offset of the lane's window inside a ring stage
     if (STAGE) {
         // bounding box of the warp's windows (lanes without a usable point do not count)
         const int bi0 = __reduce_min_sync(0xffffffffu, anygeo ? i0 - 1 : INT_MAX);
@@ -355,8 +389,9 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
         bw = bi1 - bi0 + 1; bh = bj1 - bj0 + 1;
         staged = bi0 != INT_MAX && bw <= SBW && bh <= SBH;
         if (staged) {
-            boff = (size_t)(bj0 - gj.py0 + (lane < bh ? lane : 0)) * pnx + (bi0 - gj.px0);    // lane r copies box row r
-            if (anygeo) sw_ = s_win + (j0 - 1 - bj0) * SROW + (i0 - 1 - bi0);
+            boff = (size_t)(bj0 - gj.py0 + (lane < bh ? lane : 0)) * pnx + (bi0 - gj.px0);    // STAGE 1: lane r copies box row r
+            bc0 = 4 * (bi0 - gj.px0); bc1 = bj0 - gj.py0;                                     // STAGE 2: box origin in tensor coordinates
+            if (anygeo) sw_off = (unsigned)(((j0 - 1 - bj0) * SROW + (i0 - 1 - bi0)) * 16);
         }
     }
     const unsigned bar0 = smem_u32(s_bar), win0 = smem_u32(s_win);
@@ -368,22 +403,22 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
         }
         __syncwarp();
     }
-    // Output addressing: byte offsets of the strip's first point / bitmap word; the per-level base pointers are warp-uniform
-    // (constant bank).  Levels past a job's last one have their pointers aimed at a dump area by the host, so the pack loop
-    // has no level test at all; stores are predicated, not branched around.
+    // Output addressing: element index of the strip's points / bitmap words (32-bit: a plane has fewer than 2^31 points), so
+    // that an address is one IMAD.WIDE on a level's base pointer.  Levels past a job's last one have their pointers aimed at
+    // a dump area by the host, so the pack loop has no level test at all; stores are predicated, not branched around.
     const unsigned colw = __ballot_sync(0xffffffffu, ii < nx);   // lanes inside the grid
     const unsigned rowsm = (1u << min(R, ny - jj0)) - 1u;     // rows of the strip that exist
-    const unsigned poff0 = (unsigned)(((size_t)jj0 * nx + ii) * sizeof(float)), prow = (unsigned)(nx * sizeof(float));
-    const unsigned woff0 = (unsigned)(((size_t)jj0 * gj.nxw + tx) * sizeof(int)), wrow = (unsigned)(gj.nxw * sizeof(int));
-    int it0 = 0;                                 // packs this block has taken through the ring so far (stage / phase bookkeeping)
+    const int idx0 = jj0 * nx + ii;
+    const int widx = (jj0 + (lane < R ? lane : 0)) * gj.nxw + tx;     // lane p < R writes the bitmap words of strip row p
+    const bool wrow = lane < R && ((rowsm >> lane) & 1u);
+    unsigned stg = 0, par = 0;                   // ring stage of the next pack to be consumed and its barrier phase
 
     for (int sg = 0; sg < wk.nseg; ++sg) {
         const StripSeg seg = P.seg[wk.seg0 + sg];
         const StripJob& jb = P.job[seg.job];
-        const bool msg0 = jb.msg == 0.0f;
         // ---- the job's point logic (interp_met_field :2490-2541): process_bdy_width interior and landmask == masked
         // receive fill_missing; masked=both selects the interp mask (flag nibble) by the landmask
-        unsigned fillm = 0, fastm = geom, cfsh = cfsh0;
+        unsigned fillm = 0, fastm = geom, nibm = 0;
         {
             const int pw = jb.pw, di = jb.sm1 + ii;
             const bool fill_i = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw;
@@ -393,31 +428,49 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                 const bool act = ii < nx && jj < ny;
                 const float lm = jb.has_lm ? __ldg(jb.landmask + (size_t)min(jj, ny - 1) * nx + min(ii, nx - 1)) : 0.0f;
                 bool fill = fill_i && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw, lm_ok = true;
+                bool hi_nib = false;
                 if (jb.both) {
-                    if (lm == 1.0f) cfsh += 4u << (5 * p);      // land point: interp_water_mask, flag bits 4-7
+                    hi_nib = lm == 1.0f;                        // land point: interp_water_mask, flag bits 4-7
                     lm_ok = lm == 0.0f || lm == 1.0f;
                 } else fill = fill || (jb.has_lm && lm == jb.masked);
                 if (fill && act) fillm |= 1u << p;
                 if (fill || !lm_ok) fastm &= ~(1u << p);
+                nibm |= (hi_nib ? 0xf0u : 0x0fu) << (8 * p);
             }
         }
+        // flag test of a pack in two instructions: byte p of prmt(flag word, 0, csel) is the flag byte of point p's stencil
+        // (a zero byte for points that cannot take the window path); the point is clean iff its nibble is all ones
+        unsigned csel = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) csel |= (p < R && ((fastm >> p) & 1u) ? ((csel0 >> (4 * p)) & 3u) : 4u) << (4 * p);
         const bool anyfill = __any_sync(0xffffffffu, fillm != 0u);
         const float fillv = jb.fill;
+        const int nslab = jb.nslab, gslab0 = jb.gslab0;
         const float4* __restrict__ Ta = jb.TA + (size_t)seg.pack0 * pstride + toff;
         const unsigned* __restrict__ cfp = jb.cf + (size_t)seg.pack0 * pstride + toff;
         const float4* __restrict__ Pw = jb.P + (size_t)seg.pack0 * pstride + woff;
         const float4* Pbox = jb.P + (size_t)seg.pack0 * pstride + boff;
+        const void* tmap = &P.tmap[seg.job];
         const int npk = seg.npk;
-        const int slab00 = jb.slab0 + seg.pack0 * 4;
-        auto issue = [&](int pk) {      // bulk copies of the segment's pack pk box rows into the next ring stage
-            const int st = (it0 + pk) % SNS;
-            if (lane == 0) mbar_expect_tx(bar0 + 8 * st, (unsigned)(bw * bh * 16));
-            __syncwarp();
-            if (lane < bh) bulk_g2s(win0 + (unsigned)((st * SBH + lane) * SROW * 16), Pbox + (size_t)pk * pstride, (unsigned)(bw * 16), bar0 + 8 * st);
+        const StripOut* outp = P.out + jb.slab0 + seg.pack0 * 4;
+        // copy of the segment's pack pk box into ring stage st
+        auto issue = [&](int pk, unsigned st) {
+            const unsigned bar = bar0 + 8 * st;
+            if (STAGE == 2) {
+                if (elect_one()) {
+                    mbar_expect_tx(bar, (unsigned)(SBW * SBH * 16));
+                    tma_g2s_3d(win0 + st * STG_BYTES, tmap, bc0, bc1, seg.pack0 + pk, bar);
+                }
+            } else {
+                if (lane == 0) mbar_expect_tx(bar, (unsigned)(bw * bh * 16));
+                __syncwarp();
+                if (lane < bh) bulk_g2s(win0 + st * STG_BYTES + (unsigned)(lane * SROW * 16), Pbox + (size_t)pk * pstride, (unsigned)(bw * 16), bar);
+            }
         };
         if (STAGE && staged) {
             __syncwarp();                            // the previous segment's last stages have been read by every lane
-            for (int pk = 0; pk < SNS - 1 && pk < npk; ++pk) issue(pk);
+            unsigned st = stg;
+            for (int pk = 0; pk < SNS - 1 && pk < npk; ++pk) { issue(pk, st); st = st + 1 == SNS ? 0 : st + 1; }
         }
         float4 ta = __ldg(Ta);
         unsigned cfv = __ldg(cfp);                   // flag word of the window origin for the pack
@@ -425,6 +478,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
         // the pack loop exists twice (windows from the ring / from global memory) so that neither carries the other's loads
         auto packs = [&](auto direct_tag) {
             constexpr bool DIRECT = decltype(direct_tag)::value;
+#pragma unroll 1
             for (int pk = 0; pk < npk; ++pk) {
                 const float4 cta = ta;
                 const unsigned ccf = cfv;
@@ -433,26 +487,34 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                     ta = __ldg(Ta);
                     cfv = __ldg(cfp);
                 }
-                const int stg = (it0 + pk) % SNS;
+                unsigned swa = 0;
                 if (!DIRECT) {
+                    const unsigned prev = stg == 0 ? SNS - 1 : stg - 1;
                     __syncwarp();                        // every lane has finished reading the stage that is refilled now
-                    if (pk + SNS - 1 < npk) issue(pk + SNS - 1);
-                    mbar_wait(bar0 + 8 * stg, (unsigned)(((it0 + pk) / SNS) & 1));
+                    if (pk + SNS - 1 < npk) issue(pk + SNS - 1, prev);
+                    mbar_wait(bar0 + 8 * stg, par);
+                    swa = win0 + stg * STG_BYTES + sw_off;
+                    stg = stg + 1 == SNS ? 0 : stg + 1;
+                    par ^= stg == 0 ? 1u : 0u;
                 }
-                const float4* __restrict__ sw = sw_ + stg * SBH * SROW;
                 float2 a01[R], a23[R];
                 bool g[R];                               // the guard holds for every row and level of point p so far
+                // the point's stencil must be clean for all four levels (under the mask the landmask selects, masked=both)
+                const unsigned dirty = ~__byte_perm(ccf, 0u, csel) & nibm;
 #pragma unroll
                 for (int p = 0; p < R; ++p) {
                     a01[p] = make_float2(0.0f, 0.0f); a23[p] = a01[p];
-                    // the point's stencil must be clean for all four levels (under the mask the landmask selects, masked=both)
-                    g[p] = ((fastm >> p) & 1u) && ((ccf >> ((cfsh >> (5 * p)) & 31u)) & 0xfu) == 0xfu;
+                    g[p] = (dirty & (0xffu << (8 * p))) == 0u;
                 }
 #pragma unroll
                 for (int l = 0; l < WIN; ++l) {
                     float4 v[WIN];
 #pragma unroll
-                    for (int k = 0; k < WIN; ++k) v[k] = DIRECT ? __ldg(Pw + l * pnx + k) : sw[l * SROW + k];
+                    for (int k = 0; k < WIN; ++k) {
+                        if (DIRECT) v[k] = __ldg(Pw + l * pnx + k);
+                        else asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[k].x), "=f"(v[k].y), "=f"(v[k].z), "=f"(v[k].w)
+                                          : "r"(swa + (unsigned)((l * SROW + k) * 16)));
+                    }
                     float wyr[R];
                     if (R == 4) {
                         const float4 w4 = s_wy[l * 32 + lane];
@@ -478,65 +540,57 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                 if (DIRECT) Pw += pstride;
                 // ---- outputs.  The guard is joint over the pack's four levels: a point either delivers all of them or hands
                 // all of them to the slow pass, so one ballot per point serves the pack.
-                const int sl0 = slab00 + pk * 4;
-                const bool standin = __any_sync(0xffffffffu, cta.x == 1.0e-21f || cta.y == 1.0e-21f || cta.z == 1.0e-21f || cta.w == 1.0e-21f);
+                // a result equal to the zero stand-in becomes 0 (:1317): possible only where a whole window consists of
+                // stand-ins, i.e. its threshold sits at the 1e-21 floor (warp-uniform test, one branch per pack)
+                if (__any_sync(0xffffffffu, cta.x == 1.0e-21f || cta.y == 1.0e-21f || cta.z == 1.0e-21f || cta.w == 1.0e-21f)) {
+#pragma unroll
+                    for (int p = 0; p < R; ++p) {
+                        a01[p].x = a01[p].x == 1.0e-20f ? 0.0f : a01[p].x; a01[p].y = a01[p].y == 1.0e-20f ? 0.0f : a01[p].y;
+                        a23[p].x = a23[p].x == 1.0e-20f ? 0.0f : a23[p].x; a23[p].y = a23[p].y == 1.0e-20f ? 0.0f : a23[p].y;
+                    }
+                }
+                // "value /= missing_value" (:2558) needs no test: jobs with missing_value == 0 never come here (host), and the
+                // pre-pass sends windows whose magnitudes come near |missing_value| to the slow path
+                if (anyfill) {                           // warp-uniform: fill_missing points exist in this strip row group
+#pragma unroll
+                    for (int p = 0; p < R; ++p) {
+                        const bool f = (fillm >> p) & 1u;
+                        a01[p].x = f ? fillv : a01[p].x; a01[p].y = f ? fillv : a01[p].y;
+                        a23[p].x = f ? fillv : a23[p].x; a23[p].y = f ? fillv : a23[p].y;
+                        g[p] = g[p] || f;
+                    }
+                }
+                const StripOut o0 = outp[0], o1 = outp[1], o2 = outp[2], o3 = outp[3];
+                outp += 4;
                 unsigned word[R];
 #pragma unroll
                 for (int p = 0; p < R; ++p) {
-                    float r0 = a01[p].x, r1 = a01[p].y, r2 = a23[p].x, r3 = a23[p].y;
-                    bool ok = g[p];
-                    // a result equal to the zero stand-in becomes 0 (:1317): possible only where a whole window consists of
-                    // stand-ins, i.e. its threshold sits at the 1e-21 floor (warp-uniform test)
-                    if (standin) {
-                        r0 = r0 == 1.0e-20f ? 0.0f : r0; r1 = r1 == 1.0e-20f ? 0.0f : r1;
-                        r2 = r2 == 1.0e-20f ? 0.0f : r2; r3 = r3 == 1.0e-20f ? 0.0f : r3;
-                    }
-                    // "value /= missing_value" (:2558): only a missing_value of 0 can be met by a weighted sum of usable
-                    // values (the pre-pass sends windows whose magnitudes come near |missing_value| to the slow path)
-                    if (msg0) ok = ok && r0 != 0.0f && r1 != 0.0f && r2 != 0.0f && r3 != 0.0f;
-                    if (anyfill) {                       // warp-uniform: fill_missing points exist in this strip row group
-                        const bool f = (fillm >> p) & 1u;
-                        r0 = f ? fillv : r0; r1 = f ? fillv : r1; r2 = f ? fillv : r2; r3 = f ? fillv : r3;
-                        ok = ok || f;
-                    }
-                    // (level base + p rows) is warp-uniform arithmetic; the lane adds its own offset
-                    st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 0]) + (size_t)p * prow + poff0, r0);
-                    st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 1]) + (size_t)p * prow + poff0, r1);
-                    st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 2]) + (size_t)p * prow + poff0, r2);
-                    st_f32_if(ok, reinterpret_cast<char*>(P.r_arr[sl0 + 3]) + (size_t)p * prow + poff0, r3);
-                    word[p] = __ballot_sync(0xffffffffu, ok);
+                    const int idx = idx0 + p * nx;
+                    st4_f32_if(g[p], o0.r + idx, o1.r + idx, o2.r + idx, o3.r + idx, a01[p].x, a01[p].y, a23[p].x, a23[p].y);
+                    word[p] = __ballot_sync(0xffffffffu, g[p]);
                 }
                 {
                     // flagged points (rare): one warp-uniform test per pack, the queue code stays out of the way
+                    unsigned sw[4] = { 0u, 0u, 0u, 0u };
                     unsigned any = 0;
 #pragma unroll
-                    for (int p = 0; p < R; ++p) any |= (((rowsm >> p) & 1u) ? colw : 0u) & ~word[p];
+                    for (int p = 0; p < R; ++p) { sw[p] = (((rowsm >> p) & 1u) ? colw : 0u) & ~word[p]; any |= sw[p]; }
                     if (any) {
-                        const int nl = min(4, jb.nslab - (seg.pack0 + pk) * 4);
-#pragma unroll 1
-                        for (int p = 0; p < R; ++p) {
-                            const unsigned sword = (((rowsm >> p) & 1u) ? colw : 0u) & ~word[p];
-                            if (sword) slowq_push(P.sq, sword, lane, jb.gslab0 + (seg.pack0 + pk) * 4, nl, (int)((poff0 >> 2) + p * nx));
-                        }
+                        const int pk0 = seg.pack0 + pk;
+                        strip_slow_push(P.sq, sw[0], sw[1], sw[2], sw[3], gslab0 + pk0 * 4, min(4, nslab - pk0 * 4), idx0, nx);
                     }
                 }
-                if (lane < R) {
+                {
                     // lane p writes the new_pts words of strip row p for the four levels
                     unsigned w = word[0];
 #pragma unroll
-                    for (int p = 1; p < R; ++p) if (lane == p) w = word[p];
-                    const unsigned wo = woff0 + (unsigned)lane * wrow;
-                    const bool rowok = (rowsm >> lane) & 1u;
-                    st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 0]) + wo, w);
-                    st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 1]) + wo, w);
-                    st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 2]) + wo, w);
-                    st_u32_if(rowok, reinterpret_cast<char*>(P.new_pts[sl0 + 3]) + wo, w);
+                    for (int p = 1; p < R; ++p) w = lane == p ? word[p] : w;
+                    st4_u32_if(wrow, o0.w + widx, o1.w + widx, o2.w + widx, o3.w + widx, w);
                 }
             }
         };
         if (STAGE && staged) packs(std::false_type{});
         else packs(std::true_type{});
-        it0 += npk;
     }
 }
 
