@@ -872,6 +872,40 @@ static bool same_group(const QueuedSlab& a, const QueuedSlab& b)
            x.field_stagger == y.field_stagger && x.use_landmask == y.use_landmask && x.process_bdy_width == y.process_bdy_width;
 }
 
+// strip jobs that share the destination grid, the cached coordinates and the record-array geometry form a class: a block
+// does the level-independent set-up once for all of them, and their window records lie back to back in the arena
+static bool strip_same_geometry(const Job& a, const Job& b)
+{
+    return a.strip == b.strip && a.xy == b.xy && a.nx == b.nx && a.ny == b.ny && a.sm1 == b.sm1 && a.sm2 == b.sm2 && a.bx0 == b.bx0 && a.by0 == b.by0 &&
+           a.bnx == b.bnx && a.bny == b.bny && a.minx == b.minx && a.maxx == b.maxx && a.miny == b.miny && a.maxy == b.maxy && a.bdr == b.bdr;
+}
+
+// Window records, thresholds and flag words of the strip jobs: ONE block of each per geometry class, the jobs' arrays back to
+// back in job order, so that a kernel block walks a contiguous range of packs whatever job they belong to.
+static int alloc_strip_records(wpsgpu_ctx* h, std::vector<Job>& jobs)
+{
+    std::vector<char> done(jobs.size(), 0);
+    for (size_t a = 0; a < jobs.size(); ++a) {
+        if (done[a] || jobs[a].fast != 1 || jobs[a].strip <= 0) continue;
+        size_t packs = 0;
+        std::vector<size_t> cls;
+        for (size_t b = a; b < jobs.size(); ++b)
+            if (!done[b] && jobs[b].fast == 1 && jobs[b].strip > 0 && strip_same_geometry(jobs[a], jobs[b])) { cls.push_back(b); packs += jobs[b].npack; }
+        const size_t cells = (size_t)jobs[a].bnx * jobs[a].bny;
+        float4* rec = (float4*)h->arena.take(packs * cells * sizeof(float4));
+        float4* thr = (float4*)h->arena.take(packs * cells * sizeof(float4));
+        unsigned* cfw = (unsigned*)h->arena.take(packs * cells * sizeof(unsigned));
+        WPS_CHECK(rec && thr && cfw, -3, "device arena exhausted (window records)");
+        size_t q = 0;
+        for (size_t b : cls) {
+            done[b] = 1;
+            jobs[b].rec = rec + q * cells; jobs[b].thr = thr + q * cells; jobs[b].cfw = cfw + q * cells;
+            q += jobs[b].npack;
+        }
+    }
+    return 0;
+}
+
 // Tolerance-mode sixteen_pt jobs of one pass -> as few strip launches as the parameter block allows.
 template <int R>
 static void launch_strip_kernel(const StripParams& sp, unsigned tiles, unsigned nwork, int stage, cudaStream_t st)
@@ -901,11 +935,11 @@ static EncodeTiledFn tensor_map_encoder()
 
 // The window records of a strip job, [npack][pny][pnx] float4, as the tensor the ring's tiled copies read: box = SBW cells x
 // SBH rows x 1 pack, cells past the array's edge arrive as zeros (they belong to no lane's window).
-static bool encode_window_tensor(CUtensorMap* tm, const Job& jb)
+static bool encode_window_tensor(CUtensorMap* tm, const Job& jb, int packs)
 {
     EncodeTiledFn enc = tensor_map_encoder();
     if (!enc) return false;
-    const cuuint64_t dims[3] = { (cuuint64_t)jb.bnx * 4, (cuuint64_t)jb.bny, (cuuint64_t)jb.npack };
+    const cuuint64_t dims[3] = { (cuuint64_t)jb.bnx * 4, (cuuint64_t)jb.bny, (cuuint64_t)packs };
     const cuuint64_t strides[2] = { (cuuint64_t)jb.bnx * 16, (cuuint64_t)jb.bnx * jb.bny * 16 };
     const cuuint32_t box[3] = { SBW * 4, SBH, 1 }, estr[3] = { 1, 1, 1 };
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float4*>(jb.rec), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -919,11 +953,8 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
     int stage = env_int("WPSGPU_STRIP_STAGE", 2, 0, 2);
     if (stage == 2 && !tensor_map_encoder()) stage = 1;
     const int work_packs = env_int("WPSGPU_STRIP_CHUNK", 32, 1, 64);    // packs per block
-    // jobs that share the destination grid, the cached coordinates and the record-array geometry form a class: a block
-    // does the level-independent set-up once for all of them
-    auto same_geometry = [](const Job& a, const Job& b) {
-        return a.xy == b.xy && a.nx == b.nx && a.ny == b.ny && a.sm1 == b.sm1 && a.sm2 == b.sm2 && a.bx0 == b.bx0 && a.by0 == b.by0 &&
-               a.bnx == b.bnx && a.bny == b.bny && a.minx == b.minx && a.maxx == b.maxx && a.miny == b.miny && a.maxy == b.maxy && a.bdr == b.bdr;
+    auto same_logic = [](const Job& a, const Job& b) {      // what the per-segment point logic of the kernel reads
+        return a.pw == b.pw && (a.landmask != nullptr) == (b.landmask != nullptr) && memcmp(&a.masked, &b.masked, sizeof(float)) == 0;
     };
     for (int R : { 4, 2, 1 }) {
         std::vector<int> todo;
@@ -931,8 +962,9 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
         while (!todo.empty()) {
             // one launch: classes are taken whole as long as the parameter block has room
             StripParams P;
+            const Job* seg_job[STRIP_MAX_JOBS] = {};
             P.sq = sq;
-            int nj = 0, ns = 0, nseg = 0, nwork = 0;
+            int nj = 0, ns = 0, nseg = 0, nwork = 0, ncls = 0;
             unsigned tiles = 0;
             std::vector<int> rest;
             std::vector<char> taken(todo.size(), 0);
@@ -942,28 +974,36 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                 // the class of todo[a]
                 std::vector<int> cls;
                 for (size_t b = a; b < todo.size(); ++b)
-                    if (!taken[b] && same_geometry(jobs[todo[a]], jobs[todo[b]])) cls.push_back((int)b);
+                    if (!taken[b] && strip_same_geometry(jobs[todo[a]], jobs[todo[b]])) cls.push_back((int)b);
                 int c_slots = 0, c_packs = 0;
                 for (int b : cls) { c_slots += jobs[todo[b]].npack * 4; c_packs += jobs[todo[b]].npack; }
                 const int c_work = (c_packs + work_packs - 1) / work_packs;
                 const int c_seg = (int)cls.size() + c_work;       // upper bound: every cut adds a segment
                 WPS_CHECK((int)cls.size() <= STRIP_MAX_JOBS && c_slots <= STRIP_MAX_SLABS && c_seg <= STRIP_MAX_SEGS && c_work <= STRIP_MAX_WORK, -3,
                           "sixteen_pt jobs of one grid too large for one strip launch");
-                if (nj + (int)cls.size() > STRIP_MAX_JOBS || ns + c_slots > STRIP_MAX_SLABS || nseg + c_seg > STRIP_MAX_SEGS || nwork + c_work > STRIP_MAX_WORK) {
+                if (nj + (int)cls.size() > STRIP_MAX_JOBS || ns + c_slots > STRIP_MAX_SLABS || nseg + c_seg > STRIP_MAX_SEGS || nwork + c_work > STRIP_MAX_WORK ||
+                    ncls + 1 > STRIP_MAX_CLS) {
                     full = true;
                     break;
                 }
                 // work items of equal size (e.g. 29 packs -> 15 + 14), cut across the class's jobs
                 const int per = (c_packs + c_work - 1) / c_work;
-                int in_work = 0;
-                P.work[nwork].seg0 = (short)nseg; P.work[nwork].nseg = 0;
+                int in_work = 0, cq = 0;                       // cq: class-relative index of the next pack
+                const Job& j0 = jobs[todo[cls[0]]];
+                const size_t cells = (size_t)j0.bnx * j0.bny;
+                P.cls[ncls].P = j0.rec; P.cls[ncls].TA = j0.thr; P.cls[ncls].cf = j0.cfw;
+                if (stage == 2 && R > 1) WPS_CHECK(encode_window_tensor(&P.tmap[ncls], j0, c_packs), -3, "cuTensorMapEncodeTiled failed for a window-record array");
+                P.work[nwork].seg0 = (short)nseg; P.work[nwork].nseg = 0; P.work[nwork].cls = (short)ncls; P.work[nwork].npk = 0; P.work[nwork].q0 = 0;
+                const float* cls_lm = nullptr;                // one grid, one landmask
+                for (int b : cls) if (jobs[todo[b]].landmask) cls_lm = jobs[todo[b]].landmask;
                 for (int b : cls) {
                     taken[b] = 1;
                     const Job& jb = jobs[todo[b]];
                     const bool jboth = jb.landmask != nullptr && jb.masked == WPSGPU_MASKED_BOTH;
                     const int nslot = jb.npack * 4;          // levels past the last one write to the dump area
                     StripJob& q = P.job[nj];
-                    q.xy = jb.xy; q.landmask = jb.landmask; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cfw;
+                    seg_job[nj] = &jb;
+                    q.xy = jb.xy; q.landmask = jb.landmask; q.landmask_cls = cls_lm; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cfw;
                     q.nx = jb.nx; q.ny = jb.ny; q.nxw = jb.nxw; q.sm1 = jb.sm1; q.sm2 = jb.sm2;
                     q.sd1 = jb.sd1; q.ed1 = jb.ed1; q.sd2 = jb.sd2; q.ed2 = jb.ed2; q.pw = jb.pw;
                     q.minx = jb.minx; q.maxx = jb.maxx; q.miny = jb.miny; q.maxy = jb.maxy; q.bdr = jb.bdr;
@@ -977,23 +1017,31 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                         P.out[ns + k].r = p.r_arr; P.out[ns + k].w = p.new_pts;
                     }
                     for (int k = jb.nslab; k < nslot; ++k) { P.out[ns + k].r = dump_r; P.out[ns + k].w = dump_w; }
-                    if (stage == 2 && R > 1) WPS_CHECK(encode_window_tensor(&P.tmap[nj], jb), -3, "cuTensorMapEncodeTiled failed for a window-record array");
+                    WPS_CHECK(jb.rec == j0.rec + (size_t)cq * cells && jb.thr == j0.thr + (size_t)cq * cells && jb.cfw == j0.cfw + (size_t)cq * cells, -3,
+                              "window records of a geometry class are not contiguous");
                     for (int pk = 0; pk < jb.npack;) {
                         if (in_work == per) {                 // next block
                             ++nwork;
-                            P.work[nwork].seg0 = (short)nseg; P.work[nwork].nseg = 0;
+                            P.work[nwork].seg0 = (short)nseg; P.work[nwork].nseg = 0; P.work[nwork].cls = (short)ncls; P.work[nwork].npk = 0;
+                            P.work[nwork].q0 = cq;
                             in_work = 0;
                         }
                         const int n = std::min(per - in_work, jb.npack - pk);
                         StripSeg& sgm = P.seg[nseg++];
-                        sgm.job = (short)nj; sgm.pack0 = (short)pk; sgm.npk = (short)n; sgm.pad = 0;
+                        sgm.job = (short)nj; sgm.pack0 = (short)pk; sgm.npk = (short)n;
+                        sgm.same = 0;
+                        if (P.work[nwork].nseg > 0) {
+                            const StripSeg& prev = P.seg[nseg - 2];
+                            sgm.same = (short)(prev.job == sgm.job || same_logic(jb, *seg_job[prev.job]) ? 1 : 0);
+                        }
                         P.work[nwork].nseg++;
-                        in_work += n; pk += n;
+                        P.work[nwork].npk = (short)(P.work[nwork].npk + n);
+                        in_work += n; pk += n; cq += n;
                     }
                     tiles = std::max(tiles, (unsigned)q.ntiles);
                     ns += nslot; nj++;
                 }
-                ++nwork;
+                ++nwork; ++ncls;
             }
             for (size_t a = 0; a < todo.size(); ++a) if (!taken[a]) rest.push_back(todo[a]);
             if (nwork > 0) {
@@ -1287,11 +1335,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         jb.fast = bx.fast; jb.bx0 = bx.bx0; jb.by0 = bx.by0; jb.bnx = bx.bnx; jb.bny = bx.bny; jb.npack = bx.npack;
         jb.strip = bx.fast == 1 ? bx.strip : 0;
         if (jb.fast == 1 && jb.strip > 0) {
-            const size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
-            jb.rec = (const float4*)h->arena.take(cells * sizeof(float4));
-            jb.thr = (const float4*)h->arena.take(cells * sizeof(float4));
-            jb.cfw = (const unsigned*)h->arena.take(cells * sizeof(unsigned));
-            WPS_CHECK(jb.rec && jb.thr && jb.cfw, -3, "device arena exhausted (window records)");
+            // window records: allocated per geometry class after this loop (alloc_strip_records)
         } else if (jb.fast == 1) {
             size_t cells = (size_t)jb.npack * jb.bnx * jb.bny;
             size_t cells8 = (size_t)jb.npack * ((jb.bnx + 7) / 8 * 8) * jb.bny;
@@ -1409,6 +1453,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         fs.staged[decode_hosts[k]] = t.out;
         decode_max = std::max(decode_max, n);
     }
+    WPS_TRY(alloc_strip_records(h, jobs));
     for (const auto& pr : decode_pending) sp[pr.first].src = (const float*)fs.staged[pr.second];
     for (const CopyRun& r : in_runs) { WPS_CUDA(cudaMemcpyAsync(r.d, r.h, r.bytes, cudaMemcpyHostToDevice, s_in)); h->h2d_bytes += (int64_t)r.bytes; }
     // All tables of this pass travel in ONE copy: [jobs | slab pointers | six int lists of njobs+1 entries]

@@ -37,6 +37,7 @@ constexpr int STRIP_MAX_WORK = 96;
 struct StripJob {
     const float2* xy;
     const float* landmask;
+    const float* landmask_cls;   // the landmask of the grid if ANY job of the geometry class uses one (loaded once per block)
     const float4* P;             // window records [npack][pny][pnx], float4 = 4 levels of source cell (px0 + c, py0 + r), clamped like :1227-1241
     const float4* TA;            // guard thresholds per window ORIGIN cell, same index space
     const unsigned* cf;          // per (pack, cell): flag bytes of the four stencils a strip with this window origin can use (k_pack_win)
@@ -50,8 +51,12 @@ struct StripJob {
 };
 
 struct StripOut { float* r; int* w; };                 // output plane and new_pts bitmap of one slab (level)
-struct StripSeg { short job, pack0, npk, pad; };       // consecutive packs of one job
-struct StripWork { short seg0, nseg; };                // what one block does: segments [seg0, seg0 + nseg), same geometry
+struct StripSeg { short job, pack0, npk, same; };      // consecutive packs of one job; same: point logic (fill, landmask use) as the segment before
+// what one block does: segments [seg0, seg0 + nseg) of one geometry class = packs [q0, q0 + npk) of the class arrays
+struct StripWork { short seg0, nseg, cls, npk; int q0; };
+// window records / thresholds / flag words of a geometry class: the arrays of its jobs back to back, [class packs][pny][pnx]
+struct StripClass { const float4* P; const float4* TA; const unsigned* cf; };
+constexpr int STRIP_MAX_CLS = 8;
 
 struct StripParams {
     StripJob job[STRIP_MAX_JOBS];
@@ -59,7 +64,8 @@ struct StripParams {
     StripWork work[STRIP_MAX_WORK];
     StripOut out[STRIP_MAX_SLABS];
     SlowQ sq;
-    alignas(64) CUtensorMap tmap[STRIP_MAX_JOBS];      // STAGE 2: the job's record array as a 3-d tensor (4 * pnx floats, pny, npack)
+    StripClass cls[STRIP_MAX_CLS];
+    alignas(64) CUtensorMap tmap[STRIP_MAX_CLS];       // STAGE 2: a class's record array as a 3-d tensor (4 * pnx floats, pny, class packs)
 };
 
 // ---- pre-pass: window records, guard thresholds and the slow pass's hints ------------------------------------------------
@@ -412,21 +418,64 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     const int widx = (jj0 + (lane < R ? lane : 0)) * gj.nxw + tx;     // lane p < R writes the bitmap words of strip row p
     const bool wrow = lane < R && ((rowsm >> lane) & 1u);
     unsigned stg = 0, par = 0;                   // ring stage of the next pack to be consumed and its barrier phase
+    // landmask of the strip's points, once per block (every job of the class that uses one uses the grid's)
+    float lmv[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) lmv[p] = gj.landmask_cls ? __ldg(gj.landmask_cls + (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1)) : 0.0f;
 
+    // The window records, thresholds and flag words of all jobs of a geometry class lie back to back (host), so the block's
+    // packs are ONE contiguous range [q0, q0 + nq) of the class arrays, across segment (job) boundaries: the ring copy of the
+    // pack two ahead and the threshold / flag loads of the next pack never look at the segment table.
+    const StripClass& cl = P.cls[wk.cls];
+    const int nq = wk.npk;
+    const void* tmap = &P.tmap[wk.cls];
+    const float4* Pbox = cl.P + (size_t)wk.q0 * pstride + boff;
+    int iq = 0;                                  // packs issued to the ring so far
+    auto issue_next = [&](unsigned st) {
+        if (iq < nq) {
+            const unsigned bar = bar0 + 8 * st;
+            if (STAGE == 2) {
+                if (elect_one()) {
+                    mbar_expect_tx(bar, (unsigned)(SBW * SBH * 16));
+                    tma_g2s_3d(win0 + st * STG_BYTES, tmap, bc0, bc1, wk.q0 + iq, bar);
+                }
+            } else {
+                if (lane == 0) mbar_expect_tx(bar, (unsigned)(bw * bh * 16));
+                __syncwarp();
+                if (lane < bh) bulk_g2s(win0 + st * STG_BYTES + (unsigned)(lane * SROW * 16), Pbox + (size_t)iq * pstride, (unsigned)(bw * 16), bar);
+            }
+            ++iq;
+        }
+    };
+    if (STAGE && staged) {
+#pragma unroll
+        for (int st = 0; st < SNS - 1; ++st) issue_next((unsigned)st);
+    }
+    const float4* __restrict__ Ta = cl.TA + (size_t)wk.q0 * pstride + toff;
+    const unsigned* __restrict__ cfp = cl.cf + (size_t)wk.q0 * pstride + toff;
+    const float4* __restrict__ Pw = cl.P + (size_t)wk.q0 * pstride + woff;
+    float4 ta = __ldg(Ta);                       // thresholds and flag word of the first pack; later ones one iteration ahead
+    unsigned cfv = __ldg(cfp);
+    int qleft = nq;                              // packs of the block still to be computed, the current one included
+
+    unsigned fillm = 0, nibm = 0, csel = 0;
+    bool anyfill = false;
     for (int sg = 0; sg < wk.nseg; ++sg) {
         const StripSeg seg = P.seg[wk.seg0 + sg];
         const StripJob& jb = P.job[seg.job];
         // ---- the job's point logic (interp_met_field :2490-2541): process_bdy_width interior and landmask == masked
-        // receive fill_missing; masked=both selects the interp mask (flag nibble) by the landmask
-        unsigned fillm = 0, fastm = geom, nibm = 0;
-        {
+        // receive fill_missing; masked=both selects the interp mask (flag nibble) by the landmask.  Skipped when the host
+        // found the previous segment's job to have the same settings (the levels of TT, RH, GHT ...).
+        if (sg == 0 || !seg.same) {
+            unsigned fastm = geom;
+            fillm = 0; nibm = 0;
             const int pw = jb.pw, di = jb.sm1 + ii;
             const bool fill_i = abs(di - jb.sd1) >= pw && abs(di - jb.ed1) >= pw;
 #pragma unroll
             for (int p = 0; p < R; ++p) {
                 const int jj = jj0 + p, dj = jb.sm2 + jj;
                 const bool act = ii < nx && jj < ny;
-                const float lm = jb.has_lm ? __ldg(jb.landmask + (size_t)min(jj, ny - 1) * nx + min(ii, nx - 1)) : 0.0f;
+                const float lm = jb.has_lm ? lmv[p] : 0.0f;
                 bool fill = fill_i && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw, lm_ok = true;
                 bool hi_nib = false;
                 if (jb.both) {
@@ -437,43 +486,17 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                 if (fill || !lm_ok) fastm &= ~(1u << p);
                 nibm |= (hi_nib ? 0xf0u : 0x0fu) << (8 * p);
             }
-        }
-        // flag test of a pack in two instructions: byte p of prmt(flag word, 0, csel) is the flag byte of point p's stencil
-        // (a zero byte for points that cannot take the window path); the point is clean iff its nibble is all ones
-        unsigned csel = 0;
+            // flag test of a pack in two instructions: byte p of prmt(flag word, 0, csel) is the flag byte of point p's stencil
+            // (a zero byte for points that cannot take the window path); the point is clean iff its nibble is all ones
+            csel = 0;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) csel |= (p < R && ((fastm >> p) & 1u) ? ((csel0 >> (4 * p)) & 3u) : 4u) << (4 * p);
-        const bool anyfill = __any_sync(0xffffffffu, fillm != 0u);
+            for (int p = 0; p < 4; ++p) csel |= (p < R && ((fastm >> p) & 1u) ? ((csel0 >> (4 * p)) & 3u) : 4u) << (4 * p);
+            anyfill = __any_sync(0xffffffffu, fillm != 0u);
+        }
         const float fillv = jb.fill;
         const int nslab = jb.nslab, gslab0 = jb.gslab0;
-        const float4* __restrict__ Ta = jb.TA + (size_t)seg.pack0 * pstride + toff;
-        const unsigned* __restrict__ cfp = jb.cf + (size_t)seg.pack0 * pstride + toff;
-        const float4* __restrict__ Pw = jb.P + (size_t)seg.pack0 * pstride + woff;
-        const float4* Pbox = jb.P + (size_t)seg.pack0 * pstride + boff;
-        const void* tmap = &P.tmap[seg.job];
         const int npk = seg.npk;
         const StripOut* outp = P.out + jb.slab0 + seg.pack0 * 4;
-        // copy of the segment's pack pk box into ring stage st
-        auto issue = [&](int pk, unsigned st) {
-            const unsigned bar = bar0 + 8 * st;
-            if (STAGE == 2) {
-                if (elect_one()) {
-                    mbar_expect_tx(bar, (unsigned)(SBW * SBH * 16));
-                    tma_g2s_3d(win0 + st * STG_BYTES, tmap, bc0, bc1, seg.pack0 + pk, bar);
-                }
-            } else {
-                if (lane == 0) mbar_expect_tx(bar, (unsigned)(bw * bh * 16));
-                __syncwarp();
-                if (lane < bh) bulk_g2s(win0 + st * STG_BYTES + (unsigned)(lane * SROW * 16), Pbox + (size_t)pk * pstride, (unsigned)(bw * 16), bar);
-            }
-        };
-        if (STAGE && staged) {
-            __syncwarp();                            // the previous segment's last stages have been read by every lane
-            unsigned st = stg;
-            for (int pk = 0; pk < SNS - 1 && pk < npk; ++pk) { issue(pk, st); st = st + 1 == SNS ? 0 : st + 1; }
-        }
-        float4 ta = __ldg(Ta);
-        unsigned cfv = __ldg(cfp);                   // flag word of the window origin for the pack
 
         // the pack loop exists twice (windows from the ring / from global memory) so that neither carries the other's loads
         auto packs = [&](auto direct_tag) {
@@ -482,7 +505,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
             for (int pk = 0; pk < npk; ++pk) {
                 const float4 cta = ta;
                 const unsigned ccf = cfv;
-                if (pk + 1 < npk) {                      // thresholds and stencil flags of the next pack, one iteration ahead
+                if (--qleft > 0) {                       // thresholds and stencil flags of the next pack, one iteration ahead
                     Ta += pstride; cfp += pstride;
                     ta = __ldg(Ta);
                     cfv = __ldg(cfp);
@@ -491,7 +514,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                 if (!DIRECT) {
                     const unsigned prev = stg == 0 ? SNS - 1 : stg - 1;
                     __syncwarp();                        // every lane has finished reading the stage that is refilled now
-                    if (pk + SNS - 1 < npk) issue(pk + SNS - 1, prev);
+                    issue_next(prev);
                     mbar_wait(bar0 + 8 * stg, par);
                     swa = win0 + stg * STG_BYTES + sw_off;
                     stg = stg + 1 == SNS ? 0 : stg + 1;
@@ -564,10 +587,11 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                 outp += 4;
                 unsigned word[R];
 #pragma unroll
+                for (int p = 0; p < R; ++p) word[p] = __ballot_sync(0xffffffffu, g[p]);
+#pragma unroll
                 for (int p = 0; p < R; ++p) {
                     const int idx = idx0 + p * nx;
-                    st4_f32_if(g[p], o0.r + idx, o1.r + idx, o2.r + idx, o3.r + idx, a01[p].x, a01[p].y, a23[p].x, a23[p].y);
-                    word[p] = __ballot_sync(0xffffffffu, g[p]);
+                    if (g[p]) { o0.r[idx] = a01[p].x; o1.r[idx] = a01[p].y; o2.r[idx] = a23[p].x; o3.r[idx] = a23[p].y; }
                 }
                 {
                     // flagged points (rare): one warp-uniform test per pack, the queue code stays out of the way
@@ -580,12 +604,12 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                         strip_slow_push(P.sq, sw[0], sw[1], sw[2], sw[3], gslab0 + pk0 * 4, min(4, nslab - pk0 * 4), idx0, nx);
                     }
                 }
-                {
+                if (wrow) {
                     // lane p writes the new_pts words of strip row p for the four levels
                     unsigned w = word[0];
 #pragma unroll
                     for (int p = 1; p < R; ++p) w = lane == p ? word[p] : w;
-                    st4_u32_if(wrow, o0.w + widx, o1.w + widx, o2.w + widx, o3.w + widx, w);
+                    o0.w[widx] = (int)w; o1.w[widx] = (int)w; o2.w[widx] = (int)w; o3.w[widx] = (int)w;
                 }
             }
         };
