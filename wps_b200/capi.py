@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwpsgpu.so")
+LIB_PATH = os.environ.get("WPSGPU_LIB") or os.path.join(_HERE, "libwpsgpu.so")   # WPSGPU_LIB: another build of the same library (A/B measurements)
 
 NAN = np.float32(1.0e20)
 NOT_MASKED, MASKED_BOTH, MASKED_WATER, MASKED_LAND = -2.0, -1.0, 0.0, 1.0

@@ -303,6 +303,10 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     float2 xyv[R];
 #pragma unroll
     for (int p = 0; p < R; ++p) xyv[p] = __ldg(gj.xy + (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1));   // rows / columns past the grid re-read its last point
+    // landmask of the strip's points, once per block (every job of the class that uses one uses the grid's)
+    float lmv[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) lmv[p] = gj.landmask_cls ? __ldg(gj.landmask_cls + (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1)) : 0.0f;
     bool geo[R];                                 // the point can be evaluated from a window (if the job's point logic allows)
     int ci[R], cj[R];
     float fx[R], fy[R];
@@ -417,12 +421,8 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     const int idx0 = jj0 * nx + ii;
     const int widx = (jj0 + (lane < R ? lane : 0)) * gj.nxw + tx;     // lane p < R writes the bitmap words of strip row p
     const bool wrow = lane < R && ((rowsm >> lane) & 1u);
+    const bool fulltile = colw == 0xffffffffu && jj0 + R <= ny;      // all 32 x R points of the tile exist
     unsigned stg = 0, par = 0;                   // ring stage of the next pack to be consumed and its barrier phase
-    // landmask of the strip's points, once per block (every job of the class that uses one uses the grid's)
-    float lmv[R];
-#pragma unroll
-    for (int p = 0; p < R; ++p) lmv[p] = gj.landmask_cls ? __ldg(gj.landmask_cls + (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1)) : 0.0f;
-
     // The window records, thresholds and flag words of all jobs of a geometry class lie back to back (host), so the block's
     // packs are ONE contiguous range [q0, q0 + nq) of the class arrays, across segment (job) boundaries: the ring copy of the
     // pack two ahead and the threshold / flag loads of the next pack never look at the segment table.
@@ -430,22 +430,26 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     const int nq = wk.npk;
     const void* tmap = &P.tmap[wk.cls];
     const float4* Pbox = cl.P + (size_t)wk.q0 * pstride + boff;
-    int iq = 0;                                  // packs issued to the ring so far
+    // (ileft, zq) = packs still to be issued to the ring, class index of the next one.  Kept opaque: the compiler otherwise
+    // re-derives them from the parameter block (blockIdx -> work item -> ...) through a chain of dependent constant loads
+    // in every iteration.
+    int ileft = nq, zq = wk.q0;
+    asm volatile("" : "+r"(ileft), "+r"(zq), "+l"(tmap));
     auto issue_next = [&](unsigned st) {
-        if (iq < nq) {
+        if (ileft > 0) {
             const unsigned bar = bar0 + 8 * st;
             if (STAGE == 2) {
                 if (elect_one()) {
                     mbar_expect_tx(bar, (unsigned)(SBW * SBH * 16));
-                    tma_g2s_3d(win0 + st * STG_BYTES, tmap, bc0, bc1, wk.q0 + iq, bar);
+                    tma_g2s_3d(win0 + st * STG_BYTES, tmap, bc0, bc1, zq, bar);
                 }
             } else {
                 if (lane == 0) mbar_expect_tx(bar, (unsigned)(bw * bh * 16));
                 __syncwarp();
-                if (lane < bh) bulk_g2s(win0 + st * STG_BYTES + (unsigned)(lane * SROW * 16), Pbox + (size_t)iq * pstride, (unsigned)(bw * 16), bar);
+                if (lane < bh) bulk_g2s(win0 + st * STG_BYTES + (unsigned)(lane * SROW * 16), Pbox + (size_t)(zq - wk.q0) * pstride, (unsigned)(bw * 16), bar);
             }
-            ++iq;
         }
+        --ileft; ++zq;
     };
     if (STAGE && staged) {
 #pragma unroll
@@ -457,6 +461,7 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     float4 ta = __ldg(Ta);                       // thresholds and flag word of the first pack; later ones one iteration ahead
     unsigned cfv = __ldg(cfp);
     int qleft = nq;                              // packs of the block still to be computed, the current one included
+    asm volatile("" : "+r"(qleft));
 
     unsigned fillm = 0, nibm = 0, csel = 0;
     bool anyfill = false;
@@ -585,31 +590,44 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                 }
                 const StripOut o0 = outp[0], o1 = outp[1], o2 = outp[2], o3 = outp[3];
                 outp += 4;
-                unsigned word[R];
+                bool gall = true;
 #pragma unroll
-                for (int p = 0; p < R; ++p) word[p] = __ballot_sync(0xffffffffu, g[p]);
+                for (int p = 0; p < R; ++p) gall = gall && g[p];
+                if (fulltile && __all_sync(0xffffffffu, gall)) {
+                    // the common case, warp-uniform: every point of the 32 x R tile delivers -- unconditional stores, full words
 #pragma unroll
-                for (int p = 0; p < R; ++p) {
-                    const int idx = idx0 + p * nx;
-                    if (g[p]) { o0.r[idx] = a01[p].x; o1.r[idx] = a01[p].y; o2.r[idx] = a23[p].x; o3.r[idx] = a23[p].y; }
-                }
-                {
-                    // flagged points (rare): one warp-uniform test per pack, the queue code stays out of the way
-                    unsigned sw[4] = { 0u, 0u, 0u, 0u };
-                    unsigned any = 0;
-#pragma unroll
-                    for (int p = 0; p < R; ++p) { sw[p] = (((rowsm >> p) & 1u) ? colw : 0u) & ~word[p]; any |= sw[p]; }
-                    if (any) {
-                        const int pk0 = seg.pack0 + pk;
-                        strip_slow_push(P.sq, sw[0], sw[1], sw[2], sw[3], gslab0 + pk0 * 4, min(4, nslab - pk0 * 4), idx0, nx);
+                    for (int p = 0; p < R; ++p) {
+                        const int idx = idx0 + p * nx;
+                        o0.r[idx] = a01[p].x; o1.r[idx] = a01[p].y; o2.r[idx] = a23[p].x; o3.r[idx] = a23[p].y;
                     }
-                }
-                if (wrow) {
-                    // lane p writes the new_pts words of strip row p for the four levels
-                    unsigned w = word[0];
+                    if (lane < R) { o0.w[widx] = -1; o1.w[widx] = -1; o2.w[widx] = -1; o3.w[widx] = -1; }
+                } else {
+                    unsigned word[R];
 #pragma unroll
-                    for (int p = 1; p < R; ++p) w = lane == p ? word[p] : w;
-                    o0.w[widx] = (int)w; o1.w[widx] = (int)w; o2.w[widx] = (int)w; o3.w[widx] = (int)w;
+                    for (int p = 0; p < R; ++p) word[p] = __ballot_sync(0xffffffffu, g[p]);
+#pragma unroll
+                    for (int p = 0; p < R; ++p) {
+                        const int idx = idx0 + p * nx;
+                        if (g[p]) { o0.r[idx] = a01[p].x; o1.r[idx] = a01[p].y; o2.r[idx] = a23[p].x; o3.r[idx] = a23[p].y; }
+                    }
+                    {
+                        // flagged points (rare): one warp-uniform test per pack, the queue code stays out of the way
+                        unsigned sw[4] = { 0u, 0u, 0u, 0u };
+                        unsigned any = 0;
+#pragma unroll
+                        for (int p = 0; p < R; ++p) { sw[p] = (((rowsm >> p) & 1u) ? colw : 0u) & ~word[p]; any |= sw[p]; }
+                        if (any) {
+                            const int pk0 = seg.pack0 + pk;
+                            strip_slow_push(P.sq, sw[0], sw[1], sw[2], sw[3], gslab0 + pk0 * 4, min(4, nslab - pk0 * 4), idx0, nx);
+                        }
+                    }
+                    if (wrow) {
+                        // lane p writes the new_pts words of strip row p for the four levels
+                        unsigned w = word[0];
+#pragma unroll
+                        for (int p = 1; p < R; ++p) w = lane == p ? word[p] : w;
+                        o0.w[widx] = (int)w; o1.w[widx] = (int)w; o2.w[widx] = (int)w; o3.w[widx] = (int)w;
+                    }
                 }
             }
         };
