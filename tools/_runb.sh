@@ -1,1 +1,3 @@
-for m in 12 20; do echo "MINB=$m"; WPSGPU_LIB=$PWD/gpurun_out/libwpsgpu_m$m.so python bench.py --steps 10 --warmup 3 --no-cpu --no-geogrid --no-e2e 2>gpurun_out/v5_bench_m$m.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"; done
+python -m pytest tests -m gpu -x -q -k "geogrid or geo or config3 or ref_read" > gpurun_out/pytest_geo.log 2>&1; tail -3 gpurun_out/pytest_geo.log
+python tools/geo_only.py 2>&1 | tail -3
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/geo_launches.csv python tools/geo_only.py > /dev/null 2>&1

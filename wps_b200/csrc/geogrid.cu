@@ -38,6 +38,7 @@ struct GeoState {
     struct Pending { int set, smx, sMx, smy, sMy, smz, sMz, bdr; };
     std::vector<Pending> pending;     // tiles staged (decoded, mapped) but not yet accumulated: the current batch
     int* d_first_tile = nullptr; size_t cap_first = 0;
+    int* d_dstart = nullptr;          // per tile buffer set: first level of the block hierarchy with a uniform block (k_geo_dstart)
     cudaEvent_t ev_h2d = nullptr;    // host-pointer mode: the caller's tile buffer has been read
     Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
     void* d_lit = nullptr; size_t lit_bytes = 0;
@@ -131,7 +132,36 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 // Quadtree emulation: walk the block hierarchy of process_*_block top-down for this pixel and credit the
 // first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
 // Tile-specific part of the kernel arguments: a batch launch takes several of these (blockIdx.z picks one).
-struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; };
+struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; };
+
+// Shallowest level of the tile's block hierarchy (process_*_block, proc_point_module.F:218-458) that holds a block whose four
+// corners map to one destination cell, looked for among the levels 0 .. GEO_DCAP (21845 blocks at most).  With a source much
+// finer than the domain there is none up there: every pixel's walk then skips the corner tests -- and their loads from the
+// far ends of the where_maps_to array -- of those levels.  One thread per (level, block); a block that the recursion cannot
+// reach (its parent is a <= 2 x 2 leaf, or a right / upper half that does not exist) is skipped.
+constexpr int GEO_DCAP = 7;
+constexpr int GEO_DNODES = 21845;      // (4^(GEO_DCAP+1) - 1) / 3
+__global__ void __launch_bounds__(256) k_geo_dstart(const int2* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= GEO_DNODES || I0 > I1 || J0 > J1) return;
+    int d = 0, off = 0;
+    while (off + (1 << (2 * d)) <= n) { off += 1 << (2 * d); ++d; }
+    const int local = n - off, a = local & ((1 << d) - 1), b = local >> d;
+    int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
+    for (int st = d - 1; st >= 0; --st) {
+        if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) return;      // the parent is a leaf
+        const int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
+        if ((a >> st) & 1) { if (ci >= max_i) return; min_i = ci + 1; } else max_i = ci;
+        if ((b >> st) & 1) { if (cj >= max_j) return; min_j = cj + 1; } else max_j = cj;
+    }
+    auto W = [&](int i, int j) { return wm[(size_t)(j - smy) * tnx + (i - smx)]; };
+    const int2 p = W(min_i, min_j), q = W(max_i, max_j);
+    if (p.x == q.x && p.y == q.y && p.x != GEO_OUTSIDE) {
+        const int2 r = W(min_i, max_j), t = W(max_i, min_j);
+        if (p.x == r.x && p.x == t.x && p.y == r.y && p.y == t.y) atomicMin(dstart, d);
+    }
+}
 constexpr int GEO_NB = 8;     // tiles per batch
 struct GeoBatch { GeoTile t[GEO_NB]; int n; };
 
@@ -153,13 +183,17 @@ __device__ __forceinline__ void geo_accum_body(GeoK g, const GeoTile& t, int ord
         auto W = [&](int i, int j) { return g.wm[(size_t)(j - g.smy) * g.tnx + (i - g.smx)]; };
         int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
         int2 dest;
-        for (;;) {
-            // four corners agree?  The diagonal pair is compared first: on the upper levels it already differs and
-            // the other two corners need not be fetched.
-            int2 a = W(min_i, min_j), c = W(max_i, max_j);
-            if (a.x == c.x && a.y == c.y && a.x != GEO_OUTSIDE) {
-                int2 b = W(min_i, max_j), d = W(max_i, min_j);
-                if (a.x == b.x && a.x == d.x && a.y == b.y && a.y == d.y) { dest = a; break; }
+        // levels above d0 hold no block whose corners agree (k_geo_dstart): the walk only narrows the rectangle there
+        const int d0 = t.dstart ? min(__ldg(t.dstart), GEO_DCAP + 1) : 0;
+        for (int lev = 0;; ++lev) {
+            // four corners agree?  The diagonal pair is compared first: where it differs the other two corners need
+            // not be fetched.
+            if (lev >= d0) {
+                int2 a = W(min_i, min_j), c = W(max_i, max_j);
+                if (a.x == c.x && a.y == c.y && a.x != GEO_OUTSIDE) {
+                    int2 b = W(min_i, max_j), d = W(max_i, min_j);
+                    if (a.x == b.x && a.x == d.x && a.y == b.y && a.y == d.y) { dest = a; break; }
+                }
             }
             if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = W(pi, pj); break; }
             int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
@@ -226,7 +260,7 @@ __device__ __forceinline__ GeoTile tile_of(const GeoK& g)
 {
     GeoTile t;
     t.tile = g.tile; t.wm = g.wm; t.smx = g.smx; t.sMx = g.sMx; t.smy = g.smy; t.sMy = g.sMy; t.smz = g.smz; t.sMz = g.sMz;
-    t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny;
+    t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny; t.dstart = nullptr;
     return t;
 }
 __global__ void __launch_bounds__(256) k_geo_accum(GeoK g) { geo_accum_body(g, tile_of(g), 0, nullptr); }
@@ -744,6 +778,7 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
     for (int b = 0; b < GEO_SETS; ++b) {
         if (s->d_tile[b]) cudaFree(s->d_tile[b]);
         if (s->d_wm[b]) cudaFree(s->d_wm[b]);
+        if (b == 0 && s->d_dstart) { cudaFree(s->d_dstart); s->d_dstart = nullptr; }
         if (s->ev_pre[b]) cudaEventDestroy(s->ev_pre[b]);
         if (s->ev_used[b]) cudaEventDestroy(s->ev_used[b]);
     }
@@ -897,7 +932,7 @@ static int geo_flush_batch(wpsgpu_ctx* h)
     for (int z = 0; z < bt.n; ++z) {
         const GeoState::Pending& p = s->pending[z];
         GeoTile& t = bt.t[z];
-        t.tile = s->d_tile[p.set]; t.wm = s->d_wm[p.set];
+        t.tile = s->d_tile[p.set]; t.wm = s->d_wm[p.set]; t.dstart = s->d_dstart + p.set;
         t.smx = p.smx; t.sMx = p.sMx; t.smy = p.smy; t.sMy = p.sMy; t.smz = p.smz; t.sMz = p.sMz; t.bdr = p.bdr;
         t.tnx = p.sMx - p.smx + 1; t.tny = p.sMy - p.smy + 1;
         gx = std::max(gx, (t.tnx - 2 * p.bdr + 31) / 32); gy = std::max(gy, (t.tny - 2 * p.bdr + 7) / 8);
@@ -948,6 +983,12 @@ static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, i
         g.wm = s->d_wm[set];
         k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, pre>>>(g);
         h->launches++;
+        if (geo_batchable(s) && pre != h->stream) {   // the batch kernel's walk starts where blocks with agreeing corners begin
+            if (!s->d_dstart) WPS_CUDA(cudaMalloc((void**)&s->d_dstart, GEO_SETS * sizeof(int)));
+            WPS_CUDA(cudaMemsetAsync(s->d_dstart + set, 0x7f, sizeof(int), pre));
+            k_geo_dstart<<<(GEO_DNODES + 255) / 256, 256, 0, pre>>>(g.wm, smx, smy, tnx, smx + bdr, sMx - bdr, smy + bdr, sMy - bdr, s->d_dstart + set);
+            h->launches++;
+        }
     }
     if (accum && geo_batchable(s) && pre != h->stream) {
         // batch path: the tile waits, staged, until GEO_NB tiles have come together (or the level ends)
