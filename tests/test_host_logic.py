@@ -227,3 +227,23 @@ def test_patchwise_smoothing_with_apron_equals_whole_domain(opt, npass):
         ax0, ax1, ay0, ay1 = apron_window(x0, x1, y0, y1, idim, jdim, ap - 1)
         s = O.smooth(a[ay0 - 1:ay1, ax0 - 1:ax1], npass, opt)
         assert not np.array_equal(s[y0 - ay0:y1 - ay0 + 1, x0 - ax0:x1 - ax0 + 1], whole[y0 - 1:y1, x0 - 1:x1])
+
+
+def test_output_fields_order_follows_get_next_output_field():
+    """storage_module.F:478-552 + storage_put_field :88-136, by hand: head nodes of new field names go to the FRONT of the
+    list, levels stay sorted by descending vertical_level (secondary_cmp of time-dependent fields), mask fields
+    (output_this_field = no) are skipped, and the levels of a field come out stacked in one array."""
+    from wps_b200.metgrid import FgInput, output_fields
+    from wps_b200 import capi
+
+    def fg(name, lvl, val, mask=False):
+        return FgInput(name, lvl, capi.M, np.full((2, 3), val, np.float32), np.zeros((2, 1), np.int32), None, False, mask)
+    storage = {}
+    for name, lvl, val, mask in [("TT", 85000, 1.0, False), ("LANDSEA", 200100, 9.0, True), ("TT", 200100, 2.0, False),
+                                 ("UU", 100000, 3.0, False), ("TT", 100000, 4.0, False), ("UU", 50000, 5.0, False), ("PSFC", 200100, 6.0, False)]:
+        storage[(name, lvl)] = fg(name, lvl, val, mask)
+    out = list(output_fields(storage))
+    assert [n for n, _ in out] == ["PSFC", "UU", "TT"]          # reverse of first storage, LANDSEA (mask field) skipped
+    tt = out[2][1]
+    assert tt.shape == (3, 2, 3) and [float(tt[k, 0, 0]) for k in range(3)] == [2.0, 4.0, 1.0]     # 200100, 100000, 85000
+    assert [float(out[1][1][k, 0, 0]) for k in range(2)] == [3.0, 5.0]

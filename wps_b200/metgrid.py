@@ -58,6 +58,27 @@ def halo_slab(fg: MetData):
     return s, 1, 0
 
 
+def output_fields(storage: Dict[Tuple[str, int], "FgInput"]):
+    """The output gather of process_single_met_time (:966-983): reset_next_field + get_next_output_field
+    (storage_module.F:478-552) over the stored fields.  Yields (field_name, r_array [nlevels][ny][nx]) in the order
+    the reference writes met_em variables:
+      * fields: storage_put_field pushes the head node of a NEW field name at the FRONT of the list (:88-104), so fields
+        come out in reverse order of their first storage;
+      * fields whose header says mask_field (output_this_field = no, :1186-1191) are skipped (:507-515);
+      * levels: kept sorted by secondary_cmp (datatype_module.F:124-155) -- for time-dependent and constant fields
+        (everything the record loop stores) by DESCENDING vertical_level: 200100 (surface) first, then 100000, 97500 ...
+    `storage` is the dict process_intermediate_fields returns (insertion-ordered, as Python dicts are)."""
+    first_seen: List[str] = []
+    for (name, _lvl) in storage:
+        if name not in first_seen:
+            first_seen.append(name)
+    for name in reversed(first_seen):
+        levels = sorted((lvl for (n, lvl) in storage if n == name), reverse=True)
+        if storage[(name, levels[0])].mask_field:
+            continue
+        yield name, np.stack([storage[(name, lvl)].r_arr for lvl in levels])
+
+
 class MetgridDomain:
     """One model domain: its staggered lat/lon arrays (from geo_em), LANDMASK and the device handle."""
 
