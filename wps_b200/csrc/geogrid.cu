@@ -39,6 +39,7 @@ struct GeoState {
     std::vector<Pending> pending;     // tiles staged (decoded, mapped) but not yet accumulated: the current batch
     int* d_first_tile = nullptr; size_t cap_first = 0;
     int* d_dstart = nullptr;          // per tile buffer set: first level of the block hierarchy with a uniform block (k_geo_dstart)
+    int2* d_bounds[GEO_SETS] = {}; size_t bounds_cap[GEO_SETS] = {};   // per set: level-dstart block ranges of the tile's columns, then rows
     cudaEvent_t ev_h2d = nullptr;    // host-pointer mode: the caller's tile buffer has been read
     Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
     void* d_lit = nullptr; size_t lit_bytes = 0;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 // Quadtree emulation: walk the block hierarchy of process_*_block top-down for this pixel and credit the
 // first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
 // Tile-specific part of the kernel arguments: a batch launch takes several of these (blockIdx.z picks one).
-struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; };
+struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; const int2* xb; const int2* yb; };
 
 // Shallowest level of the tile's block hierarchy (process_*_block, proc_point_module.F:218-458) that holds a block whose four
 // corners map to one destination cell, looked for among the levels 0 .. GEO_DCAP (21845 blocks at most).  With a source much
@@ -155,6 +156,9 @@ __global__ void __launch_bounds__(256) k_geo_dstart(const int2* __restrict__ wm,
         if ((a >> st) & 1) { if (ci >= max_i) return; min_i = ci + 1; } else max_i = ci;
         if ((b >> st) & 1) { if (cj >= max_j) return; min_j = cj + 1; } else max_j = cj;
     }
+    // a <= 2 x 2 leaf ends the recursion like a uniform block does: above the level found here every block splits in both
+    // directions, so the x and y ranges of a pixel's block can be followed independently (k_geo_bounds)
+    if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { atomicMin(dstart, d); return; }
     auto W = [&](int i, int j) { return wm[(size_t)(j - smy) * tnx + (i - smx)]; };
     const int2 p = W(min_i, min_j), q = W(max_i, max_j);
     if (p.x == q.x && p.y == q.y && p.x != GEO_OUTSIDE) {
@@ -164,6 +168,136 @@ __global__ void __launch_bounds__(256) k_geo_dstart(const int2* __restrict__ wm,
 }
 constexpr int GEO_NB = 8;     // tiles per batch
 struct GeoBatch { GeoTile t[GEO_NB]; int n; };
+
+// Range [lo, hi] of the level-dstart block that holds each pixel column / row of the tile's interior: the walk of
+// process_*_block down to that level without looking at where_maps_to (no block above it is uniform or a leaf).
+__global__ void __launch_bounds__(256) k_geo_bounds(const int* __restrict__ dstart, int I0, int I1, int J0, int J1, int2* __restrict__ xb, int2* __restrict__ yb)
+{
+    const int d0 = min(*dstart, GEO_DCAP + 1);
+    const int nxi = I1 - I0 + 1, nyi = J1 - J0 + 1;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nxi + nyi) return;
+    const bool isx = e < nxi;
+    const int c = isx ? I0 + e : J0 + (e - nxi);
+    int lo = isx ? I0 : J0, hi = isx ? I1 : J1;
+    for (int d = 0; d < d0; ++d) {
+        const int m = (hi + lo) / 2;
+        if (c <= m) hi = m; else lo = m + 1;
+    }
+    (isx ? xb[e] : yb[e - nxi]) = make_int2(lo, hi);
+}
+
+// Categorical accumulation of a batch of tiles (accum_categorical, proc_point_module.F:100-216, + process_categorical_block
+// :218-458): a block takes 32 x 32 pixels of one tile (4 rows per thread).  Every pixel walks the block hierarchy from level
+// dstart (k_geo_dstart / k_geo_bounds) to the first block whose corners agree or to its <= 2 x 2 leaf; the credits are
+// counted in a SHARED-MEMORY histogram over the destination cells the block's pixels map to ([category + 1 plane of
+// credit attempts][cell of the block's bounding box], integer atomics) and flushed once: one global atomic per (cell,
+// category) the block met instead of one per pixel group.  Blocks whose bounding box does not fit (a domain much finer than
+// the source) fall back to global atomics per pixel.
+constexpr int GEO_HCAP = 4096;      // shared-memory counters per block
+__global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, int* __restrict__ first_tile)
+{
+    const GeoTile& t = bt.t[blockIdx.z];
+    const int I0 = t.smx + t.bdr, I1 = t.sMx - t.bdr, J0 = t.smy + t.bdr, J1 = t.sMy - t.bdr;
+    if (I0 + (int)blockIdx.x * 32 > I1 || J0 + (int)blockIdx.y * 32 > J1) return;
+    __shared__ int s_bb[4];          // {jmin, imin, jmax, imax} of the cells this block credits
+    __shared__ int s_hist[GEO_HCAP];
+    const int tid = threadIdx.y * 32 + threadIdx.x, order = (int)blockIdx.z;
+    if (tid == 0) { s_bb[0] = INT_MAX; s_bb[1] = INT_MAX; s_bb[2] = INT_MIN; s_bb[3] = INT_MIN; }
+    __syncthreads();
+    const int d0 = min(__ldg(t.dstart), GEO_DCAP + 1);
+    const int tnx = t.tnx;
+    const int2* __restrict__ wm = t.wm - ((size_t)t.smy * tnx + t.smx);     // wm[j * tnx + i] in tile coordinates
+    const int pi = I0 + blockIdx.x * 32 + threadIdx.x;
+    const bool colok = pi <= I1;
+    const int2 xr = colok ? __ldg(t.xb + (pi - I0)) : make_int2(0, 0);
+    int cell[4];                     // destination cell of the thread's four pixels, -1 = no credit
+    int cat[4];                      // category index (>= 0), -1 = missing value, -2 = invalid category
+    int jmn = INT_MAX, imn = INT_MAX, jmx = INT_MIN, imx = INT_MIN;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int pj = J0 + blockIdx.y * 32 + threadIdx.y + 8 * r;
+        cell[r] = -1; cat[r] = -1;
+        if (!colok || pj > J1) continue;
+        const int2 yr = __ldg(t.yb + (pj - J0));
+        int min_i = xr.x, max_i = xr.y, min_j = yr.x, max_j = yr.y;
+        int2 dest;
+        for (;;) {
+            // four corners agree?  The diagonal pair is compared first: where it differs the other two need not be fetched.
+            const int2 a = wm[min_j * tnx + min_i], c = wm[max_j * tnx + max_i];
+            if (a.x == c.x && a.y == c.y && a.x != GEO_OUTSIDE) {
+                const int2 b = wm[max_j * tnx + min_i], d = wm[min_j * tnx + max_i];
+                if (a.x == b.x && a.x == d.x && a.y == b.y && a.y == d.y) { dest = a; break; }
+            }
+            if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = wm[pj * tnx + pi]; break; }
+            const int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
+            if (pi <= ci) max_i = ci; else min_i = ci + 1;
+            if (pj <= cj) max_j = cj; else min_j = cj + 1;
+        }
+        if (dest.x == GEO_OUTSIDE) continue;
+        const int ii = dest.x - g.start_i, jj = dest.y - g.start_j;
+        if (bit_test(g.processed, g.nxw, ii, jj)) continue;
+        cell[r] = jj * g.nx + ii;
+        jmn = min(jmn, jj); jmx = max(jmx, jj); imn = min(imn, ii); imx = max(imx, ii);
+        const float v = t.tile[(size_t)(pj - t.smy) * tnx + (pi - t.smx)];
+        const int cv = (int)v;
+        if (v != g.msg_val) cat[r] = (cv >= g.start_k && cv <= g.end_k) ? cv - g.start_k : -2;
+    }
+    (void)d0;
+    {   // bounding box of the credited cells: one shared-memory update per warp
+        jmn = __reduce_min_sync(0xffffffffu, jmn); imn = __reduce_min_sync(0xffffffffu, imn);
+        jmx = __reduce_max_sync(0xffffffffu, jmx); imx = __reduce_max_sync(0xffffffffu, imx);
+        if (threadIdx.x == 0 && jmn != INT_MAX) { atomicMin(&s_bb[0], jmn); atomicMin(&s_bb[1], imn); atomicMax(&s_bb[2], jmx); atomicMax(&s_bb[3], imx); }
+    }
+    __syncthreads();
+    if (s_bb[0] == INT_MAX) return;                 // the block credits nothing (warp-uniform: shared value)
+    const int bj0 = s_bb[0], bi0 = s_bb[1], bw = s_bb[3] - bi0 + 1, bh = s_bb[2] - bj0 + 1;
+    const int ncell = bw * bh, nplane = g.nk + 1;   // plane nk counts the credit attempts ("touched")
+    const bool use_hist = (long long)ncell * nplane <= GEO_HCAP;
+    if (use_hist) {
+        for (int e = tid; e < ncell * nplane; e += 256) s_hist[e] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (cell[r] < 0) continue;
+            const int jj = cell[r] / g.nx, ii = cell[r] - jj * g.nx;
+            const int lc = (jj - bj0) * bw + (ii - bi0);
+            atomicAdd(&s_hist[g.nk * ncell + lc], 1);
+            if (cat[r] >= 0) atomicAdd(&s_hist[cat[r] * ncell + lc], 1);
+            else if (cat[r] == -2) atomicAdd(g.invalid, 1ull);
+        }
+        __syncthreads();
+        for (int e = tid; e < ncell * nplane; e += 256) {
+            const int v = s_hist[e];
+            if (v == 0) continue;
+            const int k = e / ncell, lc = e - k * ncell;
+            const int jj = bj0 + lc / bw, ii = bi0 + lc % bw;
+            const size_t gc = (size_t)jj * g.nx + ii;
+            if (k == g.nk) g.touched[gc] = 1;
+            else {
+                atomicAdd(g.acc_cnt + (size_t)k * g.npts + gc, v);
+                if (__ldcg(first_tile + gc) > order) atomicMin(first_tile + gc, order);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (cell[r] < 0) continue;
+            g.touched[cell[r]] = 1;
+            if (cat[r] >= 0) {
+                atomicAdd(g.acc_cnt + (size_t)cat[r] * g.npts + cell[r], 1);
+                if (__ldcg(first_tile + cell[r]) > order) atomicMin(first_tile + cell[r], order);
+            } else if (cat[r] == -2) atomicAdd(g.invalid, 1ull);
+        }
+    }
+    // rows / columns this batch reaches (k_geo_merge_b skips the rest of the domain)
+    if (tid < 4) {
+        const int v = s_bb[tid];
+        const int cur = __ldcg(g.tbbox + tid);
+        if (tid < 2) { if (v < cur) atomicMin(g.tbbox + tid, v); }
+        else if (v > cur) atomicMax(g.tbbox + tid, v);
+    }
+}
 
 // order / first_tile: batch launches record, per destination cell, the first tile of the batch (in the caller's order) that
 // actually credited it -- the per-point pass needs to know whether a cell already held data when "its" tile was processed
@@ -260,7 +394,7 @@ __device__ __forceinline__ GeoTile tile_of(const GeoK& g)
 {
     GeoTile t;
     t.tile = g.tile; t.wm = g.wm; t.smx = g.smx; t.sMx = g.sMx; t.smy = g.smy; t.sMy = g.sMy; t.smz = g.smz; t.sMz = g.sMz;
-    t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny; t.dstart = nullptr;
+    t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny; t.dstart = nullptr; t.xb = nullptr; t.yb = nullptr;
     return t;
 }
 __global__ void __launch_bounds__(256) k_geo_accum(GeoK g) { geo_accum_body(g, tile_of(g), 0, nullptr); }
@@ -779,6 +913,7 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
         if (s->d_tile[b]) cudaFree(s->d_tile[b]);
         if (s->d_wm[b]) cudaFree(s->d_wm[b]);
         if (b == 0 && s->d_dstart) { cudaFree(s->d_dstart); s->d_dstart = nullptr; }
+        if (s->d_bounds[b]) { cudaFree(s->d_bounds[b]); s->d_bounds[b] = nullptr; s->bounds_cap[b] = 0; }
         if (s->ev_pre[b]) cudaEventDestroy(s->ev_pre[b]);
         if (s->ev_used[b]) cudaEventDestroy(s->ev_used[b]);
     }
@@ -933,6 +1068,7 @@ static int geo_flush_batch(wpsgpu_ctx* h)
         const GeoState::Pending& p = s->pending[z];
         GeoTile& t = bt.t[z];
         t.tile = s->d_tile[p.set]; t.wm = s->d_wm[p.set]; t.dstart = s->d_dstart + p.set;
+        t.xb = s->d_bounds[p.set]; t.yb = s->d_bounds[p.set] + std::max(0, (p.sMx - p.smx + 1) - 2 * p.bdr);
         t.smx = p.smx; t.sMx = p.sMx; t.smy = p.smy; t.sMy = p.sMy; t.smz = p.smz; t.sMz = p.sMz; t.bdr = p.bdr;
         t.tnx = p.sMx - p.smx + 1; t.tny = p.sMy - p.smy + 1;
         gx = std::max(gx, (t.tnx - 2 * p.bdr + 31) / 32); gy = std::max(gy, (t.tny - 2 * p.bdr + 7) / 8);
@@ -941,7 +1077,8 @@ static int geo_flush_batch(wpsgpu_ctx* h)
     }
     unsigned long long* cnt = g.counters;
     k_geo_batch_reset<<<1, 32, 0, h->stream>>>(g.tbbox, cnt);
-    k_geo_accum_b<<<dim3(gx, gy, bt.n), dim3(32, 8), 0, h->stream>>>(g, bt, s->d_first_tile);
+    if (s->l.itype == WPSGPU_CATEGORICAL) k_geo_accum_cat_b<<<dim3(gx, (gy + 3) / 4, bt.n), dim3(32, 8), 0, h->stream>>>(g, bt, s->d_first_tile);
+    else k_geo_accum_b<<<dim3(gx, gy, bt.n), dim3(32, 8), 0, h->stream>>>(g, bt, s->d_first_tile);
     const unsigned nblk = (unsigned)((s->npts + 255) / 256);
     k_geo_select_b<<<nblk, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_first_tile, s->d_cand, cnt);
     k_geo_points_b<<<h->sm_count * 2, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_cand, cnt, s->d_def);
@@ -988,6 +1125,16 @@ static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, i
             WPS_CUDA(cudaMemsetAsync(s->d_dstart + set, 0x7f, sizeof(int), pre));
             k_geo_dstart<<<(GEO_DNODES + 255) / 256, 256, 0, pre>>>(g.wm, smx, smy, tnx, smx + bdr, sMx - bdr, smy + bdr, sMy - bdr, s->d_dstart + set);
             h->launches++;
+            const int inx = tnx - 2 * bdr, iny = tny - 2 * bdr;
+            if (inx > 0 && iny > 0) {
+                if ((size_t)(inx + iny) * sizeof(int2) > s->bounds_cap[set]) {
+                    WPS_CUDA(cudaStreamSynchronize(h->stream));
+                    WPS_TRY(geo_grow((void**)&s->d_bounds[set], &s->bounds_cap[set], (size_t)(inx + iny) * sizeof(int2), pre));
+                }
+                k_geo_bounds<<<(inx + iny + 255) / 256, 256, 0, pre>>>(s->d_dstart + set, smx + bdr, sMx - bdr, smy + bdr, sMy - bdr, s->d_bounds[set],
+                                                                   s->d_bounds[set] + inx);
+                h->launches++;
+            }
         }
     }
     if (accum && geo_batchable(s) && pre != h->stream) {
