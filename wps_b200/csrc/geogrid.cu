@@ -35,10 +35,11 @@ struct GeoState {
     bool used_rec[GEO_SETS] = {};
     int parity = 0;
     void* d_raw[GEO_SETS] = {}; size_t raw_cap[GEO_SETS] = {};   // host-pointer mode: the file bytes of a tile
-    struct Pending { int set, smx, sMx, smy, sMy, smz, sMz, bdr; };
+    struct Pending { int set, smx, sMx, smy, sMy, smz, sMz, bdr; const unsigned char* raw; int wordsize, is_signed, little, flip; };
     std::vector<Pending> pending;     // tiles staged (decoded, mapped) but not yet accumulated: the current batch
     int* d_first_tile = nullptr; size_t cap_first = 0;
     int* d_dstart = nullptr;          // per tile buffer set: first level of the block hierarchy with a uniform block (k_geo_dstart)
+    float* d_terms[GEO_SETS] = {}; size_t terms_cap[GEO_SETS] = {};     // per set: separable where_maps_to terms, [tny] + 2 [tnx]
     int2* d_bounds[GEO_SETS] = {}; size_t bounds_cap[GEO_SETS] = {};   // per set: level-dstart block ranges of the tile's columns, then rows
     cudaEvent_t ev_h2d = nullptr;    // host-pointer mode: the caller's tile buffer has been read
     Deferred* d_def = nullptr; Deferred* d_def2 = nullptr;
@@ -86,29 +87,38 @@ __global__ void k_geo_tile_reset(int* tbbox, unsigned long long* counters)
 // per-row term (latitude) and a per-column term (longitude): those 2*WM_T evaluations are shared by the WM_T^2
 // pixels of the block through shared memory -- same expressions as llij_lc / llij_ps, so the same bits.
 constexpr int WM_T = 64;
-__global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
+struct GeoWmTile { int smx, smy, tnx, tny; int2* wm; const float* terms; };
+// (the tile comes as a small separate struct: assigning tile fields into a copy of the kernel's GeoK parameter makes every
+// thread copy the whole parameter block to local memory)
+__device__ __forceinline__ void geo_wm_body(const GeoK& g, const GeoWmTile& w)
 {
-    __shared__ float s_rm[WM_T], s_sin[WM_T], s_cos[WM_T], s_lat[WM_T], s_lon[WM_T];
+    __shared__ float s_rm[WM_T], s_sin[WM_T], s_cos[WM_T];
     const int ti0 = blockIdx.x * WM_T, tj0 = blockIdx.y * WM_T, t = threadIdx.x;
     const bool separable = g.src.code == WPSGPU_PROJ_LATLON && (g.dom.code == WPSGPU_PROJ_LC || g.dom.code == WPSGPU_PROJ_PS);
-    if (separable) {
+    if (separable && w.terms) {   // computed once per tile row / column
+        if (t < WM_T) { if (tj0 + t < w.tny) s_rm[t] = w.terms[tj0 + t]; }
+        else if (t < 2 * WM_T) {
+            const int c = t - WM_T;
+            if (ti0 + c < w.tnx) { s_sin[c] = w.terms[w.tny + ti0 + c]; s_cos[c] = w.terms[w.tny + w.tnx + ti0 + c]; }
+        }
+        __syncthreads();
+    } else if (separable) {
         if (t < WM_T) {   // row terms: ijll_latlon gives lat from j alone
             float lat, lon;
-            xytoll(g.src, (float)(g.smx + ti0), (float)(g.smy + tj0 + t), lat, lon, WPSGPU_M);
-            s_lat[t] = lat;
+            xytoll(g.src, (float)(w.smx + ti0), (float)(w.smy + tj0 + t), lat, lon, WPSGPU_M);
             s_rm[t] = g.dom.code == WPSGPU_PROJ_LC ? llij_lc_rm(lat, g.dom) : llij_ps_rm(lat, g.dom);
         } else if (t < 2 * WM_T) {   // column terms: lon from i alone
             int c = t - WM_T;
             float lat, lon, sn, cs;
-            xytoll(g.src, (float)(g.smx + ti0 + c), (float)(g.smy + tj0), lat, lon, WPSGPU_M);
+            xytoll(g.src, (float)(w.smx + ti0 + c), (float)(w.smy + tj0), lat, lon, WPSGPU_M);
             if (g.dom.code == WPSGPU_PROJ_LC) llij_lc_sc(lon, g.dom, sn, cs); else llij_ps_sc(lon, g.dom, sn, cs);
-            s_lon[c] = lon; s_sin[c] = sn; s_cos[c] = cs;
+            s_sin[c] = sn; s_cos[c] = cs;
         }
         __syncthreads();
     }
     for (int e = t; e < WM_T * WM_T; e += 256) {
         int li = e % WM_T, lj = e / WM_T, ti = ti0 + li, tj = tj0 + lj;
-        if (ti >= g.tnx || tj >= g.tny) continue;
+        if (ti >= w.tnx || tj >= w.tny) continue;
         float rx, ry;
         if (separable) {
             if (g.dom.code == WPSGPU_PROJ_LC) llij_lc_combine(s_rm[lj], s_sin[li], s_cos[li], g.dom, rx, ry);
@@ -118,22 +128,28 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
             else if (g.istagger == WPSGPU_CORNER) { rx = rx + 0.5f; ry = ry + 0.5f; }
         } else {
             float lat, lon;
-            xytoll(g.src, (float)(g.smx + ti), (float)(g.smy + tj), lat, lon, WPSGPU_M);
+            xytoll(g.src, (float)(w.smx + ti), (float)(w.smy + tj), lat, lon, WPSGPU_M);
             lltoxy(g.dom, lat, lon, rx, ry, g.istagger);
         }
         rx = (rx - 0.5f) * g.sr_x + 0.5f;
         ry = (ry - 0.5f) * g.sr_y + 0.5f;
-        int2 w;
-        if ((float)g.start_i <= rx && rx <= (float)g.end_i && (float)g.start_j <= ry && ry <= (float)g.end_j) { w.x = f_nint(rx); w.y = f_nint(ry); }
-        else { w.x = GEO_OUTSIDE; w.y = 0; }
-        g.wm[(size_t)tj * g.tnx + ti] = w;
+        int2 wv;
+        if ((float)g.start_i <= rx && rx <= (float)g.end_i && (float)g.start_j <= ry && ry <= (float)g.end_j) { wv.x = f_nint(rx); wv.y = f_nint(ry); }
+        else { wv.x = GEO_OUTSIDE; wv.y = 0; }
+        w.wm[(size_t)tj * w.tnx + ti] = wv;
     }
+}
+__global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
+{
+    GeoWmTile w;
+    w.smx = g.smx; w.smy = g.smy; w.tnx = g.tnx; w.tny = g.tny; w.wm = g.wm; w.terms = nullptr;
+    geo_wm_body(g, w);
 }
 
 // Quadtree emulation: walk the block hierarchy of process_*_block top-down for this pixel and credit the
 // first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
 // Tile-specific part of the kernel arguments: a batch launch takes several of these (blockIdx.z picks one).
-struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; const int2* xb; const int2* yb; };
+struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; const int2* xb; const int2* yb; float* terms; };
 
 // Shallowest level of the tile's block hierarchy (process_*_block, proc_point_module.F:218-458) that holds a block whose four
 // corners map to one destination cell, looked for among the levels 0 .. GEO_DCAP (21845 blocks at most).  With a source much
@@ -142,7 +158,7 @@ struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz,
 // reach (its parent is a <= 2 x 2 leaf, or a right / upper half that does not exist) is skipped.
 constexpr int GEO_DCAP = 7;
 constexpr int GEO_DNODES = 21845;      // (4^(GEO_DCAP+1) - 1) / 3
-__global__ void __launch_bounds__(256) k_geo_dstart(const int2* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
+__device__ __forceinline__ void geo_dstart_body(const int2* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= GEO_DNODES || I0 > I1 || J0 > J1) return;
@@ -169,9 +185,14 @@ __global__ void __launch_bounds__(256) k_geo_dstart(const int2* __restrict__ wm,
 constexpr int GEO_NB = 8;     // tiles per batch
 struct GeoBatch { GeoTile t[GEO_NB]; int n; };
 
+__global__ void __launch_bounds__(256) k_geo_dstart(const int2* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
+{
+    geo_dstart_body(wm, smx, smy, tnx, I0, I1, J0, J1, dstart);
+}
+
 // Range [lo, hi] of the level-dstart block that holds each pixel column / row of the tile's interior: the walk of
 // process_*_block down to that level without looking at where_maps_to (no block above it is uniform or a leaf).
-__global__ void __launch_bounds__(256) k_geo_bounds(const int* __restrict__ dstart, int I0, int I1, int J0, int J1, int2* __restrict__ xb, int2* __restrict__ yb)
+__device__ __forceinline__ void geo_bounds_body(const int* __restrict__ dstart, int I0, int I1, int J0, int J1, int2* __restrict__ xb, int2* __restrict__ yb)
 {
     const int d0 = min(*dstart, GEO_DCAP + 1);
     const int nxi = I1 - I0 + 1, nyi = J1 - J0 + 1;
@@ -185,6 +206,10 @@ __global__ void __launch_bounds__(256) k_geo_bounds(const int* __restrict__ dsta
         if (c <= m) hi = m; else lo = m + 1;
     }
     (isx ? xb[e] : yb[e - nxi]) = make_int2(lo, hi);
+}
+__global__ void __launch_bounds__(256) k_geo_bounds(const int* __restrict__ dstart, int I0, int I1, int J0, int J1, int2* __restrict__ xb, int2* __restrict__ yb)
+{
+    geo_bounds_body(dstart, I0, I1, J0, J1, xb, yb);
 }
 
 // Categorical accumulation of a batch of tiles (accum_categorical, proc_point_module.F:100-216, + process_categorical_block
@@ -394,7 +419,7 @@ __device__ __forceinline__ GeoTile tile_of(const GeoK& g)
 {
     GeoTile t;
     t.tile = g.tile; t.wm = g.wm; t.smx = g.smx; t.sMx = g.sMx; t.smy = g.smy; t.sMy = g.sMy; t.smz = g.smz; t.sMz = g.sMz;
-    t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny; t.dstart = nullptr; t.xb = nullptr; t.yb = nullptr;
+    t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny; t.dstart = nullptr; t.xb = nullptr; t.yb = nullptr; t.terms = nullptr;
     return t;
 }
 __global__ void __launch_bounds__(256) k_geo_accum(GeoK g) { geo_accum_body(g, tile_of(g), 0, nullptr); }
@@ -740,6 +765,105 @@ __device__ __forceinline__ void apply_tile(GeoK& g, const GeoTile& t)
     g.tile = t.tile; g.wm = const_cast<int2*>(t.wm);
     g.smx = t.smx; g.sMx = t.sMx; g.smy = t.smy; g.sMy = t.sMy; g.smz = t.smz; g.sMz = t.sMz; g.bdr = t.bdr; g.tnx = t.tnx; g.tny = t.tny;
 }
+// Pre-work of a whole batch, one launch per step (blockIdx.z = tile): decode of the raw file bytes, where_maps_to, the first
+// level with a uniform block or a leaf, the level's block ranges.  A single tile of a geogrid data set (1200 x 1200 pixels)
+// does not fill the machine; eight of them do.
+struct GeoRaw { const unsigned char* bytes; float* out; int wordsize, is_signed, little, flip, tnx, tny, tnz; };
+struct GeoRawBatch { GeoRaw r[GEO_NB]; };
+__device__ __forceinline__ void geo_decode_one(const unsigned char* __restrict__ c, int wordsize, int is_signed, int little, int flip,
+                                               int tnx, int tny, size_t e, float* __restrict__ out);
+__global__ void __launch_bounds__(256) k_geo_decode_b(GeoRawBatch rb)
+{
+    const GeoRaw& r = rb.r[blockIdx.z];
+    if (!r.bytes) return;
+    const size_t n = (size_t)r.tnx * r.tny * r.tnz;
+    if (r.wordsize == 1 && (r.tnx & 3) == 0 && (((size_t)r.bytes | (size_t)r.out) & 15) == 0) {
+        // one-byte words (land use, soil categories): four pixels of a row per thread, uchar4 in, float4 out
+        const size_t n4 = n >> 2;
+        const int tnx4 = r.tnx >> 2;
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+            const uchar4 b = reinterpret_cast<const uchar4*>(r.bytes)[q];
+            int v[4] = { b.x, b.y, b.z, b.w };
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (r.is_signed && v[u] > (1 << 7)) v[u] -= (1 << 8);      // read_geogrid.c:96-100
+            const size_t i4 = q % tnx4, j = (q / tnx4) % r.tny, k = q / ((size_t)tnx4 * r.tny);
+            const size_t jo = r.flip ? (size_t)(r.tny - 1) - j : j;
+            reinterpret_cast<float4*>(r.out)[(k * r.tny + jo) * tnx4 + i4] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+        }
+        return;
+    }
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+        geo_decode_one(r.bytes, r.wordsize, r.is_signed, r.little, r.flip, r.tnx, r.tny, e, r.out);
+}
+// row terms (latitude) and column terms (longitude) of where_maps_to for a regular lat-lon source on a Lambert / polar
+// stereographic domain: tny + tnx evaluations per tile instead of 128 per 64 x 64 block -- the same expressions, the same bits
+__global__ void __launch_bounds__(256) k_geo_wm_terms_b(GeoK g, GeoBatch bt)
+{
+    const GeoTile& t = bt.t[blockIdx.z];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= t.tnx + t.tny) return;
+    float lat, lon;
+    if (e < t.tny) {
+        xytoll(g.src, (float)t.smx, (float)(t.smy + e), lat, lon, WPSGPU_M);
+        t.terms[e] = g.dom.code == WPSGPU_PROJ_LC ? llij_lc_rm(lat, g.dom) : llij_ps_rm(lat, g.dom);
+    } else {
+        const int c = e - t.tny;
+        float sn, cs;
+        xytoll(g.src, (float)(t.smx + c), (float)t.smy, lat, lon, WPSGPU_M);
+        if (g.dom.code == WPSGPU_PROJ_LC) llij_lc_sc(lon, g.dom, sn, cs); else llij_ps_sc(lon, g.dom, sn, cs);
+        t.terms[t.tny + c] = sn; t.terms[t.tny + t.tnx + c] = cs;
+    }
+}
+// where_maps_to of a batch from the row / column terms alone: a kernel of its own, because in the general kernel the
+// compiler hoists the loop-invariant double-precision set-up of every projection branch in front of the pixel loop -- a
+// thousand instructions per thread that this path never needs.  One thread = four pixels of a row, int4 stores.
+__global__ void __launch_bounds__(256) k_geo_wm_sep_b(GeoK g, GeoBatch bt)
+{
+    const GeoTile& t = bt.t[blockIdx.z];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *const_cast<int*>(t.dstart) = INT_MAX;    // k_geo_dstart_b follows in stream order
+    const int tj = blockIdx.y;
+    if (tj >= t.tny) return;
+    const float rm = t.terms[tj];
+    const float* __restrict__ sn = t.terms + t.tny;
+    const float* __restrict__ cs = t.terms + t.tny + t.tnx;
+    int2* __restrict__ row = const_cast<int2*>(t.wm) + (size_t)tj * t.tnx;
+    const bool lc = g.dom.code == WPSGPU_PROJ_LC;
+    const float si = (float)g.start_i, ei = (float)g.end_i, sj = (float)g.start_j, ej = (float)g.end_j;
+    for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < t.tnx; ti += gridDim.x * blockDim.x) {
+        float rx, ry;
+        if (lc) llij_lc_combine(rm, sn[ti], cs[ti], g.dom, rx, ry);
+        else llij_ps_combine(rm, sn[ti], cs[ti], g.dom, rx, ry);
+        if (g.istagger == WPSGPU_U) rx = rx + 0.5f;
+        else if (g.istagger == WPSGPU_V) ry = ry + 0.5f;
+        else if (g.istagger == WPSGPU_CORNER) { rx = rx + 0.5f; ry = ry + 0.5f; }
+        rx = (rx - 0.5f) * g.sr_x + 0.5f;
+        ry = (ry - 0.5f) * g.sr_y + 0.5f;
+        int2 wv;
+        if (si <= rx && rx <= ei && sj <= ry && ry <= ej) { wv.x = f_nint(rx); wv.y = f_nint(ry); }
+        else { wv.x = GEO_OUTSIDE; wv.y = 0; }
+        row[ti] = wv;
+    }
+}
+__global__ void __launch_bounds__(256) k_geo_wm_b(GeoK g, GeoBatch bt, int have_terms)
+{
+    const GeoTile& t = bt.t[blockIdx.z];
+    if ((int)blockIdx.x * WM_T >= t.tnx || (int)blockIdx.y * WM_T >= t.tny) return;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *const_cast<int*>(t.dstart) = INT_MAX;    // k_geo_dstart_b follows in stream order
+    GeoWmTile w;
+    w.smx = t.smx; w.smy = t.smy; w.tnx = t.tnx; w.tny = t.tny; w.wm = const_cast<int2*>(t.wm); w.terms = have_terms ? t.terms : nullptr;
+    geo_wm_body(g, w);
+}
+__global__ void __launch_bounds__(256) k_geo_dstart_b(GeoBatch bt)
+{
+    const GeoTile& t = bt.t[blockIdx.z];
+    geo_dstart_body(t.wm, t.smx, t.smy, t.tnx, t.smx + t.bdr, t.sMx - t.bdr, t.smy + t.bdr, t.sMy - t.bdr, const_cast<int*>(t.dstart));
+}
+__global__ void __launch_bounds__(256) k_geo_bounds_b(GeoBatch bt)
+{
+    const GeoTile& t = bt.t[blockIdx.z];
+    geo_bounds_body(t.dstart, t.smx + t.bdr, t.sMx - t.bdr, t.smy + t.bdr, t.sMy - t.bdr, const_cast<int2*>(t.xb), const_cast<int2*>(t.yb));
+}
+
 __global__ void __launch_bounds__(256)
 k_geo_points_b(GeoK g, GeoBatch bt, const float2* __restrict__ src_xy, const int* __restrict__ cand, unsigned long long* counters,
                Deferred* def)
@@ -824,11 +948,9 @@ __global__ void k_geo_merge_bits(int* processed, const int* level, size_t nwords
 }
 
 // read_geogrid.c:91-128 + the TOP_BOTTOM row flip of source_data_module.F:2887-2898
-__global__ void k_geo_decode(const unsigned char* __restrict__ c, int wordsize, int is_signed, int little, int flip,
-                             int tnx, int tny, int tnz, float* __restrict__ out)
+__device__ __forceinline__ void geo_decode_one(const unsigned char* __restrict__ c, int wordsize, int is_signed, int little, int flip,
+                                               int tnx, int tny, size_t e, float* __restrict__ out)
 {
-    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)tnx * tny * tnz;
-    if (e >= n) return;
     int ival;
     const unsigned char* b = c + e * wordsize;
     if (wordsize == 1) { ival = b[0]; if (is_signed && ival > (1 << 7)) ival -= (1 << 8); }
@@ -838,6 +960,13 @@ __global__ void k_geo_decode(const unsigned char* __restrict__ c, int wordsize, 
     size_t i = e % tnx, j = (e / tnx) % tny, k = e / ((size_t)tnx * tny);
     size_t jo = flip ? (size_t)(tny - 1) - j : j;
     out[(k * tny + jo) * tnx + i] = (float)ival;
+}
+__global__ void k_geo_decode(const unsigned char* __restrict__ c, int wordsize, int is_signed, int little, int flip,
+                             int tnx, int tny, int tnz, float* __restrict__ out)
+{
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)tnx * tny * tnz;
+    if (e >= n) return;
+    geo_decode_one(c, wordsize, is_signed, little, flip, tnx, tny, e, out);
 }
 
 __global__ void k_geo_scale(float* __restrict__ a, size_t n, float f)
@@ -914,6 +1043,7 @@ void wpsgpu_geo_free(wpsgpu_ctx* h)
         if (s->d_wm[b]) cudaFree(s->d_wm[b]);
         if (b == 0 && s->d_dstart) { cudaFree(s->d_dstart); s->d_dstart = nullptr; }
         if (s->d_bounds[b]) { cudaFree(s->d_bounds[b]); s->d_bounds[b] = nullptr; s->bounds_cap[b] = 0; }
+        if (s->d_terms[b]) { cudaFree(s->d_terms[b]); s->d_terms[b] = nullptr; s->terms_cap[b] = 0; }
         if (s->ev_pre[b]) cudaEventDestroy(s->ev_pre[b]);
         if (s->ev_used[b]) cudaEventDestroy(s->ev_used[b]);
     }
@@ -1069,11 +1199,49 @@ static int geo_flush_batch(wpsgpu_ctx* h)
         GeoTile& t = bt.t[z];
         t.tile = s->d_tile[p.set]; t.wm = s->d_wm[p.set]; t.dstart = s->d_dstart + p.set;
         t.xb = s->d_bounds[p.set]; t.yb = s->d_bounds[p.set] + std::max(0, (p.sMx - p.smx + 1) - 2 * p.bdr);
+        t.terms = s->d_terms[p.set];
         t.smx = p.smx; t.sMx = p.sMx; t.smy = p.smy; t.sMy = p.sMy; t.smz = p.smz; t.sMz = p.sMz; t.bdr = p.bdr;
         t.tnx = p.sMx - p.smx + 1; t.tny = p.sMy - p.smy + 1;
         gx = std::max(gx, (t.tnx - 2 * p.bdr + 31) / 32); gy = std::max(gy, (t.tny - 2 * p.bdr + 7) / 8);
         tmax = std::max(tmax, std::max(t.tnx, t.tny));
-        WPS_CUDA(cudaStreamWaitEvent(h->stream, s->ev_pre[p.set], 0));   // the tile and its mapping are in place
+    }
+    {   // pre-work of the whole batch on the staging stream (behind the tiles' copies): decode, where_maps_to, level tables
+        GeoRawBatch rb;
+        memset(&rb, 0, sizeof(rb));
+        bool any_raw = false;
+        int wx = 1, wy = 1, bnd = 1;
+        size_t maxpix = 1;
+        for (int z = 0; z < bt.n; ++z) {
+            const GeoState::Pending& p = s->pending[z];
+            const GeoTile& t = bt.t[z];
+            if (p.raw) {
+                GeoRaw& r = rb.r[z];
+                r.bytes = p.raw; r.out = s->d_tile[p.set]; r.wordsize = p.wordsize; r.is_signed = p.is_signed; r.little = p.little; r.flip = p.flip;
+                r.tnx = t.tnx; r.tny = t.tny; r.tnz = p.sMz - p.smz + 1;
+                maxpix = std::max(maxpix, (size_t)t.tnx * t.tny * r.tnz);
+                any_raw = true;
+            }
+            wx = std::max(wx, (t.tnx + WM_T - 1) / WM_T); wy = std::max(wy, (t.tny + WM_T - 1) / WM_T);
+            bnd = std::max(bnd, std::max(0, t.tnx - 2 * t.bdr) + std::max(0, t.tny - 2 * t.bdr));
+        }
+        if (any_raw) { k_geo_decode_b<<<dim3((unsigned)std::min<size_t>((maxpix + 255) / 256, 4096), 1, bt.n), 256, 0, s->s_pre>>>(rb); h->launches++; }
+        const bool separable = g.src.code == WPSGPU_PROJ_LATLON && (g.dom.code == WPSGPU_PROJ_LC || g.dom.code == WPSGPU_PROJ_PS);
+        if (separable) {
+            int tmx = 1;
+            for (int z = 0; z < bt.n; ++z) tmx = std::max(tmx, bt.t[z].tnx + bt.t[z].tny);
+            k_geo_wm_terms_b<<<dim3((tmx + 255) / 256, 1, bt.n), 256, 0, s->s_pre>>>(g, bt);
+            h->launches++;
+        }
+        if (separable) {
+            int mx = 1, my = 1;
+            for (int z = 0; z < bt.n; ++z) { mx = std::max(mx, bt.t[z].tnx); my = std::max(my, bt.t[z].tny); }
+            k_geo_wm_sep_b<<<dim3((mx + 511) / 512, my, bt.n), 256, 0, s->s_pre>>>(g, bt);
+        } else k_geo_wm_b<<<dim3(wx, wy, bt.n), 256, 0, s->s_pre>>>(g, bt, 0);
+        k_geo_dstart_b<<<dim3((GEO_DNODES + 255) / 256, 1, bt.n), 256, 0, s->s_pre>>>(bt);
+        k_geo_bounds_b<<<dim3((bnd + 255) / 256, 1, bt.n), 256, 0, s->s_pre>>>(bt);
+        h->launches += 3;
+        WPS_CUDA(cudaEventRecord(s->ev_pre[s->pending[0].set], s->s_pre));
+        WPS_CUDA(cudaStreamWaitEvent(h->stream, s->ev_pre[s->pending[0].set], 0));   // the tiles and their mappings are in place
     }
     unsigned long long* cnt = g.counters;
     k_geo_batch_reset<<<1, 32, 0, h->stream>>>(g.tbbox, cnt);
@@ -1102,7 +1270,8 @@ static int geo_flush_batch(wpsgpu_ctx* h)
     return 0;
 }
 
-static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, int sMx, int smy, int sMy, int smz, int sMz, int bdr)
+static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, int sMx, int smy, int sMy, int smz, int sMz, int bdr,
+                            const GeoRaw* raw = nullptr)
 {
     GeoState* s = h->geo;
     int tnx = sMx - smx + 1, tny = sMy - smy + 1;
@@ -1118,31 +1287,30 @@ static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, i
             WPS_TRY(geo_grow((void**)&s->d_wm[set], &s->wm_cap[set], (size_t)tnx * tny * sizeof(int2), pre));
         }
         g.wm = s->d_wm[set];
-        k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, pre>>>(g);
-        h->launches++;
-        if (geo_batchable(s) && pre != h->stream) {   // the batch kernel's walk starts where blocks with agreeing corners begin
+        if (geo_batchable(s) && pre != h->stream) {
+            // batch path: where_maps_to and the level tables are computed for the whole batch at once (geo_flush_batch)
             if (!s->d_dstart) WPS_CUDA(cudaMalloc((void**)&s->d_dstart, GEO_SETS * sizeof(int)));
-            WPS_CUDA(cudaMemsetAsync(s->d_dstart + set, 0x7f, sizeof(int), pre));
-            k_geo_dstart<<<(GEO_DNODES + 255) / 256, 256, 0, pre>>>(g.wm, smx, smy, tnx, smx + bdr, sMx - bdr, smy + bdr, sMy - bdr, s->d_dstart + set);
-            h->launches++;
-            const int inx = tnx - 2 * bdr, iny = tny - 2 * bdr;
-            if (inx > 0 && iny > 0) {
-                if ((size_t)(inx + iny) * sizeof(int2) > s->bounds_cap[set]) {
-                    WPS_CUDA(cudaStreamSynchronize(h->stream));
-                    WPS_TRY(geo_grow((void**)&s->d_bounds[set], &s->bounds_cap[set], (size_t)(inx + iny) * sizeof(int2), pre));
-                }
-                k_geo_bounds<<<(inx + iny + 255) / 256, 256, 0, pre>>>(s->d_dstart + set, smx + bdr, sMx - bdr, smy + bdr, sMy - bdr, s->d_bounds[set],
-                                                                   s->d_bounds[set] + inx);
-                h->launches++;
+            const int inx = std::max(0, tnx - 2 * bdr), iny = std::max(0, tny - 2 * bdr);
+            if ((size_t)(inx + iny + 1) * sizeof(int2) > s->bounds_cap[set]) {
+                WPS_CUDA(cudaStreamSynchronize(h->stream));
+                WPS_TRY(geo_grow((void**)&s->d_bounds[set], &s->bounds_cap[set], (size_t)(inx + iny + 1) * sizeof(int2), pre));
             }
+            if ((size_t)(2 * tnx + tny) * sizeof(float) > s->terms_cap[set]) {
+                WPS_CUDA(cudaStreamSynchronize(h->stream));
+                WPS_TRY(geo_grow((void**)&s->d_terms[set], &s->terms_cap[set], (size_t)(2 * tnx + tny) * sizeof(float), pre));
+            }
+        } else {
+            k_geo_wm<<<dim3((tnx + WM_T - 1) / WM_T, (tny + WM_T - 1) / WM_T), 256, 0, pre>>>(g);
+            h->launches++;
         }
     }
     if (accum && geo_batchable(s) && pre != h->stream) {
         // batch path: the tile waits, staged, until GEO_NB tiles have come together (or the level ends)
-        WPS_CUDA(cudaEventRecord(s->ev_pre[set], pre));
         if (!s->pending.empty() && (s->pending[0].smz != smz || s->pending[0].sMz != sMz)) WPS_TRY(geo_flush_batch(h));
         GeoState::Pending p;
         p.set = set; p.smx = smx; p.sMx = sMx; p.smy = smy; p.sMy = sMy; p.smz = smz; p.sMz = sMz; p.bdr = bdr;
+        p.raw = raw ? raw->bytes : nullptr;
+        p.wordsize = raw ? raw->wordsize : 0; p.is_signed = raw ? raw->is_signed : 0; p.little = raw ? raw->little : 0; p.flip = raw ? raw->flip : 0;
         s->pending.push_back(p);
         if ((int)s->pending.size() == GEO_NB) WPS_TRY(geo_flush_batch(h));
         return 0;
@@ -1228,6 +1396,15 @@ int wpsgpu_geogrid_add_tile_raw(wpsgpu_handle_t h, const void* bytes, int wordsi
         WPS_CUDA(cudaMemcpyAsync(s->d_raw[set], bytes, n * wordsize, cudaMemcpyHostToDevice, pre));
         WPS_TRY(geo_tile_staged(h, pre));
         d_bytes = (const unsigned char*)s->d_raw[set];
+    }
+    const bool accum = s->l.itype == WPSGPU_CATEGORICAL || s->l.itype == WPSGPU_SP_CONTINUOUS;
+    if (accum && geo_batchable(s) && pre != h->stream) {
+        // batch path: the bytes are decoded together with the other tiles of the batch
+        GeoRaw raw;
+        memset(&raw, 0, sizeof(raw));
+        raw.bytes = d_bytes; raw.wordsize = wordsize; raw.is_signed = is_signed; raw.little = endian == 1; raw.flip = row_order == 2;
+        WPS_TRY(geo_process_tile(h, set, pre, src_min_x, src_max_x, src_min_y, src_max_y, src_min_z, src_max_z, bdr, &raw));
+        return 0;
     }
     k_geo_decode<<<(unsigned)((n + 255) / 256), 256, 0, pre>>>(d_bytes, wordsize, is_signed, endian == 1, row_order == 2, tnx, tny, tnz, s->d_tile[set]);
     h->launches++;
