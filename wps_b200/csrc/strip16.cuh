@@ -286,7 +286,11 @@ __device__ __noinline__ void strip_slow_push(const SlowQ Q, unsigned s0, unsigne
 // the cached coordinates and the record-array geometry, so the level-independent set-up -- cells, weights, window box --
 // is done once per block and only the landmask / fill logic is redone per job.
 template <int R, int STAGE>
+#ifdef STRIP_MAXREG
+__global__ void __launch_bounds__(32) __maxnreg__(STRIP_MAXREG)
+#else
 __global__ void __launch_bounds__(32, R == 4 ? STRIP_MINB : 20)
+#endif
 k_metgrid_strip16(const __grid_constant__ StripParams P)
 {
     constexpr int WIN = R > 1 ? 5 : 4;
