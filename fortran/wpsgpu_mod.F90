@@ -72,6 +72,16 @@ module wpsgpu_mod
       integer(c_int32_t) :: sr_x, sr_y
    end type wpsgpu_geo_level
 
+   ! mpas_mesh_type (mpas_mesh.F:5-30) as c_loc's of the module's arrays
+   type, bind(C) :: wpsgpu_mpas_mesh
+      integer(c_int32_t) :: nCells, nVertices, nEdges, maxEdges
+      type(c_ptr) :: landmask, nEdgesOnCell
+      type(c_ptr) :: cellsOnCell, verticesOnCell, edgesOnCell
+      type(c_ptr) :: cellsOnVertex
+      type(c_ptr) :: cellsOnEdge
+      type(c_ptr) :: latCell, lonCell, latVertex, lonVertex, latEdge, lonEdge
+   end type wpsgpu_mpas_mesh
+
    interface
       integer(c_int) function wpsgpu_create(device_id, handle) bind(C, name='wpsgpu_create')
          import :: c_int, c_ptr
@@ -372,6 +382,41 @@ module wpsgpu_mod
          integer(c_int), value :: si, sj, sk, ei, ej, ek, sr_y
          real(c_float), value :: dom_dy
          real(c_float) :: src(*), dst(*)
+      end function
+      ! ---- MPAS remapping (remapper.F; process_mpas_fields, process_domain_module.F:1457-1962) ----
+      integer(c_int) function wpsgpu_mpas_set_mesh(handle, mesh) bind(C, name='wpsgpu_mpas_set_mesh')
+         import :: c_int, c_ptr, wpsgpu_mpas_mesh
+         type(c_ptr), value :: handle
+         type(wpsgpu_mpas_mesh) :: mesh
+      end function
+      integer(c_int) function wpsgpu_mpas_remap_setup(handle, grid_id, lat_rad, lon_rad, nlon, nlat) bind(C, name='wpsgpu_mpas_remap_setup')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle
+         integer(c_int), value :: grid_id, nlon, nlat
+         real(c_float) :: lat_rad(*), lon_rad(*)
+      end function
+      integer(c_int) function wpsgpu_mpas_get_tables(handle, grid_id, kind, nearest, sources, weights) bind(C, name='wpsgpu_mpas_get_tables')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: grid_id, kind
+         type(c_ptr), value :: nearest, sources, weights      ! c_loc of the remap_info arrays, or c_null_ptr
+      end function
+      integer(c_int) function wpsgpu_mpas_remap_field(handle, grid_id, decomp, xtype, masked, src, nlev, nw, dst) &
+                        bind(C, name='wpsgpu_mpas_remap_field')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: grid_id, decomp, xtype, masked, nlev, nw
+         type(c_ptr), value :: src, dst                       ! c_loc(mpas_field % array2r), c_loc(wrf_field % array3r), ...
+      end function
+      integer(c_int) function wpsgpu_mpas_remap_planes(handle, grid_id, decomp, masked, src, nlev, mode, landmask, fill_missing, planes) &
+                        bind(C, name='wpsgpu_mpas_remap_planes')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle
+         integer(c_int), value :: grid_id, decomp, masked, nlev, mode
+         real(c_float) :: src(*)
+         type(c_ptr), value :: landmask                       ! c_loc(landmask) or c_null_ptr
+         real(c_float), value :: fill_missing
+         type(c_ptr) :: planes(*)                             ! c_loc(field_to_store % r_arr) of every level
       end function
    end interface
 

@@ -308,6 +308,51 @@ int wpsgpu_dfdx(wpsgpu_handle_t h, const float *src, float *dst, int si, int sj,
 int wpsgpu_dfdy(wpsgpu_handle_t h, const float *src, float *dst, int si, int sj, int sk, int ei, int ej, int ek,
                 int sr_y, const float *mapfac, float dom_dy);
 
+/* ---- metgrid: MPAS source remapping (metgrid/src/remapper.F, process_domain_module.F:1457-1962) ---- */
+#define WPSGPU_MPAS_CELLS 0      /* decomposed dimension nCells (remapper.F:445) */
+#define WPSGPU_MPAS_VERTICES 1   /* nVertices (:454) */
+#define WPSGPU_MPAS_EDGES 2      /* nEdges (:458) */
+#define WPSGPU_MPAS_MASKED_CELLS 3   /* table selector only: sourceMaskedCells / cellMaskedWeights (:448-450) */
+#define WPSGPU_MPAS_REAL 0       /* FIELD_TYPE_REAL / _DOUBLE / _INTEGER of scan_input.F */
+#define WPSGPU_MPAS_DOUBLE 1
+#define WPSGPU_MPAS_INTEGER 2
+/* mpas_mesh_type (mpas_mesh.F:5-30) as mpas_mesh_setup fills it: connectivity 1-based as in the file, Fortran
+ * (maxEdges, nCells) = C [nCells][maxEdges]; latitudes / longitudes in radians.  Always HOST arrays. */
+typedef struct wpsgpu_mpas_mesh {
+    int32_t nCells, nVertices, nEdges, maxEdges;
+    const int32_t *landmask, *nEdgesOnCell;
+    const int32_t *cellsOnCell, *verticesOnCell, *edgesOnCell;
+    const int32_t *cellsOnVertex;    /* [nVertices][3] */
+    const int32_t *cellsOnEdge;      /* [nEdges][2] */
+    const float *latCell, *lonCell, *latVertex, *lonVertex, *latEdge, *lonEdge;
+} wpsgpu_mpas_mesh;
+/* mpas_mesh_setup (mpas_mesh.F:36): the mesh is copied to the device and kept by the handle. */
+int wpsgpu_mpas_set_mesh(wpsgpu_handle_t h, const wpsgpu_mpas_mesh *mesh);
+/* target_mesh_setup(lat2d, lon2d) + remap_info_setup (remapper.F:83-286) for target grid `grid_id` (0..2: the mass, U
+ * and V grids of process_mpas_fields, :1535-1590).  lat_rad / lon_rad(nlon, nlat), x fastest, radians.  Builds
+ * nearestCell / nearestVertex / nearestEdge, the Wachspress tables of cells, vertices and edges and the masked cell
+ * table (landmask == 1 cells only, search_for_cells where all three are water) on the device; one thread per target
+ * point instead of the reference's sequential scan, which hands every point the previous point's result as the start
+ * of its greedy walk -- the walks end in the same cell / vertex / edge except where two candidates are equidistant
+ * in binary32. */
+int wpsgpu_mpas_remap_setup(wpsgpu_handle_t h, int grid_id, const float *lat_rad, const float *lon_rad, int nlon, int nlat);
+/* the tables of remap_info_type (remapper.F:19-40) for `kind`: nearest(nlon*nlat) [NULL for MASKED_CELLS],
+ * sources / weights(nlon*nlat, width) with width 3 (cells, masked cells) or maxEdges; any output may be NULL */
+int wpsgpu_mpas_get_tables(wpsgpu_handle_t h, int grid_id, int kind, int32_t *nearest, int32_t *sources, float *weights);
+/* remap_field (remapper.F:417-663): dst(nlev, nlon, nlat) from src(nlev, nNodes), level index fastest in both (nlev =
+ * product of the non-decomposed dimensions, 1 for a 1-d field).  REAL / DOUBLE: weighted sum over the first nw table
+ * entries in the reference's order (nw = 3 for 2-d and 3-d sources as :522, :535; the table width for 1-d sources as
+ * :506; 0 selects by nlev like the reference); INTEGER: nearest node.  masked != 0 selects the masked cell table. */
+int wpsgpu_mpas_remap_field(wpsgpu_handle_t h, int grid_id, int decomp, int xtype, int masked, const void *src, int nlev,
+                            int nw, void *dst);
+/* remap_field of a REAL field fused with process_mpas_fields' per-level extraction (:1700-1956): writes the r_arr
+ * planes(nlon, nlat) directly.  mode 0: plane k = level k (nVertLevels, nSoilLevels, 2-d fields); mode 1
+ * (nVertLevelsP1, :1733-1776): plane 0 = level 1 (stored at 200100), plane k = 0.5 * (level k + level k+1), k = 1 ..
+ * nlev-1.  landmask (may be NULL): `where (landmask == 0) r_arr = fill_missing` (:1854, :1948).  planes: HOST array of
+ * nlev pointers that follow the pointer mode. */
+int wpsgpu_mpas_remap_planes(wpsgpu_handle_t h, int grid_id, int decomp, int masked, const float *src, int nlev, int mode,
+                             const float *landmask, float fill_missing, float *const *planes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -464,3 +464,74 @@ def fill_missing_levels(levels, r_arr, valid):
     lv = np.ascontiguousarray(levels, np.int32)
     lib().orc_fill_missing_levels(int(nlev), lv.ctypes.data_as(C.c_void_p), fptr(r), iptr(v), int(nx), int(ny))
     return r, v
+
+
+# ---- MPAS remapping (orc_mpas.c) ----
+_MESH_INT = ("landmask", "nEdgesOnCell", "cellsOnCell", "verticesOnCell", "edgesOnCell", "cellsOnVertex", "cellsOnEdge")
+_MESH_REAL = ("latCell", "lonCell", "latVertex", "lonVertex", "latEdge", "lonEdge")
+
+
+class MpasMesh(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nCells", "nVertices", "nEdges", "maxEdges")] + [(n, C.c_void_p) for n in _MESH_INT + _MESH_REAL]
+
+
+class MpasRemap(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("nearestCell", "nearestVertex", "nearestEdge", "sourceCells", "cellWeights", "sourceVertices",
+                                          "vertexWeights", "sourceEdges", "edgeWeights", "sourceMaskedCells", "cellMaskedWeights")]
+
+
+def _mpas_mesh(mesh):
+    d = MpasMesh(nCells=mesh["nCells"], nVertices=mesh["nVertices"], nEdges=mesh["nEdges"], maxEdges=mesh["maxEdges"])
+    keep = []
+    for n in _MESH_INT + _MESH_REAL:
+        a = np.ascontiguousarray(mesh[n], dtype=np.int32 if n in _MESH_INT else np.float32)
+        keep.append(a)
+        setattr(d, n, a.ctypes.data)
+    return d, keep
+
+
+def mpas_remap_setup(mesh, lat_rad, lon_rad):
+    """remap_info_setup (remapper.F:83-286), sequential scan as in the reference; returns a dict of the tables."""
+    d, keep = _mpas_mesh(mesh)
+    nlat, nlon = lat_rad.shape
+    me = mesh["maxEdges"]
+    t = dict(nearestCell=np.zeros((nlat, nlon), np.int32), nearestVertex=np.zeros((nlat, nlon), np.int32),
+             nearestEdge=np.zeros((nlat, nlon), np.int32),
+             sourceCells=np.zeros((nlat, nlon, 3), np.int32), cellWeights=np.zeros((nlat, nlon, 3), np.float32),
+             sourceVertices=np.zeros((nlat, nlon, me), np.int32), vertexWeights=np.zeros((nlat, nlon, me), np.float32),
+             sourceEdges=np.zeros((nlat, nlon, me), np.int32), edgeWeights=np.zeros((nlat, nlon, me), np.float32),
+             sourceMaskedCells=np.zeros((nlat, nlon, 3), np.int32), cellMaskedWeights=np.zeros((nlat, nlon, 3), np.float32))
+    r = MpasRemap(**{k: v.ctypes.data for k, v in t.items()})
+    lib().orc_mpas_remap_setup(C.byref(d), fptr(np.ascontiguousarray(lat_rad)), fptr(np.ascontiguousarray(lon_rad)), nlon, nlat, C.byref(r))
+    return t
+
+
+def mpas_remap_field(sources, weights, src, nw=0):
+    """remap_field for REAL / DOUBLE sources [nNodes][nlev] with the given tables [nlat][nlon][width]."""
+    nlat, nlon, tw = sources.shape
+    src2 = src.reshape(src.shape[0], -1)
+    nlev = src2.shape[1]
+    if nw == 0:
+        nw = tw if src.ndim == 1 else 3
+    out = np.zeros((nlat, nlon, nlev), src.dtype)
+    fn = lib().orc_mpas_remap_field_real if src.dtype == np.float32 else lib().orc_mpas_remap_field_double
+    fn(iptr(np.ascontiguousarray(sources)), fptr(np.ascontiguousarray(weights)), tw, nw, C.c_long(nlat * nlon),
+       C.c_void_p(np.ascontiguousarray(src2).ctypes.data), nlev, C.c_void_p(out.ctypes.data))
+    return out
+
+
+def mpas_remap_field_int(nearest, src):
+    nlat, nlon = nearest.shape
+    src2 = np.ascontiguousarray(src.reshape(src.shape[0], -1), dtype=np.int32)
+    out = np.zeros((nlat, nlon, src2.shape[1]), np.int32)
+    lib().orc_mpas_remap_field_int(iptr(np.ascontiguousarray(nearest)), C.c_long(nlat * nlon), iptr(src2), src2.shape[1], iptr(out))
+    return out
+
+
+def mpas_extract_planes(wrf, mode=0, landmask=None, fill=0.0):
+    """process_mpas_fields' per-level planes of a remapped field wrf [nlat][nlon][nlev] -> [nlev][nlat][nlon]."""
+    nlat, nlon, nlev = wrf.shape
+    out = np.zeros((nlev, nlat, nlon), np.float32)
+    lib().orc_mpas_extract_planes(fptr(np.ascontiguousarray(wrf)), nlev, C.c_long(nlat * nlon), int(mode),
+                                  fptr(None if landmask is None else np.ascontiguousarray(landmask, dtype=np.float32)), C.c_float(fill), fptr(out))
+    return out

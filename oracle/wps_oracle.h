@@ -226,4 +226,32 @@ void orc_calc_dfdy(const float *src, float *dst, int si, int sj, int sk, int ei,
 /* fill_missing_levels vertical interpolation, process_domain_module.F:2862-2921 */
 void orc_fill_missing_levels(int nlev, const int32_t *levels, float *r_arr, int32_t *valid, int nx, int ny);
 
+/* ---- MPAS remapping (metgrid/src/remapper.F, mpas_mesh.F:5-30); connectivity 1-based, C row = Fortran last index ---- */
+typedef struct orc_mpas_mesh {
+    int nCells, nVertices, nEdges, maxEdges;
+    const int *landmask, *nEdgesOnCell;                       /* [nCells] */
+    const int *cellsOnCell, *verticesOnCell, *edgesOnCell;    /* [nCells][maxEdges] */
+    const int *cellsOnVertex;                                 /* [nVertices][3] */
+    const int *cellsOnEdge;                                   /* [nEdges][2] */
+    const float *latCell, *lonCell, *latVertex, *lonVertex, *latEdge, *lonEdge;   /* radians */
+} orc_mpas_mesh;
+typedef struct orc_mpas_remap {      /* remap_info_type, remapper.F:19-40; point index = ix + nlon * iy */
+    int *nearestCell, *nearestVertex, *nearestEdge;           /* [npts] */
+    int *sourceCells; float *cellWeights;                     /* [npts][3] */
+    int *sourceVertices; float *vertexWeights;                /* [npts][maxEdges] */
+    int *sourceEdges; float *edgeWeights;                     /* [npts][maxEdges] */
+    int *sourceMaskedCells; float *cellMaskedWeights;         /* [npts][3] */
+} orc_mpas_remap;
+int  orc_mpas_nearest_cell(const orc_mpas_mesh *m, float tlat, float tlon, int start_cell);
+int  orc_mpas_nearest_vertex(const orc_mpas_mesh *m, float tlat, float tlon, int start, int degree);
+void orc_mpas_wachspress3(const float vert[3][3], const float p[3], float w[3]);
+void orc_mpas_search_for_cells(const orc_mpas_mesh *m, float tlat, float tlon, int start, int cells[3], float w[3]);
+void orc_mpas_remap_setup(const orc_mpas_mesh *m, const float *lat, const float *lon, int nlon, int nlat, orc_mpas_remap *r);
+void orc_mpas_remap_field_real(const int *sourceNodes, const float *nodeWeights, int tw, int nw, long npts, const float *src,
+                               int nlev, float *dst);
+void orc_mpas_remap_field_double(const int *sourceNodes, const float *nodeWeights, int tw, int nw, long npts, const double *src,
+                                 int nlev, double *dst);
+void orc_mpas_remap_field_int(const int *nearest, long npts, const int *src, int nlev, int *dst);
+void orc_mpas_extract_planes(const float *wrf, int nlev, long npts, int mode, const float *landmask, float fill, float *planes);
+
 #endif

@@ -42,6 +42,12 @@ int main(void)
     OFF(wpsgpu_geo_level, src_proj); OFF(wpsgpu_geo_level, ilevel); OFF(wpsgpu_geo_level, itype); OFF(wpsgpu_geo_level, ops);
     OFF(wpsgpu_geo_level, opts); OFF(wpsgpu_geo_level, msg_val); OFF(wpsgpu_geo_level, msg_fill_val); OFF(wpsgpu_geo_level, mask_val);
     OFF(wpsgpu_geo_level, has_scale); OFF(wpsgpu_geo_level, scale_factor); OFF(wpsgpu_geo_level, sr_x); OFF(wpsgpu_geo_level, sr_y);
+    SZ(wpsgpu_mpas_mesh);
+    OFF(wpsgpu_mpas_mesh, nCells); OFF(wpsgpu_mpas_mesh, nVertices); OFF(wpsgpu_mpas_mesh, nEdges); OFF(wpsgpu_mpas_mesh, maxEdges);
+    OFF(wpsgpu_mpas_mesh, landmask); OFF(wpsgpu_mpas_mesh, nEdgesOnCell); OFF(wpsgpu_mpas_mesh, cellsOnCell); OFF(wpsgpu_mpas_mesh, verticesOnCell);
+    OFF(wpsgpu_mpas_mesh, edgesOnCell); OFF(wpsgpu_mpas_mesh, cellsOnVertex); OFF(wpsgpu_mpas_mesh, cellsOnEdge); OFF(wpsgpu_mpas_mesh, latCell);
+    OFF(wpsgpu_mpas_mesh, lonCell); OFF(wpsgpu_mpas_mesh, latVertex); OFF(wpsgpu_mpas_mesh, lonVertex); OFF(wpsgpu_mpas_mesh, latEdge);
+    OFF(wpsgpu_mpas_mesh, lonEdge);
     /* linked calls: map_set of a Lambert conformal projection (host arithmetic) and the error string of a rejected one */
     wpsgpu_map_args a;
     wpsgpu_proj p;

@@ -199,7 +199,7 @@ def test_struct_layouts_agree_between_c_ctypes_and_fortran(tmp_path):
     assert lay["map_set_ok"] == 0 and lay["map_set_without_dx"] != 0 and lay["error_text_length"] > 0
     assert abs(lay["cone"] - 0.715567) < 1e-5                   # cone factor of a 30 / 60 Lambert projection
     pairs = {"wpsgpu_proj": capi.Proj, "wpsgpu_map_args": capi.MapArgs, "wpsgpu_field_opts": capi.FieldOpts, "wpsgpu_slab": capi.Slab,
-             "wpsgpu_geo_field": capi.GeoField, "wpsgpu_geo_level": capi.GeoLevel}
+             "wpsgpu_geo_field": capi.GeoField, "wpsgpu_geo_level": capi.GeoLevel, "wpsgpu_mpas_mesh": capi.MpasMesh}
     for cname, ct in pairs.items():
         assert C.sizeof(ct) == lay["sizeof(%s)" % cname], cname
         cfields = [k.split(".")[1] for k in lay if k.startswith(cname + ".")]

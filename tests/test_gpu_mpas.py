@@ -1,0 +1,217 @@
+"""GPU parity of the MPAS remapping path (wps_b200/csrc/mpas.cu, remapper.F) through the C ABI, against oracle/orc_mpas.c."""
+import numpy as np
+import pytest
+
+from wps_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+KEYS = {0: ("nearestCell", "sourceCells", "cellWeights"), 1: ("nearestVertex", "sourceVertices", "vertexWeights"),
+        2: ("nearestEdge", "sourceEdges", "edgeWeights"), 3: (None, "sourceMaskedCells", "cellMaskedWeights")}
+
+
+def assert_weights(w, ref, what):
+    """Weights are bit-identical wherever the binary64 sin / cos / tan / asin / atan of CUDA and glibc round to the same
+    binary32 value (the shared FP64-then-round policy, as for the projections).  A 1-ulp difference in one of them is amplified
+    by the cancellation in Heron's formula on small triangles -- binary32 in the reference too, whose own weights move by up to
+    4e-4 (cells) between glibc's float and double functions -- and without bound where the 'polygon' of a cell's first three
+    vertices / edges (:204, :238) is nearly degenerate and the weights reach 1e2..1e3: those points are compared for being
+    finite at the same places only."""
+    assert np.array_equal(np.isfinite(w), np.isfinite(ref)), what
+    same = (w.view(np.int32) == ref.view(np.int32)) | ~np.isfinite(ref)
+    assert same.mean() > 0.999, (what, same.mean())
+    ok = np.isfinite(ref).all(-1) & (np.abs(np.nan_to_num(ref)).max(-1) < 50.0)
+    d = np.abs(w[ok].astype(np.float64) - ref[ok]) / np.maximum(1.0, np.abs(ref[ok]))
+    assert d.max() < 1e-3, (what, d.max())
+
+
+def lambert_target(nx, ny, dx, stagger=None):
+    """lat / lon in radians of a Lambert grid over North America (process_mpas_fields: xlat * deg2rad, :1538-1541)."""
+    from wps_b200 import capi
+    dom = synth.lambert_domain(nx, ny, dx, 30.0, 60.0, -98.0, 34.83, -81.03)
+    h = capi.Handle(0)
+    xlat, xlon = h.xytoll_grid(dom, stagger or capi.M, 1, 1, nx, ny)
+    h.close()
+    d2r = np.float32(np.arcsin(np.float32(1.0)) / np.float32(90.0))
+    return np.ascontiguousarray(xlat * d2r), np.ascontiguousarray(xlon * d2r)
+
+
+@pytest.fixture(scope="module")
+def setup(orc):
+    from wps_b200 import capi
+    mesh = synth.mpas_mesh(10242, seed=2)
+    lat, lon = lambert_target(150, 120, 60000.0)
+    orc.set_transc_mode(1)
+    t = orc.mpas_remap_setup(mesh, lat, lon)
+    h = capi.Handle(0)
+    h.mpas_set_mesh(mesh)
+    h.mpas_remap_setup(0, lat, lon)
+    yield mesh, lat, lon, t, h
+    h.close()
+
+
+def test_tables_equal_the_sequential_scan(setup):
+    """Every table of remap_info_setup, bit for bit: the device reproduces the reference's point-after-point scan (each walk
+    starts at the previous point's result), including the masked scan whose start is a cell index after a search point."""
+    mesh, lat, lon, t, h = setup
+    nsearch = 0
+    for kind, (kn, ks, kw) in KEYS.items():
+        near, src, w = h.mpas_get_tables(0, kind)
+        if kn:
+            assert np.array_equal(near, t[kn]), kn
+        assert np.array_equal(src, t[ks]), ks
+        assert_weights(w, t[kw], kw)
+        if kind == 3:
+            nsearch = int(((src[..., 1] == 1) & (src[..., 2] == 1)).sum())
+    assert nsearch > 1000            # open-ocean points went through search_for_cells
+    # start sensitivity is real on this mesh: the edge walk has points with a second fixed point
+    nodes = mesh["edgesOnCell"][t["nearestCell"] - 1]
+    assert ((nodes == t["nearestEdge"][..., None]).any(-1)).mean() < 1.0
+
+
+def test_second_grid_and_other_meshes(orc):
+    """U-staggered target on grid slot 1, a coarse and a finer mesh, a target that crosses the date line and the pole."""
+    from wps_b200 import capi
+    orc.set_transc_mode(1)
+    h = capi.Handle(0)
+    for ncells, seed in ((642, 5), (40962, 6)):
+        mesh = synth.mpas_mesh(ncells, seed=seed)
+        h.mpas_set_mesh(mesh)
+        lat, lon = lambert_target(91, 70, 90000.0, stagger=capi.U)
+        ny, nx = 40, 64
+        lat2 = np.ascontiguousarray(np.deg2rad(np.linspace(60.0, 89.9, ny, dtype=np.float32))[:, None] * np.ones((1, nx), np.float32))
+        lon2 = np.ascontiguousarray(np.deg2rad(np.linspace(-180.0, 180.0, nx, dtype=np.float32))[None, :] * np.ones((ny, 1), np.float32))
+        for slot, (la, lo) in ((1, (lat, lon)), (2, (lat2, lon2))):
+            t = orc.mpas_remap_setup(mesh, la, lo)
+            h.mpas_remap_setup(slot, la, lo)
+            for kind, (kn, ks, kw) in KEYS.items():
+                near, src, w = h.mpas_get_tables(slot, kind)
+                if kn:
+                    assert np.array_equal(near, t[kn]), (ncells, slot, kn)
+                assert np.array_equal(src, t[ks]), (ncells, slot, ks)
+                assert_weights(w, t[kw], (ncells, slot, kw))
+    h.close()
+
+
+def test_all_water_and_all_land_masks(orc):
+    """landmask all 0: every point runs search_for_cells to exhaustion (cells (1,1,1), weights 0) -- with the bounded queue of
+    2700 entries overrunning on the 10242-cell mesh; all 1: no search at all."""
+    from wps_b200 import capi
+    orc.set_transc_mode(1)
+    h = capi.Handle(0)
+    mesh = synth.mpas_mesh(10242, seed=2)
+    lat, lon = lambert_target(40, 30, 150000.0)
+    for val in (0, 1):
+        mesh["landmask"][:] = val
+        h.mpas_set_mesh(mesh)
+        h.mpas_remap_setup(0, lat, lon)
+        t = orc.mpas_remap_setup(mesh, lat, lon)
+        _, src, w = h.mpas_get_tables(0, capi.MPAS_MASKED_CELLS)
+        assert np.array_equal(src, t["sourceMaskedCells"])
+        assert_weights(w, t["cellMaskedWeights"], val)
+        if val == 0:
+            assert (src == 1).all() and (w == 0.0).all()
+    h.close()
+
+
+def device_tables(h, t):
+    """the oracle's table dict with the device's weights (identical integer tables are asserted elsewhere)"""
+    from wps_b200 import capi
+    d = dict(t)
+    for kind, (kn, ks, kw) in KEYS.items():
+        _, src, w = h.mpas_get_tables(0, kind)
+        assert np.array_equal(src, t[ks])
+        d[kw] = w
+    return d
+
+
+def test_remap_field_bit_exact(setup, orc):
+    from wps_b200 import capi
+    mesh, lat, lon, t, h = setup
+    t = device_tables(h, t)
+    for nlev in (1, 4, 55):
+        f = synth.mpas_field(mesh, nlev, seed=nlev)
+        for masked, ks, kw in ((False, "sourceCells", "cellWeights"), (True, "sourceMaskedCells", "cellMaskedWeights")):
+            got = h.mpas_remap_field(0, capi.MPAS_CELLS, f, masked=masked, nw=3)
+            ref = orc.mpas_remap_field(t[ks], t[kw], f, nw=3)
+            assert np.array_equal(got.view(np.int32), ref.view(np.int32)), (nlev, masked)
+    # 1-d sources on vertices / edges: all maxEdges table entries take part (remapper.F:506-511)
+    for decomp, where, ks, kw in ((capi.MPAS_VERTICES, "Vertex", "sourceVertices", "vertexWeights"), (capi.MPAS_EDGES, "Edge", "sourceEdges", "edgeWeights")):
+        v = synth.mpas_field(mesh, 1, seed=9, where=where)[:, 0].copy()
+        got = h.mpas_remap_field(0, decomp, v)
+        ref = orc.mpas_remap_field(t[ks], t[kw], v)
+        assert np.array_equal(got.view(np.int32), ref.view(np.int32)), where
+        v3 = synth.mpas_field(mesh, 3, seed=10, where=where)
+        got = h.mpas_remap_field(0, decomp, v3)
+        ref = orc.mpas_remap_field(t[ks], t[kw], v3)
+        assert np.array_equal(got.view(np.int32), ref.view(np.int32)), where
+    # DOUBLE (REAL weight promoted) and INTEGER (nearest node) sources
+    f64 = synth.mpas_field(mesh, 5, seed=11).astype(np.float64) * 1.0000001234
+    got = h.mpas_remap_field(0, capi.MPAS_CELLS, f64)
+    assert np.array_equal(got.view(np.int64), orc.mpas_remap_field(t["sourceCells"], t["cellWeights"], f64).view(np.int64))
+    for decomp, where, kn in ((capi.MPAS_CELLS, "Cell", "nearestCell"), (capi.MPAS_VERTICES, "Vertex", "nearestVertex"), (capi.MPAS_EDGES, "Edge", "nearestEdge")):
+        fi = (synth.mpas_field(mesh, 2, seed=12, where=where) * 100).astype(np.int32)
+        assert np.array_equal(h.mpas_remap_field(0, decomp, fi), orc.mpas_remap_field_int(t[kn], fi)), where
+
+
+def test_remap_planes_fused_extraction(setup, orc):
+    """remap + per-level planes of process_mpas_fields: plain levels, the nVertLevelsP1 rule, landmask fill of masked=water
+    fields (process_domain_module.F:1700-1956), more levels than one launch takes (256)."""
+    from wps_b200 import capi
+    mesh, lat, lon, t, h = setup
+    t = device_tables(h, t)
+    ny, nx = lat.shape
+    lm = (np.sin(np.arange(ny * nx, dtype=np.float64) * 0.37).reshape(ny, nx) > -0.2).astype(np.float32)
+    for nlev, mode, masked, landmask in ((55, 0, False, None), (56, 1, False, None), (4, 0, True, lm), (1, 0, True, lm), (300, 1, False, None)):
+        f = synth.mpas_field(mesh, nlev, seed=20 + nlev)
+        ks, kw = ("sourceMaskedCells", "cellMaskedWeights") if masked else ("sourceCells", "cellWeights")
+        wrf = orc.mpas_remap_field(t[ks], t[kw], f, nw=3)
+        ref = orc.mpas_extract_planes(wrf, mode, landmask=landmask, fill=-1.0e30)
+        planes = [np.full((ny, nx), np.nan, np.float32) for _ in range(nlev)]
+        h.mpas_remap_planes(0, capi.MPAS_CELLS, f if nlev > 1 else f[:, 0].copy(), planes, mode=mode, masked=masked, landmask=landmask, fill_missing=-1.0e30)
+        got = np.stack(planes)
+        assert np.array_equal(got.view(np.int32), ref.view(np.int32)), (nlev, mode, masked)
+
+
+def test_device_pointer_mode(setup, orc):
+    import torch
+    from wps_b200 import capi
+    mesh, lat, lon, t, h0 = setup
+    t = device_tables(h0, t)
+    h = capi.Handle(0, capi.PTR_DEVICE)
+    dev = torch.device("cuda", 0)
+    h.mpas_set_mesh(mesh)                                         # the mesh is always a host structure
+    h.mpas_remap_setup(0, torch.from_numpy(lat).to(dev), torch.from_numpy(lon).to(dev))
+    f = synth.mpas_field(mesh, 8, seed=30)
+    fd = torch.from_numpy(f).to(dev)
+    out = h.mpas_remap_field(0, capi.MPAS_CELLS, fd)
+    torch.cuda.synchronize()
+    ref = orc.mpas_remap_field(t["sourceCells"], t["cellWeights"], f, nw=3)
+    assert np.array_equal(out.cpu().numpy().view(np.int32), ref.view(np.int32))
+    planes = [torch.empty(lat.shape, dtype=torch.float32, device=dev) for _ in range(8)]
+    h.mpas_remap_planes(0, capi.MPAS_CELLS, fd, planes)
+    h.synchronize()
+    assert np.array_equal(torch.stack(planes).cpu().numpy().view(np.int32), np.moveaxis(ref, 2, 0).view(np.int32))
+    h.close()
+
+
+def test_errors(setup):
+    from wps_b200 import capi
+    mesh, lat, lon, t, _ = setup
+    h = capi.Handle(0)
+    with pytest.raises(capi.WpsGpuError, match="no MPAS mesh"):
+        h._mpas_grids = {}
+        h.mpas_remap_setup(0, lat, lon)
+    bad = dict(mesh)
+    bad["cellsOnCell"] = mesh["cellsOnCell"].copy()
+    bad["cellsOnCell"][5, 0] = mesh["nCells"] + 7
+    with pytest.raises(capi.WpsGpuError, match="limited-area|out of range"):
+        h.mpas_set_mesh(bad)
+    h.mpas_set_mesh(mesh)
+    with pytest.raises(capi.WpsGpuError, match="has not run"):
+        h._mpas_grids[1] = lat.shape
+        h.mpas_remap_field(1, capi.MPAS_CELLS, synth.mpas_field(mesh, 2))
+    with pytest.raises(capi.WpsGpuError, match="grid_id"):
+        h._mpas_grids[5] = lat.shape
+        h.mpas_remap_field(5, capi.MPAS_CELLS, synth.mpas_field(mesh, 2))
+    h.close()

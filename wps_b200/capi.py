@@ -71,6 +71,17 @@ class GeoLevel(C.Structure):
                 ("sr_x", C.c_int32), ("sr_y", C.c_int32)]
 
 
+MPAS_CELLS, MPAS_VERTICES, MPAS_EDGES, MPAS_MASKED_CELLS = 0, 1, 2, 3
+MPAS_REAL, MPAS_DOUBLE, MPAS_INTEGER = 0, 1, 2
+_MESH_INT = ("landmask", "nEdgesOnCell", "cellsOnCell", "verticesOnCell", "edgesOnCell", "cellsOnVertex", "cellsOnEdge")
+_MESH_REAL = ("latCell", "lonCell", "latVertex", "lonVertex", "latEdge", "lonEdge")
+
+
+class MpasMesh(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("nCells", "nVertices", "nEdges", "maxEdges")] + \
+               [(n, C.c_void_p) for n in _MESH_INT + _MESH_REAL]
+
+
 class WpsGpuError(RuntimeError):
     pass
 
@@ -485,6 +496,61 @@ class Handle:
         check(fn(self._h, C.c_void_p(ptr(src)), C.c_void_p(ptr(out)), 1, 1, 1, nx, ny, nz, int(sr),
                  C.c_void_p(ptr(mapfac)), C.c_float(dom_d)))
         return out
+
+    # ---- MPAS remapping (remapper.F) ----
+    def mpas_set_mesh(self, mesh):
+        """mpas_mesh_setup: `mesh` is a dict of numpy arrays (1-based connectivity, radians) as synth.mpas_mesh makes it."""
+        d = MpasMesh(nCells=mesh["nCells"], nVertices=mesh["nVertices"], nEdges=mesh["nEdges"], maxEdges=mesh["maxEdges"])
+        keep = []
+        for n in _MESH_INT + _MESH_REAL:
+            a = np.ascontiguousarray(mesh[n], dtype=np.int32 if n in _MESH_INT else np.float32)
+            keep.append(a)
+            setattr(d, n, a.ctypes.data)
+        check(lib().wpsgpu_mpas_set_mesh(self._h, C.byref(d)))
+        self._mpas_dims = (mesh["nCells"], mesh["nVertices"], mesh["nEdges"], mesh["maxEdges"])
+        self._mpas_grids = {}
+
+    def mpas_remap_setup(self, grid_id, lat_rad, lon_rad):
+        """target_mesh_setup + remap_info_setup (remapper.F:83-286); lat_rad / lon_rad [nlat][nlon] in radians."""
+        nlat, nlon = lat_rad.shape
+        check(lib().wpsgpu_mpas_remap_setup(self._h, int(grid_id), C.c_void_p(ptr(lat_rad)), C.c_void_p(ptr(lon_rad)), int(nlon), int(nlat)))
+        self._mpas_grids[grid_id] = (nlat, nlon)
+
+    def mpas_get_tables(self, grid_id, kind):
+        """(nearest [nlat][nlon] or None, sources [nlat][nlon][width], weights [nlat][nlon][width]) as host arrays."""
+        assert self.ptr_mode == PTR_HOST
+        nlat, nlon = self._mpas_grids[grid_id]
+        width = 3 if kind in (MPAS_CELLS, MPAS_MASKED_CELLS) else self._mpas_dims[3]
+        near = None if kind == MPAS_MASKED_CELLS else np.empty((nlat, nlon), np.int32)
+        src = np.empty((nlat, nlon, width), np.int32)
+        w = np.empty((nlat, nlon, width), np.float32)
+        check(lib().wpsgpu_mpas_get_tables(self._h, int(grid_id), int(kind), C.c_void_p(ptr(near)), C.c_void_p(ptr(src)), C.c_void_p(ptr(w))))
+        return near, src, w
+
+    def mpas_remap_field(self, grid_id, decomp, src, masked=False, nw=0, out=None):
+        """remap_field (remapper.F:417-663): src [nNodes][nlev] (or [nNodes]) float32 / float64 / int32 ->
+        [nlat][nlon][nlev], level index fastest as in the reference's wrf_field."""
+        nlat, nlon = self._mpas_grids[grid_id]
+        nlev = 1 if src.ndim == 1 else int(src.shape[1])
+        xtype = {"float32": MPAS_REAL, "float64": MPAS_DOUBLE, "int32": MPAS_INTEGER}[str(src.dtype).replace("torch.", "")]
+        if out is None:
+            if isinstance(src, np.ndarray):
+                out = np.empty((nlat, nlon, nlev), src.dtype)
+            else:
+                import torch
+                out = torch.empty((nlat, nlon, nlev), dtype=src.dtype, device=src.device)
+        check(lib().wpsgpu_mpas_remap_field(self._h, int(grid_id), int(decomp), xtype, int(bool(masked)), C.c_void_p(ptr(src)), nlev,
+                                            int(nw), C.c_void_p(ptr(out))))
+        return out
+
+    def mpas_remap_planes(self, grid_id, decomp, src, planes, mode=0, masked=False, landmask=None, fill_missing=0.0):
+        """remap_field fused with process_mpas_fields' per-level extraction (process_domain_module.F:1700-1956):
+        planes = sequence of nlev arrays [nlat][nlon] (the r_arr of each stored level)."""
+        nlev = 1 if src.ndim == 1 else int(src.shape[1])
+        assert len(planes) == nlev
+        pp = (C.c_void_p * nlev)(*[ptr(a) for a in planes])
+        check(lib().wpsgpu_mpas_remap_planes(self._h, int(grid_id), int(decomp), int(bool(masked)), C.c_void_p(ptr(src)), nlev, int(mode),
+                                             C.c_void_p(ptr(landmask)), C.c_float(fill_missing), pp))
 
 
 def _like(a):

@@ -371,6 +371,7 @@ int wpsgpu_create(int device_id, wpsgpu_handle_t* out)
 }
 
 void wpsgpu_geo_free(wpsgpu_ctx* h);  // geogrid.cu
+void wpsgpu_mpas_free(wpsgpu_ctx* h); // mpas.cu
 
 int wpsgpu_destroy(wpsgpu_handle_t h)
 {
@@ -381,6 +382,7 @@ int wpsgpu_destroy(wpsgpu_handle_t h)
     for (auto& g : h->grids)
         if (g.own) { cudaFree(g.d_xlat); cudaFree(g.d_xlon); if (g.d_landmask) cudaFree(g.d_landmask); }
     wpsgpu_geo_free(h);
+    wpsgpu_mpas_free(h);
     h->arena.release();
     if (h->d_counters) cudaFree(h->d_counters);
     if (h->d_search_scratch) cudaFree(h->d_search_scratch);

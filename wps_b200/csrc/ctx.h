@@ -93,6 +93,7 @@ struct QueuedSlab {
 };
 
 struct GeoState;  // geogrid.cu
+struct MpasState; // mpas.cu
 
 }  // namespace wps
 
@@ -111,6 +112,7 @@ struct wpsgpu_ctx {
     std::vector<wps::QueuedSlab> queue;
     std::deque<wpsgpu_proj> proj_pool;   // projections referenced by the queue; cleared when a flush has consumed it
     wps::GeoState* geo = nullptr;
+    wps::MpasState* mpas = nullptr;
     // small persistent device scratch (counters etc.)
     int* d_counters = nullptr;
     // search fallback scratch

@@ -127,3 +127,87 @@ CONFIGS = {
     # BASELINE.json configs[4]: ERA5-shaped 0.25 deg, 137 model levels -> 1-km 4000x4000 Lambert, sharded field x level
     "config5": dict(src=(1440, 721, -0.25, 0.25), nlev=137, dom=(4000, 4000, 1000.0, 38.5, 38.5, -97.5, 38.5, -97.5)),
 }
+
+
+def mpas_mesh(ncells=2562, seed=0, jitter=0.25):
+    """A synthetic MPAS-like mesh: spherical Voronoi tessellation (scipy) of a jittered Fibonacci lattice, in the arrays
+    mpas_mesh_setup reads (mpas_mesh.F:36-250): 1-based connectivity padded to maxEdges, counter-clockwise vertex order,
+    edge i of a cell between its vertices i and i+1, cellsOnCell(i) across that edge, radians, lonCell in [0, 2 pi).
+    The cell graph is the Delaunay triangulation, as on a real SCVT mesh, so nEdges = 3 (nCells - 2)."""
+    from scipy.spatial import SphericalVoronoi
+    rng = np.random.default_rng(seed)
+    i = np.arange(ncells) + 0.5
+    phi = np.arccos(1.0 - 2.0 * i / ncells)
+    theta = np.pi * (1.0 + 5.0 ** 0.5) * i
+    pts = np.c_[np.cos(theta) * np.sin(phi), np.sin(theta) * np.sin(phi), np.cos(phi)]
+    pts += jitter * np.sqrt(4.0 * np.pi / ncells) * 0.5 * rng.standard_normal(pts.shape)
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    sv = SphericalVoronoi(pts, 1.0, threshold=1e-12)
+    sv.sort_vertices_of_regions()
+    verts = sv.vertices
+    nv = len(verts)
+    regions = []
+    for c, reg in enumerate(sv.regions):
+        reg = list(reg)
+        a, b = verts[reg[0]], verts[reg[1]]
+        if np.dot(np.cross(a - pts[c], b - pts[c]), pts[c]) < 0.0:      # make the order counter-clockwise seen from outside
+            reg = reg[::-1]
+        regions.append(reg)
+    max_edges = max(len(r) for r in regions)
+    edge_of = {}
+    for c, reg in enumerate(regions):
+        n = len(reg)
+        for k in range(n):
+            key = (min(reg[k], reg[(k + 1) % n]), max(reg[k], reg[(k + 1) % n]))
+            edge_of.setdefault(key, []).append(c)
+    assert all(len(v) == 2 for v in edge_of.values()), "degenerate tessellation"
+    edge_id = {key: e for e, key in enumerate(sorted(edge_of))}
+    ne = len(edge_id)
+    assert ne == 3 * (ncells - 2)
+    n_edges_on_cell = np.array([len(r) for r in regions], np.int32)
+    cells_on_cell = np.zeros((ncells, max_edges), np.int32)
+    vertices_on_cell = np.zeros((ncells, max_edges), np.int32)
+    edges_on_cell = np.zeros((ncells, max_edges), np.int32)
+    cells_on_edge = np.zeros((ne, 2), np.int32)
+    cells_on_vertex = [[] for _ in range(nv)]
+    for c, reg in enumerate(regions):
+        n = len(reg)
+        for k in range(n):
+            key = (min(reg[k], reg[(k + 1) % n]), max(reg[k], reg[(k + 1) % n]))
+            pair = edge_of[key]
+            vertices_on_cell[c, k] = reg[k] + 1
+            cells_on_cell[c, k] = (pair[1] if pair[0] == c else pair[0]) + 1
+            edges_on_cell[c, k] = edge_id[key] + 1
+            cells_on_vertex[reg[k]].append(c)
+    for key, e in edge_id.items():
+        cells_on_edge[e] = [edge_of[key][0] + 1, edge_of[key][1] + 1]
+    assert all(len(v) == 3 for v in cells_on_vertex), "vertex of degree /= 3"
+    cov = np.zeros((nv, 3), np.int32)
+    for v, cs in enumerate(cells_on_vertex):
+        a, b, c3 = (pts[k] for k in cs)
+        if np.dot(np.cross(b - a, c3 - a), verts[v]) < 0.0:
+            cs = [cs[0], cs[2], cs[1]]
+        cov[v] = [k + 1 for k in cs]
+    emid = pts[cells_on_edge[:, 0] - 1] + pts[cells_on_edge[:, 1] - 1]
+    emid /= np.linalg.norm(emid, axis=1, keepdims=True)
+
+    def latlon(x):
+        lon = np.arctan2(x[:, 1], x[:, 0])
+        return np.arcsin(np.clip(x[:, 2], -1.0, 1.0)).astype(np.float32), np.where(lon < 0.0, lon + 2.0 * np.pi, lon).astype(np.float32)
+    lat_c, lon_c = latlon(pts)
+    lat_v, lon_v = latlon(verts)
+    lat_e, lon_e = latlon(emid)
+    landmask = (np.sin(5.0 * lon_c.astype(np.float64)) + np.cos(4.0 * lat_c.astype(np.float64)) > 0.3).astype(np.int32)
+    return dict(nCells=ncells, nVertices=nv, nEdges=ne, maxEdges=max_edges, landmask=landmask, nEdgesOnCell=n_edges_on_cell,
+                cellsOnCell=cells_on_cell, verticesOnCell=vertices_on_cell, edgesOnCell=edges_on_cell, cellsOnVertex=cov,
+                cellsOnEdge=cells_on_edge, latCell=lat_c, lonCell=lon_c, latVertex=lat_v, lonVertex=lon_v, latEdge=lat_e, lonEdge=lon_e)
+
+
+def mpas_field(mesh, nlev, seed=0, where="Cell"):
+    """[nNodes][nlev] binary32 values on the cells / vertices / edges of `mesh`: smooth in space plus noise, level index fastest."""
+    lat = mesh["lat" + where].astype(np.float64)[:, None]
+    lon = mesh["lon" + where].astype(np.float64)[:, None]
+    lev = np.arange(nlev, dtype=np.float64)[None, :]
+    rng = np.random.default_rng(seed)
+    v = 250.0 + 30.0 * np.sin(3.0 * lon) * np.cos(2.0 * lat) + 0.7 * lev + 0.05 * rng.standard_normal((lat.shape[0], nlev))
+    return np.ascontiguousarray(v, dtype=np.float32)
