@@ -215,3 +215,87 @@ def test_errors(setup):
         h._mpas_grids[5] = lat.shape
         h.mpas_remap_field(5, capi.MPAS_CELLS, synth.mpas_field(mesh, 2))
     h.close()
+
+
+TABLE = """
+========================================
+name=TT ; mpas_name=theta ; output_stagger=M
+========================================
+name=UU ; mpas_name=uReconstructZonal ; output_stagger=U ; is_u_field=yes
+========================================
+name=GHT ; mpas_name=zgrid
+========================================
+name=SKINTEMP ; mpas_name=skintemp ; masked=both ; fill_missing=0.
+========================================
+name=ST ; mpas_name=tslb ; masked=water ; fill_missing=285.
+========================================
+name=SM ; mpas_name=smois ; masked=water ; fill_missing=1.
+========================================
+name=SEAICE ; mpas_name=xice ; masked=water ; fill_missing=0.
+========================================
+"""
+
+
+def test_process_mpas_fields_host_mirror(orc):
+    """The field loop of process_mpas_fields (process_domain_module.F:1626-1958) above the ABI: table lookup by mpas_name,
+    renames, target grid by output stagger, masked table for masked=water fields on the mass grid, the (field, level) planes
+    of every dimension case -- values against the oracle's remap + extraction."""
+    from wps_b200 import capi, interp_option, mpas
+    orc.set_transc_mode(1)
+    mesh = synth.mpas_mesh(2562, seed=8)
+    entries = interp_option.read_interp_table(TABLE)
+    h = capi.Handle(0)
+    h.mpas_set_mesh(mesh)
+    grids = {}
+    for stag, gid in ((capi.M, 0), (capi.U, 1)):
+        lat, lon = lambert_target(60 + (stag == capi.U), 50, 120000.0, stagger=stag)
+        h.mpas_remap_setup(gid, lat, lon)
+        t = orc.mpas_remap_setup(mesh, lat, lon)
+        for kind, (kn, ks, kw) in KEYS.items():
+            t[kw] = h.mpas_get_tables(gid, kind)[2]
+        grids[gid] = t
+    ny, nx = 50, 60
+    lm = (np.cos(np.arange(ny * nx) * 0.11).reshape(ny, nx) > 0).astype(np.float32)
+
+    def ref_planes(gid, f, mode=0, masked=False, landmask=None, fill=0.0):
+        t = grids[gid]
+        ks, kw = ("sourceMaskedCells", "cellMaskedWeights") if masked else ("sourceCells", "cellWeights")
+        return orc.mpas_extract_planes(orc.mpas_remap_field(t[ks], t[kw], f, nw=3), mode, landmask=landmask, fill=fill)
+
+    def same(a, b):
+        return np.array_equal(a.view(np.int32), b.view(np.int32))
+    th = synth.mpas_field(mesh, 6, seed=1)
+    r = mpas.process_mpas_field(h, entries, "theta", ("nVertLevels", "nCells"), th, landmask=lm)
+    assert [(d["field"], d["level"], d["vertical_coord"]) for d in r] == [("TT", k, "num_mpas_levels") for k in range(1, 7)]
+    assert same(np.stack([d["r_arr"] for d in r]), ref_planes(0, th))
+    # t2m is renamed to theta (:1634): a 1-d field stored at 200100
+    t2 = np.ascontiguousarray(th[:, 0])
+    r = mpas.process_mpas_field(h, entries, "t2m", ("nCells",), t2)
+    assert [(d["field"], d["level"], d["vertical_coord"]) for d in r] == [("TT", 200100.0, "none")]
+    assert same(r[0]["r_arr"][None], ref_planes(0, t2))
+    # u10 -> uReconstructZonal -> the U grid
+    r = mpas.process_mpas_field(h, entries, "u10", ("nCells",), t2)
+    assert r[0]["stagger"] == capi.U and r[0]["r_arr"].shape == (50, 61) and same(r[0]["r_arr"][None], ref_planes(1, t2))
+    # zgrid on nVertLevelsP1: surface plane, interface means, and SOILHGT (:1733-1809)
+    zg = synth.mpas_field(mesh, 5, seed=2)
+    r = mpas.process_mpas_field(h, entries, "zgrid", ("nVertLevelsP1", "nCells"), zg)
+    assert [(d["field"], d["level"]) for d in r] == [("GHT", 200100.0), ("GHT", 1), ("GHT", 2), ("GHT", 3), ("GHT", 4), ("SOILHGT", 200100.0)]
+    assert same(np.stack([d["r_arr"] for d in r[:5]]), ref_planes(0, zg, mode=1)) and r[5]["r_arr"] is r[0]["r_arr"]
+    # soil fields: names per layer, masked table, landmask fill with the entry's fill_missing (:1811-1925)
+    ts = synth.mpas_field(mesh, 4, seed=3)
+    r = mpas.process_mpas_field(h, entries, "tslb", ("nSoilLevels", "nCells"), ts, landmask=lm)
+    assert [d["field"] for d in r] == ["ST000010", "ST010040", "ST040100", "ST100200"] and all(d["level"] == 200100.0 for d in r)
+    assert same(np.stack([d["r_arr"] for d in r]), ref_planes(0, ts, masked=True, landmask=lm, fill=285.0))
+    assert (np.stack([d["r_arr"] for d in r])[:, lm == 0] == 285.0).all()
+    with pytest.raises(capi.WpsGpuError, match="Too many soil layers"):
+        mpas.process_mpas_field(h, entries, "smois", ("nSoilLevels", "nCells"), synth.mpas_field(mesh, 5, seed=3), landmask=lm)
+    # masked=both is not masked=water: plain table, no fill (:1663, :1948)
+    sk = np.ascontiguousarray(ts[:, 1])
+    r = mpas.process_mpas_field(h, entries, "skintemp", ("nCells",), sk, landmask=lm)
+    assert same(r[0]["r_arr"][None], ref_planes(0, sk))
+    r = mpas.process_mpas_field(h, entries, "xice", ("nCells",), sk, landmask=lm)
+    assert same(r[0]["r_arr"][None], ref_planes(0, sk, masked=True, landmask=lm, fill=0.0))
+    # fields the table does not name, or that cannot be remapped, are skipped (:1648, remapper.F:339-376)
+    assert mpas.process_mpas_field(h, entries, "rainnc", ("nCells",), sk) == []
+    assert mpas.process_mpas_field(h, entries, "theta", ("nVertLevels", "nSomethingElse"), th) == []
+    h.close()
