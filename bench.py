@@ -393,6 +393,52 @@ def aux_kernels_arm(h, torch, dev, steps=5):
     return out
 
 
+def mpas_arm(h, torch, dev, steps=5):
+    """an MPAS source (synthetic 40962-cell Voronoi mesh, 55 levels) remapped onto the config-2 mass grid with
+    process_mpas_fields' per-level planes written directly (wpsgpu_mpas_remap_planes).  Algorithmic bytes per output value:
+    4 B store + (3 indices + 3 weights) = 24 B per point amortised over the levels; the source columns are L2 hits."""
+    import time
+    from wps_b200 import capi, synth
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = synth.CONFIGS["config2"]["dom"]
+    mesh = synth.mpas_mesh(40962, seed=6)
+    dom = synth.lambert_domain(nx, ny, dx, tl1, tl2, slon, rlat, rlon)
+    xlat = torch.empty((ny, nx), device=dev); xlon = torch.empty_like(xlat)
+    h.xytoll_grid(dom, capi.M, 1, 1, nx, ny, out=(xlat, xlon))
+    d2r = float(np.float32(np.arcsin(np.float32(1.0)) / np.float32(90.0)))
+    lat, lon = (xlat * d2r).contiguous(), (xlon * d2r).contiguous()
+    h.mpas_set_mesh(mesh)
+    torch.cuda.synchronize()
+    n0 = h.launch_count
+    t0 = time.perf_counter()
+    h.mpas_remap_setup(0, lat, lon)
+    h.synchronize()
+    setup_s = time.perf_counter() - t0
+    setup_launches = h.launch_count - n0
+    nlev = 55
+    src = torch.from_numpy(synth.mpas_field(mesh, nlev, seed=1)).to(dev)
+    planes = [torch.empty((ny, nx), device=dev) for _ in range(nlev)]
+    stream = torch.cuda.ExternalStream(h.stream, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for it in range(steps + 2):
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        h.mpas_remap_planes(0, capi.MPAS_CELLS, src, planes)
+        ev1.record(stream)
+        h.synchronize()
+        if it > 1:
+            ms.append(ev0.elapsed_time(ev1))
+    t = float(np.mean(ms))
+    npt = nx * ny * nlev
+    bpp = 4.0 + 24.0 / nlev
+    return {"metric": "MPAS remap output values/s (level x target point), planes written in the met_em layout", "value": npt / (t * 1e-3),
+            "unit": "points/s", "ms": t, "points": npt, "levels": nlev, "mesh_cells": mesh["nCells"], "target": "%dx%d" % (nx, ny),
+            "alg_bytes_per_point": bpp, "GBps": bpp * npt / (t * 1e-3) / 1e9, "launches_per_field": 1,
+            "setup": {"seconds": setup_s, "launches": int(setup_launches),
+                      "what": "remap_info_setup for 1.9 M target points: nearest cell / vertex / edge, four Wachspress tables, search_for_cells; "
+                              "passes of the sequential-scan recurrence until it settles"}}
+
+
 def config4_arm(h, torch, dev, steps=5):
     """BASELINE configs[3]: 27 / 9 / 3-km nests (compute_nest_locations), Lambert-grid source (NAM-218-like, 614 x 428),
     per nest TT / UU / VV x 8 levels + SST (masked land) + soil temperature (masked water, search) + SKINTEMP (masked=both),
@@ -787,12 +833,13 @@ def run_b200(args, rank, world, local_rank):
         e2e_raw_s = (time.perf_counter() - t0) / e2e_steps
         hh.close()
 
-    geo, vfill, aux, cfg4 = None, None, None, None
+    geo, vfill, aux, cfg4, mp = None, None, None, None, None
     if rank == 0 and not args.no_geogrid:
         geo = geogrid_arm(h, torch, dev, config, 3)
         vfill = vertical_fill_arm(h, torch, dev, config, 3)
         aux = aux_kernels_arm(h, torch, dev)
         cfg4 = config4_arm(h, torch, dev)
+        mp = mpas_arm(h, torch, dev)
     if rank == 0:
         peaks = {}
         try:
@@ -830,6 +877,8 @@ def run_b200(args, rank, world, local_rank):
             line["vertical_fill"] = vfill
             line["aux_kernels"] = aux
             line["config4"] = cfg4
+            mp["frac_of_hbm_peak"] = mp["GBps"] / peak
+            line["mpas_remap"] = mp
             for k in aux.values():
                 k["frac_of_hbm_peak"] = k["GBps"] / peak
         if world == 1 and not args.no_cpu:
