@@ -1,3 +1,5 @@
-python tools/mpas_only.py > gpurun_out/mpas_only.json 2> gpurun_out/mpas_only.err; cat gpurun_out/mpas_only.json; tail -3 gpurun_out/mpas_only.err
-ncu --set full --clock-control none --import-source on -k regex:k_mpas_remap_planes -s 2 -c 1 -o gpurun_out/r02_mpas_planes -f python tools/mpas_only.py > gpurun_out/ncu_mpas.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_mpas --csv --log-file gpurun_out/mpas_launches.csv python tools/mpas_only.py > /dev/null 2>&1
+python -m pytest tests -m gpu -x -q -k "metgrid or config or mirror or device" > gpurun_out/pytest_g2.log 2>&1; tail -2 gpurun_out/pytest_g2.log
+for v in base new base new; do
+  if [ $v = base ]; then export WPSGPU_LIB=$PWD/wps_b200/variants/libwpsgpu_base.so; else unset WPSGPU_LIB; fi
+  echo "VARIANT=$v"; python bench.py --steps 20 --warmup 3 --no-cpu --no-geogrid --no-e2e 2>gpurun_out/g2_$v.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); b=d['roofline']['breakdown_ms']; print(d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'], b['k_metgrid_slowlist'], b['k_pack_win'])"
+done

@@ -39,8 +39,7 @@ struct Job {
     // (bx0 + c, by0 + r) -- not clipped to the source array, columns / rows clamped instead --, thr the guard
     // thresholds (two sets for masked=both), cf the slow pass's hint bits; strip = destination points per thread
     int strip;
-    const float4* thr;
-    const unsigned* cfw;         // strip jobs: flag words (byte 0 = the cell's own stencil, like cf)
+    const uint2* tf;             // strip jobs, per (pack, cell): .x = flag word (byte 0 = the cell's own stencil, like cf), .y = guard threshold of the window (k_pack_win)
 };
 
 struct SlabPtrs {
@@ -720,7 +719,7 @@ k_metgrid_slowlist(const Job* __restrict__ jobs, int njobs, const SlabPtrs* __re
                 ci -= jb.bx0; cj -= jb.by0;
                 if ((fabsf(fx) > 0.0001f || fabsf(fy) > 0.0001f) && ci >= 0 && ci < jb.bnx && cj >= 0 && cj < jb.bny) {
                     const size_t co = ((size_t)(sl >> 2) * jb.bny + cj) * jb.bnx + ci;
-                    unsigned cfb = jb.strip > 0 ? (__ldg(jb.cfw + co) & 0xffu) : (unsigned)__ldg(jb.cf + co);
+                    unsigned cfb = jb.strip > 0 ? (__ldg(&jb.tf[co].x) & 0xffu) : (unsigned)__ldg(jb.cf + co);
                     if ((cfb >> (4 + (sl & 3))) & 1u) first = 1;
                 }
             }
@@ -893,13 +892,12 @@ static int alloc_strip_records(wpsgpu_ctx* h, std::vector<Job>& jobs)
             if (!done[b] && jobs[b].fast == 1 && jobs[b].strip > 0 && strip_same_geometry(jobs[a], jobs[b])) { cls.push_back(b); packs += jobs[b].npack; }
         const size_t cells = (size_t)jobs[a].bnx * jobs[a].bny;
         float4* rec = (float4*)h->arena.take(packs * cells * sizeof(float4));
-        float4* thr = (float4*)h->arena.take(packs * cells * sizeof(float4));
-        unsigned* cfw = (unsigned*)h->arena.take(packs * cells * sizeof(unsigned));
-        WPS_CHECK(rec && thr && cfw, -3, "device arena exhausted (window records)");
+        uint2* tf = (uint2*)h->arena.take(packs * cells * sizeof(uint2));
+        WPS_CHECK(rec && tf, -3, "device arena exhausted (window records)");
         size_t q = 0;
         for (size_t b : cls) {
             done[b] = 1;
-            jobs[b].rec = rec + q * cells; jobs[b].thr = thr + q * cells; jobs[b].cfw = cfw + q * cells;
+            jobs[b].rec = rec + q * cells; jobs[b].tf = tf + q * cells;
             q += jobs[b].npack;
         }
     }
@@ -991,7 +989,7 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                 int in_work = 0, cq = 0;                       // cq: class-relative index of the next pack
                 const Job& j0 = jobs[todo[cls[0]]];
                 const size_t cells = (size_t)j0.bnx * j0.bny;
-                P.cls[ncls].P = j0.rec; P.cls[ncls].TA = j0.thr; P.cls[ncls].cf = j0.cfw;
+                P.cls[ncls].P = j0.rec; P.cls[ncls].TF = j0.tf;
                 if (stage == 2 && R > 1) WPS_CHECK(encode_window_tensor(&P.tmap[ncls], j0, c_packs), -3, "cuTensorMapEncodeTiled failed for a window-record array");
                 P.work[nwork].seg0 = (short)nseg; P.work[nwork].nseg = 0; P.work[nwork].cls = (short)ncls; P.work[nwork].npk = 0; P.work[nwork].q0 = 0;
                 const float* cls_lm = nullptr;                // one grid, one landmask
@@ -1003,7 +1001,7 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                     const int nslot = jb.npack * 4;          // levels past the last one write to the dump area
                     StripJob& q = P.job[nj];
                     seg_job[nj] = &jb;
-                    q.xy = jb.xy; q.landmask = jb.landmask; q.landmask_cls = cls_lm; q.P = jb.rec; q.TA = jb.thr; q.cf = jb.cfw;
+                    q.xy = jb.xy; q.landmask = jb.landmask; q.landmask_cls = cls_lm; q.P = jb.rec; q.TF = jb.tf;
                     q.nx = jb.nx; q.ny = jb.ny; q.nxw = jb.nxw; q.sm1 = jb.sm1; q.sm2 = jb.sm2;
                     q.sd1 = jb.sd1; q.ed1 = jb.ed1; q.sd2 = jb.sd2; q.ed2 = jb.ed2; q.pw = jb.pw;
                     q.minx = jb.minx; q.maxx = jb.maxx; q.miny = jb.miny; q.maxy = jb.maxy; q.bdr = jb.bdr;
@@ -1017,7 +1015,7 @@ static int launch_strips(wpsgpu_ctx* h, const std::vector<Job>& jobs, const std:
                         P.out[ns + k].r = p.r_arr; P.out[ns + k].w = p.new_pts;
                     }
                     for (int k = jb.nslab; k < nslot; ++k) { P.out[ns + k].r = dump_r; P.out[ns + k].w = dump_w; }
-                    WPS_CHECK(jb.rec == j0.rec + (size_t)cq * cells && jb.thr == j0.thr + (size_t)cq * cells && jb.cfw == j0.cfw + (size_t)cq * cells, -3,
+                    WPS_CHECK(jb.rec == j0.rec + (size_t)cq * cells && jb.tf == j0.tf + (size_t)cq * cells, -3,
                               "window records of a geometry class are not contiguous");
                     for (int pk = 0; pk < jb.npack;) {
                         if (in_work == per) {                 // next block
@@ -1832,7 +1830,7 @@ static int flush_impl(wpsgpu_ctx* h, bool wait)
                 const double ppc = sqrt((double)dg.npts() / ((double)(bb[1] - bb[0] + 1) * (bb[3] - bb[2] + 1)));
                 b.strip = ppc >= 5.0 ? 4 : (ppc >= 2.5 ? 2 : 1);
                 b.strip = env_int("WPSGPU_STRIP", b.strip, 1, 4) == 3 ? 2 : env_int("WPSGPU_STRIP", b.strip, 1, 4);
-                need += (size_t)b.npack * b.bnx * b.bny * (sizeof(float4) * 2 + sizeof(unsigned)) + 1024;
+                need += (size_t)b.npack * b.bnx * b.bny * (sizeof(float4) + sizeof(uint2)) + 1024;
                 need += dg.npts() * sizeof(float) + (size_t)dg.ny() * ((dg.nx() + 31) / 32) * sizeof(int) + 512;   // dump area (per pass at most once)
             } else if (q0.fo.ops[0] == WPSGPU_SIXTEEN_POINT && bb[0] <= bb[1] && bb[2] <= bb[3]) {
                 long x0 = std::max<long>(q0.s.minx, (long)bb[0] - 1), x1 = std::min<long>(q0.s.maxx, (long)bb[1] + 2);

@@ -39,8 +39,8 @@ struct StripJob {
     const float* landmask;
     const float* landmask_cls;   // the landmask of the grid if ANY job of the geometry class uses one (loaded once per block)
     const float4* P;             // window records [npack][pny][pnx], float4 = 4 levels of source cell (px0 + c, py0 + r), clamped like :1227-1241
-    const float4* TA;            // guard thresholds per window ORIGIN cell, same index space
-    const unsigned* cf;          // per (pack, cell): flag bytes of the four stencils a strip with this window origin can use (k_pack_win)
+    const uint2* TF;             // per (pack, window ORIGIN cell): .x = flag bytes of the four stencils a strip with this window origin can use,
+                                 // .y = guard threshold of the 5 x 5 window, sign bit = a level of the window holds zero stand-ins only (k_pack_win)
     int nx, ny, nxw, sm1, sm2, sd1, ed1, sd2, ed2, pw;
     int minx, maxx, miny, maxy, bdr;
     int px0, py0, pnx, pny;
@@ -55,7 +55,7 @@ struct StripSeg { short job, pack0, npk, same; };      // consecutive packs of o
 // what one block does: segments [seg0, seg0 + nseg) of one geometry class = packs [q0, q0 + npk) of the class arrays
 struct StripWork { short seg0, nseg, cls, npk; int q0; };
 // window records / thresholds / flag words of a geometry class: the arrays of its jobs back to back, [class packs][pny][pnx]
-struct StripClass { const float4* P; const float4* TA; const unsigned* cf; };
+struct StripClass { const float4* P; const uint2* TF; };
 constexpr int STRIP_MAX_CLS = 8;
 
 struct StripParams {
@@ -74,7 +74,7 @@ struct StripParams {
 // whose ORIGIN is that cell (cells c-1..c+3, r-1..r+3) and the hint bits of the 4 x 4 stencil anchored there.
 struct PackWinTask { int job, pack; };
 
-__global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, const PackWinTask* __restrict__ tasks,
+__global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ jobs, const PackWinTask* __restrict__ tasks,
                                                   const SlabPtrs* __restrict__ slabs)
 {
     const PackWinTask t = tasks[blockIdx.y];
@@ -103,9 +103,11 @@ __global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, 
         const int gx = min(max(jb.bx0 + bx * 16 - 1 + c, sx), ex), gy = min(max(jb.by0 + by * 16 - 1 + r, sy), ey);   // clamped like :1227-1241
         const size_t off = (size_t)(gy - sy) * snx + (gx - sx);
         unsigned f = 0;
+        float v0 = 0.0f;
 #pragma unroll
         for (int lv = 0; lv < 4; ++lv) {
-            float v = 0.0f, a = 0.0f;
+            float v = v0, a = 0.0f;             // levels past the job's last one repeat the pack's first level: their results go to the
+                                                // dump area, and their row interpolants must not trip the window's (joint) guard
             if (src[lv]) {
                 v = __ldg(src[lv] + off);
                 if (v == 0.0f && msg != 0.0f) v = 1.0e-20f;     // interp_module.F:1255-1257
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, 
                 // sums finite (its own stencils are flagged and never use the record)
                 if (ismsg || !fin) { v = 0.0f; a = 0.0f; }
             }
+            if (lv == 0) v0 = v;
             s_v[lv][r][c] = v;
             s_a[lv][r][c] = a;
         }
@@ -182,21 +185,28 @@ __global__ void __launch_bounds__(256) k_pack_win(const Job* __restrict__ jobs, 
         // levels beyond the job's last: records are 0, never flagged
         return (bits & (present | (present << 4))) | ((~present & 15u) * 0x11u);
     };
-    // threshold of the 5 x 5 window whose origin is the cell: 2^-18 of the largest usable magnitude in it (an upper bound
-    // for every stencil inside the window), at least 1e-21
-    float thr[4];
+    // Guard threshold of the 5 x 5 window whose origin is the cell: 2^-18 of the largest usable magnitude in it (an upper bound
+    // for every stencil inside the window), at least 1e-21 -- ONE value for the pack's levels, their maximum: the strip kernel
+    // tests the smallest |row interpolant| over rows and levels against it (a level whose magnitudes are far below another's of
+    // the same pack sends a few more points to the exact path, nothing else changes).  Sign bit: some level sits at the floor,
+    // i.e. its window may consist of zero stand-ins only and a result can equal 1.E-20 (:1317).
+    float T = 0.0f;
+    bool at_floor = false;
 #pragma unroll
     for (int lv = 0; lv < 4; ++lv) {
+        if (!src[lv]) continue;
         float mx = 0.0f;
 #pragma unroll
         for (int r = -1; r <= 3; ++r) mx = fmaxf(mx, s_a[lv][r0 + r][c0 - 1]);
-        thr[lv] = src[lv] ? fmaxf(mx * 3.814697265625e-6f, 1.0e-21f) : -1.0f;
+        float thr = fmaxf(mx * 3.814697265625e-6f, 1.0e-21f);
+        at_floor = at_floor || thr == 1.0e-21f;
         // a weighted sum stays below 1.3 x the largest magnitude: if that cannot reach |missing_value| the kernel need not
         // compare its results with missing_value (it does when missing_value is 0); otherwise the window goes to the slow path
-        if (src[lv] && msg != 0.0f && !(mx * 2.0f < fabsf(msg))) thr[lv] = __int_as_float(0x7f800000);
+        if (msg != 0.0f && !(mx * 2.0f < fabsf(msg))) thr = __int_as_float(0x7f800000);
+        T = fmaxf(T, thr);
     }
-    const_cast<float4*>(jb.thr)[o] = make_float4(thr[0], thr[1], thr[2], thr[3]);
-    const_cast<unsigned*>(jb.cfw)[o] = stencil_byte(0, 0) | (stencil_byte(1, 0) << 8) | (stencil_byte(0, 1) << 16) | (stencil_byte(1, 1) << 24);
+    const unsigned fw = stencil_byte(0, 0) | (stencil_byte(1, 0) << 8) | (stencil_byte(0, 1) << 16) | (stencil_byte(1, 1) << 24);
+    const_cast<uint2*>(jb.tf)[o] = make_uint2(fw, __float_as_uint(at_floor ? -T : T));
 }
 
 // ---- strip kernel --------------------------------------------------------------------------------------------------------
@@ -307,10 +317,13 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
     float2 xyv[R];
 #pragma unroll
     for (int p = 0; p < R; ++p) xyv[p] = __ldg(gj.xy + (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1));   // rows / columns past the grid re-read its last point
-    // landmask of the strip's points, once per block (every job of the class that uses one uses the grid's)
-    float lmv[R];
+    // landmask of the strip's points: read where a job first needs it (the 3-d fields that come first do not; a select on an
+    // early load would make every block wait for it at its first segment), brought towards the SM now
+    if (gj.landmask_cls) {
 #pragma unroll
-    for (int p = 0; p < R; ++p) lmv[p] = gj.landmask_cls ? __ldg(gj.landmask_cls + (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1)) : 0.0f;
+        for (int p = 0; p < R; ++p)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gj.landmask_cls + (size_t)min(jj0 + p, ny - 1) * nx + min(ii, nx - 1)));
+    }
     bool geo[R];                                 // the point can be evaluated from a window (if the job's point logic allows)
     int ci[R], cj[R];
     float fx[R], fy[R];
@@ -459,11 +472,9 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
 #pragma unroll
         for (int st = 0; st < SNS - 1; ++st) issue_next((unsigned)st);
     }
-    const float4* __restrict__ Ta = cl.TA + (size_t)wk.q0 * pstride + toff;
-    const unsigned* __restrict__ cfp = cl.cf + (size_t)wk.q0 * pstride + toff;
+    const uint2* __restrict__ TFp = cl.TF + (size_t)wk.q0 * pstride + toff;
     const float4* __restrict__ Pw = cl.P + (size_t)wk.q0 * pstride + woff;
-    float4 ta = __ldg(Ta);                       // thresholds and flag word of the first pack; later ones one iteration ahead
-    unsigned cfv = __ldg(cfp);
+    uint2 tfv = __ldg(TFp);                      // flag word and threshold of the first pack; later ones one iteration ahead
     int qleft = nq;                              // packs of the block still to be computed, the current one included
     asm volatile("" : "+r"(qleft));
 
@@ -484,7 +495,8 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
             for (int p = 0; p < R; ++p) {
                 const int jj = jj0 + p, dj = jb.sm2 + jj;
                 const bool act = ii < nx && jj < ny;
-                const float lm = jb.has_lm ? lmv[p] : 0.0f;
+                float lm = 0.0f;
+                if (jb.has_lm) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(lm) : "l"(jb.landmask + (size_t)min(jj, ny - 1) * nx + min(ii, nx - 1)));
                 bool fill = fill_i && abs(dj - jb.sd2) >= pw && abs(dj - jb.ed2) >= pw, lm_ok = true;
                 bool hi_nib = false;
                 if (jb.both) {
@@ -512,12 +524,11 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
             constexpr bool DIRECT = decltype(direct_tag)::value;
 #pragma unroll 1
             for (int pk = 0; pk < npk; ++pk) {
-                const float4 cta = ta;
-                const unsigned ccf = cfv;
-                if (--qleft > 0) {                       // thresholds and stencil flags of the next pack, one iteration ahead
-                    Ta += pstride; cfp += pstride;
-                    ta = __ldg(Ta);
-                    cfv = __ldg(cfp);
+                const unsigned ccf = tfv.x;
+                const float cT = __uint_as_float(tfv.y);
+                if (--qleft > 0) {                       // stencil flags and threshold of the next pack, one iteration ahead
+                    TFp += pstride;
+                    tfv = __ldg(TFp);
                 }
                 unsigned swa = 0;
                 if (!DIRECT) {
@@ -530,13 +541,15 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                     par ^= stg == 0 ? 1u : 0u;
                 }
                 float2 a01[R], a23[R];
-                bool g[R];                               // the guard holds for every row and level of point p so far
+                bool g[R];                               // point p's stencil is clean; after the rows: and its guard holds
+                float gm[R];                             // smallest |row interpolant| of point p over the window's rows and the four levels
                 // the point's stencil must be clean for all four levels (under the mask the landmask selects, masked=both)
                 const unsigned dirty = ~__byte_perm(ccf, 0u, csel) & nibm;
 #pragma unroll
                 for (int p = 0; p < R; ++p) {
                     a01[p] = make_float2(0.0f, 0.0f); a23[p] = a01[p];
                     g[p] = (dirty & (0xffu << (8 * p))) == 0u;
+                    gm[p] = 3.0e38f;
                 }
 #pragma unroll
                 for (int l = 0; l < WIN; ++l) {
@@ -563,18 +576,24 @@ k_metgrid_strip16(const __grid_constant__ StripParams P)
                             r01 = __ffma2_rn(wx[p][k], lo2(v[k]), r01);
                             r23 = __ffma2_rn(wx[p][k], hi2(v[k]), r23);
                         }
-                        g[p] = g[p] && fabsf(r01.x) > cta.x && fabsf(r01.y) > cta.y && fabsf(r23.x) > cta.z && fabsf(r23.y) > cta.w;
+                        asm("min.abs.f32 %0, %0, %1, %2;" : "+f"(gm[p]) : "f"(r01.x), "f"(r01.y));      // FMNMX3 |a|, |b|, |c|
+                        asm("min.abs.f32 %0, %0, %1, %2;" : "+f"(gm[p]) : "f"(r23.x), "f"(r23.y));
                         const float2 wyl = make_float2(wyr[p], wyr[p]);
                         a01[p] = __ffma2_rn(wyl, r01, a01[p]);
                         a23[p] = __ffma2_rn(wyl, r23, a23[p]);
                     }
                 }
                 if (DIRECT) Pw += pstride;
+                {
+                    const float aT = fabsf(cT);
+#pragma unroll
+                    for (int p = 0; p < R; ++p) g[p] = g[p] && gm[p] > aT;
+                }
                 // ---- outputs.  The guard is joint over the pack's four levels: a point either delivers all of them or hands
                 // all of them to the slow pass, so one ballot per point serves the pack.
                 // a result equal to the zero stand-in becomes 0 (:1317): possible only where a whole window consists of
-                // stand-ins, i.e. its threshold sits at the 1e-21 floor (warp-uniform test, one branch per pack)
-                if (__any_sync(0xffffffffu, cta.x == 1.0e-21f || cta.y == 1.0e-21f || cta.z == 1.0e-21f || cta.w == 1.0e-21f)) {
+                // stand-ins, i.e. its threshold sits at the 1e-21 floor: the sign bit of the window's threshold word (warp-uniform test, one branch per pack)
+                if (__any_sync(0xffffffffu, cT < 0.0f)) {
 #pragma unroll
                     for (int p = 0; p < R; ++p) {
                         a01[p].x = a01[p].x == 1.0e-20f ? 0.0f : a01[p].x; a01[p].y = a01[p].y == 1.0e-20f ? 0.0f : a01[p].y;
