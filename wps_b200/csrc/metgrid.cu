@@ -48,6 +48,7 @@ struct SlabPtrs {
     const int* valid;
     int* new_pts;
     const int* decided;  // average_gcell: bit set = r_arr already holds the cell average (:2393-2400)
+    int job, pad_;       // the job the slab belongs to (the queue-driven kernels start from a slab index)
 };
 
 
@@ -679,16 +680,6 @@ k_metgrid_fast4(const __grid_constant__ Fast4Params P)
 }
 
 // Points the first-method kernels could not take: full generic operator chain, one thread per queue entry.
-__device__ __forceinline__ int job_of_slab(const Job* jobs, int njobs, int slab)
-{
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].slab0 <= slab) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
 #ifndef SLOW_MINBLOCKS
 #define SLOW_MINBLOCKS 8   // 64 registers
 #endif
@@ -701,8 +692,8 @@ k_metgrid_slowlist(const Job* __restrict__ jobs, int njobs, const SlabPtrs* __re
     for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const int2 en = Q.q[e];
         const int slab = en.x, idx = en.y;
-        const Job& jb = jobs[job_of_slab(jobs, njobs, slab)];
         const SlabPtrs sp = slabs[slab];
+        const Job& jb = jobs[sp.job];
         const int sl = slab - jb.slab0;
         const int jj = idx / jb.nx, ii = idx - jj * jb.nx;
         const int wwidx = jj * jb.nxw + (ii >> 5), bit = ii & 31;
@@ -782,8 +773,8 @@ k_metgrid_search(const Job* __restrict__ jobs, int njobs, const SlabPtrs* __rest
     unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     for (unsigned long long e = warp; e < n; e += nwarps) {
         Deferred d = deferred[e];
-        const Job& jb = jobs[job_of_slab(jobs, njobs, d.slab)];
         const SlabPtrs sp = slabs[d.slab];
+        const Job& jb = jobs[sp.job];
         int ii = d.idx % jb.nx, jj = d.idx / jb.nx;
         bool vbit = false;
         if (sp.valid) vbit = (__ldg(sp.valid + (size_t)jj * jb.nxw + (ii >> 5)) >> (ii & 31)) & 1;
@@ -810,8 +801,8 @@ k_metgrid_search_literal(const Job* __restrict__ jobs, int njobs, const SlabPtrs
     ls.visited = mine; ls.R = R; ls.q = reinterpret_cast<QNode*>(mine + ((vis_words + 1) & ~size_t(1))); ls.qcap = qcap;
     for (unsigned long long e = tid; e < n; e += nth) {
         Deferred d = deferred2[e];
-        const Job& jb = jobs[job_of_slab(jobs, njobs, d.slab)];
         const SlabPtrs sp = slabs[d.slab];
+        const Job& jb = jobs[sp.job];
         int ii = d.idx % jb.nx, jj = d.idx / jb.nx;
         bool vbit = false;
         if (sp.valid) vbit = (__ldg(sp.valid + (size_t)jj * jb.nxw + (ii >> 5)) >> (ii & 31)) & 1;
@@ -1352,7 +1343,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         // one pass per kind of array, so that the arrays of neighbouring levels end up next to each other
         for (int k = 0; k < ns; ++k) {
             SlabPtrs& p = sp[s0 + k];
-            p.decided = nullptr; p.valid = nullptr;
+            p.decided = nullptr; p.valid = nullptr; p.job = j; p.pad_ = 0;
             const wpsgpu_slab& s = queue[grp[k]].s;
             if (host && fs.staged.count(s.slab) && !fs.reusable(s.slab, fs.sub[g])) {   // staged for another grid with a smaller rectangle
                 fs.staged.erase(s.slab);
