@@ -17,6 +17,8 @@ module wpsgpu_mod
       real(c_float) :: lat1, lon1, lat0, lon0, dx, dy, latinc, loninc, dlon, stdlon, truelat1, truelat2, hemi, cone, &
                        polei, polej, rsw, rebydx, knowni, knownj, re_m, rho0, nc, bigc
       real(c_float) :: gauss_lat(WPSGPU_MAX_GAUSS)
+      integer(c_int32_t) :: ixdim, jydim      ! PROJ_ROTLL
+      real(c_float) :: phi, lambda
    end type wpsgpu_proj
 
    type, bind(C) :: wpsgpu_field_opts
@@ -40,7 +42,8 @@ module wpsgpu_mod
       WPSGPU_A_KNOWNI = 16, WPSGPU_A_KNOWNJ = 32, WPSGPU_A_DX = 64, WPSGPU_A_DY = 128, WPSGPU_A_LATINC = 256, &
       WPSGPU_A_LONINC = 512, WPSGPU_A_STDLON = 1024, WPSGPU_A_TRUELAT1 = 2048, WPSGPU_A_TRUELAT2 = 4096, &
       WPSGPU_A_NLAT = 8192, WPSGPU_A_NXMIN = 131072, WPSGPU_A_NXMAX = 262144, WPSGPU_A_STAGGER = 524288, &
-      WPSGPU_A_R_EARTH = 4194304
+      WPSGPU_A_R_EARTH = 4194304, WPSGPU_A_IXDIM = 32768, WPSGPU_A_JYDIM = 65536, WPSGPU_A_PHI = 1048576, &
+      WPSGPU_A_LAMBDA = 2097152
    integer(c_int), parameter :: WPSGPU_PRECISION_EXACT = 0, WPSGPU_PRECISION_TOLERANCE = 1
    integer(c_int), parameter :: WPSGPU_PTR_HOST = 0, WPSGPU_PTR_DEVICE = 1
    integer(c_int), parameter :: WPSGPU_CONTINUOUS = 0, WPSGPU_CATEGORICAL = 1, WPSGPU_SP_CONTINUOUS = 2
@@ -49,6 +52,8 @@ module wpsgpu_mod
       integer(c_int32_t) :: present      ! uint32_t in C: same size and representation
       real(c_float) :: lat1, lon1, lat0, lon0, knowni, knownj, dx, dy, latinc, loninc, stdlon, truelat1, truelat2, r_earth
       integer(c_int32_t) :: nlat, nxmin, nxmax, stagger
+      integer(c_int32_t) :: ixdim, jydim      ! PROJ_ROTLL
+      real(c_float) :: phi, lambda
    end type wpsgpu_map_args
 
    ! calc_field's arguments (process_tile_module.F:1208-1260)

@@ -57,6 +57,8 @@ typedef struct wpsgpu_proj {
     float lat1, lon1, lat0, lon0, dx, dy, latinc, loninc, dlon, stdlon, truelat1, truelat2, hemi, cone,
           polei, polej, rsw, rebydx, knowni, knownj, re_m, rho0, nc, bigc;
     float gauss_lat[WPSGPU_MAX_GAUSS];
+    int32_t ixdim, jydim;       /* PROJ_ROTLL (NMM E-grid): mass points per row / number of rows, module_map_utils.F:150-153 */
+    float phi, lambda;          /* PROJ_ROTLL: half extent of the rotated grid in latitude / longitude, degrees */
 } wpsgpu_proj;
 
 /* OPTIONAL arguments of map_set (module_map_utils.F:243-283); bit set in `present` = argument passed */
@@ -64,12 +66,15 @@ enum { WPSGPU_A_LAT1 = 1 << 0, WPSGPU_A_LON1 = 1 << 1, WPSGPU_A_LAT0 = 1 << 2, W
        WPSGPU_A_KNOWNI = 1 << 4, WPSGPU_A_KNOWNJ = 1 << 5, WPSGPU_A_DX = 1 << 6, WPSGPU_A_DY = 1 << 7,
        WPSGPU_A_LATINC = 1 << 8, WPSGPU_A_LONINC = 1 << 9, WPSGPU_A_STDLON = 1 << 10,
        WPSGPU_A_TRUELAT1 = 1 << 11, WPSGPU_A_TRUELAT2 = 1 << 12, WPSGPU_A_NLAT = 1 << 13,
+       WPSGPU_A_IXDIM = 1 << 15, WPSGPU_A_JYDIM = 1 << 16, WPSGPU_A_PHI = 1 << 20, WPSGPU_A_LAMBDA = 1 << 21,
        WPSGPU_A_NXMIN = 1 << 17, WPSGPU_A_NXMAX = 1 << 18, WPSGPU_A_STAGGER = 1 << 19,
        WPSGPU_A_R_EARTH = 1 << 22 };
 typedef struct wpsgpu_map_args {
     uint32_t present;
     float lat1, lon1, lat0, lon0, knowni, knownj, dx, dy, latinc, loninc, stdlon, truelat1, truelat2, r_earth;
     int32_t nlat, nxmin, nxmax, stagger;
+    int32_t ixdim, jydim;       /* PROJ_ROTLL */
+    float phi, lambda;
 } wpsgpu_map_args;
 
 /* ---- lifetime / errors ---- */

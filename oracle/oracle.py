@@ -18,7 +18,7 @@ NAN = np.float32(1.0e20)
 SIXTEEN_POINT, FOUR_POINT, N_NEIGHBOR, AVERAGE4, AVERAGE16, W_AVERAGE4, W_AVERAGE16, SEARCH = range(1, 9)
 M, U, V, HH, VV, CORNER = range(1, 7)
 PROJ_LATLON, PROJ_LC, PROJ_PS, PROJ_MERC, PROJ_GAUSS, PROJ_CYL, PROJ_CASSINI = 0, 1, 2, 3, 4, 5, 6
-PROJ_PS_WGS84, PROJ_ALBERS_NAD83 = 102, 105
+PROJ_PS_WGS84, PROJ_ALBERS_NAD83, PROJ_ROTLL = 102, 105, 203
 
 _A = dict(lat1=0, lon1=1, lat0=2, lon0=3, knowni=4, knownj=5, dx=6, dy=7, latinc=8, loninc=9, stdlon=10,
           truelat1=11, truelat2=12, nlat=13, nlon=14, ixdim=15, jydim=16, nxmin=17, nxmax=18, stagger=19,

@@ -25,6 +25,8 @@ int orc_get_transc_mode(void) { return g_transc_mode; }
 
 /* Fortran intrinsics on default REAL.  mode 0: glibc float functions (what gfortran calls);
  * mode 1: binary64 evaluation rounded once to binary32. */
+/* ACOS(-1.0) on default REAL: both evaluations round to 3.1415927 */
+float o_acosf_m1(void) { return g_transc_mode ? (float)acos(-1.0) : acosf(-1.0f); }
 float o_sin(float x) { return g_transc_mode ? (float)sin((double)x) : sinf(x); }
 float o_cos(float x) { return g_transc_mode ? (float)cos((double)x) : cosf(x); }
 float o_tan(float x) { return g_transc_mode ? (float)tan((double)x) : tanf(x); }
@@ -652,6 +654,64 @@ static void llij_gauss(float lat, float lon, const orc_proj *p, float *io, float
     *io = i; *jo = j;
 }
 
+/* llij_rotlatlon, module_map_utils.F:1659-1829.  REAL(KIND=HIGH) = binary64; `pi = ACOS(-1.0)` is the DEFAULT-REAL arc cosine
+ * widened, `phi / REAL(..)` a default-real division.  The routine's nearest-mass-point search (:1729-1815) ends in the locals
+ * i, j, which are never returned: the outputs are the real-valued position set at :1731-1737 / :1773-1779. */
+static double d_sin(double x) { return sin(x); }
+static void llij_rotlatlon(float lat, float lon, const orc_proj *p, float *i_real, float *j_real)
+{
+    double glatd = lat, glond = -lon;
+    double dphd = (double)(p->phi / (float)((p->jydim - 1) / 2)), dlmd = (double)(p->lambda / (float)(p->ixdim - 1));
+    double pi = (double)o_acosf_m1(), d2r = pi / 180.0, r2d = 1.0 / d2r;
+    int jmt = p->jydim / 2 + 1;
+    double glat = glatd * d2r, glon = glond * d2r;
+    double tph0 = (double)p->lat1 * d2r, tlm0 = -(double)p->lon1 * d2r;
+    double x = cos(tph0) * cos(glat) * cos(glon - tlm0) + d_sin(tph0) * d_sin(glat);
+    double y = -cos(glat) * d_sin(glon - tlm0);
+    double z = cos(tph0) * d_sin(glat) - d_sin(tph0) * cos(glat) * cos(glon - tlm0);
+    double tlat = r2d * atan(z / sqrt(x * x + y * y));
+    double tlon = r2d * atan(y / x);
+    double row = tlat / dphd + jmt, col = tlon / dlmd + p->ixdim;
+    if ((row - (int)row) > (double)0.999f) row = row + (double)0.0002f;
+    else if ((col - (int)col) > (double)0.999f) col = col + (double)0.0002f;
+    int nrow = (int)row;
+    if (p->stagger == ORC_HH) {
+        *i_real = (nrow % 2 == 0) ? (float)(col / 2.0) : (float)(col / 2.0 + 0.5);
+        *j_real = (float)row;
+    } else if (p->stagger == ORC_VV) {
+        *i_real = (nrow % 2 == 0) ? (float)(col / 2.0 + 0.5) : (float)(col / 2.0);
+        *j_real = (float)row;
+    } else { *i_real = 0.0f; *j_real = 0.0f; }      /* the reference leaves i_real, j_real unset; map_set is only given HH or VV */
+}
+/* ijll_rotlatlon, :1832-1909: dphd, dlmd, col, jj and the (jj - midrow) * dphd products are default REAL here */
+static void ijll_rotlatlon(float i, float j, const orc_proj *p, float *lat, float *lon)
+{
+    float jj = j;
+    if ((j - (float)(int)j) > 0.999f) jj = j + 0.0002f;
+    int jh = (int)jj;
+    float dphd = p->phi / (float)((p->jydim - 1) / 2), dlmd = p->lambda / (float)(p->ixdim - 1);
+    double pi = (double)o_acosf_m1(), d2r = pi / 180.0, r2d = 1.0 / d2r;
+    double tph0 = (double)p->lat1 * d2r, tlm0 = -(double)p->lon1 * d2r;
+    int midrow = (p->jydim + 1) / 2, midcol = p->ixdim;
+    float col = 2.0f * i - 1.0f + (float)abs((jh + 1) % 2);
+    double tlatd = (double)((jj - (float)midrow) * dphd), tlond = (double)((col - (float)midcol) * dlmd);
+    if (p->stagger == ORC_VV) {
+        if (jh % 2 == 0) tlond = tlond - (double)dlmd; else tlond = tlond + (double)dlmd;
+    }
+    double tlatr = tlatd * d2r, tlonr = tlond * d2r;
+    double arg1 = d_sin(tlatr) * cos(tph0) + cos(tlatr) * d_sin(tph0) * cos(tlonr);
+    double glatr = asin(arg1), glatd = glatr * r2d;
+    double arg2 = cos(tlatr) * cos(tlonr) / (cos(glatr) * cos(tph0)) - tan(glatr) * tan(tph0);
+    if (fabs(arg2) > 1.0) arg2 = fabs(arg2) / arg2;
+    double fctr = 1.0;
+    if (tlond > 0.0) fctr = -1.0;
+    double glond = tlm0 * r2d + fctr * acos(arg2) * r2d;
+    *lat = (float)glatd;
+    *lon = (float)(-glond);
+    if (*lon > 180.0f) *lon = *lon - 360.0f;
+    if (*lon < -180.0f) *lon = *lon + 360.0f;
+}
+
 /* module_map_utils.F:570-626 */
 void orc_latlon_to_ij(const orc_proj *p, float lat, float lon, float *i, float *j)
 {
@@ -665,7 +725,8 @@ void orc_latlon_to_ij(const orc_proj *p, float lat, float lon, float *i, float *
     case ORC_PROJ_GAUSS: llij_gauss(lat, lon, p, i, j); break;
     case ORC_PROJ_CYL: llij_cyl(lat, lon, p, i, j); break;
     case ORC_PROJ_CASSINI: llij_cassini(lat, lon, p, i, j); break;
-    default: *i = 0.0f; *j = 0.0f; break; /* PROJ_ROTLL (NMM E-grid) not restated */
+    case ORC_PROJ_ROTLL: llij_rotlatlon(lat, lon, p, i, j); break;
+    default: *i = 0.0f; *j = 0.0f; break;
     }
 }
 
@@ -681,6 +742,7 @@ void orc_ij_to_latlon(const orc_proj *p, float i, float j, float *lat, float *lo
     case ORC_PROJ_LC: ijll_lc(i, j, p, lat, lon); break;
     case ORC_PROJ_CYL: ijll_cyl(i, j, p, lat, lon); break;
     case ORC_PROJ_CASSINI: ijll_cassini(i, j, p, lat, lon); break;
+    case ORC_PROJ_ROTLL: ijll_rotlatlon(i, j, p, lat, lon); break;
     default: *lat = 0.0f; *lon = 0.0f; break;
     }
 }

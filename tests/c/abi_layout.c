@@ -20,12 +20,14 @@ int main(void)
     OFF(wpsgpu_proj, hemi); OFF(wpsgpu_proj, cone); OFF(wpsgpu_proj, polei); OFF(wpsgpu_proj, polej); OFF(wpsgpu_proj, rsw);
     OFF(wpsgpu_proj, rebydx); OFF(wpsgpu_proj, knowni); OFF(wpsgpu_proj, knownj); OFF(wpsgpu_proj, re_m); OFF(wpsgpu_proj, rho0);
     OFF(wpsgpu_proj, nc); OFF(wpsgpu_proj, bigc); OFF(wpsgpu_proj, gauss_lat);
+    OFF(wpsgpu_proj, ixdim); OFF(wpsgpu_proj, jydim); OFF(wpsgpu_proj, phi); OFF(wpsgpu_proj, lambda);
     SZ(wpsgpu_map_args);
     OFF(wpsgpu_map_args, present); OFF(wpsgpu_map_args, lat1); OFF(wpsgpu_map_args, lon1); OFF(wpsgpu_map_args, lat0);
     OFF(wpsgpu_map_args, lon0); OFF(wpsgpu_map_args, knowni); OFF(wpsgpu_map_args, knownj); OFF(wpsgpu_map_args, dx);
     OFF(wpsgpu_map_args, dy); OFF(wpsgpu_map_args, latinc); OFF(wpsgpu_map_args, loninc); OFF(wpsgpu_map_args, stdlon);
     OFF(wpsgpu_map_args, truelat1); OFF(wpsgpu_map_args, truelat2); OFF(wpsgpu_map_args, r_earth); OFF(wpsgpu_map_args, nlat);
     OFF(wpsgpu_map_args, nxmin); OFF(wpsgpu_map_args, nxmax); OFF(wpsgpu_map_args, stagger);
+    OFF(wpsgpu_map_args, ixdim); OFF(wpsgpu_map_args, jydim); OFF(wpsgpu_map_args, phi); OFF(wpsgpu_map_args, lambda);
     SZ(wpsgpu_field_opts);
     OFF(wpsgpu_field_opts, ops); OFF(wpsgpu_field_opts, opts); OFF(wpsgpu_field_opts, missing_value); OFF(wpsgpu_field_opts, fill_missing);
     OFF(wpsgpu_field_opts, masked); OFF(wpsgpu_field_opts, mask_val); OFF(wpsgpu_field_opts, mask_rel);

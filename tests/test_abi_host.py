@@ -91,6 +91,7 @@ PROJS = [
     ("PROJ_PS_WGS84", dict(truelat1=70., stdlon=-45., lat1=65., lon1=-50., knowni=100., knownj=100., dx=5000.)),
     ("PROJ_ALBERS_NAD83", dict(truelat1=29.5, truelat2=45.5, stdlon=-96., lat1=23., lon1=-96., knowni=1., knownj=1., dx=1000.)),
     ("PROJ_GAUSS", dict(nlat=47, lat1=88.542, lon1=0., loninc=1.875, nxmax=192)),
+    ("PROJ_ROTLL", dict(ixdim=120, jydim=241, phi=12.0, lat1=38.0, lon1=-97.0, stagger=5, **{"lambda": 10.0})),
 ]
 
 
@@ -106,6 +107,7 @@ def test_map_set_matches_oracle_bit_for_bit(orc, name, kw):
         a, b = np.float32(getattr(po, f)), np.float32(getattr(pg, f))
         assert a.tobytes() == b.tobytes(), (name, f, a, b)
     assert (po.nxmin, po.nxmax, po.nlat) == (pg.nxmin, pg.nxmax, pg.nlat)
+    assert (po.ixdim, po.jydim, po.stagger, po.phi, po.lambda_) == (pg.ixdim, pg.jydim, pg.stagger, pg.phi, getattr(pg, "lambda"))
     if name == "PROJ_GAUSS":
         assert np.array_equal(np.array(po.gauss_lat[:94], np.float32), np.array(pg.gauss_lat[:94], np.float32))
 

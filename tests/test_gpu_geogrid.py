@@ -26,10 +26,10 @@ def tiles_for(domain_ll, dxdeg, tile_n, bdr, known_lat=-89.99583, known_lon=-179
 
 
 def run_field(orc, handle, itype, chain, nk, start_k, tile_fn, tile_n, bdr, dxdeg, nx=60, ny=50, dx=9000.0,
-              landmask=None, mask_val=-1.0, msg=1e20, fill=1e20, ilevel=1, scale=None, stag=1, sr=1):
+              landmask=None, mask_val=-1.0, msg=1e20, fill=1e20, ilevel=1, scale=None, stag=1, sr=1, dom=None):
     from wps_b200 import capi
     orc.set_transc_mode(1)
-    odom, gdom = conus_like(nx, ny, dx, 30.0, 60.0, -98.0, 39.0, -105.0)
+    odom, gdom = dom if dom is not None else conus_like(nx, ny, dx, 30.0, 60.0, -98.0, 39.0, -105.0)
     gx, gy = nx + 6, ny + 6  # patch +- HALO_WIDTH as process_tile does
     xlat, xlon = orc.get_lat_lon_fields(odom, -2, -2, gx, gy, stag)
     kw = dict(dlat=dxdeg, dlon=dxdeg, known_x=1.0, known_y=1.0, known_lat=-89.99583, known_lon=-179.99583)
@@ -119,6 +119,24 @@ def test_categorical_overlay_half_area_rule(orc, handle):
     g, o, _ = run_field(orc, handle, capi.CATEGORICAL, "nearest_neighbor", 21, 1, cat_tile, 64, 0, 0.05, nx=40, ny=36,
                         dx=9000.0, ilevel=2)
     assert_bitexact(g, o, "overlay categorical")
+
+
+def test_nmm_egrid_domain(orc, handle):
+    """A rotated lat-lon (NMM E-grid, PROJ_ROTLL) domain: where_maps_to goes through llij_rotlatlon with the HH / VV stagger the
+    field is defined on (proc_point_module.F:245-310 -> llxy_module.F:800-804); categorical counts on mass points and
+    grid-cell averages on velocity points, against the oracle."""
+    from wps_b200 import capi
+    kw = dict(ixdim=40, jydim=61, phi=2.4, lat1=39.0, lon1=-100.0, stagger=capi.HH)
+    kw["lambda"] = 3.0
+    orc.set_transc_mode(1)
+    dom = (orc.map_set(orc.PROJ_ROTLL, **kw), capi.map_set(capi.PROJ_ROTLL, **kw))
+    g, o, nt = run_field(orc, handle, capi.CATEGORICAL, "nearest_neighbor", 21, 1, cat_tile, 120, 0, 0.00833333, nx=39, ny=61, stag=capi.HH, dom=dom)
+    assert nt >= 4 and (o[:, 3:-3, 3:-3].sum(0) > 0).mean() > 0.9
+    assert_bitexact(g, o, "LANDUSEF counts on E-grid mass points")
+    dom = (orc.map_set(orc.PROJ_ROTLL, **kw), capi.map_set(capi.PROJ_ROTLL, **kw))
+    g, o, nt = run_field(orc, handle, capi.SP_CONTINUOUS, "average_gcell(4.0)+four_pt+average_4pt", 1, 1, topo_tile, 120, 3, 0.00833333,
+                         nx=39, ny=61, stag=capi.VV, dom=dom)
+    assert np.abs(g - o).max() <= 1e-6 * np.abs(o).max(), "HGT_V on E-grid velocity points"
 
 
 def test_sp_continuous_topography(orc, handle):

@@ -180,3 +180,39 @@ def test_rotate_winds_cassini(orc, handle, idir):
     # without the latitudes the Cassini rotation is refused loudly
     with pytest.raises(capi.WpsGpuError):
         handle.rotate_winds(idir, pg, u.copy(), um, v.copy(), vm, xlon_u, xlon_v)
+
+
+def test_rotated_latlon_nmm_egrid(orc, handle):
+    """PROJ_ROTLL (NMM E-grid, module_map_utils.F:1659-1909) with the HH / VV staggers lltoxy and xytoll switch the projection
+    to (llxy_module.F:800-804, :851-862): device against the oracle on the same inputs -- binary64 arithmetic on both sides,
+    identical except where CUDA's and glibc's binary64 functions round differently -- and the E-grid geometry outputs."""
+    from wps_b200 import capi
+    rng = np.random.default_rng(11)
+    n = 200000
+    kw = dict(ixdim=120, jydim=241, phi=12.0, lat1=38.0, lon1=-97.0)
+    kw["lambda"] = 10.0
+    orc.set_transc_mode(1)
+    for map_stag in (capi.HH, capi.VV):
+        po, pg = orc.map_set(orc.PROJ_ROTLL, stagger=map_stag, **kw), capi.map_set(capi.PROJ_ROTLL, stagger=map_stag, **kw)
+        for stag in (capi.HH, capi.VV, capi.M):      # M: the stagger map_set was given stays in force
+            x = rng.uniform(-5, 130, n).astype(np.float32)
+            y = rng.uniform(-5, 250, n).astype(np.float32)
+            x[:2000] = np.round(x[:2000]); y[:2000] = np.round(y[:2000])       # grid points: the 0.999 / 0.0002 nudges
+            po.stagger = map_stag
+            lat_o, lon_o = orc.xytoll(po, x, y, stag)
+            lat_g, lon_g = handle.xytoll(pg, x, y, stag)
+            d = np.maximum(ulp_diff(lat_g, lat_o), ulp_diff(lon_g, lon_o))
+            assert (d > 0).mean() < 1e-4 and d.max() <= 2, ("xytoll", map_stag, stag, (d > 0).mean(), d.max())
+            po.stagger = map_stag
+            xo, yo = orc.lltoxy(po, lat_o, lon_o, stag)
+            xg, yg = handle.lltoxy(pg, lat_o, lon_o, stag)
+            d = np.maximum(ulp_diff(xg, xo), ulp_diff(yg, yo))
+            assert (d > 0).mean() < 1e-4 and d.max() <= 2, ("lltoxy", map_stag, stag, (d > 0).mean(), d.max())
+    # get_lat_lon_fields on the E-grid: mass and velocity points
+    po, pg = orc.map_set(orc.PROJ_ROTLL, stagger=capi.HH, **kw), capi.map_set(capi.PROJ_ROTLL, stagger=capi.HH, **kw)
+    for stag in (capi.HH, capi.VV):
+        po.stagger = capi.HH
+        la_o, lo_o = orc.get_lat_lon_fields(po, 1, 1, 119, 241, stag)
+        la_g, lo_g = handle.xytoll_grid(pg, stag, 1, 1, 119, 241)
+        d = np.maximum(ulp_diff(la_g, la_o), ulp_diff(lo_g, lo_o))
+        assert (d > 0).mean() < 5e-4 and d.max() <= 2, (stag, (d > 0).mean(), d.max())      # 28 k points: a handful of 1-ulp cases

@@ -191,3 +191,40 @@ def test_geogrid_golden_regression():
         a, b = g[k], now[k]
         assert a.shape == b.shape, k
         assert np.array_equal(a.view(np.int32) if a.dtype == np.float32 else a, b.view(np.int32) if b.dtype == np.float32 else b), k
+
+
+def test_rotated_latlon_known_answers(orc):
+    """PROJ_ROTLL (module_map_utils.F:1659-1909), hand-derived: the grid's centre (lat1, lon1) is rotated (0, 0), i.e. column
+    ixdim of the 2*ixdim-1 interleaved columns and row jydim/2+1; on an odd row a mass point sits at col/2 + 0.5 and a velocity
+    point at col/2 (:1731-1737, :1773-1779); along the central meridian the rotated latitude equals lat - lat1, so the row moves
+    by 1 per dphd = phi / ((jydim-1)/2) degrees; xytoll inverts lltoxy on grid points to the 0.0002 nudge of :1723-1727."""
+    orc.set_transc_mode(1)
+    kw = dict(ixdim=120, jydim=241, phi=12.0, lat1=38.0, lon1=-97.0)
+    kw["lambda"] = 10.0
+    f = np.float32
+    p = orc.map_set(orc.PROJ_ROTLL, stagger=orc.HH, **kw)
+    x, y = orc.lltoxy(p, np.array([38.0], f), np.array([-97.0], f), stagger=orc.HH)
+    assert x[0] == 60.5 and y[0] == 121.0
+    x, y = orc.lltoxy(p, np.array([38.0], f), np.array([-97.0], f), stagger=orc.VV)
+    assert x[0] == 60.0 and y[0] == 121.0
+    dphd = 12.0 / 120.0
+    x, y = orc.lltoxy(p, np.array([38.0 + 10 * dphd], f), np.array([-97.0], f), stagger=orc.HH)
+    assert abs(y[0] - 131.0) < 2e-4 + 1e-4 and abs(x[0] - 60.5) < 1e-4           # row 131 is odd as well
+    x, y = orc.lltoxy(p, np.array([38.0 + 11 * dphd], f), np.array([-97.0], f), stagger=orc.HH)
+    assert abs(y[0] - 132.0) < 3e-4 and abs(x[0] - 60.0) < 1e-4                   # even row: no half-column shift
+    rng = np.random.default_rng(3)
+    for st in (orc.HH, orc.VV):
+        ii = rng.integers(1, 120, 500).astype(f)
+        jj = rng.integers(1, 241, 500).astype(f)
+        la, lo = orc.xytoll(p, ii, jj, stagger=st)
+        x2, y2 = orc.lltoxy(p, la, lo, stagger=st)
+        assert np.abs(x2 - ii).max() < 3e-4 and np.abs(y2 - jj).max() < 3e-4
+    # a velocity point with the indices of a mass point lies one column of the interleaved grid (dlmd) to its east on odd rows,
+    # to its west on even rows (:1868-1874)
+    p.stagger = orc.HH
+    la_h, lo_h = orc.xytoll(p, np.array([60.0, 60.0], f), np.array([121.0, 122.0], f), stagger=orc.HH)
+    la_v, lo_v = orc.xytoll(p, np.array([60.0, 60.0], f), np.array([121.0, 122.0], f), stagger=orc.VV)
+    assert lo_v[0] > lo_h[0] and lo_v[1] < lo_h[1]
+    # map_set demands ixdim, jydim, phi, lambda, lat1, lon1, stagger (:394-405)
+    with pytest.raises(ValueError):
+        orc.map_set(orc.PROJ_ROTLL, ixdim=120, jydim=241, phi=12.0, lat1=38.0, lon1=-97.0, stagger=orc.HH)

@@ -26,7 +26,8 @@ MAX_OPS = 16
 MAX_GAUSS = 2048
 
 _A = dict(lat1=0, lon1=1, lat0=2, lon0=3, knowni=4, knownj=5, dx=6, dy=7, latinc=8, loninc=9, stdlon=10,
-          truelat1=11, truelat2=12, nlat=13, nxmin=17, nxmax=18, stagger=19, r_earth=22)
+          truelat1=11, truelat2=12, nlat=13, ixdim=15, jydim=16, nxmin=17, nxmax=18, stagger=19, phi=20, r_earth=22)
+_A["lambda"] = 21
 
 
 class Proj(C.Structure):
@@ -34,14 +35,14 @@ class Proj(C.Structure):
                [(n, C.c_float) for n in ("lat1", "lon1", "lat0", "lon0", "dx", "dy", "latinc", "loninc", "dlon",
                                          "stdlon", "truelat1", "truelat2", "hemi", "cone", "polei", "polej", "rsw",
                                          "rebydx", "knowni", "knownj", "re_m", "rho0", "nc", "bigc")] + \
-               [("gauss_lat", C.c_float * MAX_GAUSS)]
+               [("gauss_lat", C.c_float * MAX_GAUSS), ("ixdim", C.c_int32), ("jydim", C.c_int32), ("phi", C.c_float), ("lambda", C.c_float)]
 
 
 class MapArgs(C.Structure):
     _fields_ = [("present", C.c_uint32)] + \
                [(n, C.c_float) for n in ("lat1", "lon1", "lat0", "lon0", "knowni", "knownj", "dx", "dy", "latinc",
                                          "loninc", "stdlon", "truelat1", "truelat2", "r_earth")] + \
-               [(n, C.c_int32) for n in ("nlat", "nxmin", "nxmax", "stagger")]
+               [(n, C.c_int32) for n in ("nlat", "nxmin", "nxmax", "stagger", "ixdim", "jydim")] + [("phi", C.c_float), ("lambda", C.c_float)]
 
 
 class FieldOpts(C.Structure):

@@ -89,6 +89,7 @@ static void h_map_init(wpsgpu_proj& p)
     p.polei = -999.9f; p.polej = -999.9f; p.rsw = -999.9f; p.knowni = -999.9f; p.knownj = -999.9f;
     p.re_m = WPS_EARTH_RADIUS_M; p.init = 0; p.rho0 = 0.0f; p.nc = 0.0f; p.bigc = 0.0f; p.comp_ll = 0;
     p.code = -1;
+    p.ixdim = -999; p.jydim = -999; p.phi = -999.9f; p.lambda = -999.9f;    // map_init :215-218
 }
 
 static void h_lgord(double* f, double cosc, int n)
@@ -178,8 +179,10 @@ static int h_map_set(int code, const wpsgpu_map_args& a, wpsgpu_proj& p)
         need = WPSGPU_A_LATINC | WPSGPU_A_LONINC | WPSGPU_A_LAT1 | WPSGPU_A_LON1 | WPSGPU_A_LAT0 | WPSGPU_A_LON0 | WPSGPU_A_KNOWNI | WPSGPU_A_KNOWNJ | WPSGPU_A_STDLON; break;
     case WPSGPU_PROJ_GAUSS:
         need = WPSGPU_A_NLAT | WPSGPU_A_LAT1 | WPSGPU_A_LON1 | WPSGPU_A_LONINC; break;
+    case WPSGPU_PROJ_ROTLL:
+        need = WPSGPU_A_IXDIM | WPSGPU_A_JYDIM | WPSGPU_A_PHI | WPSGPU_A_LAMBDA | WPSGPU_A_LAT1 | WPSGPU_A_LON1 | WPSGPU_A_STAGGER; break;
     default:
-        WPS_CHECK(false, -10, "map_set: unsupported projection code %d (PROJ_ROTLL / NMM E-grid is out of scope)", code);
+        WPS_CHECK(false, -10, "map_set: Unknown projection code: %d", code);
     }
     WPS_CHECK((pr & need) == need, -11, "map_set: mandatory parameters missing for projection code %d", code);
     if (has(WPSGPU_A_LAT1)) WPS_CHECK(fabsf(a.lat1) <= 90.0f, -12, "map_set: -90N <= lat1 <= 90N required");
@@ -213,6 +216,10 @@ static int h_map_set(int code, const wpsgpu_map_args& a, wpsgpu_proj& p)
     if (has(WPSGPU_A_TRUELAT2)) p.truelat2 = a.truelat2;
     if (has(WPSGPU_A_NLAT)) p.nlat = a.nlat;
     if (has(WPSGPU_A_STAGGER)) p.stagger = a.stagger;
+    if (has(WPSGPU_A_IXDIM)) p.ixdim = a.ixdim;
+    if (has(WPSGPU_A_JYDIM)) p.jydim = a.jydim;
+    if (has(WPSGPU_A_PHI)) p.phi = a.phi;
+    if (has(WPSGPU_A_LAMBDA)) p.lambda = a.lambda;
     if (has(WPSGPU_A_R_EARTH)) p.re_m = a.r_earth;
     if (has(WPSGPU_A_DX)) {
         if (code == WPSGPU_PROJ_LC || code == WPSGPU_PROJ_PS || code == WPSGPU_PROJ_PS_WGS84 ||

@@ -46,6 +46,8 @@ struct DevProj {
     float lat1, lon1, lat0, lon0, dx, dy, latinc, loninc, dlon, stdlon, truelat1, truelat2, hemi, cone,
           polei, polej, rsw, rebydx, knowni, knownj, re_m, rho0, nc, bigc;
     const float* gauss_lat;
+    int stagger, ixdim, jydim;      // PROJ_ROTLL
+    float phi, lambda;
 };
 
 inline DevProj to_dev(const wpsgpu_proj& p, const float* gauss)
@@ -57,6 +59,7 @@ inline DevProj to_dev(const wpsgpu_proj& p, const float* gauss)
     d.truelat2 = p.truelat2; d.hemi = p.hemi; d.cone = p.cone; d.polei = p.polei; d.polej = p.polej;
     d.rsw = p.rsw; d.rebydx = p.rebydx; d.knowni = p.knowni; d.knownj = p.knownj; d.re_m = p.re_m;
     d.rho0 = p.rho0; d.nc = p.nc; d.bigc = p.bigc; d.gauss_lat = gauss;
+    d.stagger = p.stagger; d.ixdim = p.ixdim; d.jydim = p.jydim; d.phi = p.phi; d.lambda = p.lambda;
     return d;
 }
 
@@ -254,6 +257,7 @@ WPS_HD void llij_gauss(float lat, float lon, const DevProj& p, float& io, float&
     io = i; jo = j;
 }
 
+WPS_HD void llij_rotlatlon(float lat, float lon, const DevProj& p, int stagger, float& i_real, float& j_real);
 // latlon_to_ij, :570-626
 WPS_HD void latlon_to_ij(const DevProj& p, float lat, float lon, float& i, float& j)
 {
@@ -267,6 +271,7 @@ WPS_HD void latlon_to_ij(const DevProj& p, float lat, float lon, float& i, float
     case WPSGPU_PROJ_CASSINI: llij_cassini(lat, lon, p, i, j); break;
     case WPSGPU_PROJ_PS_WGS84: llij_ps_wgs84(lat, lon, p, i, j); break;
     case WPSGPU_PROJ_ALBERS_NAD83: llij_albers_nad83(lat, lon, p, i, j); break;
+    case WPSGPU_PROJ_ROTLL: llij_rotlatlon(lat, lon, p, p.stagger, i, j); break;
     default: i = 0.0f; j = 0.0f; break;
     }
 }
@@ -408,6 +413,66 @@ WPS_HD void ijll_albers_nad83(float i, float j, const DevProj& p, float& lat, fl
     lon = p.stdlon + theta * WPS_DEG_PER_RAD / p.nc;
 }
 
+// llij_rotlatlon, :1659-1829 (NMM E-grid).  REAL(KIND=HIGH) = binary64; `pi = ACOS(-1.0)` is the default-REAL arc cosine widened
+// (3.1415927410125732), `phi / REAL(..)` a default-real division.  The routine's nearest-mass-point search (:1729-1815) ends in
+// the locals i, j, which are never returned: the outputs are the real-valued position set at :1731-1737 / :1773-1779.
+#define WPS_PI_SP_AS_DP 3.1415927410125732
+WPS_HD void llij_rotlatlon(float lat, float lon, const DevProj& p, int stagger, float& i_real, float& j_real)
+{
+    const double glatd = lat, glond = -lon;
+    const double dphd = (double)(p.phi / (float)((p.jydim - 1) / 2)), dlmd = (double)(p.lambda / (float)(p.ixdim - 1));
+    const double pi = WPS_PI_SP_AS_DP, d2r = pi / 180.0, r2d = 1.0 / d2r;
+    const int jmt = p.jydim / 2 + 1;
+    const double glat = glatd * d2r, glon = glond * d2r;
+    const double tph0 = (double)p.lat1 * d2r, tlm0 = -(double)p.lon1 * d2r;
+    const double x = cos(tph0) * cos(glat) * cos(glon - tlm0) + sin(tph0) * sin(glat);
+    const double y = -cos(glat) * sin(glon - tlm0);
+    const double z = cos(tph0) * sin(glat) - sin(tph0) * cos(glat) * cos(glon - tlm0);
+    const double tlat = r2d * atan(z / sqrt(x * x + y * y));
+    const double tlon = r2d * atan(y / x);
+    double row = tlat / dphd + jmt, col = tlon / dlmd + p.ixdim;
+    if ((row - (int)row) > (double)0.999f) row = row + (double)0.0002f;
+    else if ((col - (int)col) > (double)0.999f) col = col + (double)0.0002f;
+    const int nrow = (int)row;
+    if (stagger == WPSGPU_HH) {
+        i_real = (nrow % 2 == 0) ? (float)(col / 2.0) : (float)(col / 2.0 + 0.5);
+        j_real = (float)row;
+    } else if (stagger == WPSGPU_VV) {
+        i_real = (nrow % 2 == 0) ? (float)(col / 2.0 + 0.5) : (float)(col / 2.0);
+        j_real = (float)row;
+    } else { i_real = 0.0f; j_real = 0.0f; }      // unset in the reference; map_set is only given HH or VV
+}
+// ijll_rotlatlon, :1832-1909: dphd, dlmd, col, jj and the (jj - midrow) * dphd products are default REAL here
+WPS_HD void ijll_rotlatlon(float i, float j, const DevProj& p, int stagger, float& lat, float& lon)
+{
+    float jj = j;
+    if ((j - (float)(int)j) > 0.999f) jj = j + 0.0002f;
+    const int jh = (int)jj;
+    const float dphd = p.phi / (float)((p.jydim - 1) / 2), dlmd = p.lambda / (float)(p.ixdim - 1);
+    const double pi = WPS_PI_SP_AS_DP, d2r = pi / 180.0, r2d = 1.0 / d2r;
+    const double tph0 = (double)p.lat1 * d2r, tlm0 = -(double)p.lon1 * d2r;
+    const int midrow = (p.jydim + 1) / 2, midcol = p.ixdim;
+    const int par = (jh + 1) % 2;
+    const float col = 2.0f * i - 1.0f + (float)(par < 0 ? -par : par);
+    const double tlatd = (double)((jj - (float)midrow) * dphd);
+    double tlond = (double)((col - (float)midcol) * dlmd);
+    if (stagger == WPSGPU_VV) {
+        if (jh % 2 == 0) tlond = tlond - (double)dlmd; else tlond = tlond + (double)dlmd;
+    }
+    const double tlatr = tlatd * d2r, tlonr = tlond * d2r;
+    const double arg1 = sin(tlatr) * cos(tph0) + cos(tlatr) * sin(tph0) * cos(tlonr);
+    const double glatr = asin(arg1), glatd = glatr * r2d;
+    double arg2 = cos(tlatr) * cos(tlonr) / (cos(glatr) * cos(tph0)) - tan(glatr) * tan(tph0);
+    if (fabs(arg2) > 1.0) arg2 = fabs(arg2) / arg2;
+    double fctr = 1.0;
+    if (tlond > 0.0) fctr = -1.0;
+    const double glond = tlm0 * r2d + fctr * acos(arg2) * r2d;
+    lat = (float)glatd;
+    lon = (float)(-glond);
+    if (lon > 180.0f) lon = lon - 360.0f;
+    if (lon < -180.0f) lon = lon + 360.0f;
+}
+
 // ij_to_latlon, :629-679
 WPS_HD void ij_to_latlon(const DevProj& p, float i, float j, float& lat, float& lon)
 {
@@ -420,6 +485,7 @@ WPS_HD void ij_to_latlon(const DevProj& p, float i, float j, float& lat, float& 
     case WPSGPU_PROJ_CASSINI: ijll_cassini(i, j, p, lat, lon); break;
     case WPSGPU_PROJ_PS_WGS84: ijll_ps_wgs84(i, j, p, lat, lon); break;
     case WPSGPU_PROJ_ALBERS_NAD83: ijll_albers_nad83(i, j, p, lat, lon); break;
+    case WPSGPU_PROJ_ROTLL: ijll_rotlatlon(i, j, p, p.stagger, lat, lon); break;
     default: lat = 0.0f; lon = 0.0f; break;
     }
 }
@@ -427,6 +493,10 @@ WPS_HD void ij_to_latlon(const DevProj& p, float i, float j, float& lat, float& 
 // lltoxy / xytoll, llxy_module.F:788-887
 WPS_HD void lltoxy(const DevProj& p, float xlat, float xlon, float& x, float& y, int stagger)
 {
+    if (p.code == WPSGPU_PROJ_ROTLL) {
+        // proj_stack(current_nest_number)%stagger = HH / VV (:800-804): the module state the reference mutates, by value here
+        llij_rotlatlon(xlat, xlon, p, (stagger == WPSGPU_HH || stagger == WPSGPU_VV) ? stagger : p.stagger, x, y);
+    } else
     latlon_to_ij(p, xlat, xlon, x, y);
     if (stagger == WPSGPU_U) x = x + 0.5f;
     else if (stagger == WPSGPU_V) y = y + 0.5f;
@@ -438,6 +508,12 @@ WPS_HD void xytoll(const DevProj& p, float x, float y, float& xlat, float& xlon,
     if (stagger == WPSGPU_U) rx = x - 0.5f;
     else if (stagger == WPSGPU_V) ry = y - 0.5f;
     else if (stagger == WPSGPU_CORNER) { rx = x - 0.5f; ry = y - 0.5f; }
+    if (p.code == WPSGPU_PROJ_ROTLL) {
+        // :851-862: HH, VV and CORNER overwrite proj%stagger before ij_to_latlon (CORNER makes ijll_rotlatlon take its H branch)
+        const int st = (stagger == WPSGPU_HH || stagger == WPSGPU_VV || stagger == WPSGPU_CORNER) ? stagger : p.stagger;
+        ijll_rotlatlon(rx, ry, p, st, xlat, xlon);
+        return;
+    }
     ij_to_latlon(p, rx, ry, xlat, xlon);
 }
 
