@@ -388,6 +388,23 @@ module wpsgpu_mod
          real(c_float), value :: dom_dy
          real(c_float) :: src(*), dst(*)
       end function
+      integer(c_int) function wpsgpu_smooth_egrid(handle, opt, npass, array, sx, ex, sy, ey, sz, ez, msgval, hflag) &
+                        bind(C, name='wpsgpu_smooth_egrid')
+         import :: c_int, c_ptr, c_float
+         type(c_ptr), value :: handle
+         integer(c_int), value :: opt, npass, sx, ex, sy, ey, sz, ez
+         real(c_float) :: array(*)
+         real(c_float), value :: msgval, hflag
+      end function
+      integer(c_int) function wpsgpu_rotate_winds_nmm(handle, idir, proj, u, u_mask, v, v_mask, vs1, vs2, ve1, ve2, xlat_v, xlon_v, nlev) &
+                        bind(C, name='wpsgpu_rotate_winds_nmm')
+         import :: c_int, c_int32_t, c_ptr, c_float, wpsgpu_proj
+         type(c_ptr), value :: handle
+         integer(c_int), value :: idir, vs1, vs2, ve1, ve2, nlev
+         type(wpsgpu_proj) :: proj
+         real(c_float) :: u(*), v(*), xlat_v(*), xlon_v(*)
+         integer(c_int32_t) :: u_mask(*), v_mask(*)
+      end function
       ! ---- MPAS remapping (remapper.F; process_mpas_fields, process_domain_module.F:1457-1962) ----
       integer(c_int) function wpsgpu_mpas_set_mesh(handle, mesh) bind(C, name='wpsgpu_mpas_set_mesh')
          import :: c_int, c_ptr, wpsgpu_mpas_mesh

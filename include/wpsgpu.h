@@ -241,6 +241,12 @@ int wpsgpu_rotate_winds_ll(wpsgpu_handle_t h, int idir, const wpsgpu_proj *proj,
                            int vs1, int vs2, int ve1, int ve2, const float *xlon_u, const float *xlon_v,
                            const float *xlat_u, const float *xlat_v, int nlev);
 
+/* map_to_met_nmm / met_to_map_nmm -> metmap_xform_nmm (rotate_winds_module.F:399-631): NMM E-grid, U and V collocated on the
+ * velocity points (vs1:ve1, vs2:ve2), nlev levels in place, masks [nlev][ny][nwords].  PROJ_ROTLL uses lat1 / lon1 and the
+ * latitudes / longitudes of the points; PROJ_LC / PS / CASSINI the rotation by stdlon of :571-583. */
+int wpsgpu_rotate_winds_nmm(wpsgpu_handle_t h, int idir, const wpsgpu_proj *proj, float *u, const int32_t *u_mask, float *v,
+                            const int32_t *v_mask, int vs1, int vs2, int ve1, int ve2, const float *xlat_v, const float *xlon_v, int nlev);
+
 /* ---- geogrid: calc_field (process_tile_module.F:1208-1681) ---- */
 typedef struct wpsgpu_geo_field {
     wpsgpu_proj dom_proj;           /* proj_stack(current_nest_number) */
@@ -295,6 +301,12 @@ int wpsgpu_fractions_dominant(wpsgpu_handle_t h, float *field, int64_t npts, int
 /* one_two_one / smth_desmth / smth_desmth_special (smooth_module.F:20,73,154), array(sx:ex,sy:ey,sz:ez) */
 int wpsgpu_smooth(wpsgpu_handle_t h, int opt, int npass, float *array, int sx, int ex, int sy, int ey,
                   int sz, int ez);
+/* one_two_one_egrid / smth_desmth_egrid (smooth_module.F:252-338, :448-585) for the NMM E-grid: msgval == 1.0 leaves points whose
+ * value is 0 alone, hflag == 1.0 selects mass points (else velocity points); smth-desmth_special is a no-op as in
+ * process_tile_module.F:675.  Levels other than the first: see oracle/orc_geogrid.c (the reference initialises its scratch
+ * for level index 1 only). */
+int wpsgpu_smooth_egrid(wpsgpu_handle_t h, int opt, int npass, float *array, int sx, int ex, int sy, int ey,
+                        int sz, int ez, float msgval, float hflag);
 /* get_lat_lon_fields (process_tile_module.F:1692) */
 int wpsgpu_xytoll_grid(wpsgpu_handle_t h, const wpsgpu_proj *dom, int stagger, int si, int sj, int ei, int ej,
                        float sub_x, float sub_y, float *xlat, float *xlon);

@@ -535,3 +535,20 @@ def mpas_extract_planes(wrf, mode=0, landmask=None, fill=0.0):
     lib().orc_mpas_extract_planes(fptr(np.ascontiguousarray(wrf)), nlev, C.c_long(nlat * nlon), int(mode),
                                   fptr(None if landmask is None else np.ascontiguousarray(landmask, dtype=np.float32)), C.c_float(fill), fptr(out))
     return out
+
+
+def metmap_xform_nmm(proj, u, u_mask, v, v_mask, xlat_v, xlon_v, idir):
+    """metmap_xform_nmm (rotate_winds_module.F:455-631): one level, U and V on the E-grid's velocity points; returns copies."""
+    ny, nx = u.shape
+    uo, vo = np.ascontiguousarray(u).copy(), np.ascontiguousarray(v).copy()
+    lib().orc_metmap_xform_nmm(C.byref(proj), fptr(uo), iptr(np.ascontiguousarray(u_mask)), fptr(vo), iptr(np.ascontiguousarray(v_mask)),
+                               1, 1, nx, ny, fptr(np.ascontiguousarray(xlat_v)), fptr(np.ascontiguousarray(xlon_v)), int(idir))
+    return uo, vo
+
+
+def smooth_egrid(array, npass, opt, msgval=1.0e20, hflag=1.0, sx=1, sy=1):
+    """one_two_one_egrid / smth_desmth_egrid (smooth_module.F:252-585) on array [nz][ny][nx] with lower bounds (sx, sy); returns a copy."""
+    a = np.ascontiguousarray(array).copy()
+    nz, ny, nx = a.shape
+    lib().orc_smooth_egrid(fptr(a), int(sx), int(sx + nx - 1), int(sy), int(sy + ny - 1), 1, nz, int(npass), int(opt), C.c_float(msgval), C.c_float(hflag))
+    return a

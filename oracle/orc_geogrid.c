@@ -524,3 +524,43 @@ void orc_calc_dfdy(const float *src, float *dst, int si, int sj, int sk, int ei,
 #undef S3
 #undef M2
 }
+
+/* one_two_one_egrid / smth_desmth_egrid, smooth_module.F:252-338, :448-585 (NMM E-grid; hflag 1.0 = mass points, else velocity
+ * points).  `scratch(ix,iy,1) = array(ix,iy,1)` (:291, :503) initialises level index 1 only: for the other levels of a multi-level
+ * field the reference reads uninitialised scratch at the points the first sweep does not write; here every level starts from
+ * the array's values.  smth-desmth_special is 'not currently implemented for NMM' (process_tile_module.F:675): no-op. */
+void orc_smooth_egrid(float *array, int sx, int ex, int sy, int ey, int sz, int ez, int npass, int opt, float msgval, float hflag)
+{
+    if (opt != ORC_ONETWOONE && opt != ORC_SMTHDESMTH) return;
+    int nx = ex - sx + 1, ny = ey - sy + 1, nz = ez - sz + 1;
+    long n2 = (long)nx * ny, n3 = n2 * nz;
+#define EA(a, ix, iy, iz) (a)[(long)((iz) - sz) * n2 + (long)((iy) - sy) * nx + ((ix) - sx)]
+    float *scratch = (float *)malloc(sizeof(float) * (size_t)n3);
+    int *ihe = (int *)malloc(sizeof(int) * ny), *ihw = (int *)malloc(sizeof(int) * ny), *istart = (int *)malloc(sizeof(int) * ny);
+    for (int iy = sy; iy <= ey; ++iy) {
+        if (hflag == 1.0f) { ihe[iy - sy] = abs((iy + 1) % 2); istart[iy - sy] = (iy % 2 == 0) ? sx : sx + 1; }
+        else { ihe[iy - sy] = abs(iy % 2); istart[iy - sy] = (abs(iy % 2) == 1) ? sx : sx + 1; }
+        ihw[iy - sy] = ihe[iy - sy] - 1;
+    }
+    const float cenwgt = 1.52f, endwgt = 0.26f;
+#define ECOND(ix, iy, iz) ((msgval == 1.0f && EA(array, ix, iy, iz) != 0.0f) || msgval != 1.0f)
+    for (int ipass = 1; ipass <= npass; ++ipass) {
+        memcpy(scratch, array, sizeof(float) * (size_t)n3);
+        for (int iy = sy + 1; iy <= ey - 1; ++iy) for (int ix = istart[iy - sy]; ix <= ex - 1; ++ix) for (int iz = sz; iz <= ez; ++iz)
+            if (ECOND(ix, iy, iz))
+                EA(scratch, ix, iy, iz) = 0.50f * EA(array, ix, iy, iz) + 0.25f * (EA(array, ix + ihw[iy - sy], iy - 1, iz) + EA(array, ix + ihe[iy - sy], iy + 1, iz));
+        for (int iy = sy + 1; iy <= ey - 1; ++iy) for (int ix = istart[iy - sy]; ix <= ex - 1; ++ix) for (int iz = sz; iz <= ez; ++iz)
+            if (ECOND(ix, iy, iz))
+                EA(array, ix, iy, iz) = 0.50f * EA(scratch, ix, iy, iz) + 0.25f * (EA(scratch, ix + ihe[iy - sy], iy - 1, iz) + EA(scratch, ix + ihw[iy - sy], iy + 1, iz));
+        if (opt != ORC_SMTHDESMTH) continue;
+        for (int iy = sy + 2; iy <= ey - 2; ++iy) for (int ix = istart[iy - sy]; ix <= ex - 1; ++ix) for (int iz = sz; iz <= ez; ++iz)
+            if (ECOND(ix, iy, iz))
+                EA(scratch, ix, iy, iz) = cenwgt * EA(array, ix, iy, iz) - endwgt * (EA(array, ix + ihw[iy - sy], iy - 1, iz) + EA(array, ix + ihe[iy - sy], iy + 1, iz));
+        for (int iy = sy + 2; iy <= ey - 2; ++iy) for (int ix = istart[iy - sy]; ix <= ex - 1; ++ix) for (int iz = sz; iz <= ez; ++iz)
+            if (ECOND(ix, iy, iz))
+                EA(array, ix, iy, iz) = cenwgt * EA(scratch, ix, iy, iz) - endwgt * (EA(scratch, ix + ihe[iy - sy], iy - 1, iz) + EA(scratch, ix + ihw[iy - sy], iy + 1, iz));
+    }
+#undef ECOND
+#undef EA
+    free(scratch); free(ihe); free(ihw); free(istart);
+}

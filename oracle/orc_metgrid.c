@@ -377,3 +377,43 @@ void orc_fill_missing_levels(int nlev, const int32_t *levels, float *r_arr, int3
         }
     }
 }
+
+/* metmap_xform_nmm, rotate_winds_module.F:455-631: U and V collocated on the E-grid's velocity points */
+void orc_metmap_xform_nmm(const orc_proj *proj, float *u, const int32_t *u_mask, float *v, const int32_t *v_mask,
+                          int vs1, int vs2, int ve1, int ve2, const float *xlat_v, const float *xlon_v, int idir)
+{
+    const int nx = ve1 - vs1 + 1, ny = ve2 - vs2 + 1, nxw = (nx + 31) / 32;
+    const int rot = proj->code == ORC_PROJ_ROTLL;
+    if (!rot && !(proj->code == ORC_PROJ_LC || proj->code == ORC_PROJ_PS || proj->code == ORC_PROJ_CASSINI)) return;
+    float *u_new = (float *)malloc(sizeof(float) * (size_t)nx * ny), *v_new = (float *)malloc(sizeof(float) * (size_t)nx * ny);
+    float phi0 = proj->lat1 * ORC_RAD_PER_DEG, clontemp = proj->lon1, lmbd0;
+    if (clontemp < 0.0f) lmbd0 = (clontemp + 360.0f) * ORC_RAD_PER_DEG; else lmbd0 = clontemp * ORC_RAD_PER_DEG;
+    float sin_phi0 = o_sin(phi0), cos_phi0 = o_cos(phi0);
+    const float fdir = (float)idir;
+    for (int j = 0; j < ny; ++j) for (int i = 0; i < nx; ++i) {
+        const long k = (long)j * nx + i;
+        float sin_alpha, cos_alpha;
+        if (rot) {
+            float rlat_v = xlat_v[k] * ORC_RAD_PER_DEG, rlon_v = xlon_v[k] * ORC_RAD_PER_DEG;
+            float relm = rlon_v - lmbd0;
+            float big_denominator = o_cos(o_asin(cos_phi0 * o_sin(rlat_v) - sin_phi0 * o_cos(rlat_v) * o_cos(relm)));
+            sin_alpha = sin_phi0 * o_sin(relm) / big_denominator;
+            cos_alpha = (cos_phi0 * o_cos(rlat_v) + sin_phi0 * o_sin(rlat_v) * o_cos(relm)) / big_denominator;
+        } else {
+            float diff = fdir * (xlon_v[k] - proj->stdlon);
+            if (diff > 180.0f) diff = diff - 360.0f; else if (diff < -180.0f) diff = diff + 360.0f;
+            float alpha;
+            if (proj->code == ORC_PROJ_LC) alpha = diff * proj->cone * ORC_RAD_PER_DEG * proj->hemi;
+            else alpha = diff * ORC_RAD_PER_DEG * proj->hemi;
+            sin_alpha = o_sin(alpha); cos_alpha = o_cos(alpha);
+        }
+        const int ub = orc_bit_test(u_mask, nxw, i + 1, j + 1), vb = orc_bit_test(v_mask, nxw, i + 1, j + 1);
+        if (ub) { float u_map = u[k], v_map = vb ? v[k] : 0.0f; u_new[k] = cos_alpha * u_map + fdir * sin_alpha * v_map; }
+        else u_new[k] = u[k];
+        if (vb) { float v_map = v[k], u_map = ub ? u[k] : 0.0f; v_new[k] = -fdir * sin_alpha * u_map + cos_alpha * v_map; }
+        else v_new[k] = v[k];
+    }
+    memcpy(u, u_new, sizeof(float) * (size_t)nx * ny);
+    memcpy(v, v_new, sizeof(float) * (size_t)nx * ny);
+    free(u_new); free(v_new);
+}

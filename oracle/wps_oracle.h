@@ -169,6 +169,7 @@ void orc_metmap_xform(const orc_proj *proj, float *u, const int32_t *u_mask, flo
 /* ---- geogrid ---- */
 /* smooth_module.F:20-239; opt = ORC_ONETWOONE | ORC_SMTHDESMTH | ORC_SMTHDESMTH_SPECIAL */
 void orc_smooth(float *array, int sx, int ex, int sy, int ey, int sz, int ez, int npass, int opt);
+void orc_smooth_egrid(float *array, int sx, int ex, int sy, int ey, int sz, int ez, int npass, int opt, float msgval, float hflag);
 /* one tile of accum_categorical / accum_continuous (proc_point_module.F:100-779).
  * tile(src_min_x:src_max_x, src_min_y:src_max_y, src_min_z:src_max_z) in global source index space. */
 void orc_accum_categorical(orc_proj *src, orc_proj *dom, int istagger, const float *tile,
@@ -225,6 +226,9 @@ void orc_calc_dfdy(const float *src, float *dst, int si, int sj, int sk, int ei,
 #endif
 /* fill_missing_levels vertical interpolation, process_domain_module.F:2862-2921 */
 void orc_fill_missing_levels(int nlev, const int32_t *levels, float *r_arr, int32_t *valid, int nx, int ny);
+
+void orc_metmap_xform_nmm(const orc_proj *proj, float *u, const int32_t *u_mask, float *v, const int32_t *v_mask,
+                          int vs1, int vs2, int ve1, int ve2, const float *xlat_v, const float *xlon_v, int idir);
 
 /* ---- MPAS remapping (metgrid/src/remapper.F, mpas_mesh.F:5-30); connectivity 1-based, C row = Fortran last index ---- */
 typedef struct orc_mpas_mesh {

@@ -216,3 +216,52 @@ def test_rotated_latlon_nmm_egrid(orc, handle):
         la_g, lo_g = handle.xytoll_grid(pg, stag, 1, 1, 119, 241)
         d = np.maximum(ulp_diff(la_g, la_o), ulp_diff(lo_g, lo_o))
         assert (d > 0).mean() < 5e-4 and d.max() <= 2, (stag, (d > 0).mean(), d.max())      # 28 k points: a handful of 1-ulp cases
+
+
+def test_rotate_winds_nmm(orc, handle):
+    """metmap_xform_nmm on the device (E-grid, U and V collocated), both directions, rotated lat-lon and Lambert branches,
+    partial masks, several levels in one call: <= 1 ulp against the oracle (sin / cos / asin FP64-then-round on both sides)."""
+    from wps_b200 import capi
+    rng = np.random.default_rng(21)
+    orc.set_transc_mode(1)
+    kw = dict(ixdim=60, jydim=91, phi=9.0, lat1=38.0, lon1=-97.0, stagger=capi.VV)
+    kw["lambda"] = 12.0
+    cases = [(orc.map_set(orc.PROJ_ROTLL, **kw), capi.map_set(capi.PROJ_ROTLL, **kw))]
+    lc = dict(truelat1=30., truelat2=60., stdlon=-98., lat1=34.83, lon1=-81.03, knowni=30., knownj=25., dx=30000.)
+    cases.append((orc.map_set(orc.PROJ_LC, **lc), capi.map_set(capi.PROJ_LC, **lc)))
+    po0 = cases[0][0]
+    xlat, xlon = orc.get_lat_lon_fields(po0, 1, 1, 59, 91, orc.VV)
+    ny, nx = xlat.shape
+    nlev = 4
+    u = rng.uniform(-30, 30, (nlev, ny, nx)).astype(np.float32)
+    v = rng.uniform(-30, 30, (nlev, ny, nx)).astype(np.float32)
+    um = np.stack([bool_to_bits(rng.random((ny, nx)) < p) for p in (1.0, 0.9, 0.5, 0.0)])
+    vm = np.stack([bool_to_bits(rng.random((ny, nx)) < p) for p in (1.0, 0.8, 0.5, 1.0)])
+    for po, pg in cases:
+        for idir in (1, -1):
+            ug, vg = u.copy(), v.copy()
+            handle.rotate_winds_nmm(idir, pg, ug, um, vg, vm, xlat, xlon)
+            for l in range(nlev):
+                uo, vo = orc.metmap_xform_nmm(po, u[l], um[l], v[l], vm[l], xlat, xlon, idir)
+                d = max(ulp_diff(ug[l], uo).max(), ulp_diff(vg[l], vo).max())
+                frac = max((ulp_diff(ug[l], uo) > 0).mean(), (ulp_diff(vg[l], vo) > 0).mean())
+                assert d <= 2 and frac < 1e-3, (po.code, idir, l, d, frac)
+    # a projection the routine does not rotate for leaves the arrays alone (:473, :560)
+    pm = capi.map_set(capi.PROJ_MERC, truelat1=10., lat1=5., lon1=100., knowni=30., knownj=30., dx=27000.)
+    ug, vg = u.copy(), v.copy()
+    handle.rotate_winds_nmm(1, pm, ug, um, vg, vm, xlat, xlon)
+    assert np.array_equal(ug, u) and np.array_equal(vg, v)
+
+
+@pytest.mark.parametrize("opt", [1, 2, 3])
+@pytest.mark.parametrize("hflag", [1.0, 0.0])
+def test_egrid_smoothers_on_device(orc, handle, opt, hflag):
+    """one_two_one_egrid / smth_desmth_egrid through the C ABI, bit for bit: several levels, the msgval == 1.0 rule that leaves
+    zeros alone, odd and even lower bounds (the row parity decides which diagonal neighbours a point has)."""
+    rng = np.random.default_rng(int(10 * opt + hflag))
+    a = rng.uniform(-50, 3000, (3, 67, 85)).astype(np.float32)
+    a[:, 10:20, 10:30] = 0.0
+    for msgval, sx, sy, npass in ((1.0e20, 1, 1, 1), (1.0, 1, 1, 2), (1.0e20, -2, -2, 3), (1.0, 4, 7, 1)):
+        g = a.copy()
+        handle.smooth_egrid(g, opt, npass, msgval=msgval, hflag=hflag, sx=sx, sy=sy)
+        assert_bitexact(g, orc.smooth_egrid(a, npass, opt, msgval=msgval, hflag=hflag, sx=sx, sy=sy), "egrid smooth opt=%d" % opt)

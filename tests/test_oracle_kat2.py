@@ -228,3 +228,83 @@ def test_rotated_latlon_known_answers(orc):
     # map_set demands ixdim, jydim, phi, lambda, lat1, lon1, stagger (:394-405)
     with pytest.raises(ValueError):
         orc.map_set(orc.PROJ_ROTLL, ixdim=120, jydim=241, phi=12.0, lat1=38.0, lon1=-97.0, stagger=orc.HH)
+
+
+def test_nmm_wind_rotation_known_answers(orc):
+    """metmap_xform_nmm (rotate_winds_module.F:455-631): on the central meridian of the rotated grid the angle is zero; elsewhere
+    it is a pure rotation (speed kept, idir = +1 then -1 is the identity); a masked-out partner counts as 0 and a masked-out
+    component is copied (:519-541)."""
+    orc.set_transc_mode(1)
+    f = np.float32
+    p = orc.map_set(orc.PROJ_ROTLL, ixdim=40, jydim=61, phi=6.0, lat1=40.0, lon1=-100.0, stagger=orc.VV, **{"lambda": 8.0})
+    ny, nx = 5, 7
+    xlat = (40.0 + np.arange(ny, dtype=f)[:, None] * 2.0 + np.zeros((1, nx), f)).astype(f)
+    xlon = (-100.0 + (np.arange(nx, dtype=f)[None, :] - 3.0) * 4.0 + np.zeros((ny, 1), f)).astype(f)
+    rng = np.random.default_rng(5)
+    u, v = rng.uniform(-20, 20, (ny, nx)).astype(f), rng.uniform(-20, 20, (ny, nx)).astype(f)
+    full = np.full((ny, 1), -1, np.int32)
+    u1, v1 = orc.metmap_xform_nmm(p, u, full, v, full, xlat, xlon, 1)
+    # central meridian: alpha = 0 up to the rounding of relm = -100 deg - 260 deg = -2 pi (lon1 < 0 is moved to 0..360, :483-487)
+    assert np.abs(u1[:, 3] - u[:, 3]).max() < 1e-5 and np.abs(v1[:, 3] - v[:, 3]).max() < 1e-5
+    assert np.abs(np.hypot(u1, v1) - np.hypot(u, v)).max() < 1e-4
+    assert np.abs(u1[:, 0] - u[:, 0]).max() > 0.1                                            # off it the wind does turn
+    u2, v2 = orc.metmap_xform_nmm(p, u1, full, v1, full, xlat, xlon, -1)
+    assert np.abs(u2 - u).max() < 1e-4 and np.abs(v2 - v).max() < 1e-4
+    # masks: bit 0 of each row cleared in v_mask -> U there is cos(alpha) * u, V is copied
+    vm = np.full((ny, 1), -2, np.int32)
+    u3, v3 = orc.metmap_xform_nmm(p, u, full, v, vm, xlat, xlon, 1)
+    assert np.array_equal(v3[:, 0], v[:, 0]) and np.array_equal(u3[:, 1:], u1[:, 1:]) and np.all(np.abs(u3[:, 0]) <= np.abs(u[:, 0]))
+    # the Lambert branch of the same routine (:560-612) equals the C-grid rotation at collocated points with full masks
+    pl = orc.map_set(orc.PROJ_LC, truelat1=30., truelat2=60., stdlon=-98., lat1=34.83, lon1=-81.03, knowni=30., knownj=25., dx=30000.)
+    u4, v4 = orc.metmap_xform_nmm(pl, u, full, v, full, xlat, xlon, -1)
+    diff = -1.0 * (xlon.astype(np.float64) + 98.0)
+    alpha = np.deg2rad(diff) * float(pl.cone)
+    assert np.abs(u4 - (np.cos(alpha) * u - np.sin(alpha) * v)).max() < 1e-4
+    assert np.abs(v4 - (np.sin(alpha) * u + np.cos(alpha) * v)).max() < 1e-4
+
+
+def _py_egrid_smooth(a, npass, opt, msgval, hflag, sx, sy):
+    """one_two_one_egrid / smth_desmth_egrid written from smooth_module.F:252-338, :448-585 with Python loops (one level)."""
+    f = np.float32
+    a = a.copy()
+    ny, nx = a.shape
+    ex, ey = sx + nx - 1, sy + ny - 1
+    A = lambda arr, ix, iy: arr[iy - sy, ix - sx]          # noqa: E731
+    ihe, ihw, istart = {}, {}, {}
+    for iy in range(sy, ey + 1):
+        m = lambda v: int(np.fmod(v, 2))                   # noqa: E731  Fortran MOD truncates
+        ihe[iy] = abs(m(iy + 1)) if hflag == 1.0 else abs(m(iy))
+        ihw[iy] = ihe[iy] - 1
+        istart[iy] = (sx if m(iy) == 0 else sx + 1) if hflag == 1.0 else (sx if abs(m(iy)) == 1 else sx + 1)
+    cond = lambda ix, iy: (msgval == 1.0 and A(a, ix, iy) != 0.0) or msgval != 1.0     # noqa: E731
+    for _ in range(npass):
+        s = a.copy()
+        for cw, ew, lo in ((f(0.50), f(0.25), 1),) + (((f(1.52), f(-0.26), 2),) if opt == 2 else ()):
+            for iy in range(sy + lo, ey - lo + 1):
+                for ix in range(istart[iy], ex):
+                    if cond(ix, iy):
+                        s[iy - sy, ix - sx] = f(f(cw * A(a, ix, iy)) + f(ew * f(A(a, ix + ihw[iy], iy - 1) + A(a, ix + ihe[iy], iy + 1))))
+            for iy in range(sy + lo, ey - lo + 1):
+                for ix in range(istart[iy], ex):
+                    if cond(ix, iy):
+                        a[iy - sy, ix - sx] = f(f(cw * A(s, ix, iy)) + f(ew * f(A(s, ix + ihe[iy], iy - 1) + A(s, ix + ihw[iy], iy + 1))))
+    return a
+
+
+@pytest.mark.parametrize("opt", [1, 2])
+@pytest.mark.parametrize("hflag", [1.0, 0.0])
+def test_egrid_smoothers(orc, opt, hflag):
+    rng = np.random.default_rng(int(opt * 2 + hflag))
+    a = rng.uniform(-5, 50, (1, 14, 11)).astype(np.float32)
+    a[0, 4:7, 3:6] = 0.0
+    for msgval, sx, sy in ((1.0e20, 1, 1), (1.0, 1, 1), (1.0e20, -2, -2), (1.0, 0, 3)):
+        for npass in (1, 2):
+            got = orc.smooth_egrid(a, npass, opt, msgval=msgval, hflag=hflag, sx=sx, sy=sy)
+            ref = _py_egrid_smooth(a[0], npass, opt, msgval, hflag, sx, sy)
+            assert np.array_equal(got[0].view(np.int32), ref.view(np.int32)), (msgval, sx, sy, npass)
+            if msgval == 1.0:
+                assert (got[0, 4:7, 3:6] == 0.0).all()                       # zeros are left alone (:296)
+    c = np.full((1, 9, 9), 7.0, np.float32)
+    assert np.array_equal(orc.smooth_egrid(c, 3, 1, hflag=hflag), c)          # 0.5 c + 0.25 (2 c) = c
+    # smth-desmth_special: 'not currently implemented for NMM' (process_tile_module.F:675)
+    assert np.array_equal(orc.smooth_egrid(a, 2, 3, hflag=hflag), a)

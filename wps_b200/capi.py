@@ -373,6 +373,12 @@ class Handle:
                                            C.c_void_p(ptr(xlat_v)), int(nlev)))
 
     # ---- geogrid ----
+    def rotate_winds_nmm(self, idir, proj, u, u_mask, v, v_mask, xlat_v, xlon_v):
+        """metmap_xform_nmm (rotate_winds_module.F:455-631): u, v [nlev][ny][nx] on the E-grid's velocity points, in place."""
+        nlev, ny, nx = u.shape
+        check(lib().wpsgpu_rotate_winds_nmm(self._h, int(idir), C.byref(proj), C.c_void_p(ptr(u)), C.c_void_p(ptr(u_mask)), C.c_void_p(ptr(v)),
+                                            C.c_void_p(ptr(v_mask)), 1, 1, int(nx), int(ny), C.c_void_p(ptr(xlat_v)), C.c_void_p(ptr(xlon_v)), int(nlev)))
+
     def geogrid_field_begin(self, dom_proj, istagger, xlat, xlon, start_i, start_j, start_k, field, landmask=None):
         nk, ny, nx = field.shape
         f = GeoField()
@@ -448,6 +454,12 @@ class Handle:
         a3 = array if array.ndim == 3 else array.reshape((1,) + tuple(array.shape))
         nz, ny, nx = a3.shape
         check(lib().wpsgpu_smooth(self._h, int(opt), int(npass), C.c_void_p(ptr(array)), 1, nx, 1, ny, 1, nz))
+
+    def smooth_egrid(self, array, opt, npass, msgval=1.0e20, hflag=1.0, sx=1, sy=1):
+        """one_two_one_egrid / smth_desmth_egrid (smooth_module.F:252-585) in place on array [nz][ny][nx] with lower bounds (sx, sy)."""
+        nz, ny, nx = array.shape
+        check(lib().wpsgpu_smooth_egrid(self._h, int(opt), int(npass), C.c_void_p(ptr(array)), int(sx), int(sx + nx - 1), int(sy), int(sy + ny - 1),
+                                        1, int(nz), C.c_float(msgval), C.c_float(hflag)))
 
     def xytoll_grid(self, dom, stagger, si, sj, nx, ny, sub_x=1.0, sub_y=1.0, out=None):
         if out is None:

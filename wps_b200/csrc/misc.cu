@@ -409,6 +409,62 @@ __global__ void k_create_level(float value, const float* __restrict__ src, const
     }
 }
 
+
+// one sweep of one_two_one_egrid / smth_desmth_egrid (smooth_module.F:252-338, :448-585): the two diagonal neighbours of an
+// E-grid point in the rows below and above; `second` swaps the east / west offsets as the reference's second sweep of a pair
+// does; rows [sy + ylo, ey - ylo]; cond = the array whose value gates the update when msgval == 1.0 (:296, :306)
+__global__ void __launch_bounds__(256) k_egrid_sweep(const float* __restrict__ src, float* dst, const float* cond, int nx, int ny, int sy,
+                                                     int hflag1, int ylo, float cw, float ew, int second, int msg1)
+{
+    const int ix = blockIdx.x * 32 + threadIdx.x, iy0 = blockIdx.y * 8 + threadIdx.y;
+    if (ix >= nx || iy0 < ylo || iy0 > ny - 1 - ylo) return;
+    const int iy = sy + iy0;
+    const int par = hflag1 ? (iy + 1) % 2 : iy % 2;
+    const int ihe = par < 0 ? -par : par, ihw = ihe - 1;
+    const int istart = hflag1 ? (iy % 2 == 0 ? 0 : 1) : (iy % 2 != 0 ? 0 : 1);
+    if (ix < istart || ix > nx - 2) return;
+    const size_t pl = (size_t)blockIdx.z * nx * ny, k = pl + (size_t)iy0 * nx + ix;
+    if (msg1 && cond[k] == 0.0f) return;
+    const float a = src[k - nx + (second ? ihe : ihw)], b = src[k + nx + (second ? ihw : ihe)];
+    dst[k] = cw * src[k] + ew * (a + b);
+}
+
+// metmap_xform_nmm (rotate_winds_module.F:455-631): U and V collocated on the velocity points of the E-grid; the rotation
+// angle of a point once, then every level
+__global__ void __launch_bounds__(256) k_rotate_nmm(int code, float lat1, float lon1, float stdlon, float cone, float hemi, int idir,
+                                                    const float* __restrict__ xlat_v, const float* __restrict__ xlon_v, int nx, int ny, int nlev,
+                                                    float* __restrict__ u, const int* __restrict__ u_mask, float* __restrict__ v, const int* __restrict__ v_mask)
+{
+    const int i = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 8 + threadIdx.y;
+    if (i >= nx || j >= ny) return;
+    const size_t k = (size_t)j * nx + i;
+    const float fdir = (float)idir;
+    float sin_alpha, cos_alpha;
+    if (code == WPSGPU_PROJ_ROTLL) {
+        const float phi0 = lat1 * WPS_RAD_PER_DEG;
+        const float lmbd0 = lon1 < 0.0f ? (lon1 + 360.0f) * WPS_RAD_PER_DEG : lon1 * WPS_RAD_PER_DEG;
+        const float sin_phi0 = t_sin(phi0), cos_phi0 = t_cos(phi0);
+        const float rlat_v = xlat_v[k] * WPS_RAD_PER_DEG, rlon_v = xlon_v[k] * WPS_RAD_PER_DEG;
+        const float relm = rlon_v - lmbd0;
+        const float big_denominator = t_cos(t_asin(cos_phi0 * t_sin(rlat_v) - sin_phi0 * t_cos(rlat_v) * t_cos(relm)));
+        sin_alpha = sin_phi0 * t_sin(relm) / big_denominator;
+        cos_alpha = (cos_phi0 * t_cos(rlat_v) + sin_phi0 * t_sin(rlat_v) * t_cos(relm)) / big_denominator;
+    } else {
+        float diff = fdir * (xlon_v[k] - stdlon);
+        if (diff > 180.0f) diff = diff - 360.0f; else if (diff < -180.0f) diff = diff + 360.0f;
+        const float alpha = code == WPSGPU_PROJ_LC ? diff * cone * WPS_RAD_PER_DEG * hemi : diff * WPS_RAD_PER_DEG * hemi;
+        sin_alpha = t_sin(alpha); cos_alpha = t_cos(alpha);
+    }
+    const int nxw = (nx + 31) / 32;
+    const size_t npl = (size_t)nx * ny, nwl = (size_t)ny * nxw;
+    for (int l = 0; l < nlev; ++l) {
+        const bool ub = (u_mask[l * nwl + (size_t)j * nxw + (i >> 5)] >> (i & 31)) & 1, vb = (v_mask[l * nwl + (size_t)j * nxw + (i >> 5)] >> (i & 31)) & 1;
+        const float uo = u[l * npl + k], vo = v[l * npl + k];
+        if (ub) u[l * npl + k] = cos_alpha * uo + fdir * sin_alpha * (vb ? vo : 0.0f);
+        if (vb) v[l * npl + k] = -fdir * sin_alpha * (ub ? uo : 0.0f) + cos_alpha * vo;
+    }
+}
+
 static int begin_call(wpsgpu_ctx* h, size_t host_bytes)
 {
     WPS_CHECK(h != nullptr, -1, "NULL handle");
@@ -600,6 +656,68 @@ int wpsgpu_smooth(wpsgpu_handle_t h, int opt, int npass, float* array, int sx, i
     if (h->ptr_mode == WPSGPU_PTR_DEVICE) {
         if (result != a) WPS_CUDA(cudaMemcpyAsync(a, result, bytes, cudaMemcpyDeviceToDevice, h->stream));   // single pass: s1 -> array
     } else WPS_TRY(copy_out(h, array, result, bytes));
+    return end_call(h);
+}
+
+int wpsgpu_smooth_egrid(wpsgpu_handle_t h, int opt, int npass, float* array, int sx, int ex, int sy, int ey, int sz, int ez, float msgval, float hflag)
+{
+    WPS_CHECK(h && array, -1, "wpsgpu_smooth_egrid: NULL argument");
+    WPS_CHECK(opt >= WPSGPU_ONETWOONE && opt <= WPSGPU_SMTHDESMTH_SPECIAL, -1, "unknown smooth option %d", opt);
+    if (opt == WPSGPU_SMTHDESMTH_SPECIAL) return 0;     // 'smth-desmth_special is not currently implemented for NMM. No smoothing will be done.'
+    const int nx = ex - sx + 1, ny = ey - sy + 1, nz = ez - sz + 1;
+    WPS_CHECK(nx > 0 && ny > 0 && nz > 0, -1, "wpsgpu_smooth_egrid: bad dimensions");
+    const size_t bytes = sizeof(float) * (size_t)nx * ny * nz;
+    if (npass <= 0) return 0;
+    WPS_TRY(begin_call(h, 2 * bytes + 4096));
+    if (h->ptr_mode == WPSGPU_PTR_DEVICE) WPS_TRY(h->arena.reserve(bytes + (1 << 20), h->stream));
+    void* da;
+    WPS_TRY(stage_inout(h, array, bytes, &da));
+    float* a = (float*)da;
+    float* sc = (float*)h->arena.take(bytes);
+    WPS_CHECK(sc != nullptr, -3, "device arena exhausted");
+    const dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8, nz);
+    const int h1 = hflag == 1.0f ? 1 : 0, m1 = msgval == 1.0f ? 1 : 0;
+    for (int ipass = 0; ipass < npass; ++ipass) {
+        // scratch starts from the array (the reference initialises level index 1 only, :291, :503; see orc_smooth_egrid)
+        WPS_CUDA(cudaMemcpyAsync(sc, a, bytes, cudaMemcpyDeviceToDevice, h->stream));
+        k_egrid_sweep<<<g, b, 0, h->stream>>>(a, sc, a, nx, ny, sy, h1, 1, 0.50f, 0.25f, 0, m1);
+        k_egrid_sweep<<<g, b, 0, h->stream>>>(sc, a, a, nx, ny, sy, h1, 1, 0.50f, 0.25f, 1, m1);
+        h->launches += 2;
+        if (opt == WPSGPU_SMTHDESMTH) {
+            k_egrid_sweep<<<g, b, 0, h->stream>>>(a, sc, a, nx, ny, sy, h1, 2, 1.52f, -0.26f, 0, m1);
+            k_egrid_sweep<<<g, b, 0, h->stream>>>(sc, a, a, nx, ny, sy, h1, 2, 1.52f, -0.26f, 1, m1);
+            h->launches += 2;
+        }
+    }
+    WPS_TRY(copy_out(h, array, a, bytes));
+    return end_call(h);
+}
+
+int wpsgpu_rotate_winds_nmm(wpsgpu_handle_t h, int idir, const wpsgpu_proj* proj, float* u, const int32_t* u_mask, float* v,
+                            const int32_t* v_mask, int vs1, int vs2, int ve1, int ve2, const float* xlat_v, const float* xlon_v, int nlev)
+{
+    WPS_CHECK(h && proj && u && v && u_mask && v_mask && xlat_v && xlon_v, -1, "wpsgpu_rotate_winds_nmm: NULL argument");
+    WPS_CHECK(proj->init, -1, "In metmap_xform_nmm(), uninitialized proj_info structure.");
+    WPS_CHECK(idir == 1 || idir == -1, -1, "wpsgpu_rotate_winds_nmm: idir must be +1 or -1");
+    if (!(proj->code == WPSGPU_PROJ_ROTLL || proj->code == WPSGPU_PROJ_LC || proj->code == WPSGPU_PROJ_PS || proj->code == WPSGPU_PROJ_CASSINI)) return 0;
+    const int nx = ve1 - vs1 + 1, ny = ve2 - vs2 + 1, nxw = (nx + 31) / 32;
+    WPS_CHECK(nx > 0 && ny > 0 && nlev > 0, -1, "wpsgpu_rotate_winds_nmm: bad dimensions");
+    const size_t pb = sizeof(float) * (size_t)nx * ny, mb = sizeof(int) * (size_t)ny * nxw;
+    WPS_TRY(begin_call(h, 2 * (pb + mb) * nlev + 2 * pb + 8192));
+    void *du, *dv, *dum, *dvm, *dla, *dlo;
+    WPS_TRY(stage_inout(h, u, pb * nlev, &du));
+    WPS_TRY(stage_inout(h, v, pb * nlev, &dv));
+    WPS_TRY(stage_in(h, u_mask, mb * nlev, &dum));
+    WPS_TRY(stage_in(h, v_mask, mb * nlev, &dvm));
+    WPS_TRY(stage_in(h, xlat_v, pb, &dla));
+    WPS_TRY(stage_in(h, xlon_v, pb, &dlo));
+    // every point reads and writes only its own U and V: in place
+    k_rotate_nmm<<<dim3((nx + 31) / 32, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(proj->code, proj->lat1, proj->lon1, proj->stdlon, proj->cone, proj->hemi, idir,
+                                                                                  (const float*)dla, (const float*)dlo, nx, ny, nlev, (float*)du,
+                                                                                  (const int*)dum, (float*)dv, (const int*)dvm);
+    h->launches++;
+    WPS_TRY(copy_out(h, u, du, pb * nlev));
+    WPS_TRY(copy_out(h, v, dv, pb * nlev));
     return end_call(h);
 }
 
