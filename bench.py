@@ -867,7 +867,11 @@ def run_b200(args, rank, world, local_rank):
                              "kernel": K16 if p3[1] >= p3[2] else "k_metgrid_interp", "kernel_ms": kms_avg,
                              "alg_bytes_per_point": ALG_BYTES_PER_POINT, "kernel_points": kp,
                              "breakdown_ms": {("k_pack_win" if PRECISION == 1 else "k_pack16"): t3[0], K16: t3[1], "k_metgrid_fast4": t3[3], "k_metgrid_interp(generic)": t3[2], "k_metgrid_slowlist": t3[4], "k_metgrid_search(+literal)": t3[5], "flush_first_to_last_kernel": t3[6]},
-                             "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+                             "breakdown_points": {"fast16": p3[1], "fast4": p3[3], "generic": p3[2]}, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                             # sixteen_pt sits at the machine's balance point: the FP32 view of the same kernel time
+                             "fp32": None if PRECISION != 1 else {"fma_per_point": 30, "achieved_fma_per_s": 30.0 * kp / (kms_avg * 1e-3), "peak_fma_per_s": 148 * 128 * 1.965e9,
+                                                                  "frac": 30.0 * kp / (kms_avg * 1e-3) / (148 * 128 * 1.965e9),
+                                                                  "peak_source": "148 SMs x 128 FP32 lanes x 1.965 GHz (nominal)"}},
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s * 1e3, "host_input_bytes_per_step": host_input_bytes,
                         "raw_record_ms_per_step": None if e2e_raw_s is None else e2e_raw_s * 1e3},

@@ -299,3 +299,42 @@ def test_process_mpas_fields_host_mirror(orc):
     assert mpas.process_mpas_field(h, entries, "rainnc", ("nCells",), sk) == []
     assert mpas.process_mpas_field(h, entries, "theta", ("nVertLevels", "nSomethingElse"), th) == []
     h.close()
+
+
+def test_full_size_properties(orc):
+    """BASELINE-size target (the 3-km CONUS mass grid of config 2, 1.9 M points) on a 40962-cell mesh, checked through properties
+    that do not need the oracle at that size: every table entry is a valid node, the nearest cell is the brute-force nearest on a
+    sample, weights of the cell table sum to 1, the masked table only names land cells, scaling a field by a power of two scales
+    the remap exactly, a constant field comes back as the weight sum, and the fused planes equal the level-fastest remap."""
+    from wps_b200 import capi
+    mesh = synth.mpas_mesh(40962, seed=6)
+    nx, ny, dx, tl1, tl2, slon, rlat, rlon = synth.CONFIGS["config2"]["dom"]
+    h = capi.Handle(0)
+    dom = synth.lambert_domain(nx, ny, dx, tl1, tl2, slon, rlat, rlon)
+    xlat, xlon = h.xytoll_grid(dom, capi.M, 1, 1, nx, ny)
+    d2r = np.float32(np.arcsin(np.float32(1.0)) / np.float32(90.0))
+    lat, lon = np.ascontiguousarray(xlat * d2r), np.ascontiguousarray(xlon * d2r)
+    h.mpas_set_mesh(mesh)
+    h.mpas_remap_setup(0, lat, lon)
+    near, src, w = h.mpas_get_tables(0, capi.MPAS_CELLS)
+    assert src.min() >= 1 and src.max() <= mesh["nCells"] and near.min() >= 1 and near.max() <= mesh["nCells"]
+    assert np.abs(w.sum(-1) - 1.0).max() < 1e-4
+    rng = np.random.default_rng(0)
+    pick = rng.integers(0, nx * ny, 1500)
+    la, lo = lat.ravel()[pick].astype(np.float64)[:, None], lon.ravel()[pick].astype(np.float64)[:, None]
+    lc, oc = mesh["latCell"].astype(np.float64)[None, :], mesh["lonCell"].astype(np.float64)[None, :]
+    d = np.sin(0.5 * (lc - la)) ** 2 + np.cos(la) * np.cos(lc) * np.sin(0.5 * (oc - lo)) ** 2
+    assert (d.argmin(1) + 1 == near.ravel()[pick]).mean() > 0.998           # binary32 ties aside
+    _, srcm, wm = h.mpas_get_tables(0, capi.MPAS_MASKED_CELLS)
+    used = wm != 0.0
+    assert (mesh["landmask"][srcm[used] - 1] == 1).all() and np.abs(wm.sum(-1) - 1.0).max() < 1e-4
+    f = synth.mpas_field(mesh, 8, seed=2)
+    out = h.mpas_remap_field(0, capi.MPAS_CELLS, f)
+    assert np.array_equal(h.mpas_remap_field(0, capi.MPAS_CELLS, f * np.float32(4.0)), out * np.float32(4.0))
+    const = np.full((mesh["nCells"], 1), 3.0, np.float32)
+    oc3 = h.mpas_remap_field(0, capi.MPAS_CELLS, const, nw=3)[..., 0]
+    assert np.array_equal(oc3, ((np.float32(0.0) + w[..., 0] * np.float32(3.0)) + w[..., 1] * np.float32(3.0)) + w[..., 2] * np.float32(3.0))
+    planes = [np.empty((ny, nx), np.float32) for _ in range(8)]
+    h.mpas_remap_planes(0, capi.MPAS_CELLS, f, planes)
+    assert np.array_equal(np.stack(planes), np.moveaxis(out, 2, 0))
+    h.close()
