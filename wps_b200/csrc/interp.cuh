@@ -28,6 +28,11 @@ __device__ __forceinline__ bool masked_out(const Src& s, int i, int j)
     float m = m_at(s, i, j);
     return s.rel == REL_GT ? (m > s.maskval) : (s.rel == REL_LT ? (m < s.maskval) : (m == s.maskval));
 }
+// the same test on a mask value that has been loaded already (several loads in flight instead of one after the other)
+__device__ __forceinline__ bool masked_val(const Src& s, float m)
+{
+    return s.rel == REL_GT ? (m > s.maskval) : (s.rel == REL_LT ? (m < s.maskval) : (m == s.maskval));
+}
 // source point valid in search_extrap / sixteen_pt's node branch: '>': mask<=val, '<': mask>=val,
 // ' ': mask/=val (interp_module.F:505-517,1302-1311)
 __device__ __forceinline__ bool mask_valid(const Src& s, int i, int j)
@@ -55,8 +60,11 @@ __device__ __forceinline__ int op_four_pt(const Src& s, float xx, float yy, floa
     if (min_y < s.sy || max_y > s.ey) return ST_NEXT;
     float a00 = s_at(s, min_x, min_y), a10 = s_at(s, max_x, min_y), a01 = s_at(s, min_x, max_y), a11 = s_at(s, max_x, max_y);
     if (a00 == s.msg || a10 == s.msg || a01 == s.msg || a11 == s.msg) return ST_NEXT;
-    if (s.m && (masked_out(s, min_x, min_y) || masked_out(s, max_x, min_y) || masked_out(s, min_x, max_y) || masked_out(s, max_x, max_y)))
-        return ST_NEXT;
+    if (s.m) {
+        // the four mask values together: the short-circuit chain of the source would wait for one load after the other
+        const float m00 = m_at(s, min_x, min_y), m10 = m_at(s, max_x, min_y), m01 = m_at(s, min_x, max_y), m11 = m_at(s, max_x, max_y);
+        if (masked_val(s, m00) || masked_val(s, m10) || masked_val(s, m01) || masked_val(s, m11)) return ST_NEXT;
+    }
     if (min_x == max_x) {
         if (min_y == max_y) r = a00;
         else r = a00 * ((float)max_y - yy) + a01 * (yy - (float)min_y);
@@ -90,10 +98,15 @@ __device__ __forceinline__ int op_avg4(const Src& s, float xx, float yy, float& 
         if (ifx < s.sx || icx > s.ex || ify < s.sy || icy > s.ey) return ST_FINAL_MSG;
     }
     float a_ff = s_at(s, ifx, ify), a_fc = s_at(s, ifx, icy), a_cf = s_at(s, icx, ify), a_cc = s_at(s, icx, icy);
-    if (a_ff == s.msg || masked_out(s, ifx, ify)) fxfy = 0.0f;
-    if (a_fc == s.msg || masked_out(s, ifx, icy)) fxcy = 0.0f;
-    if (a_cf == s.msg || masked_out(s, icx, ify)) cxfy = 0.0f;
-    if (a_cc == s.msg || masked_out(s, icx, icy)) cxcy = 0.0f;
+    bool m_ff = false, m_fc = false, m_cf = false, m_cc = false;
+    if (s.m) {
+        const float v_ff = m_at(s, ifx, ify), v_fc = m_at(s, ifx, icy), v_cf = m_at(s, icx, ify), v_cc = m_at(s, icx, icy);
+        m_ff = masked_val(s, v_ff); m_fc = masked_val(s, v_fc); m_cf = masked_val(s, v_cf); m_cc = masked_val(s, v_cc);
+    }
+    if (a_ff == s.msg || m_ff) fxfy = 0.0f;
+    if (a_fc == s.msg || m_fc) fxcy = 0.0f;
+    if (a_cf == s.msg || m_cf) cxfy = 0.0f;
+    if (a_cc == s.msg || m_cc) cxcy = 0.0f;
     if (fxfy == 0.0f && fxcy == 0.0f && cxfy == 0.0f && cxcy == 0.0f) return ST_NEXT;
     r = (fxfy * a_ff + fxcy * a_fc + cxfy * a_cf + cxcy * a_cc) / (fxfy + fxcy + cxfy + cxcy);
     return ST_VAL;
