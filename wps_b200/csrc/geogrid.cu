@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, in
         if (dest.x == GEO_OUTSIDE) continue;
         const int ii = dest.x - g.start_i, jj = dest.y - g.start_j;
         if (bit_test(g.processed, g.nxw, ii, jj)) continue;
-        cell[r] = jj * g.nx + ii;
+        cell[r] = (jj << 16) | ii;      // row and column of the destination cell (both < 65536)
         jmn = min(jmn, jj); jmx = max(jmx, jj); imn = min(imn, ii); imx = max(imx, ii);
         const float v = t.tile[(size_t)(pj - t.smy) * tnx + (pi - t.smx)];
         const int cv = (int)v;
@@ -285,18 +285,21 @@ __global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, in
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             if (cell[r] < 0) continue;
-            const int jj = cell[r] / g.nx, ii = cell[r] - jj * g.nx;
+            const int jj = cell[r] >> 16, ii = cell[r] & 0xffff;
             const int lc = (jj - bj0) * bw + (ii - bi0);
             atomicAdd(&s_hist[g.nk * ncell + lc], 1);
             if (cat[r] >= 0) atomicAdd(&s_hist[cat[r] * ncell + lc], 1);
             else if (cat[r] == -2) atomicAdd(g.invalid, 1ull);
         }
         __syncthreads();
+        // counter index -> (plane, row, column) by multiplication with rounded-up reciprocals: exact for e < 4096 (GEO_HCAP)
+        const unsigned rc_n = 0xffffffffu / (unsigned)ncell + 1u, rc_w = 0xffffffffu / (unsigned)bw + 1u;
         for (int e = tid; e < ncell * nplane; e += 256) {
             const int v = s_hist[e];
             if (v == 0) continue;
-            const int k = e / ncell, lc = e - k * ncell;
-            const int jj = bj0 + lc / bw, ii = bi0 + lc % bw;
+            const int k = ncell == 1 ? e : (int)__umulhi((unsigned)e, rc_n), lc = e - k * ncell;       // (the reciprocal of 1 does not fit)
+            const int lr = bw == 1 ? lc : (int)__umulhi((unsigned)lc, rc_w);
+            const int jj = bj0 + lr, ii = bi0 + (lc - lr * bw);
             const size_t gc = (size_t)jj * g.nx + ii;
             if (k == g.nk) g.touched[gc] = 1;
             else {
@@ -308,10 +311,11 @@ __global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, in
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             if (cell[r] < 0) continue;
-            g.touched[cell[r]] = 1;
+            const int gcell = (cell[r] >> 16) * g.nx + (cell[r] & 0xffff);
+            g.touched[gcell] = 1;
             if (cat[r] >= 0) {
-                atomicAdd(g.acc_cnt + (size_t)cat[r] * g.npts + cell[r], 1);
-                if (__ldcg(first_tile + cell[r]) > order) atomicMin(first_tile + cell[r], order);
+                atomicAdd(g.acc_cnt + (size_t)cat[r] * g.npts + gcell, 1);
+                if (__ldcg(first_tile + gcell) > order) atomicMin(first_tile + gcell, order);
             } else if (cat[r] == -2) atomicAdd(g.invalid, 1ull);
         }
     }
@@ -1181,6 +1185,7 @@ static bool geo_batchable(const GeoState* s)
 {
     static const bool enabled = !(getenv("WPSGPU_GEO_BATCH") && atoi(getenv("WPSGPU_GEO_BATCH")) == 0);
     if (!enabled) return false;
+    if (s->nx > 65535 || s->ny > 32767) return false;      // k_geo_accum_cat_b packs a cell's (row, column) into one int
     if (s->l.itype == WPSGPU_SP_CONTINUOUS) return true;
     return s->l.itype == WPSGPU_CATEGORICAL && s->l.ilevel == 1;
 }
