@@ -440,6 +440,13 @@ module wpsgpu_mod
          real(c_float), value :: fill_missing
          type(c_ptr) :: planes(*)                             ! c_loc(field_to_store % r_arr) of every level
       end function
+      integer(c_int) function wpsgpu_mpas_derive_tt(handle, theta, pressure, nlev, npts) bind(C, name='wpsgpu_mpas_derive_tt')
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: handle
+         type(c_ptr) :: theta(*), pressure(*)                ! c_loc(theta_field % r_arr), c_loc(pressure_field % r_arr) per level
+         integer(c_int), value :: nlev
+         integer(c_int64_t), value :: npts
+      end function
    end interface
 
 contains

@@ -369,6 +369,9 @@ int wpsgpu_mpas_remap_field(wpsgpu_handle_t h, int grid_id, int decomp, int xtyp
  * nlev pointers that follow the pointer mode. */
 int wpsgpu_mpas_remap_planes(wpsgpu_handle_t h, int grid_id, int decomp, int masked, const float *src, int nlev, int mode,
                              const float *landmask, float fill_missing, float *const *planes);
+/* derive_mpas_fields (process_domain_module.F:1957-2053): TT = theta * (pressure / P0) ** (RD / CP) in place on the stored
+ * planes of every level; theta / pressure: HOST arrays of nlev pointers that follow the pointer mode, npts values each. */
+int wpsgpu_mpas_derive_tt(wpsgpu_handle_t h, float *const *theta, const float *const *pressure, int nlev, int64_t npts);
 
 #ifdef __cplusplus
 }

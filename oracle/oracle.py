@@ -552,3 +552,10 @@ def smooth_egrid(array, npass, opt, msgval=1.0e20, hflag=1.0, sx=1, sy=1):
     nz, ny, nx = a.shape
     lib().orc_smooth_egrid(fptr(a), int(sx), int(sx + nx - 1), int(sy), int(sy + ny - 1), 1, nz, int(npass), int(opt), C.c_float(msgval), C.c_float(hflag))
     return a
+
+
+def mpas_derive_tt(theta, pressure):
+    """derive_mpas_fields (process_domain_module.F:1957-2053) on one level; returns TT."""
+    t = np.ascontiguousarray(theta).copy()
+    lib().orc_mpas_derive_tt(fptr(t), fptr(np.ascontiguousarray(pressure)), C.c_long(t.size))
+    return t

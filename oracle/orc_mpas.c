@@ -314,3 +314,14 @@ void orc_mpas_extract_planes(const float *wrf, int nlev, long npts, int mode, co
             planes[(size_t)k * npts + p] = v;
         }
 }
+
+/* derive_mpas_fields (process_domain_module.F:1957-2053), per level: exner = (pressure / P0) ** (RD / CP); theta = theta * exner
+ * (the stored field TT holds potential temperature until this step); constants_module.F:28-30 */
+void orc_mpas_derive_tt(float *theta, const float *pressure, long n)
+{
+    const float P0 = 1.0e5f, RD = 287.0f, CP = 1004.0f;
+    for (long k = 0; k < n; ++k) {
+        float exner = o_pow(pressure[k] / P0, RD / CP);
+        theta[k] = theta[k] * exner;
+    }
+}

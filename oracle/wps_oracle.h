@@ -256,6 +256,7 @@ void orc_mpas_remap_field_real(const int *sourceNodes, const float *nodeWeights,
 void orc_mpas_remap_field_double(const int *sourceNodes, const float *nodeWeights, int tw, int nw, long npts, const double *src,
                                  int nlev, double *dst);
 void orc_mpas_remap_field_int(const int *nearest, long npts, const int *src, int nlev, int *dst);
+void orc_mpas_derive_tt(float *theta, const float *pressure, long n);
 void orc_mpas_extract_planes(const float *wrf, int nlev, long npts, int mode, const float *landmask, float fill, float *planes);
 
 #endif

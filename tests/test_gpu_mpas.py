@@ -2,6 +2,7 @@
 import numpy as np
 import pytest
 
+from tests.util import ulp_diff
 from wps_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -221,6 +222,8 @@ TABLE = """
 ========================================
 name=TT ; mpas_name=theta ; output_stagger=M
 ========================================
+name=PRESSURE ; mpas_name=pressure
+========================================
 name=UU ; mpas_name=uReconstructZonal ; output_stagger=U ; is_u_field=yes
 ========================================
 name=GHT ; mpas_name=zgrid
@@ -268,6 +271,17 @@ def test_process_mpas_fields_host_mirror(orc):
     r = mpas.process_mpas_field(h, entries, "theta", ("nVertLevels", "nCells"), th, landmask=lm)
     assert [(d["field"], d["level"], d["vertical_coord"]) for d in r] == [("TT", k, "num_mpas_levels") for k in range(1, 7)]
     assert same(np.stack([d["r_arr"] for d in r]), ref_planes(0, th))
+    # derive_mpas_fields (:1957-2053): with PRESSURE on the same levels, TT = theta * (p / 1e5) ** (287 / 1004), in place
+    pr = (np.float32(1.0e5) * np.exp(-np.arange(6, dtype=np.float32) / 5.0)[None, :] * (1.0 + 0.01 * synth.mpas_field(mesh, 6, seed=7) / 300.0)).astype(np.float32)
+    rp = mpas.process_mpas_field(h, entries, "pressure", ("nVertLevels", "nCells"), pr)
+    theta_planes = np.stack([d["r_arr"] for d in r]).copy()
+    mpas.derive_mpas_fields(h, r + rp)
+    for k in range(6):
+        want = orc.mpas_derive_tt(theta_planes[k], rp[k]["r_arr"])
+        assert ulp_diff(r[k]["r_arr"], want).max() <= 1, k
+        ex = (rp[k]["r_arr"].astype(np.float64) / 1.0e5) ** (287.0 / 1004.0)
+        assert np.abs(r[k]["r_arr"] / (theta_planes[k].astype(np.float64) * ex) - 1.0).max() < 1e-6, k
+    mpas.derive_mpas_fields(h, r)                      # no PRESSURE levels: nothing happens (:1998)
     # t2m is renamed to theta (:1634): a 1-d field stored at 200100
     t2 = np.ascontiguousarray(th[:, 0])
     r = mpas.process_mpas_field(h, entries, "t2m", ("nCells",), t2)

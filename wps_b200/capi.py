@@ -565,6 +565,15 @@ class Handle:
         check(lib().wpsgpu_mpas_remap_planes(self._h, int(grid_id), int(decomp), int(bool(masked)), C.c_void_p(ptr(src)), nlev, int(mode),
                                              C.c_void_p(ptr(landmask)), C.c_float(fill_missing), pp))
 
+    def mpas_derive_tt(self, theta_planes, pressure_planes):
+        """derive_mpas_fields (process_domain_module.F:1957-2053): theta planes become TT, in place."""
+        n = len(theta_planes)
+        assert n == len(pressure_planes)
+        npts = int(np.prod(theta_planes[0].shape)) if n else 1
+        pt = (C.c_void_p * max(n, 1))(*[ptr(a) for a in theta_planes])
+        pp = (C.c_void_p * max(n, 1))(*[ptr(a) for a in pressure_planes])
+        check(lib().wpsgpu_mpas_derive_tt(self._h, pt, pp, n, C.c_int64(npts)))
+
 
 def _like(a):
     if isinstance(a, np.ndarray):

@@ -433,6 +433,17 @@ __global__ void __launch_bounds__(256) k_mpas_remap_planes(const float* __restri
     }
 }
 
+// derive_mpas_fields (process_domain_module.F:1957-2053): TT = theta * (pressure / P0) ** (RD / CP) on the stored planes
+struct MpasDerive { float* theta[MPAS_MAX_PLANES]; const float* pressure[MPAS_MAX_PLANES]; };
+__global__ void __launch_bounds__(256) k_mpas_derive_tt(const __grid_constant__ MpasDerive a, size_t npts)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const float P0 = 1.0e5f, RD = 287.0f, CP = 1004.0f;       // constants_module.F:28-30
+    const float exner = t_pow(a.pressure[blockIdx.y][p] / P0, RD / CP);
+    a.theta[blockIdx.y][p] = a.theta[blockIdx.y][p] * exner;
+}
+
 static int begin_call(wpsgpu_ctx* h, size_t host_bytes)
 {
     WPS_CHECK(h != nullptr, -1, "NULL handle");
@@ -696,6 +707,33 @@ int wpsgpu_mpas_remap_planes(wpsgpu_handle_t h, int grid_id, int decomp, int mas
         h->launches++;
     }
     for (int k = 0; k < nlev; ++k) WPS_TRY(copy_out(h, planes[k], dpl[k], sizeof(float) * npts));
+    return end_call(h);
+}
+
+int wpsgpu_mpas_derive_tt(wpsgpu_handle_t h, float* const* theta, const float* const* pressure, int nlev, int64_t npts)
+{
+    WPS_CHECK(h && theta && pressure && nlev >= 0 && npts > 0, -1, "wpsgpu_mpas_derive_tt: bad arguments");
+    if (nlev == 0) return 0;
+    const size_t bytes = sizeof(float) * (size_t)npts;
+    WPS_TRY(begin_call(h, 2 * (bytes + 256) * (size_t)nlev + 8192));
+    std::vector<float*> dt(nlev);
+    std::vector<const float*> dp(nlev);
+    for (int k = 0; k < nlev; ++k) {
+        WPS_CHECK(theta[k] && pressure[k], -1, "wpsgpu_mpas_derive_tt: NULL level array");
+        void *a, *b;
+        WPS_TRY(stage_in(h, theta[k], bytes, &a));
+        WPS_TRY(stage_in(h, pressure[k], bytes, &b));
+        dt[k] = (float*)a; dp[k] = (const float*)b;
+    }
+    for (int k0 = 0; k0 < nlev; k0 += MPAS_MAX_PLANES) {
+        const int n = std::min(nlev - k0, MPAS_MAX_PLANES);
+        MpasDerive a;
+        memset(&a, 0, sizeof(a));
+        for (int k = 0; k < n; ++k) { a.theta[k] = dt[k0 + k]; a.pressure[k] = dp[k0 + k]; }
+        k_mpas_derive_tt<<<dim3((unsigned)((npts + 255) / 256), n), 256, 0, h->stream>>>(a, (size_t)npts);
+        h->launches++;
+    }
+    for (int k = 0; k < nlev; ++k) WPS_TRY(copy_out(h, theta[k], dt[k], bytes));
     return end_call(h);
 }
 

@@ -3,8 +3,7 @@ which table drives a field, which target grid it goes to, and which (field, leve
 and the per-level extraction run on the device (wpsgpu_mpas_remap_planes); file access (scan_input.F, netCDF) stays with the
 caller, which hands over one field at a time as scan_input_next_field / scan_input_read_field would.
 
-derive_mpas_fields (:1968-2053, TT = theta * (p / p0) ** (Rd / cp) on the stored planes) is an elementwise step of the
-caller's storage module and is not restated here."""
+derive_mpas_fields (:1957-2053, TT = theta * (p / p0) ** (Rd / cp) on the stored planes) is `derive_mpas_fields` below."""
 from typing import List, Sequence
 
 import numpy as np
@@ -97,3 +96,13 @@ def process_mpas_field(h: "capi.Handle", entries, name: str, dimnames: Sequence[
                             fill_missing=ent.fill_missing)
         put(interm, 200100.0, "none", planes[0])
     return out
+
+
+def derive_mpas_fields(h: "capi.Handle", stored: List[dict]) -> None:
+    """process_domain_module.F:1957-2053 on the planes `process_mpas_field` returned: where TT and PRESSURE both exist with the
+    same number of levels, TT (potential temperature so far) is multiplied by the Exner function, level by level, in place."""
+    tt = sorted((d for d in stored if d["field"] == "TT" and d["vertical_coord"] == "num_mpas_levels"), key=lambda d: d["level"])
+    pr = sorted((d for d in stored if d["field"] == "PRESSURE" and d["vertical_coord"] == "num_mpas_levels"), key=lambda d: d["level"])
+    if not tt or len(tt) != len(pr):
+        return
+    h.mpas_derive_tt([d["r_arr"] for d in tt], [d["r_arr"] for d in pr])
