@@ -352,3 +352,34 @@ def test_full_size_properties(orc):
     h.mpas_remap_planes(0, capi.MPAS_CELLS, f, planes)
     assert np.array_equal(np.stack(planes), np.moveaxis(out, 2, 0))
     h.close()
+
+
+def test_tiny_meshes_and_degenerate_shapes(orc):
+    """The smallest meshes scipy can tessellate (12, 20, 42 cells: every walk crosses most of the sphere), a single target point, a
+    single row and a single column of targets, one level with the interface rule (plane 0 only), an empty level list."""
+    from wps_b200 import capi
+    orc.set_transc_mode(1)
+    h = capi.Handle(0)
+    for ncells in (12, 20, 42):
+        mesh = synth.mpas_mesh(ncells, seed=9)
+        h.mpas_set_mesh(mesh)
+        for shape in ((1, 1), (1, 37), (29, 1)):
+            rng = np.random.default_rng(ncells + shape[0])
+            lat = np.ascontiguousarray(rng.uniform(-1.5, 1.5, shape).astype(np.float32))
+            lon = np.ascontiguousarray(rng.uniform(-3.1, 3.1, shape).astype(np.float32))
+            t = orc.mpas_remap_setup(mesh, lat, lon)
+            h.mpas_remap_setup(0, lat, lon)
+            for kind, (kn, ks, kw) in KEYS.items():
+                near, src, w = h.mpas_get_tables(0, kind)
+                if kn:
+                    assert np.array_equal(near, t[kn]), (ncells, shape, kn)
+                assert np.array_equal(src, t[ks]), (ncells, shape, ks)
+                assert np.array_equal(np.isfinite(w), np.isfinite(t[kw])), (ncells, shape, kw)
+            _, srcc, wc = h.mpas_get_tables(0, capi.MPAS_CELLS)
+            f = synth.mpas_field(mesh, 1, seed=3)
+            plane = [np.empty(shape, np.float32)]
+            h.mpas_remap_planes(0, capi.MPAS_CELLS, f[:, 0].copy(), plane, mode=1)
+            ref = orc.mpas_extract_planes(orc.mpas_remap_field(srcc, wc, f, nw=3), 1)
+            assert np.array_equal(plane[0].view(np.int32), ref[0].view(np.int32)), (ncells, shape)
+    h.mpas_derive_tt([], [])
+    h.close()
