@@ -200,35 +200,15 @@ __global__ void k_mpas_chain(MpasMeshDev m, const float* __restrict__ lat, const
     out[p] = r;
     if (r != in[p]) *changed = 1;
 }
-// The masked table's scan (:251-283) is a recurrence of its own: after a point that goes to search_for_cells, idx holds the
-// CELL index nearest_cell returned (:272) and is the next point's start VERTEX, as written.  next[p] = idx after point p.
-__device__ __forceinline__ bool masked_needs_search(const MpasMeshDev& m, const int sc[3], float tlat, float tlon, float w3[3]);
-__global__ void k_mpas_chain_masked(MpasMeshDev m, const float* __restrict__ lat, const float* __restrict__ lon, size_t npts,
-                                    const int* __restrict__ next_in, int* __restrict__ next_out, int* __restrict__ vert_out, int* __restrict__ changed)
-{
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npts) return;
-    const float tlat = lat[p], tlon = lon[p];
-    const int v = nearest_node<3>(m, tlat, tlon, p ? next_in[p - 1] : 1);
-    int sc[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) sc[j] = m.cellsOnVertex[(size_t)(v - 1) * 3 + j];
-    float w3[3];
-    const int next = masked_needs_search(m, sc, tlat, tlon, w3) ? nearest_cell(m, tlat, tlon, sc[0]) : v;
-    vert_out[p] = v;
-    next_out[p] = next;
-    if (next != next_in[p]) *changed = 1;
-}
-
-// ---- weight tables (remapper.F:158-283) ------------------------------------------------------------------------------------
-// :264-270: Wachspress weights of the three cells, water cells zeroed; true when no positive land weight is left (w3 then holds
-// the zeroed weights, otherwise the weights before normalisation with sumWeights in w3's place is not needed by the caller)
+// The masked cell weights of a point (:264-270): Wachspress weights of the three cells of its vertex, water cells zeroed, the
+// rest divided by their sum.  Returns false -- and leaves w3 unspecified -- when no positive land weight remains: the point then
+// goes to search_for_cells (:271-281).
 __device__ __forceinline__ bool masked_weights(const MpasMeshDev& m, const int sc[3], float tlat, float tlon, float w3[3])
 {
     int nland = 0;
 #pragma unroll
     for (int j = 0; j < 3; ++j) nland += m.landmask[sc[j] - 1] == 1;
-    if (nland == 0) { w3[0] = w3[1] = w3[2] = 0.0f; return true; }     // sumWeights = 0 whatever the weights are
+    if (nland == 0) return false;                   // sumWeights = 0 whatever the weights are
     float pt[3], vc[3][3];
     convert_lx(tlat, tlon, 6371229.0f, pt);
 #pragma unroll
@@ -240,16 +220,32 @@ __device__ __forceinline__ bool masked_weights(const MpasMeshDev& m, const int s
         if (m.landmask[sc[j] - 1] == 1) sumWeights = sumWeights + w3[j];
         else w3[j] = 0.0f;
     }
-    if (!(sumWeights > 0.0f)) return true;
+    if (!(sumWeights > 0.0f)) return false;
 #pragma unroll
     for (int j = 0; j < 3; ++j) w3[j] = w3[j] / sumWeights;
-    return false;
-}
-__device__ __forceinline__ bool masked_needs_search(const MpasMeshDev& m, const int sc[3], float tlat, float tlon, float w3[3])
-{
-    return masked_weights(m, sc, tlat, tlon, w3);
+    return true;
 }
 
+// The masked table's scan (:251-283) is a recurrence of its own: after a point that goes to search_for_cells, idx holds the
+// CELL index nearest_cell returned (:272) and is the next point's start VERTEX, as written.  next[p] = idx after point p.
+__global__ void k_mpas_chain_masked(MpasMeshDev m, const float* __restrict__ lat, const float* __restrict__ lon, size_t npts,
+                                    const int* __restrict__ next_in, int* __restrict__ next_out, int* __restrict__ vert_out, int* __restrict__ changed)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npts) return;
+    const float tlat = lat[p], tlon = lon[p];
+    const int v = nearest_node<3>(m, tlat, tlon, p ? next_in[p - 1] : 1);
+    int sc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sc[j] = m.cellsOnVertex[(size_t)(v - 1) * 3 + j];
+    float w3[3];
+    const int next = masked_weights(m, sc, tlat, tlon, w3) ? v : nearest_cell(m, tlat, tlon, sc[0]);
+    vert_out[p] = v;
+    next_out[p] = next;
+    if (next != next_in[p]) *changed = 1;
+}
+
+// ---- weight tables (remapper.F:158-283) ------------------------------------------------------------------------------------
 __global__ void k_mpas_weights(MpasMeshDev m, const float* __restrict__ lat, const float* __restrict__ lon, size_t npts,
                                const int* __restrict__ ncell, const int* __restrict__ nvert, const int* __restrict__ nvertM,
                                int* __restrict__ srcC, float* __restrict__ wC, int* __restrict__ srcV, float* __restrict__ wV,
@@ -280,7 +276,7 @@ __global__ void k_mpas_weights(MpasMeshDev m, const float* __restrict__ lat, con
         int sc[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) sc[j] = m.cellsOnVertex[(size_t)(v - 1) * 3 + j];
-        if (!masked_weights(m, sc, tlat, tlon, w3)) {
+        if (masked_weights(m, sc, tlat, tlon, w3)) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) { srcM[p * 3 + j] = sc[j]; wM[p * 3 + j] = w3[j]; }
         } else {
