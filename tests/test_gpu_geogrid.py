@@ -329,3 +329,44 @@ def test_against_committed_geogrid_golden_vectors(handle):
     vm = np.full((v.shape[1], capi.nwords(v.shape[2])), -1, np.int32)
     handle.rotate_winds(1, dom, u, um, v, vm, g["xlon_u"], g["xlon_v"])
     assert ulp_diff(u[0], g["u_rot"]).max() <= 1 and ulp_diff(v[0], g["v_rot"]).max() <= 1, "golden wind rotation"
+
+
+@pytest.mark.parametrize("dxdeg,tn", [(0.01, 300), (0.3, 24)])
+def test_raw_categorical_tiles(orc, handle, dxdeg, tn):
+    """Categorical tiles handed over as file bytes: the batched accumulate kernel reads the bytes itself and the tile is only
+    decoded for the point pass (k_geo_decode_b behind a gate).  Every byte layout of read_geogrid.c, for a source finer than
+    the domain (no point-pass candidates: the gate stays shut) and a much coarser one (most points take the chain from the
+    lazily decoded tile): identical to the same tiles passed as decoded binary32 values, counts and invalid-category counter."""
+    from wps_b200 import capi
+    orc.set_transc_mode(1)
+    odom, gdom = conus_like(30, 30, 9000.0, 30.0, 60.0, -98.0, 39.0, -105.0)
+    xlat, xlon = orc.get_lat_lon_fields(odom, 1, 1, 30, 30, 1)
+    kw = dict(dlat=dxdeg, dlon=dxdeg, known_x=1.0, known_y=1.0, known_lat=37.5 - (3.0 if dxdeg > 0.1 else 0.0), known_lon=-107.0 - (3.0 if dxdeg > 0.1 else 0.0))
+    gsrc = capi.push_source_projection(capi.PROJ_LATLON, **kw)
+    rng = np.random.default_rng(5)
+    for wordsize, signed, endian, row_order in ((1, 0, 0, 1), (1, 1, 0, 2), (2, 1, 0, 1), (2, 0, 1, 2), (3, 1, 1, 1), (4, 1, 0, 2)):
+        vals = rng.integers(1, 22, (1, tn, tn)).astype(np.int64)
+        vals[0, ::7, ::5] = 30                                   # invalid categories (WARN counter, proc_point_module.F:348)
+        if signed:
+            vals[0, 1::9, 2::4] = -3
+        stored = vals[:, ::-1, :] if row_order == 2 else vals
+        us = np.where(stored < 0, stored + (1 << (8 * wordsize)), stored).astype(np.uint64)
+        order = range(wordsize) if endian == 1 else range(wordsize - 1, -1, -1)
+        raw = np.stack([((us >> (8 * b)) & 0xff).astype(np.uint8) for b in order], axis=-1).copy()
+        dec = vals.astype(np.float32)
+        res, ninv = [], []
+        for mode in ("raw", "float"):
+            field = np.zeros((21, 30, 30), np.float32)
+            handle.geogrid_field_begin(gdom, 1, xlat, xlon, 1, 1, 1, field, None)
+            handle.geogrid_level_begin(gsrc, 1, capi.CATEGORICAL, "nearest_neighbor", 1e20, 1e20, -1.0)
+            if mode == "raw":
+                handle.geogrid_add_tile_raw(raw, (1, tn, tn), wordsize, signed, endian, row_order, 1, 1, 1, 0)
+            else:
+                handle.geogrid_add_tile(dec, 1, 1, 1, 0)
+            handle.geogrid_level_end()
+            ninv.append(handle.geogrid_field_finish())
+            res.append(field)
+        what = "raw categorical wordsize=%d signed=%d endian=%d row_order=%d dx=%g" % (wordsize, signed, endian, row_order, dxdeg)
+        assert_bitexact(res[0], res[1], what)
+        assert ninv[0] == ninv[1], what
+        assert res[0].sum() > 0, what

@@ -149,7 +149,23 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 // Quadtree emulation: walk the block hierarchy of process_*_block top-down for this pixel and credit the
 // first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
 // Tile-specific part of the kernel arguments: a batch launch takes several of these (blockIdx.z picks one).
-struct GeoTile { const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; const int2* xb; const int2* yb; float* terms; };
+struct GeoTile {
+    const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; const int2* xb; const int2* yb; float* terms;
+    // categorical batches read the file's bytes directly (read_geogrid.c:91-128 + the row flip); `tile` is then decoded only if
+    // the batch's point pass has candidates (k_geo_decode_b with a gate)
+    const unsigned char* raw; int rws, rsigned, rlittle, rflip;
+};
+__device__ __forceinline__ float geo_raw_value(const GeoTile& t, int ix, int jy)
+{
+    const size_t e = (size_t)(t.rflip ? t.tny - 1 - jy : jy) * t.tnx + ix;
+    const unsigned char* b = t.raw + e * t.rws;
+    int ival;
+    if (t.rws == 1) { ival = b[0]; if (t.rsigned && ival > (1 << 7)) ival -= (1 << 8); }
+    else if (t.rws == 2) { ival = t.rlittle ? ((b[1] << 8) | b[0]) : ((b[0] << 8) | b[1]); if (t.rsigned && ival > (1 << 15)) ival -= (1 << 16); }
+    else if (t.rws == 3) { ival = t.rlittle ? ((b[2] << 16) | (b[1] << 8) | b[0]) : ((b[0] << 16) | (b[1] << 8) | b[2]); if (t.rsigned && ival > (1 << 23)) ival -= (1 << 24); }
+    else { const unsigned u = t.rlittle ? (((unsigned)b[3] << 24) | (b[2] << 16) | (b[1] << 8) | b[0]) : (((unsigned)b[0] << 24) | (b[1] << 16) | (b[2] << 8) | b[3]); ival = (int)u; }
+    return (float)ival;
+}
 
 // Shallowest level of the tile's block hierarchy (process_*_block, proc_point_module.F:218-458) that holds a block whose four
 // corners map to one destination cell, looked for among the levels 0 .. GEO_DCAP (21845 blocks at most).  With a source much
@@ -264,7 +280,7 @@ __global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, in
         if (bit_test(g.processed, g.nxw, ii, jj)) continue;
         cell[r] = (jj << 16) | ii;      // row and column of the destination cell (both < 65536)
         jmn = min(jmn, jj); jmx = max(jmx, jj); imn = min(imn, ii); imx = max(imx, ii);
-        const float v = t.tile[(size_t)(pj - t.smy) * tnx + (pi - t.smx)];
+        const float v = t.raw ? geo_raw_value(t, pi - t.smx, pj - t.smy) : t.tile[(size_t)(pj - t.smy) * tnx + (pi - t.smx)];
         const int cv = (int)v;
         if (v != g.msg_val) cat[r] = (cv >= g.start_k && cv <= g.end_k) ? cv - g.start_k : -2;
     }
@@ -424,6 +440,7 @@ __device__ __forceinline__ GeoTile tile_of(const GeoK& g)
     GeoTile t;
     t.tile = g.tile; t.wm = g.wm; t.smx = g.smx; t.sMx = g.sMx; t.smy = g.smy; t.sMy = g.sMy; t.smz = g.smz; t.sMz = g.sMz;
     t.bdr = g.bdr; t.tnx = g.tnx; t.tny = g.tny; t.dstart = nullptr; t.xb = nullptr; t.yb = nullptr; t.terms = nullptr;
+    t.raw = nullptr; t.rws = 0; t.rsigned = 0; t.rlittle = 0; t.rflip = 0;
     return t;
 }
 __global__ void __launch_bounds__(256) k_geo_accum(GeoK g) { geo_accum_body(g, tile_of(g), 0, nullptr); }
@@ -772,7 +789,7 @@ __device__ __forceinline__ void apply_tile(GeoK& g, const GeoTile& t)
 // Pre-work of a whole batch, one launch per step (blockIdx.z = tile): decode of the raw file bytes, where_maps_to, the first
 // level with a uniform block or a leaf, the level's block ranges.  A single tile of a geogrid data set (1200 x 1200 pixels)
 // does not fill the machine; eight of them do.
-struct GeoRaw { const unsigned char* bytes; float* out; int wordsize, is_signed, little, flip, tnx, tny, tnz; };
+struct GeoRaw { const unsigned char* bytes; float* out; int wordsize, is_signed, little, flip, tnx, tny, tnz; const unsigned long long* gate; };
 struct GeoRawBatch { GeoRaw r[GEO_NB]; };
 __device__ __forceinline__ void geo_decode_one(const unsigned char* __restrict__ c, int wordsize, int is_signed, int little, int flip,
                                                int tnx, int tny, size_t e, float* __restrict__ out);
@@ -780,6 +797,7 @@ __global__ void __launch_bounds__(256) k_geo_decode_b(GeoRawBatch rb)
 {
     const GeoRaw& r = rb.r[blockIdx.z];
     if (!r.bytes) return;
+    if (r.gate && *r.gate == 0ull) return;          // nobody is going to read the decoded tile
     const size_t n = (size_t)r.tnx * r.tny * r.tnz;
     if (r.wordsize == 1 && (r.tnx & 3) == 0 && (((size_t)r.bytes | (size_t)r.out) & 15) == 0) {
         // one-byte words (land use, soil categories): four pixels of a row per thread, uchar4 in, float4 out
@@ -1210,9 +1228,17 @@ static int geo_flush_batch(wpsgpu_ctx* h)
         gx = std::max(gx, (t.tnx - 2 * p.bdr + 31) / 32); gy = std::max(gy, (t.tny - 2 * p.bdr + 7) / 8);
         tmax = std::max(tmax, std::max(t.tnx, t.tny));
     }
+    // Categorical tiles that arrive as file bytes are not decoded up front: the accumulate kernel reads the bytes, and the decoded
+    // copy is only made (after the selection) for tiles whose point pass has candidates -- none where the source is finer than
+    // the domain.  One-level tiles only (a categorical tile has one level).
+    static const bool lazy_enabled = !(getenv("WPSGPU_GEO_LAZY_DECODE") && atoi(getenv("WPSGPU_GEO_LAZY_DECODE")) == 0);
+    const bool lazy = lazy_enabled && s->l.itype == WPSGPU_CATEGORICAL;
+    GeoRawBatch rb, rb_lazy;
+    bool any_lazy = false;
+    size_t lazy_maxpix = 1;
     {   // pre-work of the whole batch on the staging stream (behind the tiles' copies): decode, where_maps_to, level tables
-        GeoRawBatch rb;
         memset(&rb, 0, sizeof(rb));
+        memset(&rb_lazy, 0, sizeof(rb_lazy));
         bool any_raw = false;
         int wx = 1, wy = 1, bnd = 1;
         size_t maxpix = 1;
@@ -1220,12 +1246,17 @@ static int geo_flush_batch(wpsgpu_ctx* h)
             const GeoState::Pending& p = s->pending[z];
             const GeoTile& t = bt.t[z];
             if (p.raw) {
-                GeoRaw& r = rb.r[z];
+                GeoRaw& r = lazy ? rb_lazy.r[z] : rb.r[z];
                 r.bytes = p.raw; r.out = s->d_tile[p.set]; r.wordsize = p.wordsize; r.is_signed = p.is_signed; r.little = p.little; r.flip = p.flip;
                 r.tnx = t.tnx; r.tny = t.tny; r.tnz = p.sMz - p.smz + 1;
+                r.gate = lazy ? g.counters + 3 * z + 2 : nullptr;       // length of the tile's candidate list (k_geo_select_b)
                 maxpix = std::max(maxpix, (size_t)t.tnx * t.tny * r.tnz);
-                any_raw = true;
+                if (lazy) {
+                    any_lazy = true;
+                    bt.t[z].raw = p.raw; bt.t[z].rws = p.wordsize; bt.t[z].rsigned = p.is_signed; bt.t[z].rlittle = p.little; bt.t[z].rflip = p.flip;
+                } else any_raw = true;
             }
+            if (lazy && p.raw) lazy_maxpix = std::max(lazy_maxpix, (size_t)t.tnx * t.tny * (p.sMz - p.smz + 1));
             wx = std::max(wx, (t.tnx + WM_T - 1) / WM_T); wy = std::max(wy, (t.tny + WM_T - 1) / WM_T);
             bnd = std::max(bnd, std::max(0, t.tnx - 2 * t.bdr) + std::max(0, t.tny - 2 * t.bdr));
         }
@@ -1254,6 +1285,7 @@ static int geo_flush_batch(wpsgpu_ctx* h)
     else k_geo_accum_b<<<dim3(gx, gy, bt.n), dim3(32, 8), 0, h->stream>>>(g, bt, s->d_first_tile);
     const unsigned nblk = (unsigned)((s->npts + 255) / 256);
     k_geo_select_b<<<nblk, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_first_tile, s->d_cand, cnt);
+    if (any_lazy) { k_geo_decode_b<<<dim3((unsigned)std::min<size_t>((lazy_maxpix + 255) / 256, 4096), 1, bt.n), 256, 0, h->stream>>>(rb_lazy); h->launches++; }
     k_geo_points_b<<<h->sm_count * 2, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_cand, cnt, s->d_def);
     h->launches += 4;
     if (s->has_search) {
