@@ -9,6 +9,13 @@
 namespace wps {
 
 #define GEO_OUTSIDE 100000000  // OUTSIDE_DOMAIN, misc_definitions_module.F:18
+// where_maps_to of a source pixel: destination (x, y) as two 16-bit halves of one word (a field dimension beyond +-32767
+// is refused at field_begin), so that "four corners agree" is one comparison per pair and the array is half the size
+typedef int WmCell;
+constexpr WmCell WM_OUTSIDE = 0x00008000;          // x = -32768, y = 0
+__host__ __device__ __forceinline__ WmCell wm_pack(int x, int y) { return (WmCell)(((unsigned)y << 16) | ((unsigned)x & 0xffffu)); }
+__host__ __device__ __forceinline__ int wm_x(WmCell w) { return (int)(short)(w & 0xffff); }
+__host__ __device__ __forceinline__ int wm_y(WmCell w) { return w >> 16; }
 constexpr int GEO_SETS = 10;   // staging buffer sets: one batch (GEO_NB = 8 tiles) + two tiles being staged for the next
 
 struct GeoState {
@@ -29,7 +36,7 @@ struct GeoState {
     // GEO_SETS sets of tile / where_maps_to buffers: the decode and where_maps_to kernels of the coming tiles run on s_pre
     // while earlier tiles are accumulated, merged and point-filled on the handle's stream; a batch holds up to GEO_NB tiles.
     float* d_tile[GEO_SETS] = {}; size_t tile_cap[GEO_SETS] = {};
-    int2* d_wm[GEO_SETS] = {}; size_t wm_cap[GEO_SETS] = {};
+    WmCell* d_wm[GEO_SETS] = {}; size_t wm_cap[GEO_SETS] = {};
     cudaStream_t s_pre = nullptr;
     cudaEvent_t ev_pre[GEO_SETS] = {}, ev_used[GEO_SETS] = {};
     bool used_rec[GEO_SETS] = {};
@@ -67,7 +74,7 @@ struct GeoK {  // kernel-side view
     unsigned long long* counters;   // [0] deferred to the warp pass, [1] to the literal pass, [2] candidates of the point pass
     // current tile
     const float* tile; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny;
-    int2* wm;
+    WmCell* wm;
     int ops[WPSGPU_MAX_OPS], opts[WPSGPU_MAX_OPS];
 };
 
@@ -87,7 +94,7 @@ __global__ void k_geo_tile_reset(int* tbbox, unsigned long long* counters)
 // per-row term (latitude) and a per-column term (longitude): those 2*WM_T evaluations are shared by the WM_T^2
 // pixels of the block through shared memory -- same expressions as llij_lc / llij_ps, so the same bits.
 constexpr int WM_T = 64;
-struct GeoWmTile { int smx, smy, tnx, tny; int2* wm; const float* terms; };
+struct GeoWmTile { int smx, smy, tnx, tny; WmCell* wm; const float* terms; };
 // (the tile comes as a small separate struct: assigning tile fields into a copy of the kernel's GeoK parameter makes every
 // thread copy the whole parameter block to local memory)
 __device__ __forceinline__ void geo_wm_body(const GeoK& g, const GeoWmTile& w)
@@ -133,9 +140,8 @@ __device__ __forceinline__ void geo_wm_body(const GeoK& g, const GeoWmTile& w)
         }
         rx = (rx - 0.5f) * g.sr_x + 0.5f;
         ry = (ry - 0.5f) * g.sr_y + 0.5f;
-        int2 wv;
-        if ((float)g.start_i <= rx && rx <= (float)g.end_i && (float)g.start_j <= ry && ry <= (float)g.end_j) { wv.x = f_nint(rx); wv.y = f_nint(ry); }
-        else { wv.x = GEO_OUTSIDE; wv.y = 0; }
+        WmCell wv = WM_OUTSIDE;
+        if ((float)g.start_i <= rx && rx <= (float)g.end_i && (float)g.start_j <= ry && ry <= (float)g.end_j) wv = wm_pack(f_nint(rx), f_nint(ry));
         w.wm[(size_t)tj * w.tnx + ti] = wv;
     }
 }
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(256) k_geo_wm(GeoK g)
 // first block whose four corners agree, else the pixel's own cell at the <=2x2 leaf.
 // Tile-specific part of the kernel arguments: a batch launch takes several of these (blockIdx.z picks one).
 struct GeoTile {
-    const float* tile; const int2* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; const int2* xb; const int2* yb; float* terms;
+    const float* tile; const WmCell* wm; int smx, sMx, smy, sMy, smz, sMz, bdr, tnx, tny; const int* dstart; const int2* xb; const int2* yb; float* terms;
     // categorical batches read the file's bytes directly (read_geogrid.c:91-128 + the row flip); `tile` is then decoded only if
     // the batch's point pass has candidates (k_geo_decode_b with a gate)
     const unsigned char* raw; int rws, rsigned, rlittle, rflip;
@@ -174,7 +180,7 @@ __device__ __forceinline__ float geo_raw_value(const GeoTile& t, int ix, int jy)
 // reach (its parent is a <= 2 x 2 leaf, or a right / upper half that does not exist) is skipped.
 constexpr int GEO_DCAP = 7;
 constexpr int GEO_DNODES = 21845;      // (4^(GEO_DCAP+1) - 1) / 3
-__device__ __forceinline__ void geo_dstart_body(const int2* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
+__device__ __forceinline__ void geo_dstart_body(const WmCell* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= GEO_DNODES || I0 > I1 || J0 > J1) return;
@@ -192,16 +198,16 @@ __device__ __forceinline__ void geo_dstart_body(const int2* __restrict__ wm, int
     // directions, so the x and y ranges of a pixel's block can be followed independently (k_geo_bounds)
     if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { atomicMin(dstart, d); return; }
     auto W = [&](int i, int j) { return wm[(size_t)(j - smy) * tnx + (i - smx)]; };
-    const int2 p = W(min_i, min_j), q = W(max_i, max_j);
-    if (p.x == q.x && p.y == q.y && p.x != GEO_OUTSIDE) {
-        const int2 r = W(min_i, max_j), t = W(max_i, min_j);
-        if (p.x == r.x && p.x == t.x && p.y == r.y && p.y == t.y) atomicMin(dstart, d);
+    const WmCell p = W(min_i, min_j), q = W(max_i, max_j);
+    if (p == q && p != WM_OUTSIDE) {
+        const WmCell r = W(min_i, max_j), t = W(max_i, min_j);
+        if (p == r && p == t) atomicMin(dstart, d);
     }
 }
 constexpr int GEO_NB = 8;     // tiles per batch
 struct GeoBatch { GeoTile t[GEO_NB]; int n; };
 
-__global__ void __launch_bounds__(256) k_geo_dstart(const int2* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
+__global__ void __launch_bounds__(256) k_geo_dstart(const WmCell* __restrict__ wm, int smx, int smy, int tnx, int I0, int I1, int J0, int J1, int* __restrict__ dstart)
 {
     geo_dstart_body(wm, smx, smy, tnx, I0, I1, J0, J1, dstart);
 }
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, in
     __syncthreads();
     const int d0 = min(__ldg(t.dstart), GEO_DCAP + 1);
     const int tnx = t.tnx;
-    const int2* __restrict__ wm = t.wm - ((size_t)t.smy * tnx + t.smx);     // wm[j * tnx + i] in tile coordinates
+    const WmCell* __restrict__ wm = t.wm - ((size_t)t.smy * tnx + t.smx);     // wm[j * tnx + i] in tile coordinates
     const int pi = I0 + blockIdx.x * 32 + threadIdx.x;
     const bool colok = pi <= I1;
     const int2 xr = colok ? __ldg(t.xb + (pi - I0)) : make_int2(0, 0);
@@ -262,21 +268,21 @@ __global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, in
         if (!colok || pj > J1) continue;
         const int2 yr = __ldg(t.yb + (pj - J0));
         int min_i = xr.x, max_i = xr.y, min_j = yr.x, max_j = yr.y;
-        int2 dest;
+        WmCell dest;
         for (;;) {
             // four corners agree?  The diagonal pair is compared first: where it differs the other two need not be fetched.
-            const int2 a = wm[min_j * tnx + min_i], c = wm[max_j * tnx + max_i];
-            if (a.x == c.x && a.y == c.y && a.x != GEO_OUTSIDE) {
-                const int2 b = wm[max_j * tnx + min_i], d = wm[min_j * tnx + max_i];
-                if (a.x == b.x && a.x == d.x && a.y == b.y && a.y == d.y) { dest = a; break; }
+            const WmCell a = wm[min_j * tnx + min_i], c = wm[max_j * tnx + max_i];
+            if (a == c && a != WM_OUTSIDE) {
+                const WmCell b = wm[max_j * tnx + min_i], d = wm[min_j * tnx + max_i];
+                if (a == b && a == d) { dest = a; break; }
             }
             if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = wm[pj * tnx + pi]; break; }
             const int ci = (max_i + min_i) / 2, cj = (max_j + min_j) / 2;
             if (pi <= ci) max_i = ci; else min_i = ci + 1;
             if (pj <= cj) max_j = cj; else min_j = cj + 1;
         }
-        if (dest.x == GEO_OUTSIDE) continue;
-        const int ii = dest.x - g.start_i, jj = dest.y - g.start_j;
+        if (dest == WM_OUTSIDE) continue;
+        const int ii = wm_x(dest) - g.start_i, jj = wm_y(dest) - g.start_j;
         if (bit_test(g.processed, g.nxw, ii, jj)) continue;
         cell[r] = (jj << 16) | ii;      // row and column of the destination cell (both < 65536)
         jmn = min(jmn, jj); jmx = max(jmx, jj); imn = min(imn, ii); imx = max(imx, ii);
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(256) k_geo_accum_cat_b(GeoK g, GeoBatch bt, in
 // actually credited it -- the per-point pass needs to know whether a cell already held data when "its" tile was processed
 __device__ __forceinline__ void geo_accum_body(GeoK g, const GeoTile& t, int order, int* __restrict__ first_tile)
 {
-    g.tile = t.tile; g.wm = const_cast<int2*>(t.wm);
+    g.tile = t.tile; g.wm = const_cast<WmCell*>(t.wm);
     g.smx = t.smx; g.sMx = t.sMx; g.smy = t.smy; g.sMy = t.sMy; g.smz = t.smz; g.sMz = t.sMz; g.bdr = t.bdr; g.tnx = t.tnx; g.tny = t.tny;
     __shared__ int s_bb[4];   // {jmin, imin, jmax, imax} of the cells this block credits
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -361,17 +367,17 @@ __device__ __forceinline__ void geo_accum_body(GeoK g, const GeoTile& t, int ord
     if (credit) {
         auto W = [&](int i, int j) { return g.wm[(size_t)(j - g.smy) * g.tnx + (i - g.smx)]; };
         int min_i = I0, max_i = I1, min_j = J0, max_j = J1;
-        int2 dest;
+        WmCell dest;
         // levels above d0 hold no block whose corners agree (k_geo_dstart): the walk only narrows the rectangle there
         const int d0 = t.dstart ? min(__ldg(t.dstart), GEO_DCAP + 1) : 0;
         for (int lev = 0;; ++lev) {
             // four corners agree?  The diagonal pair is compared first: where it differs the other two corners need
             // not be fetched.
             if (lev >= d0) {
-                int2 a = W(min_i, min_j), c = W(max_i, max_j);
-                if (a.x == c.x && a.y == c.y && a.x != GEO_OUTSIDE) {
-                    int2 b = W(min_i, max_j), d = W(max_i, min_j);
-                    if (a.x == b.x && a.x == d.x && a.y == b.y && a.y == d.y) { dest = a; break; }
+                const WmCell a = W(min_i, min_j), c = W(max_i, max_j);
+                if (a == c && a != WM_OUTSIDE) {
+                    const WmCell b = W(min_i, max_j), d = W(max_i, min_j);
+                    if (a == b && a == d) { dest = a; break; }
                 }
             }
             if ((max_i - min_i + 1) <= 2 && (max_j - min_j + 1) <= 2) { dest = W(pi, pj); break; }
@@ -379,9 +385,9 @@ __device__ __forceinline__ void geo_accum_body(GeoK g, const GeoTile& t, int ord
             if (pi <= ci) max_i = ci; else min_i = ci + 1;
             if (pj <= cj) max_j = cj; else min_j = cj + 1;
         }
-        credit = dest.x != GEO_OUTSIDE;
+        credit = dest != WM_OUTSIDE;
         if (credit) {
-            ii = dest.x - g.start_i; jj = dest.y - g.start_j;
+            ii = wm_x(dest) - g.start_i; jj = wm_y(dest) - g.start_j;
             credit = !bit_test(g.processed, g.nxw, ii, jj);
         }
     }
@@ -783,7 +789,7 @@ __global__ void k_geo_points_literal(GeoK g, const float2* __restrict__ src_xy, 
 // its length at counters[3 z + 2]); deferred searches carry the tile in Deferred::slab.
 __device__ __forceinline__ void apply_tile(GeoK& g, const GeoTile& t)
 {
-    g.tile = t.tile; g.wm = const_cast<int2*>(t.wm);
+    g.tile = t.tile; g.wm = const_cast<WmCell*>(t.wm);
     g.smx = t.smx; g.sMx = t.sMx; g.smy = t.smy; g.sMy = t.sMy; g.smz = t.smz; g.sMz = t.sMz; g.bdr = t.bdr; g.tnx = t.tnx; g.tny = t.tny;
 }
 // Pre-work of a whole batch, one launch per step (blockIdx.z = tile): decode of the raw file bytes, where_maps_to, the first
@@ -848,7 +854,7 @@ __global__ void __launch_bounds__(256) k_geo_wm_sep_b(GeoK g, GeoBatch bt)
     const float rm = t.terms[tj];
     const float* __restrict__ sn = t.terms + t.tny;
     const float* __restrict__ cs = t.terms + t.tny + t.tnx;
-    int2* __restrict__ row = const_cast<int2*>(t.wm) + (size_t)tj * t.tnx;
+    WmCell* __restrict__ row = const_cast<WmCell*>(t.wm) + (size_t)tj * t.tnx;
     const bool lc = g.dom.code == WPSGPU_PROJ_LC;
     const float si = (float)g.start_i, ei = (float)g.end_i, sj = (float)g.start_j, ej = (float)g.end_j;
     for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < t.tnx; ti += gridDim.x * blockDim.x) {
@@ -860,9 +866,8 @@ __global__ void __launch_bounds__(256) k_geo_wm_sep_b(GeoK g, GeoBatch bt)
         else if (g.istagger == WPSGPU_CORNER) { rx = rx + 0.5f; ry = ry + 0.5f; }
         rx = (rx - 0.5f) * g.sr_x + 0.5f;
         ry = (ry - 0.5f) * g.sr_y + 0.5f;
-        int2 wv;
-        if (si <= rx && rx <= ei && sj <= ry && ry <= ej) { wv.x = f_nint(rx); wv.y = f_nint(ry); }
-        else { wv.x = GEO_OUTSIDE; wv.y = 0; }
+        WmCell wv = WM_OUTSIDE;
+        if (si <= rx && rx <= ei && sj <= ry && ry <= ej) wv = wm_pack(f_nint(rx), f_nint(ry));
         row[ti] = wv;
     }
 }
@@ -872,7 +877,7 @@ __global__ void __launch_bounds__(256) k_geo_wm_b(GeoK g, GeoBatch bt, int have_
     if ((int)blockIdx.x * WM_T >= t.tnx || (int)blockIdx.y * WM_T >= t.tny) return;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *const_cast<int*>(t.dstart) = INT_MAX;    // k_geo_dstart_b follows in stream order
     GeoWmTile w;
-    w.smx = t.smx; w.smy = t.smy; w.tnx = t.tnx; w.tny = t.tny; w.wm = const_cast<int2*>(t.wm); w.terms = have_terms ? t.terms : nullptr;
+    w.smx = t.smx; w.smy = t.smy; w.tnx = t.tnx; w.tny = t.tny; w.wm = const_cast<WmCell*>(t.wm); w.terms = have_terms ? t.terms : nullptr;
     geo_wm_body(g, w);
 }
 __global__ void __launch_bounds__(256) k_geo_dstart_b(GeoBatch bt)
@@ -1094,6 +1099,8 @@ int wpsgpu_geogrid_field_begin(wpsgpu_handle_t h, const wpsgpu_geo_field* f)
     s->f = *f;
     s->nx = f->end_i - f->start_i + 1; s->ny = f->end_j - f->start_j + 1; s->nk = f->end_k - f->start_k + 1;
     WPS_CHECK(s->nx > 0 && s->ny > 0 && s->nk > 0, -1, "empty field");
+    WPS_CHECK(f->start_i > -32768 && f->end_i <= 32767 && f->start_j > -32768 && f->end_j <= 32767, -1,
+              "wpsgpu_geogrid_field_begin: field indices beyond +-32767 are not supported (where_maps_to keeps 16-bit cell indices)");
     s->nxw = (s->nx + 31) / 32; s->npts = (size_t)s->nx * s->ny;
     size_t b2 = s->npts * sizeof(float), b3 = b2 * s->nk, wb = (size_t)s->ny * s->nxw * sizeof(int);
     const bool host = h->ptr_mode == WPSGPU_PTR_HOST;
@@ -1319,9 +1326,9 @@ static int geo_process_tile(wpsgpu_ctx* h, int set, cudaStream_t pre, int smx, i
     dim3 b(32, 8);
     const bool accum = s->l.itype == WPSGPU_CATEGORICAL || s->l.itype == WPSGPU_SP_CONTINUOUS;
     if (accum) {
-        if ((size_t)tnx * tny * sizeof(int2) > s->wm_cap[set]) {
+        if ((size_t)tnx * tny * sizeof(WmCell) > s->wm_cap[set]) {
             WPS_CUDA(cudaStreamSynchronize(h->stream));
-            WPS_TRY(geo_grow((void**)&s->d_wm[set], &s->wm_cap[set], (size_t)tnx * tny * sizeof(int2), pre));
+            WPS_TRY(geo_grow((void**)&s->d_wm[set], &s->wm_cap[set], (size_t)tnx * tny * sizeof(WmCell), pre));
         }
         g.wm = s->d_wm[set];
         if (geo_batchable(s) && pre != h->stream) {
