@@ -1292,7 +1292,8 @@ static int geo_flush_batch(wpsgpu_ctx* h)
     else k_geo_accum_b<<<dim3(gx, gy, bt.n), dim3(32, 8), 0, h->stream>>>(g, bt, s->d_first_tile);
     const unsigned nblk = (unsigned)((s->npts + 255) / 256);
     k_geo_select_b<<<nblk, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_first_tile, s->d_cand, cnt);
-    if (any_lazy) { k_geo_decode_b<<<dim3((unsigned)std::min<size_t>((lazy_maxpix + 255) / 256, 4096), 1, bt.n), 256, 0, h->stream>>>(rb_lazy); h->launches++; }
+    // (a small grid: the gate is shut for almost every tile, and 32 k blocks that only look at it cost 20 us)
+    if (any_lazy) { k_geo_decode_b<<<dim3((unsigned)std::min<size_t>((lazy_maxpix + 255) / 256, 148), 1, bt.n), 256, 0, h->stream>>>(rb_lazy); h->launches++; }
     k_geo_points_b<<<h->sm_count * 2, 256, 0, h->stream>>>(g, bt, s->d_src_xy, s->d_cand, cnt, s->d_def);
     h->launches += 4;
     if (s->has_search) {
