@@ -1,5 +1,4 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_f3.log 2>&1; tail -2 gpurun_out/pytest_f3.log
-WPSGPU_POISON=1 python -m pytest tests -m gpu -x -q -k "metgrid or config or mirror or device" > gpurun_out/pytest_f3_poison.log 2>&1; tail -2 gpurun_out/pytest_f3_poison.log
-python bench.py > gpurun_out/bench_f3.json 2> gpurun_out/bench_f3.err; tail -c 200 gpurun_out/bench_f3.json
-WPSGPU_PRECISION=0 python bench.py --no-cpu --no-geogrid --no-e2e > gpurun_out/bench_f3_exact.json 2> gpurun_out/bench_f3_exact.err; python -c "import json; d=json.loads(open('gpurun_out/bench_f3_exact.json').read().strip().splitlines()[-1]); print('exact', d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/geo_launches_f3.csv python tools/geo_only.py > /dev/null 2>&1
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_f4.log 2>&1; tail -2 gpurun_out/pytest_f4.log
+WPSGPU_GEO_BATCH=0 python -m pytest tests -m gpu -x -q -k "geogrid or config3 or golden" > gpurun_out/pytest_f4_nobatch.log 2>&1; tail -1 gpurun_out/pytest_f4_nobatch.log
+python bench.py > gpurun_out/bench_f4.json 2> gpurun_out/bench_f4.err; python -c "
+import json; d=json.loads(open('gpurun_out/bench_f4.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['geogrid']['ms_per_field'], d['mpas_remap']['frac_of_hbm_peak'], d['clocks'])"
