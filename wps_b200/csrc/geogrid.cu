@@ -844,31 +844,36 @@ __global__ void __launch_bounds__(256) k_geo_wm_terms_b(GeoK g, GeoBatch bt)
 }
 // where_maps_to of a batch from the row / column terms alone: a kernel of its own, because in the general kernel the
 // compiler hoists the loop-invariant double-precision set-up of every projection branch in front of the pixel loop -- a
-// thousand instructions per thread that this path never needs.  One thread = four pixels of a row, int4 stores.
+// thousand instructions per thread that this path never needs.  A block takes WMS_ROWS rows of the tile: a thread keeps the
+// column terms of its pixels and walks down the rows (a block per row lived too short to be worth scheduling).
+constexpr int WMS_ROWS = 8;
 __global__ void __launch_bounds__(256) k_geo_wm_sep_b(GeoK g, GeoBatch bt)
 {
     const GeoTile& t = bt.t[blockIdx.z];
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *const_cast<int*>(t.dstart) = INT_MAX;    // k_geo_dstart_b follows in stream order
-    const int tj = blockIdx.y;
-    if (tj >= t.tny) return;
-    const float rm = t.terms[tj];
+    const int tj0 = blockIdx.y * WMS_ROWS;
+    if (tj0 >= t.tny) return;
+    const int tj1 = min(tj0 + WMS_ROWS, t.tny);
     const float* __restrict__ sn = t.terms + t.tny;
     const float* __restrict__ cs = t.terms + t.tny + t.tnx;
-    WmCell* __restrict__ row = const_cast<WmCell*>(t.wm) + (size_t)tj * t.tnx;
     const bool lc = g.dom.code == WPSGPU_PROJ_LC;
     const float si = (float)g.start_i, ei = (float)g.end_i, sj = (float)g.start_j, ej = (float)g.end_j;
     for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < t.tnx; ti += gridDim.x * blockDim.x) {
-        float rx, ry;
-        if (lc) llij_lc_combine(rm, sn[ti], cs[ti], g.dom, rx, ry);
-        else llij_ps_combine(rm, sn[ti], cs[ti], g.dom, rx, ry);
-        if (g.istagger == WPSGPU_U) rx = rx + 0.5f;
-        else if (g.istagger == WPSGPU_V) ry = ry + 0.5f;
-        else if (g.istagger == WPSGPU_CORNER) { rx = rx + 0.5f; ry = ry + 0.5f; }
-        rx = (rx - 0.5f) * g.sr_x + 0.5f;
-        ry = (ry - 0.5f) * g.sr_y + 0.5f;
-        WmCell wv = WM_OUTSIDE;
-        if (si <= rx && rx <= ei && sj <= ry && ry <= ej) wv = wm_pack(f_nint(rx), f_nint(ry));
-        row[ti] = wv;
+        const float s = sn[ti], c = cs[ti];
+        for (int tj = tj0; tj < tj1; ++tj) {
+            const float rm = t.terms[tj];
+            float rx, ry;
+            if (lc) llij_lc_combine(rm, s, c, g.dom, rx, ry);
+            else llij_ps_combine(rm, s, c, g.dom, rx, ry);
+            if (g.istagger == WPSGPU_U) rx = rx + 0.5f;
+            else if (g.istagger == WPSGPU_V) ry = ry + 0.5f;
+            else if (g.istagger == WPSGPU_CORNER) { rx = rx + 0.5f; ry = ry + 0.5f; }
+            rx = (rx - 0.5f) * g.sr_x + 0.5f;
+            ry = (ry - 0.5f) * g.sr_y + 0.5f;
+            WmCell wv = WM_OUTSIDE;
+            if (si <= rx && rx <= ei && sj <= ry && ry <= ej) wv = wm_pack(f_nint(rx), f_nint(ry));
+            const_cast<WmCell*>(t.wm)[(size_t)tj * t.tnx + ti] = wv;
+        }
     }
 }
 __global__ void __launch_bounds__(256) k_geo_wm_b(GeoK g, GeoBatch bt, int have_terms)
@@ -1278,7 +1283,7 @@ static int geo_flush_batch(wpsgpu_ctx* h)
         if (separable) {
             int mx = 1, my = 1;
             for (int z = 0; z < bt.n; ++z) { mx = std::max(mx, bt.t[z].tnx); my = std::max(my, bt.t[z].tny); }
-            k_geo_wm_sep_b<<<dim3((mx + 511) / 512, my, bt.n), 256, 0, s->s_pre>>>(g, bt);
+            k_geo_wm_sep_b<<<dim3((mx + 255) / 256, (my + WMS_ROWS - 1) / WMS_ROWS, bt.n), 256, 0, s->s_pre>>>(g, bt);
         } else k_geo_wm_b<<<dim3(wx, wy, bt.n), 256, 0, s->s_pre>>>(g, bt, 0);
         k_geo_dstart_b<<<dim3((GEO_DNODES + 255) / 256, 1, bt.n), 256, 0, s->s_pre>>>(bt);
         k_geo_bounds_b<<<dim3((bnd + 255) / 256, 1, bt.n), 256, 0, s->s_pre>>>(bt);
