@@ -163,8 +163,8 @@ struct GeoTile {
 };
 __device__ __forceinline__ float geo_raw_value(const GeoTile& t, int ix, int jy)
 {
-    const size_t e = (size_t)(t.rflip ? t.tny - 1 - jy : jy) * t.tnx + ix;
-    const unsigned char* b = t.raw + e * t.rws;
+    const unsigned e = (unsigned)(t.rflip ? t.tny - 1 - jy : jy) * (unsigned)t.tnx + (unsigned)ix;     // one level of a tile: far below 2^31 bytes
+    const unsigned char* b = t.raw + e * (unsigned)t.rws;
     int ival;
     if (t.rws == 1) { ival = b[0]; if (t.rsigned && ival > (1 << 7)) ival -= (1 << 8); }
     else if (t.rws == 2) { ival = t.rlittle ? ((b[1] << 8) | b[0]) : ((b[0] << 8) | b[1]); if (t.rsigned && ival > (1 << 15)) ival -= (1 << 16); }
