@@ -388,6 +388,11 @@ module wpsgpu_mod
          real(c_float), value :: dom_dy
          real(c_float) :: src(*), dst(*)
       end function
+      integer(c_int) function wpsgpu_metgrid_set_timing(handle, on) bind(C, name='wpsgpu_metgrid_set_timing')
+         import :: c_int, c_ptr
+         type(c_ptr), value :: handle
+         integer(c_int), value :: on
+      end function
       integer(c_int) function wpsgpu_smooth_egrid(handle, opt, npass, array, sx, ex, sy, ey, sz, ez, msgval, hflag) &
                         bind(C, name='wpsgpu_smooth_egrid')
          import :: c_int, c_ptr, c_float

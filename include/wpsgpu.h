@@ -182,6 +182,9 @@ int wpsgpu_metgrid_flush_async(wpsgpu_handle_t h);
  * carried-over fields in; r_arr and new_pts out; the small job tables are not counted).  Chains without `search` only
  * need the rectangle of the source slab their destination grid can touch, so h2d is usually far below the slab sizes. */
 int wpsgpu_metgrid_copy_bytes(wpsgpu_handle_t h, int64_t *h2d, int64_t *d2h);
+/* Measurement aid, off by default: when on, every flush records the CUDA events wpsgpu_metgrid_last_kernel / _last_timings
+ * read (a dozen per flush, ~2 % of a config-2 step); those two calls fail after a flush that was not timed. */
+int wpsgpu_metgrid_set_timing(wpsgpu_handle_t h, int on);
 /* Device time (CUDA events on the handle's stream) of the dominant kernel of the last flush and the number of
  * (slab x destination point) outputs it produced -- for roofline reporting only. */
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float *ms, double *points);

@@ -791,3 +791,38 @@ def test_masked_both_with_landmask_outside_0_1(orc, handle, tolerance):
     else:
         assert_bitexact(r[~odd], r_ref[~odd], "masked=both, clean landmask points")
     assert (r[odd] == fill).all() and bits[odd].all(), "points with LANDMASK outside {0, 1} receive fill_missing and count as new"
+
+
+def test_timing_events_are_opt_in(handle):
+    from wps_b200 import synth
+    """wpsgpu_metgrid_set_timing: the event brackets behind metgrid_last_kernel / metgrid_last_timings are recorded only on request
+    (they cost ~2 % of a step); asking for timings of an untimed flush is an error, not stale numbers."""
+    from wps_b200 import capi
+    nx, ny = 64, 48
+    dom = synth.lambert_domain(nx, ny, 30000.0, 30.0, 60.0, -98.0, 34.83, -81.03)
+    xlat, xlon = handle.xytoll_grid(dom, capi.M, 1, 1, nx, ny)
+    kw = dict(dlat=-1.0, dlon=1.0, known_x=1.0, known_y=1.0, known_lat=90.0, known_lon=0.0, earth_radius=6371229.0)
+    src = capi.push_source_projection(capi.PROJ_LATLON, **kw)
+    handle.metgrid_set_grid(0, xlat, xlon, 1, 1)
+    handle.metgrid_set_domain(1, nx, 1, ny)
+    slab = synth.add_halo(synth.slab_np(360, 181, 0, "smooth", None, np.float32(1e20)))
+
+    def one_flush():
+        r = np.zeros((ny, nx), np.float32)
+        npw = np.zeros((ny, capi.nwords(nx)), np.int32)
+        handle.metgrid_enqueue_slab(src, capi.field_opts(synth.C3D, np.float32(1e20), np.float32(0.0)), slab, -2, 1, 3, 0, capi.M, r, npw)
+        handle.metgrid_flush()
+        return r
+    handle.metgrid_set_timing(False)
+    a = one_flush()
+    with pytest.raises(capi.WpsGpuError, match="not timed"):
+        handle.metgrid_last_kernel()
+    with pytest.raises(capi.WpsGpuError, match="not timed"):
+        handle.metgrid_last_timings()
+    handle.metgrid_set_timing(True)
+    b = one_flush()
+    ms, pts = handle.metgrid_last_kernel()
+    t7, p7 = handle.metgrid_last_timings()
+    assert ms >= 0.0 and pts == nx * ny and t7[6] > 0.0
+    handle.metgrid_set_timing(False)
+    assert np.array_equal(a.view(np.int32), b.view(np.int32))

@@ -355,6 +355,10 @@ class Handle:
                                         C.c_void_p(ptr(src)), C.c_void_p(ptr(src_valid)), C.c_void_p(ptr(r_arr)),
                                         C.c_void_p(ptr(valid_mask))))
 
+    def metgrid_set_timing(self, on=True):
+        """Record the CUDA events metgrid_last_kernel / metgrid_last_timings read (off by default: ~2 % of a step)."""
+        check(lib().wpsgpu_metgrid_set_timing(self._h, int(bool(on))))
+
     def metgrid_set_precision(self, mode):
         """PRECISION_EXACT (default, bit-identical sixteen_pt) or PRECISION_TOLERANCE (north_star's 1e-5, ~3x faster)."""
         check(lib().wpsgpu_metgrid_set_precision(self._h, int(mode)))

@@ -130,6 +130,8 @@ struct wpsgpu_ctx {
     int64_t h2d_bytes = 0, d2h_bytes = 0;           // bytes moved by the host-pointer paths of the metgrid flush
     bool async_pending = false;                     // wpsgpu_metgrid_flush_async: D2H copies may still read the arena
     int precision = WPSGPU_PRECISION_EXACT;   // wpsgpu_metgrid_set_precision
+    int timing = 0;             // wpsgpu_metgrid_set_timing: record the CUDA events that bracket the kernels of a flush
+    bool timed_flush = false;   // the last flush recorded them
     bool disable_fast = false;  // testing aid: route everything through the generic kernel
 };
 

@@ -1175,6 +1175,7 @@ int wpsgpu_metgrid_copy_bytes(wpsgpu_handle_t h, int64_t* h2d, int64_t* d2h)
 int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float* ms, double* points)
 {
     WPS_CHECK(h && ms && points, -1, "NULL argument");
+    WPS_CHECK(h->timed_flush, -2, "wpsgpu_metgrid_last_kernel: the last flush was not timed (wpsgpu_metgrid_set_timing)");
     WPS_CUDA(cudaEventSynchronize(h->ev_k1));
     WPS_CUDA(cudaEventElapsedTime(ms, h->ev_k0, h->ev_k1));
     *points = h->last_points;
@@ -1184,6 +1185,7 @@ int wpsgpu_metgrid_last_kernel(wpsgpu_handle_t h, float* ms, double* points)
 int wpsgpu_metgrid_last_timings(wpsgpu_handle_t h, float* ms3, double* points3)
 {
     WPS_CHECK(h && ms3 && points3, -1, "NULL argument");
+    WPS_CHECK(h->timed_flush, -2, "wpsgpu_metgrid_last_timings: the last flush was not timed (wpsgpu_metgrid_set_timing)");
     WPS_CUDA(cudaEventSynchronize(h->ev_t[11]));
     for (int k = 0; k < 6; ++k) {
         WPS_CUDA(cudaEventElapsedTime(&ms3[k], h->ev_t[2 * k], h->ev_t[2 * k + 1]));
@@ -1565,7 +1567,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         WPS_CUDA(cudaStreamWaitEvent(h->s_side, h->ev_fork, 0));
         s4 = h->s_side;
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[6], s4));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[6], s4));
     for (int j : cls_jobs[1]) {
         if (jobs[j].fast < 2) continue;
         Fast4Params fp;
@@ -1579,8 +1581,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         else k_metgrid_fast4<WPSGPU_N_NEIGHBOR><<<fp.jb.tiles_x * fp.jb.tiles_y, block, 0, s4>>>(fp);
         h->launches++;
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[7], s4));
-    WPS_CUDA(cudaEventRecord(h->ev_t[0], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[7], s4));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[0], h->stream));
     if (!pack_jobs.empty()) {
         k_pack16<<<dim3((pack_cells + 255) / 256, pack_max, (unsigned)pack_jobs.size()), 256, 0, h->stream>>>(d_jobs, d_pack_jobs, d_sp);
         h->launches++;
@@ -1589,8 +1591,8 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         k_pack_win<<<dim3((unsigned)win_tiles, (unsigned)win_tasks.size()), 256, 0, h->stream>>>(d_jobs, (const PackWinTask*)(d_tab + off_win), d_sp);
         h->launches++;
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
-    WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[1], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[2], h->stream));
     for (int j : cls_jobs[1]) {
         if (jobs[j].fast != 1 || jobs[j].strip > 0) continue;
         FastParams fp;
@@ -1619,12 +1621,12 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         }
         WPS_TRY(launch_strips(h, jobs, sj, sp, dump_r, dump_w, sq));
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[3], h->stream));
     if (side) {   // join: the slow pass and everything after it see the side stream's results
         WPS_CUDA(cudaEventRecord(h->ev_join, h->s_side));
         WPS_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[8], h->stream));
     if (tile_cursor[1] > 0) {
         k_metgrid_slowlist<<<h->sm_count * SLOW_MINBLOCKS, 128, 0, h->stream>>>(d_jobs, njobs, d_sp, sq, d_def, d_cnt);
         // queue overflow (cnt[1] set by a producer): the generic kernel redoes every first-method job of the pass
@@ -1632,19 +1634,19 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
                                                                                           tile_cursor[1], d_sp, d_def, d_cnt, sq.cnt + 1);
         h->launches += 2;
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[9], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[9], h->stream));
     if (env_int("WPSGPU_DEBUG_SLOW", 0, 0, 1) && tile_cursor[1] > 0) {   // diagnostic: size of the slow queue
         unsigned c[2] = { 0, 0 };
         WPS_CUDA(cudaStreamSynchronize(h->stream));
         WPS_CUDA(cudaMemcpy(c, sq.cnt, sizeof(c), cudaMemcpyDeviceToHost));
         fprintf(stderr, "[wpsgpu] slow queue: %u entries of %.0f first-method outputs (capacity %u, overflow %u)\n", c[0], fast_pairs, sq.cap, c[1]);
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[4], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[4], h->stream));
     if (tile_cursor[0] > 0) {
         k_metgrid_interp<<<tile_cursor[0], block, 0, h->stream>>>(d_jobs, d_cls_jobs[0], d_cls_tile0[0], (int)cls_jobs[0].size(), tile_cursor[0], d_sp, d_def, d_cnt, nullptr);
         h->launches++;
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[5], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[5], h->stream));
     WPS_CUDA(cudaGetLastError());
     if (last) {
         h->last_pts3[0] = fast16_points; h->last_pts3[1] = fast16_points; h->last_pts3[2] = cls_points[0]; h->last_pts3[3] = fast4_points;
@@ -1653,8 +1655,9 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         int dom = fast16_points >= cls_points[0] ? 1 : 2;
         h->ev_k0 = h->ev_t[2 * dom]; h->ev_k1 = h->ev_t[2 * dom + 1];
         h->last_points = dom == 1 ? fast16_points : cls_points[0];
+        h->timed_flush = h->timing != 0;
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[10], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[10], h->stream));
     if (any_search) {
         int sblocks = h->sm_count * 8;
         k_metgrid_search<<<sblocks, 256, 0, h->stream>>>(d_jobs, njobs, d_sp, d_def, d_cnt, d_def2, d_cnt + 1);
@@ -1678,7 +1681,7 @@ static int run_groups(wpsgpu_ctx* h, FlushShared& fs, const std::vector<int>& gs
         h->launches++;
         WPS_CUDA(cudaGetLastError());
     }
-    WPS_CUDA(cudaEventRecord(h->ev_t[11], h->stream));
+    if (h->timing) WPS_CUDA(cudaEventRecord(h->ev_t[11], h->stream));
     if (host) {
         if (s_out != h->stream) {
             WPS_CUDA(cudaEventRecord(h->ev_done, h->stream));
@@ -1946,6 +1949,13 @@ int wpsgpu_metgrid_set_precision(wpsgpu_handle_t h, int mode)
     WPS_CHECK(h != nullptr, -1, "NULL handle");
     WPS_CHECK(mode == WPSGPU_PRECISION_EXACT || mode == WPSGPU_PRECISION_TOLERANCE, -1, "unknown precision mode %d", mode);
     h->precision = mode;
+    return 0;
+}
+
+int wpsgpu_metgrid_set_timing(wpsgpu_handle_t h, int on)
+{
+    WPS_CHECK(h != nullptr, -1, "NULL handle");
+    h->timing = on ? 1 : 0;
     return 0;
 }
 
