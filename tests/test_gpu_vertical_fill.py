@@ -8,7 +8,8 @@ from tests.util import assert_bitexact, bool_to_bits, bits_to_bool
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("nx,ny,nlev,p_valid", [(70, 33, 12, 0.6), (129, 17, 35, 0.3), (31, 5, 2, 0.5), (64, 8, 9, 0.95)])
+@pytest.mark.parametrize("nx,ny,nlev,p_valid", [(70, 33, 12, 0.6), (129, 17, 35, 0.3), (31, 5, 2, 0.5), (64, 8, 9, 0.95), (40, 9, 50, 0.4), (97, 6, 64, 0.2),
+                                                  (33, 7, 70, 0.5)])
 def test_fill_missing_levels_vs_oracle(orc, handle, nx, ny, nlev, p_valid):
     from wps_b200 import capi
     rng = np.random.default_rng(nx * 1000 + nlev)

@@ -395,6 +395,57 @@ __global__ void __launch_bounds__(256) k_fill_missing_levels(VFillArgs a)
     }
 }
 
+// The same rule for up to 64 levels without walking memory level by level: a warp fetches the valid_mask words of ALL levels
+// of its 32 columns at once (lane l holds levels l and l + 32), every lane assembles the validity bits of its own column into
+// one 64-bit word, and the level loop then runs on registers -- a gap between two valid levels costs two loads (its lower and
+// upper values; a filled level hands its value on in a register) and its stores, instead of a dependent load chain per level.
+__global__ void __launch_bounds__(256) k_fill_missing_levels64(VFillArgs a)
+{
+    const int lane = threadIdx.x;
+    const int ix = blockIdx.x * 32 + lane, jx = blockIdx.y * 8 + threadIdx.y;
+    if (jx >= a.ny) return;                       // whole warps only
+    const bool in = ix < a.nx;
+    const size_t o = (size_t)jx * a.nx + ix, w = (size_t)jx * a.nxw + blockIdx.x;
+    const unsigned w0 = lane < a.nlev ? (unsigned)a.v[lane][w] : 0u;
+    const unsigned w1 = lane + 32 < a.nlev ? (unsigned)a.v[lane + 32][w] : 0u;
+    unsigned long long mask = 0ull;               // bit k: level k is valid for this lane's column
+    for (int k = 0; k < a.nlev; ++k) {
+        const unsigned wk = __shfl_sync(0xffffffffu, k < 32 ? w0 : w1, k & 31);
+        mask |= (unsigned long long)((wk >> lane) & 1u) << k;
+    }
+    int lower = -1, upper = -1;
+    float rl = 0.0f, ru = 0.0f;
+    bool rl_have = false;                         // rl holds r[lower] (a value this thread has just filled in)
+    for (int k = 0; k < a.nlev; ++k) {
+        const bool valid = (mask >> k) & 1ull;
+        bool fill = false;
+        if (in && !valid) {
+            if (upper <= k) {
+                const unsigned long long above = mask & ~((2ull << k) - 1ull);
+                upper = above ? __ffsll((long long)above) - 1 : a.nlev;
+                if (upper < a.nlev) ru = a.r[upper][o];
+            }
+            if (upper < a.nlev && lower >= 0) {
+                if (!rl_have) { rl = a.r[lower][o]; rl_have = true; }
+                const int lu = a.lev[upper], lk = a.lev[k], ll = a.lev[lower];
+                const float wl = (float)abs(lu - lk) / (float)abs(lu - ll);
+                const float wu = (float)abs(lk - ll) / (float)abs(lu - ll);
+                const float val = wl * rl + wu * ru;
+                a.r[k][o] = val;
+                rl = val;                         // level k is the lower neighbour of what follows
+                fill = true;
+            }
+        }
+        const unsigned add = __ballot_sync(0xffffffffu, fill);
+        if (add) {
+            const unsigned word = __shfl_sync(0xffffffffu, k < 32 ? w0 : w1, k & 31);
+            if (lane == 0) a.v[k][w] = (int)(word | add);
+        }
+        if (valid) { lower = k; rl_have = false; }
+        else if (fill) lower = k;
+    }
+}
+
 __global__ void k_create_level(float value, const float* __restrict__ src, const int* __restrict__ src_valid,
                                float* __restrict__ r, int* __restrict__ valid, int nx, int ny, int nxw)
 {
@@ -513,7 +564,8 @@ int wpsgpu_fill_missing_levels(wpsgpu_handle_t h, int32_t nlev, const int32_t* l
     WPS_CUDA(cudaMemcpyAsync(d_lev, levels, sizeof(int) * nlev, cudaMemcpyHostToDevice, h->stream));
     VFillArgs a;
     a.r = d_r; a.v = d_v; a.lev = d_lev; a.nlev = nlev; a.nx = nx; a.ny = ny; a.nxw = nxw;
-    k_fill_missing_levels<<<dim3(nxw, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(a);
+    if (nlev <= 64) k_fill_missing_levels64<<<dim3(nxw, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(a);
+    else k_fill_missing_levels<<<dim3(nxw, (ny + 7) / 8), dim3(32, 8), 0, h->stream>>>(a);
     h->launches++;
     WPS_CUDA(cudaGetLastError());
     if (h->ptr_mode == WPSGPU_PTR_HOST)
