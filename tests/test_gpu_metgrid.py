@@ -826,3 +826,28 @@ def test_timing_events_are_opt_in(handle):
     assert ms >= 0.0 and pts == nx * ny and t7[6] > 0.0
     handle.metgrid_set_timing(False)
     assert np.array_equal(a.view(np.int32), b.view(np.int32))
+
+
+def test_nmm_egrid_destination(orc, handle):
+    """metgrid onto an NMM E-grid (process_domain_module.F:1288-1361): mass-point fields go through interp_met_field with
+    ifieldstagger = HH and the landmask, velocity-point fields with VV on xlat_v / xlon_v; a non-M stagger widens the
+    process_bdy_width band by 2 (:2277).  Destination coordinates come from the rotated lat-lon projection."""
+    from wps_b200 import capi
+    orc.set_transc_mode(1)
+    kw = dict(ixdim=45, jydim=71, phi=6.0, lat1=38.0, lon1=-97.0, stagger=capi.HH)
+    kw["lambda"] = 8.0
+    po = orc.map_set(orc.PROJ_ROTLL, **kw)
+    src = latlon_source(360, 181, -1.0, 1.0, 90.0, 0.0)
+    ls = halo(landsea(360, 181))
+    for fstag in (capi.HH, capi.VV):
+        po.stagger = capi.HH
+        xlat, xlon = orc.get_lat_lon_fields(po, 1, 1, 44, 71, fstag)
+        ny, nx = xlat.shape
+        if fstag == capi.HH:
+            lm = (np.sin(np.arange(ny * nx) * 0.21).reshape(ny, nx) > 0.1).astype(np.float32)
+            slabs = [halo(synth_field(360, 181, 30, missing=np.float32(-1e30), frac_missing=0.1))]
+            run_case(orc, handle, xlat, xlon, slabs, src, "sixteen_pt+four_pt+wt_average_4pt+wt_average_16pt+search",
+                     missing=np.float32(-1e30), fill=1.0, masked=0.0, mask_val=(0.0, 1e20, 1e20), mask_rel="   ",
+                     masks=(ls, None, None), landmask=lm, fstag=fstag, grid_id=4)
+        run_case(orc, handle, xlat, xlon, [halo(synth_field(360, 181, 3, kind="wind"))], src, "sixteen_pt+four_pt+average_4pt", fill=0.0, pbw=4,
+                 fstag=fstag, sd=(1, nx, 1, ny), grid_id=4 + (fstag == capi.VV))
