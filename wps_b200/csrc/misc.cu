@@ -87,8 +87,16 @@ __global__ void k_rotate_u(RotArgs a, int nlev)
             v_weight = vmul(i - 1, j - 1) + vmul(i, j - 1);
             v_map = V(i - 1, j - 1) * vmul(i - 1, j - 1) + V(i, j - 1) * vmul(i, j - 1);
         } else {
-            v_weight = vmul(i - 1, j) + vmul(i - 1, j + 1) + vmul(i, j) + vmul(i, j + 1);
-            v_map = V(i - 1, j) * vmul(i - 1, j) + V(i - 1, j + 1) * vmul(i - 1, j + 1) + V(i, j) * vmul(i, j) + V(i, j + 1) * vmul(i, j + 1);
+            // the interior case, with the index arithmetic done once in 32 bits and every mask bit read once
+            const int xv = i - a.vs1, yv = j - a.vs2, ov = yv * a.vnx + xv, om = yv * a.vnxw + (xv >> 5), bi = xv & 31;
+            const unsigned w0 = (unsigned)vm[om], w1 = (unsigned)vm[om + a.vnxw];
+            unsigned wl0 = w0, wl1 = w1;
+            int bl = bi - 1;
+            if (bi == 0) { wl0 = (unsigned)vm[om - 1]; wl1 = (unsigned)vm[om + a.vnxw - 1]; bl = 31; }
+            const float m00 = ((wl0 >> bl) & 1u) ? 1.0f : 0.0f, m01 = ((wl1 >> bl) & 1u) ? 1.0f : 0.0f;     // (i - 1, j), (i - 1, j + 1)
+            const float m10 = ((w0 >> bi) & 1u) ? 1.0f : 0.0f, m11 = ((w1 >> bi) & 1u) ? 1.0f : 0.0f;       // (i, j), (i, j + 1)
+            v_weight = m00 + m01 + m10 + m11;
+            v_map = v[ov - 1] * m00 + v[ov + a.vnx - 1] * m01 + v[ov] * m10 + v[ov + a.vnx] * m11;
         }
         if (v_weight > 0.0f) res = ca * uold + sa * v_map / v_weight;
     }
@@ -124,8 +132,15 @@ __global__ void k_rotate_v(RotArgs a, int nlev)
             u_weight = umul(i, j) + umul(i, j - 1);
             u_map = U(i, j) * umul(i, j) + U(i, j - 1) * umul(i, j - 1);
         } else {
-            u_weight = umul(i, j - 1) + umul(i, j) + umul(i + 1, j - 1) + umul(i + 1, j);
-            u_map = U(i, j - 1) * umul(i, j - 1) + U(i, j) * umul(i, j) + U(i + 1, j - 1) * umul(i + 1, j - 1) + U(i + 1, j) * umul(i + 1, j);
+            const int xu = i - a.us1, yu = j - a.us2, ou = yu * a.unx + xu, om = yu * a.unxw + (xu >> 5), bi = xu & 31;
+            const unsigned w0 = (unsigned)um[om - a.unxw], w1 = (unsigned)um[om];                                // rows j - 1, j
+            unsigned wr0 = w0, wr1 = w1;
+            int br = bi + 1;
+            if (bi == 31) { wr0 = (unsigned)um[om - a.unxw + 1]; wr1 = (unsigned)um[om + 1]; br = 0; }
+            const float m00 = ((w0 >> bi) & 1u) ? 1.0f : 0.0f, m01 = ((w1 >> bi) & 1u) ? 1.0f : 0.0f;           // (i, j - 1), (i, j)
+            const float m10 = ((wr0 >> br) & 1u) ? 1.0f : 0.0f, m11 = ((wr1 >> br) & 1u) ? 1.0f : 0.0f;         // (i + 1, j - 1), (i + 1, j)
+            u_weight = m00 + m01 + m10 + m11;
+            u_map = u[ou - a.unx] * m00 + u[ou] * m01 + u[ou - a.unx + 1] * m10 + u[ou + 1] * m11;
         }
         if (u_weight > 0.0f) res = -sa * u_map / u_weight + ca * vold;
     }
