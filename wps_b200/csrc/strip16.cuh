@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ job
     const int bx = blockIdx.x % ntx, by = blockIdx.x / ntx;
     if (by * 16 >= pny) return;
     // tile of 20 x 20 cells: the block's 16 x 16 cells with one cell of halo to the left / top and three to the right / bottom
-    __shared__ float s_v[4][20][21];           // record values (zeros replaced, unusable values 0)
-    __shared__ float s_a[4][20][21];           // usable magnitude per level (0 where missing / non-finite); later its 5-wide row maximum
+    __shared__ float4 s_v[20][21];             // record values of the four levels (zeros replaced, unusable values 0)
+    __shared__ float4 s_a[20][21];             // usable magnitude per level (0 where missing / non-finite); later its 5-wide row maximum
+    // (the four levels of a cell side by side: one 16-byte shared-memory access where four 4-byte ones throttled the MIO queue)
     __shared__ unsigned short s_f[20][20];     // per cell: bit lv = missing value, bit 4+lv = unusable for sixteen_pt, bit 8 / 9 = masked under A / B
     __shared__ unsigned short s_h[20][20];     // OR of s_f over the four cells c .. c+3 of the row
     const int tid = threadIdx.x;
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ job
         const size_t off = (size_t)(gy - sy) * snx + (gx - sx);
         unsigned f = 0;
         float v0 = 0.0f;
+        float vv[4], aa[4];
 #pragma unroll
         for (int lv = 0; lv < 4; ++lv) {
             float v = v0, a = 0.0f;             // levels past the job's last one repeat the pack's first level: their results go to the
@@ -120,9 +122,10 @@ __global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ job
                 if (ismsg || !fin) { v = 0.0f; a = 0.0f; }
             }
             if (lv == 0) v0 = v;
-            s_v[lv][r][c] = v;
-            s_a[lv][r][c] = a;
+            vv[lv] = v; aa[lv] = a;
         }
+        s_v[r][c] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        s_a[r][c] = make_float4(aa[0], aa[1], aa[2], aa[3]);
         auto unusable = [&](int sel) -> bool {
             if (!jb.mask[sel]) return false;
             const float mv = __ldg(jb.mask[sel] + off);
@@ -134,7 +137,7 @@ __global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ job
     }
     __syncthreads();
     // row pass: flags of the 4 cells c .. c+3 and the largest usable magnitude of the 5 cells c .. c+4 (clipped to the tile)
-    float hm[2][4];
+    float4 hm[2];
     unsigned hf[2];
     for (int e = tid, k = 0; e < 400; e += 256, ++k) {
         const int c = e % 20, r = e / 20;
@@ -142,20 +145,20 @@ __global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ job
 #pragma unroll
         for (int d = 0; d < 4; ++d) if (c + d < 20) f |= s_f[r][c + d];
         hf[k] = f;
+        float4 m = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-        for (int lv = 0; lv < 4; ++lv) {
-            float m = 0.0f;
-#pragma unroll
-            for (int d = 0; d < 5; ++d) if (c + d < 20) m = fmaxf(m, s_a[lv][r][c + d]);
-            hm[k][lv] = m;
-        }
+        for (int d = 0; d < 5; ++d)
+            if (c + d < 20) {
+                const float4 q = s_a[r][c + d];
+                m.x = fmaxf(m.x, q.x); m.y = fmaxf(m.y, q.y); m.z = fmaxf(m.z, q.z); m.w = fmaxf(m.w, q.w);
+            }
+        hm[k] = m;
     }
     __syncthreads();
     for (int e = tid, k = 0; e < 400; e += 256, ++k) {
         const int c = e % 20, r = e / 20;
         s_h[r][c] = (unsigned short)hf[k];
-#pragma unroll
-        for (int lv = 0; lv < 4; ++lv) s_a[lv][r][c] = hm[k][lv];
+        s_a[r][c] = hm[k];
     }
     __syncthreads();
     const int tx = tid & 15, ty = tid >> 4;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ job
     if (cx >= pnx || cy >= pny) return;
     const int c0 = tx + 1, r0 = ty + 1;        // the thread's cell in the tile
     const size_t o = ((size_t)t.pack * pny + cy) * pnx + cx;
-    const_cast<float4*>(jb.rec)[o] = make_float4(s_v[0][r0][c0], s_v[1][r0][c0], s_v[2][r0][c0], s_v[3][r0][c0]);
+    const_cast<float4*>(jb.rec)[o] = s_v[r0][c0];
     // Flag byte of the 4 x 4 stencil anchored at a cell (cells c-1..c+2, r-1..r+2), per level lv:
     //   bit lv      stencil is clean under mask A: no missing / masked / non-finite value, every |v| >= 1e-21
     //   bit 4 + lv  single-mask jobs: the stencil holds a missing or masked value, so sixteen_pt is certain to hand over
@@ -192,12 +195,17 @@ __global__ void __launch_bounds__(256, 8) k_pack_win(const Job* __restrict__ job
     // i.e. its window may consist of zero stand-ins only and a result can equal 1.E-20 (:1317).
     float T = 0.0f;
     bool at_floor = false;
+    float4 cm = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int r = -1; r <= 3; ++r) {
+        const float4 q = s_a[r0 + r][c0 - 1];
+        cm.x = fmaxf(cm.x, q.x); cm.y = fmaxf(cm.y, q.y); cm.z = fmaxf(cm.z, q.z); cm.w = fmaxf(cm.w, q.w);
+    }
+    const float cmx[4] = { cm.x, cm.y, cm.z, cm.w };
 #pragma unroll
     for (int lv = 0; lv < 4; ++lv) {
         if (!src[lv]) continue;
-        float mx = 0.0f;
-#pragma unroll
-        for (int r = -1; r <= 3; ++r) mx = fmaxf(mx, s_a[lv][r0 + r][c0 - 1]);
+        const float mx = cmx[lv];
         float thr = fmaxf(mx * 3.814697265625e-6f, 1.0e-21f);
         at_floor = at_floor || thr == 1.0e-21f;
         // a weighted sum stays below 1.3 x the largest magnitude: if that cannot reach |missing_value| the kernel need not
